@@ -1,0 +1,282 @@
+/*
+ * cq.h — C ABI of the B200 batched collision-query engine (libcq.so).
+ *
+ * This is the drop-in boundary for ONE path of kelian343/swift-game-engine:
+ * the capsule CCD sweep / move-and-slide / raycast queries of
+ * Game/CollisionQuery.swift against static triangle meshes (*.static.json).
+ * The reference has no FFI of its own — the boundary there is the in-process
+ * Swift class `CollisionQuery` (Game/CollisionQuery.swift:54-160).  Every entry
+ * point below names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no C++/torch types; the library copies what it
+ *    needs, callers keep ownership of every array they pass in;
+ *  - return value: 0 = CQ_OK, negative = error (cq_last_error() has the text);
+ *    nothing throws across the ABI.  The reference's "nil" (no hit) is
+ *    triangle_index == -1 in the hit record;
+ *  - a cq_world lives on the CUDA device that was current when it was created;
+ *    one host thread at a time per world (the reference is MainActor-only and
+ *    not re-entrant, CollisionQuery.swift:787-828);
+ *  - triangle_index numbering = position in the degenerate-filtered soup, static
+ *    set first, dynamic set offset by the static count
+ *    (CollisionQuery.swift:776,782,1004);
+ *  - there is NO CPU fallback: every call fails with CQ_ERR_CUDA when no device
+ *    is usable.
+ */
+#ifndef CQ_H
+#define CQ_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CQ_OK 0
+#define CQ_ERR_INVALID (-1)   /* bad argument */
+#define CQ_ERR_CUDA (-2)      /* CUDA runtime error / no device */
+#define CQ_ERR_IO (-3)        /* file missing / unreadable */
+#define CQ_ERR_PARSE (-4)     /* malformed *.static.json */
+#define CQ_ERR_NOT_FOUND (-5) /* unknown entity id */
+
+#define CQ_LAYER_ALL 0xFFFFFFFFu /* CollisionLayer.all, Components.swift:47-50 */
+#define CQ_MAX_OVERLAP_HITS 8    /* capsuleOverlapAll default maxHits, CollisionQuery.swift:151 */
+#define CQ_MANIFOLD_MAX 4        /* ContactManifoldCache.maxCount, Systems.swift:1160 */
+
+typedef struct cq_world cq_world;
+typedef struct cq_static_mesh_asset cq_static_mesh_asset;
+
+/* ---- world construction ------------------------------------------------- */
+
+/* One collidable entity = TransformComponent + StaticMeshComponent
+ * (+ optional PhysicsBodyComponent.bodyType), as TriangleMeshSet.rebuild reads
+ * them (CollisionQuery.swift:331-417).  `model` is TransformComponent.modelMatrix
+ * (Components.swift:26-44), column-major like simd's matrix_float4x4. */
+typedef struct cq_mesh_part {
+    const float *positions_xyz; /* n_verts * 3, local space */
+    const uint32_t *indices;    /* n_indices (3 per triangle), u16 widened by the caller */
+    int32_t n_verts;
+    int32_t n_indices;
+    float model[16];
+    uint32_t layer;        /* StaticMeshComponent.collisionLayer */
+    float mu_s, mu_k;      /* SurfaceMaterial, Components.swift:704-716 */
+    uint8_t flatten_ground;
+    uint8_t is_dynamic;    /* body present && bodyType != .static  (CollisionQuery.swift:886-900) */
+    uint16_t _pad;
+    uint32_t entity_id;
+} cq_mesh_part;
+
+typedef struct cq_world_info {
+    int32_t n_static_triangles;  /* after the |e1 x e2|^2 <= 1e-10 filter */
+    int32_t n_dynamic_triangles;
+    int32_t n_static_vertices;
+    int32_t n_dynamic_vertices;
+    int32_t n_static_nodes;      /* LBVH internal nodes */
+    int32_t n_dynamic_nodes;
+    int32_t n_parts;
+    int32_t device;
+    float build_ms;              /* device time of upload+filter+Morton+sort+tree+fit */
+    float refit_ms;              /* device time of the last cq_world_update_transforms */
+} cq_world_info;
+
+/* Replaces CollisionQuery.init(world:activeEntityIDs:) (CollisionQuery.swift:57-59
+ * -> StaticTriMesh.init :717-726).  Parts are taken in the given order (the
+ * oracle fixes entity order = ascending id; the reference iterates a Dictionary). */
+int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out);
+void cq_world_destroy(cq_world *w);
+int cq_world_get_info(const cq_world *w, cq_world_info *info);
+
+/* Replaces updateStaticTransforms / updateDynamicTransforms
+ * (CollisionQuery.swift:69-83 -> TriangleMeshSet.updateTransforms :419-462 ->
+ * BVH.refit :528-575): re-transform the entities' vertices, recompute triangle
+ * bounds (no degenerate re-filter), refit the BVH.  models = n * 16 floats. */
+int cq_world_update_transforms(cq_world *w, const uint32_t *entity_ids,
+                               const float *models, int32_t n);
+
+/* Read back the world-space soup (testing / material lookup on the host).
+ * which: 0 = static set, 1 = dynamic set.  Any out pointer may be NULL. */
+int cq_world_read_soup(const cq_world *w, int32_t which,
+                       float *positions_xyz /* n_vertices*3 */,
+                       uint32_t *indices /* n_triangles*3 */,
+                       float *tri_aabbs /* n_triangles*6: min xyz, max xyz */,
+                       uint32_t *tri_layers /* n_triangles */,
+                       int32_t *tri_parts /* n_triangles: index into the parts array */);
+
+typedef struct cq_material {
+    float mu_s, mu_k;
+    int32_t flatten_ground;
+} cq_material;
+/* TriangleMeshSet.materialForTriangle (CollisionQuery.swift:464-469); index is
+ * the global triangle_index of a hit; out-of-range gives SurfaceMaterial.default. */
+int cq_world_triangle_material(const cq_world *w, int32_t triangle_index, cq_material *out);
+
+/* ---- static-mesh JSON loader ---------------------------------------------
+ * Replaces StaticMeshLoader.loadStaticMeshAsset(named:) (StaticMeshLoader.swift:30-125).
+ * Schema: StaticMeshLoader.swift:168-197.  Returns CQ_ERR_IO / CQ_ERR_PARSE where
+ * the reference returns nil; invalid parts are skipped like the reference does. */
+int cq_static_mesh_load(const char *path, cq_static_mesh_asset **out);
+void cq_static_mesh_free(cq_static_mesh_asset *a);
+int32_t cq_static_mesh_part_count(const cq_static_mesh_asset *a);
+const char *cq_static_mesh_part_name(const cq_static_mesh_asset *a, int32_t part);
+/* part transform, already converted row-major -> column-major (StaticMeshLoader.swift:127-134) */
+int cq_static_mesh_part_transform(const cq_static_mesh_asset *a, int32_t part, float out_colmajor[16]);
+/* hull = -1: the render mesh; hull >= 0: collisionHulls[hull].  Pointers stay valid until free. */
+int32_t cq_static_mesh_hull_count(const cq_static_mesh_asset *a, int32_t part);
+int cq_static_mesh_geometry(const cq_static_mesh_asset *a, int32_t part, int32_t hull,
+                            const float **positions_xyz, int32_t *n_verts,
+                            const uint32_t **indices, int32_t *n_indices);
+
+/* ---- queries ------------------------------------------------------------- */
+
+typedef struct cq_ray { /* raycast(origin:direction:maxDistance:mask:), CollisionQuery.swift:85 */
+    float origin[3];
+    float direction[3]; /* NOT normalised by the callee; maxDistance is in units of |direction| */
+    float max_distance;
+    uint32_t mask;
+} cq_ray;
+
+typedef struct cq_ray_hit { /* RaycastHit, CollisionQuery.swift:28-34 */
+    float distance;
+    float position[3];
+    float normal[3];
+    int32_t triangle_index; /* -1 = nil */
+} cq_ray_hit;
+
+#define CQ_CAST_ALL 0      /* capsuleCast          CollisionQuery.swift:96  */
+#define CQ_CAST_BLOCKING 1 /* capsuleCastBlocking  CollisionQuery.swift:109 */
+#define CQ_CAST_GROUND 2   /* capsuleCastGround    CollisionQuery.swift:122 */
+
+typedef struct cq_capsule_cast { /* capsule axis is world +Y, `from` is the centre (:1025-1027) */
+    float from[3];
+    float delta[3];
+    float radius;
+    float half_height;
+    uint32_t mask;
+    float min_normal_y; /* CQ_CAST_GROUND only */
+} cq_capsule_cast;
+
+typedef struct cq_cast_hit { /* CapsuleCastHit, CollisionQuery.swift:36-43 */
+    float toi;
+    float position[3]; /* closest point ON THE TRIANGLE at toi (:1342) */
+    float normal[3];
+    float triangle_normal[3];
+    int32_t triangle_index; /* -1 = nil */
+} cq_cast_hit;
+
+typedef struct cq_capsule { /* capsuleOverlap / capsuleOverlapAll, CollisionQuery.swift:137,148 */
+    float from[3];
+    float radius;
+    float half_height;
+    uint32_t mask;
+} cq_capsule;
+
+typedef struct cq_overlap_hit { /* CapsuleOverlapHit, CollisionQuery.swift:45-52 */
+    float depth;
+    float position[3];
+    float normal[3];
+    float triangle_normal[3];
+    int32_t triangle_index; /* -1 = nil */
+} cq_overlap_hit;
+
+/* Host-pointer, synchronous batch calls (H2D, kernel, D2H inside the call). */
+int cq_raycast_batch(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out);
+int cq_capsule_cast_batch(cq_world *w, const cq_capsule_cast *q, int32_t n, int32_t mode,
+                          cq_cast_hit *out);
+int cq_capsule_overlap_batch(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out);
+/* out = n * max_hits records, sorted deepest first (ties: smaller triangle index);
+ * counts[i] = hits written for query i; overflow[i] (may be NULL) = 1 when more than
+ * max_hits triangles overlapped (the reference then keeps its first max_hits in DFS
+ * order, :1272-1274; this library keeps the deepest).  1 <= max_hits <= 8. */
+int cq_capsule_overlap_all_batch(cq_world *w, const cq_capsule *q, int32_t n, int32_t max_hits,
+                                 cq_overlap_hit *out, int32_t *counts, uint8_t *overflow);
+
+/* Device-pointer twins: inputs/outputs already resident in HBM, enqueued on
+ * `stream` (a cudaStream_t cast to void*; NULL = the world's own stream), no
+ * synchronisation.  Same record layouts as above. */
+int cq_raycast_device(cq_world *w, const cq_ray *d_rays, int32_t n, cq_ray_hit *d_out, void *stream);
+int cq_capsule_cast_device(cq_world *w, const cq_capsule_cast *d_q, int32_t n, int32_t mode,
+                           cq_cast_hit *d_out, void *stream);
+int cq_capsule_overlap_device(cq_world *w, const cq_capsule *d_q, int32_t n, cq_overlap_hit *d_out,
+                              void *stream);
+int cq_capsule_overlap_all_device(cq_world *w, const cq_capsule *d_q, int32_t n, int32_t max_hits,
+                                  cq_overlap_hit *d_out, int32_t *d_counts, uint8_t *d_overflow,
+                                  void *stream);
+
+/* ---- move-and-slide ------------------------------------------------------
+ * One call = one fixed step of KinematicMoveStopSystem.fixedUpdate's per-entity
+ * body (Systems.swift:1842-1901) for n independent characters, without kinematic
+ * platforms and agent hits (out of scope). */
+
+typedef struct cq_controller_params { /* CharacterControllerComponent tunables, Components.swift:353-404 */
+    float radius;               /* 1.5  */
+    float half_height;          /* 1.0  */
+    float skin_width;           /* 0.3  */
+    float ground_snap_skin;     /* 0.05 */
+    float snap_distance;        /* 0.8  */
+    float fall_probe_distance;  /* 200  */
+    float ground_snap_max_speed;/* 5    */
+    float ground_snap_max_toi;  /* 0.1  */
+    float ground_snap_max_step; /* 0.1  */
+    float ground_sweep_max_step;/* 0.1  */
+    int32_t max_slide_iterations; /* 4  */
+    float min_ground_dot;       /* 0.5  */
+    uint32_t collision_mask;    /* all  */
+} cq_controller_params;
+
+typedef struct cq_character_state { /* PhysicsBodyComponent + CharacterControllerComponent state */
+    double position[3];          /* PhysicsBodyComponent.position (Double), Components.swift:551 */
+    double velocity[3];          /* linearVelocity (Double) */
+    float ground_normal[3];
+    float ground_distance;
+    float side_contact_normal[3];
+    int32_t ground_triangle_index;
+    int32_t ground_transition_frames;
+    int32_t side_contact_frames;
+    int32_t manifold_frames;     /* contactManifoldFrames */
+    int32_t manifold_count;      /* contactManifoldTriangles.count */
+    int32_t manifold_triangles[CQ_MANIFOLD_MAX];
+    float manifold_normals[CQ_MANIFOLD_MAX][3];
+    uint8_t grounded;
+    uint8_t grounded_near;
+    uint8_t ground_sliding;
+    uint8_t _pad[5];
+} cq_character_state; /* 168 bytes */
+
+#define CQ_MAS_APPLY_GRAVITY 1u /* run GravitySystem's rule first (Systems.swift:603-619) */
+
+void cq_controller_params_default(cq_controller_params *p);
+void cq_character_state_init(cq_character_state *s, const float position[3], const float velocity[3]);
+
+int cq_move_and_slide_batch(cq_world *w, cq_character_state *inout, int32_t n,
+                            const cq_controller_params *params, float dt,
+                            const float gravity[3], uint32_t flags);
+int cq_move_and_slide_device(cq_world *w, cq_character_state *d_inout, int32_t n,
+                             const cq_controller_params *params, float dt,
+                             const float gravity[3], uint32_t flags, void *stream);
+
+/* ---- instrumentation ------------------------------------------------------
+ * Work counters of the last device/batch call, accumulated on the device when
+ * counting is enabled (off by default; the reference's CollisionQueryStats,
+ * CollisionQuery.swift:280-290, plus the node count the roofline formula needs). */
+typedef struct cq_counters {
+    uint64_t queries;          /* BVH traversals started */
+    uint64_t nodes_visited;    /* child boxes tested (32 B each, algorithmic) */
+    uint64_t candidates;       /* = capsuleCandidateCount: tri AABB overlaps swept AABB, layer ok */
+    uint64_t distance_evals;   /* segmentTriangleDistance evaluations actually executed */
+    uint64_t kernel_launches;  /* kernels launched by this library since the last reset */
+} cq_counters;
+int cq_world_set_counting(cq_world *w, int32_t enabled);
+int cq_world_read_counters(cq_world *w, cq_counters *out, int32_t reset);
+
+/* pinned host memory for the batch calls (optional; plain malloc'ed memory works too) */
+void *cq_host_alloc(size_t bytes);
+void cq_host_free(void *p);
+
+const char *cq_last_error(void);
+const char *cq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CQ_H */

@@ -1,0 +1,454 @@
+// cq_api.cu — the C ABI of include/cq.h: world lifetime, transforms/refit, batch + device query
+// entry points, counters.  No CPU fallback anywhere: every path needs a usable CUDA device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "cq_internal.h"
+
+namespace cq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return CQ_OK;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return CQ_ERR_CUDA;
+}
+
+int ensure_scratch(ScratchBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return CQ_OK;
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+    size_t cap = bytes + bytes / 4 + 256;
+    int r = check_cuda(cudaMalloc(&b.ptr, cap), "scratch cudaMalloc");
+    if (r == CQ_OK) b.cap = cap;
+    return r;
+}
+
+static void make_view(cq_world *w) {
+    for (int s = 0; s < 2; s++) {
+        DeviceSet &S = w->set[s];
+        SetView &v = w->view.set[s];
+        v.tv0 = S.tv0, v.tv1 = S.tv1, v.tv2 = S.tv2;
+        v.nodes = S.nodes;
+        v.hdr = S.hdr;
+        v.triOffset = s == 0 ? 0 : w->set[0].nTris;
+    }
+    w->view.materials = w->dMaterials;
+    w->view.nParts = (int)w->parts.size();
+}
+
+} // namespace cq
+
+using namespace cq;
+
+// ---------------------------------------------------------------- host-pointer (synchronous) entry points
+// Chunked and double-buffered: chunk k's H2D copy and chunk k-1's D2H copy overlap chunk k's kernel.
+template <class In, class Out, class Launch>
+static int run_batch(cq_world *w, const In *in, size_t inStride, Out *out, size_t outStride, int n, Launch launch,
+                     bool inPlace = false) {
+    if (n <= 0) return CQ_OK;
+    CQ_CUDA(cudaSetDevice(w->device));
+    const int CH = 1 << 17;
+    int chunk = n < 2 * CH ? n : CH;
+    int nbuf = n > chunk ? 2 : 1;
+    int r;
+    if ((r = ensure_scratch(w->in, (size_t)chunk * inStride * nbuf)) != CQ_OK) return r;
+    if (!inPlace && (r = ensure_scratch(w->out, (size_t)chunk * outStride * nbuf)) != CQ_OK) return r;
+    int k = 0;
+    for (int lo = 0; lo < n; lo += chunk, k++) {
+        int cnt = std::min(chunk, n - lo);
+        int b = k & 1;
+        cudaStream_t st = w->copyStream[b];
+        char *dIn = (char *)w->in.ptr + (size_t)b * chunk * inStride;
+        char *dOut = inPlace ? dIn : (char *)w->out.ptr + (size_t)b * chunk * outStride;
+        CQ_CUDA(cudaMemcpyAsync(dIn, (const char *)in + (size_t)lo * inStride, (size_t)cnt * inStride, cudaMemcpyHostToDevice, st));
+        r = launch(dIn, dOut, cnt, lo, st);
+        if (r != CQ_OK) return r;
+        CQ_CUDA(cudaMemcpyAsync((char *)out + (size_t)lo * outStride, dOut, (size_t)cnt * outStride, cudaMemcpyDeviceToHost, st));
+    }
+    CQ_CUDA(cudaStreamSynchronize(w->copyStream[0]));
+    CQ_CUDA(cudaStreamSynchronize(w->copyStream[1]));
+    return CQ_OK;
+}
+
+extern "C" {
+
+const char *cq_last_error(void) { return g_err; }
+const char *cq_version(void) { return "cq-b200 0.1 (sm_100a)"; }
+
+void *cq_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void cq_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+void cq_controller_params_default(cq_controller_params *p) { // Components.swift:380-404
+    p->radius = 1.5f;
+    p->half_height = 1.0f;
+    p->skin_width = 0.3f;
+    p->ground_snap_skin = 0.05f;
+    p->snap_distance = 0.8f;
+    p->fall_probe_distance = 200.0f;
+    p->ground_snap_max_speed = 5.0f;
+    p->ground_snap_max_toi = 0.1f;
+    p->ground_snap_max_step = 0.1f;
+    p->ground_sweep_max_step = 0.1f;
+    p->max_slide_iterations = 4;
+    p->min_ground_dot = 0.5f;
+    p->collision_mask = CQ_LAYER_ALL;
+}
+
+void cq_character_state_init(cq_character_state *s, const float position[3], const float velocity[3]) {
+    memset(s, 0, sizeof(*s));
+    for (int k = 0; k < 3; k++) {
+        s->position[k] = (double)position[k]; // PhysicsBodyComponent.init widens Float -> Double (Components.swift:566-575)
+        s->velocity[k] = velocity ? (double)velocity[k] : 0.0;
+    }
+    s->ground_normal[1] = 1.0f;
+    s->ground_distance = 3.402823466e+38f;
+    s->ground_triangle_index = -1;
+}
+
+int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) {
+    if (!out || n_parts < 0 || (n_parts > 0 && !parts)) {
+        set_error("cq_world_create: invalid arguments");
+        return CQ_ERR_INVALID;
+    }
+    *out = nullptr;
+    int dev = 0;
+    CQ_CUDA(cudaGetDevice(&dev));
+    cq_world *w = new cq_world();
+    w->device = dev;
+    int rc = CQ_OK;
+    auto fail = [&](int r) {
+        cq_world_destroy(w);
+        return r;
+    };
+    if ((rc = check_cuda(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking), "stream")) != CQ_OK) return fail(rc);
+    for (int k = 0; k < 2; k++)
+        if ((rc = check_cuda(cudaStreamCreateWithFlags(&w->copyStream[k], cudaStreamNonBlocking), "stream")) != CQ_OK)
+            return fail(rc);
+    if ((rc = check_cuda(cudaEventCreate(&w->evA), "event")) != CQ_OK) return fail(rc);
+    if ((rc = check_cuda(cudaEventCreate(&w->evB), "event")) != CQ_OK) return fail(rc);
+
+    // host-side assembly of the two sets' input arrays (partitionEntities, CollisionQuery.swift:886-900)
+    std::vector<float4> localPos[2];
+    std::vector<uint32_t> idxIn[2], layerIn[2];
+    std::vector<int32_t> partIn[2];
+    std::vector<int> partTriStart[2]; // per part of the set, then the end
+    std::vector<int> partOfSet[2];
+    std::vector<float> models((size_t)n_parts * 16);
+    std::vector<float4> materials(n_parts);
+    w->parts.resize(n_parts);
+    for (int p = 0; p < n_parts; p++) {
+        const cq_mesh_part &mp = parts[p];
+        if (mp.n_verts < 0 || mp.n_indices < 0 || (mp.n_verts > 0 && !mp.positions_xyz) || (mp.n_indices > 0 && !mp.indices)) {
+            set_error("cq_world_create: part %d has invalid arrays", p);
+            return fail(CQ_ERR_INVALID);
+        }
+        int s = mp.is_dynamic ? 1 : 0;
+        PartInfo &pi = w->parts[p];
+        pi.entityId = mp.entity_id;
+        pi.set = s;
+        pi.material = {mp.mu_s, mp.mu_k, mp.flatten_ground ? 1 : 0};
+        pi.layer = mp.layer;
+        memcpy(&models[(size_t)p * 16], mp.model, sizeof(float) * 16);
+        materials[p] = make_float4(mp.mu_s, mp.mu_k, mp.flatten_ground ? 1.0f : 0.0f, 0.0f);
+        int baseVertex = (int)localPos[s].size();
+        pi.vertLo = baseVertex;
+        for (int v = 0; v < mp.n_verts; v++)
+            localPos[s].push_back(make_float4(mp.positions_xyz[3 * v], mp.positions_xyz[3 * v + 1], mp.positions_xyz[3 * v + 2],
+                                              __builtin_bit_cast(float, (int32_t)p)));
+        pi.vertHi = (int)localPos[s].size();
+        partTriStart[s].push_back((int)layerIn[s].size());
+        partOfSet[s].push_back(p);
+        int nt = mp.n_indices / 3; // `while tri + 2 < count` (CollisionQuery.swift:376)
+        for (int t = 0; t < nt; t++) {
+            for (int k = 0; k < 3; k++) {
+                uint32_t li = mp.indices[3 * t + k];
+                if (li >= (uint32_t)mp.n_verts) {
+                    set_error("cq_world_create: part %d index %u out of range (%d vertices)", p, li, mp.n_verts);
+                    return fail(CQ_ERR_INVALID);
+                }
+                idxIn[s].push_back((uint32_t)baseVertex + li);
+            }
+            layerIn[s].push_back(mp.layer);
+            partIn[s].push_back(p);
+        }
+    }
+    for (int s = 0; s < 2; s++) partTriStart[s].push_back((int)layerIn[s].size());
+
+    if ((rc = check_cuda(cudaMalloc((void **)&w->dModels, sizeof(float) * 16 * (size_t)std::max(n_parts, 1)), "models")) != CQ_OK)
+        return fail(rc);
+    if ((rc = check_cuda(cudaMalloc((void **)&w->dMaterials, sizeof(float4) * (size_t)std::max(n_parts, 1)), "materials")) != CQ_OK)
+        return fail(rc);
+    if ((rc = check_cuda(cudaMalloc((void **)&w->dCounters, sizeof(unsigned long long) * 4), "counters")) != CQ_OK) return fail(rc);
+    cudaMemsetAsync(w->dCounters, 0, sizeof(unsigned long long) * 4, w->stream);
+    if (n_parts) {
+        cudaMemcpyAsync(w->dModels, models.data(), sizeof(float) * 16 * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
+        cudaMemcpyAsync(w->dMaterials, materials.data(), sizeof(float4) * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
+    }
+    cudaEventRecord(w->evA, w->stream);
+    for (int s = 0; s < 2; s++) {
+        rc = build_set(w, w->set[s], localPos[s], idxIn[s], layerIn[s], partIn[s], partTriStart[s]);
+        if (rc != CQ_OK) return fail(rc);
+        for (size_t k = 0; k < partOfSet[s].size(); k++) {
+            PartInfo &pi = w->parts[partOfSet[s][k]];
+            pi.triLo = partTriStart[s][k];
+            pi.triHi = partTriStart[s][k + 1];
+        }
+    }
+    cudaEventRecord(w->evB, w->stream);
+    if ((rc = check_cuda(cudaStreamSynchronize(w->stream), "build")) != CQ_OK) return fail(rc);
+    cudaEventElapsedTime(&w->buildMs, w->evA, w->evB);
+    make_view(w);
+    *out = w;
+    return CQ_OK;
+}
+
+void cq_world_destroy(cq_world *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    for (int s = 0; s < 2; s++) free_set(w->set[s]);
+    cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters);
+    cudaFree(w->in.ptr), cudaFree(w->out.ptr), cudaFree(w->aux.ptr), cudaFree(w->aux2.ptr);
+    if (w->evA) cudaEventDestroy(w->evA);
+    if (w->evB) cudaEventDestroy(w->evB);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    for (int k = 0; k < 2; k++)
+        if (w->copyStream[k]) cudaStreamDestroy(w->copyStream[k]);
+    delete w;
+}
+
+int cq_world_get_info(const cq_world *w, cq_world_info *info) {
+    if (!w || !info) return CQ_ERR_INVALID;
+    info->n_static_triangles = w->set[0].nTris;
+    info->n_dynamic_triangles = w->set[1].nTris;
+    info->n_static_vertices = w->set[0].nVerts;
+    info->n_dynamic_vertices = w->set[1].nVerts;
+    info->n_static_nodes = std::max(w->set[0].nTris - 1, 0);
+    info->n_dynamic_nodes = std::max(w->set[1].nTris - 1, 0);
+    info->n_parts = (int)w->parts.size();
+    info->device = w->device;
+    info->build_ms = w->buildMs;
+    info->refit_ms = w->refitMs;
+    return CQ_OK;
+}
+
+int cq_world_update_transforms(cq_world *w, const uint32_t *entity_ids, const float *models, int32_t n) {
+    if (!w || n < 0 || (n > 0 && (!entity_ids || !models))) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaSetDevice(w->device));
+    std::vector<int> changed[2];
+    for (int i = 0; i < n; i++) {
+        bool found = false;
+        for (size_t p = 0; p < w->parts.size(); p++) {
+            if (w->parts[p].entityId != entity_ids[i]) continue;
+            found = true;
+            // `guard let slice = slices[e]`: entities that contributed no triangle are skipped (CollisionQuery.swift:427)
+            if (w->parts[p].triHi <= w->parts[p].triLo) continue;
+            CQ_CUDA(cudaMemcpyAsync(w->dModels + 16 * p, models + 16 * (size_t)i, sizeof(float) * 16, cudaMemcpyHostToDevice, w->stream));
+            changed[w->parts[p].set].push_back((int)p);
+        }
+        if (!found) {
+            set_error("cq_world_update_transforms: unknown entity id %u", entity_ids[i]);
+            return CQ_ERR_NOT_FOUND;
+        }
+    }
+    cudaEventRecord(w->evA, w->stream);
+    for (int s = 0; s < 2; s++) {
+        if (changed[s].empty()) continue;
+        int rc = refit_set(w, w->set[s], changed[s]);
+        if (rc != CQ_OK) return rc;
+    }
+    cudaEventRecord(w->evB, w->stream);
+    CQ_CUDA(cudaStreamSynchronize(w->stream)); // the models array is the caller's; also makes refit_ms readable
+    cudaEventElapsedTime(&w->refitMs, w->evA, w->evB);
+    return CQ_OK;
+}
+
+int cq_world_read_soup(const cq_world *w, int32_t which, float *positions_xyz, uint32_t *indices, float *tri_aabbs,
+                       uint32_t *tri_layers, int32_t *tri_parts) {
+    if (!w || which < 0 || which > 1) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaSetDevice(w->device));
+    const DeviceSet &S = w->set[which];
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    std::vector<float4> pos(S.nVerts);
+    std::vector<uint32_t> idx((size_t)S.nTris * 3);
+    if (S.nVerts) CQ_CUDA(cudaMemcpy(pos.data(), S.worldPos, sizeof(float4) * (size_t)S.nVerts, cudaMemcpyDeviceToHost));
+    if (S.nTris) CQ_CUDA(cudaMemcpy(idx.data(), S.indices, sizeof(uint32_t) * 3 * (size_t)S.nTris, cudaMemcpyDeviceToHost));
+    if (positions_xyz)
+        for (int i = 0; i < S.nVerts; i++) {
+            positions_xyz[3 * i] = pos[i].x;
+            positions_xyz[3 * i + 1] = pos[i].y;
+            positions_xyz[3 * i + 2] = pos[i].z;
+        }
+    if (indices && S.nTris) memcpy(indices, idx.data(), sizeof(uint32_t) * idx.size());
+    if (tri_aabbs && S.nTris) {
+        // bounds as stored on the device: leaf boxes of the sorted order, scattered back to soup order
+        std::vector<float4> lo(S.nTris), hi(S.nTris);
+        std::vector<uint32_t> sorted(S.nTris);
+        CQ_CUDA(cudaMemcpy(lo.data(), S.boxLo + (S.nTris - 1), sizeof(float4) * (size_t)S.nTris, cudaMemcpyDeviceToHost));
+        CQ_CUDA(cudaMemcpy(hi.data(), S.boxHi + (S.nTris - 1), sizeof(float4) * (size_t)S.nTris, cudaMemcpyDeviceToHost));
+        CQ_CUDA(cudaMemcpy(sorted.data(), S.sortedTri, sizeof(uint32_t) * (size_t)S.nTris, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < S.nTris; s++) {
+            float *o = tri_aabbs + 6 * (size_t)sorted[s];
+            o[0] = lo[s].x, o[1] = lo[s].y, o[2] = lo[s].z, o[3] = hi[s].x, o[4] = hi[s].y, o[5] = hi[s].z;
+        }
+    }
+    if (tri_layers && S.nTris)
+        CQ_CUDA(cudaMemcpy(tri_layers, S.triLayer, sizeof(uint32_t) * (size_t)S.nTris, cudaMemcpyDeviceToHost));
+    if (tri_parts && S.nTris)
+        CQ_CUDA(cudaMemcpy(tri_parts, S.triPart, sizeof(int32_t) * (size_t)S.nTris, cudaMemcpyDeviceToHost));
+    return CQ_OK;
+}
+
+int cq_world_triangle_material(const cq_world *w, int32_t triangle_index, cq_material *out) {
+    if (!w || !out) return CQ_ERR_INVALID;
+    *out = {0.8f, 0.6f, 0}; // SurfaceMaterial.default
+    for (const PartInfo &p : w->parts) {
+        int off = p.set == 0 ? 0 : w->set[0].nTris;
+        if (triangle_index >= p.triLo + off && triangle_index < p.triHi + off) {
+            *out = p.material;
+            return CQ_OK;
+        }
+    }
+    return CQ_OK;
+}
+
+int cq_world_set_counting(cq_world *w, int32_t enabled) {
+    if (!w) return CQ_ERR_INVALID;
+    w->counting = enabled ? 1 : 0;
+    return CQ_OK;
+}
+
+int cq_world_read_counters(cq_world *w, cq_counters *out, int32_t reset) {
+    if (!w || !out) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaSetDevice(w->device));
+    unsigned long long h[4];
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    CQ_CUDA(cudaMemcpy(h, w->dCounters, sizeof(h), cudaMemcpyDeviceToHost));
+    out->nodes_visited = h[0];
+    out->candidates = h[1];
+    out->distance_evals = h[2];
+    out->queries = h[3];
+    out->kernel_launches = w->launches;
+    if (reset) {
+        CQ_CUDA(cudaMemset(w->dCounters, 0, sizeof(h)));
+        w->launches = 0;
+    }
+    return CQ_OK;
+}
+
+// ---------------------------------------------------------------- device-pointer entry points
+static cudaStream_t pick_stream(cq_world *w, void *stream) { return stream ? (cudaStream_t)stream : w->stream; }
+
+int cq_raycast_device(cq_world *w, const cq_ray *d_rays, int32_t n, cq_ray_hit *d_out, void *stream) {
+    if (!w || n < 0 || (n > 0 && (!d_rays || !d_out))) return CQ_ERR_INVALID;
+    return launch_raycast(w, d_rays, n, d_out, pick_stream(w, stream));
+}
+int cq_capsule_cast_device(cq_world *w, const cq_capsule_cast *d_q, int32_t n, int32_t mode, cq_cast_hit *d_out, void *stream) {
+    if (!w || n < 0 || mode < 0 || mode > 2 || (n > 0 && (!d_q || !d_out))) return CQ_ERR_INVALID;
+    return launch_cast(w, d_q, n, mode, d_out, pick_stream(w, stream));
+}
+int cq_capsule_overlap_device(cq_world *w, const cq_capsule *d_q, int32_t n, cq_overlap_hit *d_out, void *stream) {
+    if (!w || n < 0 || (n > 0 && (!d_q || !d_out))) return CQ_ERR_INVALID;
+    return launch_overlap(w, d_q, n, d_out, pick_stream(w, stream));
+}
+int cq_capsule_overlap_all_device(cq_world *w, const cq_capsule *d_q, int32_t n, int32_t max_hits, cq_overlap_hit *d_out,
+                                  int32_t *d_counts, uint8_t *d_overflow, void *stream) {
+    if (!w || n < 0 || (n > 0 && (!d_q || !d_out || !d_counts))) return CQ_ERR_INVALID;
+    if (max_hits < 1) max_hits = 1; // max(1, maxHits), CollisionQuery.swift:157
+    if (max_hits > CQ_MAX_OVERLAP_HITS) {
+        set_error("max_hits %d > %d", max_hits, CQ_MAX_OVERLAP_HITS);
+        return CQ_ERR_INVALID;
+    }
+    return launch_overlap_all(w, d_q, n, max_hits, d_out, d_counts, d_overflow, pick_stream(w, stream));
+}
+int cq_move_and_slide_device(cq_world *w, cq_character_state *d_inout, int32_t n, const cq_controller_params *params, float dt,
+                             const float gravity[3], uint32_t flags, void *stream) {
+    if (!w || n < 0 || !params || !gravity || (n > 0 && !d_inout)) return CQ_ERR_INVALID;
+    return launch_move_and_slide(w, d_inout, n, *params, dt, gravity, flags, pick_stream(w, stream));
+}
+
+int cq_raycast_batch(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out) {
+    if (!w || n < 0 || (n > 0 && (!rays || !out))) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    return run_batch(w, rays, sizeof(cq_ray), out, sizeof(cq_ray_hit), n,
+                     [&](void *di, void *dout, int cnt, int, cudaStream_t st) {
+                         return launch_raycast(w, (const cq_ray *)di, cnt, (cq_ray_hit *)dout, st);
+                     });
+}
+
+int cq_capsule_cast_batch(cq_world *w, const cq_capsule_cast *q, int32_t n, int32_t mode, cq_cast_hit *out) {
+    if (!w || n < 0 || mode < 0 || mode > 2 || (n > 0 && (!q || !out))) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    return run_batch(w, q, sizeof(cq_capsule_cast), out, sizeof(cq_cast_hit), n,
+                     [&](void *di, void *dout, int cnt, int, cudaStream_t st) {
+                         return launch_cast(w, (const cq_capsule_cast *)di, cnt, mode, (cq_cast_hit *)dout, st);
+                     });
+}
+
+int cq_capsule_overlap_batch(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out) {
+    if (!w || n < 0 || (n > 0 && (!q || !out))) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    return run_batch(w, q, sizeof(cq_capsule), out, sizeof(cq_overlap_hit), n,
+                     [&](void *di, void *dout, int cnt, int, cudaStream_t st) {
+                         return launch_overlap(w, (const cq_capsule *)di, cnt, (cq_overlap_hit *)dout, st);
+                     });
+}
+
+int cq_capsule_overlap_all_batch(cq_world *w, const cq_capsule *q, int32_t n, int32_t max_hits, cq_overlap_hit *out,
+                                 int32_t *counts, uint8_t *overflow) {
+    if (!w || n < 0 || (n > 0 && (!q || !out || !counts))) return CQ_ERR_INVALID;
+    if (max_hits < 1) max_hits = 1;
+    if (max_hits > CQ_MAX_OVERLAP_HITS) {
+        set_error("max_hits %d > %d", max_hits, CQ_MAX_OVERLAP_HITS);
+        return CQ_ERR_INVALID;
+    }
+    if (n == 0) return CQ_OK;
+    CQ_CUDA(cudaSetDevice(w->device));
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    cudaStream_t st = w->stream;
+    int r;
+    if ((r = ensure_scratch(w->in, sizeof(cq_capsule) * (size_t)n)) != CQ_OK) return r;
+    if ((r = ensure_scratch(w->out, sizeof(cq_overlap_hit) * (size_t)n * max_hits)) != CQ_OK) return r;
+    if ((r = ensure_scratch(w->aux, sizeof(int32_t) * (size_t)n)) != CQ_OK) return r;
+    if ((r = ensure_scratch(w->aux2, (size_t)n)) != CQ_OK) return r;
+    CQ_CUDA(cudaMemcpyAsync(w->in.ptr, q, sizeof(cq_capsule) * (size_t)n, cudaMemcpyHostToDevice, st));
+    r = launch_overlap_all(w, (const cq_capsule *)w->in.ptr, n, max_hits, (cq_overlap_hit *)w->out.ptr, (int32_t *)w->aux.ptr,
+                           (uint8_t *)w->aux2.ptr, st);
+    if (r != CQ_OK) return r;
+    CQ_CUDA(cudaMemcpyAsync(out, w->out.ptr, sizeof(cq_overlap_hit) * (size_t)n * max_hits, cudaMemcpyDeviceToHost, st));
+    CQ_CUDA(cudaMemcpyAsync(counts, w->aux.ptr, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (overflow) CQ_CUDA(cudaMemcpyAsync(overflow, w->aux2.ptr, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CQ_CUDA(cudaStreamSynchronize(st));
+    return CQ_OK;
+}
+
+int cq_move_and_slide_batch(cq_world *w, cq_character_state *inout, int32_t n, const cq_controller_params *params, float dt,
+                            const float gravity[3], uint32_t flags) {
+    if (!w || n < 0 || !params || !gravity || (n > 0 && !inout)) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    return run_batch(w, inout, sizeof(cq_character_state), inout, sizeof(cq_character_state), n,
+                     [&](void *di, void *, int cnt, int, cudaStream_t st) {
+                         return launch_move_and_slide(w, (cq_character_state *)di, cnt, *params, dt, gravity, flags, st);
+                     },
+                     /*inPlace=*/true);
+}
+
+} // extern "C"

@@ -1,0 +1,595 @@
+// cq_build.cu — mesh upload + LBVH build/refit on the device (sm_100a).
+//
+// Replaces, B200-first, what the reference does on one CPU thread:
+//   TriangleMeshSet.rebuild           CollisionQuery.swift:331-417  -> k_transform, k_filter_flags, k_compact
+//   StaticTriMesh.BVH.build (top-down median split, :577-670) -> LBVH: k_centroid_bounds, k_morton,
+//        radix sort (rs_*), k_karras (Karras 2012 radix tree), k_fit (bottom-up boxes)
+//   TriangleMeshSet.updateTransforms  :419-462 + BVH.refit :528-575 -> k_transform_range + k_gather + k_fit
+// The tree differs from the reference's (allowed: capsule candidate sets are tree-independent,
+// SURVEY.md §A.4); triangle NUMBERING and world-space vertices are bit-identical to the reference's.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "cq_internal.h"
+
+namespace cq {
+
+// ---------------------------------------------------------------- small helpers
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// simd_mul(modelMatrix, (p,1)) = ((c0*x + c1*y) + c2*z) + c3*1   (CollisionQuery.swift:349-351)
+__device__ __forceinline__ float4 transform_point(const float *m, float4 p) {
+    float x = ((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12] * 1.0f;
+    float y = ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13] * 1.0f;
+    float z = ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14] * 1.0f;
+    return make_float4(x, y, z, 0.0f);
+}
+
+__global__ void k_transform(const float4 *__restrict__ local, float4 *__restrict__ world, const float *__restrict__ models,
+                            int lo, int hi) {
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    float4 p = local[i];
+    world[i] = transform_point(models + 16 * __float_as_int(p.w), p);
+}
+
+// keep flag: |cross(e1,e2)|^2 > 1e-10 in WORLD space (CollisionQuery.swift:383-389)
+__global__ void k_filter_flags(const float4 *__restrict__ world, const uint32_t *__restrict__ idxIn, int nTrisIn,
+                               uint32_t *__restrict__ flags) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTrisIn) return;
+    f3 p0 = xyz(world[idxIn[3 * t]]), p1 = xyz(world[idxIn[3 * t + 1]]), p2 = xyz(world[idxIn[3 * t + 2]]);
+    f3 e1 = p1 - p0, e2 = p2 - p0;
+    flags[t] = len2(cross(e1, e2)) <= 1e-10f ? 0u : 1u;
+}
+
+// ---------------------------------------------------------------- exclusive scan (u32), 3 kernels
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *smemWarp /*[32]*/, uint32_t &total) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) smemWarp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (blockDim.x >> 5) ? smemWarp[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        smemWarp[lane] = winc - w; // exclusive warp base
+        if (lane == 31) smemWarp[32] = winc;
+    }
+    __syncthreads();
+    total = smemWarp[32];
+    uint32_t r = smemWarp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void k_scan_tile_sums(const uint32_t *__restrict__ in, int n, uint32_t *__restrict__ tileSums) {
+    __shared__ uint32_t sw[33];
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) s += in[base + k];
+    uint32_t total;
+    block_exclusive_scan(s, sw, total);
+    if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+// single-block in-place exclusive scan of `n` entries (n up to a few million; L2 resident)
+__global__ void k_scan_single_block(uint32_t *__restrict__ data, int n, uint32_t *__restrict__ totalOut) {
+    __shared__ uint32_t sw[33];
+    int per = (n + blockDim.x - 1) / blockDim.x;
+    int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; i++) s += data[i];
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(s, sw, total);
+    for (int i = lo; i < hi; i++) {
+        uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0 && totalOut) *totalOut = total;
+}
+
+__global__ void k_scan_apply(const uint32_t *__restrict__ in, int n, const uint32_t *__restrict__ tileBase,
+                             uint32_t *__restrict__ out) {
+    __shared__ uint32_t sw[33];
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(s, sw, total) + tileBase[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void k_compact(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ offs, int nTrisIn,
+                          const uint32_t *__restrict__ idxIn, const uint32_t *__restrict__ layerIn,
+                          const int32_t *__restrict__ partIn, uint32_t *__restrict__ idxOut,
+                          uint32_t *__restrict__ layerOut, int32_t *__restrict__ partOut) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTrisIn || !flags[t]) return;
+    uint32_t o = offs[t];
+    idxOut[3 * o] = idxIn[3 * t];
+    idxOut[3 * o + 1] = idxIn[3 * t + 1];
+    idxOut[3 * o + 2] = idxIn[3 * t + 2];
+    layerOut[o] = layerIn[t];
+    partOut[o] = partIn[t];
+}
+
+__global__ void k_gather_u32(const uint32_t *__restrict__ src, const int32_t *__restrict__ pos, int n,
+                             uint32_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[pos[i]];
+}
+
+// ---------------------------------------------------------------- Morton codes
+// bounds[0..2] = ordered-int min of triangle-AABB centroids, [3..5] = max
+__global__ void k_init_bounds(int *bounds) {
+    if (threadIdx.x < 3) bounds[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = (int)0x80000000;
+}
+
+__device__ __forceinline__ f3 tri_centroid(const float4 *__restrict__ world, const uint32_t *__restrict__ idx, int t) {
+    f3 p0 = xyz(world[idx[3 * t]]), p1 = xyz(world[idx[3 * t + 1]]), p2 = xyz(world[idx[3 * t + 2]]);
+    f3 lo = vmin(p0, vmin(p1, p2)), hi = vmax(p0, vmax(p1, p2));
+    return (lo + hi) * 0.5f; // BVH.centroid, CollisionQuery.swift:700
+}
+
+__global__ void k_centroid_bounds(const float4 *__restrict__ world, const uint32_t *__restrict__ idx, int nTris,
+                                  int *__restrict__ bounds) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 lo = {FLT_MAX, FLT_MAX, FLT_MAX}, hi = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (t < nTris) lo = hi = tri_centroid(world, idx, t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(bounds + 0, float_to_ordered(lo.x));
+        atomicMin(bounds + 1, float_to_ordered(lo.y));
+        atomicMin(bounds + 2, float_to_ordered(lo.z));
+        atomicMax(bounds + 3, float_to_ordered(hi.x));
+        atomicMax(bounds + 4, float_to_ordered(hi.y));
+        atomicMax(bounds + 5, float_to_ordered(hi.z));
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) { // 10 bits -> every third bit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_morton(const float4 *__restrict__ world, const uint32_t *__restrict__ idx, int nTris,
+                         const int *__restrict__ bounds, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTris) return;
+    f3 lo = {ordered_to_float(bounds[0]), ordered_to_float(bounds[1]), ordered_to_float(bounds[2])};
+    f3 hi = {ordered_to_float(bounds[3]), ordered_to_float(bounds[4]), ordered_to_float(bounds[5])};
+    f3 c = tri_centroid(world, idx, t);
+    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    float sx = ex > 0.0f ? 1024.0f / ex : 0.0f, sy = ey > 0.0f ? 1024.0f / ey : 0.0f, sz = ez > 0.0f ? 1024.0f / ez : 0.0f;
+    uint32_t qx = min(1023u, (uint32_t)fmaxf((c.x - lo.x) * sx, 0.0f));
+    uint32_t qy = min(1023u, (uint32_t)fmaxf((c.y - lo.y) * sy, 0.0f));
+    uint32_t qz = min(1023u, (uint32_t)fmaxf((c.z - lo.z) * sz, 0.0f));
+    keys[t] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz); // 30-bit Morton
+    vals[t] = (uint32_t)t;
+}
+
+// ---------------------------------------------------------------- LSD radix sort, 8-bit digits, key/value u32
+// Per pass: tile histograms -> single-block scan (digit-major) -> stable scatter with warp
+// match/ballot ranking.  4 passes cover the 30-bit Morton key (+2 always-zero bits).
+#define RS_THREADS 256
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+#define RS_WARPS (RS_THREADS / 32)
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t *__restrict__ keys, int n, int shift,
+                                                        uint32_t *__restrict__ hist, int nBlocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * nBlocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__restrict__ keysIn,
+                                                           const uint32_t *__restrict__ valsIn,
+                                                           uint32_t *__restrict__ keysOut,
+                                                           uint32_t *__restrict__ valsOut, int n, int shift,
+                                                           const uint32_t *__restrict__ histScanned, int nBlocks) {
+    __shared__ uint32_t wh[RS_WARPS][256];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    int base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], off[RS_ITEMS];
+    const uint32_t ltMask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = base + r * 32 + lane;
+        bool valid = i < n;
+        key[r] = valid ? keysIn[i] : 0u;
+        val[r] = valid ? valsIn[i] : 0u;
+        uint32_t digit = valid ? ((key[r] >> shift) & 255u) : (256u + lane);
+        uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = wh[warp][digit];
+            wh[warp][digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        off[r] = old + __popc(peers & ltMask);
+        __syncwarp();
+    }
+    __syncthreads();
+    { // digit d = threadIdx.x: exclusive prefix over warps + global base of (digit, block)
+        uint32_t run = histScanned[threadIdx.x * nBlocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = wh[w][threadIdx.x];
+            wh[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = base + r * 32 + lane;
+        if (i < n) {
+            uint32_t digit = (key[r] >> shift) & 255u;
+            uint32_t o = wh[warp][digit] + off[r];
+            keysOut[o] = key[r];
+            valsOut[o] = val[r];
+        }
+    }
+}
+
+// NB: k_rs_hist walks the tile thread-strided while k_rs_scatter walks it warp-chunked; both count the
+// same multiset per tile, which is all the histogram needs.
+
+// ---------------------------------------------------------------- gather into the sorted float4 SoA
+__global__ void k_gather_sorted(const uint32_t *__restrict__ sortedTri, int nTris, const float4 *__restrict__ world,
+                                const uint32_t *__restrict__ idx, const uint32_t *__restrict__ layer,
+                                const int32_t *__restrict__ part, float4 *__restrict__ tv0, float4 *__restrict__ tv1,
+                                float4 *__restrict__ tv2) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nTris) return;
+    uint32_t t = sortedTri[s];
+    float4 a = world[idx[3 * t]], b = world[idx[3 * t + 1]], c = world[idx[3 * t + 2]];
+    a.w = __uint_as_float(layer[t]);
+    b.w = __int_as_float((int)t);
+    c.w = __int_as_float(part[t]);
+    tv0[s] = a;
+    tv1[s] = b;
+    tv2[s] = c;
+}
+
+// ---------------------------------------------------------------- Karras 2012 radix tree
+__device__ __forceinline__ int delta_fn(const uint32_t *__restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j); // duplicate keys: fall back to the index
+    return __clz(a ^ b);
+}
+
+__device__ __forceinline__ int leaf_ref(int start, int count) { return ~((start << 2) | (count - 1)); }
+
+__global__ void k_karras(const uint32_t *__restrict__ keys, int n, Node *__restrict__ nodes, int32_t *__restrict__ parent,
+                         int32_t *__restrict__ rangeLo, int32_t *__restrict__ rangeHi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta_fn(keys, n, i, i + 1) - delta_fn(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_fn(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta_fn(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t > 0; t >>= 1)
+        if (delta_fn(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_fn(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_fn(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    rangeLo[i] = first;
+    rangeHi[i] = last;
+    // children: [first, gamma] and [gamma+1, last]
+    int leftIsLeaf = first == gamma, rightIsLeaf = last == gamma + 1;
+    int leftBox = leftIsLeaf ? (n - 1) + gamma : gamma;             // index into boxLo/boxHi/parent
+    int rightBox = rightIsLeaf ? (n - 1) + gamma + 1 : gamma + 1;
+    parent[leftBox] = i;
+    parent[rightBox] = i;
+    if (i == 0) parent[0] = -1;
+    int lc = gamma - first + 1, rc = last - gamma;
+    int ref0 = lc <= 4 ? leaf_ref(first, lc) : gamma;
+    int ref1 = rc <= 4 ? leaf_ref(gamma + 1, rc) : gamma + 1;
+    nodes[i].n0.w = __int_as_float(ref0);
+    nodes[i].n1.w = __int_as_float(ref1);
+    // box slots of the children, stashed until k_fit overwrites n2.w/n3.w are unused afterwards
+    nodes[i].n2.w = __int_as_float(leftBox);
+    nodes[i].n3.w = __int_as_float(rightBox);
+}
+
+// bottom-up boxes: one thread per leaf slot climbs while it is the second to arrive
+__global__ void k_fit(int n, const float4 *__restrict__ tv0, const float4 *__restrict__ tv1,
+                      const float4 *__restrict__ tv2, Node *__restrict__ nodes, const int32_t *__restrict__ parent,
+                      float4 *__restrict__ boxLo, float4 *__restrict__ boxHi, int32_t *__restrict__ visit) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    f3 a = xyz(tv0[s]), b = xyz(tv1[s]), c = xyz(tv2[s]);
+    f3 lo = vmin(a, vmin(b, c)), hi = vmax(a, vmax(b, c));
+    int me = (n - 1) + s;
+    boxLo[me] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    boxHi[me] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    if (n == 1) return;
+    __threadfence();
+    int p = parent[me];
+    while (p >= 0) {
+        if (atomicAdd(&visit[p], 1) == 0) return; // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        Node nd = nodes[p];
+        int lb = __float_as_int(nd.n2.w), rb = __float_as_int(nd.n3.w);
+        // volatile-ish reads: boxes were published before the sibling's atomicAdd
+        float4 l0 = __ldcg(boxLo + lb), h0 = __ldcg(boxHi + lb), l1 = __ldcg(boxLo + rb), h1 = __ldcg(boxHi + rb);
+        nd.n0 = make_float4(l0.x, l0.y, l0.z, nd.n0.w);
+        nd.n1 = make_float4(h0.x, h0.y, h0.z, nd.n1.w);
+        nd.n2 = make_float4(l1.x, l1.y, l1.z, nd.n2.w);
+        nd.n3 = make_float4(h1.x, h1.y, h1.z, nd.n3.w);
+        nodes[p] = nd;
+        boxLo[p] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
+        boxHi[p] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
+        __threadfence();
+        p = parent[p];
+    }
+}
+
+__global__ void k_header(int n, const float4 *__restrict__ boxLo, const float4 *__restrict__ boxHi, SetHeader *hdr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    SetHeader h;
+    h.nTris = n;
+    if (n == 0) {
+        h.rootRef = CQ_REF_EMPTY;
+        h.lo[0] = h.lo[1] = h.lo[2] = FLT_MAX;
+        h.hi[0] = h.hi[1] = h.hi[2] = -FLT_MAX;
+    } else {
+        int rootBox = n == 1 ? 0 : 0; // n==1: leaf slot 0 lives at index (n-1)+0 = 0 as well
+        h.rootRef = n <= 4 ? leaf_ref(0, n) : 0;
+        float4 lo = boxLo[rootBox], hi = boxHi[rootBox];
+        h.lo[0] = lo.x, h.lo[1] = lo.y, h.lo[2] = lo.z;
+        h.hi[0] = hi.x, h.hi[1] = hi.y, h.hi[2] = hi.z;
+    }
+    *hdr = h;
+}
+
+// ---------------------------------------------------------------- host orchestration
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+template <class T> static int dalloc(T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return check_cuda(cudaMalloc((void **)p, count * sizeof(T)), "cudaMalloc");
+}
+
+void free_set(DeviceSet &S) {
+    cudaFree(S.localPos), cudaFree(S.worldPos), cudaFree(S.indices), cudaFree(S.triLayer), cudaFree(S.triPart);
+    cudaFree(S.sortedTri), cudaFree(S.tv0), cudaFree(S.tv1), cudaFree(S.tv2), cudaFree(S.nodes), cudaFree(S.parent);
+    cudaFree(S.rangeLo), cudaFree(S.rangeHi), cudaFree(S.boxLo), cudaFree(S.boxHi), cudaFree(S.visit), cudaFree(S.hdr);
+    S = DeviceSet();
+}
+
+static int exclusive_scan_u32(cq_world *w, const uint32_t *in, int n, uint32_t *out, uint32_t *tileSums /* cdiv(n,TILE)+1 */,
+                              uint32_t *dTotal) {
+    cudaStream_t st = w->stream;
+    int tiles = cdiv(n, SCAN_TILE);
+    k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(in, n, tileSums);
+    k_scan_single_block<<<1, 1024, 0, st>>>(tileSums, tiles, dTotal);
+    k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(in, n, tileSums, out);
+    w->launches += 3;
+    return check_cuda(cudaGetLastError(), "scan");
+}
+
+static int radix_sort_pairs(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTmp, uint32_t *valsTmp, int n,
+                            uint32_t *hist /* 256 * nBlocks */) {
+    cudaStream_t st = w->stream;
+    int nBlocks = cdiv(n, RS_TILE);
+    uint32_t *kin = keys, *vin = vals, *kout = keysTmp, *vout = valsTmp;
+    for (int pass = 0; pass < 4; pass++) {
+        int shift = pass * 8;
+        k_rs_hist<<<nBlocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, nBlocks);
+        k_scan_single_block<<<1, 1024, 0, st>>>(hist, 256 * nBlocks, nullptr);
+        k_rs_scatter<<<nBlocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, nBlocks);
+        w->launches += 3;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    // 4 passes: result is back in (keys, vals)
+    return check_cuda(cudaGetLastError(), "radix sort");
+}
+
+static int build_tree(cq_world *w, DeviceSet &S, const uint32_t *sortedKeys /* may be null on refit */) {
+    cudaStream_t st = w->stream;
+    int n = S.nTris;
+    if (n > 0) {
+        k_gather_sorted<<<cdiv(n, 256), 256, 0, st>>>(S.sortedTri, n, S.worldPos, S.indices, S.triLayer, S.triPart, S.tv0,
+                                                      S.tv1, S.tv2);
+        w->launches++;
+        if (n > 1) {
+            if (sortedKeys) {
+                k_karras<<<cdiv(n - 1, 256), 256, 0, st>>>(sortedKeys, n, S.nodes, S.parent, S.rangeLo, S.rangeHi);
+                w->launches++;
+            }
+            CQ_CUDA(cudaMemsetAsync(S.visit, 0, sizeof(int32_t) * (size_t)(n - 1), st));
+        }
+        k_fit<<<cdiv(n, 256), 256, 0, st>>>(n, S.tv0, S.tv1, S.tv2, S.nodes, S.parent, S.boxLo, S.boxHi, S.visit);
+        w->launches++;
+    }
+    k_header<<<1, 32, 0, st>>>(n, S.boxLo, S.boxHi, S.hdr);
+    w->launches++;
+    return check_cuda(cudaGetLastError(), "build_tree");
+}
+
+int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,
+              const std::vector<uint32_t> &triLayerIn, const std::vector<int32_t> &triPartIn,
+              std::vector<int> &partTriStartIn /* in: first input triangle of each part of this set (+ end), out: filtered */) {
+    cudaStream_t st = w->stream;
+    S.nVerts = (int)localPos.size();
+    S.nTrisIn = (int)triLayerIn.size();
+    int nIn = S.nTrisIn;
+    CQ_TRY(dalloc(&S.localPos, (size_t)S.nVerts));
+    CQ_TRY(dalloc(&S.worldPos, (size_t)S.nVerts));
+    CQ_TRY(dalloc(&S.hdr, 1));
+    uint32_t *dIdxIn = nullptr, *dLayerIn = nullptr, *dFlags = nullptr, *dOffs = nullptr, *dTileSums = nullptr, *dTotal = nullptr;
+    int32_t *dPartIn = nullptr;
+    CQ_TRY(dalloc(&dIdxIn, (size_t)nIn * 3));
+    CQ_TRY(dalloc(&dLayerIn, (size_t)nIn));
+    CQ_TRY(dalloc(&dPartIn, (size_t)nIn));
+    CQ_TRY(dalloc(&dFlags, (size_t)nIn));
+    CQ_TRY(dalloc(&dOffs, (size_t)nIn + 1));
+    CQ_TRY(dalloc(&dTileSums, (size_t)cdiv(std::max(nIn, 1), SCAN_TILE) + 1));
+    CQ_TRY(dalloc(&dTotal, 1));
+    if (S.nVerts)
+        CQ_CUDA(cudaMemcpyAsync(S.localPos, localPos.data(), sizeof(float4) * (size_t)S.nVerts, cudaMemcpyHostToDevice, st));
+    if (nIn) {
+        CQ_CUDA(cudaMemcpyAsync(dIdxIn, indicesIn.data(), sizeof(uint32_t) * 3 * (size_t)nIn, cudaMemcpyHostToDevice, st));
+        CQ_CUDA(cudaMemcpyAsync(dLayerIn, triLayerIn.data(), sizeof(uint32_t) * (size_t)nIn, cudaMemcpyHostToDevice, st));
+        CQ_CUDA(cudaMemcpyAsync(dPartIn, triPartIn.data(), sizeof(int32_t) * (size_t)nIn, cudaMemcpyHostToDevice, st));
+    }
+    uint32_t total = 0;
+    if (S.nVerts) {
+        k_transform<<<cdiv(S.nVerts, 256), 256, 0, st>>>(S.localPos, S.worldPos, w->dModels, 0, S.nVerts);
+        w->launches++;
+    }
+    if (nIn) {
+        k_filter_flags<<<cdiv(nIn, 256), 256, 0, st>>>(S.worldPos, dIdxIn, nIn, dFlags);
+        w->launches++;
+        int r = exclusive_scan_u32(w, dFlags, nIn, dOffs, dTileSums, dTotal);
+        if (r != CQ_OK) return r;
+        CQ_CUDA(cudaMemcpyAsync(&total, dTotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaStreamSynchronize(st));
+        // dOffs[nIn] = total, so slice ends can be gathered uniformly
+        CQ_CUDA(cudaMemcpyAsync(dOffs + nIn, &total, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    S.nTris = (int)total;
+    int n = S.nTris;
+    CQ_TRY(dalloc(&S.indices, (size_t)n * 3));
+    CQ_TRY(dalloc(&S.triLayer, (size_t)n));
+    CQ_TRY(dalloc(&S.triPart, (size_t)n));
+    CQ_TRY(dalloc(&S.sortedTri, (size_t)n));
+    CQ_TRY(dalloc(&S.tv0, (size_t)n));
+    CQ_TRY(dalloc(&S.tv1, (size_t)n));
+    CQ_TRY(dalloc(&S.tv2, (size_t)n));
+    CQ_TRY(dalloc(&S.nodes, (size_t)std::max(n - 1, 1)));
+    CQ_TRY(dalloc(&S.parent, (size_t)std::max(2 * n - 1, 1)));
+    CQ_TRY(dalloc(&S.rangeLo, (size_t)std::max(n - 1, 1)));
+    CQ_TRY(dalloc(&S.rangeHi, (size_t)std::max(n - 1, 1)));
+    CQ_TRY(dalloc(&S.boxLo, (size_t)std::max(2 * n - 1, 1)));
+    CQ_TRY(dalloc(&S.boxHi, (size_t)std::max(2 * n - 1, 1)));
+    CQ_TRY(dalloc(&S.visit, (size_t)std::max(n - 1, 1)));
+    // filtered slice boundaries of each part
+    if (nIn && !partTriStartIn.empty()) {
+        int np = (int)partTriStartIn.size();
+        int32_t *dPos = nullptr;
+        uint32_t *dOut = nullptr;
+        CQ_TRY(dalloc(&dPos, (size_t)np));
+        CQ_TRY(dalloc(&dOut, (size_t)np));
+        CQ_CUDA(cudaMemcpyAsync(dPos, partTriStartIn.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, st));
+        k_gather_u32<<<cdiv(np, 256), 256, 0, st>>>(dOffs, dPos, np, dOut);
+        w->launches++;
+        std::vector<uint32_t> outv(np);
+        CQ_CUDA(cudaMemcpyAsync(outv.data(), dOut, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < np; i++) partTriStartIn[i] = (int)outv[i];
+        cudaFree(dPos), cudaFree(dOut);
+    } else {
+        for (auto &v : partTriStartIn) v = 0;
+    }
+    int rc = CQ_OK;
+    if (n > 0) {
+        k_compact<<<cdiv(nIn, 256), 256, 0, st>>>(dFlags, dOffs, nIn, dIdxIn, dLayerIn, dPartIn, S.indices, S.triLayer, S.triPart);
+        w->launches++;
+        int *dBounds = nullptr;
+        uint32_t *dKeys = nullptr, *dKeysTmp = nullptr, *dValsTmp = nullptr, *dHist = nullptr;
+        CQ_TRY(dalloc(&dBounds, 8));
+        CQ_TRY(dalloc(&dKeys, (size_t)n));
+        CQ_TRY(dalloc(&dKeysTmp, (size_t)n));
+        CQ_TRY(dalloc(&dValsTmp, (size_t)n));
+        CQ_TRY(dalloc(&dHist, (size_t)256 * cdiv(n, RS_TILE)));
+        k_init_bounds<<<1, 32, 0, st>>>(dBounds);
+        k_centroid_bounds<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds);
+        k_morton<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds, dKeys, S.sortedTri);
+        w->launches += 3;
+        rc = radix_sort_pairs(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist);
+        if (rc == CQ_OK) rc = build_tree(w, S, dKeys);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (rc == CQ_OK) rc = check_cuda(e, "build sync");
+        cudaFree(dBounds), cudaFree(dKeys), cudaFree(dKeysTmp), cudaFree(dValsTmp), cudaFree(dHist);
+    } else {
+        rc = build_tree(w, S, nullptr);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (rc == CQ_OK) rc = check_cuda(e, "build sync");
+    }
+    cudaFree(dIdxIn), cudaFree(dLayerIn), cudaFree(dPartIn), cudaFree(dFlags), cudaFree(dOffs), cudaFree(dTileSums), cudaFree(dTotal);
+    return rc;
+}
+
+// TriangleMeshSet.updateTransforms + BVH.refit: re-transform the changed parts' vertices, regather the
+// sorted SoA, recompute every box bottom-up (same tree topology).  Asynchronous on the world stream.
+int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx) {
+    cudaStream_t st = w->stream;
+    for (int pi : partIdx) {
+        const PartInfo &p = w->parts[pi];
+        int nv = p.vertHi - p.vertLo;
+        if (nv <= 0) continue;
+        k_transform<<<cdiv(nv, 256), 256, 0, st>>>(S.localPos, S.worldPos, w->dModels, p.vertLo, p.vertHi);
+        w->launches++;
+    }
+    return build_tree(w, S, nullptr);
+}
+
+} // namespace cq

@@ -1,0 +1,104 @@
+// cq_internal.h — host-side world representation shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cq.h"
+#include "cq_world.cuh"
+
+namespace cq {
+
+struct PartInfo {
+    uint32_t entityId;
+    int set;          // 0 static, 1 dynamic
+    int vertLo, vertHi; // range in the set's vertex arrays
+    int triLo, triHi;   // range in the set's FILTERED triangle numbering (slice, CollisionQuery.swift:404-409)
+    cq_material material;
+    uint32_t layer;
+};
+
+// One TriangleMeshSet (CollisionQuery.swift:320-470) resident in HBM.
+struct DeviceSet {
+    int nVerts = 0;
+    int nTrisIn = 0; // before the degenerate filter
+    int nTris = 0;   // after
+    // vertex arrays
+    float4 *localPos = nullptr; // (x,y,z, bits(part index))
+    float4 *worldPos = nullptr; // (x,y,z,0)   = simd_mul(modelMatrix, (p,1))
+    // triangle arrays in soup order (the reference's numbering)
+    uint32_t *indices = nullptr;  // 3 per triangle, set-global vertex ids
+    uint32_t *triLayer = nullptr;
+    int32_t *triPart = nullptr;
+    // sorted (Morton) order
+    uint32_t *sortedTri = nullptr; // slot -> soup triangle id
+    float4 *tv0 = nullptr, *tv1 = nullptr, *tv2 = nullptr;
+    // LBVH
+    Node *nodes = nullptr;       // nTris-1 internal nodes (>= 1 allocated)
+    int32_t *parent = nullptr;   // [0,nTris-1): internal, [nTris-1, 2nTris-1): leaves
+    int32_t *rangeLo = nullptr, *rangeHi = nullptr; // per internal node
+    float4 *boxLo = nullptr, *boxHi = nullptr;      // 2nTris-1 subtree boxes (bottom-up scratch, kept for refit)
+    int32_t *visit = nullptr;    // per internal node arrival counter
+    SetHeader *hdr = nullptr;
+};
+
+struct ScratchBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace cq
+
+struct cq_world {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copyStream[2] = {nullptr, nullptr};
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    cq::DeviceSet set[2];
+    std::vector<cq::PartInfo> parts;
+    float *dModels = nullptr;    // nParts * 16
+    float4 *dMaterials = nullptr; // nParts
+    cq::WorldView view;
+    float buildMs = 0, refitMs = 0;
+    int counting = 0;
+    unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
+    uint64_t launches = 0;
+    cq::ScratchBuf in, out, aux, aux2;
+};
+
+namespace cq {
+void set_error(const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+#define CQ_CUDA(x)                                        \
+    do {                                                  \
+        int _r = cq::check_cuda((x), #x);                 \
+        if (_r != CQ_OK) return _r;                       \
+    } while (0)
+
+#define CQ_TRY(x)                  \
+    do {                           \
+        int _r = (x);              \
+        if (_r != CQ_OK) return _r; \
+    } while (0)
+
+int ensure_scratch(ScratchBuf &b, size_t bytes);
+
+// cq_build.cu
+int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,
+              const std::vector<uint32_t> &triLayerIn, const std::vector<int32_t> &triPartIn,
+              std::vector<int> &keptPerPartPrefix /* out: filtered tri count per input part, by part index */);
+int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx);
+void free_set(DeviceSet &S);
+
+// cq_query.cu
+int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, cudaStream_t st);
+int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st);
+int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, cudaStream_t st);
+int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,
+                       uint8_t *d_overflow, cudaStream_t st);
+// cq_mas.cu
+int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p, float dt,
+                          const float g[3], uint32_t flags, cudaStream_t st);
+} // namespace cq

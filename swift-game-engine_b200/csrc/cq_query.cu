@@ -1,0 +1,220 @@
+// cq_query.cu — batched query kernels: raycast, capsule cast (3 modes), capsule overlap (deepest),
+// capsule overlap-all (8 deepest).  One thread per query; the BVH walk and the narrow phase live in
+// cq_world.cuh / cq_math.cuh.  Replaces the per-call CPU entry points of CollisionQuery.swift:85-159.
+#include "cq_internal.h"
+
+namespace cq {
+
+#define Q_THREADS 128
+
+template <bool COUNT> __device__ __forceinline__ void flush_counters(const Counters &c, unsigned long long *g) {
+    if (!COUNT) return;
+    // warp-reduce, one atomic per warp per counter
+    uint32_t v[4] = {c.nodes, c.cands, c.evals, c.queries};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned long long s = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(g + k, s);
+    }
+}
+
+__device__ __forceinline__ void store3(float *o, f3 v) {
+    o[0] = v.x;
+    o[1] = v.y;
+    o[2] = v.z;
+}
+__device__ __forceinline__ f3 load3(const float *p) { return {p[0], p[1], p[2]}; }
+
+// ---------------------------------------------------------------- raycast (CollisionQuery.swift:768-785, 916-978)
+template <bool COUNT>
+__global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray *__restrict__ rays, int n,
+                                                       cq_ray_hit *__restrict__ out, unsigned long long *gctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr = {0, 0, 0, 0};
+    if (i < n) {
+        cq_ray r = rays[i];
+        f3 o = load3(r.origin), d = load3(r.direction);
+        RayResult res;
+        raycast<COUNT>(W, o, d, r.max_distance, r.mask, res, ctr);
+        cq_ray_hit h;
+        if (res.tri >= 0) {
+            h.distance = res.t;
+            store3(h.position, o + d * res.t); // :962
+            store3(h.normal, res.normal);
+            h.triangle_index = res.tri;
+        } else {
+            h.distance = 0.0f;
+            store3(h.position, mk3(0, 0, 0));
+            store3(h.normal, mk3(0, 0, 0));
+            h.triangle_index = -1;
+        }
+        out[i] = h;
+    }
+    flush_counters<COUNT>(ctr, gctr);
+}
+
+// ---------------------------------------------------------------- capsule cast (CollisionQuery.swift:787-828, 980-1117)
+template <bool COUNT>
+__global__ void __launch_bounds__(Q_THREADS) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ q, int n,
+                                                            int mode, cq_cast_hit *__restrict__ out,
+                                                            unsigned long long *gctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr = {0, 0, 0, 0};
+    if (i < n) {
+        cq_capsule_cast c = q[i];
+        CastResult res;
+        capsule_cast<COUNT>(W, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode, c.min_normal_y, res,
+                            ctr);
+        cq_cast_hit h;
+        if (res.tri >= 0) {
+            h.toi = res.hit.toi;
+            store3(h.position, res.hit.position);
+            store3(h.normal, res.hit.normal);
+            store3(h.triangle_normal, res.hit.triNormal);
+            h.triangle_index = res.tri;
+        } else {
+            h.toi = 0.0f;
+            store3(h.position, mk3(0, 0, 0));
+            store3(h.normal, mk3(0, 0, 0));
+            store3(h.triangle_normal, mk3(0, 0, 0));
+            h.triangle_index = -1;
+        }
+        out[i] = h;
+    }
+    flush_counters<COUNT>(ctr, gctr);
+}
+
+__device__ __forceinline__ void write_overlap(cq_overlap_hit &h, const OverlapRec &r) {
+    h.depth = r.depth;
+    store3(h.position, r.position);
+    store3(h.normal, r.normal);
+    store3(h.triangle_normal, r.triNormal);
+    h.triangle_index = r.tri;
+}
+__device__ __forceinline__ void write_overlap_nil(cq_overlap_hit &h) {
+    h.depth = 0.0f;
+    store3(h.position, mk3(0, 0, 0));
+    store3(h.normal, mk3(0, 0, 0));
+    store3(h.triangle_normal, mk3(0, 0, 0));
+    h.triangle_index = -1;
+}
+
+// ---------------------------------------------------------------- capsule overlap: deepest (CollisionQuery.swift:830-850, 1119-1199)
+// deepest wins; equal depth -> smallest triangle index (reference: first visited)
+template <bool COUNT>
+__global__ void __launch_bounds__(Q_THREADS) k_capsule_overlap(WorldView W, const cq_capsule *__restrict__ q, int n,
+                                                               cq_overlap_hit *__restrict__ out,
+                                                               unsigned long long *gctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr = {0, 0, 0, 0};
+    if (i < n) {
+        cq_capsule c = q[i];
+        OverlapRec best;
+        best.tri = -1;
+        best.depth = 0.0f;
+        capsule_overlap_visit<COUNT>(W, load3(c.from), c.radius, c.half_height, c.mask, ctr,
+                                     [&](float depth, int gid, int part, const Tri &T, float dist, f3 sp, f3 tp) {
+                                         bool better = depth > best.depth; // :1172 (depth <= bestDepth rejected)
+                                         bool tieWin = best.tri >= 0 && depth == best.depth && gid < best.tri;
+                                         if (!better && !tieWin) return;
+                                         overlap_contact(T, dist, sp, tp, c.radius, best);
+                                         best.tri = gid;
+                                         best.part = part;
+                                     });
+        cq_overlap_hit h;
+        if (best.tri >= 0) write_overlap(h, best);
+        else write_overlap_nil(h);
+        out[i] = h;
+    }
+    flush_counters<COUNT>(ctr, gctr);
+}
+
+// ---------------------------------------------------------------- capsule overlap-all (CollisionQuery.swift:852-882, 1201-1283)
+// Keeps the maxHits deepest (ties: smaller index), emitted deepest first — the order every caller in
+// the reference sorts into anyway (Systems.swift:759).  The reference returns its first maxHits in
+// DFS order; identical whenever <= maxHits triangles overlap, flagged `overflow` otherwise.
+template <bool COUNT>
+__global__ void __launch_bounds__(Q_THREADS) k_capsule_overlap_all(WorldView W, const cq_capsule *__restrict__ q, int n,
+                                                                   int maxHits, cq_overlap_hit *__restrict__ out,
+                                                                   int32_t *__restrict__ counts,
+                                                                   uint8_t *__restrict__ overflow,
+                                                                   unsigned long long *gctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr = {0, 0, 0, 0};
+    if (i < n) {
+        cq_capsule c = q[i];
+        OverlapRec top[CQ_MAX_OVERLAP_HITS] = {};
+        int cnt = 0, total = 0;
+        capsule_overlap_visit<COUNT>(W, load3(c.from), c.radius, c.half_height, c.mask, ctr,
+                                     [&](float depth, int gid, int part, const Tri &T, float dist, f3 sp, f3 tp) {
+                                         total++;
+                                         // position of the new record in (depth desc, index asc) order
+                                         int pos = cnt;
+                                         while (pos > 0 && (top[pos - 1].depth < depth ||
+                                                            (top[pos - 1].depth == depth && top[pos - 1].tri > gid)))
+                                             pos--;
+                                         if (pos >= maxHits) return;
+                                         int last = cnt < maxHits ? cnt : maxHits - 1;
+                                         for (int k = last; k > pos; k--) top[k] = top[k - 1];
+                                         overlap_contact(T, dist, sp, tp, c.radius, top[pos]);
+                                         top[pos].tri = gid;
+                                         top[pos].part = part;
+                                         if (cnt < maxHits) cnt++;
+                                     });
+        for (int k = 0; k < maxHits; k++) {
+            cq_overlap_hit h;
+            if (k < cnt) write_overlap(h, top[k]);
+            else write_overlap_nil(h);
+            out[(size_t)i * maxHits + k] = h;
+        }
+        counts[i] = cnt;
+        if (overflow) overflow[i] = total > maxHits ? 1 : 0;
+    }
+    flush_counters<COUNT>(ctr, gctr);
+}
+
+// ---------------------------------------------------------------- launchers
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, cudaStream_t st) {
+    if (n <= 0) return CQ_OK;
+    if (w->counting) k_raycast<true><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_rays, n, d_out, w->dCounters);
+    else k_raycast<false><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_rays, n, d_out, w->dCounters);
+    w->launches++;
+    return check_cuda(cudaGetLastError(), "k_raycast");
+}
+
+int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st) {
+    if (n <= 0) return CQ_OK;
+    if (w->counting)
+        k_capsule_cast<true><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
+    else k_capsule_cast<false><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
+    w->launches++;
+    return check_cuda(cudaGetLastError(), "k_capsule_cast");
+}
+
+int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, cudaStream_t st) {
+    if (n <= 0) return CQ_OK;
+    if (w->counting)
+        k_capsule_overlap<true><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, d_out, w->dCounters);
+    else k_capsule_overlap<false><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, d_out, w->dCounters);
+    w->launches++;
+    return check_cuda(cudaGetLastError(), "k_capsule_overlap");
+}
+
+int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,
+                       uint8_t *d_overflow, cudaStream_t st) {
+    if (n <= 0) return CQ_OK;
+    if (w->counting)
+        k_capsule_overlap_all<true><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts,
+                                                                              d_overflow, w->dCounters);
+    else
+        k_capsule_overlap_all<false><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts,
+                                                                               d_overflow, w->dCounters);
+    w->launches++;
+    return check_cuda(cudaGetLastError(), "k_capsule_overlap_all");
+}
+
+} // namespace cq

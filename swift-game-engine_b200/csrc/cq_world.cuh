@@ -1,0 +1,322 @@
+// cq_world.cuh — device-side world layout and the per-thread query routines
+// (BVH box/ray traversal + narrow phase) shared by the batch kernels and the
+// in-kernel move-and-slide.
+//
+// HBM layout of one triangle set (static or dynamic, CollisionQuery.swift:710-711):
+//   tv0/tv1/tv2 : float4 SoA, one entry per triangle in MORTON (leaf) order
+//        tv0 = (v0.xyz, bits(layer))      tv1 = (v1.xyz, bits(triangle id in the filtered soup))
+//        tv2 = (v2.xyz, bits(part index -> material))
+//   nodes       : 64-byte LBVH node = the AABBs of BOTH children + their references, so one
+//                 node fetch (4 x LDG.128) tests two boxes:
+//        n0 = (lo0.xyz, bits(ref0))  n1 = (hi0.xyz, bits(ref1))  n2 = (lo1.xyz, -)  n3 = (hi1.xyz, -)
+//        ref >= 0 : internal node index;  ref < 0 : leaf range, ~ref = (start << 2) | (count - 1),
+//        1..4 consecutive triangles of the sorted SoA (subtrees with <= 4 triangles are
+//        collapsed, mirroring the reference's leafTriangleLimit = 4, CollisionQuery.swift:473).
+//   header      : root reference + root box, kept in device memory so a refit needs no host sync.
+#pragma once
+#include "cq_math.cuh"
+
+namespace cq {
+
+#define CQ_REF_EMPTY 0x7fffffff
+#define CQ_STACK 64
+
+struct __align__(16) Node {
+    float4 n0, n1, n2, n3;
+};
+
+struct __align__(16) SetHeader {
+    float lo[3];
+    int rootRef; // CQ_REF_EMPTY when the set has no triangles
+    float hi[3];
+    int nTris;
+};
+
+struct SetView {
+    const float4 *tv0, *tv1, *tv2;
+    const Node *nodes;
+    const SetHeader *hdr;
+    int triOffset; // added to triangle ids of this set (dynamic set: static count, CollisionQuery.swift:782)
+};
+
+struct WorldView {
+    SetView set[2];
+    const float4 *materials; // per part: (muS, muK, flattenGround, -)
+    int nParts;
+};
+
+struct Counters { // per-thread work counters, flushed with atomics when COUNT
+    uint32_t nodes, cands, evals, queries;
+};
+
+__device__ __forceinline__ bool box_disjoint(f3 lo, f3 hi, f3 qlo, f3 qhi) { // CollisionQuery.swift:1047-1049
+    return hi.x < qlo.x || lo.x > qhi.x || hi.y < qlo.y || lo.y > qhi.y || hi.z < qlo.z || lo.z > qhi.z;
+}
+
+__device__ __forceinline__ Tri load_tri(const SetView &s, int i, uint32_t &layer, int &triId, int &part) {
+    float4 a = __ldg(s.tv0 + i), b = __ldg(s.tv1 + i), c = __ldg(s.tv2 + i);
+    layer = __float_as_uint(a.w);
+    triId = __float_as_int(b.w);
+    part = __float_as_int(c.w);
+    return Tri{xyz(a), xyz(b), xyz(c)};
+}
+
+// Generic box-query traversal: calls fn(sortedIndex) for every leaf triangle slot whose node chain
+// overlaps [qlo,qhi].  Traversal order is free: capsule queries never cull by distance
+// (CollisionQuery.swift:1045-1051), so the candidate set is tree-independent.
+template <bool COUNT, class Fn>
+__device__ __forceinline__ void traverse_box(const SetView &s, f3 qlo, f3 qhi, Counters &ctr, Fn fn) {
+    SetHeader h = *s.hdr;
+    if (h.rootRef == CQ_REF_EMPTY) return;
+    if (COUNT) ctr.nodes++;
+    if (box_disjoint(mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), qlo, qhi)) return;
+    int stack[CQ_STACK];
+    int sp = 0;
+    int ref = h.rootRef;
+    while (true) {
+        if (ref < 0) {
+            int enc = ~ref;
+            int start = enc >> 2, count = (enc & 3) + 1;
+#pragma unroll 1
+            for (int k = 0; k < count; k++) fn(start + k);
+        } else {
+            const Node *n = s.nodes + ref;
+            float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
+            if (COUNT) ctr.nodes += 2;
+            bool h0 = !box_disjoint(xyz(n0), xyz(n1), qlo, qhi);
+            bool h1 = !box_disjoint(xyz(n2), xyz(n3), qlo, qhi);
+            int r0 = __float_as_int(n0.w), r1 = __float_as_int(n1.w);
+            if (h0 && h1) {
+                stack[sp++] = r1;
+                ref = r0;
+                continue;
+            } else if (h0) {
+                ref = r0;
+                continue;
+            } else if (h1) {
+                ref = r1;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        ref = stack[--sp];
+    }
+}
+
+// ---------------------------------------------------------------- capsule cast
+struct CastResult {
+    int tri; // global triangle index, -1 = nil
+    int part;
+    CastHit hit;
+};
+
+#define CQ_MODE_ALL 0
+#define CQ_MODE_BLOCKING 1
+#define CQ_MODE_GROUND 2
+
+// capsuleCastCombined / capsuleCastBVH — CollisionQuery.swift:980-1117.
+// Result = the accepted candidate with the smallest toi; exact toi ties -> smallest triangle index
+// (the reference keeps the first visited, which depends on its tree).
+template <bool COUNT>
+__device__ __forceinline__ void capsule_cast(const WorldView &W, f3 from, f3 delta, float radius, float hh,
+                                             uint32_t mask, int mode, float minNormalY, CastResult &res,
+                                             Counters &ctr) {
+    res.tri = -1;
+    res.part = -1;
+    float L = len(delta);
+    if (L < 1e-6f) return; // CollisionQuery.swift:988
+    f3 dir = delta / L;
+    const f3 up = {0.0f, 1.0f, 0.0f};
+    f3 a0 = from + up * hh, b0 = from - up * hh;
+    f3 a1 = a0 + delta, b1 = b0 + delta;
+    f3 ext = {radius, radius, radius};
+    f3 qlo = vmin(vmin(a0, b0), vmin(a1, b1)) - ext;
+    f3 qhi = vmax(vmax(a0, b0), vmax(a1, b1)) + ext;
+    float bestT = L;
+#pragma unroll 1
+    for (int si = 0; si < 2; si++) {
+        const SetView &S = W.set[si];
+        if (COUNT) ctr.queries++;
+        traverse_box<COUNT>(S, qlo, qhi, ctr, [&](int slot) {
+            uint32_t layer;
+            int triId, part;
+            Tri T = load_tri(S, slot, layer, triId, part);
+            if ((layer & mask) == 0u) return;
+            f3 tlo = vmin(T.v0, vmin(T.v1, T.v2)), thi = vmax(T.v0, vmax(T.v1, T.v2));
+            if (box_disjoint(tlo, thi, qlo, qhi)) return; // CollisionQuery.swift:1060-1065
+            if (COUNT) ctr.cands++;
+            CastHit hit;
+            if (!sweep_capsule_triangle<COUNT>(from, dir, L, radius, hh, T, bestT, hit, ctr.evals)) return;
+            int gid = triId + S.triOffset;
+            bool better = hit.toi < bestT;
+            bool tieWin = res.tri >= 0 && hit.toi == bestT && gid < res.tri;
+            if (!better && !tieWin) return;
+            if (mode == CQ_MODE_BLOCKING) { // CollisionQuery.swift:1087-1094
+                if (dot(delta, hit.normal) >= 0.0f) return;
+                if (dot(delta, hit.triNormal) >= 0.0f) return;
+            } else if (mode == CQ_MODE_GROUND) { // :1095
+                if (hit.triNormal.y < minNormalY) return;
+            }
+            bestT = hit.toi;
+            res.tri = gid;
+            res.part = part;
+            res.hit = hit;
+        });
+    }
+}
+
+// ---------------------------------------------------------------- capsule overlap
+struct OverlapRec {
+    float depth;
+    f3 position, normal, triNormal;
+    int tri, part;
+};
+
+__device__ __forceinline__ void overlap_box(f3 from, float radius, float hh, f3 &qlo, f3 &qhi) { // :1126-1133
+    const f3 up = {0.0f, 1.0f, 0.0f};
+    f3 a0 = from + up * hh, b0 = from - up * hh;
+    f3 ext = {radius, radius, radius};
+    qlo = vmin(a0, b0) - ext;
+    qhi = vmax(a0, b0) + ext;
+}
+
+// contact record of one overlapping triangle — CollisionQuery.swift:1165-1190
+__device__ __forceinline__ void overlap_contact(const Tri &T, float dist, f3 segPt, f3 triPt, float radius,
+                                                OverlapRec &r) {
+    f3 triNormal = normalize(cross(T.v1 - T.v0, T.v2 - T.v0));
+    f3 n = dist < 1e-6f ? triNormal : normalize(segPt - triPt);
+    f3 triN = triNormal;
+    if (dot(triN, n) < 0.0f) triN = -triN;
+    r.depth = radius - dist;
+    r.position = triPt;
+    r.normal = n;
+    r.triNormal = triN;
+}
+
+// Visit every overlapping triangle: fn(depth, globalTri, part, slot, setIndex, T, dist, segPt, triPt)
+template <bool COUNT, class Fn>
+__device__ __forceinline__ void capsule_overlap_visit(const WorldView &W, f3 from, float radius, float hh,
+                                                      uint32_t mask, Counters &ctr, Fn fn) {
+    f3 qlo, qhi;
+    overlap_box(from, radius, hh, qlo, qhi);
+#pragma unroll 1
+    for (int si = 0; si < 2; si++) {
+        const SetView &S = W.set[si];
+        if (COUNT) ctr.queries++;
+        traverse_box<COUNT>(S, qlo, qhi, ctr, [&](int slot) {
+            uint32_t layer;
+            int triId, part;
+            Tri T = load_tri(S, slot, layer, triId, part);
+            if ((layer & mask) == 0u) return;
+            f3 tlo = vmin(T.v0, vmin(T.v1, T.v2)), thi = vmax(T.v0, vmax(T.v1, T.v2));
+            if (box_disjoint(tlo, thi, qlo, qhi)) return;
+            if (COUNT) {
+                ctr.cands++;
+                ctr.evals++;
+            }
+            f3 sp, tp;
+            float dist = segment_triangle_distance<true>(from, hh, T, sp, tp);
+            if (dist >= radius) return; // CollisionQuery.swift:1170
+            fn(radius - dist, triId + S.triOffset, part, T, dist, sp, tp);
+        });
+    }
+}
+
+// ---------------------------------------------------------------- raycast
+struct RayResult {
+    int tri, part;
+    float t;
+    f3 normal;
+};
+
+// rayAABB — CollisionQuery.swift:1603-1631 — made conservative: the box is accepted when the slab
+// interval, widened by a few ulps, is non-empty and starts before closestT.  The reference's own
+// slab test is not conservative in floating point, so which grazing hits it culls depends on its
+// tree; this library defines the result as the minimum-t triangle over ALL triangles (ties ->
+// smallest index) and only uses the boxes to skip work.
+__device__ __forceinline__ bool ray_box(f3 o, f3 inv, f3 lo, f3 hi, float closestT) {
+    // spatial pad: a float Moller-Trumbore hit can sit a few ulps outside the triangle's box
+    float ex = 2e-6f * (fabsf(o.x) + fmaxf(fabsf(lo.x), fabsf(hi.x))) + 1e-7f;
+    float ey = 2e-6f * (fabsf(o.y) + fmaxf(fabsf(lo.y), fabsf(hi.y))) + 1e-7f;
+    float ez = 2e-6f * (fabsf(o.z) + fmaxf(fabsf(lo.z), fabsf(hi.z))) + 1e-7f;
+    float t0x = ((lo.x - ex) - o.x) * inv.x, t1x = ((hi.x + ex) - o.x) * inv.x;
+    float t0y = ((lo.y - ey) - o.y) * inv.y, t1y = ((hi.y + ey) - o.y) * inv.y;
+    float t0z = ((lo.z - ez) - o.z) * inv.z, t1z = ((hi.z + ez) - o.z) * inv.z;
+    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    float pad = 1e-6f + 1e-6f * fmaxf(fabsf(tmin), fabsf(tmax)); // + a relative pad on the interval itself
+    if (tmin - pad > tmax + pad) return false;
+    if (tmax + pad < 0.0f) return false; // rayTriangle needs t >= 0
+    return tmin - pad <= closestT;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void raycast(const WorldView &W, f3 origin, f3 direction, float maxDistance, uint32_t mask,
+                                        RayResult &res, Counters &ctr) {
+    res.tri = -1;
+    res.part = -1;
+    float closestT = maxDistance;
+    // CollisionQuery.swift:1606-1608: 1/d, or greatestFiniteMagnitude when d == 0
+    f3 inv = {direction.x != 0.0f ? 1.0f / direction.x : FLT_MAX, direction.y != 0.0f ? 1.0f / direction.y : FLT_MAX,
+              direction.z != 0.0f ? 1.0f / direction.z : FLT_MAX};
+#pragma unroll 1
+    for (int si = 0; si < 2; si++) {
+        const SetView &S = W.set[si];
+        SetHeader h = *S.hdr;
+        if (h.rootRef == CQ_REF_EMPTY) continue;
+        if (COUNT) {
+            ctr.queries++;
+            ctr.nodes++;
+        }
+        if (!ray_box(origin, inv, mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), closestT)) continue;
+        int stack[CQ_STACK];
+        int sp = 0;
+        int ref = h.rootRef;
+        while (true) {
+            if (ref < 0) {
+                int enc = ~ref;
+                int start = enc >> 2, count = (enc & 3) + 1;
+                for (int k = 0; k < count; k++) {
+                    uint32_t layer;
+                    int triId, part;
+                    Tri T = load_tri(S, start + k, layer, triId, part);
+                    if ((layer & mask) == 0u) continue;
+                    if (COUNT) ctr.cands++;
+                    float t;
+                    if (!ray_triangle(origin, direction, T, t)) continue;
+                    int gid = triId + S.triOffset;
+                    if (t < closestT || (res.tri >= 0 && t == closestT && gid < res.tri)) {
+                        closestT = t;
+                        res.tri = gid;
+                        res.part = part;
+                        res.t = t;
+                        f3 n = normalize(cross(T.v1 - T.v0, T.v2 - T.v0)); // CollisionQuery.swift:960-961
+                        res.normal = dot(n, direction) > 0.0f ? -n : n;
+                    }
+                }
+            } else {
+                const Node *n = S.nodes + ref;
+                float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
+                if (COUNT) ctr.nodes += 2;
+                bool h0 = ray_box(origin, inv, xyz(n0), xyz(n1), closestT);
+                bool h1 = ray_box(origin, inv, xyz(n2), xyz(n3), closestT);
+                int r0 = __float_as_int(n0.w), r1 = __float_as_int(n1.w);
+                if (h0 && h1) {
+                    stack[sp++] = r1;
+                    ref = r0;
+                    continue;
+                } else if (h0) {
+                    ref = r0;
+                    continue;
+                } else if (h1) {
+                    ref = r1;
+                    continue;
+                }
+            }
+            if (sp == 0) break;
+            ref = stack[--sp];
+        }
+    }
+}
+
+} // namespace cq

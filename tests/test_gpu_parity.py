@@ -1,0 +1,244 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, libcq.so) against the CPU oracle on the
+same seeded inputs.  Bar (BASELINE.json north_star): hit / no-hit and triangle index bit-exact except
+flagged exact-tie cases; toi / normals / positions within 1e-4 rel, 1e-5 abs — in practice the two
+sides run the same IEEE op sequence, so the CANONICAL-order oracle must match BIT-EXACTLY on every field."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL, REL_TOL = 1e-5, 1e-4  # the stated tolerance (only used against the REFERENCE-order oracle)
+
+
+def _fields_equal(a, b, fields):
+    return {f: bool(np.array_equal(a[f], b[f])) for f in fields}
+
+
+@pytest.fixture(scope="module", params=["hulls", "render"])
+def world(request, cq, orc, scenes):
+    parts = scenes.mirror_scene(use_hulls=request.param == "hulls")
+    g = cq.CollisionQuery(parts)
+    o = orc.OracleWorld(parts)
+    yield request.param, parts, g, o
+    g.close()
+    o.close()
+
+
+def test_soup_upload_matches_reference_rebuild(world):
+    """TriangleMeshSet.rebuild (CollisionQuery.swift:331-417): world-space vertices, filtered triangle
+    numbering, per-triangle AABBs and layers must be bit-identical."""
+    name, parts, g, o = world
+    gs, os_ = g.read_soup(0), o.read_soup(0)
+    assert gs["positions"].shape == os_["positions"].shape
+    for k in ("positions", "indices", "aabbs", "layers", "parts"):
+        assert np.array_equal(gs[k], os_[k]), k
+    info = g.info()
+    assert info["n_static_triangles"] == o.counts(0)["triangles"]
+    assert info["n_dynamic_triangles"] == 0
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_capsule_cast_bit_exact_vs_canonical_oracle(world, scenes, orc, mode):
+    name, parts, g, o = world
+    lo, hi = scenes.scene_aabb(parts[1:])
+    n = 20000 if name == "hulls" else 3000
+    q = scenes.gen_casts(n, lo, hi, seed=100 + mode)
+    q["delta"][:7] = 0  # zero-length sweeps -> nil (CollisionQuery.swift:988)
+    q["mask"][7:40] = 1  # ground plane only
+    q["mask"][40:60] = 2  # nothing on this layer
+    got = [g.capsuleCast, g.capsuleCastBlocking, g.capsuleCastGround][mode](q)
+    ref = o.capsule_cast(q, mode, orc.ORDER_CANONICAL)
+    assert (got["triangle_index"][:7] == -1).all() and (got["triangle_index"][40:60] == -1).all()
+    assert np.array_equal(got["triangle_index"], ref["triangle_index"])
+    for f in ("toi", "position", "normal", "triangle_normal"):
+        assert np.array_equal(got[f], ref[f]), f
+    assert (got["triangle_index"] >= 0).sum() > n // 10
+    # against the reference's own visiting order: only exact-tie cases may name another triangle
+    ref2 = o.capsule_cast(q, mode, orc.ORDER_REFERENCE)
+    assert np.array_equal(got["triangle_index"] >= 0, ref2["triangle_index"] >= 0)
+    assert np.array_equal(got["toi"], ref2["toi"])  # the winning toi is order-independent
+    diff = got["triangle_index"] != ref2["triangle_index"]
+    # every index mismatch is an exact toi tie (degenerate edge/vertex contact)
+    assert np.array_equal(got["toi"][diff], ref2["toi"][diff])
+
+
+def test_capsule_overlap_bit_exact(world, scenes, orc):
+    name, parts, g, o = world
+    lo, hi = scenes.scene_aabb(parts[1:])
+    n = 20000 if name == "hulls" else 4000
+    c = scenes.gen_capsules(n, lo, hi, seed=7)
+    got = g.capsuleOverlap(c)
+    ref = o.capsule_overlap(c, orc.ORDER_CANONICAL)
+    for f in ("triangle_index", "depth", "position", "normal", "triangle_normal"):
+        assert np.array_equal(got[f], ref[f]), f
+    assert (got["triangle_index"] >= 0).sum() > n // 20
+
+
+def test_capsule_overlap_all_bit_exact(world, scenes, orc):
+    name, parts, g, o = world
+    lo, hi = scenes.scene_aabb(parts[1:])
+    n = 20000 if name == "hulls" else 4000
+    c = scenes.gen_capsules(n, lo, hi, seed=8)
+    for max_hits in (8, 3):
+        got, gcnt, gov = g.capsuleOverlapAll(c, max_hits)
+        ref, rcnt, rov = o.capsule_overlap_all(c, max_hits, orc.ORDER_CANONICAL)
+        assert np.array_equal(gcnt, rcnt) and np.array_equal(gov, rov)
+        for f in ("triangle_index", "depth", "position", "normal", "triangle_normal"):
+            assert np.array_equal(got[f], ref[f]), f
+        # reference order: same SET of triangles whenever it did not overflow
+        ref2, rcnt2, rov2 = o.capsule_overlap_all(c, max_hits, orc.ORDER_REFERENCE)
+        ok = rov2 == 0
+        assert np.array_equal(gcnt[ok], rcnt2[ok])
+        assert np.array_equal(np.sort(got["triangle_index"][ok], axis=1), np.sort(ref2["triangle_index"][ok], axis=1))
+
+
+def test_raycast_vs_oracle(world, scenes, orc):
+    name, parts, g, o = world
+    lo, hi = scenes.scene_aabb(parts)
+    n = 20000 if name == "hulls" else 3000
+    r = scenes.gen_rays(n, lo, hi, seed=9, expand=2.0)
+    r["direction"][:100] *= 3.5  # direction is not normalised by the callee
+    r["direction"][100:110, 0] = 0  # axis-parallel components -> 1/0 replacement path
+    r["mask"][110:130] = 2
+    got = g.raycast(r)
+    ref = o.raycast(r, orc.ORDER_CANONICAL)  # brute force over all triangles
+    for f in ("triangle_index", "distance", "position", "normal"):
+        assert np.array_equal(got[f], ref[f]), f
+    assert (got["triangle_index"] >= 0).sum() > n // 10
+    ref2 = o.raycast(r, orc.ORDER_REFERENCE)
+    # the reference's own BVH walk may miss grazing hits its non-conservative slab test culls; it must
+    # never find something closer than the all-triangles minimum
+    both = (ref2["triangle_index"] >= 0) & (got["triangle_index"] >= 0)
+    assert (got["distance"][both] <= ref2["distance"][both]).all()
+    assert (np.array_equal(got["triangle_index"], ref2["triangle_index"])
+            or (got["triangle_index"] != ref2["triangle_index"]).mean() < 0.01)
+
+
+def test_move_and_slide_bit_exact_multi_step(world, cq, scenes, orc):
+    """KinematicMoveStopSystem.fixedUpdate body (Systems.swift:1842-1901), 6 consecutive fixed steps with
+    carried state: every field of every character must equal the canonical-order oracle's."""
+    name, parts, g, o = world
+    n = 4096 if name == "hulls" else 768
+    pos, vel = scenes.gen_c3_characters(n, seed=11)
+    pos[: n // 8, 1] += 3.0  # some start in the air
+    pos[n // 8: n // 4, 1] -= 0.4  # some start penetrating the ground -> depenetration path
+    sg = cq.init_states(pos, vel)
+    so = orc.init_states(pos, vel)
+    assert sg.tobytes() == so.tobytes()
+    pg, po = cq.default_params(), orc.default_params()
+    assert pg.tobytes() == po.tobytes()
+    for step in range(6):
+        g.move_and_slide(sg, pg)
+        o.move_and_slide(so, po, order=orc.ORDER_CANONICAL)
+        for f in sg.dtype.names:
+            if f == "_pad":
+                continue
+            assert np.array_equal(sg[f], so[f]), (step, f, int((sg[f] != so[f]).sum()))
+    assert sg["grounded"].mean() > 0.5
+    assert (sg["manifold_count"] > 0).any()
+
+
+def test_move_and_slide_human_scale_params(world, cq, scenes, orc):
+    name, parts, g, o = world
+    n = 2048 if name == "hulls" else 512
+    pos, vel = scenes.gen_c3_characters(n, seed=12, radius=0.4, half_height=0.5)
+    sg, so = cq.init_states(pos, vel), orc.init_states(pos, vel)
+    pg = cq.default_params(radius=0.4, half_height=0.5, skin_width=0.08, fall_probe_distance=50.0)
+    po = orc.default_params(radius=0.4, half_height=0.5, skin_width=0.08, fall_probe_distance=50.0)
+    for step in range(4):
+        g.move_and_slide(sg, pg, flags=0)
+        o.move_and_slide(so, po, flags=0, order=orc.ORDER_CANONICAL)
+    assert sg.tobytes() == so.tobytes()
+
+
+def test_refit_matches_reference_update_transforms(cq, orc, scenes):
+    """updateDynamicTransforms -> TriangleMeshSet.updateTransforms + BVH.refit (CollisionQuery.swift:419-462,
+    528-575): spin the mirror (dynamic set) and compare soup + queries after every refit."""
+    parts = scenes.mirror_scene(use_hulls=False, mirror_dynamic=True)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    assert g.info()["n_dynamic_triangles"] == o.counts(1)["triangles"] > 10000
+    a = scenes.load_mirror_fixture()
+    t, q0, s = scenes.transform_from_matrix(scenes.mirror_model(a["transform"]))
+    lo, hi = scenes.scene_aabb(parts[1:])
+    qs = scenes.gen_casts(2000, lo - 2, hi + 2, seed=21)
+    rays = scenes.gen_rays(2000, lo, hi, seed=22)
+    for step in range(1, 4):
+        rot = scenes.quat_mul(scenes.quat_angle_axis(np.radians(7.0 * step), (0, 1, 0)), q0)
+        model = scenes.trs_model(t, rot, s)
+        g.update_transforms([1], [model])
+        o.update_transforms([1], [model])
+        assert o.check_bvh(1)
+        gs, os_ = g.read_soup(1), o.read_soup(1)
+        for k in ("positions", "aabbs"):
+            assert np.array_equal(gs[k], os_[k]), (step, k)
+        got, ref = g.capsuleCast(qs), o.capsule_cast(qs, 0, orc.ORDER_CANONICAL)
+        assert got.tobytes() == ref.tobytes()
+        gr, rr = g.raycast(rays), o.raycast(rays, orc.ORDER_CANONICAL)
+        assert np.array_equal(gr["triangle_index"], rr["triangle_index"])
+        assert np.array_equal(gr["distance"], rr["distance"])
+    with pytest.raises(cq.CQError):
+        g.update_transforms([99], [model])
+    g.close()
+    o.close()
+
+
+def test_empty_and_tiny_worlds(cq, orc, scenes):
+    # empty world: every query answers nil
+    g = cq.CollisionQuery([])
+    q = scenes.gen_casts(64, [-1, -1, -1], [1, 1, 1], seed=1)
+    assert (g.capsuleCast(q)["triangle_index"] == -1).all()
+    assert (g.raycast(scenes.gen_rays(64, [-1, -1, -1], [1, 1, 1], seed=1))["triangle_index"] == -1).all()
+    s = cq.init_states(np.zeros((8, 3), np.float32), np.ones((8, 3), np.float32))
+    g.move_and_slide(s, cq.default_params())
+    assert not s["grounded"].any()
+    assert g.capsuleCast(q[:0]).shape == (0,)
+    g.close()
+    # 1, 2, 5 triangles (leaf-collapse edge cases of the LBVH) incl. a fully degenerate part
+    v, i = scenes.plane_mesh(10.0)
+    for ntri_idx in (i[:3], i, np.concatenate([i, i[:3], i, i[:3]])):
+        parts = [scenes.part(v, ntri_idx, entity_id=0),
+                 scenes.part(np.zeros((3, 3), np.float32), [0, 1, 2], entity_id=1)]  # zero-area -> filtered
+        g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+        assert g.info()["n_static_triangles"] == o.counts(0)["triangles"]
+        q = scenes.gen_casts(512, [-5, 0, -5], [5, 3, 5], seed=3, expand=1.0)
+        assert g.capsuleCast(q).tobytes() == o.capsule_cast(q, 0, orc.ORDER_CANONICAL).tobytes()
+        g.close()
+        o.close()
+
+
+def test_static_and_dynamic_sets_index_offset(cq, orc, scenes):
+    """Dynamic-set triangle indices are offset by the static count (CollisionQuery.swift:782,1004); static
+    wins exact ties (chooseNearest <=)."""
+    v, i = scenes.plane_mesh(20.0)
+    bv, bi = scenes.box_mesh(2.0)
+    parts = [scenes.part(v, i, entity_id=0),
+             scenes.part(bv, bi, scenes.trs_model((0, 1, 0)), is_dynamic=True, entity_id=1),
+             scenes.part(bv, bi, scenes.trs_model((4, 1, 0)), entity_id=2)]
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    inf = g.info()
+    assert inf["n_static_triangles"] == 14 and inf["n_dynamic_triangles"] == 12
+    q = scenes.gen_casts(4000, [-4, 0, -4], [8, 4, 4], seed=5, radius=0.5, half_height=0.5, expand=0.5)
+    got, ref = g.capsuleCast(q), o.capsule_cast(q, 0, orc.ORDER_CANONICAL)
+    assert got.tobytes() == ref.tobytes()
+    assert (got["triangle_index"] >= 14).any()
+    assert g.triangle_material(0)["mu_s"] == pytest.approx(0.8)
+    g.close()
+    o.close()
+
+
+def test_counters_match_reference_stats(world, scenes, orc):
+    """capsuleCandidateCount (CollisionQuery.swift:1066) is tree-independent: the GPU's candidate counter
+    must equal the reference's on the same batch."""
+    name, parts, g, o = world
+    lo, hi = scenes.scene_aabb(parts[1:])
+    q = scenes.gen_casts(2000, lo, hi, seed=31)
+    st = orc.Stats()
+    o.capsule_cast(q, 0, orc.ORDER_REFERENCE, 1, st)
+    g.set_counting(True)
+    g.resetStats()
+    g.capsuleCast(q)
+    c = g.stats()
+    g.set_counting(False)
+    assert c["candidates"] == st.candidates
+    assert 0 < c["distance_evals"] <= st.distance_evals  # exact-safe pruning only removes work
+    assert c["nodes_visited"] > 0 and c["kernel_launches"] >= 1
