@@ -198,7 +198,12 @@ def run_ours(args):
     # device-resident state (inputs are 168 MB per GPU > the 126 MB L2, so no explicit L2 flush is needed)
     d_states = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     d_states.copy_(torch.from_numpy(states0.view(np.uint8).reshape(-1)))
-    stream = torch.cuda.current_stream().cuda_stream
+    # an explicit (non-default) stream: the library's NULL-stream convention means "the world's own
+    # stream", and torch.cuda.Event only sees torch's current stream, so make both the same real stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_device():
         world.move_and_slide_device(d_states.data_ptr(), n, params, DT, GRAVITY, cq.MAS_APPLY_GRAVITY, stream)

@@ -1,15 +1,19 @@
 // cq_mas.cu — in-kernel move-and-slide: one fixed step of the reference's
 // KinematicMoveStopSystem.fixedUpdate per-entity body (Game/Systems.swift:1842-1901) for a batch of
-// independent characters, one thread per character:
-//   cache decay (SYS:1105) -> VelocityGate (SYS:1037) -> pre-sweep depenetration (SYS:734,1635)
-//   -> <= maxSlideIterations blocking casts + SlideResolver plane clipping (SYS:1229,1658)
+// independent characters:
+//   gravity (SYS:603) -> cache decay (SYS:1105) -> VelocityGate (SYS:1037) -> pre-sweep depenetration
+//   (SYS:734,1635) -> <= maxSlideIterations blocking casts + SlideResolver plane clipping (SYS:1229,1658)
 //   -> GroundProbe snap/fall/offset casts (SYS:826) -> GroundSnap (SYS:945) -> SlopeFriction (SYS:965)
 //   -> writeBack (SYS:1802).
-// All casts of one character go through ONE call site driven by a small phase machine, so lanes that
-// are in different slide iterations / probe stages still execute the conservative-advancement code
-// together.  Contact-plane clipping state (remaining, slide normal, position) stays in registers; the
-// rarely touched contact-manifold cache is updated in place in the character record.
+//
+// Execution model (see cq_engine.cuh): persistent lanes, each lane owns one character at a time and is
+// a resumable state machine.  The character's controller state lives in shared memory (CharCtx, one
+// record per lane); the in-flight collision query (LaneQ: swept box, traversal cursor, conservative-
+// advancement state, best hit) lives in registers.  Each trip of the main loop runs the three
+// convergent stages L (controller logic: consume a finished query, clip against the contact plane, post
+// the next query), T (BVH walk to the next candidate) and E (one segment-triangle distance evaluation).
 // Double precision exactly where the reference uses Double (velocity; SYS:792,882,958,1045,1368).
+#include "cq_engine.cuh"
 #include "cq_internal.h"
 
 namespace cq {
@@ -23,472 +27,566 @@ struct MasArgs {
     uint32_t flags;
 };
 
+enum { W_NONE = 0, W_DEPEN, W_SLIDE, W_SNAP, W_FALL, W_OFFSET };
+enum { NX_LOAD = 0, NX_DEPEN, NX_SLIDE, NX_SNAP, NX_FALL, NX_GATE, NX_OFFSET, NX_FINISH };
+enum {
+    F_WAS_G = 1, F_WAS_GN = 2, F_HAVE_LAST = 4, F_HAVE_CENTER = 8, F_GROUNDED = 16, F_GROUNDED_NEAR = 32,
+    F_CAN_SNAP = 64, F_NEAR_GROUND = 128, F_PROBE_HIT = 256, F_DID_RESOLVE = 512
+};
+
+struct CharCtx { // per-lane controller working set, shared memory
+    cq_character_state st;
+    float pos[3], rem[3], lastN[3];
+    float slideLen;
+    float cNormal[3], cTriNormal[3];
+    float cToi, cPosY;
+    int cTri, cPart;
+    float gDistance;
+    float nSum[3];
+    float combineTol;
+    float dSum[3];
+    float dWeight;
+    int wait, slideIt, offsetIt, depenIt;
+    uint32_t flags;
+    int charIndex;
+    int _pad;
+};
+
 __device__ __forceinline__ f3 ld3(const float *p) { return {p[0], p[1], p[2]}; }
 __device__ __forceinline__ void st3(float *o, f3 v) {
     o[0] = v.x;
     o[1] = v.y;
     o[2] = v.z;
 }
+__device__ __forceinline__ d3 ldv(const cq_character_state &s) { return {s.velocity[0], s.velocity[1], s.velocity[2]}; }
+__device__ __forceinline__ void stv(cq_character_state &s, d3 v) {
+    s.velocity[0] = v.x;
+    s.velocity[1] = v.y;
+    s.velocity[2] = v.z;
+}
 
-// ---- ContactManifoldCache / DefaultContactCachePolicy on the record in global memory (SYS:1102-1205)
-__device__ __forceinline__ bool manifold_normal_for(const cq_character_state *c, int tri, f3 &out) {
-    int cnt = c->manifold_count;
+// ---- ContactManifoldCache / DefaultContactCachePolicy (SYS:1102-1205)
+__device__ __forceinline__ bool manifold_normal_for(const cq_character_state &c, int tri, f3 &out) {
+    int cnt = c.manifold_count;
     for (int i = 0; i < cnt; i++)
-        if (c->manifold_triangles[i] == tri) {
-            out = ld3(c->manifold_normals[i]);
+        if (c.manifold_triangles[i] == tri) {
+            out = ld3(c.manifold_normals[i]);
             return true;
         }
     return false;
 }
 
-__device__ __noinline__ void manifold_update(cq_character_state *c, int tri, f3 normal) {
+__device__ __noinline__ void manifold_update(cq_character_state &c, int tri, f3 normal) {
     f3 n = normal;
     if (len2(n) < 1e-8f) return;
-    c->manifold_frames = 8;
-    int cnt = c->manifold_count;
+    c.manifold_frames = 8;
+    int cnt = c.manifold_count;
     for (int i = 0; i < cnt; i++) {
-        if (c->manifold_triangles[i] == tri) {
-            f3 cached = ld3(c->manifold_normals[i]);
+        if (c.manifold_triangles[i] == tri) {
+            f3 cached = ld3(c.manifold_normals[i]);
             if (dot(cached, n) < 0.0f) n = -n;
             const float blend = 0.25f;
             f3 combined = normalize(cached * (1.0f - blend) + n * blend);
-            st3(c->manifold_normals[i], combined);
-            st3(c->side_contact_normal, combined);
+            st3(c.manifold_normals[i], combined);
+            st3(c.side_contact_normal, combined);
             return;
         }
     }
     if (cnt >= CQ_MANIFOLD_MAX) cnt -= 1; // removeLast
     for (int i = cnt; i > 0; i--) {      // insert at 0
-        c->manifold_triangles[i] = c->manifold_triangles[i - 1];
-        st3(c->manifold_normals[i], ld3(c->manifold_normals[i - 1]));
+        c.manifold_triangles[i] = c.manifold_triangles[i - 1];
+        st3(c.manifold_normals[i], ld3(c.manifold_normals[i - 1]));
     }
     f3 nn = normalize(n);
-    c->manifold_triangles[0] = tri;
-    st3(c->manifold_normals[0], nn);
-    c->manifold_count = cnt + 1;
-    st3(c->side_contact_normal, nn);
+    c.manifold_triangles[0] = tri;
+    st3(c.manifold_normals[0], nn);
+    c.manifold_count = cnt + 1;
+    st3(c.side_contact_normal, nn);
 }
 
-__device__ __forceinline__ void cache_record(cq_character_state *c, int tri, f3 normal, bool isSide) {
+__device__ __forceinline__ void cache_record(cq_character_state &c, int tri, f3 normal, bool isSide) {
     manifold_update(c, tri, normal);
     if (isSide) {
-        st3(c->side_contact_normal, normalize(normal));
-        c->side_contact_frames = 3;
+        st3(c.side_contact_normal, normalize(normal));
+        c.side_contact_frames = 3;
     }
 }
 
-enum { PH_SLIDE = 0, PH_SNAP, PH_FALL, PH_GATE, PH_OFFSET, PH_DONE };
+// SlideResolver.resolveHit, kinematicMove options, static hit (SYS:1229-1375).  Returns shouldBreak.
+__device__ __forceinline__ bool slide_resolve(CharCtx &c, const cq_controller_params &P, f3 hitN, f3 hitTriN, float hitToi,
+                                              bool haveCachedSide, f3 cachedSide, int sideFrames) {
+    const bool wasGrounded = c.flags & F_WAS_G, wasGroundedNear = c.flags & F_WAS_GN;
+    f3 position = ld3(c.pos), remaining = ld3(c.rem);
+    const float slideLen = c.slideLen;
+    f3 slideNormal = hitN;
+    bool groundLike = hitTriN.y >= P.min_ground_dot;
+    float contactSkin = groundLike ? P.ground_snap_skin : P.skin_width;
+    bool shouldBreak = false;
+    if (slideNormal.y < P.min_ground_dot && sideFrames > 0) { // SYS:1273-1292
+        if (haveCachedSide) {
+            f3 cn = cachedSide;
+            if (dot(cn, slideNormal) < 0.0f) cn = -cn;
+            slideNormal = cn;
+        } else {
+            f3 cached = ld3(c.st.side_contact_normal);
+            float cl = len2(cached);
+            if (cl > 1e-6f) {
+                f3 cn = cached / sqrtf(cl);
+                float dc = dot(cn, slideNormal);
+                if (fabsf(dc) > 0.5f) slideNormal = dc >= 0.0f ? cn : -cn;
+            }
+        }
+    }
+    bool resolved = false;
+    if (slideNormal.y < P.min_ground_dot) { // SYS:1294-1309
+        if (groundLike) slideNormal = hitTriN;
+        if (slideNormal.y < P.min_ground_dot) {
+            slideNormal.y = 0.0f;
+            float nl = len(slideNormal);
+            if (nl > 1e-5f) {
+                slideNormal = slideNormal / nl;
+            } else {
+                position = position + remaining;
+                remaining = mk3(0, 0, 0);
+                shouldBreak = true;
+                resolved = true;
+            }
+        }
+    }
+    if (!resolved) {
+        float into = dot(remaining, slideNormal);
+        float intoEps = 1e-4f * slideLen;
+        float effectiveSkin = (hitToi <= contactSkin && into < -intoEps) ? smin(contactSkin, hitToi * 0.5f) : contactSkin;
+        float sticky = contactSkin * 0.1f;
+        if (hitToi <= sticky && into < -intoEps) { // SYS:1320
+            remaining = remaining - slideNormal * into;
+            shouldBreak = false;
+        } else if (into >= -intoEps) { // SYS:1324
+            if (wasGroundedNear && !groundLike && remaining.y < 0.0f) remaining.y = 0.0f;
+            position = position + remaining;
+            remaining = mk3(0, 0, 0);
+            shouldBreak = true;
+        } else if ((hitToi <= effectiveSkin && fabsf(into) <= intoEps) || into >= 0.0f) {
+            position = position + remaining;
+            remaining = mk3(0, 0, 0);
+            shouldBreak = true;
+        } else {
+            float moveDist = smax(hitToi - effectiveSkin, 0.0f); // SYS:1343
+            if (slideNormal.y >= P.min_ground_dot && remaining.y < 0.0f && moveDist > P.ground_sweep_max_step)
+                moveDist = P.ground_sweep_max_step;
+            f3 dir = remaining / slideLen;
+            position = position + dir * moveDist;
+            f3 leftover = remaining - dir * moveDist;
+            leftover = leftover - slideNormal * dot(leftover, slideNormal);
+            if (wasGrounded && wasGroundedNear && leftover.y < 0.0f) leftover.y = 0.0f;
+            float residual = dot(leftover, slideNormal);
+            if (fabsf(residual) < 1e-5f) leftover = leftover - slideNormal * residual;
+            if (len2(leftover) < 1e-8f) {
+                remaining = mk3(0, 0, 0);
+                shouldBreak = true;
+            } else {
+                remaining = leftover;
+                d3 vel = ldv(c.st);
+                d3 sn = to_d3(slideNormal);
+                double vInto = dot(vel, sn); // SYS:1367-1372
+                if (vInto < 0.0) stv(c.st, vel - sn * vInto);
+                shouldBreak = false;
+            }
+        }
+    }
+    st3(c.pos, position);
+    st3(c.rem, remaining);
+    return shouldBreak;
+}
+
+// GroundProbe tail + GroundSnap + SlopeFriction + writeBack (SYS:923-1021, 1787-1821)
+__device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const MasArgs &A, cq_character_state *out) {
+    const cq_controller_params &P = A.p;
+    cq_character_state &S = c.st;
+    const f3 gravity = {A.gx, A.gy, A.gz};
+    const bool wasGroundedNear = c.flags & F_WAS_GN;
+    const bool grounded = c.flags & F_GROUNDED;
+    f3 position = ld3(c.pos);
+    d3 vel = ldv(S);
+    f3 centerTriNormal = ld3(c.cTriNormal), centerNormal = ld3(c.cNormal);
+    f3 gNormal = {0, 1, 0};
+    float matMuS = 0.8f, matMuK = 0.6f;
+    bool matFlatten = false;
+    if (grounded) {
+        f3 normalSum = ld3(c.nSum);
+        float nl = len(normalSum);
+        gNormal = nl > 1e-6f ? normalSum / nl : centerTriNormal;
+        if (wasGroundedNear) {
+            f3 prevNormal = ld3(S.ground_normal);
+            if (dot(prevNormal, gNormal) > 0.9f) {
+                const float blend = 0.2f;
+                gNormal = normalize(prevNormal * (1.0f - blend) + gNormal * blend);
+            }
+        }
+        if (c.cPart >= 0 && c.cPart < W.nParts) {
+            float4 m = __ldg(W.materials + c.cPart);
+            matMuS = m.x, matMuK = m.y, matFlatten = m.z != 0.0f;
+        }
+        if (matFlatten) gNormal = mk3(0, 1, 0);
+    }
+    if ((c.flags & F_CAN_SNAP) && (c.flags & F_PROBE_HIT)) { // GroundSnap.apply (SYS:945-963)
+        float moveDist = smax(c.cToi - P.ground_snap_skin, 0.0f);
+        if ((c.flags & F_NEAR_GROUND) && moveDist > P.ground_snap_max_step) moveDist = P.ground_snap_max_step;
+        position = position + mk3(0.0f, -1.0f, 0.0f) * moveDist;
+        d3 cn = to_d3(centerNormal);
+        double vIntoSnap = dot(vel, cn);
+        if (vIntoSnap < 0.0) vel = vel - cn * vIntoSnap;
+    }
+    int transitionFrames = S.ground_transition_frames;
+    bool sliding = S.ground_sliding != 0;
+    if (grounded) { // SYS:1787-1792
+        float normalUpDelta = gNormal.y - S.ground_normal[1];
+        if (c.cTri != S.ground_triangle_index && normalUpDelta > 0.02f) transitionFrames = 3;
+    }
+    if (!grounded) { // SlopeFriction.apply (SYS:965-1021)
+        sliding = false;
+    } else {
+        f3 normal = normalize(gNormal);
+        if (normal.y > 0.98f) {
+            transitionFrames = 0;
+            sliding = false;
+        } else if (transitionFrames > 0) {
+            transitionFrames -= 1;
+            sliding = false;
+        } else {
+            float gN = dot(gravity, normal);
+            f3 gTan = gravity - normal * gN;
+            float gTanLen = len(gTan);
+            if (gTanLen > 0.5f) {
+                float gNMag = fabsf(gN);
+                f3 gTanDir = gTan / gTanLen;
+                d3 gTanDirD = to_d3(gTanDir), normalD = to_d3(normal);
+                float stickLimit = matMuS * gNMag;
+                bool enterSlide = gTanLen > stickLimit * 1.05f;
+                bool exitSlide = gTanLen < stickLimit * 0.9f;
+                if (sliding) {
+                    if (exitSlide) sliding = false;
+                } else if (enterSlide) {
+                    sliding = true;
+                }
+                if (!sliding && gTanLen <= stickLimit) {
+                    d3 vTan = vel - normalD * dot(vel, normalD);
+                    double downhill = dot(vTan, gTanDirD);
+                    if (downhill > 0.0) vel = vel - gTanDirD * downhill;
+                } else {
+                    float slideAccelMag = smax(gTanLen - matMuK * gNMag, 0.0f);
+                    if (slideAccelMag > 0.0f) vel = vel + gTanDirD * (double)slideAccelMag * (double)A.dt;
+                }
+            }
+        }
+    }
+    // writeBack (SYS:1802-1821)
+    S.position[0] = (double)position.x;
+    S.position[1] = (double)position.y;
+    S.position[2] = (double)position.z;
+    stv(S, vel);
+    S.grounded = grounded ? 1 : 0;
+    S.grounded_near = (c.flags & F_GROUNDED_NEAR) ? 1 : 0;
+    S.ground_sliding = sliding ? 1 : 0;
+    S.ground_transition_frames = transitionFrames;
+    st3(S.ground_normal, grounded ? gNormal : mk3(0, 1, 0));
+    S.ground_distance = c.gDistance;
+    if (grounded) S.ground_triangle_index = c.cTri;
+    // 168-byte record out: 21 x 8-byte stores
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&S);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(out);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(cq_character_state) / 8); k++) dst[k] = src[k];
+}
+
+// Stage L of the move-and-slide kernel: consume the finished query, run the controller logic up to the
+// next query, post it.  Returns false when the lane has no more characters.
+template <bool COUNT>
+__device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, const WorldView &W, const MasArgs &A,
+                                            cq_character_state *states, int n, int stride, Counters &ctr) {
+    const cq_controller_params &P = A.p;
+    const f3 down = {0.0f, -1.0f, 0.0f};
+    int next = NX_LOAD;
+    // ---------------- consume
+    switch (c.wait) {
+    case W_DEPEN: { // DepenetrationResolver.resolve loop body after the overlap query (SYS:756-799)
+        next = NX_SLIDE;
+        float d0 = q.bestT, d1 = q.bestPos.x;
+        int t0 = q.bestTri, t1 = q.bestPart;
+        f3 n0 = q.bestN, n1 = q.bestTriN;
+        if (t0 >= 0) {
+            bool sideContact = n0.y < P.min_ground_dot;
+            int useCount = sideContact ? 1 : (t1 >= 0 ? 2 : 1);
+            float maxDepth = d0;
+            f3 frameNormal = {0, 0, 0};
+            for (int k = 0; k < useCount; k++) {
+                float hd = k == 0 ? d0 : d1;
+                int ht = k == 0 ? t0 : t1;
+                f3 hn = k == 0 ? n0 : n1;
+                maxDepth = smax(maxDepth, hd);
+                f3 nn = hn;
+                f3 cached;
+                if (manifold_normal_for(c.st, ht, cached)) nn = cached; // SYS:770-776
+                frameNormal = frameNormal + nn * hd;
+                cache_record(c.st, ht, nn, hn.y < P.min_ground_dot);
+            }
+            float fl = len(frameNormal);
+            f3 depenNormal = fl > 1e-6f ? frameNormal / fl : frameNormal;
+            const float slop = smax(P.skin_width * 0.5f, 0.001f);
+            float push = sideContact ? smax(maxDepth, 0.0f) : smax(maxDepth + slop, 0.0f);
+            if (sideContact) push = smin(push, P.skin_width);
+            if (!(push <= 1e-6f)) {
+                st3(c.pos, ld3(c.pos) + depenNormal * push);
+                d3 vel = ldv(c.st);
+                d3 dn = to_d3(depenNormal);
+                double vInto = dot(vel, dn);
+                if (vInto < 0.0) stv(c.st, vel - dn * vInto);
+                c.flags |= F_DID_RESOLVE;
+                st3(c.dSum, ld3(c.dSum) + depenNormal * maxDepth);
+                c.dWeight += maxDepth;
+                if (++c.depenIt < 4) next = NX_DEPEN;
+            }
+        }
+        if (next == NX_SLIDE && (c.flags & F_DID_RESOLVE)) { // SYS:800-807, 1651-1654
+            f3 normalSum = ld3(c.dSum);
+            f3 depenN = c.dWeight > 1e-6f ? normalize(normalSum / c.dWeight) : normalize(normalSum);
+            f3 remaining = ld3(c.rem);
+            float into = dot(remaining, depenN);
+            if (into < 0.0f) st3(c.rem, remaining - depenN * into);
+        }
+        break;
+    }
+    case W_SLIDE: { // resolveKinematicSweep loop body after the blocking cast (SYS:1683-1763)
+        c.slideIt++;
+        if (q.bestTri < 0) {
+            st3(c.pos, ld3(c.pos) + ld3(c.rem));
+            st3(c.rem, mk3(0, 0, 0));
+            next = NX_SNAP;
+            break;
+        }
+        f3 hitN = q.bestN;
+        const f3 hitTriN = q.bestTriN;
+        const int tri = q.bestTri;
+        bool haveCachedSide = false;
+        f3 cachedSide = {0, 0, 0};
+        const int sideFrames = c.st.side_contact_frames;
+        if (hitN.y < P.min_ground_dot && sideFrames > 0) { // SYS:1683-1694
+            f3 cached;
+            if (manifold_normal_for(c.st, tri, cached)) {
+                if (dot(cached, hitN) < 0.0f) cached = -cached;
+                hitN = cached;
+            }
+        }
+        if (hitN.y < P.min_ground_dot && sideFrames > 0) haveCachedSide = manifold_normal_for(c.st, tri, cachedSide);
+        bool shouldBreak = slide_resolve(c, P, hitN, hitTriN, q.bestT, haveCachedSide, cachedSide, sideFrames);
+        if (hitN.y < P.min_ground_dot) cache_record(c.st, tri, hitN, true); // SYS:1738-1743
+        if (c.flags & F_HAVE_LAST) {                                       // SYS:1744-1754
+            f3 last = ld3(c.lastN);
+            float dn = dot(last, hitN);
+            if (fabsf(dn) < 0.98f) {
+                f3 axis = cross(last, hitN);
+                float al = len(axis);
+                if (al > 1e-5f) {
+                    f3 an = axis / al;
+                    st3(c.rem, an * dot(ld3(c.rem), an));
+                }
+            }
+        }
+        st3(c.lastN, hitN);
+        c.flags |= F_HAVE_LAST;
+        next = shouldBreak ? NX_SNAP : NX_SLIDE;
+        break;
+    }
+    case W_SNAP: // centre ground cast (SYS:844-853)
+        if (q.bestTri >= 0) {
+            c.flags |= F_HAVE_CENTER;
+            c.cToi = q.bestT;
+            c.cPosY = q.bestPos.y;
+            st3(c.cNormal, q.bestN);
+            st3(c.cTriNormal, q.bestTriN);
+            c.cTri = q.bestTri;
+            c.cPart = q.bestPart;
+        }
+        next = NX_FALL;
+        break;
+    case W_FALL: // fall probe (SYS:855-866)
+        if (q.bestTri >= 0) c.gDistance = q.bestT;
+        next = NX_GATE;
+        break;
+    case W_OFFSET: // slope sample casts (SYS:906-921)
+        if (q.bestTri >= 0 && q.bestT <= c.cToi + c.combineTol) {
+            if (dot(q.bestTriN, ld3(c.cTriNormal)) > 0.98f) st3(c.nSum, ld3(c.nSum) + q.bestTriN);
+        }
+        next = ++c.offsetIt == 4 ? NX_FINISH : NX_OFFSET;
+        break;
+    default:
+        next = NX_LOAD;
+        break;
+    }
+    // ---------------- post
+    while (true) {
+        if (next == NX_LOAD) {
+            if (c.charIndex >= n) {
+                c.wait = W_NONE;
+                q_idle(q);
+                return false;
+            }
+            { // 168-byte record in
+                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(states + c.charIndex);
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(&c.st);
+#pragma unroll
+                for (int k = 0; k < (int)(sizeof(cq_character_state) / 8); k++) dst[k] = src[k];
+            }
+            cq_character_state &S = c.st;
+            const bool wasGrounded = S.grounded != 0, wasGroundedNear = S.grounded_near != 0;
+            c.flags = (wasGrounded ? F_WAS_G : 0) | (wasGroundedNear ? F_WAS_GN : 0);
+            d3 vel = ldv(S);
+            if (A.flags & CQ_MAS_APPLY_GRAVITY) { // GravitySystem (SYS:603-619)
+                if (!(wasGrounded && wasGroundedNear)) vel = vel + to_d3(mk3(A.gx, A.gy, A.gz)) * (double)A.dt;
+            }
+            st3(c.pos, mk3((float)S.position[0], (float)S.position[1], (float)S.position[2])); // positionF
+            { // decay (SYS:1105-1116)
+                int scf = S.side_contact_frames;
+                if (scf > 0) S.side_contact_frames = scf - 1;
+                int mf = S.manifold_frames;
+                if (mf > 0) {
+                    mf -= 1;
+                    S.manifold_frames = mf;
+                    if (mf == 0) {
+                        S.manifold_count = 0;
+                        st3(S.side_contact_normal, mk3(0, 0, 0));
+                    }
+                }
+            }
+            // VelocityGate (SYS:1037-1051)
+            if (wasGrounded && wasGroundedNear && vel.y < 0.0) vel.y = 0.0;
+            d3 remD = vel * (double)A.dt;
+            if (wasGrounded && wasGroundedNear && remD.y < 0.0) remD.y = 0.0;
+            stv(S, vel);
+            st3(c.rem, to_f3(remD));
+            c.depenIt = 0, c.slideIt = 0, c.offsetIt = 0;
+            st3(c.dSum, mk3(0, 0, 0));
+            c.dWeight = 0.0f;
+            c.gDistance = FLT_MAX;
+            c.cTri = -1, c.cPart = -1;
+            c.cToi = 0.0f, c.cPosY = 0.0f;
+            st3(c.cNormal, mk3(0, 0, 0));
+            st3(c.cTriNormal, mk3(0, 0, 0));
+            st3(c.nSum, mk3(0, 0, 0));
+            next = NX_DEPEN;
+        }
+        if (next == NX_DEPEN) {
+            q_begin_overlap<COUNT>(W, q, stack, ld3(c.pos), P.radius, P.half_height, P.collision_mask, ctr);
+            c.wait = W_DEPEN;
+            return true;
+        }
+        if (next == NX_SLIDE) {
+            f3 remaining = ld3(c.rem);
+            c.slideLen = len(remaining);
+            if (c.slideIt >= P.max_slide_iterations || c.slideLen < 1e-6f) { // SYS:1674-1676
+                next = NX_SNAP;
+            } else {
+                q_begin_cast<COUNT>(W, q, stack, ld3(c.pos), remaining, P.radius, P.half_height, P.collision_mask,
+                                    CQ_MODE_BLOCKING, 0.0f, ctr);
+                c.wait = W_SLIDE;
+                return true;
+            }
+        }
+        if (next == NX_SNAP) {
+            if (!(P.snap_distance > 0.0f)) { // SYS:845
+                next = NX_FALL;
+            } else {
+                q_begin_cast<COUNT>(W, q, stack, ld3(c.pos), down * P.snap_distance, P.radius, P.half_height,
+                                    P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
+                c.wait = W_SNAP;
+                return true;
+            }
+        }
+        if (next == NX_FALL) {
+            if (!(P.fall_probe_distance > 0.0f)) { // SYS:855
+                next = NX_GATE;
+            } else {
+                q_begin_cast<COUNT>(W, q, stack, ld3(c.pos), down * P.fall_probe_distance, P.radius, P.half_height,
+                                    P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
+                c.wait = W_FALL;
+                return true;
+            }
+        }
+        if (next == NX_GATE) { // validity gates after the centre + fall casts (SYS:868-925)
+            next = NX_FINISH;
+            if ((c.flags & F_HAVE_CENTER) && c.cToi <= P.snap_distance) {
+                const bool wasGroundedNear = c.flags & F_WAS_GN;
+                c.flags |= F_PROBE_HIT;
+                f3 position = ld3(c.pos);
+                float baseCenterY = position.y - P.half_height;
+                float bottomY = baseCenterY - P.radius;
+                float groundTol = smax(P.skin_width, P.ground_snap_skin);
+                bool validGroundPoint = c.cPosY <= bottomY + groundTol;
+                float groundNearThreshold = smax(P.ground_snap_skin, P.skin_width);
+                bool nearGround = c.cToi <= groundNearThreshold;
+                if (nearGround) c.flags |= F_NEAR_GROUND | F_GROUNDED_NEAR;
+                c.gDistance = c.cToi;
+                d3 vel = ldv(c.st);
+                bool groundGateVel = vel.y <= 0.0;
+                double vInto = dot(vel, to_d3(ld3(c.cNormal)));
+                bool groundGateSpeed = vInto >= -(double)P.ground_snap_max_speed;
+                bool groundGateToi = c.cToi <= P.ground_snap_max_toi;
+                bool canSnap = validGroundPoint && groundGateVel && (nearGround || groundGateSpeed || groundGateToi);
+                if (wasGroundedNear && c.cToi <= P.snap_distance) canSnap = validGroundPoint;
+                if (canSnap) c.flags |= F_CAN_SNAP;
+                if (validGroundPoint && (nearGround || canSnap)) {
+                    c.flags |= F_GROUNDED;
+                    f3 ctn = ld3(c.cTriNormal);
+                    st3(c.nSum, ctn);
+                    if (ctn.y < 0.98f && (wasGroundedNear || nearGround)) { // SYS:897
+                        c.combineTol = smax(smax(P.ground_snap_skin, P.skin_width), 0.05f);
+                        c.offsetIt = 0;
+                        next = NX_OFFSET;
+                    }
+                }
+            }
+        }
+        if (next == NX_OFFSET) { // SYS:898-914
+            float offset = P.radius * 0.6f;
+            int oi = c.offsetIt;
+            float ox = oi == 0 ? offset : (oi == 1 ? -offset : 0.0f);
+            float oz = oi == 2 ? offset : (oi == 3 ? -offset : 0.0f);
+            q_begin_cast<COUNT>(W, q, stack, ld3(c.pos) + mk3(ox, 0.0f, oz), down * P.snap_distance, P.radius, P.half_height,
+                                P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
+            c.wait = W_OFFSET;
+            return true;
+        }
+        if (next == NX_FINISH) {
+            mas_finish(c, W, A, states + c.charIndex);
+            c.charIndex += stride;
+            next = NX_LOAD;
+        }
+    }
+}
 
 template <bool COUNT>
 __global__ void __launch_bounds__(MAS_THREADS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states, int n,
                                                                 MasArgs A, unsigned long long *gctr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ CharCtx ctxs[MAS_THREADS];
+    CharCtx &c = ctxs[threadIdx.x];
+    const int stride = gridDim.x * blockDim.x;
+    c.charIndex = blockIdx.x * blockDim.x + threadIdx.x;
+    c.wait = W_NONE;
+    c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
-    if (i < n) {
-        cq_character_state *S = states + i;
-        const cq_controller_params &P = A.p;
-        const f3 gravity = {A.gx, A.gy, A.gz};
-        d3 vel = {S->velocity[0], S->velocity[1], S->velocity[2]};
-        const bool wasGrounded = S->grounded != 0, wasGroundedNear = S->grounded_near != 0;
-        if (A.flags & CQ_MAS_APPLY_GRAVITY) { // GravitySystem (SYS:603-619)
-            if (!(wasGrounded && wasGroundedNear)) vel = vel + to_d3(gravity) * (double)A.dt;
-        }
-        f3 position = {(float)S->position[0], (float)S->position[1], (float)S->position[2]}; // positionF
-        // decay (SYS:1105-1116)
-        {
-            int scf = S->side_contact_frames;
-            if (scf > 0) S->side_contact_frames = scf - 1;
-            int mf = S->manifold_frames;
-            if (mf > 0) {
-                mf -= 1;
-                S->manifold_frames = mf;
-                if (mf == 0) {
-                    S->manifold_count = 0;
-                    st3(S->side_contact_normal, mk3(0, 0, 0));
-                }
-            }
-        }
-        // VelocityGate (SYS:1037-1051)
-        if (wasGrounded && wasGroundedNear && vel.y < 0.0) vel.y = 0.0;
-        d3 remD = vel * (double)A.dt;
-        if (wasGrounded && wasGroundedNear && remD.y < 0.0) remD.y = 0.0;
-        f3 remaining = to_f3(remD);
-
-        // ---- pre-sweep depenetration (SYS:734-808, 1635-1656)
-        {
-            const float slop = smax(P.skin_width * 0.5f, 0.001f);
-            bool didResolve = false;
-            f3 normalSum = {0, 0, 0};
-            float normalWeight = 0.0f;
-#pragma unroll 1
-            for (int it = 0; it < 4; it++) {
-                // the two deepest overlaps in (depth desc, index asc) order; only they are used (SYS:764-767)
-                float d0 = 0.0f, d1 = 0.0f;
-                int t0 = -1, t1 = -1;
-                f3 n0 = {0, 0, 0}, n1 = {0, 0, 0};
-                capsule_overlap_visit<COUNT>(W, position, P.radius, P.half_height, P.collision_mask, ctr,
-                                             [&](float depth, int gid, int part, const Tri &T, float dist, f3 sp, f3 tp) {
-                                                 bool before0 = t0 < 0 || depth > d0 || (depth == d0 && gid < t0);
-                                                 bool before1 = t1 < 0 || depth > d1 || (depth == d1 && gid < t1);
-                                                 if (!before0 && !before1) return;
-                                                 OverlapRec r;
-                                                 overlap_contact(T, dist, sp, tp, P.radius, r);
-                                                 if (before0) {
-                                                     d1 = d0, t1 = t0, n1 = n0;
-                                                     d0 = depth, t0 = gid, n0 = r.normal;
-                                                 } else {
-                                                     d1 = depth, t1 = gid, n1 = r.normal;
-                                                 }
-                                             });
-                if (t0 < 0) break; // hits.isEmpty
-                bool sideContact = n0.y < P.min_ground_dot;
-                int useCount = sideContact ? 1 : (t1 >= 0 ? 2 : 1);
-                float maxDepth = d0;
-                f3 frameNormal = {0, 0, 0};
-                for (int k = 0; k < useCount; k++) {
-                    float hd = k == 0 ? d0 : d1;
-                    int ht = k == 0 ? t0 : t1;
-                    f3 hn = k == 0 ? n0 : n1;
-                    maxDepth = smax(maxDepth, hd);
-                    f3 nn = hn;
-                    f3 cached;
-                    if (manifold_normal_for(S, ht, cached)) nn = cached; // SYS:770-776
-                    frameNormal = frameNormal + nn * hd;
-                    cache_record(S, ht, nn, hn.y < P.min_ground_dot);
-                }
-                float fl = len(frameNormal);
-                f3 depenNormal = fl > 1e-6f ? frameNormal / fl : frameNormal;
-                float push = sideContact ? smax(maxDepth, 0.0f) : smax(maxDepth + slop, 0.0f);
-                if (sideContact) push = smin(push, P.skin_width);
-                if (push <= 1e-6f) break;
-                position = position + depenNormal * push;
-                d3 dn = to_d3(depenNormal);
-                double vInto = dot(vel, dn);
-                if (vInto < 0.0) vel = vel - dn * vInto;
-                didResolve = true;
-                normalSum = normalSum + depenNormal * maxDepth;
-                normalWeight += maxDepth;
-            }
-            if (didResolve) {
-                f3 depenN = normalWeight > 1e-6f ? normalize(normalSum / normalWeight) : normalize(normalSum);
-                float into = dot(remaining, depenN);
-                if (into < 0.0f) remaining = remaining - depenN * into;
-            }
-        }
-
-        // ---- slide iterations + ground probe: every cast goes through the single call site below
-        int phase = PH_SLIDE;
-        int slideIt = 0, offsetIt = 0;
-        bool haveLast = false;
-        f3 lastSlideNormal = {0, 0, 0};
-        float slideLen = 0.0f;
-        // ground-probe temporaries (SYS:826-943)
-        bool haveCenter = false, grounded = false, groundedNear = false, canSnap = false, nearGround = false;
-        bool probeHit = false; // GroundProbeResult.hit != nil
-        float centerToi = 0.0f, centerPosY = 0.0f;
-        f3 centerNormal = {0, 0, 0}, centerTriNormal = {0, 0, 0};
-        int centerTri = -1, centerPart = -1;
-        float gDistance = FLT_MAX;
-        f3 gNormal = {0, 1, 0};
-        f3 normalSum = {0, 0, 0};
-        float combineTol = 0.0f;
-        const f3 down = {0.0f, -1.0f, 0.0f};
-        const f3 snapDelta = down * P.snap_distance;
-
-#pragma unroll 1
-        while (phase != PH_DONE) {
-            f3 qfrom = position, qdelta = snapDelta;
-            int mode = CQ_MODE_GROUND;
-            if (phase == PH_SLIDE) {
-                if (slideIt >= P.max_slide_iterations) {
-                    phase = PH_SNAP;
-                    continue;
-                }
-                slideLen = len(remaining);
-                if (slideLen < 1e-6f) { // SYS:1676
-                    phase = PH_SNAP;
-                    continue;
-                }
-                qdelta = remaining;
-                mode = CQ_MODE_BLOCKING;
-            } else if (phase == PH_SNAP) {
-                if (!(P.snap_distance > 0.0f)) { // SYS:845
-                    phase = PH_FALL;
-                    continue;
-                }
-            } else if (phase == PH_FALL) {
-                if (!(P.fall_probe_distance > 0.0f)) { // SYS:855
-                    phase = PH_GATE;
-                    continue;
-                }
-                qdelta = down * P.fall_probe_distance;
-            } else if (phase == PH_GATE) {
-                // SYS:868-925: validity gates after the centre + fall casts
-                phase = PH_DONE;
-                if (!haveCenter || !(centerToi <= P.snap_distance)) continue;
-                probeHit = true;
-                float baseCenterY = position.y - P.half_height;
-                float bottomY = baseCenterY - P.radius;
-                float groundTol = smax(P.skin_width, P.ground_snap_skin);
-                bool validGroundPoint = centerPosY <= bottomY + groundTol;
-                float groundNearThreshold = smax(P.ground_snap_skin, P.skin_width);
-                nearGround = centerToi <= groundNearThreshold;
-                groundedNear = nearGround;
-                gDistance = centerToi;
-                bool groundGateVel = vel.y <= 0.0;
-                double vInto = dot(vel, to_d3(centerNormal));
-                bool groundGateSpeed = vInto >= -(double)P.ground_snap_max_speed;
-                bool groundGateToi = centerToi <= P.ground_snap_max_toi;
-                canSnap = validGroundPoint && groundGateVel && (nearGround || groundGateSpeed || groundGateToi);
-                if (wasGroundedNear && centerToi <= P.snap_distance) canSnap = validGroundPoint;
-                if (validGroundPoint && (nearGround || canSnap)) {
-                    grounded = true;
-                    normalSum = centerTriNormal;
-                    if (centerTriNormal.y < 0.98f && (wasGroundedNear || nearGround)) { // SYS:897
-                        combineTol = smax(smax(P.ground_snap_skin, P.skin_width), 0.05f);
-                        offsetIt = 0;
-                        phase = PH_OFFSET;
-                    }
-                }
-                continue;
-            } else { // PH_OFFSET (SYS:898-921)
-                float offset = P.radius * 0.6f;
-                float ox = offsetIt == 0 ? offset : (offsetIt == 1 ? -offset : 0.0f);
-                float oz = offsetIt == 2 ? offset : (offsetIt == 3 ? -offset : 0.0f);
-                qfrom = position + mk3(ox, 0.0f, oz);
-            }
-
-            CastResult res;
-            capsule_cast<COUNT>(W, qfrom, qdelta, P.radius, P.half_height, P.collision_mask, mode, P.min_ground_dot, res, ctr);
-
-            if (phase == PH_SLIDE) {
-                slideIt++;
-                if (res.tri < 0) { // SYS:1759-1763
-                    position = position + remaining;
-                    remaining = mk3(0, 0, 0);
-                    phase = PH_SNAP;
-                    continue;
-                }
-                f3 hitN = res.hit.normal;
-                const f3 hitTriN = res.hit.triNormal;
-                const float hitToi = res.hit.toi;
-                bool haveCachedSide = false;
-                f3 cachedSide = {0, 0, 0};
-                const int sideFrames = S->side_contact_frames;
-                if (hitN.y < P.min_ground_dot && sideFrames > 0) { // SYS:1683-1694
-                    f3 cached;
-                    if (manifold_normal_for(S, res.tri, cached)) {
-                        if (dot(cached, hitN) < 0.0f) cached = -cached;
-                        hitN = cached;
-                    }
-                }
-                if (hitN.y < P.min_ground_dot && sideFrames > 0) // SYS:1719-1726
-                    haveCachedSide = manifold_normal_for(S, res.tri, cachedSide);
-
-                // ---- SlideResolver.resolveHit, kinematicMove options, static hit (SYS:1229-1375)
-                bool shouldBreak = false;
-                {
-                    f3 slideNormal = hitN;
-                    bool groundLike = hitTriN.y >= P.min_ground_dot;
-                    float contactSkin = groundLike ? P.ground_snap_skin : P.skin_width;
-                    if (slideNormal.y < P.min_ground_dot && sideFrames > 0) { // SYS:1273-1292
-                        if (haveCachedSide) {
-                            f3 cn = cachedSide;
-                            if (dot(cn, slideNormal) < 0.0f) cn = -cn;
-                            slideNormal = cn;
-                        } else {
-                            f3 cached = ld3(S->side_contact_normal);
-                            float cl = len2(cached);
-                            if (cl > 1e-6f) {
-                                f3 cn = cached / sqrtf(cl);
-                                float dc = dot(cn, slideNormal);
-                                if (fabsf(dc) > 0.5f) slideNormal = dc >= 0.0f ? cn : -cn;
-                            }
-                        }
-                    }
-                    bool resolved = false;
-                    if (slideNormal.y < P.min_ground_dot) { // SYS:1294-1309
-                        if (groundLike) slideNormal = hitTriN;
-                        if (slideNormal.y < P.min_ground_dot) {
-                            slideNormal.y = 0.0f;
-                            float nl = len(slideNormal);
-                            if (nl > 1e-5f) {
-                                slideNormal = slideNormal / nl;
-                            } else {
-                                position = position + remaining;
-                                remaining = mk3(0, 0, 0);
-                                shouldBreak = true;
-                                resolved = true;
-                            }
-                        }
-                    }
-                    if (!resolved) {
-                        float into = dot(remaining, slideNormal);
-                        float intoEps = 1e-4f * slideLen;
-                        float effectiveSkin =
-                            (hitToi <= contactSkin && into < -intoEps) ? smin(contactSkin, hitToi * 0.5f) : contactSkin;
-                        float sticky = contactSkin * 0.1f;
-                        if (hitToi <= sticky && into < -intoEps) { // SYS:1320
-                            remaining = remaining - slideNormal * into;
-                            shouldBreak = false;
-                        } else if (into >= -intoEps) { // SYS:1324
-                            if (wasGroundedNear && !groundLike && remaining.y < 0.0f) remaining.y = 0.0f;
-                            position = position + remaining;
-                            remaining = mk3(0, 0, 0);
-                            shouldBreak = true;
-                        } else if ((hitToi <= effectiveSkin && fabsf(into) <= intoEps) || into >= 0.0f) {
-                            position = position + remaining;
-                            remaining = mk3(0, 0, 0);
-                            shouldBreak = true;
-                        } else {
-                            float moveDist = smax(hitToi - effectiveSkin, 0.0f); // SYS:1343
-                            if (slideNormal.y >= P.min_ground_dot && remaining.y < 0.0f && moveDist > P.ground_sweep_max_step)
-                                moveDist = P.ground_sweep_max_step;
-                            f3 dir = remaining / slideLen;
-                            position = position + dir * moveDist;
-                            f3 leftover = remaining - dir * moveDist;
-                            leftover = leftover - slideNormal * dot(leftover, slideNormal);
-                            if (wasGrounded && wasGroundedNear && leftover.y < 0.0f) leftover.y = 0.0f;
-                            float residual = dot(leftover, slideNormal);
-                            if (fabsf(residual) < 1e-5f) leftover = leftover - slideNormal * residual;
-                            if (len2(leftover) < 1e-8f) {
-                                remaining = mk3(0, 0, 0);
-                                shouldBreak = true;
-                            } else {
-                                remaining = leftover;
-                                d3 sn = to_d3(slideNormal);
-                                double vInto = dot(vel, sn); // SYS:1367-1372
-                                if (vInto < 0.0) vel = vel - sn * vInto;
-                                shouldBreak = false;
-                            }
-                        }
-                    }
-                }
-                if (hitN.y < P.min_ground_dot) cache_record(S, res.tri, hitN, true); // SYS:1738-1743
-                if (haveLast) {                                                     // SYS:1744-1754
-                    float dn = dot(lastSlideNormal, hitN);
-                    if (fabsf(dn) < 0.98f) {
-                        f3 axis = cross(lastSlideNormal, hitN);
-                        float al = len(axis);
-                        if (al > 1e-5f) {
-                            f3 an = axis / al;
-                            remaining = an * dot(remaining, an);
-                        }
-                    }
-                }
-                lastSlideNormal = hitN;
-                haveLast = true;
-                if (shouldBreak) phase = PH_SNAP;
-            } else if (phase == PH_SNAP) {
-                haveCenter = res.tri >= 0;
-                if (haveCenter) {
-                    centerToi = res.hit.toi;
-                    centerPosY = res.hit.position.y;
-                    centerNormal = res.hit.normal;
-                    centerTriNormal = res.hit.triNormal;
-                    centerTri = res.tri;
-                    centerPart = res.part;
-                }
-                phase = PH_FALL;
-            } else if (phase == PH_FALL) {
-                if (res.tri >= 0) gDistance = res.hit.toi; // SYS:864
-                phase = PH_GATE;
-            } else { // PH_OFFSET
-                if (res.tri >= 0 && res.hit.toi <= centerToi + combineTol) {
-                    if (dot(res.hit.triNormal, centerTriNormal) > 0.98f) normalSum = normalSum + res.hit.triNormal;
-                }
-                if (++offsetIt == 4) phase = PH_DONE;
-            }
-        }
-
-        // ---- finish GroundProbe.resolve (SYS:923-937)
-        float matMuS = 0.8f, matMuK = 0.6f;
-        bool matFlatten = false;
-        if (grounded) {
-            float nl = len(normalSum);
-            gNormal = nl > 1e-6f ? normalSum / nl : centerTriNormal;
-            if (wasGroundedNear) {
-                f3 prevNormal = ld3(S->ground_normal);
-                if (dot(prevNormal, gNormal) > 0.9f) {
-                    const float blend = 0.2f;
-                    gNormal = normalize(prevNormal * (1.0f - blend) + gNormal * blend);
-                }
-            }
-            if (centerPart >= 0 && centerPart < W.nParts) {
-                float4 m = __ldg(W.materials + centerPart);
-                matMuS = m.x, matMuK = m.y, matFlatten = m.z != 0.0f;
-            }
-            if (matFlatten) gNormal = mk3(0, 1, 0);
-        }
-        // ---- GroundSnap.apply (SYS:945-963)
-        if (canSnap && probeHit) {
-            float moveDist = smax(centerToi - P.ground_snap_skin, 0.0f);
-            if (nearGround && moveDist > P.ground_snap_max_step) moveDist = P.ground_snap_max_step;
-            position = position + down * moveDist;
-            d3 cn = to_d3(centerNormal);
-            double vIntoSnap = dot(vel, cn);
-            if (vIntoSnap < 0.0) vel = vel - cn * vIntoSnap;
-        }
-        // ---- resolveGroundContact tail + SlopeFriction.apply (SYS:1787-1798, 965-1021)
-        int transitionFrames = S->ground_transition_frames;
-        bool sliding = S->ground_sliding != 0;
-        if (grounded) {
-            float normalUpDelta = gNormal.y - S->ground_normal[1];
-            if (centerTri != S->ground_triangle_index && normalUpDelta > 0.02f) transitionFrames = 3;
-        }
-        if (!grounded) {
-            sliding = false;
-        } else {
-            f3 normal = normalize(gNormal);
-            if (normal.y > 0.98f) {
-                transitionFrames = 0;
-                sliding = false;
-            } else if (transitionFrames > 0) {
-                transitionFrames -= 1;
-                sliding = false;
-            } else {
-                float gN = dot(gravity, normal);
-                f3 gTan = gravity - normal * gN;
-                float gTanLen = len(gTan);
-                if (gTanLen > 0.5f) {
-                    float gNMag = fabsf(gN);
-                    f3 gTanDir = gTan / gTanLen;
-                    d3 gTanDirD = to_d3(gTanDir), normalD = to_d3(normal);
-                    float stickLimit = matMuS * gNMag;
-                    bool enterSlide = gTanLen > stickLimit * 1.05f;
-                    bool exitSlide = gTanLen < stickLimit * 0.9f;
-                    if (sliding) {
-                        if (exitSlide) sliding = false;
-                    } else if (enterSlide) {
-                        sliding = true;
-                    }
-                    if (!sliding && gTanLen <= stickLimit) {
-                        d3 vTan = vel - normalD * dot(vel, normalD);
-                        double downhill = dot(vTan, gTanDirD);
-                        if (downhill > 0.0) vel = vel - gTanDirD * downhill;
-                    } else {
-                        float slideAccelMag = smax(gTanLen - matMuK * gNMag, 0.0f);
-                        if (slideAccelMag > 0.0f) vel = vel + gTanDirD * (double)slideAccelMag * (double)A.dt;
-                    }
-                }
-            }
-        }
-        // ---- writeBack (SYS:1802-1821)
-        S->position[0] = (double)position.x;
-        S->position[1] = (double)position.y;
-        S->position[2] = (double)position.z;
-        S->velocity[0] = vel.x;
-        S->velocity[1] = vel.y;
-        S->velocity[2] = vel.z;
-        S->grounded = grounded ? 1 : 0;
-        S->grounded_near = groundedNear ? 1 : 0;
-        S->ground_sliding = sliding ? 1 : 0;
-        S->ground_transition_frames = transitionFrames;
-        st3(S->ground_normal, grounded ? gNormal : mk3(0, 1, 0));
-        S->ground_distance = gDistance;
-        if (grounded) S->ground_triangle_index = centerTri;
+    LaneQ q;
+    q_idle(q);
+    int stack[CQ_STACK];
+    bool alive = true;
+    while (true) {
+        // L: lanes whose query is finished run the controller logic and post their next query
+        if (alive && q.phase == PH_NONE && q.travDone) alive = mas_advance<COUNT>(c, q, stack, W, A, states, n, stride, ctr);
+        // T: lanes without a candidate walk the LBVH
+        if (q.phase == PH_NONE && !q.travDone) q_next_candidate<COUNT>(W, q, stack, ctr);
+        // E: one distance evaluation for every lane that holds a candidate
+        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, ctr);
+        if (__all_sync(0xffffffffu, !alive)) break;
     }
-    // counters
     if (COUNT) {
         uint32_t v[4] = {ctr.nodes, ctr.cands, ctr.evals, ctr.queries};
 #pragma unroll
@@ -509,7 +607,19 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     A.dt = dt;
     A.gx = g[0], A.gy = g[1], A.gz = g[2];
     A.flags = flags;
-    int blocks = (n + MAS_THREADS - 1) / MAS_THREADS;
+    static int blocksPerSm[2] = {0, 0}, numSms = 0;
+    const int ci = w->counting ? 1 : 0;
+    if (!blocksPerSm[ci]) {
+        cudaDeviceProp prop;
+        CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
+        numSms = prop.multiProcessorCount;
+        int b = 0;
+        if (ci) CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<true>, MAS_THREADS, 0));
+        else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<false>, MAS_THREADS, 0));
+        blocksPerSm[ci] = b > 0 ? b : 1;
+    }
+    // persistent lanes: one resident wave of CTAs (148 SMs x resident CTAs per SM), lanes stride over characters
+    int blocks = std::min((n + MAS_THREADS - 1) / MAS_THREADS, numSms * blocksPerSm[ci]);
     if (w->counting) k_move_and_slide<true><<<blocks, MAS_THREADS, 0, st>>>(w->view, d_inout, n, A, w->dCounters);
     else k_move_and_slide<false><<<blocks, MAS_THREADS, 0, st>>>(w->view, d_inout, n, A, w->dCounters);
     w->launches++;

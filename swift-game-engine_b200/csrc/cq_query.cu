@@ -1,6 +1,7 @@
 // cq_query.cu — batched query kernels: raycast, capsule cast (3 modes), capsule overlap (deepest),
 // capsule overlap-all (8 deepest).  One thread per query; the BVH walk and the narrow phase live in
 // cq_world.cuh / cq_math.cuh.  Replaces the per-call CPU entry points of CollisionQuery.swift:85-159.
+#include "cq_engine.cuh"
 #include "cq_internal.h"
 
 namespace cq {
@@ -56,32 +57,54 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 }
 
 // ---------------------------------------------------------------- capsule cast (CollisionQuery.swift:787-828, 980-1117)
+// Persistent lanes over the flat L/T/E engine (cq_engine.cuh): a lane that finishes its sweep writes the
+// hit and immediately starts its next query, so warps stay full whatever the per-query candidate and
+// iteration counts are.
 template <bool COUNT>
-__global__ void __launch_bounds__(Q_THREADS) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ q, int n,
+__global__ void __launch_bounds__(Q_THREADS) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
                                                             int mode, cq_cast_hit *__restrict__ out,
                                                             unsigned long long *gctr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    int next = blockIdx.x * blockDim.x + threadIdx.x;
+    int cur = -1;
     Counters ctr = {0, 0, 0, 0};
-    if (i < n) {
-        cq_capsule_cast c = q[i];
-        CastResult res;
-        capsule_cast<COUNT>(W, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode, c.min_normal_y, res,
-                            ctr);
-        cq_cast_hit h;
-        if (res.tri >= 0) {
-            h.toi = res.hit.toi;
-            store3(h.position, res.hit.position);
-            store3(h.normal, res.hit.normal);
-            store3(h.triangle_normal, res.hit.triNormal);
-            h.triangle_index = res.tri;
-        } else {
-            h.toi = 0.0f;
-            store3(h.position, mk3(0, 0, 0));
-            store3(h.normal, mk3(0, 0, 0));
-            store3(h.triangle_normal, mk3(0, 0, 0));
-            h.triangle_index = -1;
+    LaneQ q;
+    q_idle(q);
+    int stack[CQ_STACK];
+    bool alive = true;
+    while (true) {
+        if (alive && q.phase == PH_NONE && q.travDone) { // L: write the finished hit, fetch the next query
+            if (cur >= 0) {
+                cq_cast_hit h;
+                if (q.bestTri >= 0) {
+                    h.toi = q.bestT;
+                    store3(h.position, q.bestPos);
+                    store3(h.normal, q.bestN);
+                    store3(h.triangle_normal, q.bestTriN);
+                    h.triangle_index = q.bestTri;
+                } else {
+                    h.toi = 0.0f;
+                    store3(h.position, mk3(0, 0, 0));
+                    store3(h.normal, mk3(0, 0, 0));
+                    store3(h.triangle_normal, mk3(0, 0, 0));
+                    h.triangle_index = -1;
+                }
+                out[cur] = h;
+                cur = -1;
+            }
+            if (next < n) {
+                cq_capsule_cast c = qs[next];
+                cur = next;
+                next += stride;
+                q_begin_cast<COUNT>(W, q, stack, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
+                                    c.min_normal_y, ctr);
+            } else {
+                alive = false;
+            }
         }
-        out[i] = h;
+        if (q.phase == PH_NONE && !q.travDone) q_next_candidate<COUNT>(W, q, stack, ctr); // T
+        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, ctr);                                // E
+        if (__all_sync(0xffffffffu, !alive)) break;
     }
     flush_counters<COUNT>(ctr, gctr);
 }
@@ -188,9 +211,20 @@ int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, 
 
 int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
-    if (w->counting)
-        k_capsule_cast<true><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
-    else k_capsule_cast<false><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
+    static int blocksPerSm[2] = {0, 0}, numSms = 0;
+    const int ci = w->counting ? 1 : 0;
+    if (!blocksPerSm[ci]) {
+        cudaDeviceProp prop;
+        CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
+        numSms = prop.multiProcessorCount;
+        int b = 0;
+        if (ci) CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_cast<true>, Q_THREADS, 0));
+        else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_cast<false>, Q_THREADS, 0));
+        blocksPerSm[ci] = b > 0 ? b : 1;
+    }
+    int blocks = std::min(cdiv(n, Q_THREADS), numSms * blocksPerSm[ci]); // one resident wave of persistent lanes
+    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
+    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }

@@ -309,3 +309,77 @@ def gen_c4_casts(n, half, seed=0xC0111DE4, radius=0.4, half_height=0.5, terrain_
                           axis=1).astype(f32)
     q["radius"], q["half_height"], q["mask"], q["min_normal_y"] = radius, half_height, 0xFFFFFFFF, 0.5
     return q
+
+
+# ---------------------------------------------------------------- C1: single character, 600 frames
+
+
+def wedge_mesh(width=8.0, depth=10.0, height=4.0):
+    """A ramp like the demo's "Test Ramp" (DemoScene.swift:588-590; ProceduralMeshes.ramp): low edge at +z,
+    high edge at -z, centred on the origin.  8 triangles: slope, bottom, back wall, two sides."""
+    w, d, h = f32(width) * f32(0.5), f32(depth) * f32(0.5), f32(height) * f32(0.5)
+    v = np.array([[-w, -h, d], [w, -h, d], [-w, -h, -d], [w, -h, -d], [-w, h, -d], [w, h, -d]], f32)
+    idx = [0, 1, 5, 0, 5, 4,      # slope
+           0, 2, 3, 0, 3, 1,      # bottom
+           2, 4, 5, 2, 5, 3,      # back wall
+           0, 4, 2,               # left side
+           1, 3, 5]               # right side
+    return v, np.array(idx, np.uint32)
+
+
+def c1_scene():
+    """Static demo world restated from DemoScene.swift: ground plane 80x80 @ y=-3, wall
+    box 6 @ (0,0,-10), ramp 8x10x4 @ (8,-1,0) flattenGround muS .35, step box 2 @ (-6,-2,4), and the ornate
+    mirror hulls at their demo placement.  (Dome, 17-Cheese and Semla are left out: their assets are
+    missing blobs / not needed to exercise every controller branch.)"""
+    parts = [ground_part(0)]
+    bv, bi = box_mesh(6.0)
+    parts.append(part(bv, bi, trs_model((0, 0, -10)), entity_id=1))
+    rv, ri = wedge_mesh(8.0, 10.0, 4.0)
+    parts.append(part(rv, ri, trs_model((8, GROUND_Y + 2.0, 0)), mu_s=0.35, mu_k=0.25, flatten_ground=True,
+                      entity_id=2))
+    sv, si = box_mesh(2.0)
+    parts.append(part(sv, si, trs_model((-6, -2, 4)), entity_id=3))
+    a = load_mirror_fixture()
+    model = mirror_model(a["transform"])
+    for k, (v, i) in enumerate(a["hulls"]):
+        parts.append(part(v, i, model, layer=LAYER_MIRROR, mu_s=0.6, mu_k=0.5, entity_id=4 + k))
+    return parts
+
+
+def c1_apply_intent(states, frame, n_frames=600, speed=12.5, accel=20.0, decel=36.0, dt=1.0 / 60.0):
+    """PhysicsIntentSystem rule for a character-controller body (Systems.swift:228-233 + approachVecD :419-426):
+    horizontal velocity approaches the desired velocity by at most accel*dt; scripted heading
+    yaw = 2*pi*frame/n_frames at `speed`.  Operates in place on a STATE record array (float64 velocity)."""
+    yaw = 2.0 * np.pi * frame / n_frames
+    v = states["velocity"]
+    spd = np.broadcast_to(np.asarray(speed, np.float64), (len(v),))
+    tgt = np.stack([np.float32(np.cos(yaw) * spd).astype(np.float64), np.zeros(len(v)),
+                    np.float32(np.sin(yaw) * spd).astype(np.float64)], axis=1)
+    cur = np.stack([v[:, 0], np.zeros(len(v)), v[:, 2]], axis=1)
+    acc = np.where(np.linalg.norm(tgt, axis=1) >= np.linalg.norm(cur, axis=1), np.float32(accel), np.float32(decel))
+    max_delta = acc.astype(np.float64) * np.float64(np.float32(dt))
+    delta = tgt - cur
+    ln = np.sqrt((delta[:, 0] * delta[:, 0] + delta[:, 1] * delta[:, 1]) + delta[:, 2] * delta[:, 2])
+    reach = (ln <= max_delta) | (ln < 0.00001)
+    safe = np.where(ln > 0, ln, 1.0)
+    nxt = np.where(reach[:, None], tgt, cur + delta / safe[:, None] * max_delta[:, None])
+    v[:, 0] = nxt[:, 0]
+    v[:, 2] = nxt[:, 2]
+
+
+C1_STARTS = np.array([[0, 7.5, 0], [-18.5, 1.5, -5.05], [-13.16, 1.5, -3.16], [20.7, 1.5, -12.7]], f32)
+C1_SPEEDS = np.array([12.5, 6.0, 4.5, 8.0])
+
+
+def c1_run(step_fn, states, n_frames=600, speeds=12.5):
+    """Drive `n_frames` fixed steps: intent -> step_fn(states) (gravity + move-and-slide).  Returns the
+    per-frame record (position f64x3, grounded, grounded_near, ground_triangle_index, ground_normal)."""
+    rec = np.zeros((n_frames, len(states)), dtype=[("position", "<f8", 3), ("grounded", "u1"), ("grounded_near", "u1"),
+                                                   ("ground_triangle_index", "<i4"), ("ground_normal", "<f4", 3)])
+    for f in range(n_frames):
+        c1_apply_intent(states, f, n_frames, speeds)
+        step_fn(states)
+        for k in rec.dtype.names:
+            rec[k][f] = states[k]
+    return rec
