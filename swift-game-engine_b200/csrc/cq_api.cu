@@ -35,6 +35,12 @@ int ensure_scratch(ScratchBuf &b, size_t bytes) {
     return r;
 }
 
+int *next_work_counter(cq_world *w, cudaStream_t st) {
+    int *p = w->dWork + (w->workSeq++ % CQ_WORK_RING);
+    if (check_cuda(cudaMemsetAsync(p, 0, sizeof(int), st), "work counter") != CQ_OK) return nullptr;
+    return p;
+}
+
 static void make_view(cq_world *w) {
     for (int s = 0; s < 2; s++) {
         DeviceSet &S = w->set[s];
@@ -198,6 +204,7 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
         return fail(rc);
     if ((rc = check_cuda(cudaMalloc((void **)&w->dCounters, sizeof(unsigned long long) * 4), "counters")) != CQ_OK) return fail(rc);
     cudaMemsetAsync(w->dCounters, 0, sizeof(unsigned long long) * 4, w->stream);
+    if ((rc = check_cuda(cudaMalloc((void **)&w->dWork, sizeof(int) * CQ_WORK_RING), "work counters")) != CQ_OK) return fail(rc);
     if (n_parts) {
         cudaMemcpyAsync(w->dModels, models.data(), sizeof(float) * 16 * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
         cudaMemcpyAsync(w->dMaterials, materials.data(), sizeof(float4) * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
@@ -225,7 +232,7 @@ void cq_world_destroy(cq_world *w) {
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (int s = 0; s < 2; s++) free_set(w->set[s]);
-    cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters);
+    cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork);
     cudaFree(w->in.ptr), cudaFree(w->out.ptr), cudaFree(w->aux.ptr), cudaFree(w->aux2.ptr);
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);

@@ -66,6 +66,8 @@ struct cq_world {
     int counting = 0;
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
     uint64_t launches = 0;
+    int *dWork = nullptr; // ring of dynamic-fetch counters, one per persistent-kernel launch in flight
+    uint32_t workSeq = 0;
     cq::ScratchBuf in, out, aux, aux2;
 };
 
@@ -85,6 +87,9 @@ int check_cuda(cudaError_t e, const char *what);
     } while (0)
 
 int ensure_scratch(ScratchBuf &b, size_t bytes);
+#define CQ_WORK_RING 256
+// zeroed work counter for the next persistent-kernel launch on `st` (nullptr on CUDA error)
+int *next_work_counter(cq_world *w, cudaStream_t st);
 
 // cq_build.cu
 int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,

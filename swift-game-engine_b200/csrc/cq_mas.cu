@@ -19,6 +19,7 @@
 namespace cq {
 
 #define MAS_THREADS 128
+#define MAS_SMEM_BYTES (sizeof(CharCtx) * MAS_THREADS + sizeof(float) * CQ_LIST * 4 * MAS_THREADS)
 
 struct MasArgs {
     cq_controller_params p;
@@ -200,7 +201,8 @@ __device__ __forceinline__ bool slide_resolve(CharCtx &c, const cq_controller_pa
 }
 
 // GroundProbe tail + GroundSnap + SlopeFriction + writeBack (SYS:923-1021, 1787-1821)
-__device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const MasArgs &A, cq_character_state *out) {
+__device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const MasArgs &A, cq_character_state *out,
+                                           bool count, uint32_t evalsNow) {
     const cq_controller_params &P = A.p;
     cq_character_state &S = c.st;
     const f3 gravity = {A.gx, A.gy, A.gz};
@@ -292,6 +294,10 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
     st3(S.ground_normal, grounded ? gNormal : mk3(0, 1, 0));
     S.ground_distance = c.gDistance;
     if (grounded) S.ground_triangle_index = c.cTri;
+    if (count) { // counting build only: distance evaluations spent on this character -> _pad[1..4] (debug)
+        uint32_t e = evalsNow - (uint32_t)c._pad;
+        S._pad[1] = e & 255u, S._pad[2] = (e >> 8) & 255u, S._pad[3] = (e >> 16) & 255u, S._pad[4] = (e >> 24) & 255u;
+    }
     // 168-byte record out: 21 x 8-byte stores
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&S);
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(out);
@@ -303,7 +309,7 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
 // next query, post it.  Returns false when the lane has no more characters.
 template <bool COUNT>
 __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, const WorldView &W, const MasArgs &A,
-                                            cq_character_state *states, int n, int stride, Counters &ctr) {
+                                            cq_character_state *states, int n, int *workCounter, Counters &ctr) {
     const cq_controller_params &P = A.p;
     const f3 down = {0.0f, -1.0f, 0.0f};
     int next = NX_LOAD;
@@ -426,6 +432,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
     // ---------------- post
     while (true) {
         if (next == NX_LOAD) {
+            c.charIndex = atomicAdd(workCounter, 1); // dynamic fetch: lanes never wait on a slow neighbour's character
             if (c.charIndex >= n) {
                 c.wait = W_NONE;
                 q_idle(q);
@@ -465,6 +472,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             stv(S, vel);
             st3(c.rem, to_f3(remD));
             c.depenIt = 0, c.slideIt = 0, c.offsetIt = 0;
+            c._pad = (int)ctr.evals;
             st3(c.dSum, mk3(0, 0, 0));
             c.dWeight = 0.0f;
             c.gDistance = FLT_MAX;
@@ -557,8 +565,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             return true;
         }
         if (next == NX_FINISH) {
-            mas_finish(c, W, A, states + c.charIndex);
-            c.charIndex += stride;
+            mas_finish(c, W, A, states + c.charIndex, COUNT, ctr.evals);
             next = NX_LOAD;
         }
     }
@@ -566,11 +573,13 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
 
 template <bool COUNT>
 __global__ void __launch_bounds__(MAS_THREADS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states, int n,
-                                                                MasArgs A, unsigned long long *gctr) {
-    __shared__ CharCtx ctxs[MAS_THREADS];
+                                                                MasArgs A, int *workCounter, unsigned long long *gctr) {
+    extern __shared__ __align__(16) unsigned char masSmem[]; // MAS_SMEM_BYTES, dynamic (> 48 KB)
+    CharCtx *ctxs = reinterpret_cast<CharCtx *>(masSmem);
+    float *candMem = reinterpret_cast<float *>(masSmem + sizeof(CharCtx) * MAS_THREADS);
     CharCtx &c = ctxs[threadIdx.x];
-    const int stride = gridDim.x * blockDim.x;
-    c.charIndex = blockIdx.x * blockDim.x + threadIdx.x;
+    const CandList cl = {candMem + threadIdx.x, MAS_THREADS};
+    c.charIndex = -1;
     c.wait = W_NONE;
     c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
@@ -579,12 +588,13 @@ __global__ void __launch_bounds__(MAS_THREADS) k_move_and_slide(WorldView W, cq_
     int stack[CQ_STACK];
     bool alive = true;
     while (true) {
-        // L: lanes whose query is finished run the controller logic and post their next query
-        if (alive && q.phase == PH_NONE && q.travDone) alive = mas_advance<COUNT>(c, q, stack, W, A, states, n, stride, ctr);
-        // T: lanes without a candidate walk the LBVH
-        if (q.phase == PH_NONE && !q.travDone) q_next_candidate<COUNT>(W, q, stack, ctr);
-        // E: one distance evaluation for every lane that holds a candidate
-        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, ctr);
+        // front end: controller logic (consume a finished query, post the next) / candidate acquisition
+        while (q.phase == PH_NONE && alive) {
+            if (q.done) alive = mas_advance<COUNT>(c, q, stack, W, A, states, n, workCounter, ctr);
+            else q_acquire<COUNT>(W, q, stack, cl, ctr);
+        }
+        // back end: one distance evaluation for every lane that holds a candidate
+        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, cl, ctr);
         if (__all_sync(0xffffffffu, !alive)) break;
     }
     if (COUNT) {
@@ -614,14 +624,18 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
         CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
         numSms = prop.multiProcessorCount;
         int b = 0;
-        if (ci) CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<true>, MAS_THREADS, 0));
-        else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<false>, MAS_THREADS, 0));
+        CQ_CUDA(cudaFuncSetAttribute(k_move_and_slide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAS_SMEM_BYTES));
+        CQ_CUDA(cudaFuncSetAttribute(k_move_and_slide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAS_SMEM_BYTES));
+        if (ci) CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<true>, MAS_THREADS, MAS_SMEM_BYTES));
+        else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<false>, MAS_THREADS, MAS_SMEM_BYTES));
         blocksPerSm[ci] = b > 0 ? b : 1;
     }
     // persistent lanes: one resident wave of CTAs (148 SMs x resident CTAs per SM), lanes stride over characters
     int blocks = std::min((n + MAS_THREADS - 1) / MAS_THREADS, numSms * blocksPerSm[ci]);
-    if (w->counting) k_move_and_slide<true><<<blocks, MAS_THREADS, 0, st>>>(w->view, d_inout, n, A, w->dCounters);
-    else k_move_and_slide<false><<<blocks, MAS_THREADS, 0, st>>>(w->view, d_inout, n, A, w->dCounters);
+    int *work = next_work_counter(w, st);
+    if (!work) return CQ_ERR_CUDA;
+    if (w->counting) k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, work, w->dCounters);
+    else k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_move_and_slide");
 }

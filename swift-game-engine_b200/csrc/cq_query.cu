@@ -62,10 +62,10 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 // iteration counts are.
 template <bool COUNT>
 __global__ void __launch_bounds__(Q_THREADS) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
-                                                            int mode, cq_cast_hit *__restrict__ out,
+                                                            int mode, cq_cast_hit *__restrict__ out, int *workCounter,
                                                             unsigned long long *gctr) {
-    const int stride = gridDim.x * blockDim.x;
-    int next = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float candMem[CQ_LIST * 4 * Q_THREADS];
+    const CandList cl = {candMem + threadIdx.x, Q_THREADS};
     int cur = -1;
     Counters ctr = {0, 0, 0, 0};
     LaneQ q;
@@ -73,8 +73,12 @@ __global__ void __launch_bounds__(Q_THREADS) k_capsule_cast(WorldView W, const c
     int stack[CQ_STACK];
     bool alive = true;
     while (true) {
-        if (alive && q.phase == PH_NONE && q.travDone) { // L: write the finished hit, fetch the next query
-            if (cur >= 0) {
+        while (q.phase == PH_NONE && alive) { // front end
+            if (!q.done) {
+                q_acquire<COUNT>(W, q, stack, cl, ctr);
+                continue;
+            }
+            if (cur >= 0) { // write the finished hit
                 cq_cast_hit h;
                 if (q.bestTri >= 0) {
                     h.toi = q.bestT;
@@ -90,20 +94,18 @@ __global__ void __launch_bounds__(Q_THREADS) k_capsule_cast(WorldView W, const c
                     h.triangle_index = -1;
                 }
                 out[cur] = h;
-                cur = -1;
             }
-            if (next < n) {
-                cq_capsule_cast c = qs[next];
-                cur = next;
-                next += stride;
+            cur = atomicAdd(workCounter, 1); // dynamic fetch of the next query
+            if (cur < n) {
+                cq_capsule_cast c = qs[cur];
                 q_begin_cast<COUNT>(W, q, stack, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
                                     c.min_normal_y, ctr);
             } else {
+                cur = -1;
                 alive = false;
             }
         }
-        if (q.phase == PH_NONE && !q.travDone) q_next_candidate<COUNT>(W, q, stack, ctr); // T
-        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, ctr);                                // E
+        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, cl, ctr); // back end
         if (__all_sync(0xffffffffu, !alive)) break;
     }
     flush_counters<COUNT>(ctr, gctr);
@@ -223,8 +225,10 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
         blocksPerSm[ci] = b > 0 ? b : 1;
     }
     int blocks = std::min(cdiv(n, Q_THREADS), numSms * blocksPerSm[ci]); // one resident wave of persistent lanes
-    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
-    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, w->dCounters);
+    int *work = next_work_counter(w, st);
+    if (!work) return CQ_ERR_CUDA;
+    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, work, w->dCounters);
+    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }

@@ -1,0 +1,229 @@
+"""Pins the CPU oracle (oracle/cq_oracle.cpp) with analytic known answers.  The reference has no tests or
+golden vectors for this path (GameTests/GameTests.swift is an empty template), so these closed-form cases,
+the brute-force cross-check and the committed golden trajectory are what pin the restatement."""
+import numpy as np
+import pytest
+
+F32_MAX = np.finfo(np.float32).max
+
+
+def big_floor(scenes, y=0.0, size=200.0, eid=0, **kw):
+    v, i = scenes.plane_mesh(size)
+    return scenes.part(v, i, scenes.trs_model((0, y, 0)), entity_id=eid, **kw)
+
+
+def wall_x(scenes, x=5.0, eid=1):
+    """A large two-triangle wall in the plane x = const, facing -x."""
+    v = np.array([[x, -50, -50], [x, -50, 50], [x, 50, 50], [x, 50, -50]], np.float32)
+    return scenes.part(v, [0, 1, 2, 0, 2, 3], entity_id=eid)
+
+
+# ---------------------------------------------------------------- primitives (CollisionQuery.swift:1396-1601)
+def test_closest_point_on_triangle_regions(orc):
+    a, b, c = (0, 0, 0), (2, 0, 0), (0, 2, 0)
+    cases = [((0.5, 0.5, 3.0), (0.5, 0.5, 0), 9.0),  # face
+             ((-1, -1, 0), (0, 0, 0), 2.0),  # vertex A
+             ((3, -1, 0), (2, 0, 0), 2.0),  # vertex B
+             ((-1, 3, 0), (0, 2, 0), 2.0),  # vertex C
+             ((1, -2, 0), (1, 0, 0), 4.0),  # edge AB
+             ((-2, 1, 0), (0, 1, 0), 4.0),  # edge AC
+             ((2, 2, 0), (1, 1, 0), 2.0)]  # edge BC
+    for p, want, d2 in cases:
+        d, pt = orc.closest_point_on_triangle(p, a, b, c)
+        assert np.allclose(pt, want, atol=1e-6) and d == pytest.approx(d2, rel=1e-6)
+
+
+def test_segment_segment_distance(orc):
+    d, c1, c2 = orc.segment_segment_distance_sq((0, 1, 0), (0, -1, 0), (1, 0, -1), (1, 0, 1))  # crossing at distance 1
+    assert d == pytest.approx(1.0) and np.allclose(c1, (0, 0, 0)) and np.allclose(c2, (1, 0, 0))
+    d, c1, c2 = orc.segment_segment_distance_sq((0, 1, 0), (0, -1, 0), (3, 5, 0), (3, 2, 0))  # endpoint-endpoint
+    assert d == pytest.approx(9.0 + 1.0) and np.allclose(c1, (0, 1, 0)) and np.allclose(c2, (3, 2, 0))
+    d, _, _ = orc.segment_segment_distance_sq((0, 0, 0), (0, 0, 0), (1, 0, 0), (1, 0, 0))  # both degenerate
+    assert d == pytest.approx(1.0)
+    d, c1, c2 = orc.segment_segment_distance_sq((0, 0, 0), (0, 0, 0), (2, -1, 0), (2, 1, 0))  # first degenerate
+    assert d == pytest.approx(4.0) and np.allclose(c2, (2, 0, 0))
+
+
+def test_segment_triangle_distance(orc):
+    v0, v1, v2 = (-10, 0, -10), (10, 0, -10), (0, 0, 10)
+    d, seg, tri = orc.segment_triangle_distance((0, 3.0, 0), 1.0, v0, v1, v2)  # axis above the face
+    assert d == pytest.approx(2.0) and np.allclose(seg, (0, 2, 0)) and np.allclose(tri, (0, 0, 0))
+    d, seg, tri = orc.segment_triangle_distance((0, 0.5, 0), 1.0, v0, v1, v2)  # axis pierces the face -> 0
+    assert d == 0.0 and np.allclose(seg, tri) and np.allclose(tri, (0, 0, 0), atol=1e-6)
+    d, seg, tri = orc.segment_triangle_distance((13, 0.0, -10), 1.0, v0, v1, v2)  # beside vertex v1
+    assert d == pytest.approx(3.0) and np.allclose(tri, (10, 0, -10))
+
+
+# ---------------------------------------------------------------- casts (CollisionQuery.swift:980-1359)
+def test_vertical_drop_toi_is_gap_minus_capsule(orc, scenes):
+    """Capsule dropped onto a floor: contact when bottom sphere touches, toi = y0 - floor - r - hh.
+    refineTOI returns the upper end of 10 bisections of [lastSafeT, t], so toi is within span/1024 above."""
+    w = orc.OracleWorld([big_floor(scenes, y=-3.0)])
+    r, hh = 1.5, 1.0
+    for y0 in (2.0, 7.5, 40.0):
+        q = np.zeros(1, orc.CAST)
+        q["from"], q["delta"] = (0.3, y0, -0.2), (0, -(y0 + 10), 0)
+        q["radius"], q["half_height"], q["mask"], q["min_normal_y"] = r, hh, 0xFFFFFFFF, 0.5
+        want = y0 - (-3.0) - r - hh
+        for mode in (0, 1, 2):
+            h = w.capsule_cast(q, mode, orc.ORDER_REFERENCE)[0]
+            assert h["triangle_index"] in (0, 1)
+            assert want - 1e-5 <= h["toi"] <= want + want / 1024 + 2e-5
+            assert np.allclose(h["normal"], (0, 1, 0), atol=1e-5) and np.allclose(h["triangle_normal"], (0, 1, 0))
+            assert h["position"][1] == pytest.approx(-3.0, abs=1e-5)  # position = point ON the triangle (:1342)
+
+
+def test_horizontal_sweep_into_wall(orc, scenes):
+    w = orc.OracleWorld([wall_x(scenes, 5.0, eid=0)])
+    q = np.zeros(1, orc.CAST)
+    q["from"], q["delta"], q["radius"], q["half_height"], q["mask"] = (0, 0, 0), (10, 0, 0), 0.5, 1.0, 0xFFFFFFFF
+    h = w.capsule_cast(q, 0, orc.ORDER_REFERENCE)[0]
+    want = 5.0 - 0.5
+    assert want - 1e-5 <= h["toi"] <= want + want / 1024 + 2e-5
+    assert np.allclose(h["normal"], (-1, 0, 0), atol=1e-5)
+    assert np.allclose(h["triangle_normal"], (-1, 0, 0), atol=1e-6)  # flipped to agree with the contact normal
+    # moving away: blocking mode rejects (dot(delta, normal) >= 0), plain mode has nothing ahead
+    q["delta"] = (-3, 0, 0)
+    assert w.capsule_cast(q, 1, orc.ORDER_REFERENCE)[0]["triangle_index"] == -1
+    # sweep shorter than the gap -> nil ; zero-length sweep -> nil (CollisionQuery.swift:988)
+    q["delta"] = (4.0, 0, 0)
+    assert w.capsule_cast(q, 0, orc.ORDER_REFERENCE)[0]["triangle_index"] == -1
+    q["delta"] = (0, 0, 0)
+    assert w.capsule_cast(q, 0, orc.ORDER_REFERENCE)[0]["triangle_index"] == -1
+
+
+def test_ground_mode_filters_steep_triangles_and_layer_mask(orc, scenes):
+    parts = [wall_x(scenes, 2.0, eid=0), big_floor(scenes, y=-3.0, eid=1, layer=4)]
+    w = orc.OracleWorld(parts)
+    q = np.zeros(1, orc.CAST)
+    q["from"], q["delta"], q["radius"], q["half_height"] = (1.0, 0, 0), (0, -5, 0), 1.5, 1.0
+    q["mask"], q["min_normal_y"] = 0xFFFFFFFF, 0.5
+    # the wall (triangles 0,1) is already overlapping at t=0 but is not ground; ground mode must skip it
+    h = w.capsule_cast(q, 2, orc.ORDER_REFERENCE)[0]
+    assert h["triangle_index"] in (2, 3) and h["toi"] == pytest.approx(0.5, abs=2e-3)
+    assert w.capsule_cast(q, 0, orc.ORDER_REFERENCE)[0]["triangle_index"] in (0, 1)
+    q["mask"] = 1  # floor is on layer 4 -> invisible
+    assert w.capsule_cast(q, 2, orc.ORDER_REFERENCE)[0]["triangle_index"] == -1
+
+
+# ---------------------------------------------------------------- overlap (CollisionQuery.swift:1119-1283)
+def test_overlap_depth_is_radius_minus_distance(orc, scenes):
+    w = orc.OracleWorld([big_floor(scenes, y=0.0)])
+    c = np.zeros(3, orc.CAPSULE)
+    c["from"] = [(0.25, 2.0, 0.5), (0.25, 3.0, 0.5), (0.25, 0.5, 0.5)]
+    c["radius"], c["half_height"], c["mask"] = 1.5, 1.0, 0xFFFFFFFF
+    h = w.capsule_overlap(c, orc.ORDER_REFERENCE)
+    assert h["depth"][0] == pytest.approx(0.5, abs=1e-6) and np.allclose(h["normal"][0], (0, 1, 0))
+    assert h["triangle_index"][1] == -1  # bottom of the capsule is 0.5 above the floor
+    assert h["depth"][2] == pytest.approx(1.5) and np.allclose(h["normal"][2], (0, 1, 0))  # axis pierces: dist 0 -> tri normal
+    hits, counts, ov = w.capsule_overlap_all(c, 8, orc.ORDER_REFERENCE)
+    assert counts.tolist() == [1, 0, 2] or counts.tolist() == [2, 0, 2]
+    assert not ov.any()
+
+
+# ---------------------------------------------------------------- raycast (CollisionQuery.swift:916-978, 1575-1631)
+def test_raycast_unit_triangle(orc, scenes):
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    w = orc.OracleWorld([scenes.part(v, [0, 1, 2], entity_id=0)])
+    r = np.zeros(6, orc.RAY)
+    r["origin"] = [(0.25, 2, 0.25), (0.25, -2, 0.25), (0.75, 2, 0.75), (0.25, 2, 0.25), (0.25, 2, 0.25), (0.5, 2, 0.5)]
+    r["direction"] = [(0, -1, 0), (0, 1, 0), (0, -1, 0), (0, -4, 0), (0, 1, 0), (0, -1, 0)]
+    r["max_distance"], r["mask"] = 100.0, 0xFFFFFFFF
+    r["max_distance"][3] = 0.4  # direction is not normalised: t is in units of |direction| -> hit at t = 0.5 > 0.4
+    for order in (orc.ORDER_REFERENCE, orc.ORDER_CANONICAL):
+        h = w.raycast(r, order)
+        assert h["triangle_index"].tolist() == [0, 0, -1, -1, -1, 0]
+        assert h["distance"][0] == pytest.approx(2.0) and np.allclose(h["position"][0], (0.25, 0, 0.25))
+        assert np.allclose(h["normal"][0], (0, 1, 0)) and np.allclose(h["normal"][1], (0, -1, 0))  # opposes the ray
+        assert h["distance"][5] == pytest.approx(2.0)  # on the hypotenuse u+v == 1 is still a hit
+
+
+# ---------------------------------------------------------------- BVH (CollisionQuery.swift:496-707)
+def test_reference_bvh_equals_brute_force_except_ties(orc, scenes):
+    """Candidate sets are tree-independent; the only order-dependent outcome is WHICH triangle is named when
+    two accepted candidates have bit-identical toi."""
+    parts = scenes.mirror_scene(use_hulls=False)
+    w = orc.OracleWorld(parts)
+    assert w.check_bvh(0) and w.counts(0)["triangles"] == 14213  # 14,211 kept of 14,246 + 2 ground
+    lo, hi = scenes.scene_aabb(parts[1:])
+    q = scenes.gen_casts(1500, lo, hi, seed=5)
+    a = w.capsule_cast(q, 0, orc.ORDER_REFERENCE)
+    b = w.capsule_cast(q, 0, orc.ORDER_CANONICAL)
+    assert np.array_equal(a["toi"], b["toi"])
+    assert np.array_equal(a["triangle_index"] >= 0, b["triangle_index"] >= 0)
+    same = a["triangle_index"] == b["triangle_index"]
+    assert same.mean() > 0.5
+    assert (b["triangle_index"][~same] < a["triangle_index"][~same]).all()  # canonical = smallest index of the tie
+    r = scenes.gen_rays(1500, lo, hi, seed=6, expand=2.0)
+    ra, rb = w.raycast(r, orc.ORDER_REFERENCE), w.raycast(r, orc.ORDER_CANONICAL)
+    assert (ra["triangle_index"] != rb["triangle_index"]).mean() < 0.01
+
+
+def test_degenerate_filter_is_absolute_in_world_units(orc, scenes):
+    """|e1 x e2|^2 <= 1e-10 is tested AFTER the model transform (CollisionQuery.swift:385): the same mesh keeps
+    3,515 triangles unscaled and 14,211 at the demo's x8 scale."""
+    a = scenes.load_mirror_fixture()
+    w1 = orc.OracleWorld([scenes.part(a["positions"], a["indices"], a["transform"])])
+    assert w1.counts(0)["triangles"] == 3515
+    w8 = orc.OracleWorld([scenes.part(a["positions"], a["indices"], scenes.mirror_model(a["transform"]))])
+    assert w8.counts(0)["triangles"] == 14211
+
+
+def test_refit_keeps_bvh_consistent(orc, scenes):
+    parts = scenes.mirror_scene(use_hulls=True, mirror_dynamic=True)
+    w = orc.OracleWorld(parts)
+    a = scenes.load_mirror_fixture()
+    t, q0, s = scenes.transform_from_matrix(scenes.mirror_model(a["transform"]))
+    before = w.read_soup(1)["aabbs"].copy()
+    model = scenes.trs_model(t + np.float32([1, 0, 0]), q0, s)
+    w.update_transforms([1, 2], [model, model])
+    after = w.read_soup(1)["aabbs"]
+    assert w.check_bvh(1)
+    assert np.allclose(after[:, 0], before[:, 0] + 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------- move-and-slide (Systems.swift:734-1821)
+def test_character_lands_and_rests_on_floor(orc, scenes):
+    w = orc.OracleWorld([big_floor(scenes, y=-3.0)])
+    p = orc.default_params()
+    s = orc.init_states([[0, 7.5, 0]])
+    for _ in range(120):
+        w.move_and_slide(s, p, order=orc.ORDER_REFERENCE)
+    assert s["grounded"][0] == 1 and s["grounded_near"][0] == 1
+    # resting height = floor + r + hh + groundSnapSkin
+    assert s["position"][0][1] == pytest.approx(-3.0 + 1.5 + 1.0 + 0.05, abs=2e-3)
+    assert abs(s["velocity"][0][1]) < 1e-6 and np.allclose(s["ground_normal"][0], (0, 1, 0), atol=1e-6)
+    assert s["ground_triangle_index"][0] in (0, 1) and s["ground_distance"][0] == pytest.approx(0.05, abs=2e-3)
+
+
+def test_character_walks_and_is_stopped_by_wall(orc, scenes):
+    w = orc.OracleWorld([big_floor(scenes, y=-3.0, eid=0), wall_x(scenes, 6.0, eid=1)])
+    p = orc.default_params()
+    s = orc.init_states([[0, -0.45, 0]], [[12.5, 0, 0]])
+    xs = []
+    for _ in range(90):
+        s["velocity"][0][0] = 12.5  # keep pushing (PhysicsIntentSystem would)
+        w.move_and_slide(s, p, order=orc.ORDER_REFERENCE)
+        xs.append(s["position"][0][0])
+    assert xs[5] == pytest.approx(6 * 12.5 / 60, rel=1e-3)  # free walk: v*dt per step
+    # stopped short of the wall by radius + skinWidth (contact skin 0.3 for side hits)
+    assert 6.0 - 1.5 - 0.3 - 0.02 <= xs[-1] <= 6.0 - 1.5 + 1e-3
+    assert s["grounded"][0] == 1 and s["side_contact_frames"][0] > 0 and s["manifold_count"][0] >= 1
+    # (velocity is NOT zeroed while "sticky" at the wall: that branch returns before adjustVelocity, SYS:1320-1323)
+
+
+def test_character_pushed_out_of_floor(orc, scenes):
+    w = orc.OracleWorld([big_floor(scenes, y=-3.0)])
+    s = orc.init_states([[0, -1.0, 0]])  # bottom at -3.5: 0.5 below the floor
+    w.move_and_slide(s, orc.default_params(), order=orc.ORDER_REFERENCE)
+    assert s["position"][0][1] >= -0.5 - 1e-4 and s["grounded"][0] == 1
+
+
+def test_empty_world_free_fall(orc, scenes):
+    w = orc.OracleWorld([])
+    s = orc.init_states([[0, 0, 0]], [[1, 0, 0]])
+    w.move_and_slide(s, orc.default_params(), order=orc.ORDER_REFERENCE)
+    dt = np.float32(1.0 / 60.0)
+    vy = -98.0 * float(dt)
+    assert s["velocity"][0][1] == pytest.approx(vy) and s["position"][0][1] == pytest.approx(vy * float(dt), rel=1e-5)
+    assert s["grounded"][0] == 0 and s["ground_distance"][0] == F32_MAX
