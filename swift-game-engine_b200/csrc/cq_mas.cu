@@ -13,13 +13,15 @@
 // convergent stages L (controller logic: consume a finished query, clip against the contact plane, post
 // the next query), T (BVH walk to the next candidate) and E (one segment-triangle distance evaluation).
 // Double precision exactly where the reference uses Double (velocity; SYS:792,882,958,1045,1368).
-#include "cq_engine.cuh"
+#include "cq_pool.cuh"
 #include "cq_internal.h"
 
 namespace cq {
 
 #define MAS_THREADS 128
-#define MAS_SMEM_BYTES (sizeof(CharCtx) * MAS_THREADS + sizeof(float) * CQ_LIST * 4 * MAS_THREADS)
+#define MAS_WARPS (MAS_THREADS / 32)
+#define MAS_SMEM_BYTES \
+    (sizeof(CharCtx) * MAS_THREADS + sizeof(QShared) * MAS_THREADS + sizeof(uint32_t) * (CQ_QCAP + 2) * MAS_WARPS)
 
 struct MasArgs {
     cq_controller_params p;
@@ -308,8 +310,9 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
 // Stage L of the move-and-slide kernel: consume the finished query, run the controller logic up to the
 // next query, post it.  Returns false when the lane has no more characters.
 template <bool COUNT>
-__device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, const WorldView &W, const MasArgs &A,
-                                            cq_character_state *states, int n, int *workCounter, Counters &ctr) {
+__device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShared &s, OwnerQ &oq, int *stack,
+                                            const WorldView &W, const MasArgs &A, cq_character_state *states, int n,
+                                            int *workCounter, Counters &ctr) {
     const cq_controller_params &P = A.p;
     const f3 down = {0.0f, -1.0f, 0.0f};
     int next = NX_LOAD;
@@ -435,7 +438,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             c.charIndex = atomicAdd(workCounter, 1); // dynamic fetch: lanes never wait on a slow neighbour's character
             if (c.charIndex >= n) {
                 c.wait = W_NONE;
-                q_idle(q);
+                oq.travDone = true;
                 return false;
             }
             { // 168-byte record in
@@ -484,7 +487,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             next = NX_DEPEN;
         }
         if (next == NX_DEPEN) {
-            q_begin_overlap<COUNT>(W, q, stack, ld3(c.pos), P.radius, P.half_height, P.collision_mask, ctr);
+            pool_post_overlap<COUNT>(W, s, oq, stack, ld3(c.pos), P.radius, P.half_height, P.collision_mask, ctr);
             c.wait = W_DEPEN;
             return true;
         }
@@ -494,7 +497,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             if (c.slideIt >= P.max_slide_iterations || c.slideLen < 1e-6f) { // SYS:1674-1676
                 next = NX_SNAP;
             } else {
-                q_begin_cast<COUNT>(W, q, stack, ld3(c.pos), remaining, P.radius, P.half_height, P.collision_mask,
+                pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos), remaining, P.radius, P.half_height, P.collision_mask,
                                     CQ_MODE_BLOCKING, 0.0f, ctr);
                 c.wait = W_SLIDE;
                 return true;
@@ -504,7 +507,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             if (!(P.snap_distance > 0.0f)) { // SYS:845
                 next = NX_FALL;
             } else {
-                q_begin_cast<COUNT>(W, q, stack, ld3(c.pos), down * P.snap_distance, P.radius, P.half_height,
+                pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos), down * P.snap_distance, P.radius, P.half_height,
                                     P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
                 c.wait = W_SNAP;
                 return true;
@@ -514,7 +517,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             if (!(P.fall_probe_distance > 0.0f)) { // SYS:855
                 next = NX_GATE;
             } else {
-                q_begin_cast<COUNT>(W, q, stack, ld3(c.pos), down * P.fall_probe_distance, P.radius, P.half_height,
+                pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos), down * P.fall_probe_distance, P.radius, P.half_height,
                                     P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
                 c.wait = W_FALL;
                 return true;
@@ -559,7 +562,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, LaneQ &q, int *stack, co
             int oi = c.offsetIt;
             float ox = oi == 0 ? offset : (oi == 1 ? -offset : 0.0f);
             float oz = oi == 2 ? offset : (oi == 3 ? -offset : 0.0f);
-            q_begin_cast<COUNT>(W, q, stack, ld3(c.pos) + mk3(ox, 0.0f, oz), down * P.snap_distance, P.radius, P.half_height,
+            pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos) + mk3(ox, 0.0f, oz), down * P.snap_distance, P.radius, P.half_height,
                                 P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
             c.wait = W_OFFSET;
             return true;
@@ -576,26 +579,52 @@ __global__ void __launch_bounds__(MAS_THREADS) k_move_and_slide(WorldView W, cq_
                                                                 MasArgs A, int *workCounter, unsigned long long *gctr) {
     extern __shared__ __align__(16) unsigned char masSmem[]; // MAS_SMEM_BYTES, dynamic (> 48 KB)
     CharCtx *ctxs = reinterpret_cast<CharCtx *>(masSmem);
-    float *candMem = reinterpret_cast<float *>(masSmem + sizeof(CharCtx) * MAS_THREADS);
+    QShared *qsAll = reinterpret_cast<QShared *>(masSmem + sizeof(CharCtx) * MAS_THREADS);
+    uint32_t *rings = reinterpret_cast<uint32_t *>(masSmem + (sizeof(CharCtx) + sizeof(QShared)) * MAS_THREADS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpPool wp;
+    wp.qs = qsAll + warp * 32;
+    wp.ring = rings + warp * (CQ_QCAP + 2);
+    wp.head = wp.ring + CQ_QCAP;
+    wp.tail = wp.ring + CQ_QCAP + 1;
     CharCtx &c = ctxs[threadIdx.x];
-    const CandList cl = {candMem + threadIdx.x, MAS_THREADS};
+    QShared &mine = wp.qs[lane];
     c.charIndex = -1;
     c.wait = W_NONE;
     c.flags = 0;
+    mine.pending = 0;
+    mine.rTri = -1;
+    if (lane == 0) {
+        *wp.head = 0;
+        *wp.tail = 0;
+    }
     Counters ctr = {0, 0, 0, 0};
-    LaneQ q;
-    q_idle(q);
+    OwnerQ oq;
+    oq.travDone = true;
+    oq.sp = 0, oq.set = 1, oq.leafPos = oq.leafEnd = 0, oq.mask = 0;
+    Job job;
+    job.phase = PH_NONE;
     int stack[CQ_STACK];
     bool alive = true;
-    while (true) {
-        // front end: controller logic (consume a finished query, post the next) / candidate acquisition
-        while (q.phase == PH_NONE && alive) {
-            if (q.done) alive = mas_advance<COUNT>(c, q, stack, W, A, states, n, workCounter, ctr);
-            else q_acquire<COUNT>(W, q, stack, cl, ctr);
+    __syncwarp();
+    for (uint32_t trip = 0; trip < (1u << 24); trip++) { // (the bound is a watchdog; the loop exits through the vote)
+        // owner: a finished query (walk done, no pair pending) -> controller logic -> next query posted
+        if (alive && oq.travDone && *(volatile int *)&mine.pending == 0) {
+            QResult r;
+            pool_read_result(mine, r);
+            alive = mas_advance<COUNT>(c, r, mine, oq, stack, W, A, states, n, workCounter, ctr);
         }
-        // back end: one distance evaluation for every lane that holds a candidate
-        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, cl, ctr);
-        if (__all_sync(0xffffffffu, !alive)) break;
+        // owner: walk the LBVH, push candidate pairs into the warp's ring
+        if (!oq.travDone) pool_traverse_push<COUNT>(W, wp, mine, oq, stack, lane, ctr);
+        __syncwarp();
+        // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
+        pool_take_jobs(W, wp, job, lane);
+        Commit cm;
+        cm.kind = 0;
+        bool retired = false;
+        if (job.phase != PH_NONE) pool_eval<COUNT>(job, wp, cm, retired, ctr);
+        pool_commit(wp, job, cm, retired, lane);
+        if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE)) break;
     }
     if (COUNT) {
         uint32_t v[4] = {ctr.nodes, ctr.cands, ctr.evals, ctr.queries};

@@ -1,0 +1,378 @@
+// cq_pool.cuh — warp-cooperative query engine: owners post queries, the warp's 32 lanes share the
+// (query, candidate-triangle) work items.
+//
+// Measured facts that shape this file (B200, ncu; profiles/):
+//  * thread-per-query with nested loops runs 2.0 of 32 lanes (v1);
+//  * a flat per-lane state machine fixes the nesting but not the WORKLOAD skew: distance evaluations per
+//    character-step are median 29-37 / p99 ~1000 (hulls) and median 29 / p99 ~36,000 (render mesh) — a
+//    character that touches geometry sweeps tens of "creeping" candidates for up to L/minAdvance trips
+//    each, exactly as the reference does (CollisionQuery.swift:1295-1356).  One lane per character then
+//    leaves most of the warp idle.
+// So the unit of scheduling here is one (query, candidate) PAIR, not a query and not a character:
+//  * each lane is the OWNER of one work unit (a character / a batch query): it runs the unit's serial
+//    logic, walks the LBVH for the unit's current query and pushes every candidate triangle into a
+//    per-warp ring in shared memory;
+//  * every lane is also an EXECUTOR: it takes any pair from the ring, runs its conservative
+//    advancement one distance evaluation per trip of the main loop, and commits the contact to the
+//    owner's record.  The best accepted toi of the query is shared, so the exact-safe prune
+//    `lastSafeT > bestT` works across lanes;
+//  * a query completes when its walk is finished and its pending-pair counter is back to zero.
+// The main loop is: owner logic -> owner traversal/push -> job pickup (ballot ranked) -> ONE distance
+// evaluation on every lane that holds a pair -> serialized commit -> warp-uniform exit test.
+// Results are deterministic: a cast's answer is the accepted pair with the smallest (toi, index), an
+// order-free reduction; commits are applied one lane at a time.
+#pragma once
+#include "cq_world.cuh"
+
+namespace cq {
+
+enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
+#define CQ_KIND_OVERLAP 3 /* query mode: two-deepest overlap (move-and-slide depenetration) */
+#define CQ_QCAP 128       /* ring entries per warp */
+
+struct QShared { // one per owner lane, shared memory: what executors need + the query's result
+    float from[3], dir[3], delta[3];
+    float L, radius, hh, minNormalY, minAdvance;
+    int maxIter, mode;
+    // result.  cast: rT/rTri/rPart + contact.  overlap: two deepest, d0=rT t0=rTri n0=rN | d1=rPos[0] t1=rPart n1=rTriN
+    float rT;
+    int rTri, rPart;
+    float rPos[3], rN[3], rTriN[3];
+    int pending; // pairs pushed and not yet retired
+};
+
+struct OwnerQ { // owner-side traversal cursor (registers)
+    f3 qlo, qhi;
+    uint32_t mask;
+    int sp, set, leafPos, leafEnd;
+    bool travDone;
+};
+
+struct QResult { // what owner logic reads back (same names as the engine's result fields)
+    float bestT;
+    int bestTri, bestPart;
+    f3 bestPos, bestN, bestTriN;
+};
+
+struct Job { // executor-side pair state (registers)
+    int phase, owner;
+    f3 from, dir;
+    float L, radius, hh, minAdvance;
+    int maxIter;
+    Tri T;
+    int gid, part;
+    float t, lastSafeT, lo, hi;
+    int it, k;
+};
+
+struct Commit { // a finished pair's contribution, applied in the serialized commit step
+    int kind; // 0 none, 1 cast contact, 2 overlap
+    float key;
+    f3 pos, n, triN;
+};
+
+struct WarpPool { // per-warp shared-memory handles
+    QShared *qs;             // [32]
+    uint32_t *ring;          // [CQ_QCAP]
+    volatile uint32_t *head; // consumed
+    volatile uint32_t *tail; // produced
+};
+
+__device__ __forceinline__ void pool_read_result(const QShared &s, QResult &r) {
+    r.bestT = s.rT;
+    r.bestTri = s.rTri;
+    r.bestPart = s.rPart;
+    r.bestPos = mk3(s.rPos[0], s.rPos[1], s.rPos[2]);
+    r.bestN = mk3(s.rN[0], s.rN[1], s.rN[2]);
+    r.bestTriN = mk3(s.rTriN[0], s.rTriN[1], s.rTriN[2]);
+}
+
+__device__ __forceinline__ void pool_push_root(const WorldView &W, OwnerQ &oq, int *stack, Counters &ctr, bool count) {
+    const SetHeader *hp = oq.set ? W.set[1].hdr : W.set[0].hdr;
+    SetHeader h = *hp;
+    oq.sp = 0;
+    if (h.rootRef == CQ_REF_EMPTY) return;
+    if (count) {
+        ctr.queries++;
+        ctr.nodes++;
+    }
+    if (box_disjoint(mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), oq.qlo, oq.qhi)) return;
+    stack[oq.sp++] = h.rootRef;
+}
+
+__device__ __forceinline__ void store3s(float *o, f3 v) {
+    o[0] = v.x;
+    o[1] = v.y;
+    o[2] = v.z;
+}
+
+// capsuleCastCombined prologue — CollisionQuery.swift:980-1043
+template <bool COUNT>
+__device__ __forceinline__ void pool_post_cast(const WorldView &W, QShared &s, OwnerQ &oq, int *stack, f3 from, f3 delta,
+                                               float radius, float hh, uint32_t mask, int mode, float minNormalY,
+                                               Counters &ctr) {
+    s.rTri = -1;
+    s.rPart = -1;
+    s.pending = 0;
+    s.mode = mode;
+    oq.leafPos = oq.leafEnd = 0;
+    oq.sp = 0;
+    float L = len(delta);
+    if (L < 1e-6f) { // nil without any traversal (:988)
+        oq.travDone = true;
+        return;
+    }
+    f3 dir = delta / L;
+    float minAdvance = smax(radius * 0.02f, 1e-4f); // :1295
+    store3s(s.from, from);
+    store3s(s.dir, dir);
+    store3s(s.delta, delta);
+    s.L = L;
+    s.radius = radius;
+    s.hh = hh;
+    s.minNormalY = minNormalY;
+    s.minAdvance = minAdvance;
+    s.maxIter = min(256, (int)ceilf(L / minAdvance) + 1); // :1296
+    s.rT = L;                                             // bestT starts at |delta| (:1038)
+    const f3 up = {0.0f, 1.0f, 0.0f};
+    f3 a0 = from + up * hh, b0 = from - up * hh;
+    f3 a1 = a0 + delta, b1 = b0 + delta;
+    f3 ext = {radius, radius, radius};
+    oq.qlo = vmin(vmin(a0, b0), vmin(a1, b1)) - ext;
+    oq.qhi = vmax(vmax(a0, b0), vmax(a1, b1)) + ext;
+    oq.mask = mask;
+    oq.set = 0;
+    oq.travDone = false;
+    pool_push_root(W, oq, stack, ctr, COUNT);
+}
+
+// capsuleOverlapAll prologue — CollisionQuery.swift:1209-1216 (two deepest kept, Systems.swift:764-767)
+template <bool COUNT>
+__device__ __forceinline__ void pool_post_overlap(const WorldView &W, QShared &s, OwnerQ &oq, int *stack, f3 from,
+                                                  float radius, float hh, uint32_t mask, Counters &ctr) {
+    s.pending = 0;
+    s.mode = CQ_KIND_OVERLAP;
+    store3s(s.from, from);
+    store3s(s.dir, mk3(0, 0, 0));
+    s.L = 0.0f;
+    s.radius = radius;
+    s.hh = hh;
+    s.minAdvance = 0.0f;
+    s.maxIter = 1;
+    s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));         // deepest
+    s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0)); // second deepest
+    overlap_box(from, radius, hh, oq.qlo, oq.qhi);
+    oq.mask = mask;
+    oq.leafPos = oq.leafEnd = 0;
+    oq.set = 0;
+    oq.travDone = false;
+    pool_push_root(W, oq, stack, ctr, COUNT);
+}
+
+// owner traversal: walk the LBVH and push candidate pairs while the ring has room
+template <bool COUNT>
+__device__ __forceinline__ void pool_traverse_push(const WorldView &W, const WarpPool &wp, QShared &s, OwnerQ &oq, int *stack,
+                                                   int lane, Counters &ctr) {
+    int pushed = 0;
+    while (!oq.travDone) {
+        if (oq.leafPos < oq.leafEnd) {
+            if (*wp.tail - *wp.head > CQ_QCAP - 33u) break; // ring (nearly) full: resume next trip
+            int slot = oq.leafPos++;
+            const float4 *p0 = oq.set ? W.set[1].tv0 : W.set[0].tv0;
+            const float4 *p1 = oq.set ? W.set[1].tv1 : W.set[0].tv1;
+            const float4 *p2 = oq.set ? W.set[1].tv2 : W.set[0].tv2;
+            float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
+            if ((__float_as_uint(a.w) & oq.mask) == 0u) continue; // layer mask, CollisionQuery.swift:1057
+            f3 v0 = xyz(a), v1 = xyz(b), v2 = xyz(c);
+            f3 tlo = vmin(v0, vmin(v1, v2)), thi = vmax(v0, vmax(v1, v2));
+            if (box_disjoint(tlo, thi, oq.qlo, oq.qhi)) continue; // :1060-1065
+            if (COUNT) ctr.cands++;
+            uint32_t pos = atomicAdd((uint32_t *)wp.tail, 1u);
+            wp.ring[pos % CQ_QCAP] = ((uint32_t)lane << 27) | ((uint32_t)oq.set << 26) | (uint32_t)slot;
+            pushed++;
+        } else if (oq.sp > 0) {
+            int ref = stack[--oq.sp];
+            if (ref < 0) {
+                int enc = ~ref;
+                oq.leafPos = enc >> 2;
+                oq.leafEnd = oq.leafPos + (enc & 3) + 1;
+            } else {
+                const Node *n = (oq.set ? W.set[1].nodes : W.set[0].nodes) + ref;
+                float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
+                if (COUNT) ctr.nodes += 2;
+                if (!box_disjoint(xyz(n2), xyz(n3), oq.qlo, oq.qhi)) stack[oq.sp++] = __float_as_int(n1.w);
+                if (!box_disjoint(xyz(n0), xyz(n1), oq.qlo, oq.qhi)) stack[oq.sp++] = __float_as_int(n0.w);
+            }
+        } else if (oq.set == 0) {
+            oq.set = 1; // static set done -> dynamic set (CollisionQuery.swift:990-1008)
+            pool_push_root(W, oq, stack, ctr, COUNT);
+        } else {
+            oq.travDone = true;
+        }
+    }
+    if (pushed) atomicAdd(&s.pending, pushed);
+}
+
+// job pickup: idle lanes take ring entries, ranked by ballot
+__device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPool &wp, Job &job, int lane) {
+    uint32_t idle = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
+    uint32_t h = *wp.head, avail = *wp.tail - h;
+    if (job.phase == PH_NONE) {
+        uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+        if (rank < avail) {
+            uint32_t e = wp.ring[(h + rank) % CQ_QCAP];
+            int owner = e >> 27, set = (e >> 26) & 1, slot = e & 0x3ffffffu;
+            const QShared &s = wp.qs[owner];
+            job.owner = owner;
+            job.from = mk3(s.from[0], s.from[1], s.from[2]);
+            job.dir = mk3(s.dir[0], s.dir[1], s.dir[2]);
+            job.L = s.L;
+            job.radius = s.radius;
+            job.hh = s.hh;
+            job.minAdvance = s.minAdvance;
+            job.maxIter = s.maxIter;
+            const float4 *p0 = set ? W.set[1].tv0 : W.set[0].tv0;
+            const float4 *p1 = set ? W.set[1].tv1 : W.set[0].tv1;
+            const float4 *p2 = set ? W.set[1].tv2 : W.set[0].tv2;
+            float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
+            job.T.v0 = xyz(a), job.T.v1 = xyz(b), job.T.v2 = xyz(c);
+            job.gid = __float_as_int(b.w) + (set ? W.set[1].triOffset : 0);
+            job.part = __float_as_int(c.w);
+            job.t = 0.0f;
+            job.lastSafeT = 0.0f;
+            job.it = 0;
+            job.phase = s.mode == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *wp.head = h + min((uint32_t)__popc(idle), avail);
+}
+
+// one distance evaluation + the pair's state transition.  `retired` = the pair is finished (with or
+// without a contribution in `cm`).
+template <bool COUNT>
+__device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &cm, bool &retired, Counters &ctr) {
+    const int ph = job.phase;
+    const QShared &s = wp.qs[job.owner];
+    float tc = ph == PH_ADV ? job.t : (ph == PH_BIS ? 0.5f * (job.lo + job.hi) : job.hi);
+    f3 center = ph == PH_OVL ? job.from : job.from + job.dir * tc;
+    f3 sp, tp;
+    if (COUNT) ctr.evals++;
+    float dist = segment_triangle_distance<true>(center, job.hh, job.T, sp, tp);
+    const float bestT = *(volatile const float *)&s.rT; // shared across the query's pairs
+    if (ph == PH_ADV) { // sweepCapsuleTriangle loop body, CollisionQuery.swift:1303-1356
+        if (dist <= job.radius + 1e-5f) {
+            float c0 = smax(0.0f, smin(job.lastSafeT, job.L)); // refineTOI prologue, :1371-1377
+            float c1 = smax(0.0f, smin(job.t, job.L));
+            job.lo = smin(c0, c1);
+            job.hi = smax(c0, c1);
+            if (job.hi - job.lo < 1e-5f) {
+                if (job.hi > bestT) retired = true;
+                else job.phase = PH_FIN;
+            } else {
+                job.k = 0;
+                if (job.lo > bestT) retired = true;
+                else job.phase = PH_BIS;
+            }
+        } else {
+            job.lastSafeT = job.t;
+            float advance = smax(dist - job.radius, job.minAdvance);
+            job.t += advance <= 0.0f ? job.minAdvance : advance;
+            job.it++;
+            // next trip: `for _ in 0..<maxIter { if t > maxDistance return nil ...`; prune: toi >= lastSafeT > bestT
+            if (job.it >= job.maxIter || job.t > job.L || job.lastSafeT > bestT) retired = true;
+        }
+    } else if (ph == PH_BIS) { // refineTOI bisection, :1379-1392 (threshold is radius, not radius+eps)
+        if (dist <= job.radius) job.hi = tc;
+        else job.lo = tc;
+        job.k++;
+        if (job.k == 10) {
+            if (job.hi > bestT) retired = true;
+            else job.phase = PH_FIN;
+        } else if (job.lo > bestT) {
+            retired = true;
+        }
+    } else if (ph == PH_FIN) { // contact at tHit = hi, :1325-1346; acceptance filters of :1087-1097
+        retired = true;
+        f3 triNormal = normalize(cross(job.T.v1 - job.T.v0, job.T.v2 - job.T.v0));
+        f3 n;
+        if (dist < 1e-6f) n = dot(triNormal, job.dir) > 0.0f ? -triNormal : triNormal;
+        else n = normalize(sp - tp);
+        f3 triN = triNormal;
+        if (dot(triN, n) < 0.0f) triN = -triN;
+        bool ok = true;
+        const int mode = s.mode;
+        if (mode == CQ_MODE_BLOCKING) {
+            f3 delta = mk3(s.delta[0], s.delta[1], s.delta[2]);
+            ok = !(dot(delta, n) >= 0.0f) && !(dot(delta, triN) >= 0.0f);
+        } else if (mode == CQ_MODE_GROUND) {
+            ok = !(triN.y < s.minNormalY);
+        }
+        if (ok) {
+            cm.kind = 1;
+            cm.key = tc;
+            cm.pos = tp;
+            cm.n = n;
+            cm.triN = triN;
+        }
+    } else { // PH_OVL: capsuleOverlapBVHAll leaf body, :1248-1271
+        retired = true;
+        if (dist < job.radius) {
+            f3 triNormal = normalize(cross(job.T.v1 - job.T.v0, job.T.v2 - job.T.v0));
+            cm.kind = 2;
+            cm.key = job.radius - dist; // depth
+            cm.n = dist < 1e-6f ? triNormal : normalize(sp - tp);
+        }
+    }
+}
+
+// serialized commit: one finishing lane at a time updates its owner's record; pending counters drop
+__device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const Commit &cm, bool retired, int lane) {
+    uint32_t fin = __ballot_sync(0xffffffffu, retired);
+    uint32_t todo = __ballot_sync(0xffffffffu, retired && cm.kind != 0);
+    while (todo) {
+        int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (lane == l) {
+            QShared &s = wp.qs[job.owner];
+            if (cm.kind == 1) { // accepted candidate with the smallest (toi, index) wins (:1084,1098 + tie rule)
+                float bestT = s.rT;
+                int bestTri = s.rTri;
+                bool better = cm.key < bestT;
+                bool tieWin = bestTri >= 0 && cm.key == bestT && job.gid < bestTri;
+                if (better || tieWin) {
+                    s.rT = cm.key;
+                    s.rTri = job.gid;
+                    s.rPart = job.part;
+                    store3s(s.rPos, cm.pos);
+                    store3s(s.rN, cm.n);
+                    store3s(s.rTriN, cm.triN);
+                }
+            } else { // two deepest overlaps, (depth desc, index asc)
+                float depth = cm.key;
+                float d0 = s.rT, d1 = s.rPos[0];
+                int t0 = s.rTri, t1 = s.rPart;
+                bool before0 = t0 < 0 || depth > d0 || (depth == d0 && job.gid < t0);
+                bool before1 = t1 < 0 || depth > d1 || (depth == d1 && job.gid < t1);
+                if (before0) {
+                    s.rPos[0] = d0, s.rPart = t0;
+                    store3s(s.rTriN, mk3(s.rN[0], s.rN[1], s.rN[2]));
+                    s.rT = depth, s.rTri = job.gid;
+                    store3s(s.rN, cm.n);
+                } else if (before1) {
+                    s.rPos[0] = depth, s.rPart = job.gid;
+                    store3s(s.rTriN, cm.n);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (retired) {
+        atomicSub(&wp.qs[job.owner].pending, 1);
+        job.phase = PH_NONE;
+    }
+    (void)fin;
+    __syncwarp();
+}
+
+} // namespace cq
