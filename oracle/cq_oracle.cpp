@@ -1593,6 +1593,27 @@ float orc_segment_triangle_distance(const float center[3], float half_height, co
     st3(tri_pt, r.tri);
     return r.dist;
 }
+void orc_segment_triangle_distance_batch(int32_t n, const float *centers, const float *hh, const float *tris,
+                                         float *dist, float *seg, float *tri) {
+    for (int i = 0; i < n; i++) {
+        SegTri r = segmentTriangleDistance(ld3(centers + 3 * i), hh[i], ld3(tris + 9 * i), ld3(tris + 9 * i + 3),
+                                           ld3(tris + 9 * i + 6), nullptr);
+        dist[i] = r.dist;
+        st3(seg + 3 * i, r.seg);
+        st3(tri + 3 * i, r.tri);
+    }
+}
+void orc_ray_triangle_batch(int32_t n, const float *origins, const float *dirs, const float *tris, float *tout,
+                            int32_t *hit) {
+    for (int i = 0; i < n; i++) {
+        float t = 0;
+        hit[i] = rayTriangle(ld3(origins + 3 * i), ld3(dirs + 3 * i), ld3(tris + 9 * i), ld3(tris + 9 * i + 3),
+                             ld3(tris + 9 * i + 6), 1e-6f, t)
+                     ? 1
+                     : 0;
+        tout[i] = t;
+    }
+}
 float orc_closest_point_on_triangle(const float p[3], const float a[3], const float b[3], const float c[3],
                                     float out_pt[3]) {
     DistSqPt r = closestPointOnTriangle(ld3(p), ld3(a), ld3(b), ld3(c));

@@ -111,6 +111,10 @@ void orc_move_and_slide(orc_world *w, orc_state *inout, int32_t n, const orc_par
 /* narrow-phase primitives exposed for known-answer tests */
 float orc_segment_triangle_distance(const float center[3], float half_height, const float v0[3],
                                     const float v1[3], const float v2[3], float seg_pt[3], float tri_pt[3]);
+void orc_segment_triangle_distance_batch(int32_t n, const float *centers, const float *hh, const float *tris,
+                                         float *dist, float *seg, float *tri);
+void orc_ray_triangle_batch(int32_t n, const float *origins, const float *dirs, const float *tris, float *tout,
+                            int32_t *hit);
 float orc_closest_point_on_triangle(const float p[3], const float a[3], const float b[3],
                                     const float c[3], float out_pt[3]);
 float orc_segment_segment_distance_sq(const float p1[3], const float q1[3], const float p2[3],

@@ -88,6 +88,8 @@ def lib():
                                          C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_segment_triangle_distance.restype = C.c_float
         L.orc_segment_triangle_distance.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 5
+        L.orc_segment_triangle_distance_batch.argtypes = [C.c_int32] + [C.c_void_p] * 6
+        L.orc_ray_triangle_batch.argtypes = [C.c_int32] + [C.c_void_p] * 5
         L.orc_closest_point_on_triangle.restype = C.c_float
         L.orc_closest_point_on_triangle.argtypes = [C.c_void_p] * 5
         L.orc_segment_segment_distance_sq.restype = C.c_float
@@ -247,3 +249,23 @@ def segment_segment_distance_sq(p1, q1, p2, q2):
     c1, c2 = np.zeros(3, np.float32), np.zeros(3, np.float32)
     d = lib().orc_segment_segment_distance_sq(_ptr(v[0]), _ptr(v[1]), _ptr(v[2]), _ptr(v[3]), _ptr(c1), _ptr(c2))
     return float(d), c1, c2
+
+
+def segment_triangle_distance_batch(centers, hh, tris):
+    centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+    n = len(centers)
+    hh = np.ascontiguousarray(np.broadcast_to(np.asarray(hh, np.float32), (n,)))
+    tris = np.ascontiguousarray(tris, np.float32).reshape(n, 9)
+    dist, seg, tri = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    lib().orc_segment_triangle_distance_batch(n, _ptr(centers), _ptr(hh), _ptr(tris), _ptr(dist), _ptr(seg), _ptr(tri))
+    return dist, seg, tri
+
+
+def ray_triangle_batch(origins, dirs, tris):
+    origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    n = len(origins)
+    dirs = np.ascontiguousarray(dirs, np.float32).reshape(n, 3)
+    tris = np.ascontiguousarray(tris, np.float32).reshape(n, 9)
+    t, hit = np.zeros(n, np.float32), np.zeros(n, np.int32)
+    lib().orc_ray_triangle_batch(n, _ptr(origins), _ptr(dirs), _ptr(tris), _ptr(t), _ptr(hit))
+    return t, hit

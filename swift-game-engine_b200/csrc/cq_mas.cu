@@ -608,15 +608,20 @@ __global__ void __launch_bounds__(MAS_THREADS) k_move_and_slide(WorldView W, cq_
     bool alive = true;
     __syncwarp();
     for (uint32_t trip = 0; trip < (1u << 24); trip++) { // (the bound is a watchdog; the loop exits through the vote)
-        // owner: a finished query (walk done, no pair pending) -> controller logic -> next query posted
-        if (alive && oq.travDone && *(volatile int *)&mine.pending == 0) {
-            QResult r;
-            pool_read_result(mine, r);
-            alive = mas_advance<COUNT>(c, r, mine, oq, stack, W, A, states, n, workCounter, ctr);
+        // Front end (owner role) runs only when the ring cannot feed every idle lane this trip: batching it
+        // makes the divergent controller logic / BVH walk run with many owners at once instead of 2-3.
+        const uint32_t idleNow = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
+        if (*wp.tail - *wp.head < (uint32_t)__popc(idleNow)) {
+            // owner: a finished query (walk done, no pair pending) -> controller logic -> next query posted
+            if (alive && oq.travDone && *(volatile int *)&mine.pending == 0) {
+                QResult r;
+                pool_read_result(mine, r);
+                alive = mas_advance<COUNT>(c, r, mine, oq, stack, W, A, states, n, workCounter, ctr);
+            }
+            // owner: walk the LBVH, push candidate pairs into the warp's ring
+            if (!oq.travDone) pool_traverse_push<COUNT>(W, wp, mine, oq, stack, lane, ctr);
+            __syncwarp();
         }
-        // owner: walk the LBVH, push candidate pairs into the warp's ring
-        if (!oq.travDone) pool_traverse_push<COUNT>(W, wp, mine, oq, stack, lane, ctr);
-        __syncwarp();
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
         pool_take_jobs(W, wp, job, lane);
         Commit cm;

@@ -103,67 +103,9 @@ __device__ __forceinline__ void traverse_box(const SetView &s, f3 qlo, f3 qhi, C
     }
 }
 
-// ---------------------------------------------------------------- capsule cast
-struct CastResult {
-    int tri; // global triangle index, -1 = nil
-    int part;
-    CastHit hit;
-};
-
 #define CQ_MODE_ALL 0
 #define CQ_MODE_BLOCKING 1
 #define CQ_MODE_GROUND 2
-
-// capsuleCastCombined / capsuleCastBVH — CollisionQuery.swift:980-1117.
-// Result = the accepted candidate with the smallest toi; exact toi ties -> smallest triangle index
-// (the reference keeps the first visited, which depends on its tree).
-template <bool COUNT>
-__device__ __forceinline__ void capsule_cast(const WorldView &W, f3 from, f3 delta, float radius, float hh,
-                                             uint32_t mask, int mode, float minNormalY, CastResult &res,
-                                             Counters &ctr) {
-    res.tri = -1;
-    res.part = -1;
-    float L = len(delta);
-    if (L < 1e-6f) return; // CollisionQuery.swift:988
-    f3 dir = delta / L;
-    const f3 up = {0.0f, 1.0f, 0.0f};
-    f3 a0 = from + up * hh, b0 = from - up * hh;
-    f3 a1 = a0 + delta, b1 = b0 + delta;
-    f3 ext = {radius, radius, radius};
-    f3 qlo = vmin(vmin(a0, b0), vmin(a1, b1)) - ext;
-    f3 qhi = vmax(vmax(a0, b0), vmax(a1, b1)) + ext;
-    float bestT = L;
-#pragma unroll 1
-    for (int si = 0; si < 2; si++) {
-        const SetView &S = W.set[si];
-        if (COUNT) ctr.queries++;
-        traverse_box<COUNT>(S, qlo, qhi, ctr, [&](int slot) {
-            uint32_t layer;
-            int triId, part;
-            Tri T = load_tri(S, slot, layer, triId, part);
-            if ((layer & mask) == 0u) return;
-            f3 tlo = vmin(T.v0, vmin(T.v1, T.v2)), thi = vmax(T.v0, vmax(T.v1, T.v2));
-            if (box_disjoint(tlo, thi, qlo, qhi)) return; // CollisionQuery.swift:1060-1065
-            if (COUNT) ctr.cands++;
-            CastHit hit;
-            if (!sweep_capsule_triangle<COUNT>(from, dir, L, radius, hh, T, bestT, hit, ctr.evals)) return;
-            int gid = triId + S.triOffset;
-            bool better = hit.toi < bestT;
-            bool tieWin = res.tri >= 0 && hit.toi == bestT && gid < res.tri;
-            if (!better && !tieWin) return;
-            if (mode == CQ_MODE_BLOCKING) { // CollisionQuery.swift:1087-1094
-                if (dot(delta, hit.normal) >= 0.0f) return;
-                if (dot(delta, hit.triNormal) >= 0.0f) return;
-            } else if (mode == CQ_MODE_GROUND) { // :1095
-                if (hit.triNormal.y < minNormalY) return;
-            }
-            bestT = hit.toi;
-            res.tri = gid;
-            res.part = part;
-            res.hit = hit;
-        });
-    }
-}
 
 // ---------------------------------------------------------------- capsule overlap
 struct OverlapRec {
