@@ -19,6 +19,9 @@
 namespace cq {
 
 #define MAS_THREADS 128
+#ifndef MAS_MIN_BLOCKS
+#define MAS_MIN_BLOCKS 4
+#endif
 #define MAS_WARPS (MAS_THREADS / 32)
 #define MAS_SMEM_BYTES \
     (sizeof(CharCtx) * MAS_THREADS + sizeof(QShared) * MAS_THREADS + sizeof(uint32_t) * (CQ_QCAP + 2) * MAS_WARPS)
@@ -575,7 +578,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(MAS_THREADS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states, int n,
+__global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states, int n,
                                                                 MasArgs A, int *workCounter, unsigned long long *gctr) {
     extern __shared__ __align__(16) unsigned char masSmem[]; // MAS_SMEM_BYTES, dynamic (> 48 KB)
     CharCtx *ctxs = reinterpret_cast<CharCtx *>(masSmem);
