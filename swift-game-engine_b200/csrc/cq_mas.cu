@@ -591,59 +591,17 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     wp.head = wp.ring + CQ_QCAP;
     wp.tail = wp.ring + CQ_QCAP + 1;
     CharCtx &c = ctxs[threadIdx.x];
-    QShared &mine = wp.qs[lane];
     c.charIndex = -1;
     c.wait = W_NONE;
     c.flags = 0;
-    mine.pending = 0;
-    mine.rTri = -1;
-    if (lane == 0) {
-        *wp.head = 0;
-        *wp.tail = 0;
-    }
     Counters ctr = {0, 0, 0, 0};
-    OwnerQ oq;
-    oq.travDone = true;
-    oq.sp = 0, oq.set = 1, oq.leafPos = oq.leafEnd = 0, oq.mask = 0;
-    Job job;
-    job.phase = PH_NONE;
     int stack[CQ_STACK];
-    bool alive = true;
-    __syncwarp();
-    for (uint32_t trip = 0; trip < (1u << 24); trip++) { // (the bound is a watchdog; the loop exits through the vote)
-        // Front end (owner role) runs only when the ring cannot feed every idle lane this trip: batching it
-        // makes the divergent controller logic / BVH walk run with many owners at once instead of 2-3.
-        const uint32_t idleNow = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
-        if (*wp.tail - *wp.head < (uint32_t)__popc(idleNow)) {
-            // owner: a finished query (walk done, no pair pending) -> controller logic -> next query posted
-            if (alive && oq.travDone && *(volatile int *)&mine.pending == 0) {
-                QResult r;
-                pool_read_result(mine, r);
-                alive = mas_advance<COUNT>(c, r, mine, oq, stack, W, A, states, n, workCounter, ctr);
-            }
-            // owner: walk the LBVH, push candidate pairs into the warp's ring
-            if (!oq.travDone) pool_traverse_push<COUNT>(W, wp, mine, oq, stack, lane, ctr);
-            __syncwarp();
-        }
-        // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
-        pool_take_jobs(W, wp, job, lane);
-        Commit cm;
-        cm.kind = 0;
-        bool retired = false;
-        if (job.phase != PH_NONE) pool_eval<COUNT>(job, wp, cm, retired, ctr);
-        pool_commit(wp, job, cm, retired, lane);
-        if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE)) break;
-    }
-    if (COUNT) {
-        uint32_t v[4] = {ctr.nodes, ctr.cands, ctr.evals, ctr.queries};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            unsigned long long s = v[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if ((threadIdx.x & 31) == 0 && s) atomicAdd(gctr + k, s);
-        }
-    }
+    pool_run<COUNT>(W, wp, lane, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+        QResult r;
+        pool_read_result(mine, r);
+        return mas_advance<COUNT>(c, r, mine, oq, stk, W, A, states, n, workCounter, ct);
+    });
+    pool_flush_counters(ctr, gctr, COUNT);
 }
 
 int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p, float dt,

@@ -375,4 +375,58 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
     __syncwarp();
 }
 
+// The warp's main loop.  `advance(mine, oq, stack, ctr)` is the owner-role callback: it is invoked when the
+// lane's current query is complete (walk finished, no pair pending), consumes the result from `mine`,
+// runs the unit's serial logic and posts the next query (pool_post_*) — or returns false when the lane has
+// no more work units.
+template <bool COUNT, class Advance>
+__device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int *stack, Counters &ctr,
+                                         Advance advance) {
+    QShared &mine = wp.qs[lane];
+    mine.pending = 0;
+    mine.rTri = -1;
+    if (lane == 0) {
+        *wp.head = 0;
+        *wp.tail = 0;
+    }
+    OwnerQ oq;
+    oq.travDone = true;
+    oq.sp = 0, oq.set = 1, oq.leafPos = oq.leafEnd = 0, oq.mask = 0;
+    oq.qlo = oq.qhi = mk3(0, 0, 0);
+    Job job;
+    job.phase = PH_NONE;
+    bool alive = true;
+    __syncwarp();
+    for (uint32_t trip = 0; trip < (1u << 26); trip++) { // (the bound is a watchdog; the loop exits through the vote)
+        // Front end (owner role) runs only when the ring cannot feed every idle lane this trip: batching it
+        // makes the divergent unit logic / BVH walk run with many owners at once instead of 2-3.
+        const uint32_t idleNow = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
+        if (*wp.tail - *wp.head < (uint32_t)__popc(idleNow)) {
+            if (alive && oq.travDone && *(volatile int *)&mine.pending == 0) alive = advance(mine, oq, stack, ctr);
+            if (!oq.travDone) pool_traverse_push<COUNT>(W, wp, mine, oq, stack, lane, ctr);
+            __syncwarp();
+        }
+        // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
+        pool_take_jobs(W, wp, job, lane);
+        Commit cm;
+        cm.kind = 0;
+        bool retired = false;
+        if (job.phase != PH_NONE) pool_eval<COUNT>(job, wp, cm, retired, ctr);
+        pool_commit(wp, job, cm, retired, lane);
+        if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE)) break;
+    }
+}
+
+__device__ __forceinline__ void pool_flush_counters(const Counters &c, unsigned long long *g, bool count) {
+    if (!count) return;
+    uint32_t v[4] = {c.nodes, c.cands, c.evals, c.queries};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned long long s = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(g + k, s);
+    }
+}
+
 } // namespace cq

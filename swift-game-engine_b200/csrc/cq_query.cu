@@ -1,7 +1,7 @@
 // cq_query.cu — batched query kernels: raycast, capsule cast (3 modes), capsule overlap (deepest),
 // capsule overlap-all (8 deepest).  One thread per query; the BVH walk and the narrow phase live in
 // cq_world.cuh / cq_math.cuh.  Replaces the per-call CPU entry points of CollisionQuery.swift:85-159.
-#include "cq_engine.cuh"
+#include "cq_pool.cuh"
 #include "cq_internal.h"
 
 namespace cq {
@@ -57,57 +57,54 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 }
 
 // ---------------------------------------------------------------- capsule cast (CollisionQuery.swift:787-828, 980-1117)
-// Persistent lanes over the flat L/T/E engine (cq_engine.cuh): a lane that finishes its sweep writes the
-// hit and immediately starts its next query, so warps stay full whatever the per-query candidate and
-// iteration counts are.
+// Warp-cooperative pool engine (cq_pool.cuh): every lane owns one sweep at a time (fetched dynamically),
+// walks the LBVH for it and pushes its candidate triangles into the warp's ring; all 32 lanes execute
+// the (sweep, triangle) pairs, one distance evaluation per trip.
+#define CAST_WARPS (Q_THREADS / 32)
 template <bool COUNT>
-__global__ void __launch_bounds__(Q_THREADS) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
-                                                            int mode, cq_cast_hit *__restrict__ out, int *workCounter,
-                                                            unsigned long long *gctr) {
-    __shared__ float candMem[CQ_LIST * 4 * Q_THREADS];
-    const CandList cl = {candMem + threadIdx.x, Q_THREADS};
-    int cur = -1;
+__global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
+                                                               int mode, cq_cast_hit *__restrict__ out, int *workCounter,
+                                                               unsigned long long *gctr) {
+    __shared__ QShared qsAll[Q_THREADS];
+    __shared__ uint32_t rings[(CQ_QCAP + 2) * CAST_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpPool wp;
+    wp.qs = qsAll + warp * 32;
+    wp.ring = rings + warp * (CQ_QCAP + 2);
+    wp.head = wp.ring + CQ_QCAP;
+    wp.tail = wp.ring + CQ_QCAP + 1;
     Counters ctr = {0, 0, 0, 0};
-    LaneQ q;
-    q_idle(q);
     int stack[CQ_STACK];
-    bool alive = true;
-    while (true) {
-        while (q.phase == PH_NONE && alive) { // front end
-            if (!q.done) {
-                q_acquire<COUNT>(W, q, stack, cl, ctr);
-                continue;
-            }
-            if (cur >= 0) { // write the finished hit
-                cq_cast_hit h;
-                if (q.bestTri >= 0) {
-                    h.toi = q.bestT;
-                    store3(h.position, q.bestPos);
-                    store3(h.normal, q.bestN);
-                    store3(h.triangle_normal, q.bestTriN);
-                    h.triangle_index = q.bestTri;
-                } else {
-                    h.toi = 0.0f;
-                    store3(h.position, mk3(0, 0, 0));
-                    store3(h.normal, mk3(0, 0, 0));
-                    store3(h.triangle_normal, mk3(0, 0, 0));
-                    h.triangle_index = -1;
-                }
-                out[cur] = h;
-            }
-            cur = atomicAdd(workCounter, 1); // dynamic fetch of the next query
-            if (cur < n) {
-                cq_capsule_cast c = qs[cur];
-                q_begin_cast<COUNT>(W, q, stack, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
-                                    c.min_normal_y, ctr);
+    int cur = -1;
+    pool_run<COUNT>(W, wp, lane, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+        if (cur >= 0) { // write the finished hit
+            cq_cast_hit h;
+            if (mine.rTri >= 0) {
+                h.toi = mine.rT;
+                store3(h.position, mk3(mine.rPos[0], mine.rPos[1], mine.rPos[2]));
+                store3(h.normal, mk3(mine.rN[0], mine.rN[1], mine.rN[2]));
+                store3(h.triangle_normal, mk3(mine.rTriN[0], mine.rTriN[1], mine.rTriN[2]));
+                h.triangle_index = mine.rTri;
             } else {
-                cur = -1;
-                alive = false;
+                h.toi = 0.0f;
+                store3(h.position, mk3(0, 0, 0));
+                store3(h.normal, mk3(0, 0, 0));
+                store3(h.triangle_normal, mk3(0, 0, 0));
+                h.triangle_index = -1;
             }
+            out[cur] = h;
         }
-        if (q.phase != PH_NONE) q_eval_step<COUNT>(q, cl, ctr); // back end
-        if (__all_sync(0xffffffffu, !alive)) break;
-    }
+        cur = atomicAdd(workCounter, 1); // dynamic fetch of the next sweep
+        if (cur >= n) {
+            cur = -1;
+            oq.travDone = true;
+            return false;
+        }
+        cq_capsule_cast c = qs[cur];
+        pool_post_cast<COUNT>(W, mine, oq, stk, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
+                              c.min_normal_y, ct);
+        return true;
+    });
     flush_counters<COUNT>(ctr, gctr);
 }
 

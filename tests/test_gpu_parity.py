@@ -242,3 +242,37 @@ def test_counters_match_reference_stats(world, scenes, orc):
     assert c["candidates"] == st.candidates
     assert 0 < c["distance_evals"] <= st.distance_evals  # exact-safe pruning only removes work
     assert c["nodes_visited"] > 0 and c["kernel_launches"] >= 1
+
+
+def test_terrain_lbvh_and_blocking_sweeps(cq, orc, scenes):
+    """Config C4 scaled down (300x300 cells = 180,000 triangles): device LBVH build (Morton + radix sort +
+    Karras + fit) at a size where every radix pass spans many tiles, sweeps checked against the oracle."""
+    parts, half = scenes.terrain_scene(cells=300, cell=2.0)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    assert g.info()["n_static_triangles"] == o.counts(0)["triangles"] == 180000
+    gs, os_ = g.read_soup(0), o.read_soup(0)
+    assert np.array_equal(gs["positions"], os_["positions"]) and np.array_equal(gs["aabbs"], os_["aabbs"])
+    for r, hh in ((0.4, 0.5), (1.5, 1.0)):
+        q = scenes.gen_c4_casts(20000, half, seed=41, radius=r, half_height=hh)
+        got, ref = g.capsuleCastBlocking(q), o.capsule_cast(q, 1, orc.ORDER_CANONICAL)
+        assert got.tobytes() == ref.tobytes()
+        assert (got["triangle_index"] >= 0).mean() > 0.2
+    rays = scenes.gen_rays(20000, [-half, -10, -half], [half, 30, half], seed=42, expand=0.0)
+    gr, rr = g.raycast(rays), o.raycast(rays, orc.ORDER_REFERENCE)
+    assert (gr["triangle_index"] != rr["triangle_index"]).mean() < 0.002
+    both = (gr["triangle_index"] >= 0) & (rr["triangle_index"] >= 0)
+    assert (gr["distance"][both] <= rr["distance"][both]).all()
+    # characters walking on the terrain, human scale
+    x = np.random.default_rng(3).uniform(-half + 10, half - 10, (4096, 2))
+    y = scenes.terrain_height(x[:, 0], x[:, 1]) + 0.9 + 0.3
+    pos = np.stack([x[:, 0], y, x[:, 1]], axis=1).astype(np.float32)
+    vel = np.random.default_rng(4).uniform(-4, 4, (4096, 3)).astype(np.float32) * np.float32([1, 0, 1])
+    sg, so = cq.init_states(pos, vel), orc.init_states(pos, vel)
+    kw = dict(radius=0.4, half_height=0.5, skin_width=0.08)
+    for _ in range(4):
+        g.move_and_slide(sg, cq.default_params(**kw))
+        o.move_and_slide(so, orc.default_params(**kw), order=orc.ORDER_CANONICAL)
+    assert sg.tobytes() == so.tobytes()
+    assert sg["grounded"].mean() > 0.8
+    g.close()
+    o.close()
