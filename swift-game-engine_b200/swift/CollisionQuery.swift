@@ -1,0 +1,168 @@
+// CollisionQuery.swift — Swift binding of libcq.so (SOURCE ONLY: no Swift toolchain exists in the build
+// environment, so this file has never been compiled; see INTEGRATION.md).
+//
+// Drop-in for the reference's `final class CollisionQuery` (Game/CollisionQuery.swift:54-160): same method
+// names and signatures, implemented over the C ABI of include/cq.h through a module map
+// (`module CQ { header "cq.h" link "cq" }`).  The engine's `World` is flattened into `cq_mesh_part`s by
+// `makeParts(world:activeEntityIDs:)` exactly as `TriangleMeshSet.rebuild` walks it (:331-417).
+import CQ
+import simd
+
+public final class CollisionQuery {
+    private var handle: OpaquePointer?
+
+    public init(world: World, activeEntityIDs: Set<UInt32>? = nil) {
+        var keepAlive: [Any] = []
+        var parts = CollisionQuery.makeParts(world: world, activeEntityIDs: activeEntityIDs, keepAlive: &keepAlive)
+        var h: OpaquePointer?
+        _ = cq_world_create(&parts, Int32(parts.count), &h)   // on failure `handle` stays nil: every query answers nil
+        handle = h
+    }
+
+    deinit { cq_world_destroy(handle) }
+
+    public func updateStaticTransforms(world: World, entities: [Entity], activeEntityIDs: Set<UInt32>? = nil) {
+        update(world: world, entities: entities, activeEntityIDs: activeEntityIDs)
+    }
+
+    public func updateDynamicTransforms(world: World, entities: [Entity], activeEntityIDs: Set<UInt32>? = nil) {
+        update(world: world, entities: entities, activeEntityIDs: activeEntityIDs)
+    }
+
+    public func raycast(origin: SIMD3<Float>, direction: SIMD3<Float>, maxDistance: Float,
+                        mask: UInt32 = CollisionLayer.all) -> RaycastHit? {
+        var r = cq_ray(origin: (origin.x, origin.y, origin.z), direction: (direction.x, direction.y, direction.z),
+                       max_distance: maxDistance, mask: mask)
+        var h = cq_ray_hit()
+        guard cq_raycast_batch(handle, &r, 1, &h) == CQ_OK, h.triangle_index >= 0 else { return nil }
+        return RaycastHit(distance: h.distance, position: v3(h.position), normal: v3(h.normal),
+                          triangleIndex: Int(h.triangle_index), material: material(h.triangle_index))
+    }
+
+    public func capsuleCast(from: SIMD3<Float>, delta: SIMD3<Float>, radius: Float, halfHeight: Float,
+                            mask: UInt32 = CollisionLayer.all) -> CapsuleCastHit? {
+        cast(from, delta, radius, halfHeight, mask, CQ_CAST_ALL, 0)
+    }
+
+    public func capsuleCastBlocking(from: SIMD3<Float>, delta: SIMD3<Float>, radius: Float, halfHeight: Float,
+                                    mask: UInt32 = CollisionLayer.all) -> CapsuleCastHit? {
+        cast(from, delta, radius, halfHeight, mask, CQ_CAST_BLOCKING, 0)
+    }
+
+    public func capsuleCastGround(from: SIMD3<Float>, delta: SIMD3<Float>, radius: Float, halfHeight: Float,
+                                  minNormalY: Float, mask: UInt32 = CollisionLayer.all) -> CapsuleCastHit? {
+        cast(from, delta, radius, halfHeight, mask, CQ_CAST_GROUND, minNormalY)
+    }
+
+    public func capsuleOverlap(from: SIMD3<Float>, radius: Float, halfHeight: Float,
+                               mask: UInt32 = CollisionLayer.all) -> CapsuleOverlapHit? {
+        var c = cq_capsule(from: (from.x, from.y, from.z), radius: radius, half_height: halfHeight, mask: mask)
+        var h = cq_overlap_hit()
+        guard cq_capsule_overlap_batch(handle, &c, 1, &h) == CQ_OK, h.triangle_index >= 0 else { return nil }
+        return overlapHit(h)
+    }
+
+    public func capsuleOverlapAll(from: SIMD3<Float>, radius: Float, halfHeight: Float, maxHits: Int = 8,
+                                  mask: UInt32 = CollisionLayer.all) -> [CapsuleOverlapHit] {
+        let cap = min(max(1, maxHits), Int(CQ_MAX_OVERLAP_HITS))
+        var c = cq_capsule(from: (from.x, from.y, from.z), radius: radius, half_height: halfHeight, mask: mask)
+        var hits = [cq_overlap_hit](repeating: cq_overlap_hit(), count: cap)
+        var count: Int32 = 0
+        guard cq_capsule_overlap_all_batch(handle, &c, 1, Int32(cap), &hits, &count, nil) == CQ_OK else { return [] }
+        return hits.prefix(Int(count)).map(overlapHit)
+    }
+
+    /// Batched replacement of KinematicMoveStopSystem.fixedUpdate's per-entity loop (Systems.swift:1842-1901).
+    public func moveAndSlide(states: inout [cq_character_state], params: cq_controller_params, dt: Float,
+                             gravity: SIMD3<Float> = SIMD3<Float>(0, -98, 0), applyGravity: Bool = true) -> Bool {
+        var p = params
+        var g = (gravity.x, gravity.y, gravity.z)
+        return withUnsafePointer(to: &g) { gp in
+            gp.withMemoryRebound(to: Float.self, capacity: 3) {
+                cq_move_and_slide_batch(handle, &states, Int32(states.count), &p, dt, $0,
+                                        applyGravity ? UInt32(CQ_MAS_APPLY_GRAVITY) : 0) == CQ_OK
+            }
+        }
+    }
+
+    // MARK: - private
+
+    private func v3(_ t: (Float, Float, Float)) -> SIMD3<Float> { SIMD3<Float>(t.0, t.1, t.2) }
+
+    private func material(_ tri: Int32) -> SurfaceMaterial {
+        var m = cq_material()
+        cq_world_triangle_material(handle, tri, &m)
+        return SurfaceMaterial(muS: m.mu_s, muK: m.mu_k, flattenGround: m.flatten_ground != 0)
+    }
+
+    private func overlapHit(_ h: cq_overlap_hit) -> CapsuleOverlapHit {
+        CapsuleOverlapHit(depth: h.depth, position: v3(h.position), normal: v3(h.normal),
+                          triangleNormal: v3(h.triangle_normal), triangleIndex: Int(h.triangle_index),
+                          material: material(h.triangle_index))
+    }
+
+    private func cast(_ from: SIMD3<Float>, _ delta: SIMD3<Float>, _ radius: Float, _ halfHeight: Float, _ mask: UInt32,
+                      _ mode: Int32, _ minNormalY: Float) -> CapsuleCastHit? {
+        var q = cq_capsule_cast(from: (from.x, from.y, from.z), delta: (delta.x, delta.y, delta.z), radius: radius,
+                                half_height: halfHeight, mask: mask, min_normal_y: minNormalY)
+        var h = cq_cast_hit()
+        guard cq_capsule_cast_batch(handle, &q, 1, mode, &h) == CQ_OK, h.triangle_index >= 0 else { return nil }
+        return CapsuleCastHit(toi: h.toi, position: v3(h.position), normal: v3(h.normal),
+                              triangleNormal: v3(h.triangle_normal), triangleIndex: Int(h.triangle_index),
+                              material: material(h.triangle_index))
+    }
+
+    private func update(world: World, entities: [Entity], activeEntityIDs: Set<UInt32>?) {
+        let tStore = world.store(TransformComponent.self)
+        let filtered = entities.filter { activeEntityIDs?.contains($0.id) ?? true }
+        var ids: [UInt32] = []
+        var models: [Float] = []
+        for e in filtered {
+            guard let t = tStore[e] else { continue }
+            ids.append(e.id)
+            let m = t.modelMatrix
+            for c in [m.columns.0, m.columns.1, m.columns.2, m.columns.3] { models += [c.x, c.y, c.z, c.w] }
+        }
+        _ = cq_world_update_transforms(handle, ids, models, Int32(ids.count))
+    }
+
+    /// Entities with Transform + StaticMesh (collides), ascending id (the reference iterates a Dictionary, i.e. in
+    /// per-process random order — World.swift:99-118; the library fixes the order so triangle numbering is stable).
+    private static func makeParts(world: World, activeEntityIDs: Set<UInt32>?, keepAlive: inout [Any]) -> [cq_mesh_part] {
+        let tStore = world.store(TransformComponent.self)
+        let mStore = world.store(StaticMeshComponent.self)
+        let pStore = world.store(PhysicsBodyComponent.self)
+        var parts: [cq_mesh_part] = []
+        let entities = world.query(TransformComponent.self, StaticMeshComponent.self).sorted { $0.id < $1.id }
+        for e in entities {
+            if let active = activeEntityIDs, !active.contains(e.id) { continue }
+            guard let t = tStore[e], let m = mStore[e], m.collides else { continue }
+            let mesh = m.collisionMesh ?? m.mesh
+            let pos = UnsafeMutablePointer<Float>.allocate(capacity: mesh.streams.positions.count * 3)
+            for (i, p) in mesh.streams.positions.enumerated() { pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z }
+            let idx32: [UInt32] = mesh.indices16?.map { UInt32($0) } ?? mesh.indices32 ?? []
+            let idx = UnsafeMutablePointer<UInt32>.allocate(capacity: max(idx32.count, 1))
+            idx.initialize(from: idx32, count: idx32.count)
+            keepAlive.append(pos); keepAlive.append(idx)
+            var part = cq_mesh_part()
+            part.positions_xyz = UnsafePointer(pos)
+            part.indices = UnsafePointer(idx)
+            part.n_verts = Int32(mesh.streams.positions.count)
+            part.n_indices = Int32(idx32.count)
+            let mm = t.modelMatrix
+            withUnsafeMutableBytes(of: &part.model) { raw in
+                let f = raw.bindMemory(to: Float.self)
+                var k = 0
+                for c in [mm.columns.0, mm.columns.1, mm.columns.2, mm.columns.3] { f[k] = c.x; f[k + 1] = c.y; f[k + 2] = c.z; f[k + 3] = c.w; k += 4 }
+            }
+            part.layer = m.collisionLayer
+            part.mu_s = m.material.muS
+            part.mu_k = m.material.muK
+            part.flatten_ground = m.material.flattenGround ? 1 : 0
+            part.is_dynamic = (pStore[e].map { $0.bodyType != .static } ?? false) ? 1 : 0
+            part.entity_id = e.id
+            parts.append(part)
+        }
+        return parts
+    }
+}

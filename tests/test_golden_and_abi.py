@@ -174,3 +174,16 @@ def test_sharded_characters_equal_single_rank_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_header_is_plain_c_and_cpp_mirror_compiles(tmp_path):
+    """include/cq.h must be a C header (no C++/torch types in the signatures); the C++ host mirror of the
+    reference class must compile against it."""
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "cq.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "use.cpp"
+    src.write_text('#include "%s"\nint main(){ cqhost::Float3 a{0,0,0}; (void)a; return sizeof(cq_character_state)==168 ? 0 : 1; }\n'
+                   % os.path.join(ROOT, "swift-game-engine_b200", "cpp", "CollisionQuery.hpp"))
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
