@@ -148,7 +148,69 @@ CQ_HD float segment_segment_dist2(f3 p1, f3 q1, f3 p2, f3 q2, f3 &c1, f3 &c2) {
     return len2(c1 - c2);
 }
 
-// segmentTriangleIntersect — CollisionQuery.swift:1440-1462
+// ---- vertical-axis specialisations ------------------------------------------------------------------
+// The capsule axis is world +Y, so the segment handed to the two functions below is a = c + (0,hh,0),
+// b = c - (0,hh,0) and d1 = b - a = (0, dy, 0) with dy = b.y - a.y (b.x - a.x and b.z - a.z are exactly
+// zero: both are c.x -+ 0*hh).  Multiplying by an exact zero and adding the resulting (signed) zero never
+// changes a non-zero value, so the reference's general expressions reduce EXACTLY (same roundings) to the
+// shorter ones used here; only the sign of a zero result can differ, which no comparison and no non-zero
+// output depends on.  tests/test_device_math_on_host.py checks these against the oracle's literal,
+// unspecialised restatement on millions of inputs.
+
+// segmentSegmentDistanceSq(p1: a, q1: b, p2, q2) — CollisionQuery.swift:1519-1569, d1 = (0, dy, 0), aa = dy*dy
+CQ_HD float vseg_segment_dist2(f3 p1, float dy, float aa, f3 p2, f3 q2, f3 &c1, f3 &c2) {
+    f3 d2 = q2 - p2, r = p1 - p2;
+    float e = dot(d2, d2), f = dot(d2, r);
+    const float eps = 1e-6f;
+    float c = dy * r.y; // dot(d1, r)
+    if (aa <= eps || e <= eps) { // degenerate segment(s): rare, kept as the reference's branches (:1534-1547)
+        if (aa <= eps && e <= eps) {
+            c1 = p1;
+            c2 = p2;
+            return len2(p1 - p2);
+        }
+        if (aa <= eps) {
+            float t = clamp01(f / e);
+            c1 = p1;
+            c2 = p2 + d2 * t;
+            return len2(p1 - c2);
+        }
+        float s = clamp01(-c / aa);
+        c1 = mk3(p1.x, p1.y + dy * s, p1.z);
+        c2 = p2;
+        return len2(c1 - p2);
+    }
+    float b = dy * d2.y; // dot(d1, d2)
+    float denom = aa * e - b * b;
+    float s0 = (denom != 0.0f) ? clamp01((b * f - c * e) / denom) : 0.0f;
+    float tNom = b * s0 + f;
+    bool lo = tNom < 0.0f, hi = !lo && tNom > e;
+    float num = lo ? -c : (hi ? (b - c) : tNom); // one division: -c/a | (b-c)/a | tNom/e
+    float den = (lo || hi) ? aa : e;
+    float q = num / den;
+    float s = (lo || hi) ? clamp01(q) : s0;
+    float t = lo ? 0.0f : (hi ? 1.0f : q);
+    c1 = mk3(p1.x, p1.y + dy * s, p1.z); // p1 + d1*s
+    c2 = p2 + d2 * t;
+    return len2(c1 - c2);
+}
+
+// segmentTriangleIntersect(a, b, …) — CollisionQuery.swift:1440-1462, dir = (0, dy, 0)
+CQ_HD bool vseg_triangle_intersect(f3 a, float dy, const Tri &T, f3 &out) {
+    f3 e1 = T.v1 - T.v0, e2 = T.v2 - T.v0;
+    float pvx = dy * e2.z, pvz = -(dy * e2.x); // cross(dir, e2) = (dy*e2.z, 0, -dy*e2.x)
+    float det = e1.x * pvx + e1.z * pvz;       // dot(e1, pvec)
+    float invDet = 1.0f / det;
+    f3 tvec = a - T.v0;
+    float u = (tvec.x * pvx + tvec.z * pvz) * invDet;
+    f3 qvec = cross(tvec, e1);
+    float v = (dy * qvec.y) * invDet; // dot(dir, qvec)
+    float t = dot(e2, qvec) * invDet;
+    out = mk3(a.x, a.y + dy * t, a.z); // a + dir*t
+    return !(fabsf(det) < 1e-6f) && !(u < 0.0f || u > 1.0f) && !(v < 0.0f || (u + v) > 1.0f) && !(t < 0.0f || t > 1.0f);
+}
+
+// general-direction versions (kept for reference / tests of the specialisations)
 CQ_HD bool segment_triangle_intersect(f3 a, f3 b, const Tri &T, f3 &out) {
     f3 dir = b - a;
     f3 e1 = T.v1 - T.v0, e2 = T.v2 - T.v0;
@@ -175,8 +237,10 @@ CQ_HD float segment_triangle_distance(f3 center, float hh, const Tri &T, f3 &seg
     const f3 up = {0.0f, 1.0f, 0.0f};
     const f3 a = center + up * hh;
     const f3 b = center - up * hh;
+    const float dy = b.y - a.y; // (b - a) = (0, dy, 0)
+    const float aa = dy * dy;   // dot(b - a, b - a)
     f3 hit;
-    bool pierced = segment_triangle_intersect(a, b, T, hit);
+    bool pierced = vseg_triangle_intersect(a, dy, T, hit);
     float best = FLT_MAX;
     f3 bs = a, bt = T.v0;
     f3 p = a;
@@ -195,7 +259,7 @@ CQ_HD float segment_triangle_distance(f3 center, float hh, const Tri &T, f3 &seg
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
         f3 s, t;
-        float d = segment_segment_dist2(a, b, e0, e1, s, t);
+        float d = vseg_segment_dist2(a, dy, aa, e0, e1, s, t);
         if (d < best) {
             best = d;
             bs = s;
