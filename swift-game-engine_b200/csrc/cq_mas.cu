@@ -20,7 +20,7 @@ namespace cq {
 
 #define MAS_THREADS 128
 #ifndef MAS_MIN_BLOCKS
-#define MAS_MIN_BLOCKS 4
+#define MAS_MIN_BLOCKS 5
 #endif
 #define MAS_WARPS (MAS_THREADS / 32)
 #define MAS_SMEM_BYTES \
@@ -40,8 +40,10 @@ enum {
     F_CAN_SNAP = 64, F_NEAR_GROUND = 128, F_PROBE_HIT = 256, F_DID_RESOLVE = 512
 };
 
-struct CharCtx { // per-lane controller working set, shared memory
-    cq_character_state st;
+struct CharCtx { // per-lane controller working set, shared memory (the 168-byte record itself stays in HBM/L2:
+                 // it is touched only by the owner's logic, a few times per step, and keeping it out of shared
+                 // memory lets 5-6 CTAs share an SM instead of 4)
+    cq_character_state *st;
     float pos[3], rem[3], lastN[3];
     float slideLen;
     float cNormal[3], cTriNormal[3];
@@ -134,7 +136,7 @@ __device__ __forceinline__ bool slide_resolve(CharCtx &c, const cq_controller_pa
             if (dot(cn, slideNormal) < 0.0f) cn = -cn;
             slideNormal = cn;
         } else {
-            f3 cached = ld3(c.st.side_contact_normal);
+            f3 cached = ld3(c.st->side_contact_normal);
             float cl = len2(cached);
             if (cl > 1e-6f) {
                 f3 cn = cached / sqrtf(cl);
@@ -192,10 +194,10 @@ __device__ __forceinline__ bool slide_resolve(CharCtx &c, const cq_controller_pa
                 shouldBreak = true;
             } else {
                 remaining = leftover;
-                d3 vel = ldv(c.st);
+                d3 vel = ldv(*c.st);
                 d3 sn = to_d3(slideNormal);
                 double vInto = dot(vel, sn); // SYS:1367-1372
-                if (vInto < 0.0) stv(c.st, vel - sn * vInto);
+                if (vInto < 0.0) stv(*c.st, vel - sn * vInto);
                 shouldBreak = false;
             }
         }
@@ -209,7 +211,7 @@ __device__ __forceinline__ bool slide_resolve(CharCtx &c, const cq_controller_pa
 __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const MasArgs &A, cq_character_state *out,
                                            bool count, uint32_t evalsNow) {
     const cq_controller_params &P = A.p;
-    cq_character_state &S = c.st;
+    cq_character_state &S = *c.st;
     const f3 gravity = {A.gx, A.gy, A.gz};
     const bool wasGroundedNear = c.flags & F_WAS_GN;
     const bool grounded = c.flags & F_GROUNDED;
@@ -303,11 +305,7 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
         uint32_t e = evalsNow - (uint32_t)c._pad;
         S._pad[1] = e & 255u, S._pad[2] = (e >> 8) & 255u, S._pad[3] = (e >> 16) & 255u, S._pad[4] = (e >> 24) & 255u;
     }
-    // 168-byte record out: 21 x 8-byte stores
-    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&S);
-    unsigned long long *dst = reinterpret_cast<unsigned long long *>(out);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(cq_character_state) / 8); k++) dst[k] = src[k];
+    (void)out; // the record was updated in place
 }
 
 // Stage L of the move-and-slide kernel: consume the finished query, run the controller logic up to the
@@ -338,9 +336,9 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
                 maxDepth = smax(maxDepth, hd);
                 f3 nn = hn;
                 f3 cached;
-                if (manifold_normal_for(c.st, ht, cached)) nn = cached; // SYS:770-776
+                if (manifold_normal_for(*c.st, ht, cached)) nn = cached; // SYS:770-776
                 frameNormal = frameNormal + nn * hd;
-                cache_record(c.st, ht, nn, hn.y < P.min_ground_dot);
+                cache_record(*c.st, ht, nn, hn.y < P.min_ground_dot);
             }
             float fl = len(frameNormal);
             f3 depenNormal = fl > 1e-6f ? frameNormal / fl : frameNormal;
@@ -349,10 +347,10 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             if (sideContact) push = smin(push, P.skin_width);
             if (!(push <= 1e-6f)) {
                 st3(c.pos, ld3(c.pos) + depenNormal * push);
-                d3 vel = ldv(c.st);
+                d3 vel = ldv(*c.st);
                 d3 dn = to_d3(depenNormal);
                 double vInto = dot(vel, dn);
-                if (vInto < 0.0) stv(c.st, vel - dn * vInto);
+                if (vInto < 0.0) stv(*c.st, vel - dn * vInto);
                 c.flags |= F_DID_RESOLVE;
                 st3(c.dSum, ld3(c.dSum) + depenNormal * maxDepth);
                 c.dWeight += maxDepth;
@@ -381,17 +379,17 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
         const int tri = q.bestTri;
         bool haveCachedSide = false;
         f3 cachedSide = {0, 0, 0};
-        const int sideFrames = c.st.side_contact_frames;
+        const int sideFrames = c.st->side_contact_frames;
         if (hitN.y < P.min_ground_dot && sideFrames > 0) { // SYS:1683-1694
             f3 cached;
-            if (manifold_normal_for(c.st, tri, cached)) {
+            if (manifold_normal_for(*c.st, tri, cached)) {
                 if (dot(cached, hitN) < 0.0f) cached = -cached;
                 hitN = cached;
             }
         }
-        if (hitN.y < P.min_ground_dot && sideFrames > 0) haveCachedSide = manifold_normal_for(c.st, tri, cachedSide);
+        if (hitN.y < P.min_ground_dot && sideFrames > 0) haveCachedSide = manifold_normal_for(*c.st, tri, cachedSide);
         bool shouldBreak = slide_resolve(c, P, hitN, hitTriN, q.bestT, haveCachedSide, cachedSide, sideFrames);
-        if (hitN.y < P.min_ground_dot) cache_record(c.st, tri, hitN, true); // SYS:1738-1743
+        if (hitN.y < P.min_ground_dot) cache_record(*c.st, tri, hitN, true); // SYS:1738-1743
         if (c.flags & F_HAVE_LAST) {                                       // SYS:1744-1754
             f3 last = ld3(c.lastN);
             float dn = dot(last, hitN);
@@ -419,7 +417,10 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             c.cTri = q.bestTri;
             c.cPart = q.bestPart;
         }
-        next = NX_FALL;
+        // Dead-query elimination (exact): the fall probe only feeds state.distance (SYS:864), and that field is
+        // overwritten by centerHit.toi as soon as the guard `centerHit.toi <= snapDistance` passes (SYS:868-880).
+        // Queries have no other side effect, so the 200 m probe is issued only when the guard will fail.
+        next = ((c.flags & F_HAVE_CENTER) && c.cToi <= P.snap_distance) ? NX_GATE : NX_FALL;
         break;
     case W_FALL: // fall probe (SYS:855-866)
         if (q.bestTri >= 0) c.gDistance = q.bestT;
@@ -444,13 +445,8 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
                 oq.travDone = true;
                 return false;
             }
-            { // 168-byte record in
-                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(states + c.charIndex);
-                unsigned long long *dst = reinterpret_cast<unsigned long long *>(&c.st);
-#pragma unroll
-                for (int k = 0; k < (int)(sizeof(cq_character_state) / 8); k++) dst[k] = src[k];
-            }
-            cq_character_state &S = c.st;
+            c.st = states + c.charIndex;
+            cq_character_state &S = *c.st;
             const bool wasGrounded = S.grounded != 0, wasGroundedNear = S.grounded_near != 0;
             c.flags = (wasGrounded ? F_WAS_G : 0) | (wasGroundedNear ? F_WAS_GN : 0);
             d3 vel = ldv(S);
@@ -540,7 +536,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
                 bool nearGround = c.cToi <= groundNearThreshold;
                 if (nearGround) c.flags |= F_NEAR_GROUND | F_GROUNDED_NEAR;
                 c.gDistance = c.cToi;
-                d3 vel = ldv(c.st);
+                d3 vel = ldv(*c.st);
                 bool groundGateVel = vel.y <= 0.0;
                 double vInto = dot(vel, to_d3(ld3(c.cNormal)));
                 bool groundGateSpeed = vInto >= -(double)P.ground_snap_max_speed;
