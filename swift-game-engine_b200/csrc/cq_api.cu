@@ -2,6 +2,7 @@
 // entry points, counters.  No CPU fallback anywhere: every path needs a usable CUDA device.
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <map>
 
@@ -59,32 +60,49 @@ static void make_view(cq_world *w) {
 using namespace cq;
 
 // ---------------------------------------------------------------- host-pointer (synchronous) entry points
-// Chunked and double-buffered: chunk k's H2D copy and chunk k-1's D2H copy overlap chunk k's kernel.
+// Three-stage pipeline over chunks of the batch: a dedicated H2D stream streams the inputs in back to back,
+// two alternating compute streams run the chunk kernels (so one chunk's tail overlaps the next chunk's
+// head), a dedicated D2H stream streams the results out; events order chunk k's copy -> kernel -> copy.
+// PCIe is full duplex, so the wall time approaches max(H2D, kernels, D2H) instead of their sum.
+// Chunking adapts to the previous call of the same entry point: when that call was compute-bound (wall time
+// >> PCIe time of its bytes) the next one uses two chunks only, because every chunk kernel pays its own tail.
 template <class In, class Out, class Launch>
 static int run_batch(cq_world *w, const In *in, size_t inStride, Out *out, size_t outStride, int n, Launch launch,
-                     bool inPlace = false) {
+                     bool inPlace = false, float *computeBoundHint = nullptr) {
     if (n <= 0) return CQ_OK;
     CQ_CUDA(cudaSetDevice(w->device));
     const int CH = 1 << 17;
-    int chunk = n < 2 * CH ? n : CH;
-    int nbuf = n > chunk ? 2 : 1;
+    int nChunks = (n + CH - 1) / CH;
+    if (computeBoundHint && *computeBoundHint > 3.0f && nChunks > 2) nChunks = 2;
+    if (nChunks > CQ_PIPE_EVENTS) nChunks = CQ_PIPE_EVENTS;
+    const auto t0 = std::chrono::steady_clock::now();
+    int chunk = (n + nChunks - 1) / nChunks;
     int r;
-    if ((r = ensure_scratch(w->in, (size_t)chunk * inStride * nbuf)) != CQ_OK) return r;
-    if (!inPlace && (r = ensure_scratch(w->out, (size_t)chunk * outStride * nbuf)) != CQ_OK) return r;
+    if ((r = ensure_scratch(w->in, (size_t)n * inStride)) != CQ_OK) return r;
+    if (!inPlace && (r = ensure_scratch(w->out, (size_t)n * outStride)) != CQ_OK) return r;
     int k = 0;
     for (int lo = 0; lo < n; lo += chunk, k++) {
         int cnt = std::min(chunk, n - lo);
-        int b = k & 1;
-        cudaStream_t st = w->copyStream[b];
-        char *dIn = (char *)w->in.ptr + (size_t)b * chunk * inStride;
-        char *dOut = inPlace ? dIn : (char *)w->out.ptr + (size_t)b * chunk * outStride;
-        CQ_CUDA(cudaMemcpyAsync(dIn, (const char *)in + (size_t)lo * inStride, (size_t)cnt * inStride, cudaMemcpyHostToDevice, st));
-        r = launch(dIn, dOut, cnt, lo, st);
+        cudaStream_t cs = w->copyStream[k & 1]; // compute streams
+        char *dIn = (char *)w->in.ptr + (size_t)lo * inStride;
+        char *dOut = inPlace ? dIn : (char *)w->out.ptr + (size_t)lo * outStride;
+        CQ_CUDA(cudaMemcpyAsync(dIn, (const char *)in + (size_t)lo * inStride, (size_t)cnt * inStride, cudaMemcpyHostToDevice,
+                                w->h2dStream));
+        CQ_CUDA(cudaEventRecord(w->evIn[k], w->h2dStream));
+        CQ_CUDA(cudaStreamWaitEvent(cs, w->evIn[k], 0));
+        r = launch(dIn, dOut, cnt, lo, cs);
         if (r != CQ_OK) return r;
-        CQ_CUDA(cudaMemcpyAsync((char *)out + (size_t)lo * outStride, dOut, (size_t)cnt * outStride, cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaEventRecord(w->evDone[k], cs));
+        CQ_CUDA(cudaStreamWaitEvent(w->d2hStream, w->evDone[k], 0));
+        CQ_CUDA(cudaMemcpyAsync((char *)out + (size_t)lo * outStride, dOut, (size_t)cnt * outStride, cudaMemcpyDeviceToHost,
+                                w->d2hStream));
     }
-    CQ_CUDA(cudaStreamSynchronize(w->copyStream[0]));
-    CQ_CUDA(cudaStreamSynchronize(w->copyStream[1]));
+    CQ_CUDA(cudaStreamSynchronize(w->d2hStream));
+    if (computeBoundHint) {
+        double wallMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        double pcieMs = (double)n * (double)std::max(inStride, outStride) / 50.0e6; // ~50 GB/s per direction, duplex
+        *computeBoundHint = (float)(wallMs / std::max(pcieMs, 1e-3));
+    }
     return CQ_OK;
 }
 
@@ -148,6 +166,12 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
     for (int k = 0; k < 2; k++)
         if ((rc = check_cuda(cudaStreamCreateWithFlags(&w->copyStream[k], cudaStreamNonBlocking), "stream")) != CQ_OK)
             return fail(rc);
+    if ((rc = check_cuda(cudaStreamCreateWithFlags(&w->h2dStream, cudaStreamNonBlocking), "stream")) != CQ_OK) return fail(rc);
+    if ((rc = check_cuda(cudaStreamCreateWithFlags(&w->d2hStream, cudaStreamNonBlocking), "stream")) != CQ_OK) return fail(rc);
+    for (int k = 0; k < CQ_PIPE_EVENTS; k++) {
+        if ((rc = check_cuda(cudaEventCreateWithFlags(&w->evIn[k], cudaEventDisableTiming), "event")) != CQ_OK) return fail(rc);
+        if ((rc = check_cuda(cudaEventCreateWithFlags(&w->evDone[k], cudaEventDisableTiming), "event")) != CQ_OK) return fail(rc);
+    }
     if ((rc = check_cuda(cudaEventCreate(&w->evA), "event")) != CQ_OK) return fail(rc);
     if ((rc = check_cuda(cudaEventCreate(&w->evB), "event")) != CQ_OK) return fail(rc);
 
@@ -237,6 +261,12 @@ void cq_world_destroy(cq_world *w) {
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);
     if (w->stream) cudaStreamDestroy(w->stream);
+    if (w->h2dStream) cudaStreamDestroy(w->h2dStream);
+    if (w->d2hStream) cudaStreamDestroy(w->d2hStream);
+    for (int k = 0; k < CQ_PIPE_EVENTS; k++) {
+        if (w->evIn[k]) cudaEventDestroy(w->evIn[k]);
+        if (w->evDone[k]) cudaEventDestroy(w->evDone[k]);
+    }
     for (int k = 0; k < 2; k++)
         if (w->copyStream[k]) cudaStreamDestroy(w->copyStream[k]);
     delete w;
@@ -407,7 +437,8 @@ int cq_capsule_cast_batch(cq_world *w, const cq_capsule_cast *q, int32_t n, int3
     return run_batch(w, q, sizeof(cq_capsule_cast), out, sizeof(cq_cast_hit), n,
                      [&](void *di, void *dout, int cnt, int, cudaStream_t st) {
                          return launch_cast(w, (const cq_capsule_cast *)di, cnt, mode, (cq_cast_hit *)dout, st);
-                     });
+                     },
+                     false, &w->hintCast);
 }
 
 int cq_capsule_overlap_batch(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out) {
@@ -455,7 +486,7 @@ int cq_move_and_slide_batch(cq_world *w, cq_character_state *inout, int32_t n, c
                      [&](void *di, void *, int cnt, int, cudaStream_t st) {
                          return launch_move_and_slide(w, (cq_character_state *)di, cnt, *params, dt, gravity, flags, st);
                      },
-                     /*inPlace=*/true);
+                     /*inPlace=*/true, &w->hintMas);
 }
 
 } // extern "C"

@@ -52,10 +52,14 @@ struct ScratchBuf {
 
 } // namespace cq
 
+#define CQ_PIPE_EVENTS 64
+
 struct cq_world {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copyStream[2] = {nullptr, nullptr};
+    cudaStream_t copyStream[2] = {nullptr, nullptr}; // the two alternating compute streams of the batch pipeline
+    cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
+    cudaEvent_t evIn[CQ_PIPE_EVENTS] = {}, evDone[CQ_PIPE_EVENTS] = {};
     cudaEvent_t evA = nullptr, evB = nullptr;
     cq::DeviceSet set[2];
     std::vector<cq::PartInfo> parts;
@@ -66,6 +70,7 @@ struct cq_world {
     int counting = 0;
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
     uint64_t launches = 0;
+    float hintMas = 0.0f, hintCast = 0.0f; // wall/PCIe ratio of the previous host-pointer call (chunking heuristic)
     int *dWork = nullptr; // ring of dynamic-fetch counters, one per persistent-kernel launch in flight
     uint32_t workSeq = 0;
     cq::ScratchBuf in, out, aux, aux2;
