@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "cq_internal.h"
 
@@ -287,6 +288,125 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__res
     }
 }
 
+// ---------------------------------------------------------------- onesweep (Adinets & Merrill 2022)
+// One upfront histogram kernel counts all four digits of every key; then each of the four passes is ONE
+// kernel: tiles are handed out in launch order by an atomic ticket, every tile publishes its per-digit
+// counts in a status word (aggregate / inclusive flag in the two top bits) and resolves its exclusive
+// prefix by decoupled look-back over the preceding tiles, then scatters with the same stable
+// warp-match ranking as the classic path.  3 key reads + 4 key/value read-write sweeps in total instead
+// of 4 x (2 reads + 1 read-write) and 13 launches instead of 12 + scans of per-tile histograms.
+#define OS_FLAG_AGG 0x40000000u
+#define OS_FLAG_INC 0x80000000u
+#define OS_MASK 0x3fffffffu
+
+__global__ void __launch_bounds__(RS_THREADS) k_os_histogram(const uint32_t *__restrict__ keys, int n,
+                                                             uint32_t *__restrict__ hist /* [4][256] */) {
+    __shared__ uint32_t h[4][256];
+    for (int i = threadIdx.x; i < 1024; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) {
+        uint32_t k = keys[i];
+        atomicAdd(&h[0][k & 255u], 1u);
+        atomicAdd(&h[1][(k >> 8) & 255u], 1u);
+        atomicAdd(&h[2][(k >> 16) & 255u], 1u);
+        atomicAdd(&h[3][(k >> 24) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += RS_THREADS) {
+        uint32_t v = (&h[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+}
+
+__global__ void k_os_scan(uint32_t *__restrict__ hist /* [4][256] -> exclusive per pass */) {
+    __shared__ uint32_t sw[33];
+    for (int p = 0; p < 4; p++) {
+        uint32_t v = hist[p * 256 + threadIdx.x];
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(v, sw, total);
+        hist[p * 256 + threadIdx.x] = ex;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint32_t *__restrict__ keysIn,
+                                                        const uint32_t *__restrict__ valsIn,
+                                                        uint32_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut,
+                                                        int n, int shift, const uint32_t *__restrict__ digitBase /* [256] */,
+                                                        volatile uint32_t *status /* [nTiles][256] */, uint32_t *ticket,
+                                                        int *errorFlag) {
+    __shared__ uint32_t wh[RS_WARPS][256];
+    __shared__ uint32_t sTile;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u); // tiles are claimed in launch order: look-back never waits on a
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0; // tile whose CTA has not started
+    __syncthreads();
+    const int tile = (int)sTile;
+    int base = tile * RS_TILE + warp * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], off[RS_ITEMS];
+    const uint32_t ltMask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = base + r * 32 + lane;
+        bool valid = i < n;
+        key[r] = valid ? keysIn[i] : 0u;
+        val[r] = valid ? valsIn[i] : 0u;
+        uint32_t digit = valid ? ((key[r] >> shift) & 255u) : (256u + lane);
+        uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = wh[warp][digit];
+            wh[warp][digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        off[r] = old + __popc(peers & ltMask);
+        __syncwarp();
+    }
+    __syncthreads();
+    { // thread d owns digit d: tile count -> publish -> look back -> exclusive prefix -> per-warp bases
+        const int d = threadIdx.x;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) cnt += wh[w][d];
+        volatile uint32_t *mine = status + (size_t)tile * 256 + d;
+        *mine = cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG);
+        uint32_t prefix = 0;
+        for (int t = tile - 1; t >= 0; t--) {
+            volatile uint32_t *p = status + (size_t)t * 256 + d;
+            uint32_t s = *p;
+            uint32_t spins = 0;
+            while ((s & (OS_FLAG_AGG | OS_FLAG_INC)) == 0u) {
+                if (++spins > (1u << 26)) { // watchdog: never hang the device
+                    *errorFlag = 1;
+                    break;
+                }
+                s = *p;
+            }
+            prefix += s & OS_MASK;
+            if (s & OS_FLAG_INC) break;
+        }
+        if (tile > 0) *mine = ((prefix + cnt) & OS_MASK) | OS_FLAG_INC;
+        uint32_t run = digitBase[d] + prefix;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = wh[w][d];
+            wh[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = base + r * 32 + lane;
+        if (i < n) {
+            uint32_t digit = (key[r] >> shift) & 255u;
+            uint32_t o = wh[warp][digit] + off[r];
+            keysOut[o] = key[r];
+            valsOut[o] = val[r];
+        }
+    }
+}
+
 // NB: k_rs_hist walks the tile thread-strided while k_rs_scatter walks it warp-chunked; both count the
 // same multiset per tile, which is all the histogram needs.
 
@@ -434,8 +554,8 @@ static int exclusive_scan_u32(cq_world *w, const uint32_t *in, int n, uint32_t *
     return check_cuda(cudaGetLastError(), "scan");
 }
 
-static int radix_sort_pairs(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTmp, uint32_t *valsTmp, int n,
-                            uint32_t *hist /* 256 * nBlocks */) {
+static int radix_sort_pairs_classic(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTmp, uint32_t *valsTmp,
+                                    int n, uint32_t *hist /* 256 * nBlocks */) {
     cudaStream_t st = w->stream;
     int nBlocks = cdiv(n, RS_TILE);
     uint32_t *kin = keys, *vin = vals, *kout = keysTmp, *vout = valsTmp;
@@ -450,6 +570,46 @@ static int radix_sort_pairs(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_
     }
     // 4 passes: result is back in (keys, vals)
     return check_cuda(cudaGetLastError(), "radix sort");
+}
+
+// onesweep: status = [4][nTiles][256] u32 + [4] tickets + [4][256] digit histograms + error flag, in `scratch`
+static int radix_sort_pairs_onesweep(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTmp, uint32_t *valsTmp,
+                                     int n, uint32_t *scratch, size_t scratchWords) {
+    cudaStream_t st = w->stream;
+    int nTiles = cdiv(n, RS_TILE);
+    size_t statusWords = (size_t)4 * nTiles * 256;
+    if (statusWords + 4 + 1024 + 1 > scratchWords) {
+        set_error("onesweep scratch too small");
+        return CQ_ERR_INVALID;
+    }
+    uint32_t *status = scratch, *tickets = scratch + statusWords, *hist = tickets + 4;
+    int *err = (int *)(hist + 1024);
+    CQ_CUDA(cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * (statusWords + 4 + 1024 + 1), st));
+    int hb = std::min(nTiles, 148 * 8);
+    k_os_histogram<<<hb, RS_THREADS, 0, st>>>(keys, n, hist);
+    k_os_scan<<<1, 256, 0, st>>>(hist);
+    w->launches += 2;
+    uint32_t *kin = keys, *vin = vals, *kout = keysTmp, *vout = valsTmp;
+    for (int pass = 0; pass < 4; pass++) {
+        k_os_pass<<<nTiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, pass * 8, hist + pass * 256,
+                                                 status + (size_t)pass * nTiles * 256, tickets + pass, err);
+        w->launches++;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    int hostErr = 0;
+    CQ_CUDA(cudaMemcpyAsync(&hostErr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CQ_CUDA(cudaStreamSynchronize(st));
+    if (hostErr) {
+        set_error("onesweep look-back watchdog fired");
+        return CQ_ERR_CUDA;
+    }
+    return check_cuda(cudaGetLastError(), "onesweep");
+}
+
+static bool use_classic_sort() {
+    const char *e = getenv("CQ_SORT");
+    return e && !strcmp(e, "classic");
 }
 
 static int build_tree(cq_world *w, DeviceSet &S, const uint32_t *sortedKeys /* may be null on refit */) {
@@ -559,12 +719,14 @@ int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, co
         CQ_TRY(dalloc(&dKeys, (size_t)n));
         CQ_TRY(dalloc(&dKeysTmp, (size_t)n));
         CQ_TRY(dalloc(&dValsTmp, (size_t)n));
-        CQ_TRY(dalloc(&dHist, (size_t)256 * cdiv(n, RS_TILE)));
+        const size_t histWords = (size_t)4 * 256 * cdiv(n, RS_TILE) + 4 + 1024 + 1; // classic needs 256*tiles; onesweep 4x + extras
+        CQ_TRY(dalloc(&dHist, histWords));
         k_init_bounds<<<1, 32, 0, st>>>(dBounds);
         k_centroid_bounds<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds);
         k_morton<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds, dKeys, S.sortedTri);
         w->launches += 3;
-        rc = radix_sort_pairs(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist);
+        rc = use_classic_sort() ? radix_sort_pairs_classic(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist)
+                                : radix_sort_pairs_onesweep(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist, histWords);
         if (rc == CQ_OK) rc = build_tree(w, S, dKeys);
         cudaError_t e = cudaStreamSynchronize(st);
         if (rc == CQ_OK) rc = check_cuda(e, "build sync");

@@ -187,3 +187,56 @@ def test_header_is_plain_c_and_cpp_mirror_compiles(tmp_path):
                    % os.path.join(ROOT, "swift-game-engine_b200", "cpp", "CollisionQuery.hpp"))
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+class _RecorderWorld:
+    """Stands in for the CUDA query object so the service policy can be tested without a GPU."""
+    log = []
+
+    def __init__(self, parts):
+        self.parts = parts
+        _RecorderWorld.log.append(("build", [p["entity_id"] for p in parts], [bool(p["is_dynamic"]) for p in parts]))
+
+    def updateStaticTransforms(self, ids, models):
+        _RecorderWorld.log.append(("static", list(ids)))
+
+    def updateDynamicTransforms(self, ids, models):
+        _RecorderWorld.log.append(("dynamic", list(ids)))
+
+    def close(self):
+        pass
+
+
+def test_collision_query_service_rebuild_vs_refit_policy(cq, scenes):
+    """CollisionQueryService.update (SceneServices.swift:52-169): what triggers a rebuild, what a refit."""
+    v, i = scenes.plane_mesh(10.0)
+    bv, bi = scenes.box_mesh(2.0)
+    ents = [dict(entity_id=0, positions=v, indices=i, body_type="static"),
+            dict(entity_id=1, positions=bv, indices=bi, translation=(0, 1, 0), body_type="kinematic"),
+            dict(entity_id=2, positions=bv, indices=bi, translation=(4, 1, 0)),
+            dict(entity_id=3, positions=bv, indices=bi, collides=False)]
+    _RecorderWorld.log = []
+    svc = cq.CollisionQueryService(world_factory=_RecorderWorld)
+    svc.update(ents)
+    assert svc.last_action == "rebuild" and _RecorderWorld.log[-1] == ("build", [0, 1, 2], [False, True, False])
+    svc.update(ents)
+    assert svc.last_action == "none"
+    ents[1]["translation"] = (0, 1.5, 0)  # kinematic platform moved -> dynamic refit
+    svc.update(ents)
+    assert svc.last_action == "refit" and _RecorderWorld.log[-1] == ("dynamic", [1])
+    ents[2]["rotation"] = tuple(scenes.quat_angle_axis(0.3, (0, 1, 0)))  # body-less entity -> static refit
+    svc.update(ents)
+    assert _RecorderWorld.log[-1] == ("static", [2])
+    ents[2]["translation"] = (4, 1 + 5e-4, 0)  # squared delta 2.5e-7 <= 1e-6: below the threshold
+    svc.update(ents)
+    assert svc.last_action == "none"
+    n_builds = sum(1 for x in _RecorderWorld.log if x[0] == "build")
+    for mutate in (lambda: ents[2].__setitem__("dirty", True), lambda: ents[1].__setitem__("body_type", "dynamic"),
+                   lambda: ents[3].__setitem__("collides", True), lambda: ents[0].__setitem__("indices", i[:3]),
+                   lambda: svc.markDirty()):
+        mutate()
+        svc.update(ents)
+        n_builds += 1
+        assert svc.last_action == "rebuild" and sum(1 for x in _RecorderWorld.log if x[0] == "build") == n_builds
+    svc.update(ents, active_ids={0, 1})  # active set changed -> rebuild with the filtered entities
+    assert _RecorderWorld.log[-1][0] == "build" and _RecorderWorld.log[-1][1] == [0, 1]
