@@ -233,7 +233,7 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
         cudaMemcpyAsync(w->dModels, models.data(), sizeof(float) * 16 * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
         cudaMemcpyAsync(w->dMaterials, materials.data(), sizeof(float4) * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
     }
-    cudaEventRecord(w->evA, w->stream);
+    w->buildMs = 0.0f; // accumulated by build_set: device time of the build kernels only
     for (int s = 0; s < 2; s++) {
         rc = build_set(w, w->set[s], localPos[s], idxIn[s], layerIn[s], partIn[s], partTriStart[s]);
         if (rc != CQ_OK) return fail(rc);
@@ -243,9 +243,7 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
             pi.triHi = partTriStart[s][k + 1];
         }
     }
-    cudaEventRecord(w->evB, w->stream);
     if ((rc = check_cuda(cudaStreamSynchronize(w->stream), "build")) != CQ_OK) return fail(rc);
-    cudaEventElapsedTime(&w->buildMs, w->evA, w->evB);
     make_view(w);
     *out = w;
     return CQ_OK;

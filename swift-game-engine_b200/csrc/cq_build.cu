@@ -178,13 +178,20 @@ __global__ void k_centroid_bounds(const float4 *__restrict__ world, const uint32
         hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
         hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(bounds + 0, float_to_ordered(lo.x));
-        atomicMin(bounds + 1, float_to_ordered(lo.y));
-        atomicMin(bounds + 2, float_to_ordered(lo.z));
-        atomicMax(bounds + 3, float_to_ordered(hi.x));
-        atomicMax(bounds + 4, float_to_ordered(hi.y));
-        atomicMax(bounds + 5, float_to_ordered(hi.z));
+    // block-level reduction, then six atomics per CTA (one per warp made this kernel atomic-bound)
+    __shared__ float red[6][8];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[0][warp] = lo.x, red[1][warp] = lo.y, red[2][warp] = lo.z;
+        red[3][warp] = hi.x, red[4][warp] = hi.y, red[5][warp] = hi.z;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = red[threadIdx.x][0];
+        int nw = blockDim.x >> 5;
+        for (int k = 1; k < nw; k++) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][k]) : fmaxf(v, red[threadIdx.x][k]);
+        if (threadIdx.x < 3) atomicMin(bounds + threadIdx.x, float_to_ordered(v));
+        else atomicMax(bounds + threadIdx.x, float_to_ordered(v));
     }
 }
 
@@ -530,16 +537,22 @@ __global__ void k_header(int n, const float4 *__restrict__ boxLo, const float4 *
 // ---------------------------------------------------------------- host orchestration
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-template <class T> static int dalloc(T **p, size_t count) {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    return check_cuda(cudaMalloc((void **)p, count * sizeof(T)), "cudaMalloc");
-}
+// One cudaMalloc per triangle set (+ one for build temporaries): GB-scale cudaMalloc/cudaFree calls cost
+// tens to hundreds of milliseconds each on this driver, far more than the build kernels themselves.
+struct Arena {
+    char *base = nullptr;
+    size_t off = 0, cap = 0;
+    template <class T> T *take(size_t count) {
+        if (count == 0) count = 1;
+        off = (off + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
 
 void free_set(DeviceSet &S) {
-    cudaFree(S.localPos), cudaFree(S.worldPos), cudaFree(S.indices), cudaFree(S.triLayer), cudaFree(S.triPart);
-    cudaFree(S.sortedTri), cudaFree(S.tv0), cudaFree(S.tv1), cudaFree(S.tv2), cudaFree(S.nodes), cudaFree(S.parent);
-    cudaFree(S.rangeLo), cudaFree(S.rangeHi), cudaFree(S.boxLo), cudaFree(S.boxHi), cudaFree(S.visit), cudaFree(S.hdr);
+    cudaFree(S.arena);
     S = DeviceSet();
 }
 
@@ -634,32 +647,89 @@ static int build_tree(cq_world *w, DeviceSet &S, const uint32_t *sortedKeys /* m
     return check_cuda(cudaGetLastError(), "build_tree");
 }
 
+template <class Fn> static size_t arena_layout(Fn fn) { // run the carving once without memory to learn the size
+    Arena a;
+    fn(a);
+    return a.off + 256;
+}
+
 int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,
               const std::vector<uint32_t> &triLayerIn, const std::vector<int32_t> &triPartIn,
               std::vector<int> &partTriStartIn /* in: first input triangle of each part of this set (+ end), out: filtered */) {
     cudaStream_t st = w->stream;
     S.nVerts = (int)localPos.size();
     S.nTrisIn = (int)triLayerIn.size();
-    int nIn = S.nTrisIn;
-    CQ_TRY(dalloc(&S.localPos, (size_t)S.nVerts));
-    CQ_TRY(dalloc(&S.worldPos, (size_t)S.nVerts));
-    CQ_TRY(dalloc(&S.hdr, 1));
-    uint32_t *dIdxIn = nullptr, *dLayerIn = nullptr, *dFlags = nullptr, *dOffs = nullptr, *dTileSums = nullptr, *dTotal = nullptr;
-    int32_t *dPartIn = nullptr;
-    CQ_TRY(dalloc(&dIdxIn, (size_t)nIn * 3));
-    CQ_TRY(dalloc(&dLayerIn, (size_t)nIn));
-    CQ_TRY(dalloc(&dPartIn, (size_t)nIn));
-    CQ_TRY(dalloc(&dFlags, (size_t)nIn));
-    CQ_TRY(dalloc(&dOffs, (size_t)nIn + 1));
-    CQ_TRY(dalloc(&dTileSums, (size_t)cdiv(std::max(nIn, 1), SCAN_TILE) + 1));
-    CQ_TRY(dalloc(&dTotal, 1));
+    const int nIn = S.nTrisIn;
+    const int nCap = std::max(nIn, 1); // nTris (after the filter) <= nIn: size everything by the upper bound
+    // ---- persistent arrays
+    auto carve = [&](Arena &a) {
+        S.localPos = a.take<float4>(S.nVerts);
+        S.worldPos = a.take<float4>(S.nVerts);
+        S.hdr = a.take<SetHeader>(1);
+        S.indices = a.take<uint32_t>((size_t)nCap * 3);
+        S.triLayer = a.take<uint32_t>(nCap);
+        S.triPart = a.take<int32_t>(nCap);
+        S.sortedTri = a.take<uint32_t>(nCap);
+        S.tv0 = a.take<float4>(nCap);
+        S.tv1 = a.take<float4>(nCap);
+        S.tv2 = a.take<float4>(nCap);
+        S.nodes = a.take<Node>(nCap);
+        S.parent = a.take<int32_t>((size_t)2 * nCap);
+        S.rangeLo = a.take<int32_t>(nCap);
+        S.rangeHi = a.take<int32_t>(nCap);
+        S.boxLo = a.take<float4>((size_t)2 * nCap);
+        S.boxHi = a.take<float4>((size_t)2 * nCap);
+        S.visit = a.take<int32_t>(nCap);
+    };
+    Arena arena;
+    arena.cap = arena_layout(carve);
+    CQ_CUDA(cudaMalloc((void **)&arena.base, arena.cap));
+    S.arena = arena.base;
+    carve(arena);
+    // ---- temporaries
+    uint32_t *dIdxIn, *dLayerIn, *dFlags, *dOffs, *dTileSums, *dTotal, *dKeys, *dKeysTmp, *dValsTmp, *dHist, *dGatherOut;
+    int32_t *dPartIn, *dGatherPos;
+    int *dBounds;
+    const int np = (int)partTriStartIn.size();
+    const size_t histWords = (size_t)4 * 256 * cdiv(nCap, RS_TILE) + 4 + 1024 + 1; // classic: 256*tiles; onesweep: 4x + extras
+    auto carveTmp = [&](Arena &a) {
+        dIdxIn = a.take<uint32_t>((size_t)nCap * 3);
+        dLayerIn = a.take<uint32_t>(nCap);
+        dPartIn = a.take<int32_t>(nCap);
+        dFlags = a.take<uint32_t>(nCap);
+        dOffs = a.take<uint32_t>((size_t)nCap + 1);
+        dTileSums = a.take<uint32_t>((size_t)cdiv(nCap, SCAN_TILE) + 1);
+        dTotal = a.take<uint32_t>(1);
+        dKeys = a.take<uint32_t>(nCap);
+        dKeysTmp = a.take<uint32_t>(nCap);
+        dValsTmp = a.take<uint32_t>(nCap);
+        dHist = a.take<uint32_t>(histWords);
+        dBounds = a.take<int>(8);
+        dGatherPos = a.take<int32_t>(std::max(np, 1));
+        dGatherOut = a.take<uint32_t>(std::max(np, 1));
+    };
+    Arena tmp;
+    tmp.cap = arena_layout(carveTmp);
+    CQ_CUDA(cudaMalloc((void **)&tmp.base, tmp.cap));
+    carveTmp(tmp);
+    auto done = [&](int rc) {
+        cudaFree(tmp.base);
+        return rc;
+    };
+    // ---- upload
     if (S.nVerts)
         CQ_CUDA(cudaMemcpyAsync(S.localPos, localPos.data(), sizeof(float4) * (size_t)S.nVerts, cudaMemcpyHostToDevice, st));
     if (nIn) {
         CQ_CUDA(cudaMemcpyAsync(dIdxIn, indicesIn.data(), sizeof(uint32_t) * 3 * (size_t)nIn, cudaMemcpyHostToDevice, st));
         CQ_CUDA(cudaMemcpyAsync(dLayerIn, triLayerIn.data(), sizeof(uint32_t) * (size_t)nIn, cudaMemcpyHostToDevice, st));
         CQ_CUDA(cudaMemcpyAsync(dPartIn, triPartIn.data(), sizeof(int32_t) * (size_t)nIn, cudaMemcpyHostToDevice, st));
+        if (np) CQ_CUDA(cudaMemcpyAsync(dGatherPos, partTriStartIn.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, st));
     }
+    // ---- kernels (timed: build_ms is device time of the build kernels, uploads and allocations excluded)
+    cudaEvent_t e0, e1;
+    CQ_CUDA(cudaEventCreate(&e0));
+    CQ_CUDA(cudaEventCreate(&e1));
+    cudaEventRecord(e0, st);
     uint32_t total = 0;
     if (S.nVerts) {
         k_transform<<<cdiv(S.nVerts, 256), 256, 0, st>>>(S.localPos, S.worldPos, w->dModels, 0, S.nVerts);
@@ -669,75 +739,43 @@ int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, co
         k_filter_flags<<<cdiv(nIn, 256), 256, 0, st>>>(S.worldPos, dIdxIn, nIn, dFlags);
         w->launches++;
         int r = exclusive_scan_u32(w, dFlags, nIn, dOffs, dTileSums, dTotal);
-        if (r != CQ_OK) return r;
+        if (r != CQ_OK) return done(r);
+        CQ_CUDA(cudaMemcpyAsync(dOffs + nIn, dTotal, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st)); // dOffs[nIn] = total
+        if (np) {
+            k_gather_u32<<<cdiv(np, 256), 256, 0, st>>>(dOffs, dGatherPos, np, dGatherOut);
+            w->launches++;
+        }
+        std::vector<uint32_t> outv(std::max(np, 1));
         CQ_CUDA(cudaMemcpyAsync(&total, dTotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CQ_CUDA(cudaStreamSynchronize(st));
-        // dOffs[nIn] = total, so slice ends can be gathered uniformly
-        CQ_CUDA(cudaMemcpyAsync(dOffs + nIn, &total, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    }
-    S.nTris = (int)total;
-    int n = S.nTris;
-    CQ_TRY(dalloc(&S.indices, (size_t)n * 3));
-    CQ_TRY(dalloc(&S.triLayer, (size_t)n));
-    CQ_TRY(dalloc(&S.triPart, (size_t)n));
-    CQ_TRY(dalloc(&S.sortedTri, (size_t)n));
-    CQ_TRY(dalloc(&S.tv0, (size_t)n));
-    CQ_TRY(dalloc(&S.tv1, (size_t)n));
-    CQ_TRY(dalloc(&S.tv2, (size_t)n));
-    CQ_TRY(dalloc(&S.nodes, (size_t)std::max(n - 1, 1)));
-    CQ_TRY(dalloc(&S.parent, (size_t)std::max(2 * n - 1, 1)));
-    CQ_TRY(dalloc(&S.rangeLo, (size_t)std::max(n - 1, 1)));
-    CQ_TRY(dalloc(&S.rangeHi, (size_t)std::max(n - 1, 1)));
-    CQ_TRY(dalloc(&S.boxLo, (size_t)std::max(2 * n - 1, 1)));
-    CQ_TRY(dalloc(&S.boxHi, (size_t)std::max(2 * n - 1, 1)));
-    CQ_TRY(dalloc(&S.visit, (size_t)std::max(n - 1, 1)));
-    // filtered slice boundaries of each part
-    if (nIn && !partTriStartIn.empty()) {
-        int np = (int)partTriStartIn.size();
-        int32_t *dPos = nullptr;
-        uint32_t *dOut = nullptr;
-        CQ_TRY(dalloc(&dPos, (size_t)np));
-        CQ_TRY(dalloc(&dOut, (size_t)np));
-        CQ_CUDA(cudaMemcpyAsync(dPos, partTriStartIn.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, st));
-        k_gather_u32<<<cdiv(np, 256), 256, 0, st>>>(dOffs, dPos, np, dOut);
-        w->launches++;
-        std::vector<uint32_t> outv(np);
-        CQ_CUDA(cudaMemcpyAsync(outv.data(), dOut, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, st));
-        CQ_CUDA(cudaStreamSynchronize(st));
+        if (np) CQ_CUDA(cudaMemcpyAsync(outv.data(), dGatherOut, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaStreamSynchronize(st)); // the filtered triangle count sizes the remaining launches
         for (int i = 0; i < np; i++) partTriStartIn[i] = (int)outv[i];
-        cudaFree(dPos), cudaFree(dOut);
     } else {
         for (auto &v : partTriStartIn) v = 0;
     }
+    S.nTris = (int)total;
+    const int n = S.nTris;
     int rc = CQ_OK;
     if (n > 0) {
         k_compact<<<cdiv(nIn, 256), 256, 0, st>>>(dFlags, dOffs, nIn, dIdxIn, dLayerIn, dPartIn, S.indices, S.triLayer, S.triPart);
-        w->launches++;
-        int *dBounds = nullptr;
-        uint32_t *dKeys = nullptr, *dKeysTmp = nullptr, *dValsTmp = nullptr, *dHist = nullptr;
-        CQ_TRY(dalloc(&dBounds, 8));
-        CQ_TRY(dalloc(&dKeys, (size_t)n));
-        CQ_TRY(dalloc(&dKeysTmp, (size_t)n));
-        CQ_TRY(dalloc(&dValsTmp, (size_t)n));
-        const size_t histWords = (size_t)4 * 256 * cdiv(n, RS_TILE) + 4 + 1024 + 1; // classic needs 256*tiles; onesweep 4x + extras
-        CQ_TRY(dalloc(&dHist, histWords));
         k_init_bounds<<<1, 32, 0, st>>>(dBounds);
         k_centroid_bounds<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds);
         k_morton<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds, dKeys, S.sortedTri);
-        w->launches += 3;
+        w->launches += 4;
         rc = use_classic_sort() ? radix_sort_pairs_classic(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist)
                                 : radix_sort_pairs_onesweep(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist, histWords);
         if (rc == CQ_OK) rc = build_tree(w, S, dKeys);
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (rc == CQ_OK) rc = check_cuda(e, "build sync");
-        cudaFree(dBounds), cudaFree(dKeys), cudaFree(dKeysTmp), cudaFree(dValsTmp), cudaFree(dHist);
     } else {
         rc = build_tree(w, S, nullptr);
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (rc == CQ_OK) rc = check_cuda(e, "build sync");
     }
-    cudaFree(dIdxIn), cudaFree(dLayerIn), cudaFree(dPartIn), cudaFree(dFlags), cudaFree(dOffs), cudaFree(dTileSums), cudaFree(dTotal);
-    return rc;
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == CQ_OK) rc = check_cuda(e, "build sync");
+    float ms = 0;
+    if (rc == CQ_OK && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) w->buildMs += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return done(rc);
 }
 
 // TriangleMeshSet.updateTransforms + BVH.refit: re-transform the changed parts' vertices, regather the

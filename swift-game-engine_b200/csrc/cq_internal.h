@@ -23,6 +23,7 @@ struct PartInfo {
 
 // One TriangleMeshSet (CollisionQuery.swift:320-470) resident in HBM.
 struct DeviceSet {
+    void *arena = nullptr; // one allocation holds every array below
     int nVerts = 0;
     int nTrisIn = 0; // before the degenerate filter
     int nTris = 0;   // after

@@ -276,3 +276,23 @@ def test_terrain_lbvh_and_blocking_sweeps(cq, orc, scenes):
     assert sg["grounded"].mean() > 0.8
     g.close()
     o.close()
+
+
+def test_onesweep_sort_builds_the_same_tree_as_the_classic_sort(cq, orc, scenes, monkeypatch):
+    """The onesweep radix sort (decoupled look-back) and the classic 3-kernel-per-pass sort are both stable LSD
+    sorts of the same (Morton key, triangle) pairs, so the two LBVHs — hence every traversal counter — must be
+    identical; results are checked against the oracle as well."""
+    parts, half = scenes.terrain_scene(cells=400, cell=2.0)  # 320,000 triangles = 79 tiles of 4096 keys
+    q = scenes.gen_c4_casts(30000, half, seed=77, radius=1.5, half_height=1.0)
+    out = {}
+    for mode in ("classic", "onesweep"):
+        monkeypatch.setenv("CQ_SORT", mode)
+        g = cq.CollisionQuery(parts)
+        g.set_counting(True)
+        g.resetStats()
+        hits = g.capsuleCastBlocking(q)
+        out[mode] = (hits.tobytes(), g.stats()["nodes_visited"], g.stats()["candidates"])
+        g.close()
+    assert out["classic"] == out["onesweep"]
+    o = orc.OracleWorld(parts)
+    assert out["onesweep"][0] == o.capsule_cast(q, 1, orc.ORDER_CANONICAL).tobytes()
