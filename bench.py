@@ -248,8 +248,15 @@ def run_ours(args):
     achieved = algo_bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     evals_per_launch = ctr["distance_evals"] / args.steps
     fp32_peak_tinst = 148 * 128 * 1.965e9 / 1e12  # lanes x clock: issue ceiling with FMA off (1 flop / lane / clk)
+    traffic = None  # DRAM bytes per launch from the committed ncu capture (profiles/r1_traffic.json), scaled to n
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_move_and_slide"]
+        if args.mesh == "hulls":
+            traffic = tj["dram_bytes_per_character"] * n
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "kernel": "k_move_and_slide", "kernel_ms": kernel_ms,
         "algorithmic_bytes_per_launch": algo_bytes_per_launch,
         "per_query": {"nodes": ctr["nodes_visited"] / (n * args.steps), "candidates": ctr["candidates"] / (n * args.steps),
