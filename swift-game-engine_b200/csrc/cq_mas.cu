@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
         QResult r;
         pool_read_result(mine, r);
         return mas_advance<COUNT>(c, r, mine, oq, stk, W, A, states, n, workCounter, ct);
-    });
+    }, OverlapTop2());
     pool_flush_counters(ctr, gctr, COUNT);
 }
 

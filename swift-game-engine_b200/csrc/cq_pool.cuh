@@ -56,6 +56,7 @@ struct QResult { // what owner logic reads back (same names as the engine's resu
 
 struct Job { // executor-side pair state (registers)
     int phase, owner;
+    uint32_t enc; // ring entry (owner | set | slot): lets an owner reload a winning triangle later
     f3 from, dir;
     float L, radius, hh, minAdvance;
     int maxIter;
@@ -224,6 +225,7 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
             int owner = e >> 27, set = (e >> 26) & 1, slot = e & 0x3ffffffu;
             const QShared &s = wp.qs[owner];
             job.owner = owner;
+            job.enc = e;
             job.from = mk3(s.from[0], s.from[1], s.from[2]);
             job.dir = mk3(s.dir[0], s.dir[1], s.dir[2]);
             job.L = s.L;
@@ -327,7 +329,28 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
 }
 
 // serialized commit: one finishing lane at a time updates its owner's record; pending counters drop
-__device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const Commit &cm, bool retired, int lane) {
+// default overlap commit: the two deepest overlaps kept in the owner's QShared (move-and-slide depenetration)
+struct OverlapTop2 {
+    __device__ __forceinline__ void operator()(QShared &s, float depth, int gid, uint32_t, f3 n) const {
+        float d0 = s.rT, d1 = s.rPos[0];
+        int t0 = s.rTri, t1 = s.rPart;
+        bool before0 = t0 < 0 || depth > d0 || (depth == d0 && gid < t0);
+        bool before1 = t1 < 0 || depth > d1 || (depth == d1 && gid < t1);
+        if (before0) {
+            s.rPos[0] = d0, s.rPart = t0;
+            store3s(s.rTriN, mk3(s.rN[0], s.rN[1], s.rN[2]));
+            s.rT = depth, s.rTri = gid;
+            store3s(s.rN, n);
+        } else if (before1) {
+            s.rPos[0] = depth, s.rPart = gid;
+            store3s(s.rTriN, n);
+        }
+    }
+};
+
+template <class OvlCommit>
+__device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const Commit &cm, bool retired, int lane,
+                                            OvlCommit ovl) {
     uint32_t fin = __ballot_sync(0xffffffffu, retired);
     uint32_t todo = __ballot_sync(0xffffffffu, retired && cm.kind != 0);
     while (todo) {
@@ -348,21 +371,8 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                     store3s(s.rN, cm.n);
                     store3s(s.rTriN, cm.triN);
                 }
-            } else { // two deepest overlaps, (depth desc, index asc)
-                float depth = cm.key;
-                float d0 = s.rT, d1 = s.rPos[0];
-                int t0 = s.rTri, t1 = s.rPart;
-                bool before0 = t0 < 0 || depth > d0 || (depth == d0 && job.gid < t0);
-                bool before1 = t1 < 0 || depth > d1 || (depth == d1 && job.gid < t1);
-                if (before0) {
-                    s.rPos[0] = d0, s.rPart = t0;
-                    store3s(s.rTriN, mk3(s.rN[0], s.rN[1], s.rN[2]));
-                    s.rT = depth, s.rTri = job.gid;
-                    store3s(s.rN, cm.n);
-                } else if (before1) {
-                    s.rPos[0] = depth, s.rPart = job.gid;
-                    store3s(s.rTriN, cm.n);
-                }
+            } else { // overlap: (depth desc, index asc) bookkeeping is the kernel's (top-2 or top-K)
+                ovl(s, cm.key, job.gid, job.enc, cm.n);
             }
         }
         __syncwarp();
@@ -379,9 +389,9 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
 // lane's current query is complete (walk finished, no pair pending), consumes the result from `mine`,
 // runs the unit's serial logic and posts the next query (pool_post_*) — or returns false when the lane has
 // no more work units.
-template <bool COUNT, class Advance>
+template <bool COUNT, class Advance, class OvlCommit>
 __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int *stack, Counters &ctr,
-                                         Advance advance) {
+                                         Advance advance, OvlCommit ovl) {
     QShared &mine = wp.qs[lane];
     mine.pending = 0;
     mine.rTri = -1;
@@ -412,7 +422,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         cm.kind = 0;
         bool retired = false;
         if (job.phase != PH_NONE) pool_eval<COUNT>(job, wp, cm, retired, ctr);
-        pool_commit(wp, job, cm, retired, lane);
+        pool_commit(wp, job, cm, retired, lane, ovl);
         if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE)) break;
     }
 }

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, cons
         pool_post_cast<COUNT>(W, mine, oq, stk, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
                               c.min_normal_y, ct);
         return true;
-    });
+    }, OverlapTop2());
     flush_counters<COUNT>(ctr, gctr);
 }
 
@@ -123,77 +123,111 @@ __device__ __forceinline__ void write_overlap_nil(cq_overlap_hit &h) {
     h.triangle_index = -1;
 }
 
-// ---------------------------------------------------------------- capsule overlap: deepest (CollisionQuery.swift:830-850, 1119-1199)
-// deepest wins; equal depth -> smallest triangle index (reference: first visited)
-template <bool COUNT>
-__global__ void __launch_bounds__(Q_THREADS) k_capsule_overlap(WorldView W, const cq_capsule *__restrict__ q, int n,
-                                                               cq_overlap_hit *__restrict__ out,
-                                                               unsigned long long *gctr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    Counters ctr = {0, 0, 0, 0};
-    if (i < n) {
-        cq_capsule c = q[i];
-        OverlapRec best;
-        best.tri = -1;
-        best.depth = 0.0f;
-        capsule_overlap_visit<COUNT>(W, load3(c.from), c.radius, c.half_height, c.mask, ctr,
-                                     [&](float depth, int gid, int part, const Tri &T, float dist, f3 sp, f3 tp) {
-                                         bool better = depth > best.depth; // :1172 (depth <= bestDepth rejected)
-                                         bool tieWin = best.tri >= 0 && depth == best.depth && gid < best.tri;
-                                         if (!better && !tieWin) return;
-                                         overlap_contact(T, dist, sp, tp, c.radius, best);
-                                         best.tri = gid;
-                                         best.part = part;
-                                     });
-        cq_overlap_hit h;
-        if (best.tri >= 0) write_overlap(h, best);
-        else write_overlap_nil(h);
-        out[i] = h;
+// ---------------------------------------------------------------- capsule overlap / overlap-all
+// (CollisionQuery.swift:830-882, 1119-1283) on the pair pool: one distance evaluation per (capsule, triangle)
+// pair, shared by the warp.  The owner keeps the maxHits deepest overlaps as (depth, triangle, ring entry) in
+// shared memory — inserted in the serialized commit step, order (depth desc, index asc) — and, when its
+// query completes, re-evaluates those <= 8 winners to emit the full contact records (same arithmetic, so the
+// records are bit-identical to what the pair's executor saw).
+//   capsuleOverlap    = the deepest one (ties -> smallest index; the reference: first visited)
+//   capsuleOverlapAll = the maxHits deepest, deepest first — the order every caller in the reference sorts into
+//                       (Systems.swift:759); the reference returns its first maxHits in DFS order, identical
+//                       whenever <= maxHits triangles overlap, flagged `overflow` otherwise.
+struct OvlTop {
+    float depth[CQ_MAX_OVERLAP_HITS];
+    int gid[CQ_MAX_OVERLAP_HITS];
+    uint32_t enc[CQ_MAX_OVERLAP_HITS];
+    int count, total, cap, _pad;
+};
+
+struct OverlapTopK {
+    OvlTop *tops; // the warp's 32 records
+    __device__ __forceinline__ void operator()(QShared &, float depth, int gid, uint32_t enc, f3) const {
+        OvlTop &t = tops[enc >> 27];
+        t.total++;
+        int pos = t.count;
+        while (pos > 0 && (t.depth[pos - 1] < depth || (t.depth[pos - 1] == depth && t.gid[pos - 1] > gid))) pos--;
+        if (pos >= t.cap) return;
+        int last = t.count < t.cap ? t.count : t.cap - 1;
+        for (int k = last; k > pos; k--) {
+            t.depth[k] = t.depth[k - 1];
+            t.gid[k] = t.gid[k - 1];
+            t.enc[k] = t.enc[k - 1];
+        }
+        t.depth[pos] = depth;
+        t.gid[pos] = gid;
+        t.enc[pos] = enc;
+        if (t.count < t.cap) t.count++;
     }
-    flush_counters<COUNT>(ctr, gctr);
+};
+
+// contact record of a winning triangle — CollisionQuery.swift:1165-1190 (re-evaluated by the owner)
+__device__ __forceinline__ void overlap_record(const WorldView &W, uint32_t enc, int gid, f3 from, float radius, float hh,
+                                               cq_overlap_hit &h) {
+    int set = (enc >> 26) & 1, slot = enc & 0x3ffffffu;
+    const SetView &S = W.set[set];
+    uint32_t layer;
+    int triId, part;
+    Tri T = load_tri(S, slot, layer, triId, part);
+    f3 sp, tp;
+    float dist = segment_triangle_distance<true>(from, hh, T, sp, tp);
+    OverlapRec r;
+    overlap_contact(T, dist, sp, tp, radius, r);
+    r.tri = gid;
+    write_overlap(h, r);
 }
 
-// ---------------------------------------------------------------- capsule overlap-all (CollisionQuery.swift:852-882, 1201-1283)
-// Keeps the maxHits deepest (ties: smaller index), emitted deepest first — the order every caller in
-// the reference sorts into anyway (Systems.swift:759).  The reference returns its first maxHits in
-// DFS order; identical whenever <= maxHits triangles overlap, flagged `overflow` otherwise.
-template <bool COUNT>
-__global__ void __launch_bounds__(Q_THREADS) k_capsule_overlap_all(WorldView W, const cq_capsule *__restrict__ q, int n,
-                                                                   int maxHits, cq_overlap_hit *__restrict__ out,
-                                                                   int32_t *__restrict__ counts,
-                                                                   uint8_t *__restrict__ overflow,
-                                                                   unsigned long long *gctr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+template <bool COUNT, bool ALL>
+__global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView W, const cq_capsule *__restrict__ qs, int n,
+                                                                       int maxHits, cq_overlap_hit *__restrict__ out,
+                                                                       int32_t *__restrict__ counts,
+                                                                       uint8_t *__restrict__ overflow, int *workCounter,
+                                                                       unsigned long long *gctr) {
+    __shared__ QShared qsAll[Q_THREADS];
+    __shared__ OvlTop tops[Q_THREADS];
+    __shared__ uint32_t rings[(CQ_QCAP + 2) * CAST_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpPool wp;
+    wp.qs = qsAll + warp * 32;
+    wp.ring = rings + warp * (CQ_QCAP + 2);
+    wp.head = wp.ring + CQ_QCAP;
+    wp.tail = wp.ring + CQ_QCAP + 1;
+    OvlTop &top = tops[threadIdx.x];
     Counters ctr = {0, 0, 0, 0};
-    if (i < n) {
-        cq_capsule c = q[i];
-        OverlapRec top[CQ_MAX_OVERLAP_HITS] = {};
-        int cnt = 0, total = 0;
-        capsule_overlap_visit<COUNT>(W, load3(c.from), c.radius, c.half_height, c.mask, ctr,
-                                     [&](float depth, int gid, int part, const Tri &T, float dist, f3 sp, f3 tp) {
-                                         total++;
-                                         // position of the new record in (depth desc, index asc) order
-                                         int pos = cnt;
-                                         while (pos > 0 && (top[pos - 1].depth < depth ||
-                                                            (top[pos - 1].depth == depth && top[pos - 1].tri > gid)))
-                                             pos--;
-                                         if (pos >= maxHits) return;
-                                         int last = cnt < maxHits ? cnt : maxHits - 1;
-                                         for (int k = last; k > pos; k--) top[k] = top[k - 1];
-                                         overlap_contact(T, dist, sp, tp, c.radius, top[pos]);
-                                         top[pos].tri = gid;
-                                         top[pos].part = part;
-                                         if (cnt < maxHits) cnt++;
-                                     });
-        for (int k = 0; k < maxHits; k++) {
-            cq_overlap_hit h;
-            if (k < cnt) write_overlap(h, top[k]);
-            else write_overlap_nil(h);
-            out[(size_t)i * maxHits + k] = h;
+    int stack[CQ_STACK];
+    int cur = -1;
+    f3 curFrom = {0, 0, 0};
+    float curR = 0.0f, curHH = 0.0f;
+    pool_run<COUNT>(W, wp, lane, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+        if (cur >= 0) { // emit the finished query
+            const int stride = ALL ? maxHits : 1;
+            for (int k = 0; k < stride; k++) {
+                cq_overlap_hit h;
+                if (k < top.count) {
+                    if (COUNT) ct.evals++;
+                    overlap_record(W, top.enc[k], top.gid[k], curFrom, curR, curHH, h);
+                } else {
+                    write_overlap_nil(h);
+                }
+                out[(size_t)cur * stride + k] = h;
+            }
+            if (ALL) {
+                counts[cur] = top.count;
+                if (overflow) overflow[cur] = top.total > maxHits ? 1 : 0;
+            }
         }
-        counts[i] = cnt;
-        if (overflow) overflow[i] = total > maxHits ? 1 : 0;
-    }
+        cur = atomicAdd(workCounter, 1);
+        if (cur >= n) {
+            cur = -1;
+            oq.travDone = true;
+            return false;
+        }
+        cq_capsule c = qs[cur];
+        curFrom = load3(c.from), curR = c.radius, curHH = c.half_height;
+        top.count = 0, top.total = 0, top.cap = ALL ? maxHits : 1;
+        pool_post_overlap<COUNT>(W, mine, oq, stk, curFrom, curR, curHH, c.mask, ct);
+        return true;
+    }, OverlapTopK{tops + warp * 32});
     flush_counters<COUNT>(ctr, gctr);
 }
 
@@ -230,26 +264,39 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }
 
-int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, cudaStream_t st) {
+template <bool ALL>
+static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,
+                               uint8_t *d_overflow, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
+    static int blocksPerSm = 0, numSms = 0;
+    if (!blocksPerSm) {
+        cudaDeviceProp prop;
+        CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
+        numSms = prop.multiProcessorCount;
+        int b = 0;
+        CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_overlap_pool<false, ALL>, Q_THREADS, 0));
+        blocksPerSm = b > 0 ? b : 1;
+    }
+    int blocks = std::min(cdiv(n, Q_THREADS), numSms * blocksPerSm);
+    int *work = next_work_counter(w, st);
+    if (!work) return CQ_ERR_CUDA;
     if (w->counting)
-        k_capsule_overlap<true><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, d_out, w->dCounters);
-    else k_capsule_overlap<false><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, d_out, w->dCounters);
+        k_capsule_overlap_pool<true, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
+                                                                       work, w->dCounters);
+    else
+        k_capsule_overlap_pool<false, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
+                                                                        work, w->dCounters);
     w->launches++;
-    return check_cuda(cudaGetLastError(), "k_capsule_overlap");
+    return check_cuda(cudaGetLastError(), "k_capsule_overlap_pool");
+}
+
+int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, cudaStream_t st) {
+    return launch_overlap_pool<false>(w, d_q, n, 1, d_out, nullptr, nullptr, st);
 }
 
 int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,
                        uint8_t *d_overflow, cudaStream_t st) {
-    if (n <= 0) return CQ_OK;
-    if (w->counting)
-        k_capsule_overlap_all<true><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts,
-                                                                              d_overflow, w->dCounters);
-    else
-        k_capsule_overlap_all<false><<<cdiv(n, Q_THREADS), Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts,
-                                                                               d_overflow, w->dCounters);
-    w->launches++;
-    return check_cuda(cudaGetLastError(), "k_capsule_overlap_all");
+    return launch_overlap_pool<true>(w, d_q, n, maxHits, d_out, d_counts, d_overflow, st);
 }
 
 } // namespace cq
