@@ -464,19 +464,102 @@ def run_c4(args):
     return 0
 
 
+def run_c2(args):
+    """Config C2: 65,536 plain capsuleCast sweeps against the Semla mesh (FBX-regenerated stand-in for the
+    missing Semla.static.json) at its demo placement, every field checked against the oracle."""
+    torch, dist, ws, rank, lrank, dev, tstream, barrier, red = _torch_setup()
+    cq = importlib.import_module("swift-game-engine_b200")
+    cq.build()
+    sc = cq.scenes
+    parts = sc.semla_scene(use_hulls=False)
+    world = cq.CollisionQuery(parts)
+    info = world.info()
+    lo, hi = sc.scene_aabb(parts[1:])
+    n = args.queries
+    q = sc.gen_casts(n, lo, hi, seed=0xC0111DE2 + rank)  # from ~ U(AABB + 3 m), |delta| ~ U[0.05, 2], r=1.5 hh=1.0
+    d_q = torch.from_numpy(q.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_out = torch.empty(n * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=dev)
+    stream = tstream.cuda_stream
+
+    def step():
+        world.capsule_cast_device(d_q.data_ptr(), n, cq.CAST_ALL, d_out.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    world.resetStats()
+    sampler = ClockSampler(lrank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = world.stats()["kernel_launches"]
+    ms = red(e0.elapsed_time(e1), dist.ReduceOp.MAX) / args.steps
+    world.set_counting(True)
+    world.resetStats()
+    step()
+    torch.cuda.synchronize()
+    ctr = world.stats(reset=True)
+    world.set_counting(False)
+    hits = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=cq.CAST_HIT)
+    t0 = time.perf_counter()
+    host_hits = world.capsuleCast(q)
+    e2e_s = time.perf_counter() - t0
+    algo = n * (40 + 44) + 32 * ctr["nodes_visited"] + 52 * ctr["candidates"]
+    peak, peak_src = load_peaks()
+    cpu_baseline, parity = None, None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        cores = os.cpu_count() or 1
+        ow = orc.OracleWorld(parts)
+        ns = min(n, 16384)
+        st = orc.Stats()
+        t0 = time.perf_counter()
+        ref = ow.capsule_cast(q[:ns], 0, orc.ORDER_REFERENCE, cores, st)
+        cdt = time.perf_counter() - t0
+        can = ow.capsule_cast(q[:ns], 0, orc.ORDER_CANONICAL, cores)
+        parity = {"sample": ns, "bit_exact_vs_canonical_oracle": bool(can.tobytes() == hits[:ns].tobytes()),
+                  "toi_equal_vs_reference_order": bool(np.array_equal(ref["toi"], hits["toi"][:ns])),
+                  "index_mismatch_vs_reference_order_all_exact_ties": float((ref["triangle_index"] != hits["triangle_index"][:ns]).mean()),
+                  "reference_distance_evals_per_sweep": st.distance_evals / ns}
+        cpu_baseline = {"value": ns / cdt, "unit": "sweeps/s", "cores": cores, "kind": "port",
+                        "sample": f"first {ns} of {n} sweeps, {cdt:.2f} s wall, reference BVH + DFS order"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "capsule_sweeps_per_sec", "value": n * ws / (ms * 1e-3), "unit": "sweeps/s", "n_gpus": ws,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2: {n} capsuleCast sweeps vs Semla render mesh ({info['n_static_triangles']} tris incl. ground), "
+                                   "r=1.5 hh=1.0, |delta| in [0.05, 2]", "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
+                       "parity": parity, "e2e_matches_device_path": bool(host_hits.tobytes() == hits.tobytes())},
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_capsule_cast", "kernel_ms": ms, "algorithmic_bytes_per_launch": algo,
+                         "per_query": {k: ctr[k] / n for k in ("nodes_visited", "candidates", "distance_evals")},
+                         "fp32_secondary": {"achieved_tflops": 430.0 * ctr["distance_evals"] / (ms * 1e-3) / 1e12,
+                                            "frac": 430.0 * ctr["distance_evals"] / (ms * 1e-3) / 1e12 / 37.22496}},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": n / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": n * 40, "d2h_bytes_per_step": n * 44},
+            "gpu_launches": int(launches), "clocks": clocks}), flush=True)
+    world.close()
+    return 0
+
+
 def run_c5(args):
     """Config C5: batched raycasts + a BVH refit of the spinning (dynamic-set) mirror every step."""
     torch, dist, ws, rank, lrank, dev, tstream, barrier, red = _torch_setup()
     cq = importlib.import_module("swift-game-engine_b200")
     cq.build()
     sc = cq.scenes
-    parts = sc.mirror_scene(use_hulls=False, mirror_dynamic=True)
+    parts = sc.merged_scene(mirror_dynamic=True)  # ground + 17-Cheese + Semla (FBX-regenerated stand-ins) + spinning mirror
     a = sc.load_mirror_fixture()
-    # stand-ins for the two missing assets (17-Cheese, Semla): the mirror mesh again at their demo offsets, static
     base_t, base_q, base_s = sc.transform_from_matrix(sc.mirror_model(a["transform"]))
-    for k, off in enumerate(((18.0, 0.0, 10.0), (10.0, 0.0, -14.0))):
-        parts.append(sc.part(a["positions"], a["indices"], sc.trs_model(base_t + np.float32(off) - np.float32([-10, 1, 4]), base_q, base_s),
-                             layer=1 << 3, entity_id=10 + k))
+    mirror_id = parts[-1]["entity_id"]
     world = cq.CollisionQuery(parts)
     info = world.info()
     lo, hi = sc.scene_aabb(parts[1:])
@@ -490,7 +573,7 @@ def run_c5(args):
     def step():
         angle[0] += 1.0
         rot = sc.quat_mul(sc.quat_angle_axis(np.radians(angle[0]), (0, 1, 0)), base_q)
-        world.update_transforms([1], [sc.trs_model(base_t, rot, base_s)])  # refit (synchronous: returns refit_ms)
+        world.update_transforms([mirror_id], [sc.trs_model(base_t, rot, base_s)])  # refit (synchronous: returns refit_ms)
         world.raycast_device(d_r.data_ptr(), n, d_out.data_ptr(), stream)
 
     for _ in range(args.warmup):
@@ -532,7 +615,7 @@ def run_c5(args):
         ow = orc.OracleWorld(parts)
         rot = sc.quat_mul(sc.quat_angle_axis(np.radians(angle[0]), (0, 1, 0)), base_q)
         t0 = time.perf_counter()
-        ow.update_transforms([1], [sc.trs_model(base_t, rot, base_s)])
+        ow.update_transforms([mirror_id], [sc.trs_model(base_t, rot, base_s)])
         cpu_refit = time.perf_counter() - t0
         ns = min(n, 262144)
         t0 = time.perf_counter()
@@ -550,7 +633,7 @@ def run_c5(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C5: {n} raycasts/GPU + refit of the spinning mirror (dynamic set, "
                                    f"{info['n_dynamic_triangles']} tris) each step; static set {info['n_static_triangles']} tris "
-                                   "(ground + 2 stand-ins for the missing 17-Cheese / Semla assets)",
+                                   "(ground + 17-Cheese + Semla render meshes regenerated from FBX, tools/fbx_to_static_mesh.py)",
                        "refit_ms_mean": float(np.mean(refit_ms)), "raycast_kernel_ms": ray_ms,
                        "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
                        "timing": "host wall clock around (refit + raycast) steps, device synchronised"},
@@ -565,7 +648,7 @@ def run_c5(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--cells", type=int, default=2236)
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--radius", type=float, default=0.4)
@@ -580,6 +663,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "c2":
+        args.queries = args.queries or 65536
+        return run_c2(args)
     if args.workload == "c4":
         args.queries = args.queries or (1 << 23)
         return run_c4(args)

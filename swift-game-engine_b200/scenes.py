@@ -133,6 +133,54 @@ def load_mirror_fixture():
             "positions": z["positions"], "indices": z["indices"].astype(np.uint32), "hulls": hulls}
 
 
+def load_asset_fixture(name):
+    """tests/golden/{semla,cheese}.npz: stand-ins for the reference's missing Semla.static.json / 17-Cheese.static.json,
+    regenerated from the FBX sources by tools/fbx_to_static_mesh.py (render mesh exact up to vertex order and a
+    few quad diagonals; collision hulls are scipy convex-hull stand-ins)."""
+    z = np.load(os.path.join(_GOLDEN, name + ".npz"))
+    hulls = [(z[f"hull{i}_positions"], z[f"hull{i}_indices"].astype(np.uint32)) for i in range(int(z["n_hulls"]))]
+    return {"name": str(z["name"]), "transform": rowmajor_to_colmajor(z["transform_rowmajor"]),
+            "positions": z["positions"], "indices": z["indices"].astype(np.uint32), "hulls": hulls}
+
+
+LAYER_SEMLA = 1 << 3
+
+
+def semla_model(asset_transform):
+    """Demo placement of Semla (DemoScene.swift:217-221): part transform + (18, 0, 10)."""
+    t, q, s = transform_from_matrix(asset_transform)
+    return trs_model(t + np.array([18, 0, 10], f32), q, s)
+
+
+def cheese_model(asset_transform):
+    """Demo placement of 17-Cheese (DemoScene.swift:167-168): the part transform as is."""
+    t, q, s = transform_from_matrix(asset_transform)
+    return trs_model(t, q, s)
+
+
+def semla_scene(use_hulls=False, with_ground=True):
+    """C2 world: Semla at its demo placement (layer 1<<3) + the ground plane."""
+    a = load_asset_fixture("semla")
+    parts = [ground_part(0)] if with_ground else []
+    geoms = a["hulls"] if use_hulls else [(a["positions"], a["indices"])]
+    for k, (v, i) in enumerate(geoms):
+        parts.append(part(v, i, semla_model(a["transform"]), layer=LAYER_SEMLA, mu_s=0.6, mu_k=0.5, entity_id=len(parts)))
+    return parts
+
+
+def merged_scene(mirror_dynamic=True):
+    """C5 world: 17-Cheese + Semla + ornate_mirror render meshes merged at their demo placements (~136k triangles)
+    + the ground plane; the mirror is in the dynamic set so it can spin and be refitted every step."""
+    parts = [ground_part(0)]
+    c, sm, m = load_asset_fixture("cheese"), load_asset_fixture("semla"), load_mirror_fixture()
+    parts.append(part(c["positions"], c["indices"], cheese_model(c["transform"]), mu_s=0.6, mu_k=0.5, entity_id=1))
+    parts.append(part(sm["positions"], sm["indices"], semla_model(sm["transform"]), layer=LAYER_SEMLA, mu_s=0.6, mu_k=0.5,
+                      entity_id=2))
+    parts.append(part(m["positions"], m["indices"], mirror_model(m["transform"]), layer=LAYER_MIRROR, mu_s=0.6, mu_k=0.5,
+                      is_dynamic=mirror_dynamic, entity_id=3))
+    return parts
+
+
 def ground_part(entity_id=0):
     v, i = plane_mesh(80.0)
     return part(v, i, trs_model(translation=(0, GROUND_Y, 0)), layer=LAYER_DEFAULT, mu_s=0.9, mu_k=0.8,

@@ -296,3 +296,48 @@ def test_onesweep_sort_builds_the_same_tree_as_the_classic_sort(cq, orc, scenes,
     assert out["classic"] == out["onesweep"]
     o = orc.OracleWorld(parts)
     assert out["onesweep"][0] == o.capsule_cast(q, 1, orc.ORDER_CANONICAL).tobytes()
+
+
+def test_c2_sweeps_against_semla(cq, orc, scenes):
+    """Config C2 (scaled to 4,096 sweeps for the oracle's sake): plain capsuleCast against the Semla render mesh
+    (50,002 triangles, FBX-regenerated stand-in) at its demo placement."""
+    parts = scenes.semla_scene(use_hulls=False)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    assert g.info()["n_static_triangles"] == o.counts(0)["triangles"] == 50004
+    lo, hi = scenes.scene_aabb(parts[1:])
+    q = scenes.gen_casts(4096, lo, hi, seed=0xC0111DE2)
+    got = g.capsuleCast(q)
+    assert got.tobytes() == o.capsule_cast(q, 0, orc.ORDER_CANONICAL, 8).tobytes()
+    ref = o.capsule_cast(q, 0, orc.ORDER_REFERENCE, 8)
+    assert np.array_equal(got["toi"], ref["toi"]) and np.array_equal(got["triangle_index"] >= 0, ref["triangle_index"] >= 0)
+    assert (got["triangle_index"] >= 0).mean() > 0.4
+    hq = scenes.gen_casts(4096, lo, hi, seed=5)
+    gh, oh = cq.CollisionQuery(scenes.semla_scene(use_hulls=True)), orc.OracleWorld(scenes.semla_scene(use_hulls=True))
+    assert gh.capsuleCastBlocking(hq).tobytes() == oh.capsule_cast(hq, 1, orc.ORDER_CANONICAL).tobytes()
+    for w in (g, o, gh, oh):
+        w.close()
+
+
+def test_c5_merged_scene_rays_and_refit(cq, orc, scenes):
+    """Config C5 scaled down: 17-Cheese + Semla + mirror merged (~132k triangles), the mirror spinning in the
+    dynamic set; after every refit rays and sweeps must still match the oracle."""
+    parts = scenes.merged_scene(mirror_dynamic=True)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    assert g.info()["n_static_triangles"] == o.counts(0)["triangles"] and g.info()["n_dynamic_triangles"] == 14211
+    a = scenes.load_mirror_fixture()
+    t, q0, s = scenes.transform_from_matrix(scenes.mirror_model(a["transform"]))
+    lo, hi = scenes.scene_aabb(parts[1:])
+    rays = scenes.gen_rays(20000, lo, hi, seed=0xC0111DE5, expand=5.0, y_range=(0.0, 12.0))
+    for step in range(1, 3):
+        rot = scenes.quat_mul(scenes.quat_angle_axis(np.radians(float(step)), (0, 1, 0)), q0)
+        model = scenes.trs_model(t, rot, s)
+        g.update_transforms([3], [model])
+        o.update_transforms([3], [model])
+        gr, rr = g.raycast(rays), o.raycast(rays, orc.ORDER_REFERENCE, 8)
+        both = (gr["triangle_index"] >= 0) & (rr["triangle_index"] >= 0)
+        assert (gr["triangle_index"] != rr["triangle_index"]).mean() < 0.002
+        assert (gr["distance"][both] <= rr["distance"][both]).all()
+    qs = scenes.gen_casts(1500, lo, hi, seed=9, expand=1.0)
+    assert g.capsuleCast(qs).tobytes() == o.capsule_cast(qs, 0, orc.ORDER_CANONICAL, 8).tobytes()
+    g.close()
+    o.close()
