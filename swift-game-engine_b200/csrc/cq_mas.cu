@@ -575,7 +575,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
 
 template <bool COUNT>
 __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states, int n,
-                                                                MasArgs A, int *workCounter, unsigned long long *gctr) {
+                                                                MasArgs A, int ownersPerWarp, int *workCounter, unsigned long long *gctr) {
     extern __shared__ __align__(16) unsigned char masSmem[]; // MAS_SMEM_BYTES, dynamic (> 48 KB)
     CharCtx *ctxs = reinterpret_cast<CharCtx *>(masSmem);
     QShared *qsAll = reinterpret_cast<QShared *>(masSmem + sizeof(CharCtx) * MAS_THREADS);
@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
     int stack[CQ_STACK];
-    pool_run<COUNT>(W, wp, lane, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+    pool_run<COUNT>(W, wp, lane, ownersPerWarp, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return mas_advance<COUNT>(c, r, mine, oq, stk, W, A, states, n, workCounter, ct);
@@ -625,8 +625,11 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     int blocks = std::min((n + MAS_THREADS - 1) / MAS_THREADS, numSms * blocksPerSm[ci]);
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
-    if (w->counting) k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, work, w->dCounters);
-    else k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, work, w->dCounters);
+    blocks = std::min((n + 3) / 4, numSms * blocksPerSm[ci]); // small batches: still fill the machine (>= 4 units per CTA)
+    const int opw = pool_owners_per_warp(n, (long long)blocks * MAS_WARPS);
+    if (w->counting)
+        k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, work, w->dCounters);
+    else k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_move_and_slide");
 }

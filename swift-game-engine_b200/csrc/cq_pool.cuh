@@ -389,9 +389,12 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
 // lane's current query is complete (walk finished, no pair pending), consumes the result from `mine`,
 // runs the unit's serial logic and posts the next query (pool_post_*) — or returns false when the lane has
 // no more work units.
+// `ownersPerWarp` (1..32): how many lanes of each warp take the owner role.  Small batches of heavy units
+// use fewer owners per warp so that every owner still processes several units (dynamic fetch then balances
+// the warps against each other) while all 32 lanes keep executing pairs.
 template <bool COUNT, class Advance, class OvlCommit>
-__device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int *stack, Counters &ctr,
-                                         Advance advance, OvlCommit ovl) {
+__device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int ownersPerWarp, int *stack,
+                                         Counters &ctr, Advance advance, OvlCommit ovl) {
     QShared &mine = wp.qs[lane];
     mine.pending = 0;
     mine.rTri = -1;
@@ -405,7 +408,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
     oq.qlo = oq.qhi = mk3(0, 0, 0);
     Job job;
     job.phase = PH_NONE;
-    bool alive = true;
+    bool alive = lane < ownersPerWarp;
     __syncwarp();
     for (uint32_t trip = 0; trip < (1u << 26); trip++) { // (the bound is a watchdog; the loop exits through the vote)
         // Front end (owner role) runs only when the ring cannot feed every idle lane this trip: batching it
@@ -425,6 +428,13 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         pool_commit(wp, job, cm, retired, lane, ovl);
         if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE)) break;
     }
+}
+
+// host side: owners per warp for a batch of n units on `warps` resident warps (aim: >= 4 units per owner)
+static inline int pool_owners_per_warp(long long n, long long warps) {
+    if (n >= warps * 32) return 32;      // at least one unit per lane: every lane owns
+    long long o = n / (warps * 4);       // otherwise aim at >= 4 units per owner
+    return (int)(o < 4 ? 4 : (o > 32 ? 32 : o));
 }
 
 __device__ __forceinline__ void pool_flush_counters(const Counters &c, unsigned long long *g, bool count) {

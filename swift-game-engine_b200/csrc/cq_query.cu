@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 #define CAST_WARPS (Q_THREADS / 32)
 template <bool COUNT>
 __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
-                                                               int mode, cq_cast_hit *__restrict__ out, int *workCounter,
-                                                               unsigned long long *gctr) {
+                                                               int mode, cq_cast_hit *__restrict__ out, int ownersPerWarp,
+                                                               int *workCounter, unsigned long long *gctr) {
     __shared__ QShared qsAll[Q_THREADS];
     __shared__ uint32_t rings[(CQ_QCAP + 2) * CAST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, cons
     Counters ctr = {0, 0, 0, 0};
     int stack[CQ_STACK];
     int cur = -1;
-    pool_run<COUNT>(W, wp, lane, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+    pool_run<COUNT>(W, wp, lane, ownersPerWarp, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
         if (cur >= 0) { // write the finished hit
             cq_cast_hit h;
             if (mine.rTri >= 0) {
@@ -181,8 +181,8 @@ template <bool COUNT, bool ALL>
 __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView W, const cq_capsule *__restrict__ qs, int n,
                                                                        int maxHits, cq_overlap_hit *__restrict__ out,
                                                                        int32_t *__restrict__ counts,
-                                                                       uint8_t *__restrict__ overflow, int *workCounter,
-                                                                       unsigned long long *gctr) {
+                                                                       uint8_t *__restrict__ overflow, int ownersPerWarp,
+                                                                       int *workCounter, unsigned long long *gctr) {
     __shared__ QShared qsAll[Q_THREADS];
     __shared__ OvlTop tops[Q_THREADS];
     __shared__ uint32_t rings[(CQ_QCAP + 2) * CAST_WARPS];
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
     int cur = -1;
     f3 curFrom = {0, 0, 0};
     float curR = 0.0f, curHH = 0.0f;
-    pool_run<COUNT>(W, wp, lane, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+    pool_run<COUNT>(W, wp, lane, ownersPerWarp, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
         if (cur >= 0) { // emit the finished query
             const int stride = ALL ? maxHits : 1;
             for (int k = 0; k < stride; k++) {
@@ -255,11 +255,12 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
         else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_cast<false>, Q_THREADS, 0));
         blocksPerSm[ci] = b > 0 ? b : 1;
     }
-    int blocks = std::min(cdiv(n, Q_THREADS), numSms * blocksPerSm[ci]); // one resident wave of persistent lanes
+    int blocks = std::min(cdiv(n, 4), numSms * blocksPerSm[ci]); // one resident wave of persistent lanes
+    const int opw = pool_owners_per_warp(n, (long long)blocks * CAST_WARPS);
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
-    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, work, w->dCounters);
-    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, work, w->dCounters);
+    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, work, w->dCounters);
+    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }
@@ -277,15 +278,16 @@ static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int ma
         CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_overlap_pool<false, ALL>, Q_THREADS, 0));
         blocksPerSm = b > 0 ? b : 1;
     }
-    int blocks = std::min(cdiv(n, Q_THREADS), numSms * blocksPerSm);
+    int blocks = std::min(cdiv(n, 4), numSms * blocksPerSm);
+    const int opw = pool_owners_per_warp(n, (long long)blocks * CAST_WARPS);
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
     if (w->counting)
         k_capsule_overlap_pool<true, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
-                                                                       work, w->dCounters);
+                                                                       opw, work, w->dCounters);
     else
         k_capsule_overlap_pool<false, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
-                                                                        work, w->dCounters);
+                                                                        opw, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_overlap_pool");
 }
