@@ -42,6 +42,17 @@ int *next_work_counter(cq_world *w, cudaStream_t st) {
     return p;
 }
 
+void *pool_node_scratch(cq_world *w, size_t warps) {
+    ScratchBuf &b = w->nodeScratch[w->nodeSeq++ & 3];
+    size_t bytes = warps * (size_t)2048 /* CQ_NSCAP */ * sizeof(uint2);
+    if (bytes > b.cap) {
+        // growing frees the old block: make sure no launch still uses it
+        if (b.ptr && check_cuda(cudaDeviceSynchronize(), "node scratch sync") != CQ_OK) return nullptr;
+        if (ensure_scratch(b, bytes) != CQ_OK) return nullptr;
+    }
+    return b.ptr;
+}
+
 static void make_view(cq_world *w) {
     for (int s = 0; s < 2; s++) {
         DeviceSet &S = w->set[s];
@@ -256,6 +267,7 @@ void cq_world_destroy(cq_world *w) {
     for (int s = 0; s < 2; s++) free_set(w->set[s]);
     cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork);
     cudaFree(w->in.ptr), cudaFree(w->out.ptr), cudaFree(w->aux.ptr), cudaFree(w->aux2.ptr);
+    for (int k = 0; k < 4; k++) cudaFree(w->nodeScratch[k].ptr);
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);
     if (w->stream) cudaStreamDestroy(w->stream);

@@ -71,6 +71,8 @@ struct cq_world {
     int counting = 0;
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
     uint64_t launches = 0;
+    cq::ScratchBuf nodeScratch[4];
+    uint32_t nodeSeq = 0;
     float hintMas = 0.0f, hintCast = 0.0f; // wall/PCIe ratio of the previous host-pointer call (chunking heuristic)
     int *dWork = nullptr; // ring of dynamic-fetch counters, one per persistent-kernel launch in flight
     uint32_t workSeq = 0;
@@ -96,6 +98,9 @@ int ensure_scratch(ScratchBuf &b, size_t bytes);
 #define CQ_WORK_RING 256
 // zeroed work counter for the next persistent-kernel launch on `st` (nullptr on CUDA error)
 int *next_work_counter(cq_world *w, cudaStream_t st);
+// node-stack scratch for one persistent-kernel launch with `warps` warps (CQ_NSCAP uint2 entries per warp);
+// four regions are used round-robin so that up to four launches may be in flight.  nullptr on CUDA error.
+void *pool_node_scratch(cq_world *w, size_t warps);
 
 // cq_build.cu
 int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,

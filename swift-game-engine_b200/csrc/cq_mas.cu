@@ -24,7 +24,7 @@ namespace cq {
 #endif
 #define MAS_WARPS (MAS_THREADS / 32)
 #define MAS_SMEM_BYTES \
-    (sizeof(CharCtx) * MAS_THREADS + sizeof(QShared) * MAS_THREADS + sizeof(uint32_t) * (CQ_QCAP + 2) * MAS_WARPS)
+    (sizeof(CharCtx) * MAS_THREADS + sizeof(QShared) * MAS_THREADS + sizeof(uint32_t) * CQ_POOL_WORDS * MAS_WARPS)
 
 struct MasArgs {
     cq_controller_params p;
@@ -311,7 +311,7 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
 // Stage L of the move-and-slide kernel: consume the finished query, run the controller logic up to the
 // next query, post it.  Returns false when the lane has no more characters.
 template <bool COUNT>
-__device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShared &s, OwnerQ &oq, int *stack,
+__device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShared &s, const WarpPool &wp, int lane,
                                             const WorldView &W, const MasArgs &A, cq_character_state *states, int n,
                                             int *workCounter, Counters &ctr) {
     const cq_controller_params &P = A.p;
@@ -442,7 +442,6 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             c.charIndex = atomicAdd(workCounter, 1); // dynamic fetch: lanes never wait on a slow neighbour's character
             if (c.charIndex >= n) {
                 c.wait = W_NONE;
-                oq.travDone = true;
                 return false;
             }
             c.st = states + c.charIndex;
@@ -486,7 +485,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             next = NX_DEPEN;
         }
         if (next == NX_DEPEN) {
-            pool_post_overlap<COUNT>(W, s, oq, stack, ld3(c.pos), P.radius, P.half_height, P.collision_mask, ctr);
+            pool_post_overlap<COUNT>(W, wp, lane, s, ld3(c.pos), P.radius, P.half_height, P.collision_mask, ctr);
             c.wait = W_DEPEN;
             return true;
         }
@@ -496,7 +495,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             if (c.slideIt >= P.max_slide_iterations || c.slideLen < 1e-6f) { // SYS:1674-1676
                 next = NX_SNAP;
             } else {
-                pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos), remaining, P.radius, P.half_height, P.collision_mask,
+                pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos), remaining, P.radius, P.half_height, P.collision_mask,
                                     CQ_MODE_BLOCKING, 0.0f, ctr);
                 c.wait = W_SLIDE;
                 return true;
@@ -506,7 +505,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             if (!(P.snap_distance > 0.0f)) { // SYS:845
                 next = NX_FALL;
             } else {
-                pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos), down * P.snap_distance, P.radius, P.half_height,
+                pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos), down * P.snap_distance, P.radius, P.half_height,
                                     P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
                 c.wait = W_SNAP;
                 return true;
@@ -516,7 +515,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             if (!(P.fall_probe_distance > 0.0f)) { // SYS:855
                 next = NX_GATE;
             } else {
-                pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos), down * P.fall_probe_distance, P.radius, P.half_height,
+                pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos), down * P.fall_probe_distance, P.radius, P.half_height,
                                     P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
                 c.wait = W_FALL;
                 return true;
@@ -561,7 +560,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             int oi = c.offsetIt;
             float ox = oi == 0 ? offset : (oi == 1 ? -offset : 0.0f);
             float oz = oi == 2 ? offset : (oi == 3 ? -offset : 0.0f);
-            pool_post_cast<COUNT>(W, s, oq, stack, ld3(c.pos) + mk3(ox, 0.0f, oz), down * P.snap_distance, P.radius, P.half_height,
+            pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos) + mk3(ox, 0.0f, oz), down * P.snap_distance, P.radius, P.half_height,
                                 P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
             c.wait = W_OFFSET;
             return true;
@@ -574,28 +573,26 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states, int n,
-                                                                MasArgs A, int ownersPerWarp, int *workCounter, unsigned long long *gctr) {
-    extern __shared__ __align__(16) unsigned char masSmem[]; // MAS_SMEM_BYTES, dynamic (> 48 KB)
+__global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states,
+                                                                                int n, MasArgs A, int ownersPerWarp,
+                                                                                uint2 *nodeScratch, int *workCounter,
+                                                                                unsigned long long *gctr) {
+    extern __shared__ __align__(16) unsigned char masSmem[]; // MAS_SMEM_BYTES, dynamic
     CharCtx *ctxs = reinterpret_cast<CharCtx *>(masSmem);
     QShared *qsAll = reinterpret_cast<QShared *>(masSmem + sizeof(CharCtx) * MAS_THREADS);
-    uint32_t *rings = reinterpret_cast<uint32_t *>(masSmem + (sizeof(CharCtx) + sizeof(QShared)) * MAS_THREADS);
+    uint32_t *words = reinterpret_cast<uint32_t *>(masSmem + (sizeof(CharCtx) + sizeof(QShared)) * MAS_THREADS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpPool wp;
-    wp.qs = qsAll + warp * 32;
-    wp.ring = rings + warp * (CQ_QCAP + 2);
-    wp.head = wp.ring + CQ_QCAP;
-    wp.tail = wp.ring + CQ_QCAP + 1;
+    pool_bind(wp, qsAll, words, nodeScratch, warp, MAS_WARPS);
     CharCtx &c = ctxs[threadIdx.x];
     c.charIndex = -1;
     c.wait = W_NONE;
     c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
-    int stack[CQ_STACK];
-    pool_run<COUNT>(W, wp, lane, ownersPerWarp, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+    pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
-        return mas_advance<COUNT>(c, r, mine, oq, stk, W, A, states, n, workCounter, ct);
+        return mas_advance<COUNT>(c, r, mine, wp, lane, W, A, states, n, workCounter, ct);
     }, OverlapTop2());
     pool_flush_counters(ctr, gctr, COUNT);
 }
@@ -627,9 +624,11 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     if (!work) return CQ_ERR_CUDA;
     blocks = std::min((n + 3) / 4, numSms * blocksPerSm[ci]); // small batches: still fill the machine (>= 4 units per CTA)
     const int opw = pool_owners_per_warp(n, (long long)blocks * MAS_WARPS);
+    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * MAS_WARPS);
+    if (!ns) return CQ_ERR_CUDA;
     if (w->counting)
-        k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, work, w->dCounters);
-    else k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, work, w->dCounters);
+        k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, w->dCounters);
+    else k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_move_and_slide");
 }

@@ -28,27 +28,23 @@ namespace cq {
 
 enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #define CQ_KIND_OVERLAP 3 /* query mode: two-deepest overlap (move-and-slide depenetration) */
-#define CQ_QCAP 128       /* ring entries per warp */
+#define CQ_QCAP 256       /* pair-ring entries per warp */
+#define CQ_NSCAP 2048     /* node-stack entries per warp (global memory; 32 concurrent walks x depth <= 64) */
 
 struct QShared { // one per owner lane, shared memory: what executors need + the query's result
     float from[3], dir[3], delta[3];
     float L, radius, hh, minNormalY, minAdvance;
     int maxIter, mode;
+    float qlo[3], qhi[3]; // the query's (swept) AABB: node / triangle boxes are tested against it
+    uint32_t mask;
     // result.  cast: rT/rTri/rPart + contact.  overlap: two deepest, d0=rT t0=rTri n0=rN | d1=rPos[0] t1=rPart n1=rTriN
     float rT;
     int rTri, rPart;
     float rPos[3], rN[3], rTriN[3];
-    int pending; // pairs pushed and not yet retired
+    int pending; // stack entries + pairs pushed for this query and not yet consumed; 0 = query complete
 };
 
-struct OwnerQ { // owner-side traversal cursor (registers)
-    f3 qlo, qhi;
-    uint32_t mask;
-    int sp, set, leafPos, leafEnd;
-    bool travDone;
-};
-
-struct QResult { // what owner logic reads back (same names as the engine's result fields)
+struct QResult { // what owner logic reads back
     float bestT;
     int bestTri, bestPart;
     f3 bestPos, bestN, bestTriN;
@@ -72,12 +68,25 @@ struct Commit { // a finished pair's contribution, applied in the serialized com
     f3 pos, n, triN;
 };
 
-struct WarpPool { // per-warp shared-memory handles
-    QShared *qs;             // [32]
-    uint32_t *ring;          // [CQ_QCAP]
-    volatile uint32_t *head; // consumed
-    volatile uint32_t *tail; // produced
+struct WarpPool { // per-warp handles
+    QShared *qs;             // [32]                shared
+    uint32_t *ring;          // [CQ_QCAP] pairs     shared
+    volatile uint32_t *head; // pairs consumed      shared
+    volatile uint32_t *tail; // pairs produced      shared
+    volatile uint32_t *ntop; // node-stack height   shared
+    uint2 *nstack;           // [CQ_NSCAP] (owner<<2 | set<<1 | isLeaf, ref)   global (L2 resident)
 };
+#define CQ_POOL_WORDS (CQ_QCAP + 3) /* shared words per warp besides QShared */
+
+__device__ __forceinline__ void pool_bind(WarpPool &wp, QShared *qsAll, uint32_t *words, uint2 *nodeScratch, int warp,
+                                          int warpsPerBlock) {
+    wp.qs = qsAll + warp * 32;
+    wp.ring = words + warp * CQ_POOL_WORDS;
+    wp.head = wp.ring + CQ_QCAP;
+    wp.tail = wp.ring + CQ_QCAP + 1;
+    wp.ntop = wp.ring + CQ_QCAP + 2;
+    wp.nstack = nodeScratch + ((size_t)blockIdx.x * warpsPerBlock + warp) * CQ_NSCAP;
+}
 
 __device__ __forceinline__ void pool_read_result(const QShared &s, QResult &r) {
     r.bestT = s.rT;
@@ -88,41 +97,45 @@ __device__ __forceinline__ void pool_read_result(const QShared &s, QResult &r) {
     r.bestTriN = mk3(s.rTriN[0], s.rTriN[1], s.rTriN[2]);
 }
 
-__device__ __forceinline__ void pool_push_root(const WorldView &W, OwnerQ &oq, int *stack, Counters &ctr, bool count) {
-    const SetHeader *hp = oq.set ? W.set[1].hdr : W.set[0].hdr;
-    SetHeader h = *hp;
-    oq.sp = 0;
-    if (h.rootRef == CQ_REF_EMPTY) return;
-    if (count) {
-        ctr.queries++;
-        ctr.nodes++;
-    }
-    if (box_disjoint(mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), oq.qlo, oq.qhi)) return;
-    stack[oq.sp++] = h.rootRef;
-}
-
 __device__ __forceinline__ void store3s(float *o, f3 v) {
     o[0] = v.x;
     o[1] = v.y;
     o[2] = v.z;
 }
 
+// push the roots of both triangle sets (static first, CollisionQuery.swift:990-1008) onto the warp's node stack
+__device__ __forceinline__ void pool_push_roots(const WorldView &W, const WarpPool &wp, int lane, QShared &s, f3 qlo, f3 qhi,
+                                                Counters &ctr, bool count) {
+    int pushed = 0;
+#pragma unroll 1
+    for (int set = 0; set < 2; set++) {
+        SetHeader h = *(set ? W.set[1].hdr : W.set[0].hdr);
+        if (h.rootRef == CQ_REF_EMPTY) continue;
+        if (count) {
+            ctr.queries++;
+            ctr.nodes++;
+        }
+        if (box_disjoint(mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), qlo, qhi)) continue;
+        bool leaf = h.rootRef < 0;
+        uint32_t pos = atomicAdd((uint32_t *)wp.ntop, 1u);
+        wp.nstack[pos] = make_uint2(((uint32_t)lane << 2) | ((uint32_t)set << 1) | (leaf ? 1u : 0u),
+                                    (uint32_t)(leaf ? ~h.rootRef : h.rootRef));
+        pushed++;
+    }
+    s.pending = pushed;
+}
+
 // capsuleCastCombined prologue — CollisionQuery.swift:980-1043
 template <bool COUNT>
-__device__ __forceinline__ void pool_post_cast(const WorldView &W, QShared &s, OwnerQ &oq, int *stack, f3 from, f3 delta,
+__device__ __forceinline__ void pool_post_cast(const WorldView &W, const WarpPool &wp, int lane, QShared &s, f3 from, f3 delta,
                                                float radius, float hh, uint32_t mask, int mode, float minNormalY,
                                                Counters &ctr) {
     s.rTri = -1;
     s.rPart = -1;
     s.pending = 0;
     s.mode = mode;
-    oq.leafPos = oq.leafEnd = 0;
-    oq.sp = 0;
     float L = len(delta);
-    if (L < 1e-6f) { // nil without any traversal (:988)
-        oq.travDone = true;
-        return;
-    }
+    if (L < 1e-6f) return; // nil without any traversal (:988)
     f3 dir = delta / L;
     float minAdvance = smax(radius * 0.02f, 1e-4f); // :1295
     store3s(s.from, from);
@@ -139,19 +152,18 @@ __device__ __forceinline__ void pool_post_cast(const WorldView &W, QShared &s, O
     f3 a0 = from + up * hh, b0 = from - up * hh;
     f3 a1 = a0 + delta, b1 = b0 + delta;
     f3 ext = {radius, radius, radius};
-    oq.qlo = vmin(vmin(a0, b0), vmin(a1, b1)) - ext;
-    oq.qhi = vmax(vmax(a0, b0), vmax(a1, b1)) + ext;
-    oq.mask = mask;
-    oq.set = 0;
-    oq.travDone = false;
-    pool_push_root(W, oq, stack, ctr, COUNT);
+    f3 qlo = vmin(vmin(a0, b0), vmin(a1, b1)) - ext;
+    f3 qhi = vmax(vmax(a0, b0), vmax(a1, b1)) + ext;
+    store3s(s.qlo, qlo);
+    store3s(s.qhi, qhi);
+    s.mask = mask;
+    pool_push_roots(W, wp, lane, s, qlo, qhi, ctr, COUNT);
 }
 
 // capsuleOverlapAll prologue — CollisionQuery.swift:1209-1216 (two deepest kept, Systems.swift:764-767)
 template <bool COUNT>
-__device__ __forceinline__ void pool_post_overlap(const WorldView &W, QShared &s, OwnerQ &oq, int *stack, f3 from,
+__device__ __forceinline__ void pool_post_overlap(const WorldView &W, const WarpPool &wp, int lane, QShared &s, f3 from,
                                                   float radius, float hh, uint32_t mask, Counters &ctr) {
-    s.pending = 0;
     s.mode = CQ_KIND_OVERLAP;
     store3s(s.from, from);
     store3s(s.dir, mk3(0, 0, 0));
@@ -162,56 +174,75 @@ __device__ __forceinline__ void pool_post_overlap(const WorldView &W, QShared &s
     s.maxIter = 1;
     s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));         // deepest
     s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0)); // second deepest
-    overlap_box(from, radius, hh, oq.qlo, oq.qhi);
-    oq.mask = mask;
-    oq.leafPos = oq.leafEnd = 0;
-    oq.set = 0;
-    oq.travDone = false;
-    pool_push_root(W, oq, stack, ctr, COUNT);
+    f3 qlo, qhi;
+    overlap_box(from, radius, hh, qlo, qhi);
+    store3s(s.qlo, qlo);
+    store3s(s.qhi, qhi);
+    s.mask = mask;
+    pool_push_roots(W, wp, lane, s, qlo, qhi, ctr, COUNT);
 }
 
-// owner traversal: walk the LBVH and push candidate pairs while the ring has room
+// Cooperative LBVH walk: all 32 lanes pop one stack entry each (any owner's), test it against that owner's
+// query box, and push what survives — internal children / leaf ranges back on the stack, candidate triangles
+// (layer mask + triangle AABB passed, CollisionQuery.swift:1057-1065) into the pair ring.  One round of the walk
+// for the whole warp costs what one step of a single lane's walk used to cost.
 template <bool COUNT>
-__device__ __forceinline__ void pool_traverse_push(const WorldView &W, const WarpPool &wp, QShared &s, OwnerQ &oq, int *stack,
-                                                   int lane, Counters &ctr) {
-    int pushed = 0;
-    while (!oq.travDone) {
-        if (oq.leafPos < oq.leafEnd) {
-            if (*wp.tail - *wp.head > CQ_QCAP - 33u) break; // ring (nearly) full: resume next trip
-            int slot = oq.leafPos++;
-            const float4 *p0 = oq.set ? W.set[1].tv0 : W.set[0].tv0;
-            const float4 *p1 = oq.set ? W.set[1].tv1 : W.set[0].tv1;
-            const float4 *p2 = oq.set ? W.set[1].tv2 : W.set[0].tv2;
-            float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
-            if ((__float_as_uint(a.w) & oq.mask) == 0u) continue; // layer mask, CollisionQuery.swift:1057
-            f3 v0 = xyz(a), v1 = xyz(b), v2 = xyz(c);
-            f3 tlo = vmin(v0, vmin(v1, v2)), thi = vmax(v0, vmax(v1, v2));
-            if (box_disjoint(tlo, thi, oq.qlo, oq.qhi)) continue; // :1060-1065
-            if (COUNT) ctr.cands++;
-            uint32_t pos = atomicAdd((uint32_t *)wp.tail, 1u);
-            wp.ring[pos % CQ_QCAP] = ((uint32_t)lane << 27) | ((uint32_t)oq.set << 26) | (uint32_t)slot;
-            pushed++;
-        } else if (oq.sp > 0) {
-            int ref = stack[--oq.sp];
-            if (ref < 0) {
-                int enc = ~ref;
-                oq.leafPos = enc >> 2;
-                oq.leafEnd = oq.leafPos + (enc & 3) + 1;
-            } else {
-                const Node *n = (oq.set ? W.set[1].nodes : W.set[0].nodes) + ref;
-                float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
-                if (COUNT) ctr.nodes += 2;
-                if (!box_disjoint(xyz(n2), xyz(n3), oq.qlo, oq.qhi)) stack[oq.sp++] = __float_as_int(n1.w);
-                if (!box_disjoint(xyz(n0), xyz(n1), oq.qlo, oq.qhi)) stack[oq.sp++] = __float_as_int(n0.w);
+__device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPool &wp, int lane, Counters &ctr) {
+    const uint32_t top = *wp.ntop;
+    const uint32_t poppers = (top + 96u > (uint32_t)CQ_NSCAP) ? 1u : 32u; // nearly full: depth-first with one lane
+    const uint32_t k = min(top, poppers);
+    uint2 e = make_uint2(0u, 0u);
+    const bool have = (uint32_t)lane < k;
+    if (have) e = wp.nstack[top - 1u - (uint32_t)lane];
+    __syncwarp();
+    if (lane == 0) *wp.ntop = top - k;
+    __syncwarp();
+    if (have) {
+        const int owner = e.x >> 2, set = (e.x >> 1) & 1;
+        QShared &s = wp.qs[owner];
+        const f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
+        int net = -1; // this entry is consumed
+        if ((e.x & 1u) == 0u) { // internal node: test both children
+            const Node *n = (set ? W.set[1].nodes : W.set[0].nodes) + e.y;
+            float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
+            if (COUNT) ctr.nodes += 2;
+            bool h0 = !box_disjoint(xyz(n0), xyz(n1), qlo, qhi), h1 = !box_disjoint(xyz(n2), xyz(n3), qlo, qhi);
+            int cnt = (h0 ? 1 : 0) + (h1 ? 1 : 0);
+            if (cnt) {
+                uint32_t pos = atomicAdd((uint32_t *)wp.ntop, (uint32_t)cnt);
+                if (h0) {
+                    int r = __float_as_int(n0.w);
+                    wp.nstack[pos++] = make_uint2((e.x & ~1u) | (r < 0 ? 1u : 0u), (uint32_t)(r < 0 ? ~r : r));
+                }
+                if (h1) {
+                    int r = __float_as_int(n1.w);
+                    wp.nstack[pos] = make_uint2((e.x & ~1u) | (r < 0 ? 1u : 0u), (uint32_t)(r < 0 ? ~r : r));
+                }
+                net += cnt;
             }
-        } else if (oq.set == 0) {
-            oq.set = 1; // static set done -> dynamic set (CollisionQuery.swift:990-1008)
-            pool_push_root(W, oq, stack, ctr, COUNT);
-        } else {
-            oq.travDone = true;
+        } else { // leaf range: 1..4 consecutive triangles of the sorted SoA
+            const int start = (int)(e.y >> 2), count = (int)(e.y & 3u) + 1;
+            const uint32_t mask = s.mask;
+            const float4 *p0 = set ? W.set[1].tv0 : W.set[0].tv0;
+            const float4 *p1 = set ? W.set[1].tv1 : W.set[0].tv1;
+            const float4 *p2 = set ? W.set[1].tv2 : W.set[0].tv2;
+#pragma unroll 1
+            for (int i = 0; i < count; i++) {
+                const int slot = start + i;
+                float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
+                if ((__float_as_uint(a.w) & mask) == 0u) continue; // layer mask, CollisionQuery.swift:1057
+                f3 v0 = xyz(a), v1 = xyz(b), v2 = xyz(c);
+                f3 tlo = vmin(v0, vmin(v1, v2)), thi = vmax(v0, vmax(v1, v2));
+                if (box_disjoint(tlo, thi, qlo, qhi)) continue; // :1060-1065
+                if (COUNT) ctr.cands++;
+                uint32_t pos = atomicAdd((uint32_t *)wp.tail, 1u);
+                wp.ring[pos % CQ_QCAP] = ((uint32_t)owner << 27) | ((uint32_t)set << 26) | (uint32_t)slot;
+                net++;
+            }
         }
+        if (net) atomicAdd(&s.pending, net);
     }
-    if (pushed) atomicAdd(&s.pending, pushed);
+    __syncwarp();
 }
 
 // job pickup: idle lanes take ring entries, ranked by ballot
@@ -385,39 +416,37 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
     __syncwarp();
 }
 
-// The warp's main loop.  `advance(mine, oq, stack, ctr)` is the owner-role callback: it is invoked when the
-// lane's current query is complete (walk finished, no pair pending), consumes the result from `mine`,
-// runs the unit's serial logic and posts the next query (pool_post_*) — or returns false when the lane has
-// no more work units.
+// The warp's main loop.  `advance(mine, ctr)` is the owner-role callback: it is invoked when the lane's
+// current query is complete (pending == 0), consumes the result from `mine`, runs the unit's serial logic and
+// posts the next query (pool_post_*) — or returns false when the lane has no more work units.
 // `ownersPerWarp` (1..32): how many lanes of each warp take the owner role.  Small batches of heavy units
 // use fewer owners per warp so that every owner still processes several units (dynamic fetch then balances
 // the warps against each other) while all 32 lanes keep executing pairs.
 template <bool COUNT, class Advance, class OvlCommit>
-__device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int ownersPerWarp, int *stack,
-                                         Counters &ctr, Advance advance, OvlCommit ovl) {
+__device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int ownersPerWarp, Counters &ctr,
+                                         Advance advance, OvlCommit ovl) {
     QShared &mine = wp.qs[lane];
     mine.pending = 0;
     mine.rTri = -1;
     if (lane == 0) {
         *wp.head = 0;
         *wp.tail = 0;
+        *wp.ntop = 0;
     }
-    OwnerQ oq;
-    oq.travDone = true;
-    oq.sp = 0, oq.set = 1, oq.leafPos = oq.leafEnd = 0, oq.mask = 0;
-    oq.qlo = oq.qhi = mk3(0, 0, 0);
     Job job;
     job.phase = PH_NONE;
     bool alive = lane < ownersPerWarp;
     __syncwarp();
     for (uint32_t trip = 0; trip < (1u << 26); trip++) { // (the bound is a watchdog; the loop exits through the vote)
-        // Front end (owner role) runs only when the ring cannot feed every idle lane this trip: batching it
-        // makes the divergent unit logic / BVH walk run with many owners at once instead of 2-3.
-        const uint32_t idleNow = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
-        if (*wp.tail - *wp.head < (uint32_t)__popc(idleNow)) {
-            if (alive && oq.travDone && *(volatile int *)&mine.pending == 0) alive = advance(mine, oq, stack, ctr);
-            if (!oq.travDone) pool_traverse_push<COUNT>(W, wp, mine, oq, stack, lane, ctr);
+        // Front end runs only when the pair ring cannot feed every idle lane this trip: batching it makes the
+        // divergent unit logic run with many owners at once, and the LBVH walk is warp-cooperative anyway.
+        const uint32_t idleNow = (uint32_t)__popc(__ballot_sync(0xffffffffu, job.phase == PH_NONE));
+        if (*wp.tail - *wp.head < idleNow) {
+            if (alive && *(volatile int *)&mine.pending == 0) alive = advance(mine, ctr);
             __syncwarp();
+            // cooperative walk: rounds until the ring holds ~3 trips of work (or the stack is empty)
+            while (*wp.ntop != 0u && *wp.tail - *wp.head < 96u && *wp.tail - *wp.head + 128u <= (uint32_t)CQ_QCAP)
+                pool_walk_round<COUNT>(W, wp, lane, ctr);
         }
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
         pool_take_jobs(W, wp, job, lane);
@@ -426,7 +455,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         bool retired = false;
         if (job.phase != PH_NONE) pool_eval<COUNT>(job, wp, cm, retired, ctr);
         pool_commit(wp, job, cm, retired, lane, ovl);
-        if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE)) break;
+        if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE) && *wp.ntop == 0u && *wp.tail == *wp.head) break;
     }
 }
 

@@ -64,19 +64,16 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 template <bool COUNT>
 __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
                                                                int mode, cq_cast_hit *__restrict__ out, int ownersPerWarp,
-                                                               int *workCounter, unsigned long long *gctr) {
+                                                               uint2 *nodeScratch, int *workCounter,
+                                                               unsigned long long *gctr) {
     __shared__ QShared qsAll[Q_THREADS];
-    __shared__ uint32_t rings[(CQ_QCAP + 2) * CAST_WARPS];
+    __shared__ uint32_t words[CQ_POOL_WORDS * CAST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpPool wp;
-    wp.qs = qsAll + warp * 32;
-    wp.ring = rings + warp * (CQ_QCAP + 2);
-    wp.head = wp.ring + CQ_QCAP;
-    wp.tail = wp.ring + CQ_QCAP + 1;
+    pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS);
     Counters ctr = {0, 0, 0, 0};
-    int stack[CQ_STACK];
     int cur = -1;
-    pool_run<COUNT>(W, wp, lane, ownersPerWarp, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+    pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         if (cur >= 0) { // write the finished hit
             cq_cast_hit h;
             if (mine.rTri >= 0) {
@@ -97,11 +94,10 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, cons
         cur = atomicAdd(workCounter, 1); // dynamic fetch of the next sweep
         if (cur >= n) {
             cur = -1;
-            oq.travDone = true;
             return false;
         }
         cq_capsule_cast c = qs[cur];
-        pool_post_cast<COUNT>(W, mine, oq, stk, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
+        pool_post_cast<COUNT>(W, wp, lane, mine, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
                               c.min_normal_y, ct);
         return true;
     }, OverlapTop2());
@@ -182,23 +178,20 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
                                                                        int maxHits, cq_overlap_hit *__restrict__ out,
                                                                        int32_t *__restrict__ counts,
                                                                        uint8_t *__restrict__ overflow, int ownersPerWarp,
-                                                                       int *workCounter, unsigned long long *gctr) {
+                                                                       uint2 *nodeScratch, int *workCounter,
+                                                                       unsigned long long *gctr) {
     __shared__ QShared qsAll[Q_THREADS];
     __shared__ OvlTop tops[Q_THREADS];
-    __shared__ uint32_t rings[(CQ_QCAP + 2) * CAST_WARPS];
+    __shared__ uint32_t words[CQ_POOL_WORDS * CAST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpPool wp;
-    wp.qs = qsAll + warp * 32;
-    wp.ring = rings + warp * (CQ_QCAP + 2);
-    wp.head = wp.ring + CQ_QCAP;
-    wp.tail = wp.ring + CQ_QCAP + 1;
+    pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS);
     OvlTop &top = tops[threadIdx.x];
     Counters ctr = {0, 0, 0, 0};
-    int stack[CQ_STACK];
     int cur = -1;
     f3 curFrom = {0, 0, 0};
     float curR = 0.0f, curHH = 0.0f;
-    pool_run<COUNT>(W, wp, lane, ownersPerWarp, stack, ctr, [&](QShared &mine, OwnerQ &oq, int *stk, Counters &ct) {
+    pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         if (cur >= 0) { // emit the finished query
             const int stride = ALL ? maxHits : 1;
             for (int k = 0; k < stride; k++) {
@@ -219,13 +212,12 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
         cur = atomicAdd(workCounter, 1);
         if (cur >= n) {
             cur = -1;
-            oq.travDone = true;
             return false;
         }
         cq_capsule c = qs[cur];
         curFrom = load3(c.from), curR = c.radius, curHH = c.half_height;
         top.count = 0, top.total = 0, top.cap = ALL ? maxHits : 1;
-        pool_post_overlap<COUNT>(W, mine, oq, stk, curFrom, curR, curHH, c.mask, ct);
+        pool_post_overlap<COUNT>(W, wp, lane, mine, curFrom, curR, curHH, c.mask, ct);
         return true;
     }, OverlapTopK{tops + warp * 32});
     flush_counters<COUNT>(ctr, gctr);
@@ -259,8 +251,10 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
     const int opw = pool_owners_per_warp(n, (long long)blocks * CAST_WARPS);
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
-    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, work, w->dCounters);
-    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, work, w->dCounters);
+    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS);
+    if (!ns) return CQ_ERR_CUDA;
+    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, w->dCounters);
+    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }
@@ -282,12 +276,14 @@ static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int ma
     const int opw = pool_owners_per_warp(n, (long long)blocks * CAST_WARPS);
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
+    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS);
+    if (!ns) return CQ_ERR_CUDA;
     if (w->counting)
         k_capsule_overlap_pool<true, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
-                                                                       opw, work, w->dCounters);
+                                                                       opw, ns, work, w->dCounters);
     else
         k_capsule_overlap_pool<false, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
-                                                                        opw, work, w->dCounters);
+                                                                        opw, ns, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_overlap_pool");
 }
