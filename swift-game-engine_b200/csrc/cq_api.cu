@@ -43,14 +43,15 @@ int *next_work_counter(cq_world *w, cudaStream_t st) {
 }
 
 void *pool_node_scratch(cq_world *w, size_t warps) {
-    ScratchBuf &b = w->nodeScratch[w->nodeSeq++ & 3];
     size_t bytes = warps * (size_t)2048 /* CQ_NSCAP */ * sizeof(uint2);
-    if (bytes > b.cap) {
-        // growing frees the old block: make sure no launch still uses it
-        if (b.ptr && check_cuda(cudaDeviceSynchronize(), "node scratch sync") != CQ_OK) return nullptr;
-        if (ensure_scratch(b, bytes) != CQ_OK) return nullptr;
+    if (bytes > w->nodeScratch[0].cap) {
+        // grow all four regions at once (a cudaMalloc inside a timed step costs milliseconds); growing frees the
+        // old blocks, so make sure no launch still uses them
+        if (check_cuda(cudaDeviceSynchronize(), "node scratch sync") != CQ_OK) return nullptr;
+        for (int k = 0; k < 4; k++)
+            if (ensure_scratch(w->nodeScratch[k], bytes) != CQ_OK) return nullptr;
     }
-    return b.ptr;
+    return w->nodeScratch[w->nodeSeq++ & 3].ptr;
 }
 
 static void make_view(cq_world *w) {
