@@ -341,3 +341,46 @@ def test_c5_merged_scene_rays_and_refit(cq, orc, scenes):
     assert g.capsuleCast(qs).tobytes() == o.capsule_cast(qs, 0, orc.ORDER_CANONICAL, 8).tobytes()
     g.close()
     o.close()
+
+
+def test_c1_trajectory_matches_golden(cq, scenes):
+    """Config C1 on the GPU: 4 characters driven for 600 fixed steps over the demo's static world must reproduce
+    the committed golden trajectory (tests/golden/c1_trajectory.npz, canonical order) bit for bit."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_trajectory.npz"))
+    g = cq.CollisionQuery(scenes.c1_scene())
+    s = cq.init_states(scenes.C1_STARTS)
+    p = cq.default_params()
+    rec = scenes.c1_run(lambda st: g.move_and_slide(st, p), s, 600, scenes.C1_SPEEDS)
+    for k in rec.dtype.names:
+        assert np.array_equal(rec[k], z[f"canonical_{k}"]), k
+    g.close()
+
+
+def test_parameter_edge_cases(cq, orc, scenes):
+    """Sphere (halfHeight 0), tiny radius (minAdvance floor 1e-4), one slide iteration, no snap / no fall probe,
+    layer masks, overlap-all overflow flag."""
+    parts = scenes.mirror_scene(use_hulls=True)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    lo, hi = scenes.scene_aabb(parts[1:])
+    for r, hh in ((0.5, 0.0), (0.003, 0.2), (3.0, 2.0)):
+        q = scenes.gen_casts(3000, lo, hi, seed=int(r * 1000), radius=r, half_height=hh, len_range=(0.001, 1.0))
+        for mode in (0, 1, 2):
+            got = [g.capsuleCast, g.capsuleCastBlocking, g.capsuleCastGround][mode](q)
+            assert got.tobytes() == o.capsule_cast(q, mode, orc.ORDER_CANONICAL).tobytes(), (r, hh, mode)
+    pos, vel = scenes.gen_c3_characters(1024, seed=5)
+    for kw in (dict(max_slide_iterations=1), dict(snap_distance=0.0), dict(fall_probe_distance=0.0),
+               dict(collision_mask=1), dict(collision_mask=1 << 4), dict(skin_width=0.0, ground_snap_skin=0.0)):
+        sg, so = cq.init_states(pos, vel), orc.init_states(pos, vel)
+        for _ in range(3):
+            g.move_and_slide(sg, cq.default_params(**kw))
+            o.move_and_slide(so, orc.default_params(**kw), order=orc.ORDER_CANONICAL)
+        assert sg.tobytes() == so.tobytes(), kw
+    rparts = scenes.mirror_scene(use_hulls=False)
+    gr, orr = cq.CollisionQuery(rparts), orc.OracleWorld(rparts)
+    c = scenes.gen_capsules(2000, lo, hi, seed=8, expand=0.2)
+    got, cnt, ov = gr.capsuleOverlapAll(c, 8)
+    ref, rcnt, rov = orr.capsule_overlap_all(c, 8, orc.ORDER_CANONICAL)
+    assert ov.sum() > 100 and np.array_equal(ov, rov) and np.array_equal(cnt, rcnt) and got.tobytes() == ref.tobytes()
+    for w in (g, o, gr, orr):
+        w.close()
