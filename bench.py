@@ -102,13 +102,32 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+TERRAIN_PARAMS = dict(radius=0.4, half_height=0.5, skin_width=0.08)  # human-scale capsule
+
+
 def make_workload(cq, mesh, n, rank):
+    if mesh == "terrain":  # the north-star target scene: 10 M-triangle procedural terrain, walkers all over it
+        parts, half = cq.scenes.terrain_scene(cells=2236, cell=2.0)
+        rng = np.random.default_rng(SEED + 77 + rank)
+        x = rng.uniform(-half + 10, half - 10, (n, 2))
+        y = cq.scenes.terrain_height(x[:, 0], x[:, 1]) + np.float32(0.9 + 0.2)
+        pos = np.stack([x[:, 0], y, x[:, 1]], axis=1).astype(np.float32)
+        heading, speed = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 4.5, n)
+        vel = np.stack([np.cos(heading) * speed, np.zeros(n), np.sin(heading) * speed], axis=1).astype(np.float32)
+        return parts, pos, vel
     parts = cq.scenes.mirror_scene(use_hulls=(mesh == "hulls"))
     pos, vel = cq.scenes.gen_c3_characters(n, seed=SEED + rank)
     return parts, pos, vel
 
 
+def controller_params(mod, mesh):
+    return mod.default_params(**TERRAIN_PARAMS) if mesh == "terrain" else mod.default_params()
+
+
 def workload_name(mesh, n):
+    if mesh == "terrain":
+        return (f"target scene: {n} characters/GPU x 1 move-and-slide fixed step over the procedural terrain of "
+                "9,999,392 triangles (cell 2 m), human-scale controller r=0.4 hh=0.5 skin 0.08, dt=1/60, gravity on")
     tri = "2 collision hulls (76 tris) + ground plane (2 tris)" if mesh == "hulls" else \
         "render mesh (14,211 tris after the area filter) + ground plane (2 tris)"
     return (f"C3: {n} characters/GPU x 1 move-and-slide fixed step (<=4 slide casts + ground probes), "
@@ -125,11 +144,11 @@ def run_reference(args):
     from oracle import oracle as orc
     cq = importlib.import_module("swift-game-engine_b200")  # scenes only (numpy); no CUDA call is made
     cores = os.cpu_count() or 1
-    n = args.ref_sample or (CHARS_PER_GPU if args.mesh == "hulls" else 65536)
+    n = args.ref_sample or {"hulls": CHARS_PER_GPU, "render": 65536, "terrain": 262144}[args.mesh]
     parts, pos, vel = make_workload(cq, args.mesh, n, 0)
     w = orc.OracleWorld(parts)
     s = orc.init_states(pos, vel)
-    p = orc.default_params()
+    p = controller_params(orc, args.mesh)
     for _ in range(args.warmup):
         w.move_and_slide(s, p, DT, GRAVITY, 1, orc.ORDER_REFERENCE, cores)
     t0 = time.perf_counter()
@@ -191,7 +210,7 @@ def run_ours(args):
     parts, pos, vel = make_workload(cq, args.mesh, n, rank)
     world = cq.CollisionQuery(parts)
     info = world.info()
-    params = cq.default_params()
+    params = controller_params(cq, args.mesh)
     states0 = cq.init_states(pos, vel)
     nbytes = states0.nbytes
 
@@ -294,12 +313,12 @@ def run_ours(args):
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
-        ns = CHARS_PER_GPU if args.mesh == "hulls" else 65536
+        ns = {"hulls": CHARS_PER_GPU, "render": 65536, "terrain": 262144}[args.mesh]
         ns = min(ns, n)
         ow = orc.OracleWorld(parts)
         snap_np = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=orc.STATE)[:ns].copy()
         t0 = time.perf_counter()
-        ow.move_and_slide(snap_np, orc.default_params(), DT, GRAVITY, 1, orc.ORDER_REFERENCE, cores)
+        ow.move_and_slide(snap_np, controller_params(orc, args.mesh), DT, GRAVITY, 1, orc.ORDER_REFERENCE, cores)
         cdt = time.perf_counter() - t0
         cpu_baseline = {"value": ns / cdt, "unit": "queries/s", "cores": cores, "kind": "port",
                         "sample": f"first {ns} of the {n} characters, the first timed step, {cdt:.2f} s wall; "
@@ -657,7 +676,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mesh", default="hulls", choices=["hulls", "render"])
+    ap.add_argument("--mesh", default="hulls", choices=["hulls", "render", "terrain"])
     ap.add_argument("--chars", type=int, default=CHARS_PER_GPU)
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

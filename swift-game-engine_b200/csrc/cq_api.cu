@@ -268,7 +268,7 @@ void cq_world_destroy(cq_world *w) {
     for (int s = 0; s < 2; s++) free_set(w->set[s]);
     cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork);
     cudaFree(w->in.ptr), cudaFree(w->out.ptr), cudaFree(w->aux.ptr), cudaFree(w->aux2.ptr);
-    for (int k = 0; k < 4; k++) cudaFree(w->nodeScratch[k].ptr);
+    for (int k = 0; k < 4; k++) cudaFree(w->nodeScratch[k].ptr), cudaFree(w->orderScratch[k].ptr);
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);
     if (w->stream) cudaStreamDestroy(w->stream);

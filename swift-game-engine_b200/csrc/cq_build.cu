@@ -587,8 +587,9 @@ static int radix_sort_pairs_classic(cq_world *w, uint32_t *keys, uint32_t *vals,
 
 // onesweep: status = [4][nTiles][256] u32 + [4] tickets + [4][256] digit histograms + error flag, in `scratch`
 static int radix_sort_pairs_onesweep(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTmp, uint32_t *valsTmp,
-                                     int n, uint32_t *scratch, size_t scratchWords) {
-    cudaStream_t st = w->stream;
+                                     int n, uint32_t *scratch, size_t scratchWords, cudaStream_t st = nullptr,
+                                     bool checkError = true) {
+    if (!st) st = w->stream;
     int nTiles = cdiv(n, RS_TILE);
     size_t statusWords = (size_t)4 * nTiles * 256;
     if (statusWords + 4 + 1024 + 1 > scratchWords) {
@@ -610,6 +611,7 @@ static int radix_sort_pairs_onesweep(cq_world *w, uint32_t *keys, uint32_t *vals
         std::swap(kin, kout);
         std::swap(vin, vout);
     }
+    if (!checkError) return check_cuda(cudaGetLastError(), "onesweep"); // asynchronous use: no host round trip
     int hostErr = 0;
     CQ_CUDA(cudaMemcpyAsync(&hostErr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CQ_CUDA(cudaStreamSynchronize(st));
@@ -776,6 +778,53 @@ int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, co
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return done(rc);
+}
+
+// ---------------------------------------------------------------- coherent processing order for big worlds
+// Queries arrive in arbitrary order; on a world that does not fit the caches (10 M triangles = 1.1 GB of nodes
+// + triangles) neighbouring lanes then touch unrelated subtrees.  For such worlds the persistent kernels fetch
+// their work units through `order[]`, the units' indices sorted by the 30-bit Morton code of their position
+// (same onesweep sort as the build).  Results are written to the units' own slots, so the order is invisible.
+__global__ void k_order_keys(const unsigned char *__restrict__ base, size_t stride, int isDouble, int n,
+                             const SetHeader *__restrict__ hdr, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char *p = base + (size_t)i * stride;
+    float x, y, z;
+    if (isDouble) {
+        const double *d = reinterpret_cast<const double *>(p);
+        x = (float)d[0], y = (float)d[1], z = (float)d[2];
+    } else {
+        const float *f = reinterpret_cast<const float *>(p);
+        x = f[0], y = f[1], z = f[2];
+    }
+    SetHeader h = *hdr;
+    float ex = h.hi[0] - h.lo[0], ey = h.hi[1] - h.lo[1], ez = h.hi[2] - h.lo[2];
+    float sx = ex > 0.0f ? 1024.0f / ex : 0.0f, sy = ey > 0.0f ? 1024.0f / ey : 0.0f, sz = ez > 0.0f ? 1024.0f / ez : 0.0f;
+    uint32_t qx = min(1023u, (uint32_t)fmaxf((x - h.lo[0]) * sx, 0.0f));
+    uint32_t qy = min(1023u, (uint32_t)fmaxf((y - h.lo[1]) * sy, 0.0f));
+    uint32_t qz = min(1023u, (uint32_t)fmaxf((z - h.lo[2]) * sz, 0.0f));
+    keys[i] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz);
+    vals[i] = (uint32_t)i;
+}
+
+const uint32_t *make_unit_order(cq_world *w, const void *dUnits, size_t stride, bool positionIsDouble, int n, cudaStream_t st) {
+    if (n < (1 << 16) || w->set[0].nTris < (1 << 18)) return nullptr; // small world / batch: everything is cache resident
+    const int tiles = cdiv(n, RS_TILE);
+    const size_t sortWords = (size_t)4 * 256 * tiles + 4 + 1024 + 1;
+    const size_t words = (size_t)4 * n + sortWords + 64;
+    ScratchBuf &b = w->orderScratch[w->orderSeq++ & 3];
+    if (words * 4 > b.cap) {
+        if (check_cuda(cudaDeviceSynchronize(), "order scratch sync") != CQ_OK) return nullptr;
+        for (int k = 0; k < 4; k++)
+            if (ensure_scratch(w->orderScratch[k], words * 4) != CQ_OK) return nullptr;
+    }
+    uint32_t *keys = (uint32_t *)b.ptr, *vals = keys + n, *keysTmp = vals + n, *valsTmp = keysTmp + n, *scratch = valsTmp + n;
+    k_order_keys<<<cdiv(n, 256), 256, 0, st>>>((const unsigned char *)dUnits, stride, positionIsDouble ? 1 : 0, n, w->set[0].hdr,
+                                               keys, vals);
+    w->launches++;
+    if (radix_sort_pairs_onesweep(w, keys, vals, keysTmp, valsTmp, n, scratch, sortWords, st, false) != CQ_OK) return nullptr;
+    return vals;
 }
 
 // TriangleMeshSet.updateTransforms + BVH.refit: re-transform the changed parts' vertices, regather the

@@ -71,7 +71,8 @@ struct cq_world {
     int counting = 0;
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
     uint64_t launches = 0;
-    cq::ScratchBuf nodeScratch[4];
+    cq::ScratchBuf nodeScratch[4], orderScratch[4];
+    uint32_t orderSeq = 0;
     uint32_t nodeSeq = 0;
     float hintMas = 0.0f, hintCast = 0.0f; // wall/PCIe ratio of the previous host-pointer call (chunking heuristic)
     int *dWork = nullptr; // ring of dynamic-fetch counters, one per persistent-kernel launch in flight
@@ -108,6 +109,9 @@ int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, co
               std::vector<int> &keptPerPartPrefix /* out: filtered tri count per input part, by part index */);
 int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx);
 void free_set(DeviceSet &S);
+// Morton-sorted processing order of n work units whose position (3 floats or 3 doubles) sits at the start of each
+// `stride`-byte record; nullptr when ordering is not worthwhile (small world / batch) or on error
+const uint32_t *make_unit_order(cq_world *w, const void *dUnits, size_t stride, bool positionIsDouble, int n, cudaStream_t st);
 
 // cq_query.cu
 int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, cudaStream_t st);

@@ -313,7 +313,7 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
 template <bool COUNT>
 __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShared &s, const WarpPool &wp, int lane,
                                             const WorldView &W, const MasArgs &A, cq_character_state *states, int n,
-                                            int *workCounter, Counters &ctr) {
+                                            int *workCounter, const uint32_t *order, Counters &ctr) {
     const cq_controller_params &P = A.p;
     const f3 down = {0.0f, -1.0f, 0.0f};
     int next = NX_LOAD;
@@ -444,6 +444,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
                 c.wait = W_NONE;
                 return false;
             }
+            if (order) c.charIndex = (int)order[c.charIndex]; // Morton-coherent processing order (big worlds)
             c.st = states + c.charIndex;
             cq_character_state &S = *c.st;
             const bool wasGrounded = S.grounded != 0, wasGroundedNear = S.grounded_near != 0;
@@ -576,6 +577,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states,
                                                                                 int n, MasArgs A, int ownersPerWarp,
                                                                                 uint2 *nodeScratch, int *workCounter,
+                                                                                const uint32_t *__restrict__ order,
                                                                                 unsigned long long *gctr) {
     extern __shared__ __align__(16) unsigned char masSmem[]; // MAS_SMEM_BYTES, dynamic
     CharCtx *ctxs = reinterpret_cast<CharCtx *>(masSmem);
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
-        return mas_advance<COUNT>(c, r, mine, wp, lane, W, A, states, n, workCounter, ct);
+        return mas_advance<COUNT>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);
     }, OverlapTop2());
     pool_flush_counters(ctr, gctr, COUNT);
 }
@@ -626,9 +628,11 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     const int opw = pool_owners_per_warp(n, (long long)blocks * MAS_WARPS);
     uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * MAS_WARPS);
     if (!ns) return CQ_ERR_CUDA;
+    const uint32_t *order = make_unit_order(w, d_inout, sizeof(cq_character_state), true, n, st);
     if (w->counting)
-        k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, w->dCounters);
-    else k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, w->dCounters);
+        k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
+    else
+        k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_move_and_slide");
 }

@@ -65,6 +65,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
                                                                int mode, cq_cast_hit *__restrict__ out, int ownersPerWarp,
                                                                uint2 *nodeScratch, int *workCounter,
+                                                               const uint32_t *__restrict__ order,
                                                                unsigned long long *gctr) {
     __shared__ QShared qsAll[Q_THREADS];
     __shared__ uint32_t words[CQ_POOL_WORDS * CAST_WARPS];
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, cons
             cur = -1;
             return false;
         }
+        if (order) cur = (int)order[cur]; // Morton-coherent processing order (big worlds)
         cq_capsule_cast c = qs[cur];
         pool_post_cast<COUNT>(W, wp, lane, mine, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
                               c.min_normal_y, ct);
@@ -253,8 +255,10 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
     if (!work) return CQ_ERR_CUDA;
     uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS);
     if (!ns) return CQ_ERR_CUDA;
-    if (w->counting) k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, w->dCounters);
-    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, w->dCounters);
+    const uint32_t *order = make_unit_order(w, d_q, sizeof(cq_capsule_cast), false, n, st);
+    if (w->counting)
+        k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, order, w->dCounters);
+    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, order, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }
