@@ -60,6 +60,7 @@ static void make_view(cq_world *w) {
         SetView &v = w->view.set[s];
         v.tv0 = S.tv0, v.tv1 = S.tv1, v.tv2 = S.tv2;
         v.nodes = S.nodes;
+        v.nodes4 = S.nodes4;
         v.hdr = S.hdr;
         v.triOffset = s == 0 ? 0 : w->set[0].nTris;
     }

@@ -516,6 +516,62 @@ __global__ void k_fit(int n, const float4 *__restrict__ tv0, const float4 *__res
     }
 }
 
+// depth parity of every internal node (root = depth 0): only even-depth nodes become 4-wide nodes
+__global__ void k_depth_parity(int nInternal, const int32_t *__restrict__ parent, uint8_t *__restrict__ parity) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nInternal) return;
+    int d = 0;
+    for (int p = parent[i]; p >= 0; p = parent[p]) d++;
+    parity[i] = (uint8_t)(d & 1);
+}
+
+// collapse: wide node i = binary node i (even depth) with its internal children replaced by THEIR children
+__global__ void k_collapse4(int nInternal, const Node *__restrict__ nodes, const uint8_t *__restrict__ parity,
+                            Node4 *__restrict__ nodes4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nInternal || parity[i]) return;
+    Node nb = nodes[i];
+    float4 lo[4], hi[4];
+    int ref[4];
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        float4 clo = c == 0 ? nb.n0 : nb.n2, chi = c == 0 ? nb.n1 : nb.n3;
+        int r = __float_as_int(c == 0 ? nb.n0.w : nb.n1.w);
+        if (r < 0) {
+            lo[cnt] = clo, hi[cnt] = chi, ref[cnt] = r;
+            cnt++;
+        } else {
+            Node nc = nodes[r];
+            lo[cnt] = nc.n0, hi[cnt] = nc.n1, ref[cnt] = __float_as_int(nc.n0.w);
+            cnt++;
+            lo[cnt] = nc.n2, hi[cnt] = nc.n3, ref[cnt] = __float_as_int(nc.n1.w);
+            cnt++;
+        }
+    }
+    Node4 w;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        bool used = k < cnt;
+        float4 l = used ? lo[k] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.0f);
+        float4 h = used ? hi[k] : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f);
+        int r = used ? ref[k] : CQ_REF_EMPTY;
+        if (k < 2) {
+            w.q[2 * k] = make_float4(l.x, l.y, l.z, __int_as_float(r));
+            w.q[2 * k + 1] = make_float4(h.x, h.y, h.z, 0.0f);
+        } else {
+            w.q[2 * k] = make_float4(l.x, l.y, l.z, 0.0f);
+            w.q[2 * k + 1] = make_float4(h.x, h.y, h.z, 0.0f);
+        }
+    }
+    // refs: q[0].w = ref0, q[1].w = ref1, q[2].w = ref2, q[3].w = ref3
+    w.q[0].w = __int_as_float(cnt > 0 ? ref[0] : CQ_REF_EMPTY);
+    w.q[1].w = __int_as_float(cnt > 1 ? ref[1] : CQ_REF_EMPTY);
+    w.q[2].w = __int_as_float(cnt > 2 ? ref[2] : CQ_REF_EMPTY);
+    w.q[3].w = __int_as_float(cnt > 3 ? ref[3] : CQ_REF_EMPTY);
+    nodes4[i] = w;
+}
+
 __global__ void k_header(int n, const float4 *__restrict__ boxLo, const float4 *__restrict__ boxHi, SetHeader *hdr) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     SetHeader h;
@@ -643,6 +699,14 @@ static int build_tree(cq_world *w, DeviceSet &S, const uint32_t *sortedKeys /* m
         }
         k_fit<<<cdiv(n, 256), 256, 0, st>>>(n, S.tv0, S.tv1, S.tv2, S.nodes, S.parent, S.boxLo, S.boxHi, S.visit);
         w->launches++;
+        if (n > 1) {
+            if (sortedKeys) { // topology is new: depth parities
+                k_depth_parity<<<cdiv(n - 1, 256), 256, 0, st>>>(n - 1, S.parent, S.depthParity);
+                w->launches++;
+            }
+            k_collapse4<<<cdiv(n - 1, 256), 256, 0, st>>>(n - 1, S.nodes, S.depthParity, S.nodes4);
+            w->launches++;
+        }
     }
     k_header<<<1, 32, 0, st>>>(n, S.boxLo, S.boxHi, S.hdr);
     w->launches++;
@@ -676,6 +740,8 @@ int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, co
         S.tv1 = a.take<float4>(nCap);
         S.tv2 = a.take<float4>(nCap);
         S.nodes = a.take<Node>(nCap);
+        S.nodes4 = a.take<Node4>(nCap);
+        S.depthParity = a.take<uint8_t>(nCap);
         S.parent = a.take<int32_t>((size_t)2 * nCap);
         S.rangeLo = a.take<int32_t>(nCap);
         S.rangeHi = a.take<int32_t>(nCap);

@@ -39,6 +39,8 @@ struct DeviceSet {
     float4 *tv0 = nullptr, *tv1 = nullptr, *tv2 = nullptr;
     // LBVH
     Node *nodes = nullptr;       // nTris-1 internal nodes (>= 1 allocated)
+    Node4 *nodes4 = nullptr;     // 4-wide collapse of `nodes`, indexed by the binary node each was made from
+    uint8_t *depthParity = nullptr; // per internal node: depth & 1
     int32_t *parent = nullptr;   // [0,nTris-1): internal, [nTris-1, 2nTris-1): leaves
     int32_t *rangeLo = nullptr, *rangeHi = nullptr; // per internal node
     float4 *boxLo = nullptr, *boxHi = nullptr;      // 2nTris-1 subtree boxes (bottom-up scratch, kept for refit)

@@ -189,7 +189,7 @@ __device__ __forceinline__ void pool_post_overlap(const WorldView &W, const Warp
 template <bool COUNT>
 __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPool &wp, int lane, Counters &ctr) {
     const uint32_t top = *wp.ntop;
-    const uint32_t poppers = (top + 96u > (uint32_t)CQ_NSCAP) ? 1u : 32u; // nearly full: depth-first with one lane
+    const uint32_t poppers = (top + 160u > (uint32_t)CQ_NSCAP) ? 1u : 32u; // nearly full: depth-first with one lane
     const uint32_t k = min(top, poppers);
     uint2 e = make_uint2(0u, 0u);
     const bool have = (uint32_t)lane < k;
@@ -202,22 +202,23 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
         QShared &s = wp.qs[owner];
         const f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
         int net = -1; // this entry is consumed
-        if ((e.x & 1u) == 0u) { // internal node: test both children
-            const Node *n = (set ? W.set[1].nodes : W.set[0].nodes) + e.y;
-            float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
-            if (COUNT) ctr.nodes += 2;
-            bool h0 = !box_disjoint(xyz(n0), xyz(n1), qlo, qhi), h1 = !box_disjoint(xyz(n2), xyz(n3), qlo, qhi);
-            int cnt = (h0 ? 1 : 0) + (h1 ? 1 : 0);
+        if ((e.x & 1u) == 0u) { // 4-wide internal node: test up to four children
+            const Node4 *n = (set ? W.set[1].nodes4 : W.set[0].nodes4) + e.y;
+            float4 q0 = __ldg(&n->q[0]), q1 = __ldg(&n->q[1]), q2 = __ldg(&n->q[2]), q3 = __ldg(&n->q[3]);
+            float4 q4 = __ldg(&n->q[4]), q5 = __ldg(&n->q[5]), q6 = __ldg(&n->q[6]), q7 = __ldg(&n->q[7]);
+            const int r0 = __float_as_int(q0.w), r1 = __float_as_int(q1.w), r2 = __float_as_int(q2.w), r3 = __float_as_int(q3.w);
+            // empty children have inverted boxes: they fail the overlap test by themselves
+            bool h0 = !box_disjoint(xyz(q0), xyz(q1), qlo, qhi), h1 = !box_disjoint(xyz(q2), xyz(q3), qlo, qhi);
+            bool h2 = !box_disjoint(xyz(q4), xyz(q5), qlo, qhi), h3 = !box_disjoint(xyz(q6), xyz(q7), qlo, qhi);
+            if (COUNT) ctr.nodes += 2 + (r2 != CQ_REF_EMPTY) + (r3 != CQ_REF_EMPTY);
+            int cnt = (h0 ? 1 : 0) + (h1 ? 1 : 0) + (h2 ? 1 : 0) + (h3 ? 1 : 0);
             if (cnt) {
                 uint32_t pos = atomicAdd((uint32_t *)wp.ntop, (uint32_t)cnt);
-                if (h0) {
-                    int r = __float_as_int(n0.w);
-                    wp.nstack[pos++] = make_uint2((e.x & ~1u) | (r < 0 ? 1u : 0u), (uint32_t)(r < 0 ? ~r : r));
-                }
-                if (h1) {
-                    int r = __float_as_int(n1.w);
-                    wp.nstack[pos] = make_uint2((e.x & ~1u) | (r < 0 ? 1u : 0u), (uint32_t)(r < 0 ? ~r : r));
-                }
+                const uint32_t tag = e.x & ~1u;
+                if (h0) wp.nstack[pos++] = make_uint2(tag | (r0 < 0 ? 1u : 0u), (uint32_t)(r0 < 0 ? ~r0 : r0));
+                if (h1) wp.nstack[pos++] = make_uint2(tag | (r1 < 0 ? 1u : 0u), (uint32_t)(r1 < 0 ? ~r1 : r1));
+                if (h2) wp.nstack[pos++] = make_uint2(tag | (r2 < 0 ? 1u : 0u), (uint32_t)(r2 < 0 ? ~r2 : r2));
+                if (h3) wp.nstack[pos] = make_uint2(tag | (r3 < 0 ? 1u : 0u), (uint32_t)(r3 < 0 ? ~r3 : r3));
                 net += cnt;
             }
         } else { // leaf range: 1..4 consecutive triangles of the sorted SoA

@@ -25,6 +25,16 @@ struct __align__(16) Node {
     float4 n0, n1, n2, n3;
 };
 
+// 4-wide node used by the cooperative walk: the binary LBVH collapsed two levels at a time (every internal
+// node at even depth absorbs its internal children), so a query descends half as many levels — and the walk
+// rounds are latency bound on exactly that dependent chain of node fetches.  128 bytes:
+//   q[0] = (lo0, ref0) q[1] = (hi0, ref1) q[2] = (lo1, ref2) q[3] = (hi1, ref3) q[4..7] = lo2 hi2 lo3 hi3
+// ref >= 0: wide node index (= index of the binary node it was made from); ref < 0: leaf range as in Node;
+// CQ_REF_EMPTY: unused child (its box is inverted, so it never overlaps anything).
+struct __align__(16) Node4 {
+    float4 q[8];
+};
+
 struct __align__(16) SetHeader {
     float lo[3];
     int rootRef; // CQ_REF_EMPTY when the set has no triangles
@@ -35,6 +45,7 @@ struct __align__(16) SetHeader {
 struct SetView {
     const float4 *tv0, *tv1, *tv2;
     const Node *nodes;
+    const Node4 *nodes4;
     const SetHeader *hdr;
     int triOffset; // added to triangle ids of this set (dynamic set: static count, CollisionQuery.swift:782)
 };
