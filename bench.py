@@ -32,6 +32,39 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# Libraries (NCCL, torch) may print to stdout; the contract is ONE JSON line there.  Keep the real stdout aside
+# and send everything else to stderr.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node its GPU hangs
+    off, so that 8 ranks do not push all their PCIe traffic through one socket's memory."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 CHARS_PER_GPU = 1 << 20
 SEED = 0xC0111DE3
 DT = 1.0 / 60.0
@@ -98,8 +131,15 @@ class ClockSampler:
             for k, nm in enumerate(names):
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        # "under load" = samples whose power draw is above the idle floor (the first samples precede the first launch)
+        if power:
+            thr = min(power) + 0.25 * (max(power) - min(power))
+            loaded = [c for c, p in zip(sm, power) if p >= thr] or sm
+        else:
+            loaded = sm
+        return {"sm_mhz": float(np.median(loaded)) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "samples_under_load": len(loaded),
+                "reasons": sorted(reasons)}
 
 
 TERRAIN_PARAMS = dict(radius=0.4, half_height=0.5, skin_width=0.08)  # human-scale capsule
@@ -168,7 +208,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -184,6 +224,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -227,16 +268,16 @@ def run_ours(args):
     def step_device():
         world.move_and_slide_device(d_states.data_ptr(), n, params, DT, GRAVITY, cq.MAS_APPLY_GRAVITY, stream)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # runs through warm-up, the timed region and a short identical load after it (see below)
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
     snapshot = d_states.clone()
 
-    sampler = ClockSampler(local_rank)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     world.resetStats()
     barrier()
-    sampler.start()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -246,8 +287,16 @@ def run_ours(args):
         evs[k][1].record()
     t_end.record()
     barrier()
-    clocks = sampler.stop()
     launches = world.stats()["kernel_launches"]
+    # the timed region lasts tens of milliseconds, shorter than one nvidia-smi sampling period: keep the identical
+    # load running (untimed) until the sampler has seen the GPU under it for at least ~0.7 s
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.7:
+        for _ in range(8):
+            step_device()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed region + 0.7 s of the same steps right after it (untimed)"
     total_ms = max_over_ranks(t_start.elapsed_time(t_end))
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     value = n * world_size * args.steps / (total_ms * 1e-3)
@@ -334,7 +383,7 @@ def run_ours(args):
                        "triangles": info["n_static_triangles"] + info["n_dynamic_triangles"],
                        "l2": "inputs (168 B x characters = %.0f MB per GPU) exceed the 126 MB L2; no flush" % (nbytes / 1e6),
                        "parallelism": f"queries sharded over {world_size} GPU(s), mesh+BVH replicated, no collective",
-                       "bvh_build_ms": info["build_ms"], "grounded_fraction_after": grounded_frac,
+                       "bvh_build_ms": info["build_ms"], "grounded_fraction_after": grounded_frac, "numa_node": numa_node,
                        "e2e_matches_device_path": same},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -344,7 +393,7 @@ def run_ours(args):
             "gpu_launches": int(total_launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     world.close()
     if world_size > 1:
         dist.destroy_process_group()
@@ -362,6 +411,7 @@ def _torch_setup():
         raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
     tstream = torch.cuda.Stream(device=dev)
@@ -461,7 +511,7 @@ def run_c4(args):
                                   "(differences = exact toi ties)"}
     tot_launch = red(launches, dist.ReduceOp.SUM)
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "capsule_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": ws, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -478,7 +528,7 @@ def run_c4(args):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": n * ws * args.steps / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": n * 40 * ws,
                     "d2h_bytes_per_step": n * 44 * ws},
-            "gpu_launches": int(tot_launch), "clocks": clocks}), flush=True)
+            "gpu_launches": int(tot_launch), "clocks": clocks}))
     world.close()
     return 0
 
@@ -549,7 +599,7 @@ def run_c2(args):
         cpu_baseline = {"value": ns / cdt, "unit": "sweeps/s", "cores": cores, "kind": "port",
                         "sample": f"first {ns} of {n} sweeps, {cdt:.2f} s wall, reference BVH + DFS order"}
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "capsule_sweeps_per_sec", "value": n * ws / (ms * 1e-3), "unit": "sweeps/s", "n_gpus": ws,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -564,7 +614,7 @@ def run_c2(args):
                                             "frac": 430.0 * ctr["distance_evals"] / (ms * 1e-3) / 1e12 / 37.22496}},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": n / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": n * 40, "d2h_bytes_per_step": n * 44},
-            "gpu_launches": int(launches), "clocks": clocks}), flush=True)
+            "gpu_launches": int(launches), "clocks": clocks}))
     world.close()
     return 0
 
@@ -646,7 +696,7 @@ def run_c5(args):
                                   f"index agreement with the GPU on the sample {agree:.5f}"}
     tot_launch = red(launches, dist.ReduceOp.SUM)
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "raycasts_per_sec_with_refit", "value": n * ws * args.steps / wall, "unit": "rays/s", "n_gpus": ws,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -660,7 +710,7 @@ def run_c5(args):
                          "frac": algo / (ray_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "k_raycast", "kernel_ms": ray_ms, "algorithmic_bytes_per_launch": algo,
                          "per_query": {k: ctr[k] / n for k in ("nodes_visited", "candidates")}},
-            "cpu_baseline": cpu_baseline, "e2e": None, "gpu_launches": int(tot_launch), "clocks": clocks}), flush=True)
+            "cpu_baseline": cpu_baseline, "e2e": None, "gpu_launches": int(tot_launch), "clocks": clocks}))
     world.close()
     return 0
 
