@@ -302,6 +302,9 @@ int cq_world_get_info(const cq_world *w, cq_world_info *info) {
 int cq_world_update_transforms(cq_world *w, const uint32_t *entity_ids, const float *models, int32_t n) {
     if (!w || n < 0 || (n > 0 && (!entity_ids || !models))) return CQ_ERR_INVALID;
     CQ_CUDA(cudaSetDevice(w->device));
+    // A refit mutates the world: every query still in flight on any stream (the *_device calls are asynchronous)
+    // must have finished reading the old boxes first.
+    CQ_CUDA(cudaDeviceSynchronize());
     std::vector<int> changed[2];
     for (int i = 0; i < n; i++) {
         bool found = false;
