@@ -1,6 +1,5 @@
-// cq_world.cuh — device-side world layout and the per-thread query routines
-// (BVH box/ray traversal + narrow phase) shared by the batch kernels and the
-// in-kernel move-and-slide.
+// cq_world.cuh — device-side world layout (triangle SoA, LBVH nodes, views) and small helpers shared by
+// the query kernels (cq_pool.cuh, cq_query.cu, cq_mas.cu).
 //
 // HBM layout of one triangle set (static or dynamic, CollisionQuery.swift:710-711):
 //   tv0/tv1/tv2 : float4 SoA, one entry per triangle in MORTON (leaf) order
@@ -72,48 +71,6 @@ __device__ __forceinline__ Tri load_tri(const SetView &s, int i, uint32_t &layer
     return Tri{xyz(a), xyz(b), xyz(c)};
 }
 
-// Generic box-query traversal: calls fn(sortedIndex) for every leaf triangle slot whose node chain
-// overlaps [qlo,qhi].  Traversal order is free: capsule queries never cull by distance
-// (CollisionQuery.swift:1045-1051), so the candidate set is tree-independent.
-template <bool COUNT, class Fn>
-__device__ __forceinline__ void traverse_box(const SetView &s, f3 qlo, f3 qhi, Counters &ctr, Fn fn) {
-    SetHeader h = *s.hdr;
-    if (h.rootRef == CQ_REF_EMPTY) return;
-    if (COUNT) ctr.nodes++;
-    if (box_disjoint(mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), qlo, qhi)) return;
-    int stack[CQ_STACK];
-    int sp = 0;
-    int ref = h.rootRef;
-    while (true) {
-        if (ref < 0) {
-            int enc = ~ref;
-            int start = enc >> 2, count = (enc & 3) + 1;
-#pragma unroll 1
-            for (int k = 0; k < count; k++) fn(start + k);
-        } else {
-            const Node *n = s.nodes + ref;
-            float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
-            if (COUNT) ctr.nodes += 2;
-            bool h0 = !box_disjoint(xyz(n0), xyz(n1), qlo, qhi);
-            bool h1 = !box_disjoint(xyz(n2), xyz(n3), qlo, qhi);
-            int r0 = __float_as_int(n0.w), r1 = __float_as_int(n1.w);
-            if (h0 && h1) {
-                stack[sp++] = r1;
-                ref = r0;
-                continue;
-            } else if (h0) {
-                ref = r0;
-                continue;
-            } else if (h1) {
-                ref = r1;
-                continue;
-            }
-        }
-        if (sp == 0) break;
-        ref = stack[--sp];
-    }
-}
-
 #define CQ_MODE_ALL 0
 #define CQ_MODE_BLOCKING 1
 #define CQ_MODE_GROUND 2
@@ -146,42 +103,7 @@ __device__ __forceinline__ void overlap_contact(const Tri &T, float dist, f3 seg
     r.triNormal = triN;
 }
 
-// Visit every overlapping triangle: fn(depth, globalTri, part, slot, setIndex, T, dist, segPt, triPt)
-template <bool COUNT, class Fn>
-__device__ __forceinline__ void capsule_overlap_visit(const WorldView &W, f3 from, float radius, float hh,
-                                                      uint32_t mask, Counters &ctr, Fn fn) {
-    f3 qlo, qhi;
-    overlap_box(from, radius, hh, qlo, qhi);
-#pragma unroll 1
-    for (int si = 0; si < 2; si++) {
-        const SetView &S = W.set[si];
-        if (COUNT) ctr.queries++;
-        traverse_box<COUNT>(S, qlo, qhi, ctr, [&](int slot) {
-            uint32_t layer;
-            int triId, part;
-            Tri T = load_tri(S, slot, layer, triId, part);
-            if ((layer & mask) == 0u) return;
-            f3 tlo = vmin(T.v0, vmin(T.v1, T.v2)), thi = vmax(T.v0, vmax(T.v1, T.v2));
-            if (box_disjoint(tlo, thi, qlo, qhi)) return;
-            if (COUNT) {
-                ctr.cands++;
-                ctr.evals++;
-            }
-            f3 sp, tp;
-            float dist = segment_triangle_distance<true>(from, hh, T, sp, tp);
-            if (dist >= radius) return; // CollisionQuery.swift:1170
-            fn(radius - dist, triId + S.triOffset, part, T, dist, sp, tp);
-        });
-    }
-}
-
 // ---------------------------------------------------------------- raycast
-struct RayResult {
-    int tri, part;
-    float t;
-    f3 normal;
-};
-
 // rayAABB — CollisionQuery.swift:1603-1631 — made conservative: the box is accepted when the slab
 // interval, widened by a few ulps, is non-empty and starts before closestT.  The reference's own
 // slab test is not conservative in floating point, so which grazing hits it culls depends on its
@@ -201,75 +123,6 @@ __device__ __forceinline__ bool ray_box(f3 o, f3 inv, f3 lo, f3 hi, float closes
     if (tmin - pad > tmax + pad) return false;
     if (tmax + pad < 0.0f) return false; // rayTriangle needs t >= 0
     return tmin - pad <= closestT;
-}
-
-template <bool COUNT>
-__device__ __forceinline__ void raycast(const WorldView &W, f3 origin, f3 direction, float maxDistance, uint32_t mask,
-                                        RayResult &res, Counters &ctr) {
-    res.tri = -1;
-    res.part = -1;
-    float closestT = maxDistance;
-    // CollisionQuery.swift:1606-1608: 1/d, or greatestFiniteMagnitude when d == 0
-    f3 inv = {direction.x != 0.0f ? 1.0f / direction.x : FLT_MAX, direction.y != 0.0f ? 1.0f / direction.y : FLT_MAX,
-              direction.z != 0.0f ? 1.0f / direction.z : FLT_MAX};
-#pragma unroll 1
-    for (int si = 0; si < 2; si++) {
-        const SetView &S = W.set[si];
-        SetHeader h = *S.hdr;
-        if (h.rootRef == CQ_REF_EMPTY) continue;
-        if (COUNT) {
-            ctr.queries++;
-            ctr.nodes++;
-        }
-        if (!ray_box(origin, inv, mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), closestT)) continue;
-        int stack[CQ_STACK];
-        int sp = 0;
-        int ref = h.rootRef;
-        while (true) {
-            if (ref < 0) {
-                int enc = ~ref;
-                int start = enc >> 2, count = (enc & 3) + 1;
-                for (int k = 0; k < count; k++) {
-                    uint32_t layer;
-                    int triId, part;
-                    Tri T = load_tri(S, start + k, layer, triId, part);
-                    if ((layer & mask) == 0u) continue;
-                    if (COUNT) ctr.cands++;
-                    float t;
-                    if (!ray_triangle(origin, direction, T, t)) continue;
-                    int gid = triId + S.triOffset;
-                    if (t < closestT || (res.tri >= 0 && t == closestT && gid < res.tri)) {
-                        closestT = t;
-                        res.tri = gid;
-                        res.part = part;
-                        res.t = t;
-                        f3 n = normalize(cross(T.v1 - T.v0, T.v2 - T.v0)); // CollisionQuery.swift:960-961
-                        res.normal = dot(n, direction) > 0.0f ? -n : n;
-                    }
-                }
-            } else {
-                const Node *n = S.nodes + ref;
-                float4 n0 = __ldg(&n->n0), n1 = __ldg(&n->n1), n2 = __ldg(&n->n2), n3 = __ldg(&n->n3);
-                if (COUNT) ctr.nodes += 2;
-                bool h0 = ray_box(origin, inv, xyz(n0), xyz(n1), closestT);
-                bool h1 = ray_box(origin, inv, xyz(n2), xyz(n3), closestT);
-                int r0 = __float_as_int(n0.w), r1 = __float_as_int(n1.w);
-                if (h0 && h1) {
-                    stack[sp++] = r1;
-                    ref = r0;
-                    continue;
-                } else if (h0) {
-                    ref = r0;
-                    continue;
-                } else if (h1) {
-                    ref = r1;
-                    continue;
-                }
-            }
-            if (sp == 0) break;
-            ref = stack[--sp];
-        }
-    }
 }
 
 } // namespace cq
