@@ -245,6 +245,15 @@ typedef struct cq_character_state { /* PhysicsBodyComponent + CharacterControlle
 
 #define CQ_MAS_APPLY_GRAVITY 1u /* run GravitySystem's rule first (Systems.swift:603-619) */
 
+/* A kinematic platform as PlatformCarry.computeDelta sees it (Systems.swift:644-732): the world AABB of its
+ * collision mesh under the CURRENT transform (meshWorldAABB, :627-642) and its motion over this fixed step
+ * (positionF - prevPositionF).  Its triangles are ordinary dynamic-set parts of the world. */
+typedef struct cq_platform {
+    float aabb_min[3];
+    float aabb_max[3];
+    float delta[3];
+} cq_platform;
+
 void cq_controller_params_default(cq_controller_params *p);
 void cq_character_state_init(cq_character_state *s, const float position[3], const float velocity[3]);
 
@@ -254,6 +263,17 @@ int cq_move_and_slide_batch(cq_world *w, cq_character_state *inout, int32_t n,
 int cq_move_and_slide_device(cq_world *w, cq_character_state *d_inout, int32_t n,
                              const cq_controller_params *params, float dt,
                              const float gravity[3], uint32_t flags, void *stream);
+
+/* Same step with kinematic platforms: before the velocity gate every character is carried by the platform it
+ * stands on / pushed by a platform moving into its side (applyPlatformDelta, Systems.swift:1618-1633).
+ * Platforms are taken in the given order (the reference iterates a Dictionary). */
+int cq_move_and_slide_batch_ex(cq_world *w, cq_character_state *inout, int32_t n,
+                               const cq_controller_params *params, float dt, const float gravity[3],
+                               uint32_t flags, const cq_platform *platforms, int32_t n_platforms);
+int cq_move_and_slide_device_ex(cq_world *w, cq_character_state *d_inout, int32_t n,
+                                const cq_controller_params *params, float dt, const float gravity[3],
+                                uint32_t flags, const cq_platform *platforms /* HOST pointer */,
+                                int32_t n_platforms, void *stream);
 
 /* ---- instrumentation ------------------------------------------------------
  * Work counters of the last device/batch call, accumulated on the device when

@@ -1251,9 +1251,60 @@ GroundProbeResult groundProbe(const StaticTriMesh &q, QueryCtx &ctx, F3 position
     return r;
 }
 
+// PlatformCarry.computeDelta (SYS:644-732); a platform = world AABB of its mesh + its motion this step
+F3 platformCarryDelta(F3 position, const orc_params &c, const orc_platform *platforms, int nPlatforms) {
+    if (nPlatforms <= 0) return {0, 0, 0};
+    float capsuleHalf = c.half_height + c.radius;
+    float baseY = position.y - capsuleHalf;
+    F3 capMin = {position.x - c.radius, position.y - capsuleHalf, position.z - c.radius};
+    F3 capMax = {position.x + c.radius, position.y + capsuleHalf, position.z + c.radius};
+    float sideTol = smax(c.skin_width, c.ground_snap_skin);
+    F3 bestCarry = {0, 0, 0}, pushDelta = {0, 0, 0};
+    for (int k = 0; k < nPlatforms; k++) {
+        F3 pDelta = ld3(platforms[k].delta);
+        if (length_squared(pDelta) < 1e-8f) continue;
+        F3 amin = ld3(platforms[k].aabb_min), amax = ld3(platforms[k].aabb_max);
+        F3 emin = amin - f3(sideTol, sideTol, sideTol), emax = amax + f3(sideTol, sideTol, sideTol);
+        bool overlap = capMin.x <= emax.x && capMax.x >= emin.x && capMin.y <= emax.y && capMax.y >= emin.y &&
+                       capMin.z <= emax.z && capMax.z >= emin.z;
+        if (!overlap) continue;
+        bool withinXZ = position.x >= amin.x - c.radius && position.x <= amax.x + c.radius &&
+                        position.z >= amin.z - c.radius && position.z <= amax.z + c.radius;
+        float topY = amax.y;
+        float topTol = c.snap_distance + smax(c.skin_width, c.ground_snap_skin) + 0.05f;
+        bool onTop = withinXZ && baseY >= topY - topTol && baseY <= topY + topTol;
+        if (onTop) {
+            if (length_squared(pDelta) > length_squared(bestCarry)) bestCarry = pDelta;
+        } else {
+            float yMin = amin.y - capsuleHalf, yMax = amax.y + capsuleHalf;
+            if (position.y >= yMin && position.y <= yMax) {
+                bool outsideX = position.x < amin.x - c.radius || position.x > amax.x + c.radius;
+                bool outsideZ = position.z < amin.z - c.radius || position.z > amax.z + c.radius;
+                if (!outsideX && !outsideZ) continue;
+                float cx = smax(amin.x, smin(position.x, amax.x));
+                float cz = smax(amin.z, smin(position.z, amax.z));
+                float dx = position.x - cx, dz = position.z - cz;
+                float sideDistSq = dx * dx + dz * dz;
+                float sidePushTol = c.radius + sideTol;
+                if (sideDistSq <= sidePushTol * sidePushTol) {
+                    float dirLen = sqrtf(smax(sideDistSq, 0.0f));
+                    if (dirLen > 1e-5f) {
+                        F3 dir = {dx / dirLen, 0, dz / dirLen};
+                        float moveToward = dot(f3(pDelta.x, 0, pDelta.z), dir);
+                        if (moveToward > 0) pushDelta = pushDelta + f3(pDelta.x, 0, pDelta.z);
+                    }
+                }
+            }
+        }
+    }
+    if (length_squared(bestCarry) > 1e-8f) return bestCarry;
+    if (length_squared(pushDelta) > 1e-8f) return pushDelta;
+    return {0, 0, 0};
+}
+
 // one character, one fixed step: KinematicMoveStopSystem.fixedUpdate loop body (SYS:1842-1901)
 void moveAndSlideOne(const StaticTriMesh &q, QueryCtx &ctx, orc_state &s, const orc_params &p, float dt,
-                     F3 gravity, uint32_t flags) {
+                     F3 gravity, uint32_t flags, const orc_platform *platforms = nullptr, int nPlatforms = 0) {
     Character ch;
     ch.s = &s;
     ch.p = &p;
@@ -1263,6 +1314,10 @@ void moveAndSlideOne(const StaticTriMesh &q, QueryCtx &ctx, orc_state &s, const 
     }
     F3 position = {(float)s.position[0], (float)s.position[1], (float)s.position[2]}; // positionF
     cacheDecay(s);                                                                   // SYS:1848
+    { // applyPlatformDelta (SYS:1618-1633)
+        F3 platformDelta = platformCarryDelta(position, p, platforms, nPlatforms);
+        if (length_squared(platformDelta) > 1e-8f) position = position + platformDelta;
+    }
     bool wasGrounded = s.grounded != 0, wasGroundedNear = s.grounded_near != 0;
     // VelocityGate.apply (SYS:1037-1051)
     if (wasGrounded && wasGroundedNear && ch.velocity.y < 0) ch.velocity.y = 0;
@@ -1571,6 +1626,12 @@ void orc_capsule_overlap_all(orc_world *w, const orc_capsule *q, int32_t n, int3
 void orc_move_and_slide(orc_world *w, orc_state *inout, int32_t n, const orc_params *params, float dt,
                         const float gravity[3], uint32_t flags, int32_t order, int32_t n_threads,
                         orc_stats *stats) {
+    orc_move_and_slide_ex(w, inout, n, params, dt, gravity, flags, order, n_threads, stats, nullptr, 0);
+}
+
+void orc_move_and_slide_ex(orc_world *w, orc_state *inout, int32_t n, const orc_params *params, float dt,
+                           const float gravity[3], uint32_t flags, int32_t order, int32_t n_threads,
+                           orc_stats *stats, const orc_platform *platforms, int32_t n_platforms) {
     std::vector<Stats> per(std::max(1, n_threads));
     F3 g = ld3(gravity);
     parallelFor(n, n_threads, [&](int t, int lo, int hi) {
@@ -1578,7 +1639,7 @@ void orc_move_and_slide(orc_world *w, orc_state *inout, int32_t n, const orc_par
             QueryCtx ctx;
             ctx.order = order;
             ctx.stats = stats ? &per[t] : nullptr;
-            moveAndSlideOne(w->mesh, ctx, inout[i], *params, dt, g, flags);
+            moveAndSlideOne(w->mesh, ctx, inout[i], *params, dt, g, flags, platforms, n_platforms);
             if (ctx.tie) per[t].ties++;
             if (ctx.overflow) per[t].overflows++;
         }

@@ -108,6 +108,11 @@ void orc_move_and_slide(orc_world *w, orc_state *inout, int32_t n, const orc_par
                         const float gravity[3], uint32_t flags, int32_t order, int32_t n_threads,
                         orc_stats *stats);
 
+typedef struct orc_platform { float aabb_min[3], aabb_max[3], delta[3]; } orc_platform;
+void orc_move_and_slide_ex(orc_world *w, orc_state *inout, int32_t n, const orc_params *params, float dt,
+                           const float gravity[3], uint32_t flags, int32_t order, int32_t n_threads,
+                           orc_stats *stats, const orc_platform *platforms, int32_t n_platforms);
+
 /* narrow-phase primitives exposed for known-answer tests */
 float orc_segment_triangle_distance(const float center[3], float half_height, const float v0[3],
                                     const float v1[3], const float v2[3], float seg_pt[3], float tri_pt[3]);

@@ -35,6 +35,7 @@ STATE = np.dtype([("position", "<f8", 3), ("velocity", "<f8", 3), ("ground_norma
 assert STATE.itemsize == 168 and CAST.itemsize == 40 and CAST_HIT.itemsize == 44 and RAY.itemsize == 32
 assert RAY_HIT.itemsize == 32 and CAPSULE.itemsize == 24 and PARAMS.itemsize == 52
 
+PLATFORM = np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("delta", "<f4", 3)])
 ORDER_REFERENCE, ORDER_CANONICAL = 0, 1
 
 
@@ -86,6 +87,8 @@ def lib():
                                               C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_move_and_slide.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_void_p,
                                          C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
+        L.orc_move_and_slide_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_void_p,
+                                            C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_segment_triangle_distance.restype = C.c_float
         L.orc_segment_triangle_distance.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 5
         L.orc_segment_triangle_distance_batch.argtypes = [C.c_int32] + [C.c_void_p] * 6
@@ -219,13 +222,14 @@ class OracleWorld:
         return out, counts, overflow
 
     def move_and_slide(self, states, params, dt=1.0 / 60.0, gravity=(0.0, -98.0, 0.0), flags=1,
-                       order=ORDER_CANONICAL, n_threads=1, stats=None):
+                       order=ORDER_CANONICAL, n_threads=1, stats=None, platforms=None):
         """In place on `states` (a STATE array); returns it."""
         assert states.dtype == STATE and states.flags["C_CONTIGUOUS"]
         params = np.ascontiguousarray(params, PARAMS)
         g = np.asarray(gravity, np.float32)
-        lib().orc_move_and_slide(self._h, _ptr(states), len(states), _ptr(params), np.float32(dt), _ptr(g), flags,
-                                 order, n_threads, C.byref(stats) if stats is not None else None)
+        pl = np.ascontiguousarray(platforms if platforms is not None else np.zeros(0, PLATFORM), PLATFORM)
+        lib().orc_move_and_slide_ex(self._h, _ptr(states), len(states), _ptr(params), np.float32(dt), _ptr(g), flags,
+                                    order, n_threads, C.byref(stats) if stats is not None else None, _ptr(pl), len(pl))
         return states
 
 

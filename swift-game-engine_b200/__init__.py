@@ -45,6 +45,7 @@ STATE = np.dtype([("position", "<f8", 3), ("velocity", "<f8", 3), ("ground_norma
                   ("grounded", "u1"), ("grounded_near", "u1"), ("ground_sliding", "u1"), ("_pad", "u1", 5)])
 assert STATE.itemsize == 168 and CAST.itemsize == 40 and CAST_HIT.itemsize == 44 and RAY.itemsize == 32
 
+PLATFORM = np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("delta", "<f4", 3)])
 CAST_ALL, CAST_BLOCKING, CAST_GROUND = 0, 1, 2
 MAS_APPLY_GRAVITY = 1
 LAYER_ALL = 0xFFFFFFFF
@@ -83,7 +84,8 @@ EXPORTS = [
     "cq_static_mesh_geometry", "cq_raycast_batch", "cq_capsule_cast_batch", "cq_capsule_overlap_batch",
     "cq_capsule_overlap_all_batch", "cq_raycast_device", "cq_capsule_cast_device", "cq_capsule_overlap_device",
     "cq_capsule_overlap_all_device", "cq_controller_params_default", "cq_character_state_init",
-    "cq_move_and_slide_batch", "cq_move_and_slide_device", "cq_world_set_counting", "cq_world_read_counters",
+    "cq_move_and_slide_batch", "cq_move_and_slide_device", "cq_move_and_slide_batch_ex",
+    "cq_move_and_slide_device_ex", "cq_world_set_counting", "cq_world_read_counters",
     "cq_host_alloc", "cq_host_free", "cq_last_error", "cq_version",
 ]
 
@@ -146,6 +148,8 @@ def lib():
         L.cq_character_state_init.argtypes = [vp, vp, vp]
         L.cq_move_and_slide_batch.argtypes = [vp, vp, i32, vp, f32, vp, u32]
         L.cq_move_and_slide_device.argtypes = [vp, vp, i32, vp, f32, vp, u32, vp]
+        L.cq_move_and_slide_batch_ex.argtypes = [vp, vp, i32, vp, f32, vp, u32, vp, i32]
+        L.cq_move_and_slide_device_ex.argtypes = [vp, vp, i32, vp, f32, vp, u32, vp, i32, vp]
         L.cq_world_set_counting.argtypes = [vp, i32]
         L.cq_world_read_counters.argtypes = [vp, C.POINTER(Counters), i32]
         _lib = L
@@ -355,12 +359,15 @@ class CollisionQuery:
         return out, counts, overflow
 
     # KinematicMoveStopSystem.fixedUpdate body for a batch (Systems.swift:1842-1901)
-    def move_and_slide(self, states, params, dt=1.0 / 60.0, gravity=(0.0, -98.0, 0.0), flags=MAS_APPLY_GRAVITY):
+    def move_and_slide(self, states, params, dt=1.0 / 60.0, gravity=(0.0, -98.0, 0.0), flags=MAS_APPLY_GRAVITY,
+                       platforms=None):
+        """platforms: optional PLATFORM record array (kinematic platforms: world AABB + motion of this step)."""
         assert states.dtype == STATE and states.flags["C_CONTIGUOUS"]
         params = np.ascontiguousarray(params, PARAMS)
         g = np.asarray(gravity, np.float32)
-        _check(lib().cq_move_and_slide_batch(self._h, _ptr(states), len(states), _ptr(params), C.c_float(dt), _ptr(g),
-                                             flags))
+        pl = np.ascontiguousarray(platforms if platforms is not None else np.zeros(0, PLATFORM), PLATFORM)
+        _check(lib().cq_move_and_slide_batch_ex(self._h, _ptr(states), len(states), _ptr(params), C.c_float(dt), _ptr(g),
+                                                flags, _ptr(pl), len(pl)))
         return states
 
     def move_and_slide_device(self, d_states_ptr, n, params, dt=1.0 / 60.0, gravity=(0.0, -98.0, 0.0),

@@ -431,10 +431,15 @@ int cq_capsule_overlap_all_device(cq_world *w, const cq_capsule *d_q, int32_t n,
     }
     return launch_overlap_all(w, d_q, n, max_hits, d_out, d_counts, d_overflow, pick_stream(w, stream));
 }
+int cq_move_and_slide_device_ex(cq_world *w, cq_character_state *d_inout, int32_t n, const cq_controller_params *params,
+                                float dt, const float gravity[3], uint32_t flags, const cq_platform *platforms,
+                                int32_t n_platforms, void *stream) {
+    if (!w || n < 0 || !params || !gravity || (n > 0 && !d_inout)) return CQ_ERR_INVALID;
+    return launch_move_and_slide(w, d_inout, n, *params, dt, gravity, flags, platforms, n_platforms, pick_stream(w, stream));
+}
 int cq_move_and_slide_device(cq_world *w, cq_character_state *d_inout, int32_t n, const cq_controller_params *params, float dt,
                              const float gravity[3], uint32_t flags, void *stream) {
-    if (!w || n < 0 || !params || !gravity || (n > 0 && !d_inout)) return CQ_ERR_INVALID;
-    return launch_move_and_slide(w, d_inout, n, *params, dt, gravity, flags, pick_stream(w, stream));
+    return cq_move_and_slide_device_ex(w, d_inout, n, params, dt, gravity, flags, nullptr, 0, stream);
 }
 
 int cq_raycast_batch(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out) {
@@ -495,11 +500,17 @@ int cq_capsule_overlap_all_batch(cq_world *w, const cq_capsule *q, int32_t n, in
 
 int cq_move_and_slide_batch(cq_world *w, cq_character_state *inout, int32_t n, const cq_controller_params *params, float dt,
                             const float gravity[3], uint32_t flags) {
+    return cq_move_and_slide_batch_ex(w, inout, n, params, dt, gravity, flags, nullptr, 0);
+}
+
+int cq_move_and_slide_batch_ex(cq_world *w, cq_character_state *inout, int32_t n, const cq_controller_params *params, float dt,
+                               const float gravity[3], uint32_t flags, const cq_platform *platforms, int32_t n_platforms) {
     if (!w || n < 0 || !params || !gravity || (n > 0 && !inout)) return CQ_ERR_INVALID;
     CQ_CUDA(cudaStreamSynchronize(w->stream));
     return run_batch(w, inout, sizeof(cq_character_state), inout, sizeof(cq_character_state), n,
                      [&](void *di, void *, int cnt, int, cudaStream_t st) {
-                         return launch_move_and_slide(w, (cq_character_state *)di, cnt, *params, dt, gravity, flags, st);
+                         return launch_move_and_slide(w, (cq_character_state *)di, cnt, *params, dt, gravity, flags, platforms,
+                                                      n_platforms, st);
                      },
                      /*inPlace=*/true, &w->hintMas);
 }

@@ -72,6 +72,8 @@ struct cq_world {
     float buildMs = 0, refitMs = 0;
     int counting = 0;
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
+    int occ[5][2] = {}; // resident CTAs per SM of each persistent kernel ([counting build]), filled on first launch
+    int numSms = 0;
     uint64_t launches = 0;
     cq::ScratchBuf nodeScratch[4], orderScratch[4];
     uint32_t orderSeq = 0;
@@ -123,5 +125,5 @@ int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, c
                        uint8_t *d_overflow, cudaStream_t st);
 // cq_mas.cu
 int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p, float dt,
-                          const float g[3], uint32_t flags, cudaStream_t st);
+                          const float g[3], uint32_t flags, const cq_platform *platforms, int nPlatforms, cudaStream_t st);
 } // namespace cq

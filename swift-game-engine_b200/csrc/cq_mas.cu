@@ -14,6 +14,8 @@
 // the next query), T (BVH walk to the next candidate) and E (one segment-triangle distance evaluation).
 // Double precision exactly where the reference uses Double (velocity; SYS:792,882,958,1045,1368).
 #include "cq_pool.cuh"
+#include <cstring>
+
 #include "cq_internal.h"
 
 namespace cq {
@@ -26,12 +28,68 @@ namespace cq {
 #define MAS_SMEM_BYTES \
     (sizeof(CharCtx) * MAS_THREADS + sizeof(QShared) * MAS_THREADS + sizeof(uint32_t) * CQ_POOL_WORDS * MAS_WARPS)
 
+#define MAS_MAX_PLATFORMS 64
+
 struct MasArgs {
     cq_controller_params p;
     float dt;
     float gx, gy, gz;
     uint32_t flags;
+    int nPlatforms;
+    cq_platform platforms[MAS_MAX_PLATFORMS]; // kinematic platforms travel in the kernel arguments (2.3 KB at most)
 };
+
+// PlatformCarry.computeDelta (SYS:644-732): carry by the platform stood on, push by a platform moving into the side
+__device__ __noinline__ f3 platform_carry_delta(f3 position, const cq_controller_params &c, const cq_platform *platforms,
+                                                int nPlatforms) {
+    float capsuleHalf = c.half_height + c.radius;
+    float baseY = position.y - capsuleHalf;
+    f3 capMin = {position.x - c.radius, position.y - capsuleHalf, position.z - c.radius};
+    f3 capMax = {position.x + c.radius, position.y + capsuleHalf, position.z + c.radius};
+    float sideTol = smax(c.skin_width, c.ground_snap_skin);
+    f3 bestCarry = {0, 0, 0}, pushDelta = {0, 0, 0};
+    for (int k = 0; k < nPlatforms; k++) {
+        const cq_platform &pl = platforms[k];
+        f3 pDelta = {pl.delta[0], pl.delta[1], pl.delta[2]};
+        if (len2(pDelta) < 1e-8f) continue;
+        f3 amin = {pl.aabb_min[0], pl.aabb_min[1], pl.aabb_min[2]}, amax = {pl.aabb_max[0], pl.aabb_max[1], pl.aabb_max[2]};
+        f3 emin = amin - mk3(sideTol, sideTol, sideTol), emax = amax + mk3(sideTol, sideTol, sideTol);
+        bool overlap = capMin.x <= emax.x && capMax.x >= emin.x && capMin.y <= emax.y && capMax.y >= emin.y &&
+                       capMin.z <= emax.z && capMax.z >= emin.z;
+        if (!overlap) continue;
+        bool withinXZ = position.x >= amin.x - c.radius && position.x <= amax.x + c.radius &&
+                        position.z >= amin.z - c.radius && position.z <= amax.z + c.radius;
+        float topY = amax.y;
+        float topTol = c.snap_distance + smax(c.skin_width, c.ground_snap_skin) + 0.05f;
+        bool onTop = withinXZ && baseY >= topY - topTol && baseY <= topY + topTol;
+        if (onTop) {
+            if (len2(pDelta) > len2(bestCarry)) bestCarry = pDelta;
+        } else {
+            float yMin = amin.y - capsuleHalf, yMax = amax.y + capsuleHalf;
+            if (position.y >= yMin && position.y <= yMax) {
+                bool outsideX = position.x < amin.x - c.radius || position.x > amax.x + c.radius;
+                bool outsideZ = position.z < amin.z - c.radius || position.z > amax.z + c.radius;
+                if (!outsideX && !outsideZ) continue;
+                float cx = smax(amin.x, smin(position.x, amax.x));
+                float cz = smax(amin.z, smin(position.z, amax.z));
+                float dx = position.x - cx, dz = position.z - cz;
+                float sideDistSq = dx * dx + dz * dz;
+                float sidePushTol = c.radius + sideTol;
+                if (sideDistSq <= sidePushTol * sidePushTol) {
+                    float dirLen = sqrtf(smax(sideDistSq, 0.0f));
+                    if (dirLen > 1e-5f) {
+                        f3 dir = {dx / dirLen, 0.0f, dz / dirLen};
+                        float moveToward = dot(mk3(pDelta.x, 0.0f, pDelta.z), dir);
+                        if (moveToward > 0.0f) pushDelta = pushDelta + mk3(pDelta.x, 0.0f, pDelta.z);
+                    }
+                }
+            }
+        }
+    }
+    if (len2(bestCarry) > 1e-8f) return bestCarry;
+    if (len2(pushDelta) > 1e-8f) return pushDelta;
+    return mk3(0, 0, 0);
+}
 
 enum { W_NONE = 0, W_DEPEN, W_SLIDE, W_SNAP, W_FALL, W_OFFSET };
 enum { NX_LOAD = 0, NX_DEPEN, NX_SLIDE, NX_SNAP, NX_FALL, NX_GATE, NX_OFFSET, NX_FINISH };
@@ -467,6 +525,11 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
                     }
                 }
             }
+            if (A.nPlatforms > 0) { // applyPlatformDelta (SYS:1618-1633)
+                f3 position = ld3(c.pos);
+                f3 platformDelta = platform_carry_delta(position, A.p, A.platforms, A.nPlatforms);
+                if (len2(platformDelta) > 1e-8f) st3(c.pos, position + platformDelta);
+            }
             // VelocityGate (SYS:1037-1051)
             if (wasGrounded && wasGroundedNear && vel.y < 0.0) vel.y = 0.0;
             d3 remD = vel * (double)A.dt;
@@ -575,7 +638,8 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
 
 template <bool COUNT>
 __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states,
-                                                                                int n, MasArgs A, int ownersPerWarp,
+                                                                                int n, const __grid_constant__ MasArgs A,
+                                                                                int ownersPerWarp,
                                                                                 uint2 *nodeScratch, int *workCounter,
                                                                                 const uint32_t *__restrict__ order,
                                                                                 unsigned long long *gctr) {
@@ -599,15 +663,23 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     pool_flush_counters(ctr, gctr, COUNT);
 }
 
+#define CQ_OCC_SLOT 0
 int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p, float dt,
-                          const float g[3], uint32_t flags, cudaStream_t st) {
+                          const float g[3], uint32_t flags, const cq_platform *platforms, int nPlatforms, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
+    if (nPlatforms < 0 || nPlatforms > MAS_MAX_PLATFORMS || (nPlatforms > 0 && !platforms)) {
+        set_error("cq_move_and_slide: 0..%d platforms supported, got %d", MAS_MAX_PLATFORMS, nPlatforms);
+        return CQ_ERR_INVALID;
+    }
     MasArgs A;
+    memset(&A, 0, sizeof(A));
     A.p = p;
     A.dt = dt;
     A.gx = g[0], A.gy = g[1], A.gz = g[2];
     A.flags = flags;
-    static int blocksPerSm[2] = {0, 0}, numSms = 0;
+    A.nPlatforms = nPlatforms;
+    for (int k = 0; k < nPlatforms; k++) A.platforms[k] = platforms[k];
+    int *blocksPerSm = w->occ[CQ_OCC_SLOT]; int &numSms = w->numSms;
     const int ci = w->counting ? 1 : 0;
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;

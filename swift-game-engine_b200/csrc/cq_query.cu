@@ -313,9 +313,11 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
 // ---------------------------------------------------------------- launchers
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+#undef CQ_OCC_SLOT
+#define CQ_OCC_SLOT 1
 int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
-    static int blocksPerSm[2] = {0, 0}, numSms = 0;
+    int *blocksPerSm = w->occ[CQ_OCC_SLOT]; int &numSms = w->numSms;
     const int ci = w->counting ? 1 : 0;
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;
@@ -336,9 +338,11 @@ int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, 
     return check_cuda(cudaGetLastError(), "k_raycast");
 }
 
+#undef CQ_OCC_SLOT
+#define CQ_OCC_SLOT 2
 int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
-    static int blocksPerSm[2] = {0, 0}, numSms = 0;
+    int *blocksPerSm = w->occ[CQ_OCC_SLOT]; int &numSms = w->numSms;
     const int ci = w->counting ? 1 : 0;
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;
@@ -363,11 +367,13 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }
 
+#undef CQ_OCC_SLOT
+#define CQ_OCC_SLOT (3 + (ALL ? 1 : 0))
 template <bool ALL>
 static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,
                                uint8_t *d_overflow, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
-    static int blocksPerSm = 0, numSms = 0;
+    int &blocksPerSm = w->occ[CQ_OCC_SLOT][0]; int &numSms = w->numSms;
     if (!blocksPerSm) {
         cudaDeviceProp prop;
         CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));

@@ -274,6 +274,18 @@ def terrain_scene(cells=2236, cell=2.0, seed=0xC0111DE4):
     return [part(pos, idx, entity_id=0)], half
 
 
+def platform_record(positions, model, prev_translation, translation):
+    """cq_platform of a kinematic platform: world AABB of its mesh under the current model matrix
+    (meshWorldAABB, Systems.swift:627-642) and positionF - prevPositionF."""
+    m = np.asarray(model, f32).reshape(4, 4).T
+    p = np.asarray(positions, f32).reshape(-1, 3)
+    w = ((m[:3, 0][None, :] * p[:, 0:1] + m[:3, 1][None, :] * p[:, 1:2]) + m[:3, 2][None, :] * p[:, 2:3]) + m[:3, 3][None, :]
+    rec = np.zeros(1, np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("delta", "<f4", 3)]))
+    rec["aabb_min"], rec["aabb_max"] = w.min(0), w.max(0)
+    rec["delta"] = np.asarray(translation, f32) - np.asarray(prev_translation, f32)
+    return rec
+
+
 # ---------------------------------------------------------------- dtypes of the query records (include/cq.h)
 
 RAY = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("max_distance", "<f4"), ("mask", "<u4")])

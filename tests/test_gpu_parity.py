@@ -384,3 +384,39 @@ def test_parameter_edge_cases(cq, orc, scenes):
     assert ov.sum() > 100 and np.array_equal(ov, rov) and np.array_equal(cnt, rcnt) and got.tobytes() == ref.tobytes()
     for w in (g, o, gr, orr):
         w.close()
+
+
+def test_kinematic_platforms_carry_and_push(cq, orc, scenes):
+    """applyPlatformDelta + the dynamic triangle set: an elevator and a horizontal mover (DemoScene-like) in the
+    dynamic set, moved and refitted every step; characters on top of / beside / far from them."""
+    bv, bi = scenes.box_mesh(4.0)
+    v, i = scenes.plane_mesh(80.0)
+    t0 = [np.float32([0, -1.0, 0]), np.float32([12, -1.0, 0])]
+    parts = [scenes.part(v, i, scenes.trs_model((0, -3, 0)), entity_id=0),
+             scenes.part(bv, bi, scenes.trs_model(t0[0]), is_dynamic=True, entity_id=1),
+             scenes.part(bv, bi, scenes.trs_model(t0[1]), is_dynamic=True, entity_id=2)]
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    rng = np.random.default_rng(3)
+    n = 3000
+    pos = np.stack([rng.uniform(-6, 18, n), np.full(n, -0.45), rng.uniform(-5, 5, n)], axis=1).astype(np.float32)
+    on_top = (np.abs(pos[:, 0]) < 2) & (np.abs(pos[:, 2]) < 2) | (np.abs(pos[:, 0] - 12) < 2) & (np.abs(pos[:, 2]) < 2)
+    pos[on_top, 1] = 1.0 + 2.5 + 0.05
+    vel = (rng.uniform(-3, 3, (n, 3)) * [1, 0, 1]).astype(np.float32)
+    sg, so = cq.init_states(pos, vel), orc.init_states(pos, vel)
+    prev = [t.copy() for t in t0]
+    for step in range(1, 7):
+        cur = [t0[0] + np.float32([0, 0.08 * step, 0]), t0[1] + np.float32([0.12 * step, 0, 0])]
+        models = [scenes.trs_model(c) for c in cur]
+        g.update_transforms([1, 2], models)
+        o.update_transforms([1, 2], models)
+        plats = np.concatenate([scenes.platform_record(bv, models[k], prev[k], cur[k]) for k in range(2)])
+        g.move_and_slide(sg, cq.default_params(), platforms=plats)
+        o.move_and_slide(so, orc.default_params(), platforms=plats, order=orc.ORDER_CANONICAL)
+        assert sg.tobytes() == so.tobytes(), step
+        prev = cur
+    carried = sg["position"][:, 1] > 2.0
+    assert carried.sum() > 20 and (sg["position"][on_top, 1] > pos[on_top, 1] + 0.2).mean() > 0.5
+    with pytest.raises(cq.CQError):
+        g.move_and_slide(sg, cq.default_params(), platforms=np.zeros(65, cq.PLATFORM))
+    g.close()
+    o.close()

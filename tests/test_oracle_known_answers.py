@@ -227,3 +227,34 @@ def test_empty_world_free_fall(orc, scenes):
     vy = -98.0 * float(dt)
     assert s["velocity"][0][1] == pytest.approx(vy) and s["position"][0][1] == pytest.approx(vy * float(dt), rel=1e-5)
     assert s["grounded"][0] == 0 and s["ground_distance"][0] == F32_MAX
+
+
+def test_platform_carry_and_side_push(orc, scenes):
+    """PlatformCarry.computeDelta (Systems.swift:644-732): a character standing on an elevator is carried by the
+    platform's motion; a platform moving into a character's side pushes it horizontally; a platform that does not
+    move (|delta|^2 < 1e-8) or is out of reach does nothing."""
+    bv, bi = scenes.box_mesh(4.0)
+    prev, cur = np.float32([0, 0, 0]), np.float32([0.05, 0.1, 0])  # elevator top at y = 2 -> 2.1
+    model = scenes.trs_model(cur)
+    parts = [big_floor(scenes, y=-3.0, eid=0), scenes.part(bv, bi, model, is_dynamic=True, entity_id=1)]
+    w = orc.OracleWorld(parts)
+    plat = scenes.platform_record(bv, model, prev, cur)
+    p = orc.default_params()
+    rest = 2.1 + 1.5 + 1.0 + 0.05  # standing on the moved top with groundSnapSkin
+    s = orc.init_states([[0.0, rest - 0.1, 0.0], [30.0, -0.45, 0.0], [-(2.0 + 1.5 + 0.2) + 0.05, -0.45, 0.0]])
+    before = s["position"].copy()
+    w.move_and_slide(s, p, platforms=plat, order=orc.ORDER_REFERENCE)
+    assert s["position"][0][0] == pytest.approx(before[0][0] + 0.05, abs=1e-5)  # carried sideways with the platform
+    # carried up by 0.1 too, then one step of gravity (-98/60^2 = -0.027) before the ground probe catches it
+    assert rest - 0.05 <= s["position"][0][1] <= rest + 0.01 and s["grounded"][0] == 1
+    assert np.allclose(s["position"][1], before[1], atol=1e-5)  # far away: untouched
+    s2 = orc.init_states([[-(2.0 + 1.5 + 0.2) + 0.05, -0.45, 0.0]])
+    mover = plat.copy()
+    mover["delta"] = (-0.1, 0, 0)  # moving toward -x, into the character standing left of it
+    w.move_and_slide(s2, p, platforms=mover, order=orc.ORDER_REFERENCE)
+    assert s2["position"][0][0] < before[2][0] - 0.05
+    still = plat.copy()
+    still["delta"] = (5e-5, 0, 0)
+    s3 = orc.init_states([[0.0, rest, 0.0]])
+    w.move_and_slide(s3, p, platforms=still, order=orc.ORDER_REFERENCE)
+    assert s3["position"][0][0] == pytest.approx(0.0, abs=1e-6)
