@@ -244,6 +244,13 @@ typedef struct cq_character_state { /* PhysicsBodyComponent + CharacterControlle
 } cq_character_state; /* 168 bytes */
 
 #define CQ_MAS_APPLY_GRAVITY 1u /* run GravitySystem's rule first (Systems.swift:603-619) */
+/* Every character of the batch is a solid agent (AgentCollisionComponent defaults, Components.swift): each slide
+ * iteration also sweeps the capsule against every other character's capsule, taken from a snapshot of positions and
+ * (post-gravity) velocities made before any character of the step moves (AgentSweepSolver / collectAgentStates,
+ * Systems.swift:1023-1091, 1592-1611), and HitSelector (1378-1399) picks between the static and the agent hit.
+ * The batch is the crowd: characters of different calls do not see each other, and a host-pointer call runs as one
+ * chunk.  Calls with this flag on one world must be stream-ordered (they share the snapshot scratch). */
+#define CQ_MAS_AGENTS 2u
 
 /* A kinematic platform as PlatformCarry.computeDelta sees it (Systems.swift:644-732): the world AABB of its
  * collision mesh under the CURRENT transform (meshWorldAABB, :627-642) and its motion over this fixed step

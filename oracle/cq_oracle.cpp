@@ -1020,17 +1020,181 @@ bool depenetrate(const StaticTriMesh &q, QueryCtx &ctx, F3 &position, Character 
     return true;
 }
 
-// SlideResolver.resolveHit with SlideOptions.kinematicMove, static hit only (SYS:1229-1375)
+// ---- capsule-capsule CCD between agents (SYS:1417-1590, 1023-1091)
+struct AgentState { // AgentSweepState (SYS:1023-1029): snapshot taken before any character of the step moves
+    F3 position, velocity;
+    float radius, halfHeight;
+};
+struct AgentSnapshot {
+    const AgentState *agents;
+    int count;
+};
+struct CapsuleCapsuleHit {
+    float toi;
+    F3 normal;
+    int other;
+};
+
+bool clampInterval(float start, float end, float &s, float &e) { // SYS:1417-1424
+    s = smax(start, 0.0f);
+    e = smin(end, 1.0f);
+    return !(e < s);
+}
+bool intervalGreaterEqual(float y0, float vy, float threshold, float &s, float &e) { // SYS:1426-1436
+    if (fabsf(vy) < 1e-6f) {
+        s = 0, e = 1;
+        return y0 >= threshold;
+    }
+    float t = (threshold - y0) / vy;
+    if (vy > 0) return clampInterval(t, 1, s, e);
+    return clampInterval(0, t, s, e);
+}
+bool intervalLessEqual(float y0, float vy, float threshold, float &s, float &e) { // SYS:1438-1448
+    if (fabsf(vy) < 1e-6f) {
+        s = 0, e = 1;
+        return y0 <= threshold;
+    }
+    float t = (threshold - y0) / vy;
+    if (vy > 0) return clampInterval(0, t, s, e);
+    return clampInterval(t, 1, s, e);
+}
+bool earliestRoot(float A, float B, float C, float tMin, float tMax, float &out) { // SYS:1450-1472
+    const float eps = 1e-6f;
+    if (fabsf(A) < eps) {
+        if (fabsf(B) < eps) {
+            out = tMin;
+            return C <= 0;
+        }
+        float t = -C / B;
+        out = t;
+        return t >= tMin && t <= tMax;
+    }
+    float disc = B * B - 4 * A * C;
+    if (disc < 0) return false;
+    float sqrtD = sqrtf(disc);
+    float inv2A = 1 / (2 * A);
+    float t0 = (-B - sqrtD) * inv2A, t1 = (-B + sqrtD) * inv2A;
+    float enter = smin(t0, t1), exit_ = smax(t0, t1);
+    float s = smax(enter, tMin), e = smin(exit_, tMax);
+    out = s;
+    return e >= s;
+}
+float capsuleCapsuleSeparationY(float yRel, float halfHeightSum) { // SYS:1474-1482
+    if (yRel > halfHeightSum) return yRel - halfHeightSum;
+    if (yRel < -halfHeightSum) return yRel + halfHeightSum;
+    return 0;
+}
+F3 capsuleCapsuleHitNormal(F3 rel, float halfHeightSum) { // SYS:1484-1497
+    float sepY = capsuleCapsuleSeparationY(rel.y, halfHeightSum);
+    F3 sep = {rel.x, sepY, rel.z};
+    float lenSq = length_squared(sep);
+    if (lenSq > 1e-8f) return sep / sqrtf(lenSq);
+    F3 lateral = {rel.x, 0, rel.z};
+    float lateralLenSq = length_squared(lateral);
+    if (lateralLenSq > 1e-8f) return lateral / sqrtf(lateralLenSq);
+    return {1, 0, 0};
+}
+bool capsuleCapsuleOverlap(F3 rel, float radiusSum, float halfHeightSum) { // SYS:1499-1503
+    float sepY = capsuleCapsuleSeparationY(rel.y, halfHeightSum);
+    float distSq = rel.x * rel.x + rel.z * rel.z + sepY * sepY;
+    return distSq <= radiusSum * radiusSum;
+}
+bool capsuleCapsuleSweep(F3 from, F3 delta, float radius, float halfHeight, int other, F3 otherPos, F3 otherDelta,
+                         float otherRadius, float otherHalfHeight, CapsuleCapsuleHit &out) { // SYS:1505-1590
+    F3 relStart = from - otherPos, relDelta = delta - otherDelta;
+    float rSum = radius + otherRadius, hSum = halfHeight + otherHalfHeight;
+    float relLen = length(relDelta), moveLen = length(delta);
+    if (relLen < 1e-6f) {
+        if (capsuleCapsuleOverlap(relStart, rSum, hSum)) {
+            out = {0, capsuleCapsuleHitNormal(relStart, hSum), other};
+            return true;
+        }
+        return false;
+    }
+    float y0 = relStart.y, vy = relDelta.y, vx = relDelta.x, vz = relDelta.z, r0x = relStart.x, r0z = relStart.z;
+    bool have = false;
+    float bestT = 0, s, e, t;
+    if (intervalGreaterEqual(y0, vy, hSum, s, e)) {
+        float A = vx * vx + vz * vz + vy * vy;
+        float B = 2 * (r0x * vx + r0z * vz + (y0 - hSum) * vy);
+        float C = r0x * r0x + r0z * r0z + (y0 - hSum) * (y0 - hSum) - rSum * rSum;
+        if (earliestRoot(A, B, C, s, e, t)) {
+            bestT = t;
+            have = true;
+        }
+    }
+    if (intervalLessEqual(y0, vy, -hSum, s, e)) {
+        float A = vx * vx + vz * vz + vy * vy;
+        float B = 2 * (r0x * vx + r0z * vz + (y0 + hSum) * vy);
+        float C = r0x * r0x + r0z * r0z + (y0 + hSum) * (y0 + hSum) - rSum * rSum;
+        if (earliestRoot(A, B, C, s, e, t)) {
+            if (!have || t < bestT) {
+                bestT = t;
+                have = true;
+            }
+        }
+    }
+    if (fabsf(vy) < 1e-6f) {
+        if (fabsf(y0) <= hSum) {
+            float A = vx * vx + vz * vz, B = 2 * (r0x * vx + r0z * vz), C = r0x * r0x + r0z * r0z - rSum * rSum;
+            if (earliestRoot(A, B, C, 0, 1, t)) {
+                if (!have || t < bestT) {
+                    bestT = t;
+                    have = true;
+                }
+            }
+        }
+    } else {
+        float t1 = (hSum - y0) / vy, t2 = (-hSum - y0) / vy;
+        if (clampInterval(smin(t1, t2), smax(t1, t2), s, e)) {
+            float A = vx * vx + vz * vz, B = 2 * (r0x * vx + r0z * vz), C = r0x * r0x + r0z * r0z - rSum * rSum;
+            if (earliestRoot(A, B, C, s, e, t)) {
+                if (!have || t < bestT) {
+                    bestT = t;
+                    have = true;
+                }
+            }
+        }
+    }
+    if (!have) return false;
+    F3 relAtHit = relStart + relDelta * bestT;
+    out = {bestT * moveLen, capsuleCapsuleHitNormal(relAtHit, hSum), other};
+    return true;
+}
+// AgentSweepSolver.bestHit (SYS:1053-1091): every other agent, strict '<' keeps the first of equal tois
+bool agentBestHit(F3 position, F3 remaining, float remainingLen, float baseMoveLen, float dt, int selfIndex,
+                  float selfRadius, float halfHeight, const AgentSnapshot &snap, CapsuleCapsuleHit &best) {
+    bool have = false;
+    float timeScale = baseMoveLen > 1e-6f ? smin(remainingLen / baseMoveLen, 1.0f) : 1.0f;
+    float segmentDt = dt * timeScale;
+    for (int k = 0; k < snap.count; k++) {
+        if (k == selfIndex) continue;
+        const AgentState &o = snap.agents[k];
+        F3 otherDelta = o.velocity * segmentDt;
+        CapsuleCapsuleHit hit;
+        if (capsuleCapsuleSweep(position, remaining, selfRadius, halfHeight, k, o.position, otherDelta, o.radius,
+                                o.halfHeight, hit)) {
+            if (!have || hit.toi < best.toi) {
+                best = hit;
+                have = true;
+            }
+        }
+    }
+    return have;
+}
+
+// SlideResolver.resolveHit with SlideOptions.kinematicMove (SYS:1229-1375); `agent` selects the .agentHit case
 bool slideResolveHit(F3 &remaining, float len, const CapsuleCastHit &sHit, Character &ch, bool wasGrounded,
-                     bool wasGroundedNear, F3 &position, bool haveCachedSide, F3 cachedSideNormal) {
+                     bool wasGroundedNear, F3 &position, bool haveCachedSide, F3 cachedSideNormal,
+                     const CapsuleCapsuleHit *agent = nullptr) {
     const orc_params &p = *ch.p;
     const orc_state &c = *ch.s;
-    float hitToi = sHit.toi;
-    F3 slideNormal = sHit.normal;
-    bool hitIsGroundLike = sHit.triangleNormal.y >= p.min_ground_dot;
-    float contactSkin = hitIsGroundLike ? p.ground_snap_skin : p.skin_width; // useGroundSnapSkinForStatic
-    F3 hitTriNormal = sHit.triangleNormal;
-    const bool hitIsStatic = true;
+    const bool hitIsStatic = agent == nullptr;
+    float hitToi = hitIsStatic ? sHit.toi : agent->toi;
+    F3 slideNormal = hitIsStatic ? sHit.normal : agent->normal;
+    bool hitIsGroundLike = hitIsStatic && sHit.triangleNormal.y >= p.min_ground_dot;
+    float contactSkin = !hitIsStatic ? 0.0f : (hitIsGroundLike ? p.ground_snap_skin : p.skin_width); // SYS:1255-1271
+    F3 hitTriNormal = hitIsStatic ? sHit.triangleNormal : f3(0, 0, 0);
 
     if (hitIsStatic && slideNormal.y < p.min_ground_dot && c.side_contact_frames > 0) { // SYS:1273-1292
         if (haveCachedSide) {
@@ -1110,9 +1274,12 @@ bool slideResolveHit(F3 &remaining, float len, const CapsuleCastHit &sHit, Chara
 
 // KinematicMoveStopSystem.resolveKinematicSweep without agents (SYS:1658-1765)
 void resolveKinematicSweep(const StaticTriMesh &q, QueryCtx &ctx, F3 &position, F3 &remaining, Character &ch,
-                           bool wasGrounded, bool wasGroundedNear) {
+                           bool wasGrounded, bool wasGroundedNear, const AgentSnapshot *snap = nullptr,
+                           int selfIndex = -1, float dt = 0) {
     orc_state &c = *ch.s;
     const orc_params &p = *ch.p;
+    F3 baseMove = f3(ch.velocity) * dt; // body.linearVelocityF * dt (SYS:1671-1672)
+    float baseMoveLen = length(baseMove);
     bool haveLast = false;
     F3 lastSlideNormal = {0, 0, 0};
     for (int it = 0; it < p.max_slide_iterations; it++) {
@@ -1128,7 +1295,36 @@ void resolveKinematicSweep(const StaticTriMesh &q, QueryCtx &ctx, F3 &position, 
                 sHit.normal = cachedN;
             }
         }
-        if (haveHit) {
+        CapsuleCapsuleHit aHit;
+        bool haveAgent = snap && agentBestHit(position, remaining, len, baseMoveLen, dt, selfIndex, p.radius, p.half_height,
+                                              *snap, aHit); // SYS:1695-1705
+        bool useAgent = false;
+        if (haveHit && haveAgent) { // HitSelector.selectBestHit (SYS:1378-1399)
+            float staticSkin = sHit.normal.y >= p.min_ground_dot ? p.ground_snap_skin : p.skin_width;
+            float staticStop = smax(sHit.toi - staticSkin, 0.0f), agentStop = smax(aHit.toi, 0.0f);
+            useAgent = !(staticStop <= agentStop);
+        } else if (haveAgent) {
+            useAgent = true;
+        }
+        if (useAgent) {
+            F3 hitNormal = aHit.normal;
+            bool shouldBreak = slideResolveHit(remaining, len, sHit, ch, wasGrounded, wasGroundedNear, position, false,
+                                               f3(0, 0, 0), &aHit);
+            if (haveLast) { // SYS:1744-1754
+                float dotN = dot(lastSlideNormal, hitNormal);
+                if (fabsf(dotN) < 0.98f) {
+                    F3 axis = cross(lastSlideNormal, hitNormal);
+                    float axisLen = length(axis);
+                    if (axisLen > 1e-5f) {
+                        F3 axisN = axis / axisLen;
+                        remaining = axisN * dot(remaining, axisN);
+                    }
+                }
+            }
+            lastSlideNormal = hitNormal;
+            haveLast = true;
+            if (shouldBreak) break;
+        } else if (haveHit) {
             F3 hitNormal = sHit.normal;
             bool haveCachedSide = false;
             F3 cachedSide = {0, 0, 0};
@@ -1304,7 +1500,8 @@ F3 platformCarryDelta(F3 position, const orc_params &c, const orc_platform *plat
 
 // one character, one fixed step: KinematicMoveStopSystem.fixedUpdate loop body (SYS:1842-1901)
 void moveAndSlideOne(const StaticTriMesh &q, QueryCtx &ctx, orc_state &s, const orc_params &p, float dt,
-                     F3 gravity, uint32_t flags, const orc_platform *platforms = nullptr, int nPlatforms = 0) {
+                     F3 gravity, uint32_t flags, const orc_platform *platforms = nullptr, int nPlatforms = 0,
+                     const AgentSnapshot *snap = nullptr, int selfIndex = -1) {
     Character ch;
     ch.s = &s;
     ch.p = &p;
@@ -1330,7 +1527,7 @@ void moveAndSlideOne(const StaticTriMesh &q, QueryCtx &ctx, orc_state &s, const 
         float into = dot(remaining, depenNormal);
         if (into < 0) remaining = remaining - depenNormal * into;
     }
-    resolveKinematicSweep(q, ctx, position, remaining, ch, wasGrounded, wasGroundedNear);
+    resolveKinematicSweep(q, ctx, position, remaining, ch, wasGrounded, wasGroundedNear, snap, selfIndex, dt);
     // resolveGroundContact (SYS:1767-1800)
     GroundProbeResult probe = groundProbe(q, ctx, position, ch, wasGroundedNear, ld3(s.ground_normal));
     GroundContactState gs = probe.state;
@@ -1634,12 +1831,27 @@ void orc_move_and_slide_ex(orc_world *w, orc_state *inout, int32_t n, const orc_
                            orc_stats *stats, const orc_platform *platforms, int32_t n_platforms) {
     std::vector<Stats> per(std::max(1, n_threads));
     F3 g = ld3(gravity);
+    // flags & 2: every character is a solid agent (AgentCollisionComponent defaults); collectAgentStates (SYS:1592-1611)
+    // snapshots position / velocity of all of them BEFORE the loop — after GravitySystem, which ran as system #3
+    std::vector<AgentState> agents;
+    AgentSnapshot snap = {nullptr, 0};
+    if (flags & 2u) {
+        agents.resize(n);
+        for (int i = 0; i < n; i++) {
+            D3 v = {inout[i].velocity[0], inout[i].velocity[1], inout[i].velocity[2]};
+            if ((flags & 1u) && !(inout[i].grounded && inout[i].grounded_near)) v = v + d3(g) * (double)dt;
+            agents[i] = {f3((float)inout[i].position[0], (float)inout[i].position[1], (float)inout[i].position[2]), f3(v),
+                         params->radius, params->half_height};
+        }
+        snap = {agents.data(), n};
+    }
     parallelFor(n, n_threads, [&](int t, int lo, int hi) {
         for (int i = lo; i < hi; i++) {
             QueryCtx ctx;
             ctx.order = order;
             ctx.stats = stats ? &per[t] : nullptr;
-            moveAndSlideOne(w->mesh, ctx, inout[i], *params, dt, g, flags, platforms, n_platforms);
+            moveAndSlideOne(w->mesh, ctx, inout[i], *params, dt, g, flags, platforms, n_platforms,
+                            (flags & 2u) ? &snap : nullptr, i);
             if (ctx.tie) per[t].ties++;
             if (ctx.overflow) per[t].overflows++;
         }
@@ -1662,6 +1874,20 @@ void orc_segment_triangle_distance_batch(int32_t n, const float *centers, const 
         dist[i] = r.dist;
         st3(seg + 3 * i, r.seg);
         st3(tri + 3 * i, r.tri);
+    }
+}
+// capsuleCapsuleSweep, packed: from/delta/otherPos/otherDelta (n,3), radius/halfHeight pairs (n,4) = r, hh, oR, oHh
+// -> hit (n), toi (n), normal (n,3)
+void orc_capsule_capsule_sweep_batch(int32_t n, const float *from, const float *delta, const float *otherPos,
+                                     const float *otherDelta, const float *dims, int32_t *hit, float *toi, float *normal) {
+    for (int i = 0; i < n; i++) {
+        CapsuleCapsuleHit h = {0, f3(0, 0, 0), -1};
+        hit[i] = capsuleCapsuleSweep(ld3(from + 3 * i), ld3(delta + 3 * i), dims[4 * i], dims[4 * i + 1], i,
+                                     ld3(otherPos + 3 * i), ld3(otherDelta + 3 * i), dims[4 * i + 2], dims[4 * i + 3], h)
+                     ? 1
+                     : 0;
+        toi[i] = h.toi;
+        st3(normal + 3 * i, h.normal);
     }
 }
 void orc_ray_triangle_batch(int32_t n, const float *origins, const float *dirs, const float *tris, float *tout,

@@ -120,6 +120,9 @@ void orc_segment_triangle_distance_batch(int32_t n, const float *centers, const 
                                          float *dist, float *seg, float *tri);
 void orc_ray_triangle_batch(int32_t n, const float *origins, const float *dirs, const float *tris, float *tout,
                             int32_t *hit);
+/* capsuleCapsuleSweep (Systems.swift:1505-1590), packed; dims (n,4) = radius, halfHeight, otherRadius, otherHalfHeight */
+void orc_capsule_capsule_sweep_batch(int32_t n, const float *from, const float *delta, const float *otherPos,
+                                     const float *otherDelta, const float *dims, int32_t *hit, float *toi, float *normal);
 float orc_closest_point_on_triangle(const float p[3], const float a[3], const float b[3],
                                     const float c[3], float out_pt[3]);
 float orc_segment_segment_distance_sq(const float p1[3], const float q1[3], const float p2[3],

@@ -93,6 +93,7 @@ def lib():
         L.orc_segment_triangle_distance.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 5
         L.orc_segment_triangle_distance_batch.argtypes = [C.c_int32] + [C.c_void_p] * 6
         L.orc_ray_triangle_batch.argtypes = [C.c_int32] + [C.c_void_p] * 5
+        L.orc_capsule_capsule_sweep_batch.argtypes = [C.c_int32] + [C.c_void_p] * 8
         L.orc_closest_point_on_triangle.restype = C.c_float
         L.orc_closest_point_on_triangle.argtypes = [C.c_void_p] * 5
         L.orc_segment_segment_distance_sq.restype = C.c_float
@@ -231,6 +232,15 @@ class OracleWorld:
         lib().orc_move_and_slide_ex(self._h, _ptr(states), len(states), _ptr(params), np.float32(dt), _ptr(g), flags,
                                     order, n_threads, C.byref(stats) if stats is not None else None, _ptr(pl), len(pl))
         return states
+
+
+def capsule_capsule_sweep_batch(frm, delta, other_pos, other_delta, dims):
+    """capsuleCapsuleSweep over n packed cases; dims (n,4) = radius, halfHeight, otherRadius, otherHalfHeight."""
+    a = [np.ascontiguousarray(x, np.float32) for x in (frm, delta, other_pos, other_delta, dims)]
+    n = len(a[0])
+    hit, toi, normal = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+    lib().orc_capsule_capsule_sweep_batch(n, *[_ptr(x) for x in a], _ptr(hit), _ptr(toi), _ptr(normal))
+    return hit, toi, normal
 
 
 def segment_triangle_distance(center, half_height, v0, v1, v2):

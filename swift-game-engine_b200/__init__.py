@@ -48,6 +48,7 @@ assert STATE.itemsize == 168 and CAST.itemsize == 40 and CAST_HIT.itemsize == 44
 PLATFORM = np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("delta", "<f4", 3)])
 CAST_ALL, CAST_BLOCKING, CAST_GROUND = 0, 1, 2
 MAS_APPLY_GRAVITY = 1
+MAS_AGENTS = 2  # characters of the batch collide with each other (capsule-capsule CCD)
 LAYER_ALL = 0xFFFFFFFF
 
 

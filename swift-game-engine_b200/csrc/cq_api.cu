@@ -81,13 +81,14 @@ using namespace cq;
 // >> PCIe time of its bytes) the next one uses two chunks only, because every chunk kernel pays its own tail.
 template <class In, class Out, class Launch>
 static int run_batch(cq_world *w, const In *in, size_t inStride, Out *out, size_t outStride, int n, Launch launch,
-                     bool inPlace = false, float *computeBoundHint = nullptr) {
+                     bool inPlace = false, float *computeBoundHint = nullptr, bool singleChunk = false) {
     if (n <= 0) return CQ_OK;
     CQ_CUDA(cudaSetDevice(w->device));
     const int CH = 1 << 17;
     int nChunks = (n + CH - 1) / CH;
     if (computeBoundHint && *computeBoundHint > 3.0f && nChunks > 2) nChunks = 2;
     if (nChunks > CQ_PIPE_EVENTS) nChunks = CQ_PIPE_EVENTS;
+    if (singleChunk) nChunks = 1; // the units interact (agents): every one must be resident before the kernel starts
     const auto t0 = std::chrono::steady_clock::now();
     int chunk = (n + nChunks - 1) / nChunks;
     int r;
@@ -270,6 +271,7 @@ void cq_world_destroy(cq_world *w) {
     cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork);
     cudaFree(w->in.ptr), cudaFree(w->out.ptr), cudaFree(w->aux.ptr), cudaFree(w->aux2.ptr);
     for (int k = 0; k < 4; k++) cudaFree(w->nodeScratch[k].ptr), cudaFree(w->orderScratch[k].ptr);
+    cudaFree(w->agentScratch.ptr);
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -512,7 +514,7 @@ int cq_move_and_slide_batch_ex(cq_world *w, cq_character_state *inout, int32_t n
                          return launch_move_and_slide(w, (cq_character_state *)di, cnt, *params, dt, gravity, flags, platforms,
                                                       n_platforms, st);
                      },
-                     /*inPlace=*/true, &w->hintMas);
+                     /*inPlace=*/true, &w->hintMas, /*singleChunk=*/(flags & CQ_MAS_AGENTS) != 0);
 }
 
 } // extern "C"

@@ -893,6 +893,120 @@ const uint32_t *make_unit_order(cq_world *w, const void *dUnits, size_t stride, 
     return vals;
 }
 
+// ---------------------------------------------------------------- agent snapshot + grid (CQ_MAS_AGENTS)
+// bounds: [0..1] min x,z  [2..3] max x,z  [4] max |v|  (ordered ints)
+__global__ void k_agent_bounds_init(int *bounds) {
+    if (threadIdx.x < 5) {
+        const float init = threadIdx.x < 2 ? FLT_MAX : (threadIdx.x < 4 ? -FLT_MAX : 0.0f);
+        bounds[threadIdx.x] = float_to_ordered(init);
+    }
+}
+__global__ void k_agent_snapshot(const cq_character_state *__restrict__ states, int n, float dt, float gx, float gy, float gz,
+                                 uint32_t flags, float4 *__restrict__ pos, float4 *__restrict__ vel, int *bounds) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v[5] = {FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f};
+    if (i < n) {
+        const cq_character_state &S = states[i];
+        d3 vd = {S.velocity[0], S.velocity[1], S.velocity[2]};
+        // collectAgentStates runs after GravitySystem (system #3), so the snapshot carries the post-gravity velocity
+        if ((flags & CQ_MAS_APPLY_GRAVITY) && !(S.grounded != 0 && S.grounded_near != 0))
+            vd = vd + to_d3(mk3(gx, gy, gz)) * (double)dt;
+        f3 p = {(float)S.position[0], (float)S.position[1], (float)S.position[2]};
+        f3 vf = to_f3(vd);
+        pos[i] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        vel[i] = make_float4(vf.x, vf.y, vf.z, 0.0f);
+        v[0] = p.x, v[1] = p.z, v[2] = p.x, v[3] = p.z;
+        v[4] = sqrtf(vf.x * vf.x + vf.y * vf.y + vf.z * vf.z);
+    }
+    __shared__ float red[5][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        float x = v[k];
+        for (int o = 16; o > 0; o >>= 1) {
+            float y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = k < 2 ? fminf(x, y) : fmaxf(x, y);
+        }
+        if (lane == 0) red[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        const int k = threadIdx.x;
+        float x = red[k][0];
+        for (int wi = 1; wi < (int)(blockDim.x >> 5); wi++) x = k < 2 ? fminf(x, red[k][wi]) : fmaxf(x, red[k][wi]);
+        if (k < 2) atomicMin(bounds + k, float_to_ordered(x));
+        else atomicMax(bounds + k, float_to_ordered(x));
+    }
+}
+
+// cell = the farthest two agents can be apart (XZ) and still touch within one step, so a sweep looks at 3x3 cells;
+// any cell size is exact (the kernel derives its cell range from the actual reach), this one is just the fast one
+__global__ void k_agent_grid_params(const int *bounds, float radius, float dt, AgentGridParams *out) {
+    float minX = ordered_to_float(bounds[0]), minZ = ordered_to_float(bounds[1]);
+    float maxX = ordered_to_float(bounds[2]), maxZ = ordered_to_float(bounds[3]);
+    float vmax = ordered_to_float(bounds[4]);
+    if (!(vmax >= 0.0f) || vmax > 1e18f) vmax = 1e18f;
+    float cell = (2.0f * radius + 2.0f * vmax * dt) * 1.01f + 1e-3f;
+    float ex = fmaxf(maxX - minX, 0.0f), ez = fmaxf(maxZ - minZ, 0.0f);
+    if (!(ex < 1e30f)) ex = 1e30f;
+    if (!(ez < 1e30f)) ez = 1e30f;
+    const float maxDim = 32767.0f; // 15 bits per axis -> 30-bit keys, what the radix sort handles
+    cell = fmaxf(cell, fmaxf(ex, ez) / (maxDim - 1.0f));
+    out->originX = minX, out->originZ = minZ;
+    out->cell = cell, out->invCell = 1.0f / cell;
+    out->dimX = (int)fminf(floorf(ex / cell) + 1.0f, maxDim);
+    out->dimZ = (int)fminf(floorf(ez / cell) + 1.0f, maxDim);
+    out->maxSpeed = vmax;
+    out->_pad = 0.0f;
+}
+
+__global__ void k_agent_keys(const float4 *__restrict__ pos, int n, const AgentGridParams *__restrict__ gp, uint32_t *keys,
+                             uint32_t *vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const AgentGridParams G = *gp;
+    float4 p = pos[i];
+    keys[i] = (uint32_t)agent_cell(p.z, G.originZ, G.invCell, G.dimZ) * (uint32_t)G.dimX +
+              (uint32_t)agent_cell(p.x, G.originX, G.invCell, G.dimX);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void k_agent_gather(const uint32_t *__restrict__ vals, int n, const float4 *__restrict__ pos,
+                               const float4 *__restrict__ vel, float4 *__restrict__ posS, float4 *__restrict__ velS) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t j = vals[i];
+    posS[i] = pos[j];
+    velS[i] = vel[j];
+}
+
+int make_agent_grid(cq_world *w, const cq_character_state *dStates, int n, float radius, float dt, const float g[3],
+                    uint32_t flags, cudaStream_t st, AgentGrid &out) {
+    const int tiles = cdiv(n, RS_TILE);
+    const size_t sortWords = (size_t)4 * 256 * tiles + 4 + 1024 + 1;
+    // [pos n][vel n][posS n][velS n] float4, [keys n][vals n][keysTmp n][valsTmp n] u32, sort scratch, bounds, params
+    const size_t bytes = (size_t)n * 64 + ((size_t)4 * n + sortWords + 64) * 4;
+    if (bytes > w->agentScratch.cap) {
+        CQ_CUDA(cudaDeviceSynchronize());
+        CQ_TRY(ensure_scratch(w->agentScratch, bytes));
+    }
+    float4 *pos = (float4 *)w->agentScratch.ptr, *vel = pos + n, *posS = vel + n, *velS = posS + n;
+    uint32_t *keys = (uint32_t *)(velS + n), *vals = keys + n, *keysTmp = vals + n, *valsTmp = keysTmp + n;
+    uint32_t *scratch = valsTmp + n;
+    int *bounds = (int *)(scratch + sortWords);
+    AgentGridParams *gp = (AgentGridParams *)(bounds + 8);
+    k_agent_bounds_init<<<1, 32, 0, st>>>(bounds);
+    k_agent_snapshot<<<cdiv(n, 256), 256, 0, st>>>(dStates, n, dt, g[0], g[1], g[2], flags, pos, vel, bounds);
+    k_agent_grid_params<<<1, 1, 0, st>>>(bounds, radius, dt, gp);
+    k_agent_keys<<<cdiv(n, 256), 256, 0, st>>>(pos, n, gp, keys, vals);
+    w->launches += 4;
+    CQ_TRY(radix_sort_pairs_onesweep(w, keys, vals, keysTmp, valsTmp, n, scratch, sortWords, st, false));
+    k_agent_gather<<<cdiv(n, 256), 256, 0, st>>>(vals, n, pos, vel, posS, velS);
+    w->launches++;
+    out.pos = posS, out.vel = velS, out.keys = keys, out.params = gp, out.n = n;
+    return check_cuda(cudaGetLastError(), "agent grid");
+}
+
 // TriangleMeshSet.updateTransforms + BVH.refit: re-transform the changed parts' vertices, regather the
 // sorted SoA, recompute every box bottom-up (same tree topology).  Asynchronous on the world stream.
 int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx) {

@@ -82,6 +82,7 @@ struct cq_world {
     int *dWork = nullptr; // ring of dynamic-fetch counters, one per persistent-kernel launch in flight
     uint32_t workSeq = 0;
     cq::ScratchBuf in, out, aux, aux2;
+    cq::ScratchBuf agentScratch; // agent snapshot + grid of the move-and-slide call in flight (CQ_MAS_AGENTS)
 };
 
 namespace cq {
@@ -115,6 +116,9 @@ int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx);
 void free_set(DeviceSet &S);
 // Morton-sorted processing order of n work units whose position (3 floats or 3 doubles) sits at the start of each
 // `stride`-byte record; nullptr when ordering is not worthwhile (small world / batch) or on error
+// CQ_MAS_AGENTS pre-pass: snapshot (after the gravity rule), XZ grid, sort by cell.  Stream-ordered on `st`.
+int make_agent_grid(cq_world *w, const cq_character_state *dStates, int n, float radius, float dt, const float g[3],
+                    uint32_t flags, cudaStream_t st, AgentGrid &out);
 const uint32_t *make_unit_order(cq_world *w, const void *dUnits, size_t stride, bool positionIsDouble, int n, cudaStream_t st);
 
 // cq_query.cu

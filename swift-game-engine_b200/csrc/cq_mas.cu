@@ -37,6 +37,7 @@ struct MasArgs {
     uint32_t flags;
     int nPlatforms;
     cq_platform platforms[MAS_MAX_PLATFORMS]; // kinematic platforms travel in the kernel arguments (2.3 KB at most)
+    AgentGrid agents;                         // CQ_MAS_AGENTS: snapshot + grid of this launch
 };
 
 // PlatformCarry.computeDelta (SYS:644-732): carry by the platform stood on, push by a platform moving into the side
@@ -91,6 +92,48 @@ __device__ __noinline__ f3 platform_carry_delta(f3 position, const cq_controller
     return mk3(0, 0, 0);
 }
 
+// AgentSweepSolver.bestHit (SYS:1053-1091) over the grid cells the sweep can reach instead of every agent.  Exact:
+// an agent outside the reach box cannot produce a hit, and ties keep the smallest index, which is what the
+// reference's strict `<` over its index-ordered loop keeps.
+__device__ __noinline__ bool agent_best_hit(const AgentGrid &G, f3 position, f3 remaining, float remainingLen, float baseMoveLen,
+                                            float dt, int selfIndex, float radius, float halfHeight, AgentHit &best) {
+    const AgentGridParams gp = *G.params;
+    const float timeScale = baseMoveLen > 1e-6f ? smin(remainingLen / baseMoveLen, 1.0f) : 1.0f;
+    const float segmentDt = dt * timeScale;
+    // XZ reach: both radii + own motion + the fastest agent's motion over the segment, padded against rounding
+    const float reach = (2.0f * radius + remainingLen + gp.maxSpeed * fabsf(segmentDt)) * 1.001f + 1e-3f;
+    const int ix0 = agent_cell(position.x - reach, gp.originX, gp.invCell, gp.dimX);
+    const int ix1 = agent_cell(position.x + reach, gp.originX, gp.invCell, gp.dimX);
+    const int iz0 = agent_cell(position.z - reach, gp.originZ, gp.invCell, gp.dimZ);
+    const int iz1 = agent_cell(position.z + reach, gp.originZ, gp.invCell, gp.dimZ);
+    bool have = false;
+    for (int iz = iz0; iz <= iz1; iz++) {
+        const uint32_t keyLo = (uint32_t)iz * (uint32_t)gp.dimX + (uint32_t)ix0, keyHi = keyLo + (uint32_t)(ix1 - ix0);
+        int lo = 0, hi = G.n; // lower_bound(keyLo): a row of cells is one contiguous key range
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(G.keys + mid) < keyLo) lo = mid + 1;
+            else hi = mid;
+        }
+        for (int j = lo; j < G.n && __ldg(G.keys + j) <= keyHi; j++) {
+            const float4 op = __ldg(G.pos + j);
+            const int other = __float_as_int(op.w);
+            if (other == selfIndex) continue;
+            const float4 ov = __ldg(G.vel + j);
+            const f3 otherDelta = mk3(ov.x, ov.y, ov.z) * segmentDt;
+            AgentHit hit;
+            if (capsule_pair_sweep(position, remaining, radius, halfHeight, other, mk3(op.x, op.y, op.z), otherDelta, radius,
+                                   halfHeight, hit)) {
+                if (!have || hit.toi < best.toi || (hit.toi == best.toi && hit.other < best.other)) {
+                    best = hit;
+                    have = true;
+                }
+            }
+        }
+    }
+    return have;
+}
+
 enum { W_NONE = 0, W_DEPEN, W_SLIDE, W_SNAP, W_FALL, W_OFFSET };
 enum { NX_LOAD = 0, NX_DEPEN, NX_SLIDE, NX_SNAP, NX_FALL, NX_GATE, NX_OFFSET, NX_FINISH };
 enum {
@@ -109,7 +152,7 @@ struct CharCtx { // per-lane controller working set, shared memory (the 168-byte
     int cTri, cPart;
     float gDistance;
     float nSum[3];
-    float combineTol;
+    float combineTol; // slide phase (agents): baseMoveLen
     float dSum[3];
     float dWeight;
     int wait, slideIt, offsetIt, depenIt;
@@ -179,16 +222,17 @@ __device__ __forceinline__ void cache_record(cq_character_state &c, int tri, f3 
 }
 
 // SlideResolver.resolveHit, kinematicMove options, static hit (SYS:1229-1375).  Returns shouldBreak.
+// `isStatic` false selects the .agentHit case: no skin, never ground-like, no cached side normal.
 __device__ __forceinline__ bool slide_resolve(CharCtx &c, const cq_controller_params &P, f3 hitN, f3 hitTriN, float hitToi,
-                                              bool haveCachedSide, f3 cachedSide, int sideFrames) {
+                                              bool haveCachedSide, f3 cachedSide, int sideFrames, bool isStatic) {
     const bool wasGrounded = c.flags & F_WAS_G, wasGroundedNear = c.flags & F_WAS_GN;
     f3 position = ld3(c.pos), remaining = ld3(c.rem);
     const float slideLen = c.slideLen;
     f3 slideNormal = hitN;
-    bool groundLike = hitTriN.y >= P.min_ground_dot;
-    float contactSkin = groundLike ? P.ground_snap_skin : P.skin_width;
+    bool groundLike = isStatic && hitTriN.y >= P.min_ground_dot;
+    float contactSkin = !isStatic ? 0.0f : (groundLike ? P.ground_snap_skin : P.skin_width); // SYS:1255-1271
     bool shouldBreak = false;
-    if (slideNormal.y < P.min_ground_dot && sideFrames > 0) { // SYS:1273-1292
+    if (isStatic && slideNormal.y < P.min_ground_dot && sideFrames > 0) { // SYS:1273-1292
         if (haveCachedSide) {
             f3 cn = cachedSide;
             if (dot(cn, slideNormal) < 0.0f) cn = -cn;
@@ -228,7 +272,7 @@ __device__ __forceinline__ bool slide_resolve(CharCtx &c, const cq_controller_pa
             remaining = remaining - slideNormal * into;
             shouldBreak = false;
         } else if (into >= -intoEps) { // SYS:1324
-            if (wasGroundedNear && !groundLike && remaining.y < 0.0f) remaining.y = 0.0f;
+            if (wasGroundedNear && isStatic && !groundLike && remaining.y < 0.0f) remaining.y = 0.0f;
             position = position + remaining;
             remaining = mk3(0, 0, 0);
             shouldBreak = true;
@@ -426,28 +470,45 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
     }
     case W_SLIDE: { // resolveKinematicSweep loop body after the blocking cast (SYS:1683-1763)
         c.slideIt++;
-        if (q.bestTri < 0) {
-            st3(c.pos, ld3(c.pos) + ld3(c.rem));
-            st3(c.rem, mk3(0, 0, 0));
-            next = NX_SNAP;
-            break;
-        }
+        const bool haveHit = q.bestTri >= 0;
         f3 hitN = q.bestN;
-        const f3 hitTriN = q.bestTriN;
+        f3 hitTriN = q.bestTriN;
+        float hitToi = q.bestT;
         const int tri = q.bestTri;
         bool haveCachedSide = false;
         f3 cachedSide = {0, 0, 0};
         const int sideFrames = c.st->side_contact_frames;
-        if (hitN.y < P.min_ground_dot && sideFrames > 0) { // SYS:1683-1694
+        if (haveHit && hitN.y < P.min_ground_dot && sideFrames > 0) { // SYS:1683-1694
             f3 cached;
             if (manifold_normal_for(*c.st, tri, cached)) {
                 if (dot(cached, hitN) < 0.0f) cached = -cached;
                 hitN = cached;
             }
         }
-        if (hitN.y < P.min_ground_dot && sideFrames > 0) haveCachedSide = manifold_normal_for(*c.st, tri, cachedSide);
-        bool shouldBreak = slide_resolve(c, P, hitN, hitTriN, q.bestT, haveCachedSide, cachedSide, sideFrames);
-        if (hitN.y < P.min_ground_dot) cache_record(*c.st, tri, hitN, true); // SYS:1738-1743
+        bool useAgent = false;
+        if (A.flags & CQ_MAS_AGENTS) { // AgentSweepSolver.bestHit + HitSelector.selectBestHit (SYS:1695-1705, 1378-1399)
+            AgentHit aHit;
+            if (agent_best_hit(A.agents, ld3(c.pos), ld3(c.rem), c.slideLen, c.combineTol, A.dt, c.charIndex, P.radius,
+                               P.half_height, aHit)) {
+                useAgent = true;
+                if (haveHit) {
+                    float staticSkin = hitN.y >= P.min_ground_dot ? P.ground_snap_skin : P.skin_width;
+                    float staticStop = smax(hitToi - staticSkin, 0.0f), agentStop = smax(aHit.toi, 0.0f);
+                    useAgent = !(staticStop <= agentStop);
+                }
+                if (useAgent) hitN = aHit.normal, hitTriN = mk3(0, 0, 0), hitToi = aHit.toi;
+            }
+        }
+        if (!haveHit && !useAgent) {
+            st3(c.pos, ld3(c.pos) + ld3(c.rem));
+            st3(c.rem, mk3(0, 0, 0));
+            next = NX_SNAP;
+            break;
+        }
+        const bool sideCache = !useAgent && hitN.y < P.min_ground_dot;
+        if (sideCache && sideFrames > 0) haveCachedSide = manifold_normal_for(*c.st, tri, cachedSide);
+        bool shouldBreak = slide_resolve(c, P, hitN, hitTriN, hitToi, haveCachedSide, cachedSide, sideFrames, !useAgent);
+        if (sideCache) cache_record(*c.st, tri, hitN, true); // SYS:1738-1743
         if (c.flags & F_HAVE_LAST) {                                       // SYS:1744-1754
             f3 last = ld3(c.lastN);
             float dn = dot(last, hitN);
@@ -556,6 +617,9 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
         if (next == NX_SLIDE) {
             f3 remaining = ld3(c.rem);
             c.slideLen = len(remaining);
+            // baseMoveLen = |linearVelocityF * dt| at sweep entry (SYS:1671-1672); parked in combineTol, which the
+            // ground probe only starts using after the slide loop
+            if ((A.flags & CQ_MAS_AGENTS) && c.slideIt == 0) c.combineTol = len(to_f3(ldv(*c.st)) * A.dt);
             if (c.slideIt >= P.max_slide_iterations || c.slideLen < 1e-6f) { // SYS:1674-1676
                 next = NX_SNAP;
             } else {
@@ -701,6 +765,7 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * MAS_WARPS);
     if (!ns) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_inout, sizeof(cq_character_state), true, n, st);
+    if (flags & CQ_MAS_AGENTS) CQ_TRY(make_agent_grid(w, d_inout, n, p.radius, dt, g, flags, st, A.agents));
     if (w->counting)
         k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
     else

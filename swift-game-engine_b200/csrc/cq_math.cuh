@@ -303,4 +303,119 @@ CQ_HD bool ray_triangle(f3 origin, f3 direction, const Tri &T, float &tOut) {
     return false;
 }
 
+// ---- capsule-capsule CCD between agents (vertical capsules; Systems.swift:1417-1590)
+struct AgentHit {
+    float toi;
+    f3 normal;
+    int other;
+};
+
+CQ_HD bool clamp_interval(float start, float end, float &s, float &e) { // SYS:1417-1424
+    s = smax(start, 0.0f);
+    e = smin(end, 1.0f);
+    return !(e < s);
+}
+CQ_HD bool interval_ge(float y0, float vy, float threshold, float &s, float &e) { // SYS:1426-1436
+    if (fabsf(vy) < 1e-6f) {
+        s = 0.0f, e = 1.0f;
+        return y0 >= threshold;
+    }
+    float t = (threshold - y0) / vy;
+    return vy > 0.0f ? clamp_interval(t, 1.0f, s, e) : clamp_interval(0.0f, t, s, e);
+}
+CQ_HD bool interval_le(float y0, float vy, float threshold, float &s, float &e) { // SYS:1438-1448
+    if (fabsf(vy) < 1e-6f) {
+        s = 0.0f, e = 1.0f;
+        return y0 <= threshold;
+    }
+    float t = (threshold - y0) / vy;
+    return vy > 0.0f ? clamp_interval(0.0f, t, s, e) : clamp_interval(t, 1.0f, s, e);
+}
+CQ_HD bool earliest_root(float A, float B, float C, float tMin, float tMax, float &out) { // SYS:1450-1472
+    const float eps = 1e-6f;
+    if (fabsf(A) < eps) {
+        if (fabsf(B) < eps) {
+            out = tMin;
+            return C <= 0.0f;
+        }
+        float t = -C / B;
+        out = t;
+        return t >= tMin && t <= tMax;
+    }
+    float disc = B * B - 4.0f * A * C;
+    if (disc < 0.0f) return false;
+    float sqrtD = sqrtf(disc);
+    float inv2A = 1.0f / (2.0f * A);
+    float t0 = (-B - sqrtD) * inv2A, t1 = (-B + sqrtD) * inv2A;
+    float enter = smin(t0, t1), exit_ = smax(t0, t1);
+    float s = smax(enter, tMin), e = smin(exit_, tMax);
+    out = s;
+    return e >= s;
+}
+CQ_HD float capsule_pair_separation_y(float yRel, float hSum) { // SYS:1474-1482
+    if (yRel > hSum) return yRel - hSum;
+    if (yRel < -hSum) return yRel + hSum;
+    return 0.0f;
+}
+CQ_HD f3 capsule_pair_normal(f3 rel, float hSum) { // SYS:1484-1497
+    float sepY = capsule_pair_separation_y(rel.y, hSum);
+    f3 sep = {rel.x, sepY, rel.z};
+    float l2 = len2(sep);
+    if (l2 > 1e-8f) return sep / sqrtf(l2);
+    f3 lateral = {rel.x, 0.0f, rel.z};
+    float ll2 = len2(lateral);
+    if (ll2 > 1e-8f) return lateral / sqrtf(ll2);
+    return {1.0f, 0.0f, 0.0f};
+}
+CQ_HD bool capsule_pair_overlap(f3 rel, float rSum, float hSum) { // SYS:1499-1503
+    float sepY = capsule_pair_separation_y(rel.y, hSum);
+    float d2 = rel.x * rel.x + rel.z * rel.z + sepY * sepY;
+    return d2 <= rSum * rSum;
+}
+// capsuleCapsuleSweep (SYS:1505-1590): relative motion against the two cap spheres and the cylinder band
+CQ_HD bool capsule_pair_sweep(f3 from, f3 delta, float radius, float halfHeight, int other, f3 otherPos, f3 otherDelta,
+                              float otherRadius, float otherHalfHeight, AgentHit &out) {
+    f3 relStart = from - otherPos, relDelta = delta - otherDelta;
+    float rSum = radius + otherRadius, hSum = halfHeight + otherHalfHeight;
+    float relLen = len(relDelta), moveLen = len(delta);
+    if (relLen < 1e-6f) {
+        if (capsule_pair_overlap(relStart, rSum, hSum)) {
+            out.toi = 0.0f, out.normal = capsule_pair_normal(relStart, hSum), out.other = other;
+            return true;
+        }
+        return false;
+    }
+    float y0 = relStart.y, vy = relDelta.y, vx = relDelta.x, vz = relDelta.z, r0x = relStart.x, r0z = relStart.z;
+    bool have = false;
+    float bestT = 0.0f, s, e, t;
+    if (interval_ge(y0, vy, hSum, s, e)) {
+        float A = vx * vx + vz * vz + vy * vy;
+        float B = 2.0f * (r0x * vx + r0z * vz + (y0 - hSum) * vy);
+        float C = r0x * r0x + r0z * r0z + (y0 - hSum) * (y0 - hSum) - rSum * rSum;
+        if (earliest_root(A, B, C, s, e, t)) bestT = t, have = true;
+    }
+    if (interval_le(y0, vy, -hSum, s, e)) {
+        float A = vx * vx + vz * vz + vy * vy;
+        float B = 2.0f * (r0x * vx + r0z * vz + (y0 + hSum) * vy);
+        float C = r0x * r0x + r0z * r0z + (y0 + hSum) * (y0 + hSum) - rSum * rSum;
+        if (earliest_root(A, B, C, s, e, t) && (!have || t < bestT)) bestT = t, have = true;
+    }
+    if (fabsf(vy) < 1e-6f) {
+        if (fabsf(y0) <= hSum) {
+            float A = vx * vx + vz * vz, B = 2.0f * (r0x * vx + r0z * vz), C = r0x * r0x + r0z * r0z - rSum * rSum;
+            if (earliest_root(A, B, C, 0.0f, 1.0f, t) && (!have || t < bestT)) bestT = t, have = true;
+        }
+    } else {
+        float t1 = (hSum - y0) / vy, t2 = (-hSum - y0) / vy;
+        if (clamp_interval(smin(t1, t2), smax(t1, t2), s, e)) {
+            float A = vx * vx + vz * vz, B = 2.0f * (r0x * vx + r0z * vz), C = r0x * r0x + r0z * r0z - rSum * rSum;
+            if (earliest_root(A, B, C, s, e, t) && (!have || t < bestT)) bestT = t, have = true;
+        }
+    }
+    if (!have) return false;
+    f3 relAtHit = relStart + relDelta * bestT;
+    out.toi = bestT * moveLen, out.normal = capsule_pair_normal(relAtHit, hSum), out.other = other;
+    return true;
+}
+
 } // namespace cq

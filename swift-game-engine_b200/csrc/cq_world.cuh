@@ -55,6 +55,26 @@ struct WorldView {
     int nParts;
 };
 
+// Snapshot of every agent of a move-and-slide batch, taken before any character of the step moves
+// (collectAgentStates, Systems.swift:1592-1611), binned into a uniform XZ grid and sorted by cell key.
+struct AgentGridParams { // written by k_agent_grid_params, read by the move-and-slide kernel
+    float originX, originZ, invCell, cell;
+    int dimX, dimZ;
+    float maxSpeed; // max |velocity| over the snapshot
+    float _pad;
+};
+struct AgentGrid {
+    const float4 *pos;  // sorted by cell key; w = original index (bits)
+    const float4 *vel;  // same order
+    const uint32_t *keys; // sorted cell keys: iz * dimX + ix
+    const AgentGridParams *params;
+    int n;
+};
+__device__ __forceinline__ int agent_cell(float x, float origin, float invCell, int dim) { // monotonic in x
+    float c = floorf((x - origin) * invCell);
+    return (int)fminf(fmaxf(c, 0.0f), (float)(dim - 1));
+}
+
 struct Counters { // per-thread work counters, flushed with atomics when COUNT
     uint32_t nodes, cands, evals, queries;
 };

@@ -36,4 +36,20 @@ void hm_ray_triangle_batch(int n, const float *origins, const float *dirs, const
         tout[i] = t;
     }
 }
+
+void hm_capsule_capsule_sweep_batch(int n, const float *from, const float *delta, const float *otherPos,
+                                    const float *otherDelta, const float *dims, int *hit, float *toi, float *normal) {
+    for (int i = 0; i < n; i++) {
+        cq::AgentHit h = {0.0f, {0.0f, 0.0f, 0.0f}, -1};
+        hit[i] = cq::capsule_pair_sweep(cq::f3{from[3 * i], from[3 * i + 1], from[3 * i + 2]},
+                                        cq::f3{delta[3 * i], delta[3 * i + 1], delta[3 * i + 2]}, dims[4 * i], dims[4 * i + 1], i,
+                                        cq::f3{otherPos[3 * i], otherPos[3 * i + 1], otherPos[3 * i + 2]},
+                                        cq::f3{otherDelta[3 * i], otherDelta[3 * i + 1], otherDelta[3 * i + 2]}, dims[4 * i + 2],
+                                        dims[4 * i + 3], h)
+                     ? 1
+                     : 0;
+        toi[i] = h.toi;
+        normal[3 * i] = h.normal.x, normal[3 * i + 1] = h.normal.y, normal[3 * i + 2] = h.normal.z;
+    }
+}
 }

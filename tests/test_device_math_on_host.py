@@ -25,6 +25,7 @@ def hm():
     L = C.CDLL(LIB)
     L.hm_segment_triangle_distance_batch.argtypes = [C.c_int] + [C.c_void_p] * 6
     L.hm_ray_triangle_batch.argtypes = [C.c_int] + [C.c_void_p] * 5
+    L.hm_capsule_capsule_sweep_batch.argtypes = [C.c_int] + [C.c_void_p] * 8
     return L
 
 
@@ -82,3 +83,34 @@ def test_ray_triangle_bit_exact(hm, orc):
     hm.hm_ray_triangle_batch(n, _p(np.ascontiguousarray(origins)), _p(np.ascontiguousarray(dirs)), _p(tris), _p(t), _p(hit))
     assert np.array_equal(hit, ohit) and np.array_equal(t[hit == 1], ot[ohit == 1])
     assert 0.3 < hit.mean() < 0.95
+
+
+def test_capsule_capsule_sweep_bit_exact(hm, orc):
+    """capsule_pair_sweep (device source) vs the oracle's capsuleCapsuleSweep (Systems.swift:1505-1590): approaching,
+    receding, resting (|relative motion| < 1e-6), vertically stacked and purely vertical relative motion."""
+    rng = np.random.default_rng(77)
+    n = 1_000_000
+    dims = np.stack([rng.choice(np.float32([0.3, 1.5]), n), rng.choice(np.float32([0.0, 0.6, 1.0]), n),
+                     rng.choice(np.float32([0.3, 1.5]), n), rng.choice(np.float32([0.0, 0.6, 1.0]), n)], axis=1).astype(np.float32)
+    frm = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+    other = (frm + rng.standard_normal((n, 3)) * [3, 3, 3]).astype(np.float32)
+    delta = (rng.standard_normal((n, 3)) * 10.0 ** rng.uniform(-3, 0.7, (n, 1))).astype(np.float32)
+    odelta = (rng.standard_normal((n, 3)) * 10.0 ** rng.uniform(-3, 0.7, (n, 1))).astype(np.float32)
+    kind = rng.integers(0, 6, n)
+    odelta[kind == 0] = delta[kind == 0]                      # no relative motion -> overlap test only
+    delta[kind == 1, 1] = 0                                   # horizontal relative motion (|vy| < 1e-6 branch)
+    odelta[kind == 1, 1] = 0
+    other[kind == 2] = frm[kind == 2] + np.float32([0, 1, 0]) * rng.uniform(0, 6, ((kind == 2).sum(), 1)).astype(np.float32)
+    aim = kind == 3                                           # aimed straight at the other capsule
+    delta[aim] = ((other[aim] - frm[aim]) * rng.uniform(0.2, 1.5, (aim.sum(), 1))).astype(np.float32)
+    odelta[kind == 4] = 0                                     # static obstacle
+    delta[kind == 5, 0] = 0                                   # purely vertical relative motion
+    delta[kind == 5, 2] = 0
+    odelta[kind == 5, 0] = 0
+    odelta[kind == 5, 2] = 0
+    oh, ot, on = orc.capsule_capsule_sweep_batch(frm, delta, other, odelta, dims)
+    hit, toi, normal = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+    hm.hm_capsule_capsule_sweep_batch(n, _p(frm), _p(delta), _p(other), _p(odelta), _p(dims), _p(hit), _p(toi), _p(normal))
+    assert 0.1 < oh.mean() < 0.9
+    assert np.array_equal(oh, hit)
+    assert ot.tobytes() == toi.tobytes() and on.tobytes() == normal.tobytes()

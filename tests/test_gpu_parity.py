@@ -420,3 +420,47 @@ def test_kinematic_platforms_carry_and_push(cq, orc, scenes):
         g.move_and_slide(sg, cq.default_params(), platforms=np.zeros(65, cq.PLATFORM))
     g.close()
     o.close()
+
+
+@pytest.mark.gpu
+def test_agents_capsule_capsule_ccd(cq, orc, scenes):
+    """CQ_MAS_AGENTS: every character also sweeps against a pre-step snapshot of all the others (AgentSweepSolver,
+    HitSelector; Systems.swift:1023-1091, 1378-1399, 1505-1590).  The GPU finds partners through a uniform grid, the
+    oracle loops over everybody like the reference: states must stay identical over several steps of a dense crowd
+    on a terrain, with the walk intent re-applied each step so that agents keep pressing into each other."""
+    parts, half_world = scenes.terrain_scene(cells=96, cell=1.5, seed=5)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    rng = np.random.default_rng(11)
+    n = 3000
+    p = cq.default_params()
+    p["radius"], p["half_height"] = 0.4, 0.5
+    p["skin_width"], p["snap_distance"] = 0.08, 0.3
+    # ~35% area coverage inside a square -> plenty of pairs within reach every step
+    half = min(np.sqrt(n * np.pi * 0.4 ** 2 / 0.35) / 2, half_world - 4.0)
+    x, z = rng.uniform(-half, half, n), rng.uniform(-half, half, n)
+    y = scenes.terrain_height(x, z, 5) + np.float32(0.9 + 0.05) + rng.uniform(0, 0.3, n)
+    pos = np.stack([x, y, z], axis=1).astype(np.float32)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    walk = (np.stack([np.cos(ang), np.zeros(n), np.sin(ang)], axis=1) * rng.uniform(2, 9, (n, 1))).astype(np.float32)
+    sg, so = cq.init_states(pos, walk), orc.init_states(pos, walk)
+    agent_hits = 0
+    for step in range(8):
+        ghost = so.copy()
+        g.move_and_slide(sg, p, flags=cq.MAS_APPLY_GRAVITY | cq.MAS_AGENTS)
+        o.move_and_slide(so, p, flags=3, order=orc.ORDER_CANONICAL, n_threads=8)
+        assert sg.tobytes() == so.tobytes(), step
+        o.move_and_slide(ghost, p, flags=1, order=orc.ORDER_CANONICAL, n_threads=8)
+        agent_hits += int((ghost["position"] != so["position"]).any(axis=1).sum())
+        for s in (sg, so):
+            s["velocity"][:, 0] = walk[:, 0]
+            s["velocity"][:, 2] = walk[:, 2]
+    assert agent_hits > n // 4  # the agent path really decided a good share of the moves
+    # a lone character is not its own obstacle, and an empty batch is fine
+    one = cq.init_states(pos[:1], walk[:1])
+    ref = orc.init_states(pos[:1], walk[:1])
+    g.move_and_slide(one, p, flags=3)
+    o.move_and_slide(ref, p, flags=3, order=orc.ORDER_CANONICAL)
+    assert one.tobytes() == ref.tobytes()
+    g.move_and_slide(one[:0].copy(), p, flags=3)
+    g.close()
+    o.close()

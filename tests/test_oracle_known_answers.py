@@ -258,3 +258,45 @@ def test_platform_carry_and_side_push(orc, scenes):
     s3 = orc.init_states([[0.0, rest, 0.0]])
     w.move_and_slide(s3, p, platforms=still, order=orc.ORDER_REFERENCE)
     assert s3["position"][0][0] == pytest.approx(0.0, abs=1e-6)
+
+
+def test_capsule_capsule_sweep_known_answers(orc):
+    """capsuleCapsuleSweep (Systems.swift:1505-1590) on cases with closed-form answers."""
+    dims = np.float32([[1.5, 1.0, 1.5, 1.0]])
+    # head-on along x, other static, 10 m apart: contact when the centres are rSum = 3 apart -> toi 7 of a 10 m move
+    hit, toi, n = orc.capsule_capsule_sweep_batch([[0, 0, 0]], [[10, 0, 0]], [[10, 0, 0]], [[0, 0, 0]], dims)
+    assert hit[0] == 1 and toi[0] == pytest.approx(7.0, rel=1e-6) and np.allclose(n[0], [-1, 0, 0])
+    # both moving toward each other at the same speed: they meet halfway, toi measured along the mover's own path
+    hit, toi, n = orc.capsule_capsule_sweep_batch([[0, 0, 0]], [[5, 0, 0]], [[10, 0, 0]], [[-5, 0, 0]], dims)
+    assert hit[0] == 1 and toi[0] == pytest.approx(3.5, rel=1e-6)
+    # moving away / passing at a lateral distance > rSum: no hit
+    hit, _, _ = orc.capsule_capsule_sweep_batch([[0, 0, 0], [0, 0, 3.01]], [[-10, 0, 0], [20, 0, 0]], [[10, 0, 0]] * 2,
+                                                [[0, 0, 0]] * 2, np.repeat(dims, 2, 0))
+    assert hit.tolist() == [0, 0]
+    # landing on top of another capsule: cap spheres meet when the centres are hSum + rSum = 5 apart vertically
+    hit, toi, n = orc.capsule_capsule_sweep_batch([[0, 9, 0]], [[0, -6, 0]], [[0, 0, 0]], [[0, 0, 0]], dims)
+    assert hit[0] == 1 and toi[0] == pytest.approx(4.0, rel=1e-6) and np.allclose(n[0], [0, 1, 0])
+    # no relative motion: overlap test only, toi 0 with the separating normal
+    hit, toi, n = orc.capsule_capsule_sweep_batch([[0, 0, 0], [0, 0, 0]], [[1, 0, 0]] * 2, [[2, 0, 0], [4, 0, 0]],
+                                                  [[1, 0, 0]] * 2, np.repeat(dims, 2, 0))
+    assert hit.tolist() == [1, 0] and toi[0] == 0.0 and np.allclose(n[0], [-1, 0, 0])
+
+
+def test_agents_block_each_other(orc, scenes):
+    """flags & 2 (every character a solid agent): two walkers heading for each other stop at rSum instead of passing
+    through; a third one far away is unaffected; without the flag they walk through each other."""
+    parts = [big_floor(scenes, y=-3.0, eid=0)]
+    w = orc.OracleWorld(parts)
+    p = orc.default_params()
+    y = -3.0 + 2.5 + 0.05
+    pos = [[-4.0, y, 0.0], [4.0, y, 0.0], [40.0, y, 0.0]]
+    vel = [[6.0, 0, 0], [-6.0, 0, 0], [6.0, 0, 0]]
+    solid, ghost = orc.init_states(pos, vel), orc.init_states(pos, vel)
+    for _ in range(90):
+        w.move_and_slide(solid, p, flags=3, order=orc.ORDER_REFERENCE)
+        w.move_and_slide(ghost, p, flags=1, order=orc.ORDER_REFERENCE)
+        solid["velocity"][:, 0] = ghost["velocity"][:, 0] = [6.0, -6.0, 6.0]  # the walk intent is re-applied every step
+    assert solid["position"][0][0] == pytest.approx(-1.5, abs=0.02) and solid["position"][1][0] == pytest.approx(1.5, abs=0.02)
+    assert solid["position"][2][0] == pytest.approx(ghost["position"][2][0]) and ghost["position"][2][0] > 48.0
+    assert ghost["position"][0][0] > 4.0 and ghost["position"][1][0] < -4.0  # passed through each other
+    assert solid["grounded"].tolist() == [1, 1, 1]
