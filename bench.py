@@ -145,11 +145,14 @@ class ClockSampler:
 TERRAIN_PARAMS = dict(radius=0.4, half_height=0.5, skin_width=0.08)  # human-scale capsule
 
 
-def make_workload(cq, mesh, n, rank):
+def make_workload(cq, mesh, n, rank, agents=0.0):
     if mesh == "terrain":  # the north-star target scene: 10 M-triangle procedural terrain, walkers all over it
         parts, half = cq.scenes.terrain_scene(cells=2236, cell=2.0)
         rng = np.random.default_rng(SEED + 77 + rank)
-        x = rng.uniform(-half + 10, half - 10, (n, 2))
+        span = half - 10
+        if agents > 0:  # a crowd: the walkers' footprints cover `agents` of a square in the middle of the terrain
+            span = min(span, float(np.sqrt(n * np.pi * TERRAIN_PARAMS["radius"] ** 2 / agents)) / 2)
+        x = rng.uniform(-span, span, (n, 2))
         y = cq.scenes.terrain_height(x[:, 0], x[:, 1]) + np.float32(0.9 + 0.2)
         pos = np.stack([x[:, 0], y, x[:, 1]], axis=1).astype(np.float32)
         heading, speed = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 4.5, n)
@@ -164,10 +167,12 @@ def controller_params(mod, mesh):
     return mod.default_params(**TERRAIN_PARAMS) if mesh == "terrain" else mod.default_params()
 
 
-def workload_name(mesh, n):
+def workload_name(mesh, n, agents=0.0):
     if mesh == "terrain":
+        crowd = (f"; every character a solid agent (capsule-capsule CCD against a pre-step snapshot of the others), "
+                 f"crowd footprint coverage {agents:g}") if agents > 0 else ""
         return (f"target scene: {n} characters/GPU x 1 move-and-slide fixed step over the procedural terrain of "
-                "9,999,392 triangles (cell 2 m), human-scale controller r=0.4 hh=0.5 skin 0.08, dt=1/60, gravity on")
+                "9,999,392 triangles (cell 2 m), human-scale controller r=0.4 hh=0.5 skin 0.08, dt=1/60, gravity on" + crowd)
     tri = "2 collision hulls (76 tris) + ground plane (2 tris)" if mesh == "hulls" else \
         "render mesh (14,211 tris after the area filter) + ground plane (2 tris)"
     return (f"C3: {n} characters/GPU x 1 move-and-slide fixed step (<=4 slide casts + ground probes), "
@@ -185,23 +190,30 @@ def run_reference(args):
     cq = importlib.import_module("swift-game-engine_b200")  # scenes only (numpy); no CUDA call is made
     cores = os.cpu_count() or 1
     n = args.ref_sample or {"hulls": CHARS_PER_GPU, "render": 65536, "terrain": 262144}[args.mesh]
-    parts, pos, vel = make_workload(cq, args.mesh, n, 0)
+    mas_flags = 1
+    if args.agents > 0:  # the reference's agent loop is O(n^2): a smaller crowd of the SAME density
+        n = args.ref_sample or 32768
+        mas_flags = 3
+    parts, pos, vel = make_workload(cq, args.mesh, n, 0, args.agents)
     w = orc.OracleWorld(parts)
     s = orc.init_states(pos, vel)
     p = controller_params(orc, args.mesh)
     for _ in range(args.warmup):
-        w.move_and_slide(s, p, DT, GRAVITY, 1, orc.ORDER_REFERENCE, cores)
+        w.move_and_slide(s, p, DT, GRAVITY, mas_flags, orc.ORDER_REFERENCE, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        w.move_and_slide(s, p, DT, GRAVITY, 1, orc.ORDER_REFERENCE, cores)
+        w.move_and_slide(s, p, DT, GRAVITY, mas_flags, orc.ORDER_REFERENCE, cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     sample = f"{n} of {CHARS_PER_GPU} characters per step, {args.steps} steps, state carried"
+    if args.agents > 0:
+        sample = (f"a crowd of {n} characters at the same density (the reference tests every agent against every other: "
+                  f"its cost per character grows with the crowd), {args.steps} steps, state carried")
     line = {
         "impl": "reference", "metric": "move_and_slide_queries_per_sec", "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.mesh, CHARS_PER_GPU), "mesh": args.mesh,
+        "config": {"workload": workload_name(args.mesh, CHARS_PER_GPU, args.agents), "mesh": args.mesh,
                    "reference_impl": "C++ restatement of CollisionQuery.swift + Systems.swift move-and-slide "
                                      "(oracle/), reference BVH + DFS order; not swiftc-compiled"},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
@@ -248,7 +260,8 @@ def run_ours(args):
     cq = importlib.import_module("swift-game-engine_b200")
     cq.build()
     n = args.chars
-    parts, pos, vel = make_workload(cq, args.mesh, n, rank)
+    parts, pos, vel = make_workload(cq, args.mesh, n, rank, args.agents)
+    mas_flags = cq.MAS_APPLY_GRAVITY | (cq.MAS_AGENTS if args.agents > 0 else 0)
     world = cq.CollisionQuery(parts)
     info = world.info()
     params = controller_params(cq, args.mesh)
@@ -266,7 +279,7 @@ def run_ours(args):
     assert stream != 0
 
     def step_device():
-        world.move_and_slide_device(d_states.data_ptr(), n, params, DT, GRAVITY, cq.MAS_APPLY_GRAVITY, stream)
+        world.move_and_slide_device(d_states.data_ptr(), n, params, DT, GRAVITY, mas_flags, stream)
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # runs through warm-up, the timed region and a short identical load after it (see below)
@@ -341,13 +354,13 @@ def run_ours(args):
     pinned = cq.PinnedArray((n,), cq.STATE)
     torch.cuda.synchronize()
     pinned.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)
-    world.move_and_slide(pinned.array, params, DT, GRAVITY, cq.MAS_APPLY_GRAVITY)  # warm the staging buffers
+    world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)  # warm the staging buffers
     pinned.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)
     e2e_steps = args.steps
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        world.move_and_slide(pinned.array, params, DT, GRAVITY, cq.MAS_APPLY_GRAVITY)
+        world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -365,12 +378,24 @@ def run_ours(args):
         ns = {"hulls": CHARS_PER_GPU, "render": 65536, "terrain": 262144}[args.mesh]
         ns = min(ns, n)
         ow = orc.OracleWorld(parts)
-        snap_np = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=orc.STATE)[:ns].copy()
+        snap_all = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=orc.STATE)
+        what = f"first {ns} of the {n} characters"
+        if args.agents > 0:
+            # the reference tests every agent against every other (O(n^2)): time a sub-crowd of the SAME density,
+            # the characters inside a centred square holding ~32768 of them
+            px, pz = snap_all["position"][:, 0], snap_all["position"][:, 2]
+            lim = max(np.abs(px).max(), np.abs(pz).max()) * np.sqrt(min(1.0, 32768 / n))
+            snap_np = snap_all[(np.abs(px) <= lim) & (np.abs(pz) <= lim)].copy()
+            ns = len(snap_np)
+            what = f"the {ns} characters of a centred sub-square of the crowd (same density; the reference's agent loop is O(n^2))"
+        else:
+            snap_np = snap_all[:ns].copy()
         t0 = time.perf_counter()
-        ow.move_and_slide(snap_np, controller_params(orc, args.mesh), DT, GRAVITY, 1, orc.ORDER_REFERENCE, cores)
+        ow.move_and_slide(snap_np, controller_params(orc, args.mesh), DT, GRAVITY, 3 if args.agents > 0 else 1,
+                          orc.ORDER_REFERENCE, cores)
         cdt = time.perf_counter() - t0
         cpu_baseline = {"value": ns / cdt, "unit": "queries/s", "cores": cores, "kind": "port",
-                        "sample": f"first {ns} of the {n} characters, the first timed step, {cdt:.2f} s wall; "
+                        "sample": f"{what}, the first timed step, {cdt:.2f} s wall; "
                                   "restated reference (C++), not swiftc-compiled"}
 
     total_launches = sum_over_ranks(launches)
@@ -379,7 +404,7 @@ def run_ours(args):
             "metric": "move_and_slide_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.mesh, n), "mesh": args.mesh, "characters_per_gpu": n,
+            "config": {"workload": workload_name(args.mesh, n, args.agents), "mesh": args.mesh, "characters_per_gpu": n,
                        "triangles": info["n_static_triangles"] + info["n_dynamic_triangles"],
                        "l2": "inputs (168 B x characters = %.0f MB per GPU) exceed the 126 MB L2; no flush" % (nbytes / 1e6),
                        "parallelism": f"queries sharded over {world_size} GPU(s), mesh+BVH replicated, no collective",
@@ -728,6 +753,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", default="hulls", choices=["hulls", "render", "terrain"])
     ap.add_argument("--chars", type=int, default=CHARS_PER_GPU)
+    ap.add_argument("--agents", type=float, default=0.0,
+                    help="terrain mesh only: characters collide with each other; value = crowd footprint coverage (e.g. 0.1)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -412,7 +412,7 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
 
 // Stage L of the move-and-slide kernel: consume the finished query, run the controller logic up to the
 // next query, post it.  Returns false when the lane has no more characters.
-template <bool COUNT>
+template <bool COUNT, bool AGENTS>
 __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShared &s, const WarpPool &wp, int lane,
                                             const WorldView &W, const MasArgs &A, cq_character_state *states, int n,
                                             int *workCounter, const uint32_t *order, Counters &ctr) {
@@ -486,7 +486,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             }
         }
         bool useAgent = false;
-        if (A.flags & CQ_MAS_AGENTS) { // AgentSweepSolver.bestHit + HitSelector.selectBestHit (SYS:1695-1705, 1378-1399)
+        if (AGENTS) { // AgentSweepSolver.bestHit + HitSelector.selectBestHit (SYS:1695-1705, 1378-1399)
             AgentHit aHit;
             if (agent_best_hit(A.agents, ld3(c.pos), ld3(c.rem), c.slideLen, c.combineTol, A.dt, c.charIndex, P.radius,
                                P.half_height, aHit)) {
@@ -619,7 +619,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             c.slideLen = len(remaining);
             // baseMoveLen = |linearVelocityF * dt| at sweep entry (SYS:1671-1672); parked in combineTol, which the
             // ground probe only starts using after the slide loop
-            if ((A.flags & CQ_MAS_AGENTS) && c.slideIt == 0) c.combineTol = len(to_f3(ldv(*c.st)) * A.dt);
+            if (AGENTS && c.slideIt == 0) c.combineTol = len(to_f3(ldv(*c.st)) * A.dt);
             if (c.slideIt >= P.max_slide_iterations || c.slideLen < 1e-6f) { // SYS:1674-1676
                 next = NX_SNAP;
             } else {
@@ -700,7 +700,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, bool AGENTS>
 __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states,
                                                                                 int n, const __grid_constant__ MasArgs A,
                                                                                 int ownersPerWarp,
@@ -722,12 +722,13 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
-        return mas_advance<COUNT>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);
+        return mas_advance<COUNT, AGENTS>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);
     }, OverlapTop2());
     pool_flush_counters(ctr, gctr, COUNT);
 }
 
 #define CQ_OCC_SLOT 0
+#define CQ_OCC_SLOT_AGENTS 5
 int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p, float dt,
                           const float g[3], uint32_t flags, const cq_platform *platforms, int nPlatforms, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
@@ -743,17 +744,22 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     A.flags = flags;
     A.nPlatforms = nPlatforms;
     for (int k = 0; k < nPlatforms; k++) A.platforms[k] = platforms[k];
-    int *blocksPerSm = w->occ[CQ_OCC_SLOT]; int &numSms = w->numSms;
+    const bool agents = (flags & CQ_MAS_AGENTS) != 0;
+    int *blocksPerSm = w->occ[agents ? CQ_OCC_SLOT_AGENTS : CQ_OCC_SLOT];
+    int &numSms = w->numSms;
     const int ci = w->counting ? 1 : 0;
+    using Kernel = void (*)(WorldView, cq_character_state *, int, const MasArgs, int, uint2 *, int *, const uint32_t *,
+                            unsigned long long *);
+    static const Kernel kernels[2][2] = {{k_move_and_slide<false, false>, k_move_and_slide<true, false>},
+                                         {k_move_and_slide<false, true>, k_move_and_slide<true, true>}};
+    const Kernel kernel = kernels[agents ? 1 : 0][ci];
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;
         CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
         numSms = prop.multiProcessorCount;
         int b = 0;
-        CQ_CUDA(cudaFuncSetAttribute(k_move_and_slide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAS_SMEM_BYTES));
-        CQ_CUDA(cudaFuncSetAttribute(k_move_and_slide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAS_SMEM_BYTES));
-        if (ci) CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<true>, MAS_THREADS, MAS_SMEM_BYTES));
-        else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move_and_slide<false>, MAS_THREADS, MAS_SMEM_BYTES));
+        CQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAS_SMEM_BYTES));
+        CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, MAS_THREADS, MAS_SMEM_BYTES));
         blocksPerSm[ci] = b > 0 ? b : 1;
     }
     // persistent lanes: one resident wave of CTAs (148 SMs x resident CTAs per SM), lanes stride over characters
@@ -766,10 +772,7 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     if (!ns) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_inout, sizeof(cq_character_state), true, n, st);
     if (flags & CQ_MAS_AGENTS) CQ_TRY(make_agent_grid(w, d_inout, n, p.radius, dt, g, flags, st, A.agents));
-    if (w->counting)
-        k_move_and_slide<true><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
-    else
-        k_move_and_slide<false><<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
+    kernel<<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_move_and_slide");
 }
