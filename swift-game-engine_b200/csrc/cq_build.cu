@@ -980,18 +980,58 @@ __global__ void k_agent_gather(const uint32_t *__restrict__ vals, int n, const f
     velS[i] = vel[j];
 }
 
+// one thread per agent: the three sorted-array ranges its 3x3 cell neighbourhood occupies (binary searches done here,
+// at full occupancy, instead of by a lone lane inside the move-and-slide kernel)
+__global__ void k_agent_rows(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
+                             const AgentGridParams *__restrict__ gp, int4 *__restrict__ rows) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int dimX = gp->dimX, dimZ = gp->dimZ;
+    const uint32_t key = keys[j];
+    const int iz = (int)(key / (uint32_t)dimX), ix = (int)(key % (uint32_t)dimX);
+    int se[6];
+    for (int dz = -1; dz <= 1; dz++) {
+        int row = iz + dz, start = 0, end = 0;
+        if (row >= 0 && row < dimZ) {
+            const uint32_t keyLo = (uint32_t)row * (uint32_t)dimX + (uint32_t)max(ix - 1, 0);
+            const uint32_t keyHi = (uint32_t)row * (uint32_t)dimX + (uint32_t)min(ix + 1, dimX - 1);
+            int lo = 0, hi = n;
+            while (lo < hi) { // lower_bound(keyLo)
+                int mid = (lo + hi) >> 1;
+                if (keys[mid] < keyLo) lo = mid + 1;
+                else hi = mid;
+            }
+            start = lo;
+            hi = n;
+            while (lo < hi) { // upper_bound(keyHi)
+                int mid = (lo + hi) >> 1;
+                if (keys[mid] <= keyHi) lo = mid + 1;
+                else hi = mid;
+            }
+            end = lo;
+        }
+        se[2 * (dz + 1)] = start, se[2 * (dz + 1) + 1] = end;
+    }
+    const uint32_t orig = vals[j];
+    rows[2 * (size_t)orig] = make_int4(se[0], se[1], se[2], se[3]);
+    rows[2 * (size_t)orig + 1] = make_int4(se[4], se[5], ix, iz);
+}
+
 int make_agent_grid(cq_world *w, const cq_character_state *dStates, int n, float radius, float dt, const float g[3],
                     uint32_t flags, cudaStream_t st, AgentGrid &out) {
     const int tiles = cdiv(n, RS_TILE);
     const size_t sortWords = (size_t)4 * 256 * tiles + 4 + 1024 + 1;
-    // [pos n][vel n][posS n][velS n] float4, [keys n][vals n][keysTmp n][valsTmp n] u32, sort scratch, bounds, params
-    const size_t bytes = (size_t)n * 64 + ((size_t)4 * n + sortWords + 64) * 4;
+    // [pos n][vel n][posS n][velS n] float4, [rows 2n] int4, [firstHit n] float4, [keys n][vals n][keysTmp n][valsTmp n] u32, sort scratch,
+    // bounds, params
+    const size_t bytes = (size_t)n * 112 + ((size_t)4 * n + sortWords + 64) * 4;
     if (bytes > w->agentScratch.cap) {
         CQ_CUDA(cudaDeviceSynchronize());
         CQ_TRY(ensure_scratch(w->agentScratch, bytes));
     }
     float4 *pos = (float4 *)w->agentScratch.ptr, *vel = pos + n, *posS = vel + n, *velS = posS + n;
-    uint32_t *keys = (uint32_t *)(velS + n), *vals = keys + n, *keysTmp = vals + n, *valsTmp = keysTmp + n;
+    int4 *rows = (int4 *)(velS + n);
+    float4 *firstHit = (float4 *)(rows + 2 * (size_t)n);
+    uint32_t *keys = (uint32_t *)(firstHit + n), *vals = keys + n, *keysTmp = vals + n, *valsTmp = keysTmp + n;
     uint32_t *scratch = valsTmp + n;
     int *bounds = (int *)(scratch + sortWords);
     AgentGridParams *gp = (AgentGridParams *)(bounds + 8);
@@ -1002,8 +1042,9 @@ int make_agent_grid(cq_world *w, const cq_character_state *dStates, int n, float
     w->launches += 4;
     CQ_TRY(radix_sort_pairs_onesweep(w, keys, vals, keysTmp, valsTmp, n, scratch, sortWords, st, false));
     k_agent_gather<<<cdiv(n, 256), 256, 0, st>>>(vals, n, pos, vel, posS, velS);
-    w->launches++;
-    out.pos = posS, out.vel = velS, out.keys = keys, out.params = gp, out.n = n;
+    k_agent_rows<<<cdiv(n, 256), 256, 0, st>>>(keys, vals, n, gp, rows);
+    w->launches += 2;
+    out.pos = posS, out.vel = velS, out.keys = keys, out.params = gp, out.rows = rows, out.firstHit = firstHit, out.n = n;
     return check_cuda(cudaGetLastError(), "agent grid");
 }
 

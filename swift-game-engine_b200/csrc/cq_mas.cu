@@ -107,18 +107,35 @@ __device__ __noinline__ bool agent_best_hit(const AgentGrid &G, f3 position, f3 
     const int iz0 = agent_cell(position.z - reach, gp.originZ, gp.invCell, gp.dimZ);
     const int iz1 = agent_cell(position.z + reach, gp.originZ, gp.invCell, gp.dimZ);
     bool have = false;
-    for (int iz = iz0; iz <= iz1; iz++) {
-        const uint32_t keyLo = (uint32_t)iz * (uint32_t)gp.dimX + (uint32_t)ix0, keyHi = keyLo + (uint32_t)(ix1 - ix0);
-        int lo = 0, hi = G.n; // lower_bound(keyLo): a row of cells is one contiguous key range
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(G.keys + mid) < keyLo) lo = mid + 1;
-            else hi = mid;
+    // fast path: the reach stays inside the 3x3 cells around the agent's snapshot cell (the cell size is chosen so
+    // that it does unless a platform or a depenetration push moved it far): ranges were found in the pre-pass
+    const int4 r0 = __ldg(G.rows + 2 * (size_t)selfIndex), r1 = __ldg(G.rows + 2 * (size_t)selfIndex + 1);
+    const bool precomputed = ix0 >= r1.z - 1 && ix1 <= r1.z + 1 && iz0 >= r1.w - 1 && iz1 <= r1.w + 1;
+    const int rowLo = precomputed ? r1.w - 1 : iz0, rowHi = precomputed ? r1.w + 1 : iz1;
+    for (int iz = rowLo; iz <= rowHi; iz++) {
+        int j, end;
+        if (precomputed) {
+            const int k = iz - (r1.w - 1);
+            j = k == 0 ? r0.x : (k == 1 ? r0.z : r1.x);
+            end = k == 0 ? r0.y : (k == 1 ? r0.w : r1.y);
+        } else {
+            const uint32_t keyLo = (uint32_t)iz * (uint32_t)gp.dimX + (uint32_t)ix0, keyHi = keyLo + (uint32_t)(ix1 - ix0);
+            int lo = 0, hi = G.n; // lower_bound(keyLo): a row of cells is one contiguous key range
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (__ldg(G.keys + mid) < keyLo) lo = mid + 1;
+                else hi = mid;
+            }
+            j = lo;
+            for (end = lo; end < G.n && __ldg(G.keys + end) <= keyHi;) end++;
         }
-        for (int j = lo; j < G.n && __ldg(G.keys + j) <= keyHi; j++) {
+        for (; j < end; j++) {
             const float4 op = __ldg(G.pos + j);
             const int other = __float_as_int(op.w);
             if (other == selfIndex) continue;
+            // cheap exact reject: farther apart in XZ than the reach -> the sweep cannot hit
+            const float dx = op.x - position.x, dz = op.z - position.z;
+            if (dx * dx + dz * dz > reach * reach) continue;
             const float4 ov = __ldg(G.vel + j);
             const f3 otherDelta = mk3(ov.x, ov.y, ov.z) * segmentDt;
             AgentHit hit;
@@ -132,6 +149,46 @@ __device__ __noinline__ bool agent_best_hit(const AgentGrid &G, f3 position, f3 
         }
     }
     return have;
+}
+
+// What a character brings into its fixed step: GravitySystem (SYS:603-619), positionF, applyPlatformDelta
+// (SYS:1618-1633), VelocityGate (SYS:1037-1051).  Shared by the kernel's load stage and the agent pre-pass so that
+// both derive bit-identical sweep inputs.
+__device__ __forceinline__ void mas_entry_motion(const cq_character_state &S, const MasArgs &A, f3 &pos, f3 &rem, d3 &vel) {
+    const bool wasGrounded = S.grounded != 0, wasGroundedNear = S.grounded_near != 0;
+    vel = d3{S.velocity[0], S.velocity[1], S.velocity[2]};
+    if (A.flags & CQ_MAS_APPLY_GRAVITY) {
+        if (!(wasGrounded && wasGroundedNear)) vel = vel + to_d3(mk3(A.gx, A.gy, A.gz)) * (double)A.dt;
+    }
+    pos = mk3((float)S.position[0], (float)S.position[1], (float)S.position[2]);
+    if (A.nPlatforms > 0) {
+        f3 platformDelta = platform_carry_delta(pos, A.p, A.platforms, A.nPlatforms);
+        if (len2(platformDelta) > 1e-8f) pos = pos + platformDelta;
+    }
+    if (wasGrounded && wasGroundedNear && vel.y < 0.0) vel.y = 0.0;
+    d3 remD = vel * (double)A.dt;
+    if (wasGrounded && wasGroundedNear && remD.y < 0.0) remD.y = 0.0;
+    rem = to_f3(remD);
+}
+
+// Agent pre-pass: the agent hit of every character's FIRST slide iteration, one thread per character at full
+// occupancy.  Valid whenever depenetration leaves the character alone (the kernel checks); later iterations and
+// pushed characters run agent_best_hit inside the kernel.
+__global__ void k_agent_first_hit(const cq_character_state *__restrict__ states, int n, const __grid_constant__ MasArgs A) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 pos, rem;
+    d3 vel;
+    mas_entry_motion(states[i], A, pos, rem, vel);
+    const float slideLen = len(rem);
+    float4 out = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+    if (!(slideLen < 1e-6f)) {
+        const float baseMoveLen = len(to_f3(vel) * A.dt);
+        AgentHit hit;
+        if (agent_best_hit(A.agents, pos, rem, slideLen, baseMoveLen, A.dt, i, A.p.radius, A.p.half_height, hit))
+            out = make_float4(hit.normal.x, hit.normal.y, hit.normal.z, hit.toi);
+    }
+    A.agents.firstHit[i] = out;
 }
 
 enum { W_NONE = 0, W_DEPEN, W_SLIDE, W_SNAP, W_FALL, W_OFFSET };
@@ -488,8 +545,16 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
         bool useAgent = false;
         if (AGENTS) { // AgentSweepSolver.bestHit + HitSelector.selectBestHit (SYS:1695-1705, 1378-1399)
             AgentHit aHit;
-            if (agent_best_hit(A.agents, ld3(c.pos), ld3(c.rem), c.slideLen, c.combineTol, A.dt, c.charIndex, P.radius,
-                               P.half_height, aHit)) {
+            bool haveAgent;
+            if (c.slideIt == 1 && !(c.flags & F_DID_RESOLVE)) { // untouched since load: the pre-pass had the same inputs
+                const float4 m = __ldg(A.agents.firstHit + c.charIndex);
+                haveAgent = m.w != -1.0f;
+                aHit.toi = m.w, aHit.normal = mk3(m.x, m.y, m.z), aHit.other = -1;
+            } else {
+                haveAgent = agent_best_hit(A.agents, ld3(c.pos), ld3(c.rem), c.slideLen, c.combineTol, A.dt, c.charIndex,
+                                           P.radius, P.half_height, aHit);
+            }
+            if (haveAgent) {
                 useAgent = true;
                 if (haveHit) {
                     float staticSkin = hitN.y >= P.min_ground_dot ? P.ground_snap_skin : P.skin_width;
@@ -568,11 +633,10 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             cq_character_state &S = *c.st;
             const bool wasGrounded = S.grounded != 0, wasGroundedNear = S.grounded_near != 0;
             c.flags = (wasGrounded ? F_WAS_G : 0) | (wasGroundedNear ? F_WAS_GN : 0);
-            d3 vel = ldv(S);
-            if (A.flags & CQ_MAS_APPLY_GRAVITY) { // GravitySystem (SYS:603-619)
-                if (!(wasGrounded && wasGroundedNear)) vel = vel + to_d3(mk3(A.gx, A.gy, A.gz)) * (double)A.dt;
-            }
-            st3(c.pos, mk3((float)S.position[0], (float)S.position[1], (float)S.position[2])); // positionF
+            f3 position, remaining;
+            d3 vel;
+            mas_entry_motion(S, A, position, remaining, vel); // gravity, positionF, platform carry, VelocityGate
+            st3(c.pos, position);
             { // decay (SYS:1105-1116)
                 int scf = S.side_contact_frames;
                 if (scf > 0) S.side_contact_frames = scf - 1;
@@ -586,17 +650,8 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
                     }
                 }
             }
-            if (A.nPlatforms > 0) { // applyPlatformDelta (SYS:1618-1633)
-                f3 position = ld3(c.pos);
-                f3 platformDelta = platform_carry_delta(position, A.p, A.platforms, A.nPlatforms);
-                if (len2(platformDelta) > 1e-8f) st3(c.pos, position + platformDelta);
-            }
-            // VelocityGate (SYS:1037-1051)
-            if (wasGrounded && wasGroundedNear && vel.y < 0.0) vel.y = 0.0;
-            d3 remD = vel * (double)A.dt;
-            if (wasGrounded && wasGroundedNear && remD.y < 0.0) remD.y = 0.0;
             stv(S, vel);
-            st3(c.rem, to_f3(remD));
+            st3(c.rem, remaining);
             c.depenIt = 0, c.slideIt = 0, c.offsetIt = 0;
             c._pad = (int)ctr.evals;
             st3(c.dSum, mk3(0, 0, 0));
@@ -771,7 +826,11 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * MAS_WARPS);
     if (!ns) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_inout, sizeof(cq_character_state), true, n, st);
-    if (flags & CQ_MAS_AGENTS) CQ_TRY(make_agent_grid(w, d_inout, n, p.radius, dt, g, flags, st, A.agents));
+    if (flags & CQ_MAS_AGENTS) {
+        CQ_TRY(make_agent_grid(w, d_inout, n, p.radius, dt, g, flags, st, A.agents));
+        k_agent_first_hit<<<(n + 255) / 256, 256, 0, st>>>(d_inout, n, A);
+        w->launches++;
+    }
     kernel<<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_move_and_slide");

@@ -68,6 +68,10 @@ struct AgentGrid {
     const float4 *vel;  // same order
     const uint32_t *keys; // sorted cell keys: iz * dimX + ix
     const AgentGridParams *params;
+    const int4 *rows; // per ORIGINAL index, 2 x int4: (start,end) in the sorted arrays of the cells ix-1..ix+1 of the rows
+                      // iz-1, iz, iz+1 around the agent's snapshot cell, then (ix, iz) -- found once, in parallel
+    float4 *firstHit; // per ORIGINAL index: (normal, toi) of the agent hit of the FIRST slide iteration, computed by a
+                      // pre-pass under the assumption that depenetration does not move the character; toi -1 = none
     int n;
 };
 __device__ __forceinline__ int agent_cell(float x, float origin, float invCell, int dim) { // monotonic in x

@@ -455,6 +455,24 @@ def test_agents_capsule_capsule_ccd(cq, orc, scenes):
             s["velocity"][:, 0] = walk[:, 0]
             s["velocity"][:, 2] = walk[:, 2]
     assert agent_hits > n // 4  # the agent path really decided a good share of the moves
+    # characters carried far from their snapshot cell by a platform (the grid's precomputed 3x3 ranges do not apply:
+    # the kernel falls back to searching the cells its reach really covers)
+    fv, fi = scenes.plane_mesh(80.0)
+    flat = [scenes.part(fv, fi, scenes.trs_model((0, -3, 0)), entity_id=0)]
+    g2, o2 = cq.CollisionQuery(flat), orc.OracleWorld(flat)
+    m = 1500
+    fpos = np.stack([rng.uniform(-16, 16, m), np.full(m, -3.0 + 0.9 + 0.05), rng.uniform(-16, 16, m)], axis=1).astype(np.float32)
+    fwalk = walk[:m]
+    plat = np.zeros(1, cq.PLATFORM)
+    plat["aabb_min"], plat["aabb_max"], plat["delta"] = (-6, -4, -6), (6, -3, 6), (3.0, 0.0, 0.7)
+    fg, fo = cq.init_states(fpos, fwalk), orc.init_states(fpos, fwalk)
+    for step in range(3):
+        g2.move_and_slide(fg, p, flags=3, platforms=plat)
+        o2.move_and_slide(fo, p, flags=3, platforms=plat, order=orc.ORDER_CANONICAL, n_threads=8)
+        assert fg.tobytes() == fo.tobytes(), step
+    assert (np.abs(fg["position"][:, 0] - fpos[:, 0]) > 2.5).sum() > 50  # many were carried several cells away
+    g2.close()
+    o2.close()
     # a lone character is not its own obstacle, and an empty batch is fine
     one = cq.init_states(pos[:1], walk[:1])
     ref = orc.init_states(pos[:1], walk[:1])
