@@ -17,7 +17,7 @@ import subprocess
 import numpy as np
 
 from . import scenes  # noqa: F401  (re-export)
-from .service import CollisionQueryService  # noqa: F401,E402
+from .service import ActiveChunkSet, CollisionQueryService, chunk_to_world, world_to_chunk  # noqa: E402,F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")

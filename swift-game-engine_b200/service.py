@@ -127,3 +127,52 @@ class CollisionQueryService:
             self.query.updateDynamicTransforms([e["entity_id"] for e in dy], [self._model(e) for e in dy])
             self.last_action = "refit"
         self._refresh_cache(entities, active_ids)
+
+
+# ---------------------------------------------------------------- streaming active set (Systems.swift:2354-2411)
+CHUNK_SIZE = 512.0  # WorldPosition.chunkSize (Components.swift:55)
+
+
+def world_to_chunk(world):
+    """WorldPosition.fromWorld (Components.swift:58-69): per axis chunk = floor((v + 256) / 512), local = v - chunk*512.
+    Returns (chunk int64 (...,3), local float64 (...,3))."""
+    w = np.asarray(world, np.float64)
+    chunk = np.floor((w + CHUNK_SIZE * 0.5) / CHUNK_SIZE).astype(np.int64)
+    return chunk, w - chunk.astype(np.float64) * CHUNK_SIZE
+
+
+def chunk_to_world(chunk, local):
+    """WorldPosition.toWorld (Components.swift:87-93)."""
+    return np.asarray(chunk, np.int64).astype(np.float64) * CHUNK_SIZE + np.asarray(local, np.float64)
+
+
+class ActiveChunkSet:
+    """ActiveChunkSystem.fixedUpdate (Systems.swift:2354-2396): the entities whose chunk lies within `radius_chunks`
+    (Chebyshev distance, ActiveChunkComponent.radiusChunks default 2, Components.swift:150) of the player's chunk.
+    `update` returns (active_entity_ids, active_static_entity_ids); feed the first to CollisionQueryService.update —
+    a changed set is what triggers the rebuild there (SceneServices.swift:55-58)."""
+
+    def __init__(self, radius_chunks=2):
+        self.radius_chunks = radius_chunks
+        self.center_chunk = np.zeros(3, np.int64)
+        self.active_entity_ids = set()
+        self.active_static_entity_ids = set()
+
+    def update(self, player_world_position, entities):
+        """entities: dicts with entity_id and either `chunk` (3 ints) or `world_position` / `translation` (3 floats);
+        `body_type` None or "static" with a mesh counts as static (StaticMeshComponent present)."""
+        center, _ = world_to_chunk(player_world_position)
+        radius = max(int(self.radius_chunks), 0)
+        active, active_static = set(), set()
+        for e in entities:
+            if "chunk" in e:
+                chunk = np.asarray(e["chunk"], np.int64)
+            else:
+                chunk, _ = world_to_chunk(e.get("world_position", e.get("translation", (0, 0, 0))))
+            if int(np.abs(chunk - center).max()) <= radius:
+                active.add(e["entity_id"])
+                if "positions" in e:  # staticStore.contains(e): the entity carries a StaticMeshComponent
+                    active_static.add(e["entity_id"])
+        self.center_chunk = center
+        self.active_entity_ids, self.active_static_entity_ids = active, active_static
+        return active, active_static

@@ -240,3 +240,35 @@ def test_collision_query_service_rebuild_vs_refit_policy(cq, scenes):
         assert svc.last_action == "rebuild" and sum(1 for x in _RecorderWorld.log if x[0] == "build") == n_builds
     svc.update(ents, active_ids={0, 1})  # active set changed -> rebuild with the filtered entities
     assert _RecorderWorld.log[-1][0] == "build" and _RecorderWorld.log[-1][1] == [0, 1]
+
+
+def test_active_chunk_set_drives_rebuilds(cq, scenes):
+    """ActiveChunkSystem (Systems.swift:2354-2396) + WorldPosition.fromWorld (Components.swift:58-69): 512 m chunks
+    centred on multiples of 512, Chebyshev radius 2; a player crossing a chunk border changes the active set, and the
+    changed set is what makes CollisionQueryService rebuild (SceneServices.swift:55-58)."""
+    ch, lo = cq.world_to_chunk([[255.9, -256.0, 256.0], [-256.1, 767.9, 0.0]])
+    assert ch.tolist() == [[0, 0, 1], [-1, 1, 0]]
+    assert np.allclose(lo, [[255.9, -256.0, -256.0], [255.9, 255.9, 0.0]])
+    assert np.allclose(cq.chunk_to_world(ch, lo), [[255.9, -256.0, 256.0], [-256.1, 767.9, 0.0]])
+    bv, bi = scenes.box_mesh(2.0)
+    ents = [dict(entity_id=k, positions=bv, indices=bi, translation=(512.0 * k, 0, 0)) for k in range(8)]
+    ents.append(dict(entity_id=100, translation=(0, 0, 0)))  # a mesh-less entity (e.g. the player itself)
+    acs = cq.ActiveChunkSet()
+    active, static = acs.update((10.0, 0.0, 0.0), ents)
+    assert active == {0, 1, 2, 100} and static == {0, 1, 2}
+    _RecorderWorld.log = []
+    svc = cq.CollisionQueryService(world_factory=_RecorderWorld)
+    meshes = ents[:8]
+    svc.update(meshes, active_ids=static)
+    assert _RecorderWorld.log[-1][:2] == ("build", [0, 1, 2])
+    active, static = acs.update((250.0, 0.0, 0.0), ents)  # same chunk: same set, nothing to do
+    svc.update(meshes, active_ids=static)
+    assert svc.last_action == "none"
+    active, static = acs.update((260.0, 0.0, 0.0), ents)  # crossed into chunk 1: entity 3 streams in
+    assert static == {0, 1, 2, 3} and acs.center_chunk.tolist() == [1, 0, 0]
+    svc.update(meshes, active_ids=static)
+    assert svc.last_action == "rebuild" and _RecorderWorld.log[-1][1] == [0, 1, 2, 3]
+    active, static = acs.update((512.0 * 5, 0.0, 0.0), ents)
+    assert static == {3, 4, 5, 6, 7}
+    acs.radius_chunks = -3  # max(radiusChunks, 0)
+    assert acs.update((512.0 * 5, 0.0, 0.0), ents)[1] == {5}
