@@ -1183,17 +1183,31 @@ bool agentBestHit(F3 position, F3 remaining, float remainingLen, float baseMoveL
     return have;
 }
 
-// SlideResolver.resolveHit with SlideOptions.kinematicMove (SYS:1229-1375); `agent` selects the .agentHit case
+struct SlideOptions { // SYS:1208-1222
+    bool allowHorizontalGroundPass, adjustVelocity, useGroundSnapSkinForStatic, allowTriangleNormalGroundLike;
+};
+const SlideOptions kSlideKinematicMove = {false, true, true, true};
+const SlideOptions kSlideAgentSeparation = {true, false, false, false};
+
+// SlideResolver.resolveHit (SYS:1229-1375); `agent` selects the .agentHit case
 bool slideResolveHit(F3 &remaining, float len, const CapsuleCastHit &sHit, Character &ch, bool wasGrounded,
                      bool wasGroundedNear, F3 &position, bool haveCachedSide, F3 cachedSideNormal,
-                     const CapsuleCapsuleHit *agent = nullptr) {
+                     const CapsuleCapsuleHit *agent = nullptr, const SlideOptions &opt = kSlideKinematicMove) {
     const orc_params &p = *ch.p;
     const orc_state &c = *ch.s;
     const bool hitIsStatic = agent == nullptr;
+    if (opt.allowHorizontalGroundPass && hitIsStatic && fabsf(remaining.y) < 1e-5f &&
+        sHit.normal.y >= p.min_ground_dot) { // SYS:1240-1247
+        position = position + remaining;
+        remaining = {0, 0, 0};
+        return true;
+    }
     float hitToi = hitIsStatic ? sHit.toi : agent->toi;
     F3 slideNormal = hitIsStatic ? sHit.normal : agent->normal;
     bool hitIsGroundLike = hitIsStatic && sHit.triangleNormal.y >= p.min_ground_dot;
-    float contactSkin = !hitIsStatic ? 0.0f : (hitIsGroundLike ? p.ground_snap_skin : p.skin_width); // SYS:1255-1271
+    float contactSkin = !hitIsStatic ? 0.0f
+                                     : ((opt.useGroundSnapSkinForStatic && hitIsGroundLike) ? p.ground_snap_skin
+                                                                                            : p.skin_width); // SYS:1255-1271
     F3 hitTriNormal = hitIsStatic ? sHit.triangleNormal : f3(0, 0, 0);
 
     if (hitIsStatic && slideNormal.y < p.min_ground_dot && c.side_contact_frames > 0) { // SYS:1273-1292
@@ -1212,7 +1226,7 @@ bool slideResolveHit(F3 &remaining, float len, const CapsuleCastHit &sHit, Chara
         }
     }
     if (slideNormal.y < p.min_ground_dot) { // SYS:1294-1309
-        if (hitIsStatic && hitIsGroundLike) slideNormal = hitTriNormal; // allowTriangleNormalGroundLike
+        if (hitIsStatic && hitIsGroundLike && opt.allowTriangleNormalGroundLike) slideNormal = hitTriNormal;
         if (slideNormal.y < p.min_ground_dot) {
             slideNormal.y = 0;
             float nLen = length(slideNormal);
@@ -1267,8 +1281,10 @@ bool slideResolveHit(F3 &remaining, float len, const CapsuleCastHit &sHit, Chara
         return true;
     }
     remaining = leftover;
-    double vInto = dot(ch.velocity, d3(slideNormal)); // adjustVelocity SYS:1367
-    if (vInto < 0) ch.velocity = ch.velocity - d3(slideNormal) * vInto;
+    if (opt.adjustVelocity) { // SYS:1366-1372
+        double vInto = dot(ch.velocity, d3(slideNormal));
+        if (vInto < 0) ch.velocity = ch.velocity - d3(slideNormal) * vInto;
+    }
     return false;
 }
 
@@ -1353,6 +1369,158 @@ void resolveKinematicSweep(const StaticTriMesh &q, QueryCtx &ctx, F3 &position, 
             break;
         }
     }
+}
+
+// ---- AgentSeparationSystem (SYS:1906-2210): sequential pair resolution in entity order over a uniform XZ grid,
+// then a per-agent slide from the pre-separation position and a snap to the ground
+struct SepAgent { // AgentSeparationSystem.Agent (SYS:1907-1915); the controller copy is the character's orc_state
+    F3 position, velocity;
+    float radius, halfHeight, invWeight;
+};
+struct SepCell {
+    int64_t x, z;
+    bool operator==(const SepCell &o) const { return x == o.x && z == o.z; }
+};
+struct SepCellHash {
+    size_t operator()(const SepCell &c) const {
+        return std::hash<int64_t>()(c.x * 0x9E3779B97F4A7C15ll ^ (c.z + 0x7F4A7C15ll) * 0xC2B2AE3D27D4EB4Fll);
+    }
+};
+struct SepGrid { // AgentSeparationGrid (SYS:1917-1944)
+    float cellSize;
+    std::unordered_map<SepCell, std::vector<int>, SepCellHash> cells;
+    SepCell cellCoord(F3 pos) const { return {(int64_t)floorf(pos.x / cellSize), (int64_t)floorf(pos.z / cellSize)}; }
+    void rebuild(const std::vector<SepAgent> &agents) {
+        cells.clear();
+        for (int i = 0; i < (int)agents.size(); i++) cells[cellCoord(agents[i].position)].push_back(i);
+    }
+};
+
+// AgentSeparationResolver.resolve (SYS:1946-2041)
+void agentSeparationResolve(std::vector<SepAgent> &agents, const SepGrid &grid, const orc_params &p, float separationMargin,
+                            float heightMargin, const StaticTriMesh *query, QueryCtx &ctx, int64_t *pairCount) {
+    for (int i = 0; i < (int)agents.size(); i++) {
+        const SepAgent a = agents[i]; // `let a = agents[i]`: a copy taken at the start of i's turn
+        SepCell cell = grid.cellCoord(a.position);
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dx = -1; dx <= 1; dx++) {
+                auto it = grid.cells.find(SepCell{cell.x + dx, cell.z + dz});
+                if (it == grid.cells.end()) continue;
+                for (int j : it->second) {
+                    if (!(j > i)) continue;
+                    const SepAgent b = agents[j];
+                    float aMin = a.position.y - a.halfHeight, aMax = a.position.y + a.halfHeight;
+                    float bMin = b.position.y - b.halfHeight, bMax = b.position.y + b.halfHeight;
+                    float ddx = a.position.x - b.position.x, ddz = a.position.z - b.position.z;
+                    float distSq = ddx * ddx + ddz * ddz;
+                    float skinAllowance = smin(p.skin_width, p.skin_width);
+                    float margin = smin(separationMargin, skinAllowance);
+                    float minDist = a.radius + b.radius + margin;
+                    bool heightSeparated = aMax < bMin - heightMargin || aMin > bMax + heightMargin;
+                    if (heightSeparated) continue;
+                    if (distSq >= minDist * minDist) continue;
+                    float dist = sqrtf(smax(distSq, 1e-8f));
+                    float nx = ddx / dist, nz = ddz / dist;
+                    float penetration = minDist - dist;
+                    float wSum = a.invWeight + b.invWeight;
+                    if (wSum <= 0) continue;
+                    if (pairCount) (*pairCount)++;
+                    float corr = penetration / wSum;
+                    F3 moveA = {nx * corr * a.invWeight, 0, nz * corr * a.invWeight};
+                    F3 moveB = {-nx * corr * b.invWeight, 0, -nz * corr * b.invWeight};
+                    F3 relV = a.velocity - b.velocity;
+                    float vn = relV.x * nx + relV.z * nz;
+                    if (vn < 0) { // SYS:1985-1993
+                        float impulse = -vn;
+                        float scaleA = a.invWeight / wSum, scaleB = b.invWeight / wSum;
+                        agents[i].velocity.x += nx * impulse * scaleA;
+                        agents[i].velocity.z += nz * impulse * scaleA;
+                        agents[j].velocity.x -= nx * impulse * scaleB;
+                        agents[j].velocity.z -= nz * impulse * scaleB;
+                    }
+                    if (query) { // SYS:1994-2033
+                        const float eps = 1e-6f;
+                        bool blockedA = false, blockedB = false;
+                        CapsuleCastHit hit;
+                        if (length(moveA) > eps &&
+                            query->capsuleCastBlocking(agents[i].position, moveA, a.radius, a.halfHeight, p.collision_mask, ctx,
+                                                       hit) &&
+                            hit.toi <= p.skin_width && hit.normal.y < p.min_ground_dot)
+                            blockedA = true;
+                        if (length(moveB) > eps &&
+                            query->capsuleCastBlocking(agents[j].position, moveB, b.radius, b.halfHeight, p.collision_mask, ctx,
+                                                       hit) &&
+                            hit.toi <= p.skin_width && hit.normal.y < p.min_ground_dot)
+                            blockedB = true;
+                        if (blockedA && !blockedB) {
+                            moveA = {0, 0, 0};
+                            moveB = {-nx * penetration, 0, -nz * penetration};
+                        } else if (blockedB && !blockedA) {
+                            moveB = {0, 0, 0};
+                            moveA = {nx * penetration, 0, nz * penetration};
+                        } else if (blockedA && blockedB) {
+                            continue;
+                        }
+                    }
+                    agents[i].position = agents[i].position + moveA;
+                    agents[j].position = agents[j].position + moveB;
+                }
+            }
+    }
+}
+
+// AgentSeparationPostProcessor.apply (SYS:2043-2117) + the write-back of fixedUpdate (SYS:2196-2208)
+void agentSeparationPost(const StaticTriMesh *query, QueryCtx &ctx, const SepAgent &agent, F3 start, orc_state &s,
+                         const orc_params &p) {
+    F3 position = agent.position;
+    if (query) {
+        F3 delta = position - start;
+        float len = length(delta);
+        bool moved = false;
+        if (len > 1e-6f) {
+            moved = true;
+            F3 remaining = delta;
+            position = start;
+            Character ch;
+            ch.s = &s;
+            ch.p = &p;
+            ch.velocity = {s.velocity[0], s.velocity[1], s.velocity[2]};
+            for (int it = 0; it < 2; it++) {
+                float segLen = length(remaining);
+                if (segLen < 1e-6f) break;
+                CapsuleCastHit hit;
+                if (query->capsuleCastBlocking(position, remaining, agent.radius, agent.halfHeight, p.collision_mask, ctx, hit)) {
+                    bool done = slideResolveHit(remaining, segLen, hit, ch, false, false, position, false, f3(0, 0, 0), nullptr,
+                                                kSlideAgentSeparation);
+                    if (done) break;
+                } else {
+                    position = position + remaining;
+                    remaining = {0, 0, 0};
+                    break;
+                }
+            }
+        }
+        if (moved && s.velocity[1] <= 0) { // body.linearVelocity.y (Double, still the pre-separation value)
+            if (p.snap_distance > 0) {
+                F3 down = {0, -1, 0};
+                F3 snapDelta = down * p.snap_distance;
+                CapsuleCastHit hit;
+                if (query->capsuleCastGround(position, snapDelta, agent.radius, agent.halfHeight, p.min_ground_dot,
+                                             p.collision_mask, ctx, hit) &&
+                    hit.toi <= p.snap_distance) {
+                    float rawMove = smax(hit.toi - p.ground_snap_skin, 0.0f);
+                    float moveDist = smin(rawMove, p.ground_snap_max_step);
+                    position = position + down * moveDist;
+                    s.grounded = 1;
+                    s.grounded_near = hit.toi <= smax(p.ground_snap_skin, p.skin_width) ? 1 : 0;
+                    st3(s.ground_normal, hit.material.flatten ? f3(0, 1, 0) : hit.triangleNormal);
+                    s.ground_triangle_index = hit.triangleIndex;
+                }
+            }
+        }
+    }
+    s.position[0] = (double)position.x, s.position[1] = (double)position.y, s.position[2] = (double)position.z;
+    s.velocity[0] = (double)agent.velocity.x, s.velocity[1] = (double)agent.velocity.y, s.velocity[2] = (double)agent.velocity.z;
 }
 
 struct GroundContactState { // SYS:810-817
@@ -1701,6 +1869,45 @@ int32_t orc_world_check_bvh(const orc_world *w, int32_t which) {
         }
     }
     return 1;
+}
+
+// AgentSeparationSystem.fixedUpdate (SYS:2136-2210): every character of the batch is a solid agent;
+// mass_weight per agent (null = 1.0 each, AgentCollisionComponent default); use_query = setQuery(...) was given
+void orc_agent_separation(orc_world *w, orc_state *inout, int32_t n, const orc_params *params, const float *mass_weight,
+                          int32_t iterations, float separation_margin, float height_margin, int32_t use_query, int32_t order,
+                          int32_t n_threads, int64_t *pair_count) {
+    if (pair_count) *pair_count = 0;
+    if (n <= 1) return; // `guard agents.count > 1`
+    const orc_params &p = *params;
+    std::vector<SepAgent> agents(n);
+    std::vector<F3> originalPositions(n);
+    float maxRadius = 0;
+    for (int i = 0; i < n; i++) {
+        float mw = mass_weight ? mass_weight[i] : 1.0f;
+        float invWeight = mw > 0 ? 1.0f / mw : 0.0f;
+        maxRadius = smax(maxRadius, p.radius);
+        F3 pos = {(float)inout[i].position[0], (float)inout[i].position[1], (float)inout[i].position[2]};
+        F3 vel = {(float)inout[i].velocity[0], (float)inout[i].velocity[1], (float)inout[i].velocity[2]};
+        agents[i] = {pos, vel, p.radius, p.half_height, invWeight};
+        originalPositions[i] = pos;
+    }
+    SepGrid grid;
+    grid.cellSize = smax(maxRadius * 2 + separation_margin, 0.001f);
+    QueryCtx ctx;
+    ctx.order = order;
+    const StaticTriMesh *query = use_query ? &w->mesh : nullptr;
+    iterations = std::max(1, iterations);
+    for (int it = 0; it < iterations; it++) {
+        grid.rebuild(agents);
+        agentSeparationResolve(agents, grid, p, separation_margin, height_margin, query, ctx, pair_count);
+    }
+    parallelFor(n, n_threads, [&](int, int lo, int hi) {
+        for (int i = lo; i < hi; i++) {
+            QueryCtx c2;
+            c2.order = order;
+            agentSeparationPost(query, c2, agents[i], originalPositions[i], inout[i], p);
+        }
+    });
 }
 
 void orc_raycast(orc_world *w, const orc_ray *rays, int32_t n, orc_ray_hit *out, int32_t order, int32_t n_threads,

@@ -95,6 +95,12 @@ void orc_world_update_transforms(orc_world *w, const uint32_t *entity_ids, const
  * flag: returns 1 if every internal node equals merge(children) and every leaf equals its range. */
 int32_t orc_world_check_bvh(const orc_world *w, int32_t which);
 
+/* AgentSeparationSystem.fixedUpdate (Systems.swift:2136-2210) over the batch (every character a solid agent):
+ * `iterations` sequential grid + pair-resolution sweeps in index order, then per agent a <= 2-cast slide from its
+ * pre-separation position and a ground snap.  mass_weight: per agent or NULL (1.0); use_query 0 = no world casts. */
+void orc_agent_separation(orc_world *w, orc_state *inout, int32_t n, const orc_params *params, const float *mass_weight,
+                          int32_t iterations, float separation_margin, float height_margin, int32_t use_query, int32_t order,
+                          int32_t n_threads, int64_t *pair_count);
 void orc_raycast(orc_world *w, const orc_ray *rays, int32_t n, orc_ray_hit *out, int32_t order,
                  int32_t n_threads, orc_stats *stats);
 void orc_capsule_cast(orc_world *w, const orc_cast *q, int32_t n, int32_t mode, orc_cast_hit *out,

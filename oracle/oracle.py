@@ -94,6 +94,8 @@ def lib():
         L.orc_segment_triangle_distance_batch.argtypes = [C.c_int32] + [C.c_void_p] * 6
         L.orc_ray_triangle_batch.argtypes = [C.c_int32] + [C.c_void_p] * 5
         L.orc_capsule_capsule_sweep_batch.argtypes = [C.c_int32] + [C.c_void_p] * 8
+        L.orc_agent_separation.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                           C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_closest_point_on_triangle.restype = C.c_float
         L.orc_closest_point_on_triangle.argtypes = [C.c_void_p] * 5
         L.orc_segment_segment_distance_sq.restype = C.c_float
@@ -232,6 +234,19 @@ class OracleWorld:
         lib().orc_move_and_slide_ex(self._h, _ptr(states), len(states), _ptr(params), np.float32(dt), _ptr(g), flags,
                                     order, n_threads, C.byref(stats) if stats is not None else None, _ptr(pl), len(pl))
         return states
+
+    def agent_separation(self, states, params, mass_weight=None, iterations=2, separation_margin=0.2, height_margin=0.1,
+                         use_query=True, order=ORDER_CANONICAL, n_threads=1):
+        """AgentSeparationSystem.fixedUpdate over the batch, in place; returns the number of resolved pairs."""
+        assert states.dtype == STATE and states.flags["C_CONTIGUOUS"]
+        params = np.ascontiguousarray(params, PARAMS)
+        mw = None if mass_weight is None else np.ascontiguousarray(mass_weight, np.float32)
+        assert mw is None or len(mw) == len(states)
+        pairs = C.c_int64(0)
+        lib().orc_agent_separation(self._h, _ptr(states), len(states), _ptr(params), None if mw is None else _ptr(mw),
+                                   iterations, separation_margin, height_margin, 1 if use_query else 0, order, n_threads,
+                                   C.byref(pairs))
+        return pairs.value
 
 
 def capsule_capsule_sweep_batch(frm, delta, other_pos, other_delta, dims):

@@ -300,3 +300,57 @@ def test_agents_block_each_other(orc, scenes):
     assert solid["position"][2][0] == pytest.approx(ghost["position"][2][0]) and ghost["position"][2][0] > 48.0
     assert ghost["position"][0][0] > 4.0 and ghost["position"][1][0] < -4.0  # passed through each other
     assert solid["grounded"].tolist() == [1, 1, 1]
+
+
+def test_agent_separation_known_answers(orc, scenes):
+    """AgentSeparationSystem (Systems.swift:1906-2210) on cases with closed-form answers: minDist = rA + rB +
+    min(separationMargin 0.2, skinWidth 0.3) = 3.2 for default capsules; the correction is split by inverse mass; closing
+    velocity along the pair normal is removed the same way; agents separated in height do not interact; velocity is
+    rounded through Float by the write-back; a wall behind one agent hands the whole correction to the other."""
+    w = orc.OracleWorld([big_floor(scenes, y=-3.0, eid=0)])
+    p = orc.default_params()
+    y = -3.0 + 2.5 + 0.05
+    s = orc.init_states([[0.0, y, 0.0], [2.6, y, 0.0]], [[1.0, 0, 0.5], [-1.0, 0, 0.5]])
+    s["grounded"] = s["grounded_near"] = 1
+    n_pairs = w.agent_separation(s, p, iterations=1, use_query=False)
+    assert n_pairs == 1
+    assert s["position"][:, 0] == pytest.approx([-0.3, 2.9], abs=1e-6)  # penetration 0.6 split evenly
+    assert s["velocity"][:, 0] == pytest.approx([0.0, 0.0], abs=1e-6)    # closing speed 2 along x removed, half each
+    assert s["velocity"][:, 2] == pytest.approx([0.5, 0.5])              # tangential part untouched
+    # mass weights 500 : 1 -> the light one takes 500/501 of the correction
+    s = orc.init_states([[0.0, y, 0.0], [2.6, y, 0.0]])
+    w.agent_separation(s, p, mass_weight=[500.0, 1.0], iterations=1, use_query=False)
+    assert s["position"][0][0] == pytest.approx(-0.6 / 501, abs=1e-6) and s["position"][1][0] == pytest.approx(2.6 + 0.6 * 500 / 501, abs=1e-5)
+    # massWeight <= 0 -> invWeight 0: immovable; two immovable agents are skipped
+    s = orc.init_states([[0.0, y, 0.0], [2.6, y, 0.0]])
+    w.agent_separation(s, p, mass_weight=[0.0, 1.0], iterations=1, use_query=False)
+    assert s["position"][0][0] == 0.0 and s["position"][1][0] == pytest.approx(3.2, abs=1e-6)
+    s = orc.init_states([[0.0, y, 0.0], [2.6, y, 0.0]])
+    assert w.agent_separation(s, p, mass_weight=[0.0, -1.0], iterations=1, use_query=False) == 0
+    # separated in height by more than heightMargin: no interaction (hh = 1: [y-1, y+1] against [y+2.2-1, ...])
+    s = orc.init_states([[0.0, y, 0.0], [1.0, y + 2.2, 0.0]])
+    assert w.agent_separation(s, p, iterations=2, use_query=False) == 0
+    # sequential (Gauss-Seidel) order: pair (0,1) moves 1 to 3.1 BEFORE pair (1,2) is measured, so (1,2) sees a
+    # penetration of 0.2, not 0.1 — a simultaneous (Jacobi) resolution would end at [-0.1, 3.05, 6.15]
+    s = orc.init_states([[0.0, y, 0.0], [3.0, y, 0.0], [6.1, y, 0.0]])
+    w.agent_separation(s, p, iterations=1, use_query=False)
+    assert s["position"][:, 0] == pytest.approx([-0.1, 3.0, 6.2], abs=1e-5)
+    # velocity goes through Float even without any contact (linearVelocityF -> d3), position too
+    s = orc.init_states([[0.1, y, 0.0], [50.0, y, 0.0]], [[0.1, 0, 0], [0, 0, 0]])
+    s["velocity"][0][0] = 0.1  # not representable in float32
+    w.agent_separation(s, p, use_query=False)
+    assert s["velocity"][0][0] == float(np.float32(0.1)) and s["position"][0][0] == float(np.float32(0.1))
+    # fewer than two agents: the system returns before touching anything
+    one = orc.init_states([[0.1, y, 0.0]], [[0.1, 0, 0]])
+    one["velocity"][0][0] = 0.1
+    w.agent_separation(one, p)
+    assert one["velocity"][0][0] == 0.1
+    # a wall right behind agent 1: its share of the push is blocked (toi <= skinWidth, side normal) -> agent 0 takes it all
+    bv, bi = scenes.box_mesh(8.0)
+    wall = scenes.part(bv, bi, scenes.trs_model((2.6 + 1.5 + 0.05 + 4.0, 0.0, 0.0)), entity_id=1)
+    w2 = orc.OracleWorld([big_floor(scenes, y=-3.0, eid=0), wall])
+    s = orc.init_states([[0.0, y, 0.0], [2.6, y, 0.0]])
+    s["grounded"] = s["grounded_near"] = 1
+    w2.agent_separation(s, p, iterations=1, use_query=True, order=orc.ORDER_REFERENCE)
+    assert s["position"][1][0] == pytest.approx(2.6, abs=1e-6) and s["position"][0][0] == pytest.approx(-0.6, abs=1e-5)
+    assert s["grounded"].tolist() == [1, 1]
