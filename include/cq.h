@@ -282,6 +282,22 @@ int cq_move_and_slide_device_ex(cq_world *w, cq_character_state *d_inout, int32_
                                 uint32_t flags, const cq_platform *platforms /* HOST pointer */,
                                 int32_t n_platforms, void *stream);
 
+/* AgentSeparationSystem.fixedUpdate (Systems.swift:1906-2210) over the batch — every character a solid agent, entity
+ * order = index order: `iterations` (reference default 2) sweeps of {rebuild the XZ grid with cell 2r + separation_margin,
+ * resolve overlapping pairs SEQUENTIALLY in index order: positional correction split by inverse mass, closing velocity
+ * removed, each agent's share of the push vetoed by a blocking capsule cast when use_query != 0}, then per agent a
+ * <= 2-cast slide from its pre-separation position (SlideOptions.agentSeparation) and a ground snap; position and
+ * velocity are written back through Float as the reference does.  The sequential semantics are reproduced exactly (the
+ * turns are scheduled along their conflict DAG).  mass_weight: AgentCollisionComponent.massWeight per character
+ * (<= 0 = immovable), NULL = 1.0.  separation_margin 0.2, height_margin 0.1 are the reference defaults.  n < 2 is a
+ * no-op.  The _device variant is stream-ordered but synchronises the stream internally (the schedule is host-driven). */
+int cq_agent_separation_batch(cq_world *w, cq_character_state *inout, int32_t n, const cq_controller_params *params,
+                              const float *mass_weight, int32_t iterations, float separation_margin, float height_margin,
+                              int32_t use_query);
+int cq_agent_separation_device(cq_world *w, cq_character_state *d_inout, int32_t n, const cq_controller_params *params,
+                               const float *d_mass_weight, int32_t iterations, float separation_margin, float height_margin,
+                               int32_t use_query, void *stream);
+
 /* ---- instrumentation ------------------------------------------------------
  * Work counters of the last device/batch call, accumulated on the device when
  * counting is enabled (off by default; the reference's CollisionQueryStats,

@@ -86,7 +86,8 @@ EXPORTS = [
     "cq_capsule_overlap_all_batch", "cq_raycast_device", "cq_capsule_cast_device", "cq_capsule_overlap_device",
     "cq_capsule_overlap_all_device", "cq_controller_params_default", "cq_character_state_init",
     "cq_move_and_slide_batch", "cq_move_and_slide_device", "cq_move_and_slide_batch_ex",
-    "cq_move_and_slide_device_ex", "cq_world_set_counting", "cq_world_read_counters",
+    "cq_move_and_slide_device_ex", "cq_agent_separation_batch", "cq_agent_separation_device",
+    "cq_world_set_counting", "cq_world_read_counters",
     "cq_host_alloc", "cq_host_free", "cq_last_error", "cq_version",
 ]
 
@@ -151,6 +152,8 @@ def lib():
         L.cq_move_and_slide_device.argtypes = [vp, vp, i32, vp, f32, vp, u32, vp]
         L.cq_move_and_slide_batch_ex.argtypes = [vp, vp, i32, vp, f32, vp, u32, vp, i32]
         L.cq_move_and_slide_device_ex.argtypes = [vp, vp, i32, vp, f32, vp, u32, vp, i32, vp]
+        L.cq_agent_separation_batch.argtypes = [vp, vp, i32, vp, vp, i32, f32, f32, i32]
+        L.cq_agent_separation_device.argtypes = [vp, vp, i32, vp, vp, i32, f32, f32, i32, vp]
         L.cq_world_set_counting.argtypes = [vp, i32]
         L.cq_world_read_counters.argtypes = [vp, C.POINTER(Counters), i32]
         _lib = L
@@ -370,6 +373,26 @@ class CollisionQuery:
         _check(lib().cq_move_and_slide_batch_ex(self._h, _ptr(states), len(states), _ptr(params), C.c_float(dt), _ptr(g),
                                                 flags, _ptr(pl), len(pl)))
         return states
+
+    def agent_separation(self, states, params, mass_weight=None, iterations=2, separation_margin=0.2, height_margin=0.1,
+                         use_query=True):
+        """AgentSeparationSystem.fixedUpdate over the batch (Systems.swift:1906-2210), in place, sequential semantics."""
+        assert states.dtype == STATE and states.flags["C_CONTIGUOUS"]
+        params = np.ascontiguousarray(params, PARAMS)
+        mw = None if mass_weight is None else np.ascontiguousarray(mass_weight, np.float32)
+        assert mw is None or len(mw) == len(states)
+        _check(lib().cq_agent_separation_batch(self._h, _ptr(states), len(states), _ptr(params),
+                                               None if mw is None else _ptr(mw), iterations, separation_margin,
+                                               height_margin, 1 if use_query else 0))
+        return states
+
+    def agent_separation_device(self, d_states_ptr, n, params, d_mass_weight_ptr=None, iterations=2, separation_margin=0.2,
+                                height_margin=0.1, use_query=True, stream=None):
+        params = np.ascontiguousarray(params, PARAMS)
+        _check(lib().cq_agent_separation_device(self._h, C.c_void_p(d_states_ptr), n, _ptr(params),
+                                                C.c_void_p(d_mass_weight_ptr) if d_mass_weight_ptr else None, iterations,
+                                                separation_margin, height_margin, 1 if use_query else 0,
+                                                C.c_void_p(stream) if stream else None))
 
     def move_and_slide_device(self, d_states_ptr, n, params, dt=1.0 / 60.0, gravity=(0.0, -98.0, 0.0),
                               flags=MAS_APPLY_GRAVITY, stream=None):

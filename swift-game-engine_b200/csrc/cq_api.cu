@@ -272,6 +272,7 @@ void cq_world_destroy(cq_world *w) {
     cudaFree(w->in.ptr), cudaFree(w->out.ptr), cudaFree(w->aux.ptr), cudaFree(w->aux2.ptr);
     for (int k = 0; k < 4; k++) cudaFree(w->nodeScratch[k].ptr), cudaFree(w->orderScratch[k].ptr);
     cudaFree(w->agentScratch.ptr);
+    cudaFree(w->sepScratch.ptr);
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -515,6 +516,37 @@ int cq_move_and_slide_batch_ex(cq_world *w, cq_character_state *inout, int32_t n
                                                       n_platforms, st);
                      },
                      /*inPlace=*/true, &w->hintMas, /*singleChunk=*/(flags & CQ_MAS_AGENTS) != 0);
+}
+
+int cq_agent_separation_device(cq_world *w, cq_character_state *d_inout, int32_t n, const cq_controller_params *params,
+                               const float *d_mass_weight, int32_t iterations, float separation_margin, float height_margin,
+                               int32_t use_query, void *stream) {
+    if (!w || n < 0 || !params || (n > 0 && !d_inout)) return CQ_ERR_INVALID;
+    CQ_CUDA(cudaSetDevice(w->device));
+    return launch_agent_separation(w, d_inout, n, *params, d_mass_weight, iterations, separation_margin, height_margin, use_query,
+                                   pick_stream(w, stream));
+}
+
+int cq_agent_separation_batch(cq_world *w, cq_character_state *inout, int32_t n, const cq_controller_params *params,
+                              const float *mass_weight, int32_t iterations, float separation_margin, float height_margin,
+                              int32_t use_query) {
+    if (!w || n < 0 || !params || (n > 0 && !inout)) return CQ_ERR_INVALID;
+    if (n == 0) return CQ_OK;
+    CQ_CUDA(cudaSetDevice(w->device));
+    CQ_CUDA(cudaStreamSynchronize(w->stream));
+    int r;
+    if ((r = ensure_scratch(w->in, sizeof(cq_character_state) * (size_t)n)) != CQ_OK) return r;
+    if (mass_weight && (r = ensure_scratch(w->aux, sizeof(float) * (size_t)n)) != CQ_OK) return r;
+    cudaStream_t st = w->stream;
+    cq_character_state *d = (cq_character_state *)w->in.ptr;
+    CQ_CUDA(cudaMemcpyAsync(d, inout, sizeof(cq_character_state) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (mass_weight) CQ_CUDA(cudaMemcpyAsync(w->aux.ptr, mass_weight, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+    r = launch_agent_separation(w, d, n, *params, mass_weight ? (const float *)w->aux.ptr : nullptr, iterations,
+                                separation_margin, height_margin, use_query, st);
+    if (r != CQ_OK) return r;
+    CQ_CUDA(cudaMemcpyAsync(inout, d, sizeof(cq_character_state) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CQ_CUDA(cudaStreamSynchronize(st));
+    return CQ_OK;
 }
 
 } // extern "C"

@@ -893,6 +893,12 @@ const uint32_t *make_unit_order(cq_world *w, const void *dUnits, size_t stride, 
     return vals;
 }
 
+size_t sort_scratch_words(int n) { return (size_t)4 * 256 * cdiv(n, RS_TILE) + 4 + 1024 + 1; }
+int sort_pairs_u32(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTmp, uint32_t *valsTmp, int n, uint32_t *scratch,
+                   size_t scratchWords, cudaStream_t st) {
+    return radix_sort_pairs_onesweep(w, keys, vals, keysTmp, valsTmp, n, scratch, scratchWords, st, false);
+}
+
 // ---------------------------------------------------------------- agent snapshot + grid (CQ_MAS_AGENTS)
 // bounds: [0..1] min x,z  [2..3] max x,z  [4] max |v|  (ordered ints)
 __global__ void k_agent_bounds_init(int *bounds) {

@@ -83,6 +83,8 @@ struct cq_world {
     uint32_t workSeq = 0;
     cq::ScratchBuf in, out, aux, aux2;
     cq::ScratchBuf agentScratch; // agent snapshot + grid of the move-and-slide call in flight (CQ_MAS_AGENTS)
+    cq::ScratchBuf sepScratch;   // cq_agent_separation working set
+    int occSep[2][2] = {};       // resident CTAs per SM of k_sep_turns / k_sep_post ([counting build])
 };
 
 namespace cq {
@@ -121,6 +123,11 @@ int make_agent_grid(cq_world *w, const cq_character_state *dStates, int n, float
                     uint32_t flags, cudaStream_t st, AgentGrid &out);
 const uint32_t *make_unit_order(cq_world *w, const void *dUnits, size_t stride, bool positionIsDouble, int n, cudaStream_t st);
 
+// 32-bit key / value LSD radix sort (onesweep); `scratch` holds sort_scratch_words(n) words.  Result in (keys, vals).
+size_t sort_scratch_words(int n);
+int sort_pairs_u32(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTmp, uint32_t *valsTmp, int n, uint32_t *scratch,
+                   size_t scratchWords, cudaStream_t st);
+
 // cq_query.cu
 int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, cudaStream_t st);
 int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st);
@@ -130,4 +137,8 @@ int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, c
 // cq_mas.cu
 int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p, float dt,
                           const float g[3], uint32_t flags, const cq_platform *platforms, int nPlatforms, cudaStream_t st);
+// cq_sep.cu
+int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p,
+                            const float *d_massWeight, int iterations, float sepMargin, float heightMargin, int useQuery,
+                            cudaStream_t st);
 } // namespace cq

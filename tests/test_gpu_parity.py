@@ -482,3 +482,59 @@ def test_agents_capsule_capsule_ccd(cq, orc, scenes):
     g.move_and_slide(one[:0].copy(), p, flags=3)
     g.close()
     o.close()
+
+
+@pytest.mark.gpu
+def test_agent_separation_sequential_semantics(cq, orc, scenes):
+    """cq_agent_separation_batch vs the oracle's literal sequential loop (AgentSeparationSystem, Systems.swift:1906-2210):
+    a dense crowd on a terrain with walls (so that the blocking casts veto pushes), mixed mass weights including
+    immovable agents, the full crowd step = move-and-slide with agent CCD, then separation, for several steps.  Every
+    byte of every record must match although the GPU runs the turns along their conflict DAG, not one after another."""
+    tparts, half_world = scenes.terrain_scene(cells=96, cell=1.5, seed=5)
+    bv, bi = scenes.box_mesh(6.0)
+    walls = [scenes.part(bv, bi, scenes.trs_model((x, float(scenes.terrain_height(np.float32([x]), np.float32([z]), 5)[0]), z)),
+                         entity_id=10 + k) for k, (x, z) in enumerate([(-8.0, 3.0), (9.0, -6.0), (2.0, 12.0)])]
+    parts = tparts + walls
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    rng = np.random.default_rng(21)
+    n = 2500
+    p = cq.default_params()
+    p["radius"], p["half_height"] = 0.4, 0.5
+    p["skin_width"], p["snap_distance"] = 0.08, 0.3
+    half = np.sqrt(n * np.pi * 0.4 ** 2 / 0.45) / 2  # 45% footprint coverage: plenty of overlapping pairs
+    x, z = rng.uniform(-half, half, n), rng.uniform(-half, half, n)
+    y = scenes.terrain_height(x, z, 5) + np.float32(0.9 + 0.05) + rng.uniform(0, 0.2, n)
+    pos = np.stack([x, y, z], axis=1).astype(np.float32)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    walk = (np.stack([np.cos(ang), np.zeros(n), np.sin(ang)], axis=1) * rng.uniform(1, 7, (n, 1))).astype(np.float32)
+    mass = rng.choice(np.float32([1.0, 3.0, 500.0, 0.0]), n, p=[0.6, 0.25, 0.1, 0.05])
+    sg, so = cq.init_states(pos, walk), orc.init_states(pos, walk)
+    total_pairs = 0
+    for step in range(5):
+        g.move_and_slide(sg, p, flags=3)
+        o.move_and_slide(so, p, flags=3, order=orc.ORDER_CANONICAL, n_threads=8)
+        assert sg.tobytes() == so.tobytes(), ("move", step)
+        g.agent_separation(sg, p, mass_weight=mass)
+        total_pairs += o.agent_separation(so, p, mass_weight=mass, order=orc.ORDER_CANONICAL, n_threads=8)
+        assert sg.tobytes() == so.tobytes(), ("separation", step)
+        for s in (sg, so):
+            s["velocity"][:, 0] = walk[:, 0]
+            s["velocity"][:, 2] = walk[:, 2]
+    assert total_pairs > 2 * n
+    # no world casts (setQuery never called), one sweep, default masses; and the trivial sizes
+    a, b = sg.copy(), so.copy()
+    g.agent_separation(a, p, iterations=1, use_query=False)
+    o.agent_separation(b, p, iterations=1, use_query=False)
+    assert a.tobytes() == b.tobytes()
+    one = sg[:1].copy()
+    g.agent_separation(one, p)
+    assert one.tobytes() == sg[:1].tobytes()
+    g.agent_separation(sg[:0].copy(), p)
+    # agents sorted along x (index correlates with space): the conflict DAG degenerates towards a chain, still exact
+    order = np.argsort(sg["position"][:, 0], kind="stable")
+    a, b = np.ascontiguousarray(sg[order]), np.ascontiguousarray(so[order])
+    g.agent_separation(a, p, mass_weight=mass[order])
+    o.agent_separation(b, p, mass_weight=mass[order], order=orc.ORDER_CANONICAL, n_threads=8)
+    assert a.tobytes() == b.tobytes()
+    g.close()
+    o.close()
