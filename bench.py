@@ -167,10 +167,12 @@ def controller_params(mod, mesh):
     return mod.default_params(**TERRAIN_PARAMS) if mesh == "terrain" else mod.default_params()
 
 
-def workload_name(mesh, n, agents=0.0):
+def workload_name(mesh, n, agents=0.0, separation=False):
     if mesh == "terrain":
         crowd = (f"; every character a solid agent (capsule-capsule CCD against a pre-step snapshot of the others), "
                  f"crowd footprint coverage {agents:g}") if agents > 0 else ""
+        if separation:
+            crowd += ", followed by AgentSeparationSystem (2 sequential pair-resolution sweeps + slide + snap)"
         return (f"target scene: {n} characters/GPU x 1 move-and-slide fixed step over the procedural terrain of "
                 "9,999,392 triangles (cell 2 m), human-scale controller r=0.4 hh=0.5 skin 0.08, dt=1/60, gravity on" + crowd)
     tri = "2 collision hulls (76 tris) + ground plane (2 tris)" if mesh == "hulls" else \
@@ -198,11 +200,16 @@ def run_reference(args):
     w = orc.OracleWorld(parts)
     s = orc.init_states(pos, vel)
     p = controller_params(orc, args.mesh)
-    for _ in range(args.warmup):
+    def ref_step():
         w.move_and_slide(s, p, DT, GRAVITY, mas_flags, orc.ORDER_REFERENCE, cores)
+        if args.separation:
+            w.agent_separation(s, p, order=orc.ORDER_REFERENCE, n_threads=cores)
+
+    for _ in range(args.warmup):
+        ref_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        w.move_and_slide(s, p, DT, GRAVITY, mas_flags, orc.ORDER_REFERENCE, cores)
+        ref_step()
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     sample = f"{n} of {CHARS_PER_GPU} characters per step, {args.steps} steps, state carried"
@@ -213,7 +220,7 @@ def run_reference(args):
         "impl": "reference", "metric": "move_and_slide_queries_per_sec", "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.mesh, CHARS_PER_GPU, args.agents), "mesh": args.mesh,
+        "config": {"workload": workload_name(args.mesh, CHARS_PER_GPU, args.agents, args.separation), "mesh": args.mesh,
                    "reference_impl": "C++ restatement of CollisionQuery.swift + Systems.swift move-and-slide "
                                      "(oracle/), reference BVH + DFS order; not swiftc-compiled"},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
@@ -280,6 +287,8 @@ def run_ours(args):
 
     def step_device():
         world.move_and_slide_device(d_states.data_ptr(), n, params, DT, GRAVITY, mas_flags, stream)
+        if args.separation:  # the reference's fixed step runs AgentSeparationSystem right after the kinematic move
+            world.agent_separation_device(d_states.data_ptr(), n, params, stream=stream)
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # runs through warm-up, the timed region and a short identical load after it (see below)
@@ -355,12 +364,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     pinned.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)
     world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)  # warm the staging buffers
+    if args.separation:
+        world.agent_separation(pinned.array, params)
     pinned.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)
     e2e_steps = args.steps
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)
+        if args.separation:
+            world.agent_separation(pinned.array, params)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -393,6 +406,8 @@ def run_ours(args):
         t0 = time.perf_counter()
         ow.move_and_slide(snap_np, controller_params(orc, args.mesh), DT, GRAVITY, 3 if args.agents > 0 else 1,
                           orc.ORDER_REFERENCE, cores)
+        if args.separation:
+            ow.agent_separation(snap_np, controller_params(orc, args.mesh), order=orc.ORDER_REFERENCE, n_threads=cores)
         cdt = time.perf_counter() - t0
         cpu_baseline = {"value": ns / cdt, "unit": "queries/s", "cores": cores, "kind": "port",
                         "sample": f"{what}, the first timed step, {cdt:.2f} s wall; "
@@ -404,7 +419,7 @@ def run_ours(args):
             "metric": "move_and_slide_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.mesh, n, args.agents), "mesh": args.mesh, "characters_per_gpu": n,
+            "config": {"workload": workload_name(args.mesh, n, args.agents, args.separation), "mesh": args.mesh, "characters_per_gpu": n,
                        "triangles": info["n_static_triangles"] + info["n_dynamic_triangles"],
                        "l2": "inputs (168 B x characters = %.0f MB per GPU) exceed the 126 MB L2; no flush" % (nbytes / 1e6),
                        "parallelism": f"queries sharded over {world_size} GPU(s), mesh+BVH replicated, no collective",
@@ -753,6 +768,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", default="hulls", choices=["hulls", "render", "terrain"])
     ap.add_argument("--chars", type=int, default=CHARS_PER_GPU)
+    ap.add_argument("--separation", action="store_true",
+                    help="with --agents: also run AgentSeparationSystem (exact sequential semantics) every step")
     ap.add_argument("--agents", type=float, default=0.0,
                     help="terrain mesh only: characters collide with each other; value = crowd footprint coverage (e.g. 0.1)")
     ap.add_argument("--ref-sample", type=int, default=0)

@@ -41,6 +41,8 @@ struct SepArgs {
     const int2 *cell0;      // rebuild cell of every agent (relative coordinates)
     const uint32_t *keys;   // sorted cell keys
     const uint32_t *sidx;   // agent indices in (cell, index) order = the reference's per-cell lists
+    const int4 *rows;       // per agent, 2 x int4: [start, end) of the rows cz-1, cz, cz+1 (cells cx-1..cx+1) around its
+                            // REBUILD cell in the sorted arrays — valid for the turn when the agent has not left that cell
     const SepGridParams *gp;
     const int *queue;       // ready turns of this round
     const int *qcount;
@@ -134,6 +136,28 @@ __global__ void k_sep_keys(const int2 *__restrict__ cellRaw, int n, const SepGri
     vals[i] = (uint32_t)i;
 }
 
+// the three sorted-array ranges of an agent's 3x3 neighbourhood (a row of cells is one contiguous key range, and
+// (key, index) order inside it = the reference's dx-then-list order), found once per sweep at full occupancy
+__device__ __forceinline__ void sep_row_range(const uint32_t *keys, int n, int dimX, int dimZ, int cx, int z, int &k0, int &k1) {
+    k0 = k1 = 0;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimX - 1);
+    if (z < 0 || z >= dimZ || x0 > x1) return; // no agent was registered there: `cells[neighbor]` is nil
+    const uint32_t keyLo = (uint32_t)z * (uint32_t)dimX + (uint32_t)x0, keyHi = keyLo + (uint32_t)(x1 - x0);
+    k0 = sep_lower_bound(keys, n, keyLo);
+    k1 = sep_upper_bound(keys, n, keyHi, k0);
+}
+
+__global__ void k_sep_rows(const uint32_t *__restrict__ keys, const int2 *__restrict__ cell0,
+                           const SepGridParams *__restrict__ gp, int n, int4 *rows) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const int2 c = cell0[h];
+    int se[6];
+    for (int r = 0; r < 3; r++) sep_row_range(keys, n, gp->dimX, gp->dimZ, c.x, c.y + r - 1, se[2 * r], se[2 * r + 1]);
+    rows[2 * (size_t)h] = make_int4(se[0], se[1], se[2], se[3]);
+    rows[2 * (size_t)h + 1] = make_int4(se[4], se[5], 0, 0);
+}
+
 // blockers(h) = lower-indexed agents whose rebuild cell is within D cells (Chebyshev) of h's
 __global__ void k_sep_count_blockers(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ sidx,
                                      const int2 *__restrict__ cell0, const SepGridParams *__restrict__ gp, int n, int D,
@@ -189,7 +213,8 @@ struct SepCtx { // per-lane turn state, shared memory
     float aInvW;
     float cPos[3], cVel[3]; // agents[i] as the turn's own corrections accumulate
     int cx, cz;             // current cell (relative coordinates)
-    int cellIt, k0, k1;     // which of the 9 cells, cursor / end in the sorted arrays
+    int cellIt, k0, k1;     // which of the 3 rows of cells, cursor / end in the sorted arrays
+    int rowSE[6];           // the rows' ranges when the agent still sits in its rebuild cell, else rowSE[0] = -1
     int j;                  // the pair in flight
     float nx, nz, penetration;
     float moveA[3], moveB[3], bPos[3];
@@ -203,15 +228,13 @@ __device__ __forceinline__ void sst3(float *o, f3 v) {
     o[2] = v.z;
 }
 
-// position the cursor on cell number c.cellIt of the 3x3 block (dz outer, dx inner: SYS:1955-1956)
+// position the cursor on row number c.cellIt of the 3x3 block (dz outer, dx inner: SYS:1955-1956)
 __device__ __forceinline__ void sep_open_cell(SepCtx &c, const SepArgs &A) {
-    const int dimX = A.gp->dimX, dimZ = A.gp->dimZ;
-    const int x = c.cx + (c.cellIt % 3) - 1, z = c.cz + (c.cellIt / 3) - 1;
-    c.k0 = c.k1 = 0;
-    if (x < 0 || x >= dimX || z < 0 || z >= dimZ) return; // no agent was registered there: `cells[neighbor]` is nil
-    const uint32_t key = (uint32_t)z * (uint32_t)dimX + (uint32_t)x;
-    c.k0 = sep_lower_bound(A.keys, A.n, key);
-    c.k1 = sep_upper_bound(A.keys, A.n, key, c.k0);
+    if (c.rowSE[0] >= 0) {
+        c.k0 = c.rowSE[2 * c.cellIt], c.k1 = c.rowSE[2 * c.cellIt + 1];
+        return;
+    }
+    sep_row_range(A.keys, A.n, A.gp->dimX, A.gp->dimZ, c.cx, c.cz + c.cellIt - 1, c.k0, c.k1);
 }
 
 __device__ __forceinline__ void sep_apply_pair(SepCtx &c, const SepArgs &A) { // SYS:2035-2036
@@ -283,13 +306,18 @@ __device__ __forceinline__ bool sep_advance(SepCtx &c, const QResult &q, QShared
             c.cz = sep_cell(p.z, A.cellSize) - A.gp->minZ;
             const int2 c0 = A.cell0[h];
             if (abs(c.cx - c0.x) > A.R || abs(c.cz - c0.y) > A.R) atomicExch(A.flags, 1); // drifted too far: schedule unsafe
+            c.rowSE[0] = -1;
+            if (c.cx == c0.x && c.cz == c0.y) { // still in the rebuild cell: the pre-pass already found the ranges
+                const int4 r0 = A.rows[2 * (size_t)h], r1 = A.rows[2 * (size_t)h + 1];
+                c.rowSE[0] = r0.x, c.rowSE[1] = r0.y, c.rowSE[2] = r0.z, c.rowSE[3] = r0.w, c.rowSE[4] = r1.x, c.rowSE[5] = r1.y;
+            }
             c.cellIt = 0;
             sep_open_cell(c, A);
         }
         bool posted = false;
         while (true) {
             if (c.k0 >= c.k1) {
-                if (++c.cellIt == 9) break;
+                if (++c.cellIt == 3) break;
                 sep_open_cell(c, A);
                 continue;
             }
@@ -602,14 +630,16 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
     if (n <= 1) return CQ_OK; // `guard agents.count > 1` (SYS:2178)
     iterations = std::max(1, iterations);
     const size_t sortWords = sort_scratch_words(n);
-    // float4 x5 (pos vel orig posSave velSave), int2 x2 (cellRaw cell0), int x3 (cnt queueA queueB), u32 x4 (sort), scratch
-    const size_t bytes = (size_t)n * (5 * 16 + 2 * 8 + 3 * 4 + 4 * 4) + sortWords * 4 + 256;
+    // float4 x5 (pos vel orig posSave velSave), int4 x2 (rows), int2 x2 (cellRaw cell0), int x3 (cnt queueA queueB),
+    // u32 x4 (sort), scratch
+    const size_t bytes = (size_t)n * (7 * 16 + 2 * 8 + 3 * 4 + 4 * 4) + sortWords * 4 + 256;
     if (bytes > w->sepScratch.cap) {
         CQ_CUDA(cudaDeviceSynchronize());
         CQ_TRY(ensure_scratch(w->sepScratch, bytes));
     }
     float4 *pos = (float4 *)w->sepScratch.ptr, *vel = pos + n, *orig = vel + n, *posSave = orig + n, *velSave = posSave + n;
-    int2 *cellRaw = (int2 *)(velSave + n), *cell0 = cellRaw + n;
+    int4 *rows = (int4 *)(velSave + n);
+    int2 *cellRaw = (int2 *)(rows + 2 * (size_t)n), *cell0 = cellRaw + n;
     int *cnt = (int *)(cell0 + n), *queueA = cnt + n, *queueB = queueA + n;
     uint32_t *keys = (uint32_t *)(queueB + n), *vals = keys + n, *keysTmp = vals + n, *valsTmp = keysTmp + n;
     uint32_t *scratch = valsTmp + n;
@@ -637,7 +667,7 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
     A.p = p;
     A.sepMargin = sepMargin, A.heightMargin = heightMargin, A.cellSize = cellSize;
     A.useQuery = useQuery, A.n = n;
-    A.pos = pos, A.vel = vel, A.cell0 = cell0, A.keys = keys, A.sidx = vals, A.gp = gp, A.flags = flags;
+    A.pos = pos, A.vel = vel, A.cell0 = cell0, A.keys = keys, A.sidx = vals, A.rows = rows, A.gp = gp, A.flags = flags;
 
     for (int it = 0; it < iterations; it++) {
         // grid.rebuild(agents) (SYS:1931-1937): cells of the CURRENT positions; a stable sort keeps each cell's list in
@@ -648,6 +678,8 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
         k_sep_keys<<<cdiv(n, 256), 256, 0, st>>>(cellRaw, n, gp, keys, vals, cell0);
         w->launches += 4;
         CQ_TRY(sort_pairs_u32(w, keys, vals, keysTmp, valsTmp, n, scratch, sortWords, st));
+        k_sep_rows<<<cdiv(n, 256), 256, 0, st>>>(keys, cell0, gp, n, rows);
+        w->launches++;
         CQ_CUDA(cudaMemcpyAsync(posSave, pos, sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));
         CQ_CUDA(cudaMemcpyAsync(velSave, vel, sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));
         bool done = false;
