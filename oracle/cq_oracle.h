@@ -2,8 +2,8 @@
  * cq_oracle.h — C interface of the CPU oracle.
  *
  * TEST INFRASTRUCTURE ONLY.  A plain C++ restatement of the reference's
- * algorithm (Game/CollisionQuery.swift:320-1632 and the move-and-slide driver
- * Game/Systems.swift:734-1400,1613-1821).  Only tests/, __graft_entry__.smoke()
+ * algorithm (Game/CollisionQuery.swift:320-1632, the move-and-slide driver
+ * Game/Systems.swift:603-1821 and AgentSeparationSystem :1906-2210).  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may load it; the product
  * (libcq.so) never links, loads or calls anything in this directory.
  *
