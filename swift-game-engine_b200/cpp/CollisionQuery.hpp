@@ -109,6 +109,19 @@ class CollisionQuery {
                       const float gravity[3], bool applyGravity = true) {
         return cq_move_and_slide_batch(w_, inout, n, &p, dt, gravity, applyGravity ? CQ_MAS_APPLY_GRAVITY : 0u) == CQ_OK;
     }
+    // the same with kinematic platforms (PlatformCarry, Systems.swift:644-732) and, with agents = true, capsule-capsule CCD
+    // between the characters of the batch (AgentSweepSolver, Systems.swift:1053-1091)
+    bool moveAndSlide(cq_character_state *inout, int32_t n, const cq_controller_params &p, float dt, const float gravity[3],
+                      const cq_platform *platforms, int32_t nPlatforms, bool agents, bool applyGravity = true) {
+        uint32_t flags = (applyGravity ? CQ_MAS_APPLY_GRAVITY : 0u) | (agents ? CQ_MAS_AGENTS : 0u);
+        return cq_move_and_slide_batch_ex(w_, inout, n, &p, dt, gravity, flags, platforms, nPlatforms) == CQ_OK;
+    }
+    // AgentSeparationSystem.fixedUpdate (Systems.swift:2136-2210); massWeight may be null (1.0 each)
+    bool agentSeparation(cq_character_state *inout, int32_t n, const cq_controller_params &p, const float *massWeight = nullptr,
+                         int iterations = 2, float separationMargin = 0.2f, float heightMargin = 0.1f, bool useQuery = true) {
+        return cq_agent_separation_batch(w_, inout, n, &p, massWeight, iterations, separationMargin, heightMargin,
+                                         useQuery ? 1 : 0) == CQ_OK;
+    }
 
     cq_world *handle() const { return w_; }
 

@@ -6,12 +6,12 @@
 //   -> GroundProbe snap/fall/offset casts (SYS:826) -> GroundSnap (SYS:945) -> SlopeFriction (SYS:965)
 //   -> writeBack (SYS:1802).
 //
-// Execution model (see cq_engine.cuh): persistent lanes, each lane owns one character at a time and is
-// a resumable state machine.  The character's controller state lives in shared memory (CharCtx, one
-// record per lane); the in-flight collision query (LaneQ: swept box, traversal cursor, conservative-
-// advancement state, best hit) lives in registers.  Each trip of the main loop runs the three
-// convergent stages L (controller logic: consume a finished query, clip against the contact plane, post
-// the next query), T (BVH walk to the next candidate) and E (one segment-triangle distance evaluation).
+// Execution model (cq_pool.cuh): persistent warps; each lane OWNS one character at a time and is a resumable state
+// machine.  Its controller working set lives in shared memory (CharCtx), the 168-byte record stays in HBM/L2.  The
+// owner posts one collision query at a time into the warp's pool (QShared slot + roots on the warp's node stack); the
+// LBVH walk and the (query, triangle) distance evaluations are shared by all 32 lanes of the warp; when the query's
+// pending counter returns to zero the owner's logic (`mas_advance`) consumes the result, clips against the contact
+// plane, and posts the next query — without leaving the kernel.
 // Double precision exactly where the reference uses Double (velocity; SYS:792,882,958,1045,1368).
 #include "cq_pool.cuh"
 #include <cstring>

@@ -85,6 +85,31 @@ public final class CollisionQuery {
         }
     }
 
+    /// The same step with kinematic platforms (PlatformCarry, Systems.swift:644-732) and, with `agents`, capsule-capsule
+    /// CCD between the characters of the batch (AgentSweepSolver / HitSelector, Systems.swift:1053-1091, 1378-1399).
+    public func moveAndSlide(states: inout [cq_character_state], params: cq_controller_params, dt: Float,
+                             gravity: SIMD3<Float> = SIMD3<Float>(0, -98, 0), platforms: [cq_platform], agents: Bool,
+                             applyGravity: Bool = true) -> Bool {
+        var p = params
+        var g = (gravity.x, gravity.y, gravity.z)
+        let flags = (applyGravity ? UInt32(CQ_MAS_APPLY_GRAVITY) : 0) | (agents ? UInt32(CQ_MAS_AGENTS) : 0)
+        return withUnsafePointer(to: &g) { gp in
+            gp.withMemoryRebound(to: Float.self, capacity: 3) {
+                cq_move_and_slide_batch_ex(handle, &states, Int32(states.count), &p, dt, $0, flags, platforms,
+                                           Int32(platforms.count)) == CQ_OK
+            }
+        }
+    }
+
+    /// Batched AgentSeparationSystem.fixedUpdate (Systems.swift:2136-2210), sequential pair-resolution semantics kept.
+    public func agentSeparation(states: inout [cq_character_state], params: cq_controller_params, massWeights: [Float]? = nil,
+                                iterations: Int = 2, separationMargin: Float = 0.2, heightMargin: Float = 0.1,
+                                useQuery: Bool = true) -> Bool {
+        var p = params
+        return cq_agent_separation_batch(handle, &states, Int32(states.count), &p, massWeights, Int32(max(1, iterations)),
+                                         separationMargin, heightMargin, useQuery ? 1 : 0) == CQ_OK
+    }
+
     // MARK: - private
 
     private func v3(_ t: (Float, Float, Float)) -> SIMD3<Float> { SIMD3<Float>(t.0, t.1, t.2) }
