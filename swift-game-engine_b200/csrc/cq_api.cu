@@ -66,6 +66,7 @@ static void make_view(cq_world *w) {
     }
     w->view.materials = w->dMaterials;
     w->view.nParts = (int)w->parts.size();
+    w->view.stagedLeaves = (w->set[0].nTris + w->set[1].nTris) >= 4096 ? 1 : 0;
 }
 
 } // namespace cq

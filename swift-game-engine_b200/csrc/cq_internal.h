@@ -72,7 +72,7 @@ struct cq_world {
     float buildMs = 0, refitMs = 0;
     int counting = 0;
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
-    int occ[6][2] = {}; // resident CTAs per SM of each persistent kernel ([counting build]), filled on first launch
+    int occ[6][4] = {}; // resident CTAs per SM of each persistent kernel ([counting + 2 * staged-walk variant])
     int numSms = 0;
     uint64_t launches = 0;
     cq::ScratchBuf nodeScratch[4], orderScratch[4];

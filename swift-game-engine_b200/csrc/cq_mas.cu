@@ -755,7 +755,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
     }
 }
 
-template <bool COUNT, bool AGENTS>
+template <bool COUNT, bool AGENTS, bool STAGED>
 __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(WorldView W, cq_character_state *__restrict__ states,
                                                                                 int n, const __grid_constant__ MasArgs A,
                                                                                 int ownersPerWarp,
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     c.wait = W_NONE;
     c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return mas_advance<COUNT, AGENTS>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);
@@ -802,11 +802,14 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     const bool agents = (flags & CQ_MAS_AGENTS) != 0;
     int *blocksPerSm = w->occ[agents ? CQ_OCC_SLOT_AGENTS : CQ_OCC_SLOT];
     int &numSms = w->numSms;
-    const int ci = w->counting ? 1 : 0;
+    const int staged = w->view.stagedLeaves ? 1 : 0;
+    const int ci = (w->counting ? 1 : 0) + 2 * staged;
     using Kernel = void (*)(WorldView, cq_character_state *, int, const MasArgs, int, uint2 *, int *, const uint32_t *,
                             unsigned long long *);
-    static const Kernel kernels[2][2] = {{k_move_and_slide<false, false>, k_move_and_slide<true, false>},
-                                         {k_move_and_slide<false, true>, k_move_and_slide<true, true>}};
+    static const Kernel kernels[2][4] = {{k_move_and_slide<false, false, false>, k_move_and_slide<true, false, false>,
+                                          k_move_and_slide<false, false, true>, k_move_and_slide<true, false, true>},
+                                         {k_move_and_slide<false, true, false>, k_move_and_slide<true, true, false>,
+                                          k_move_and_slide<false, true, true>, k_move_and_slide<true, true, true>}};
     const Kernel kernel = kernels[agents ? 1 : 0][ci];
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;

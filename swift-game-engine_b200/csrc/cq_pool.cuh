@@ -75,8 +75,10 @@ struct WarpPool { // per-warp handles
     volatile uint32_t *tail; // pairs produced      shared
     volatile uint32_t *ntop; // node-stack height   shared
     uint2 *nstack;           // [CQ_NSCAP] (owner<<2 | set<<1 | isLeaf, ref)   global (L2 resident)
+    uint32_t *stage;         // [CQ_STAGE] triangles of the leaf ranges popped in this walk round   shared
 };
-#define CQ_POOL_WORDS (CQ_QCAP + 3) /* shared words per warp besides QShared */
+#define CQ_STAGE 128 /* 32 leaf ranges x <= 4 triangles */
+#define CQ_POOL_WORDS (CQ_QCAP + 3 + CQ_STAGE) /* shared words per warp besides QShared */
 
 __device__ __forceinline__ void pool_bind(WarpPool &wp, QShared *qsAll, uint32_t *words, uint2 *nodeScratch, int warp,
                                           int warpsPerBlock) {
@@ -85,6 +87,7 @@ __device__ __forceinline__ void pool_bind(WarpPool &wp, QShared *qsAll, uint32_t
     wp.head = wp.ring + CQ_QCAP;
     wp.tail = wp.ring + CQ_QCAP + 1;
     wp.ntop = wp.ring + CQ_QCAP + 2;
+    wp.stage = wp.ring + CQ_QCAP + 3;
     wp.nstack = nodeScratch + ((size_t)blockIdx.x * warpsPerBlock + warp) * CQ_NSCAP;
 }
 
@@ -186,7 +189,7 @@ __device__ __forceinline__ void pool_post_overlap(const WorldView &W, const Warp
 // query box, and push what survives — internal children / leaf ranges back on the stack, candidate triangles
 // (layer mask + triangle AABB passed, CollisionQuery.swift:1057-1065) into the pair ring.  One round of the walk
 // for the whole warp costs what one step of a single lane's walk used to cost.
-template <bool COUNT>
+template <bool COUNT, bool STAGED>
 __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPool &wp, int lane, Counters &ctr) {
     const uint32_t top = *wp.ntop;
     const uint32_t poppers = (top + 160u > (uint32_t)CQ_NSCAP) ? 1u : 32u; // nearly full: depth-first with one lane
@@ -197,36 +200,46 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
     __syncwarp();
     if (lane == 0) *wp.ntop = top - k;
     __syncwarp();
-    if (have) {
+    const bool isLeaf = have && (e.x & 1u) != 0u;
+    if (have && !isLeaf) { // 4-wide internal node: test up to four children
         const int owner = e.x >> 2, set = (e.x >> 1) & 1;
         QShared &s = wp.qs[owner];
         const f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
         int net = -1; // this entry is consumed
-        if ((e.x & 1u) == 0u) { // 4-wide internal node: test up to four children
-            const Node4 *n = (set ? W.set[1].nodes4 : W.set[0].nodes4) + e.y;
-            float4 q0 = __ldg(&n->q[0]), q1 = __ldg(&n->q[1]), q2 = __ldg(&n->q[2]), q3 = __ldg(&n->q[3]);
-            float4 q4 = __ldg(&n->q[4]), q5 = __ldg(&n->q[5]), q6 = __ldg(&n->q[6]), q7 = __ldg(&n->q[7]);
-            const int r0 = __float_as_int(q0.w), r1 = __float_as_int(q1.w), r2 = __float_as_int(q2.w), r3 = __float_as_int(q3.w);
-            // empty children have inverted boxes: they fail the overlap test by themselves
-            bool h0 = !box_disjoint(xyz(q0), xyz(q1), qlo, qhi), h1 = !box_disjoint(xyz(q2), xyz(q3), qlo, qhi);
-            bool h2 = !box_disjoint(xyz(q4), xyz(q5), qlo, qhi), h3 = !box_disjoint(xyz(q6), xyz(q7), qlo, qhi);
-            if (COUNT) ctr.nodes += 2 + (r2 != CQ_REF_EMPTY) + (r3 != CQ_REF_EMPTY);
-            int cnt = (h0 ? 1 : 0) + (h1 ? 1 : 0) + (h2 ? 1 : 0) + (h3 ? 1 : 0);
-            if (cnt) {
-                uint32_t pos = atomicAdd((uint32_t *)wp.ntop, (uint32_t)cnt);
-                const uint32_t tag = e.x & ~1u;
-                if (h0) wp.nstack[pos++] = make_uint2(tag | (r0 < 0 ? 1u : 0u), (uint32_t)(r0 < 0 ? ~r0 : r0));
-                if (h1) wp.nstack[pos++] = make_uint2(tag | (r1 < 0 ? 1u : 0u), (uint32_t)(r1 < 0 ? ~r1 : r1));
-                if (h2) wp.nstack[pos++] = make_uint2(tag | (r2 < 0 ? 1u : 0u), (uint32_t)(r2 < 0 ? ~r2 : r2));
-                if (h3) wp.nstack[pos] = make_uint2(tag | (r3 < 0 ? 1u : 0u), (uint32_t)(r3 < 0 ? ~r3 : r3));
-                net += cnt;
-            }
-        } else { // leaf range: 1..4 consecutive triangles of the sorted SoA
+        const Node4 *n = (set ? W.set[1].nodes4 : W.set[0].nodes4) + e.y;
+        float4 q0 = __ldg(&n->q[0]), q1 = __ldg(&n->q[1]), q2 = __ldg(&n->q[2]), q3 = __ldg(&n->q[3]);
+        float4 q4 = __ldg(&n->q[4]), q5 = __ldg(&n->q[5]), q6 = __ldg(&n->q[6]), q7 = __ldg(&n->q[7]);
+        const int r0 = __float_as_int(q0.w), r1 = __float_as_int(q1.w), r2 = __float_as_int(q2.w), r3 = __float_as_int(q3.w);
+        // empty children have inverted boxes: they fail the overlap test by themselves
+        bool h0 = !box_disjoint(xyz(q0), xyz(q1), qlo, qhi), h1 = !box_disjoint(xyz(q2), xyz(q3), qlo, qhi);
+        bool h2 = !box_disjoint(xyz(q4), xyz(q5), qlo, qhi), h3 = !box_disjoint(xyz(q6), xyz(q7), qlo, qhi);
+        if (COUNT) ctr.nodes += 2 + (r2 != CQ_REF_EMPTY) + (r3 != CQ_REF_EMPTY);
+        int cnt = (h0 ? 1 : 0) + (h1 ? 1 : 0) + (h2 ? 1 : 0) + (h3 ? 1 : 0);
+        if (cnt) {
+            uint32_t pos = atomicAdd((uint32_t *)wp.ntop, (uint32_t)cnt);
+            const uint32_t tag = e.x & ~1u;
+            if (h0) wp.nstack[pos++] = make_uint2(tag | (r0 < 0 ? 1u : 0u), (uint32_t)(r0 < 0 ? ~r0 : r0));
+            if (h1) wp.nstack[pos++] = make_uint2(tag | (r1 < 0 ? 1u : 0u), (uint32_t)(r1 < 0 ? ~r1 : r1));
+            if (h2) wp.nstack[pos++] = make_uint2(tag | (r2 < 0 ? 1u : 0u), (uint32_t)(r2 < 0 ? ~r2 : r2));
+            if (h3) wp.nstack[pos] = make_uint2(tag | (r3 < 0 ? 1u : 0u), (uint32_t)(r3 < 0 ? ~r3 : r3));
+            net += cnt;
+        }
+        if (net) atomicAdd(&s.pending, net);
+    }
+    // Leaf ranges (1..4 consecutive triangles of the sorted SoA).  Big worlds: expanded to ONE TRIANGLE PER LANE through
+    // a staging list, so that the triangle fetches of the whole round are in flight together instead of a few lanes
+    // looping over their ranges while the others wait (C4: +18%, terrain move-and-slide: +10%).
+    if (!STAGED) { // tiny worlds (everything L1 resident): the plain per-lane loop has less overhead and less code
+        if (isLeaf) {
+            const int owner = e.x >> 2, set = (e.x >> 1) & 1;
+            QShared &s = wp.qs[owner];
+            const f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
             const int start = (int)(e.y >> 2), count = (int)(e.y & 3u) + 1;
             const uint32_t mask = s.mask;
             const float4 *p0 = set ? W.set[1].tv0 : W.set[0].tv0;
             const float4 *p1 = set ? W.set[1].tv1 : W.set[0].tv1;
             const float4 *p2 = set ? W.set[1].tv2 : W.set[0].tv2;
+            int net = -1;
 #pragma unroll 1
             for (int i = 0; i < count; i++) {
                 const int slot = start + i;
@@ -240,8 +253,43 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
                 wp.ring[pos % CQ_QCAP] = ((uint32_t)owner << 27) | ((uint32_t)set << 26) | (uint32_t)slot;
                 net++;
             }
+            if (net) atomicAdd(&s.pending, net);
         }
-        if (net) atomicAdd(&s.pending, net);
+        __syncwarp();
+        return;
+    }
+    const uint32_t leafMask = __ballot_sync(0xffffffffu, isLeaf);
+    const int total = __popc(leafMask) * 4; // four staging slots per leaf range, unused ones marked empty
+    if (total) {
+        if (isLeaf) {
+            const uint32_t owner = e.x >> 2, set = (e.x >> 1) & 1u;
+            const uint32_t item = (owner << 27) | (set << 26) | (e.y >> 2);
+            const uint32_t count = (e.y & 3u) + 1u;
+            uint32_t *slot4 = wp.stage + 4 * __popc(leafMask & ((1u << lane) - 1u));
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) slot4[i] = i < count ? item + i : 0xffffffffu;
+            atomicAdd(&wp.qs[owner].pending, -1); // this entry is consumed
+        }
+        __syncwarp();
+        for (int t = lane; t < total; t += 32) {
+            const uint32_t item = wp.stage[t];
+            if (item == 0xffffffffu) continue;
+            const int owner = item >> 27, set = (item >> 26) & 1, slot = item & 0x3ffffffu;
+            QShared &s = wp.qs[owner];
+            const float4 *p0 = set ? W.set[1].tv0 : W.set[0].tv0;
+            const float4 *p1 = set ? W.set[1].tv1 : W.set[0].tv1;
+            const float4 *p2 = set ? W.set[1].tv2 : W.set[0].tv2;
+            float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
+            if ((__float_as_uint(a.w) & s.mask) == 0u) continue; // layer mask, CollisionQuery.swift:1057
+            const f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
+            f3 v0 = xyz(a), v1 = xyz(b), v2 = xyz(c);
+            f3 tlo = vmin(v0, vmin(v1, v2)), thi = vmax(v0, vmax(v1, v2));
+            if (box_disjoint(tlo, thi, qlo, qhi)) continue; // :1060-1065
+            if (COUNT) ctr.cands++;
+            uint32_t pos = atomicAdd((uint32_t *)wp.tail, 1u);
+            wp.ring[pos % CQ_QCAP] = item;
+            atomicAdd(&s.pending, 1);
+        }
     }
     __syncwarp();
 }
@@ -423,7 +471,7 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
 // `ownersPerWarp` (1..32): how many lanes of each warp take the owner role.  Small batches of heavy units
 // use fewer owners per warp so that every owner still processes several units (dynamic fetch then balances
 // the warps against each other) while all 32 lanes keep executing pairs.
-template <bool COUNT, class Advance, class OvlCommit>
+template <bool COUNT, bool STAGED, class Advance, class OvlCommit>
 __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int ownersPerWarp, Counters &ctr,
                                          Advance advance, OvlCommit ovl) {
     QShared &mine = wp.qs[lane];
@@ -447,7 +495,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
             __syncwarp();
             // cooperative walk: rounds until the ring holds ~3 trips of work (or the stack is empty)
             while (*wp.ntop != 0u && *wp.tail - *wp.head < 96u && *wp.tail - *wp.head + 128u <= (uint32_t)CQ_QCAP)
-                pool_walk_round<COUNT>(W, wp, lane, ctr);
+                pool_walk_round<COUNT, STAGED>(W, wp, lane, ctr);
         }
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
         pool_take_jobs(W, wp, job, lane);

@@ -146,8 +146,11 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 // walks the LBVH for it and pushes its candidate triangles into the warp's ring; all 32 lanes execute
 // the (sweep, triangle) pairs, one distance evaluation per trip.
 #define CAST_WARPS (Q_THREADS / 32)
-template <bool COUNT>
-__global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
+#ifndef CAST_MIN_BLOCKS
+#define CAST_MIN_BLOCKS 5 /* 96 registers: +9% on C4 against 4 CTAs/SM (107 registers); 6 CTAs/SM (80) gains nothing */
+#endif
+template <bool COUNT, bool STAGED>
+__global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
                                                                int mode, cq_cast_hit *__restrict__ out, int ownersPerWarp,
                                                                uint2 *nodeScratch, int *workCounter,
                                                                const uint32_t *__restrict__ order,
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_cast(WorldView W, cons
     pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS);
     Counters ctr = {0, 0, 0, 0};
     int cur = -1;
-    pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         if (cur >= 0) { // write the finished hit
             cq_cast_hit h;
             if (mine.rTri >= 0) {
@@ -260,7 +263,7 @@ __device__ __forceinline__ void overlap_record(const WorldView &W, uint32_t enc,
     write_overlap(h, r);
 }
 
-template <bool COUNT, bool ALL>
+template <bool COUNT, bool ALL, bool STAGED>
 __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView W, const cq_capsule *__restrict__ qs, int n,
                                                                        int maxHits, cq_overlap_hit *__restrict__ out,
                                                                        int32_t *__restrict__ counts,
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
     int cur = -1;
     f3 curFrom = {0, 0, 0};
     float curR = 0.0f, curHH = 0.0f;
-    pool_run<COUNT>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         if (cur >= 0) { // emit the finished query
             const int stride = ALL ? maxHits : 1;
             for (int k = 0; k < stride; k++) {
@@ -343,14 +346,18 @@ int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, 
 int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
     int *blocksPerSm = w->occ[CQ_OCC_SLOT]; int &numSms = w->numSms;
-    const int ci = w->counting ? 1 : 0;
+    const int ci = (w->counting ? 1 : 0) + 2 * (w->view.stagedLeaves ? 1 : 0);
+    using Kernel = void (*)(WorldView, const cq_capsule_cast *, int, int, cq_cast_hit *, int, uint2 *, int *, const uint32_t *,
+                            unsigned long long *);
+    static const Kernel kernels[4] = {k_capsule_cast<false, false>, k_capsule_cast<true, false>, k_capsule_cast<false, true>,
+                                      k_capsule_cast<true, true>};
+    const Kernel kernel = kernels[ci];
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;
         CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
         numSms = prop.multiProcessorCount;
         int b = 0;
-        if (ci) CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_cast<true>, Q_THREADS, 0));
-        else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_cast<false>, Q_THREADS, 0));
+        CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, Q_THREADS, 0));
         blocksPerSm[ci] = b > 0 ? b : 1;
     }
     int blocks = std::min(cdiv(n, 4), numSms * blocksPerSm[ci]); // one resident wave of persistent lanes
@@ -360,9 +367,7 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
     uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS);
     if (!ns) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_q, sizeof(cq_capsule_cast), false, n, st);
-    if (w->counting)
-        k_capsule_cast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, order, w->dCounters);
-    else k_capsule_cast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, order, w->dCounters);
+    kernel<<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, order, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_cast");
 }
@@ -373,13 +378,20 @@ template <bool ALL>
 static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,
                                uint8_t *d_overflow, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
-    int &blocksPerSm = w->occ[CQ_OCC_SLOT][0]; int &numSms = w->numSms;
+    int &numSms = w->numSms;
+    const int ci = (w->counting ? 1 : 0) + 2 * (w->view.stagedLeaves ? 1 : 0);
+    int &blocksPerSm = w->occ[CQ_OCC_SLOT][ci];
+    using Kernel = void (*)(WorldView, const cq_capsule *, int, int, cq_overlap_hit *, int32_t *, uint8_t *, int, uint2 *, int *,
+                            unsigned long long *);
+    static const Kernel kernels[4] = {k_capsule_overlap_pool<false, ALL, false>, k_capsule_overlap_pool<true, ALL, false>,
+                                      k_capsule_overlap_pool<false, ALL, true>, k_capsule_overlap_pool<true, ALL, true>};
+    const Kernel kernel = kernels[ci];
     if (!blocksPerSm) {
         cudaDeviceProp prop;
         CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
         numSms = prop.multiProcessorCount;
         int b = 0;
-        CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_capsule_overlap_pool<false, ALL>, Q_THREADS, 0));
+        CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, Q_THREADS, 0));
         blocksPerSm = b > 0 ? b : 1;
     }
     int blocks = std::min(cdiv(n, 4), numSms * blocksPerSm);
@@ -388,12 +400,7 @@ static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int ma
     if (!work) return CQ_ERR_CUDA;
     uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS);
     if (!ns) return CQ_ERR_CUDA;
-    if (w->counting)
-        k_capsule_overlap_pool<true, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
-                                                                       opw, ns, work, w->dCounters);
-    else
-        k_capsule_overlap_pool<false, ALL><<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow,
-                                                                        opw, ns, work, w->dCounters);
+    kernel<<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow, opw, ns, work, w->dCounters);
     w->launches++;
     return check_cuda(cudaGetLastError(), "k_capsule_overlap_pool");
 }

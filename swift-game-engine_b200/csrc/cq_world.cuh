@@ -53,6 +53,8 @@ struct WorldView {
     SetView set[2];
     const float4 *materials; // per part: (muS, muK, flattenGround, -)
     int nParts;
+    int stagedLeaves; // which kernel variant the launchers pick: 1 = walk expands leaf ranges one triangle per lane
+                      // (worlds that do not fit L1); the tiny-world variant keeps the shorter per-lane loop
 };
 
 // Snapshot of every agent of a move-and-slide batch, taken before any character of the step moves
