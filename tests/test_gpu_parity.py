@@ -530,6 +530,26 @@ def test_agent_separation_sequential_semantics(cq, orc, scenes):
     g.agent_separation(one, p)
     assert one.tobytes() == sg[:1].tobytes()
     g.agent_separation(sg[:0].copy(), p)
+    # a light agent shoved across several grid cells by a row of immovable lower-indexed agents BEFORE its own turn:
+    # the schedule's drift assumption (R = 1 cell) fails, the sweep must be detected, restored and rerun with a wider
+    # safety radius — and still equal the sequential loop
+    fv, fi = scenes.plane_mesh(80.0)
+    flat = [scenes.part(fv, fi, scenes.trs_model((0, -3, 0)), entity_id=0)]
+    g2, o2 = cq.CollisionQuery(flat), orc.OracleWorld(flat)
+    fy = -3.0 + 0.9 + 0.05
+    rows = []
+    for r in range(40):  # 40 independent rows, each: 8 immovable pushers then the light agent, then a bystander
+        zr = 3.0 * r - 60.0
+        rows += [[-0.3 + 0.4 * k, fy, zr] for k in range(8)] + [[0.0, fy, zr], [3.38, fy, zr + 0.3]]
+    dmass = np.tile(np.float32([0.0] * 8 + [1.0, 1.0]), 40)
+    for uq in (False, True):
+        a, b = cq.init_states(rows), orc.init_states(rows)
+        g2.agent_separation(a, p, mass_weight=dmass, iterations=2, use_query=uq)
+        o2.agent_separation(b, p, mass_weight=dmass, iterations=2, use_query=uq, order=orc.ORDER_CANONICAL)
+        assert a.tobytes() == b.tobytes(), uq
+        assert (a["position"][8::10, 0] > 2.0).all()  # every light agent was pushed more than two cells
+    g2.close()
+    o2.close()
     # agents sorted along x (index correlates with space): the conflict DAG degenerates towards a chain, still exact
     order = np.argsort(sg["position"][:, 0], kind="stable")
     a, b = np.ascontiguousarray(sg[order]), np.ascontiguousarray(so[order])
