@@ -85,7 +85,11 @@ static int run_batch(cq_world *w, const In *in, size_t inStride, Out *out, size_
                      bool inPlace = false, float *computeBoundHint = nullptr, bool singleChunk = false) {
     if (n <= 0) return CQ_OK;
     CQ_CUDA(cudaSetDevice(w->device));
-    const int CH = 1 << 17;
+    static const int CH = [] { // units per chunk of the copy/compute pipeline (CQ_CHUNK overrides, for tuning)
+        const char *e = getenv("CQ_CHUNK");
+        int v = e ? atoi(e) : 0;
+        return v >= 1024 ? v : (1 << 17);
+    }();
     int nChunks = (n + CH - 1) / CH;
     if (computeBoundHint && *computeBoundHint > 3.0f && nChunks > 2) nChunks = 2;
     if (nChunks > CQ_PIPE_EVENTS) nChunks = CQ_PIPE_EVENTS;
