@@ -195,12 +195,29 @@ __global__ void k_centroid_bounds(const float4 *__restrict__ world, const uint32
     }
 }
 
-__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) { // 10 bits -> every third bit
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
+// 30-bit Morton code with the bits handed out longest-cell-axis first: every bit halves the currently longest side of
+// the cell, so cells stay as cubic as the bounds allow.  For a cubic bound this IS the classic x,y,z interleave; for a
+// flat world (a 4.5 km x 50 m x 4.5 km terrain) the classic code spends 10 bits on the 50 m and resolves only 4.4 m in
+// the plane, so ~10 terrain triangles share a code and the leaves built from them overlap; this one resolves ~0.5 m.
+__device__ __forceinline__ uint32_t morton30_adaptive(f3 p, f3 lo, f3 ext) {
+    float ux = ext.x > 0.0f ? fminf(fmaxf((p.x - lo.x) / ext.x, 0.0f), 0.99999994f) : 0.0f;
+    float uy = ext.y > 0.0f ? fminf(fmaxf((p.y - lo.y) / ext.y, 0.0f), 0.99999994f) : 0.0f;
+    float uz = ext.z > 0.0f ? fminf(fmaxf((p.z - lo.z) / ext.z, 0.0f), 0.99999994f) : 0.0f;
+    float cx = ext.x, cy = ext.y, cz = ext.z;
+    uint32_t key = 0;
+#pragma unroll 1
+    for (int b = 0; b < 30; b++) {
+        const int axis = (cx >= cy && cx >= cz) ? 0 : (cy >= cz ? 1 : 2); // ties: x, y, z — the classic order
+        float u = axis == 0 ? ux : (axis == 1 ? uy : uz);
+        u *= 2.0f;
+        const uint32_t bit = u >= 1.0f ? 1u : 0u;
+        u -= (float)bit;
+        key = (key << 1) | bit;
+        if (axis == 0) ux = u, cx *= 0.5f;
+        else if (axis == 1) uy = u, cy *= 0.5f;
+        else uz = u, cz *= 0.5f;
+    }
+    return key;
 }
 
 __global__ void k_morton(const float4 *__restrict__ world, const uint32_t *__restrict__ idx, int nTris,
@@ -210,12 +227,7 @@ __global__ void k_morton(const float4 *__restrict__ world, const uint32_t *__res
     f3 lo = {ordered_to_float(bounds[0]), ordered_to_float(bounds[1]), ordered_to_float(bounds[2])};
     f3 hi = {ordered_to_float(bounds[3]), ordered_to_float(bounds[4]), ordered_to_float(bounds[5])};
     f3 c = tri_centroid(world, idx, t);
-    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
-    float sx = ex > 0.0f ? 1024.0f / ex : 0.0f, sy = ey > 0.0f ? 1024.0f / ey : 0.0f, sz = ez > 0.0f ? 1024.0f / ez : 0.0f;
-    uint32_t qx = min(1023u, (uint32_t)fmaxf((c.x - lo.x) * sx, 0.0f));
-    uint32_t qy = min(1023u, (uint32_t)fmaxf((c.y - lo.y) * sy, 0.0f));
-    uint32_t qz = min(1023u, (uint32_t)fmaxf((c.z - lo.z) * sz, 0.0f));
-    keys[t] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz); // 30-bit Morton
+    keys[t] = morton30_adaptive(c, lo, hi - lo);
     vals[t] = (uint32_t)t;
 }
 
@@ -865,12 +877,8 @@ __global__ void k_order_keys(const unsigned char *__restrict__ base, size_t stri
         x = f[0], y = f[1], z = f[2];
     }
     SetHeader h = *hdr;
-    float ex = h.hi[0] - h.lo[0], ey = h.hi[1] - h.lo[1], ez = h.hi[2] - h.lo[2];
-    float sx = ex > 0.0f ? 1024.0f / ex : 0.0f, sy = ey > 0.0f ? 1024.0f / ey : 0.0f, sz = ez > 0.0f ? 1024.0f / ez : 0.0f;
-    uint32_t qx = min(1023u, (uint32_t)fmaxf((x - h.lo[0]) * sx, 0.0f));
-    uint32_t qy = min(1023u, (uint32_t)fmaxf((y - h.lo[1]) * sy, 0.0f));
-    uint32_t qz = min(1023u, (uint32_t)fmaxf((z - h.lo[2]) * sz, 0.0f));
-    keys[i] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz);
+    const f3 lo = {h.lo[0], h.lo[1], h.lo[2]}, hi = {h.hi[0], h.hi[1], h.hi[2]};
+    keys[i] = morton30_adaptive(mk3(x, y, z), lo, hi - lo);
     vals[i] = (uint32_t)i;
 }
 
