@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     c.wait = W_NONE;
     c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT, STAGED>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED, 16>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return mas_advance<COUNT, AGENTS>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);

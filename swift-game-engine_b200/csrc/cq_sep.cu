@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_turns(WorldView W, const
     c.agent = -1;
     c.wait = SW_NONE;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT, true>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, true, 8>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return sep_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_post(WorldView W, const 
     c.agent = -1;
     c.wait = PW_NONE;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT, true>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, true, 8>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return post_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);
