@@ -558,3 +558,32 @@ def test_agent_separation_sequential_semantics(cq, orc, scenes):
     assert a.tobytes() == b.tobytes()
     g.close()
     o.close()
+
+
+@pytest.mark.gpu
+def test_full_size_c3_sharding_invariance_and_sampled_parity(cq, orc, scenes):
+    """BASELINE config C3 at its full size (1,048,576 characters, hulls scene): characters are independent units, so
+    (1) stepping the whole batch equals stepping its two halves separately (what multi-GPU sharding relies on), and
+    (2) any sample of it must equal the oracle stepping just that sample.  Two steps, every byte compared."""
+    parts = scenes.mirror_scene(use_hulls=True)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    n = 1 << 20
+    pos, vel = scenes.gen_c3_characters(n, seed=0xC0111DE3)
+    p = cq.default_params()
+    whole = cq.init_states(pos, vel)
+    halves = whole.copy()
+    rng = np.random.default_rng(17)
+    pick = np.sort(rng.choice(n, 20000, replace=False))
+    sample = np.ascontiguousarray(orc.init_states(pos[pick], vel[pick]))
+    for step in range(2):
+        g.move_and_slide(whole, p)
+        a, b = np.ascontiguousarray(halves[: n // 2]), np.ascontiguousarray(halves[n // 2:])
+        g.move_and_slide(a, p)
+        g.move_and_slide(b, p)
+        halves = np.concatenate([a, b])
+        assert whole.tobytes() == halves.tobytes(), step
+        o.move_and_slide(sample, p, order=orc.ORDER_CANONICAL, n_threads=8)
+        assert whole[pick].tobytes() == sample.tobytes(), step
+    assert whole["grounded"].mean() > 0.99
+    g.close()
+    o.close()

@@ -354,3 +354,36 @@ def test_agent_separation_known_answers(orc, scenes):
     w2.agent_separation(s, p, iterations=1, use_query=True, order=orc.ORDER_REFERENCE)
     assert s["position"][1][0] == pytest.approx(2.6, abs=1e-6) and s["position"][0][0] == pytest.approx(-0.6, abs=1e-5)
     assert s["grounded"].tolist() == [1, 1]
+
+
+def test_agent_layer_size_independent_properties(orc, scenes):
+    """Properties that hold at any crowd size (used at full bench sizes as well): (1) a capsule-capsule sweep that hits
+    at toi keeps that toi when the mover's path is extended beyond the contact (same direction, other static);
+    (2) without world casts and with equal masses every separation correction is equal and opposite, so the crowd's
+    centroid in XZ does not move, heights never change, and no pair ends up closer than it started beyond float noise."""
+    rng = np.random.default_rng(9)
+    n = 20000
+    dims = np.tile(np.float32([0.4, 0.5, 0.4, 0.5]), (n, 1))
+    frm = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    other = (frm + rng.standard_normal((n, 3)) * 2).astype(np.float32)
+    delta = ((other - frm) * rng.uniform(0.5, 1.2, (n, 1))).astype(np.float32)
+    zero = np.zeros((n, 3), np.float32)
+    h1, t1, _ = orc.capsule_capsule_sweep_batch(frm, delta, other, zero, dims)
+    h2, t2, _ = orc.capsule_capsule_sweep_batch(frm, delta * np.float32(2), other, zero, dims)
+    both = (h1 == 1) & (t1 > 1e-3)
+    assert both.sum() > n // 4 and (h2[both] == 1).all()
+    assert np.allclose(t1[both], t2[both], rtol=2e-4, atol=2e-5)
+    w = orc.OracleWorld([big_floor(scenes, y=-3.0, eid=0)])
+    p = orc.default_params()
+    p["radius"], p["half_height"], p["skin_width"] = 0.4, 0.5, 0.08
+    m = 4000
+    half = np.sqrt(m * np.pi * 0.16 / 0.5) / 2
+    pos = np.stack([rng.uniform(-half, half, m), np.full(m, -3.0 + 0.95), rng.uniform(-half, half, m)], axis=1).astype(np.float32)
+    s = orc.init_states(pos)
+    pairs = w.agent_separation(s, p, iterations=2, use_query=False)
+    assert pairs > m
+    after = s["position"]
+    assert np.allclose(after[:, [0, 2]].mean(0), pos[:, [0, 2]].astype(np.float64).mean(0), atol=1e-4)
+    assert np.array_equal(after[:, 1], pos[:, 1].astype(np.float64))
+    moved = np.linalg.norm(after[:, [0, 2]] - pos[:, [0, 2]], axis=1)
+    assert 0 < moved.max() < 2.0 and (moved > 0).mean() > 0.5
