@@ -1,0 +1,216 @@
+"""A SECOND, independent restatement of the reference's narrow phase and conservative-advancement sweep
+(Game/CollisionQuery.swift:1285-1573), written straight from the Swift in scalar Python with numpy.float32
+arithmetic (every operation rounded to IEEE single, left-to-right like the Swift expressions).
+
+TEST INFRASTRUCTURE ONLY.  The reference cannot be compiled here (no swiftc), so the C++ oracle cannot be pinned by
+reference outputs; this file reduces the remaining risk — a transcription slip in the oracle — by checking the
+oracle bit-for-bit against a separately written transliteration (tests/test_oracle_known_answers.py).  It shares
+only the documented `simd` shim with the oracle: dot = (x*x' + y*y') + z*z', normalize = v * (1/sqrt),
+Swift's generic min/max.
+"""
+import numpy as np
+
+F = np.float32
+ZERO, ONE, HALF = F(0), F(1), F(0.5)
+FLT_MAX = np.finfo(np.float32).max
+
+
+def smax(x, y):  # Swift max(x, y): y >= x ? y : x
+    return y if y >= x else x
+
+
+def smin(x, y):  # Swift min(x, y): y < x ? y : x
+    return y if y < x else x
+
+
+def v(x, y, z):
+    return (F(x), F(y), F(z))
+
+
+def add(a, b):
+    return (a[0] + b[0], a[1] + b[1], a[2] + b[2])
+
+
+def sub(a, b):
+    return (a[0] - b[0], a[1] - b[1], a[2] - b[2])
+
+
+def mul(a, s):
+    return (a[0] * s, a[1] * s, a[2] * s)
+
+
+def neg(a):
+    return (-a[0], -a[1], -a[2])
+
+
+def dot(a, b):
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+
+def cross(a, b):
+    return (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])
+
+
+def length_squared(a):
+    return dot(a, a)
+
+
+def normalize(a):
+    with np.errstate(all="ignore"):
+        return mul(a, ONE / np.sqrt(dot(a, a)))
+
+
+def clamp(x, lo, hi):  # :1571-1573  min(max(v, minV), maxV)
+    return smin(smax(x, lo), hi)
+
+
+def closest_point_on_triangle(p, a, b, c):  # :1464-1517
+    ab, ac, ap = sub(b, a), sub(c, a), sub(p, a)
+    d1, d2 = dot(ab, ap), dot(ac, ap)
+    if d1 <= ZERO and d2 <= ZERO:
+        return length_squared(sub(p, a)), a
+    bp = sub(p, b)
+    d3, d4 = dot(ab, bp), dot(ac, bp)
+    if d3 >= ZERO and d4 <= d3:
+        return length_squared(sub(p, b)), b
+    vc = d1 * d4 - d3 * d2
+    if vc <= ZERO and d1 >= ZERO and d3 <= ZERO:
+        vv = d1 / (d1 - d3)
+        point = add(a, mul(ab, vv))
+        return length_squared(sub(p, point)), point
+    cp = sub(p, c)
+    d5, d6 = dot(ab, cp), dot(ac, cp)
+    if d6 >= ZERO and d5 <= d6:
+        return length_squared(sub(p, c)), c
+    vb = d5 * d2 - d1 * d6
+    if vb <= ZERO and d2 >= ZERO and d6 <= ZERO:
+        w = d2 / (d2 - d6)
+        point = add(a, mul(ac, w))
+        return length_squared(sub(p, point)), point
+    va = d3 * d6 - d5 * d4
+    if va <= ZERO and (d4 - d3) >= ZERO and (d5 - d6) >= ZERO:
+        w = (d4 - d3) / ((d4 - d3) + (d5 - d6))
+        point = add(b, mul(sub(c, b), w))
+        return length_squared(sub(p, point)), point
+    denom = ONE / (va + vb + vc)
+    vv, w = vb * denom, vc * denom
+    point = add(add(a, mul(ab, vv)), mul(ac, w))
+    return length_squared(sub(p, point)), point
+
+
+def segment_segment_distance_sq(p1, q1, p2, q2):  # :1519-1569
+    d1, d2, r = sub(q1, p1), sub(q2, p2), sub(p1, p2)
+    a, e, f = dot(d1, d1), dot(d2, d2), dot(d2, r)
+    eps = F(1e-6)
+    if a <= eps and e <= eps:
+        return length_squared(sub(p1, p2)), p1, p2
+    if a <= eps:
+        t = clamp(f / e, ZERO, ONE)
+        c2 = add(p2, mul(d2, t))
+        return length_squared(sub(p1, c2)), p1, c2
+    c = dot(d1, r)
+    if e <= eps:
+        s = clamp(-c / a, ZERO, ONE)
+        c1 = add(p1, mul(d1, s))
+        return length_squared(sub(c1, p2)), c1, p2
+    b = dot(d1, d2)
+    denom = a * e - b * b
+    s = clamp((b * f - c * e) / denom, ZERO, ONE) if denom != ZERO else ZERO
+    t_nom = b * s + f
+    if t_nom < ZERO:
+        t = ZERO
+        s = clamp(-c / a, ZERO, ONE)
+    elif t_nom > e:
+        t = ONE
+        s = clamp((b - c) / a, ZERO, ONE)
+    else:
+        t = t_nom / e
+    c1, c2 = add(p1, mul(d1, s)), add(p2, mul(d2, t))
+    return length_squared(sub(c1, c2)), c1, c2
+
+
+def segment_triangle_intersect(a, b, v0, v1, v2):  # :1440-1462
+    d = sub(b, a)
+    e1, e2 = sub(v1, v0), sub(v2, v0)
+    pvec = cross(d, e2)
+    det = dot(e1, pvec)
+    if abs(det) < F(1e-6):
+        return None
+    inv_det = ONE / det
+    tvec = sub(a, v0)
+    u = dot(tvec, pvec) * inv_det
+    if u < ZERO or u > ONE:
+        return None
+    qvec = cross(tvec, e1)
+    vv = dot(d, qvec) * inv_det
+    if vv < ZERO or (u + vv) > ONE:
+        return None
+    t = dot(e2, qvec) * inv_det
+    if t < ZERO or t > ONE:
+        return None
+    return add(a, mul(d, t))
+
+
+def segment_triangle_distance(center, half_height, v0, v1, v2):  # :1396-1438
+    up = v(0, 1, 0)
+    a, b = add(center, mul(up, half_height)), sub(center, mul(up, half_height))
+    hit = segment_triangle_intersect(a, b, v0, v1, v2)
+    if hit is not None:
+        return ZERO, hit, hit
+    best, best_seg, best_tri = FLT_MAX, a, v0
+    d0, p0 = closest_point_on_triangle(a, v0, v1, v2)
+    if d0 < best:
+        best, best_seg, best_tri = d0, a, p0
+    d1, p1 = closest_point_on_triangle(b, v0, v1, v2)
+    if d1 < best:
+        best, best_seg, best_tri = d1, b, p1
+    for e0, e1 in ((v0, v1), (v1, v2), (v2, v0)):
+        d, s, t = segment_segment_distance_sq(a, b, e0, e1)
+        if d < best:
+            best, best_seg, best_tri = d, s, t
+    return np.sqrt(smax(best, ZERO)), best_seg, best_tri
+
+
+def refine_toi(frm, direction, radius, half_height, v0, v1, v2, t0, t1, max_distance):  # :1361-1394
+    c0, c1 = smax(ZERO, smin(t0, max_distance)), smax(ZERO, smin(t1, max_distance))
+    lo, hi = smin(c0, c1), smax(c0, c1)
+    if hi - lo < F(1e-5):
+        return hi
+    for _ in range(10):
+        mid = HALF * (lo + hi)
+        dist, _, _ = segment_triangle_distance(add(frm, mul(direction, mid)), half_height, v0, v1, v2)
+        if dist <= radius:
+            hi = mid
+        else:
+            lo = mid
+    return hi
+
+
+def sweep_capsule_triangle(frm, direction, max_distance, radius, half_height, v0, v1, v2):  # :1285-1359
+    """Returns None or (toi, position, normal, triangleNormal, iterations)."""
+    min_advance = smax(radius * F(0.02), F(1e-4))
+    max_iter = min(256, int(np.ceil(max_distance / min_advance)) + 1)
+    contact_eps = F(1e-5)
+    tri_normal = normalize(cross(sub(v1, v0), sub(v2, v0)))
+    t, last_safe = ZERO, ZERO
+    iterations = 0
+    for _ in range(max_iter):
+        iterations += 1
+        if t > max_distance:
+            return None
+        dist, _, _ = segment_triangle_distance(add(frm, mul(direction, t)), half_height, v0, v1, v2)
+        if dist <= radius + contact_eps:
+            t_hit = refine_toi(frm, direction, radius, half_height, v0, v1, v2, last_safe, t, max_distance)
+            hit_dist, hit_seg, hit_tri = segment_triangle_distance(add(frm, mul(direction, t_hit)), half_height, v0, v1, v2)
+            if hit_dist < F(1e-6):
+                n = neg(tri_normal) if dot(tri_normal, direction) > ZERO else tri_normal
+            else:
+                n = normalize(sub(hit_seg, hit_tri))
+            tri_n = tri_normal
+            if dot(tri_n, n) < ZERO:
+                tri_n = neg(tri_n)
+            return t_hit, hit_tri, n, tri_n, iterations
+        last_safe = t
+        advance = smax(dist - radius, min_advance)
+        t = t + (min_advance if advance <= ZERO else advance)
+    return None

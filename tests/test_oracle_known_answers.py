@@ -387,3 +387,69 @@ def test_agent_layer_size_independent_properties(orc, scenes):
     assert np.array_equal(after[:, 1], pos[:, 1].astype(np.float64))
     moved = np.linalg.norm(after[:, [0, 2]] - pos[:, [0, 2]], axis=1)
     assert 0 < moved.max() < 2.0 and (moved > 0).mean() > 0.5
+
+
+def test_oracle_matches_an_independent_transliteration(orc, scenes):
+    """The C++ oracle against tests/independent_narrow_phase.py — a second restatement written separately, straight
+    from CollisionQuery.swift:1285-1573, in scalar float32 Python.  Bit-for-bit: segmentTriangleDistance on random /
+    touching / piercing / degenerate-edge cases, and whole conservative-advancement sweeps (toi, contact point, both
+    normals) through the oracle's public capsuleCast against one triangle each."""
+    import independent_narrow_phase as ind
+    F = np.float32
+    rng = np.random.default_rng(2024)
+    n = 60000
+    scale = 10.0 ** rng.uniform(-1.5, 1.0, (n, 1))
+    tris = (rng.standard_normal((n, 9)) * scale).astype(np.float32)
+    wts = rng.dirichlet((1, 1, 1), n)
+    on_tri = (tris.reshape(n, 3, 3) * wts[:, :, None]).sum(1)
+    kind = rng.integers(0, 4, n)
+    centers = on_tri + rng.standard_normal((n, 3)) * scale * np.where(kind == 0, 3.0, np.where(kind == 1, 0.3, 1e-3))[:, None]
+    centers[kind == 3] = on_tri[kind == 3] + [0, 1.5, 0]
+    hh = rng.choice(np.float32([0.0, 1e-4, 0.5, 1.0]), n)
+    deg = rng.random(n) < 0.03  # an edge shorter than 1e-3: the e <= 1e-6 branches of the segment-segment test
+    tris[deg, 3:6] = tris[deg, 0:3] + (rng.standard_normal((deg.sum(), 3)) * 3e-4).astype(np.float32)
+    centers = centers.astype(np.float32)
+    od, oseg, otri = orc.segment_triangle_distance_batch(centers, hh, tris)
+    pierced = 0
+    for i in range(n):
+        t = tris[i]
+        d, s, q = ind.segment_triangle_distance(tuple(centers[i]), hh[i], tuple(t[0:3]), tuple(t[3:6]), tuple(t[6:9]))
+        assert F(d).tobytes() == od[i].tobytes(), i
+        assert np.float32(s).tobytes() == oseg[i].tobytes() and np.float32(q).tobytes() == otri[i].tobytes(), i
+        pierced += d == 0
+    assert 100 < pierced < n // 2
+    # sweeps: 6000 triangles 200 m apart in one world, one capsule cast aimed at (or past) each
+    m = 6000
+    base = np.stack([200.0 * np.arange(m), np.zeros(m), np.zeros(m)], axis=1)
+    tv = (rng.standard_normal((m, 3, 3)) * rng.uniform(0.5, 4.0, (m, 1, 1)) + base[:, None, :]).astype(np.float32)
+    parts = [scenes.part(tv.reshape(-1, 3), np.arange(3 * m, dtype=np.uint32), entity_id=0)]
+    w = orc.OracleWorld(parts)
+    assert w.counts(0)["triangles"] == m  # nothing filtered: triangle index == its position
+    q = np.zeros(m, scenes.CAST)
+    wts = rng.dirichlet((1, 1, 1), m)
+    target = (tv * wts[:, :, None]).sum(1) + rng.standard_normal((m, 3)) * 0.5
+    start = target + rng.standard_normal((m, 3)) * rng.uniform(1.5, 6.0, (m, 1))
+    q["from"] = start.astype(np.float32)
+    q["delta"] = ((target - start) * rng.uniform(0.6, 1.6, (m, 1))).astype(np.float32)
+    q["radius"] = rng.choice(np.float32([0.4, 1.5]), m)
+    q["half_height"] = rng.choice(np.float32([0.0, 0.5, 1.0]), m)
+    q["mask"] = 0xFFFFFFFF
+    ref = w.capsule_cast(q, 0, orc.ORDER_REFERENCE)
+    hits = 0
+    for i in range(m):
+        d = tuple(q["delta"][i])
+        length = np.sqrt(ind.dot(d, d))
+        direction = (d[0] / length, d[1] / length, d[2] / length)
+        got = ind.sweep_capsule_triangle(tuple(q["from"][i]), direction, length, q["radius"][i], q["half_height"][i],
+                                         tuple(tv[i, 0]), tuple(tv[i, 1]), tuple(tv[i, 2]))
+        if got is None:
+            assert ref["triangle_index"][i] == -1, i
+            continue
+        hits += 1
+        toi, pos, nrm, tri_n, _ = got
+        assert ref["triangle_index"][i] == i
+        assert F(toi).tobytes() == ref["toi"][i].tobytes(), i
+        assert np.float32(pos).tobytes() == ref["position"][i].tobytes(), i
+        assert np.float32(nrm).tobytes() == ref["normal"][i].tobytes(), i
+        assert np.float32(tri_n).tobytes() == ref["triangle_normal"][i].tobytes(), i
+    assert m // 4 < hits < m
