@@ -214,3 +214,114 @@ def sweep_capsule_triangle(frm, direction, max_distance, radius, half_height, v0
         advance = smax(dist - radius, min_advance)
         t = t + (min_advance if advance <= ZERO else advance)
     return None
+
+
+# ---------------------------------------------------------------- Game/Systems.swift:1417-1590 (agent CCD)
+def clamp_interval(start, end):  # :1417-1424
+    s, e = smax(start, ZERO), smin(end, ONE)
+    return None if e < s else (s, e)
+
+
+def interval_greater_equal(y0, vy, threshold):  # :1426-1436
+    if abs(vy) < F(1e-6):
+        return (ZERO, ONE) if y0 >= threshold else None
+    t = (threshold - y0) / vy
+    return clamp_interval(t, ONE) if vy > ZERO else clamp_interval(ZERO, t)
+
+
+def interval_less_equal(y0, vy, threshold):  # :1438-1448
+    if abs(vy) < F(1e-6):
+        return (ZERO, ONE) if y0 <= threshold else None
+    t = (threshold - y0) / vy
+    return clamp_interval(ZERO, t) if vy > ZERO else clamp_interval(t, ONE)
+
+
+def earliest_root(a, b, c, t_min, t_max):  # :1450-1472
+    eps = F(1e-6)
+    if abs(a) < eps:
+        if abs(b) < eps:
+            return t_min if c <= ZERO else None
+        t = -c / b
+        return t if (t >= t_min and t <= t_max) else None
+    disc = b * b - F(4) * a * c
+    if disc < ZERO:
+        return None
+    sqrt_d = np.sqrt(disc)
+    inv2a = ONE / (F(2) * a)
+    t0, t1 = (-b - sqrt_d) * inv2a, (-b + sqrt_d) * inv2a
+    s, e = smax(smin(t0, t1), t_min), smin(smax(t0, t1), t_max)
+    return s if e >= s else None
+
+
+def capsule_pair_separation_y(y_rel, h_sum):  # :1474-1482
+    if y_rel > h_sum:
+        return y_rel - h_sum
+    if y_rel < -h_sum:
+        return y_rel + h_sum
+    return ZERO
+
+
+def capsule_pair_hit_normal(rel, h_sum):  # :1484-1497
+    sep = (rel[0], capsule_pair_separation_y(rel[1], h_sum), rel[2])
+    len_sq = length_squared(sep)
+    if len_sq > F(1e-8):
+        d = np.sqrt(len_sq)
+        return (sep[0] / d, sep[1] / d, sep[2] / d)
+    lateral = (rel[0], ZERO, rel[2])
+    lat_sq = length_squared(lateral)
+    if lat_sq > F(1e-8):
+        d = np.sqrt(lat_sq)
+        return (lateral[0] / d, lateral[1] / d, lateral[2] / d)
+    return v(1, 0, 0)
+
+
+def capsule_pair_overlap(rel, r_sum, h_sum):  # :1499-1503
+    sep_y = capsule_pair_separation_y(rel[1], h_sum)
+    return rel[0] * rel[0] + rel[2] * rel[2] + sep_y * sep_y <= r_sum * r_sum
+
+
+def capsule_capsule_sweep(frm, delta, radius, half_height, other_pos, other_delta, other_radius, other_half_height):
+    """:1505-1590.  Returns None or (toi, normal)."""
+    rel_start, rel_delta = sub(frm, other_pos), sub(delta, other_delta)
+    r_sum, h_sum = radius + other_radius, half_height + other_half_height
+    rel_len, move_len = np.sqrt(dot(rel_delta, rel_delta)), np.sqrt(dot(delta, delta))
+    if rel_len < F(1e-6):
+        if capsule_pair_overlap(rel_start, r_sum, h_sum):
+            return ZERO, capsule_pair_hit_normal(rel_start, h_sum)
+        return None
+    y0, vy, vx, vz, r0x, r0z = rel_start[1], rel_delta[1], rel_delta[0], rel_delta[2], rel_start[0], rel_start[2]
+    best = None
+    upper = interval_greater_equal(y0, vy, h_sum)
+    if upper is not None:
+        a = vx * vx + vz * vz + vy * vy
+        b = F(2) * (r0x * vx + r0z * vz + (y0 - h_sum) * vy)
+        c = r0x * r0x + r0z * r0z + (y0 - h_sum) * (y0 - h_sum) - r_sum * r_sum
+        t = earliest_root(a, b, c, upper[0], upper[1])
+        if t is not None:
+            best = t
+    lower = interval_less_equal(y0, vy, -h_sum)
+    if lower is not None:
+        a = vx * vx + vz * vz + vy * vy
+        b = F(2) * (r0x * vx + r0z * vz + (y0 + h_sum) * vy)
+        c = r0x * r0x + r0z * r0z + (y0 + h_sum) * (y0 + h_sum) - r_sum * r_sum
+        t = earliest_root(a, b, c, lower[0], lower[1])
+        if t is not None and (best is None or t < best):
+            best = t
+    if abs(vy) < F(1e-6):
+        if abs(y0) <= h_sum:
+            a, b, c = vx * vx + vz * vz, F(2) * (r0x * vx + r0z * vz), r0x * r0x + r0z * r0z - r_sum * r_sum
+            t = earliest_root(a, b, c, ZERO, ONE)
+            if t is not None and (best is None or t < best):
+                best = t
+    else:
+        t1, t2 = (h_sum - y0) / vy, (-h_sum - y0) / vy
+        overlap = clamp_interval(smin(t1, t2), smax(t1, t2))
+        if overlap is not None:
+            a, b, c = vx * vx + vz * vz, F(2) * (r0x * vx + r0z * vz), r0x * r0x + r0z * r0z - r_sum * r_sum
+            t = earliest_root(a, b, c, overlap[0], overlap[1])
+            if t is not None and (best is None or t < best):
+                best = t
+    if best is None:
+        return None
+    rel_at_hit = add(rel_start, mul(rel_delta, best))
+    return best * move_len, capsule_pair_hit_normal(rel_at_hit, h_sum)

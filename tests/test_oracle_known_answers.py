@@ -453,3 +453,40 @@ def test_oracle_matches_an_independent_transliteration(orc, scenes):
         assert np.float32(nrm).tobytes() == ref["normal"][i].tobytes(), i
         assert np.float32(tri_n).tobytes() == ref["triangle_normal"][i].tobytes(), i
     assert m // 4 < hits < m
+
+
+def test_oracle_capsule_pair_sweep_matches_independent_transliteration(orc):
+    """capsuleCapsuleSweep (Systems.swift:1417-1590): the C++ oracle against the separately written Python version, bit for
+    bit, on approaching / receding / resting / stacked / vertical-only relative motion."""
+    import warnings
+    import independent_narrow_phase as ind
+    rng = np.random.default_rng(4242)
+    n = 40000
+    dims = np.stack([rng.choice(np.float32([0.3, 1.5]), n), rng.choice(np.float32([0.0, 0.6, 1.0]), n),
+                     rng.choice(np.float32([0.3, 1.5]), n), rng.choice(np.float32([0.0, 0.6, 1.0]), n)], axis=1).astype(np.float32)
+    frm = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+    other = (frm + rng.standard_normal((n, 3)) * 3).astype(np.float32)
+    delta = (rng.standard_normal((n, 3)) * 10.0 ** rng.uniform(-3, 0.7, (n, 1))).astype(np.float32)
+    odelta = (rng.standard_normal((n, 3)) * 10.0 ** rng.uniform(-3, 0.7, (n, 1))).astype(np.float32)
+    kind = rng.integers(0, 6, n)
+    odelta[kind == 0] = delta[kind == 0]
+    delta[kind == 1, 1] = odelta[kind == 1, 1] = 0
+    other[kind == 2] = frm[kind == 2] + np.float32([0, 1, 0]) * rng.uniform(0, 6, ((kind == 2).sum(), 1)).astype(np.float32)
+    aim = kind == 3
+    delta[aim] = ((other[aim] - frm[aim]) * rng.uniform(0.2, 1.5, (aim.sum(), 1))).astype(np.float32)
+    odelta[kind == 4] = 0
+    for a in (delta, odelta):
+        a[kind == 5, 0] = a[kind == 5, 2] = 0
+    oh, ot, on = orc.capsule_capsule_sweep_batch(frm, delta, other, odelta, dims)
+    hits = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # float32 overflow / divide warnings of numpy scalars: inf and NaN are part of the contract
+        for i in range(n):
+            got = ind.capsule_capsule_sweep(tuple(frm[i]), tuple(delta[i]), dims[i, 0], dims[i, 1], tuple(other[i]),
+                                            tuple(odelta[i]), dims[i, 2], dims[i, 3])
+            assert (got is not None) == bool(oh[i]), i
+            if got is not None:
+                hits += 1
+                assert np.float32(got[0]).tobytes() == ot[i].tobytes(), i
+                assert np.float32(got[1]).tobytes() == on[i].tobytes(), i
+    assert n // 10 < hits < n
