@@ -490,3 +490,89 @@ def test_oracle_capsule_pair_sweep_matches_independent_transliteration(orc):
                 assert np.float32(got[0]).tobytes() == ot[i].tobytes(), i
                 assert np.float32(got[1]).tobytes() == on[i].tobytes(), i
     assert n // 10 < hits < n
+
+
+def _state_equal(a, b):
+    """Every field of two STATE records; manifold arrays only up to manifold_count (slots beyond it are dead storage)."""
+    for name in a.dtype.names:
+        if name in ("manifold_triangles", "manifold_normals", "_pad"):
+            continue
+        if a[name].tobytes() != b[name].tobytes():
+            return name
+    cnt = int(a["manifold_count"])
+    if a["manifold_triangles"][:cnt].tobytes() != b["manifold_triangles"][:cnt].tobytes():
+        return "manifold_triangles"
+    if a["manifold_normals"][:cnt].tobytes() != b["manifold_normals"][:cnt].tobytes():
+        return "manifold_normals"
+    return None
+
+
+@pytest.mark.parametrize("scene", ["hulls", "ramps"])
+def test_oracle_controller_matches_independent_transliteration(orc, scenes, scene):
+    """KinematicMoveStopSystem's per-character step (Systems.swift:603-1021, 1037-1051, 1102-1205, 1229-1375,
+    1613-1901): the C++ oracle's move_and_slide against tests/independent_controller.py, a second transliteration of
+    the controller logic written separately in scalar Python (Float = float32, Double = float64) that only borrows
+    the oracle's three collision queries.  Every field of every character record after every step, bit for bit:
+    walkers pressed into the mirror's hulls (side contacts, manifold cache, slide clipping, platform pushes) and
+    human-scale walkers on ramps of 11-39 degrees (offset probes, normal smoothing, slope friction: stick / slide,
+    flattenGround, ground transitions) next to a wall."""
+    import independent_controller as ctl
+    rng = np.random.default_rng(31)
+    dt, gravity = 1.0 / 60.0, (0.0, -98.0, 0.0)
+    if scene == "hulls":
+        parts = scenes.mirror_scene(use_hulls=True)
+        p = orc.default_params()
+        pos, vel = scenes.gen_c3_characters(64, seed=5)
+        plat = np.zeros(1, orc.PLATFORM)
+        plat["aabb_min"], plat["aabb_max"], plat["delta"] = (-13, -4, 2), (-11, -3, 4), (0.03, 0.0, 0.02)
+        steps = 80
+    else:
+        # ramps of 11, 22, 31 and 39 degrees (one flattenGround, one slippery) on a floor, plus a wall to run into
+        fv, fi = scenes.plane_mesh(80.0)
+        parts = [scenes.part(fv, fi, scenes.trs_model((0, -3, 0)), entity_id=0)]
+        ramps = []
+        for k, (h, mu_s, mu_k, flat) in enumerate([(2.0, 0.8, 0.6, False), (4.0, 0.3, 0.2, False), (6.0, 0.35, 0.25, True),
+                                                    (8.0, 0.6, 0.5, False)]):
+            rv, ri = scenes.wedge_mesh(8.0, 10.0, h)
+            cx = -18.0 + 12.0 * k
+            parts.append(scenes.part(rv, ri, scenes.trs_model((cx, -3.0 + h / 2, 0)), mu_s=mu_s, mu_k=mu_k,
+                                     flatten_ground=flat, entity_id=1 + k))
+            ramps.append((cx, h))
+        bv, bi = scenes.box_mesh(6.0)
+        parts.append(scenes.part(bv, bi, scenes.trs_model((0, 0, 12)), entity_id=9))
+        p = orc.default_params(radius=0.4, half_height=0.5, skin_width=0.08)
+        pos, vel = [], []
+        for i in range(64):
+            cx, h = ramps[i % 4]
+            z = rng.uniform(-4.0, 4.5)
+            y_slope = -3.0 + h * (5.0 - z) / 10.0  # ramp surface: low edge at z = +5, high edge at z = -5
+            pos.append([cx + rng.uniform(-3, 3), y_slope + 0.9 + rng.uniform(0.05, 0.4), z])
+            ang = rng.uniform(0, 2 * np.pi)
+            vel.append([np.cos(ang) * rng.uniform(0, 5), 0.0, np.sin(ang) * rng.uniform(0, 5)])
+        pos, vel = np.float32(pos), np.float32(vel)
+        plat = np.zeros(0, orc.PLATFORM)
+        steps = 90
+    w = orc.OracleWorld(parts)
+    q = ctl.Queries(orc, w, parts, orc.ORDER_CANONICAL)
+    so, sp = orc.init_states(pos, vel), orc.init_states(pos, vel)
+    walk = vel.copy()
+    seen = {"side": 0, "slide": 0, "transition": 0, "manifold": 0}
+    for step in range(steps):
+        w.move_and_slide(so, p, dt, gravity, 1, orc.ORDER_CANONICAL, platforms=plat)
+        for i in range(len(sp)):
+            ctl.fixed_step(sp[i], p, q, dt, gravity, True, plat)
+        for i in range(len(sp)):
+            bad = _state_equal(so[i], sp[i])
+            assert bad is None, (scene, step, i, bad, so[i][bad], sp[i][bad])
+        seen["side"] += int((so["side_contact_frames"] > 0).sum())
+        seen["slide"] += int(so["ground_sliding"].sum())
+        seen["transition"] += int((so["ground_transition_frames"] > 0).sum())
+        seen["manifold"] += int((so["manifold_count"] > 1).sum())
+        if step % 10 == 9:  # walk intent re-applied: keeps the walkers pressing into walls / climbing slopes
+            for s in (so, sp):
+                s["velocity"][:, 0], s["velocity"][:, 2] = walk[:, 0], walk[:, 2]
+    assert so["grounded"].mean() > 0.6
+    if scene == "hulls":
+        assert seen["side"] > 50 and seen["manifold"] > 0
+    else:
+        assert seen["slide"] > 20 and seen["transition"] > 0
