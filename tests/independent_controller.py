@@ -260,14 +260,26 @@ def depenetrate(c, position, q):
     return position, normalize(normal_sum)
 
 
-# ---------------------------------------------------------------- SlideResolver.resolveHit, kinematicMove, static hit (:1229-1375)
-def resolve_hit(c, position, remaining, seg_len, hit, was_grounded, was_grounded_near, cached_side):
-    """Returns (position, remaining, shouldBreak)."""
+# ---------------------------------------------------------------- SlideResolver.resolveHit (:1207-1375)
+KINEMATIC_MOVE = dict(horizontal_ground_pass=False, adjust_velocity=True, ground_snap_skin_for_static=True, tri_normal_ground_like=True)
+AGENT_SEPARATION = dict(horizontal_ground_pass=True, adjust_velocity=False, ground_snap_skin_for_static=False, tri_normal_ground_like=False)
+
+
+def resolve_hit(c, position, remaining, seg_len, hit, was_grounded, was_grounded_near, cached_side, opt=KINEMATIC_MOVE):
+    """hit: a static hit (dict with triangle_normal) or an agent hit (dict with "agent": True).  Returns (position,
+    remaining, shouldBreak)."""
+    is_static = not hit.get("agent", False)
+    if opt["horizontal_ground_pass"] and is_static and abs(remaining[1]) < F(1e-5) and hit["normal"][1] >= c.min_ground_dot:
+        return add(position, remaining), (ZERO, ZERO, ZERO), True
     hit_toi, slide_n = hit["toi"], hit["normal"]
-    ground_like = hit["triangle_normal"][1] >= c.min_ground_dot
-    skin = c.ground_snap_skin if ground_like else c.skin_width
-    tri_n = hit["triangle_normal"]
-    if slide_n[1] < c.min_ground_dot and c.side_contact_frames > 0:
+    ground_like, tri_n = False, (ZERO, ZERO, ZERO)
+    if is_static:
+        ground_like = hit["triangle_normal"][1] >= c.min_ground_dot
+        skin = c.ground_snap_skin if (opt["ground_snap_skin_for_static"] and ground_like) else c.skin_width
+        tri_n = hit["triangle_normal"]
+    else:
+        skin = ZERO
+    if is_static and slide_n[1] < c.min_ground_dot and c.side_contact_frames > 0:
         if cached_side is not None:
             cn = cached_side
             if dot(cn, slide_n) < ZERO:
@@ -282,7 +294,7 @@ def resolve_hit(c, position, remaining, seg_len, hit, was_grounded, was_grounded
                 if abs(dc) > F(0.5):
                     slide_n = cn if dc >= ZERO else neg(cn)
     if slide_n[1] < c.min_ground_dot:
-        if ground_like:
+        if is_static and ground_like and opt["tri_normal_ground_like"]:
             slide_n = tri_n
         if slide_n[1] < c.min_ground_dot:
             slide_n = (slide_n[0], ZERO, slide_n[2])
@@ -298,7 +310,7 @@ def resolve_hit(c, position, remaining, seg_len, hit, was_grounded, was_grounded
     if hit_toi <= sticky and into < -into_eps:
         return position, sub(remaining, mul(slide_n, into)), False
     if into >= -into_eps:
-        if was_grounded_near and not ground_like and remaining[1] < ZERO:
+        if was_grounded_near and is_static and not ground_like and remaining[1] < ZERO:
             remaining = (remaining[0], ZERO, remaining[2])
         return add(position, remaining), (ZERO, ZERO, ZERO), True
     if (hit_toi <= eff and abs(into) <= into_eps) or into >= ZERO:
@@ -317,38 +329,68 @@ def resolve_hit(c, position, remaining, seg_len, hit, was_grounded, was_grounded
         left = sub(left, mul(slide_n, residual))
     if length_squared(left) < F(1e-8):
         return position, (ZERO, ZERO, ZERO), True
-    snd = d3(slide_n)
-    v_into = ddot(c.velocity, snd)
-    if v_into < 0:
-        c.velocity = dsub_scaled(c.velocity, snd, v_into)
+    if opt["adjust_velocity"]:
+        snd = d3(slide_n)
+        v_into = ddot(c.velocity, snd)
+        if v_into < 0:
+            c.velocity = dsub_scaled(c.velocity, snd, v_into)
     return position, left, False
 
 
-# ---------------------------------------------------------------- slide loop without agents (:1658-1765)
-def kinematic_sweep(c, position, remaining, was_grounded, was_grounded_near, q):
+# ---------------------------------------------------------------- agents (:1053-1091, 1378-1399) + slide loop (:1658-1765)
+def agent_best_hit(position, remaining, remaining_len, base_move_len, dt, self_index, c, agents):
+    """agents: list of (position, velocity) Float3 snapshots, one per character (all solid, controller radius)."""
+    best = None
+    time_scale = smin(remaining_len / base_move_len, ONE) if base_move_len > F(1e-6) else ONE
+    segment_dt = dt * time_scale
+    for k, (o_pos, o_vel) in enumerate(agents):
+        if k == self_index:
+            continue
+        hit = ind.capsule_capsule_sweep(position, remaining, c.radius, c.half_height, o_pos, mul(o_vel, segment_dt),
+                                        c.radius, c.half_height)
+        if hit is not None and (best is None or hit[0] < best["toi"]):
+            best = {"toi": hit[0], "normal": hit[1], "agent": True}
+    return best
+
+
+def select_best_hit(c, static_hit, agent_hit):  # HitSelector.selectBestHit
+    if static_hit is not None and agent_hit is not None:
+        skin = c.ground_snap_skin if static_hit["normal"][1] >= c.min_ground_dot else c.skin_width
+        static_stop, agent_stop = smax(static_hit["toi"] - skin, ZERO), smax(agent_hit["toi"], ZERO)
+        return static_hit if static_stop <= agent_stop else agent_hit
+    return static_hit if static_hit is not None else agent_hit
+
+
+def kinematic_sweep(c, position, remaining, was_grounded, was_grounded_near, q, dt=None, agents=None, self_index=-1):
+    base_move_len = length(mul(f3(c.velocity), dt)) if agents is not None else ZERO
     last = None
     for _ in range(c.max_slide_iterations):
         seg_len = length(remaining)
         if seg_len < F(1e-6):
             break
-        hit = q.blocking(c, position, remaining)
+        static_hit = q.blocking(c, position, remaining)
+        if static_hit is not None and static_hit["normal"][1] < c.min_ground_dot and c.side_contact_frames > 0:
+            cached = cached_normal(c, static_hit["triangle_index"])
+            if cached is not None:
+                if dot(cached, static_hit["normal"]) < ZERO:
+                    cached = neg(cached)
+                static_hit["normal"] = cached
+        agent_hit = None
+        if agents is not None:
+            agent_hit = agent_best_hit(position, remaining, seg_len, base_move_len, dt, self_index, c, agents)
+        hit = select_best_hit(c, static_hit, agent_hit)
         if hit is None:
             position = add(position, remaining)
             remaining = (ZERO, ZERO, ZERO)
             break
-        if hit["normal"][1] < c.min_ground_dot and c.side_contact_frames > 0:
-            cached = cached_normal(c, hit["triangle_index"])
-            if cached is not None:
-                if dot(cached, hit["normal"]) < ZERO:
-                    cached = neg(cached)
-                hit["normal"] = cached
         hit_normal = hit["normal"]
+        is_static = not hit.get("agent", False)
         cached_side = None
-        if hit_normal[1] < c.min_ground_dot and c.side_contact_frames > 0:
+        if is_static and hit_normal[1] < c.min_ground_dot and c.side_contact_frames > 0:
             cached_side = cached_normal(c, hit["triangle_index"])
         position, remaining, should_break = resolve_hit(c, position, remaining, seg_len, hit, was_grounded,
                                                         was_grounded_near, cached_side)
-        if hit_normal[1] < c.min_ground_dot:
+        if is_static and hit_normal[1] < c.min_ground_dot:
             cache_record(c, hit["triangle_index"], hit_normal, True)
         if last is not None:
             dn = dot(last, hit_normal)
@@ -463,7 +505,7 @@ def ground_contact(c, position, q, was_grounded_near, gravity, dt):
 
 
 # ---------------------------------------------------------------- one fixed step of one character (:603-619, 1823-1901)
-def fixed_step(rec, params, q, dt, gravity, apply_gravity=True, platforms=()):
+def fixed_step(rec, params, q, dt, gravity, apply_gravity=True, platforms=(), agents=None, self_index=-1):
     c = Controller(rec, params)
     dt = F(dt)
     gravity = tuple(F(x) for x in gravity)
@@ -488,7 +530,7 @@ def fixed_step(rec, params, q, dt, gravity, apply_gravity=True, platforms=()):
         into = dot(remaining, depen_n)
         if into < ZERO:
             remaining = sub(remaining, mul(depen_n, into))
-    position, remaining = kinematic_sweep(c, position, remaining, was_grounded, was_grounded_near, q)
+    position, remaining = kinematic_sweep(c, position, remaining, was_grounded, was_grounded_near, q, dt, agents, self_index)
     position, state = ground_contact(c, position, q, was_grounded_near, gravity, dt)
     # writeBack (:1802-1821)
     c.position = d3(position)
@@ -498,3 +540,136 @@ def fixed_step(rec, params, q, dt, gravity, apply_gravity=True, platforms=()):
     if state["grounded"]:
         c.ground_triangle_index = state["triangle_index"]
     c.store(rec)
+
+
+def collect_agent_states(states, dt, gravity, apply_gravity=True):
+    """collectAgentStates (:1592-1611) for a batch in which every character carries an AgentCollisionComponent: positionF
+    and linearVelocityF of everybody, taken after GravitySystem ran and before anybody moves."""
+    out = []
+    g = d3(tuple(F(x) for x in gravity))
+    for rec in states:
+        vel = tuple(float(x) for x in rec["velocity"])
+        if apply_gravity and not (bool(rec["grounded"]) and bool(rec["grounded_near"])):
+            vel = (vel[0] + g[0] * float(F(dt)), vel[1] + g[1] * float(F(dt)), vel[2] + g[2] * float(F(dt)))
+        out.append((f3(tuple(float(x) for x in rec["position"])), f3(vel)))
+    return out
+
+
+# ---------------------------------------------------------------- AgentSeparationSystem (:1906-2210)
+def agent_separation(states, params, q, mass_weight=None, iterations=2, separation_margin=0.2, height_margin=0.1,
+                     use_query=True):
+    n = len(states)
+    if n <= 1:
+        return
+    cs = [Controller(states[i], params) for i in range(n)]
+    sep_margin, h_margin = F(separation_margin), F(height_margin)
+    agents = []
+    max_radius = ZERO
+    for i, c in enumerate(cs):
+        mw = F(1.0) if mass_weight is None else F(mass_weight[i])
+        inv_w = ONE / mw if mw > ZERO else ZERO
+        max_radius = smax(max_radius, c.radius)
+        agents.append({"position": f3(c.position), "velocity": f3(c.velocity), "radius": c.radius, "hh": c.half_height,
+                       "inv_w": inv_w})
+    original = [a["position"] for a in agents]
+    cell_size = smax(max_radius * F(2) + sep_margin, F(0.001))
+
+    def cell_of(pos):
+        return (int(np.floor(pos[0] / cell_size)), int(np.floor(pos[2] / cell_size)))
+
+    for _ in range(max(1, iterations)):
+        cells = {}
+        for i, a in enumerate(agents):
+            cells.setdefault(cell_of(a["position"]), []).append(i)
+        for i in range(n):
+            a = dict(agents[i])  # `let a = agents[i]`
+            ccell = cell_of(a["position"])
+            c = cs[i]
+            for dz in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    lst = cells.get((ccell[0] + dx, ccell[1] + dz))
+                    if lst is None:
+                        continue
+                    for j in lst:
+                        if not j > i:
+                            continue
+                        b = dict(agents[j])
+                        a_min, a_max = a["position"][1] - a["hh"], a["position"][1] + a["hh"]
+                        b_min, b_max = b["position"][1] - b["hh"], b["position"][1] + b["hh"]
+                        ddx, ddz = a["position"][0] - b["position"][0], a["position"][2] - b["position"][2]
+                        dist_sq = ddx * ddx + ddz * ddz
+                        margin = smin(sep_margin, smin(cs[i].skin_width, cs[j].skin_width))
+                        min_dist = a["radius"] + b["radius"] + margin
+                        if a_max < b_min - h_margin or a_min > b_max + h_margin:
+                            continue
+                        if dist_sq >= min_dist * min_dist:
+                            continue
+                        dist = np.sqrt(smax(dist_sq, F(1e-8)))
+                        nx, nz = ddx / dist, ddz / dist
+                        pen = min_dist - dist
+                        w_sum = a["inv_w"] + b["inv_w"]
+                        if w_sum <= ZERO:
+                            continue
+                        corr = pen / w_sum
+                        move_a = (nx * corr * a["inv_w"], ZERO, nz * corr * a["inv_w"])
+                        move_b = (-nx * corr * b["inv_w"], ZERO, -nz * corr * b["inv_w"])
+                        rel_v = sub(a["velocity"], b["velocity"])
+                        vn = rel_v[0] * nx + rel_v[2] * nz
+                        if vn < ZERO:
+                            impulse = -vn
+                            scale_a, scale_b = a["inv_w"] / w_sum, b["inv_w"] / w_sum
+                            va, vb = agents[i]["velocity"], agents[j]["velocity"]
+                            agents[i]["velocity"] = (va[0] + nx * impulse * scale_a, va[1], va[2] + nz * impulse * scale_a)
+                            agents[j]["velocity"] = (vb[0] - nx * impulse * scale_b, vb[1], vb[2] - nz * impulse * scale_b)
+                        if use_query:
+                            blocked_a = blocked_b = False
+                            if length(move_a) > F(1e-6):
+                                h = q.blocking(c, agents[i]["position"], move_a)
+                                blocked_a = h is not None and h["toi"] <= c.skin_width and h["normal"][1] < c.min_ground_dot
+                            if length(move_b) > F(1e-6):
+                                h = q.blocking(cs[j], agents[j]["position"], move_b)
+                                blocked_b = (h is not None and h["toi"] <= cs[j].skin_width and
+                                             h["normal"][1] < cs[j].min_ground_dot)
+                            if blocked_a and not blocked_b:
+                                move_a, move_b = (ZERO, ZERO, ZERO), (-nx * pen, ZERO, -nz * pen)
+                            elif blocked_b and not blocked_a:
+                                move_b, move_a = (ZERO, ZERO, ZERO), (nx * pen, ZERO, nz * pen)
+                            elif blocked_a and blocked_b:
+                                continue
+                        agents[i]["position"] = add(agents[i]["position"], move_a)
+                        agents[j]["position"] = add(agents[j]["position"], move_b)
+    down = (ZERO, F(-1), ZERO)
+    for i in range(n):  # AgentSeparationPostProcessor.apply + write-back (:2043-2117, 2196-2208)
+        c, agent = cs[i], agents[i]
+        position = agent["position"]
+        if use_query:
+            delta = sub(position, original[i])
+            moved = False
+            if length(delta) > F(1e-6):
+                moved = True
+                remaining, position = delta, original[i]
+                for _ in range(2):
+                    seg_len = length(remaining)
+                    if seg_len < F(1e-6):
+                        break
+                    hit = q.blocking(c, position, remaining)
+                    if hit is None:
+                        position = add(position, remaining)
+                        remaining = (ZERO, ZERO, ZERO)
+                        break
+                    position, remaining, done = resolve_hit(c, position, remaining, seg_len, hit, False, False, None,
+                                                            AGENT_SEPARATION)
+                    if done:
+                        break
+            if moved and c.velocity[1] <= 0 and c.snap_distance > ZERO:
+                hit = q.ground(c, position, mul(down, c.snap_distance))
+                if hit is not None and hit["toi"] <= c.snap_distance:
+                    move = smin(smax(hit["toi"] - c.ground_snap_skin, ZERO), c.ground_snap_max_step)
+                    position = add(position, mul(down, move))
+                    c.grounded = True
+                    c.grounded_near = bool(hit["toi"] <= smax(c.ground_snap_skin, c.skin_width))
+                    c.ground_normal = (ZERO, ONE, ZERO) if hit["material"][2] else hit["triangle_normal"]
+                    c.ground_triangle_index = hit["triangle_index"]
+        c.position = d3(position)
+        c.velocity = d3(agent["velocity"])
+        c.store(states[i])

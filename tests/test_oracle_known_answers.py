@@ -576,3 +576,47 @@ def test_oracle_controller_matches_independent_transliteration(orc, scenes, scen
         assert seen["side"] > 50 and seen["manifold"] > 0
     else:
         assert seen["slide"] > 20 and seen["transition"] > 0
+
+
+def test_oracle_crowd_step_matches_independent_transliteration(orc, scenes):
+    """The crowd step — move-and-slide with agent CCD (AgentSweepSolver + HitSelector + the .agentHit case of
+    SlideResolver, Systems.swift:1053-1091, 1378-1399) followed by AgentSeparationSystem (:1906-2210: grid, sequential
+    pair resolver with its blocking-cast vetoes, post slide + snap, Float write-back) — the C++ oracle against the
+    separately written Python version, every field of every record after each of the two phases of every step."""
+    import independent_controller as ctl
+    rng = np.random.default_rng(77)
+    dt, gravity = 1.0 / 60.0, (0.0, -98.0, 0.0)
+    fv, fi = scenes.plane_mesh(80.0)
+    bv, bi = scenes.box_mesh(6.0)
+    rv, ri = scenes.wedge_mesh(8.0, 10.0, 3.0)
+    parts = [scenes.part(fv, fi, scenes.trs_model((0, -3, 0)), entity_id=0),
+             scenes.part(bv, bi, scenes.trs_model((5.5, 0, 0)), entity_id=1),
+             scenes.part(rv, ri, scenes.trs_model((-6, -1.5, 0)), mu_s=0.4, mu_k=0.3, entity_id=2)]
+    w = orc.OracleWorld(parts)
+    q = ctl.Queries(orc, w, parts, orc.ORDER_CANONICAL)
+    p = orc.default_params(radius=0.4, half_height=0.5, skin_width=0.08)
+    n = 70
+    pos = np.stack([rng.uniform(-3, 2.4, n), np.full(n, -3.0 + 0.95) + rng.uniform(0, 0.2, n), rng.uniform(-3, 3, n)],
+                   axis=1).astype(np.float32)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    walk = (np.stack([np.cos(ang), np.zeros(n), np.sin(ang)], axis=1) * rng.uniform(1, 6, (n, 1))).astype(np.float32)
+    walk[: n // 3] = np.float32([4.0, 0, 0]) * rng.uniform(0.5, 1.5, (n // 3, 1)).astype(np.float32)  # a third walks into the wall
+    mass = rng.choice(np.float32([1.0, 3.0, 500.0, 0.0]), n, p=[0.55, 0.25, 0.15, 0.05])
+    so, sp = orc.init_states(pos, walk), orc.init_states(pos, walk)
+    pairs = 0
+    for step in range(25):
+        agents = ctl.collect_agent_states(sp, dt, gravity)
+        w.move_and_slide(so, p, dt, gravity, 3, orc.ORDER_CANONICAL)
+        for i in range(n):
+            ctl.fixed_step(sp[i], p, q, dt, gravity, True, (), agents, i)
+        for i in range(n):
+            bad = _state_equal(so[i], sp[i])
+            assert bad is None, ("move", step, i, bad, so[i][bad], sp[i][bad])
+        pairs += w.agent_separation(so, p, mass_weight=mass, order=orc.ORDER_CANONICAL)
+        ctl.agent_separation(sp, p, q, mass_weight=mass)
+        for i in range(n):
+            bad = _state_equal(so[i], sp[i])
+            assert bad is None, ("separation", step, i, bad, so[i][bad], sp[i][bad])
+        for s in (so, sp):
+            s["velocity"][:, 0], s["velocity"][:, 2] = walk[:, 0], walk[:, 2]
+    assert pairs > 10 * n
