@@ -325,3 +325,133 @@ def capsule_capsule_sweep(frm, delta, radius, half_height, other_pos, other_delt
         return None
     rel_at_hit = add(rel_start, mul(rel_delta, best))
     return best * move_len, capsule_pair_hit_normal(rel_at_hit, h_sum)
+
+
+# ---------------------------------------------------------------- Game/CollisionQuery.swift:980-1283 (query layer)
+# Brute force over every triangle in index order: the candidate SET of the reference's BVH walk is tree independent
+# (node boxes only cull), and a strict `<` over ascending indices keeps the smallest index of equal tois — the
+# canonical tie rule.  `tris` = list of (v0, v1, v2, layer) in triangle-index order, static set first.
+def _vmin(a, b):
+    return (min(a[0], b[0]), min(a[1], b[1]), min(a[2], b[2]))
+
+
+def _vmax(a, b):
+    return (max(a[0], b[0]), max(a[1], b[1]), max(a[2], b[2]))
+
+
+def _disjoint(tlo, thi, lo, hi):
+    return (thi[0] < lo[0] or tlo[0] > hi[0] or thi[1] < lo[1] or tlo[1] > hi[1] or thi[2] < lo[2] or tlo[2] > hi[2])
+
+
+def capsule_cast(tris, n_static, frm, delta, radius, half_height, mask, blocking_only, min_normal_y):
+    """capsuleCastCombined (:980-1117).  Returns None or (toi, position, normal, triangleNormal, triangleIndex)."""
+    seg_len = np.sqrt(dot(delta, delta))
+    if seg_len < F(1e-6):
+        return None
+    direction = (delta[0] / seg_len, delta[1] / seg_len, delta[2] / seg_len)
+    up = v(0, 1, 0)
+    a0, b0 = add(frm, mul(up, half_height)), sub(frm, mul(up, half_height))
+    a1, b1 = add(a0, delta), add(b0, delta)
+    ext = (radius, radius, radius)
+    lo = sub(_vmin(_vmin(a0, b0), _vmin(a1, b1)), ext)
+    hi = add(_vmax(_vmax(a0, b0), _vmax(a1, b1)), ext)
+    best = [None, None]  # per set, then chooseNearest (:909-914)
+    best_t = [seg_len, seg_len]
+    for index, (v0, v1, v2, layer) in enumerate(tris):
+        which = 0 if index < n_static else 1
+        if (int(layer) & int(mask)) == 0:
+            continue
+        if _disjoint(_vmin(v0, _vmin(v1, v2)), _vmax(v0, _vmax(v1, v2)), lo, hi):
+            continue
+        hit = sweep_capsule_triangle(frm, direction, seg_len, radius, half_height, v0, v1, v2)
+        if hit is None or not hit[0] < best_t[which]:
+            continue
+        toi, pos, nrm, tri_n, _ = hit
+        if blocking_only and (dot(delta, nrm) >= ZERO or dot(delta, tri_n) >= ZERO):
+            continue
+        if min_normal_y is not None and tri_n[1] < min_normal_y:
+            continue
+        best_t[which] = toi
+        best[which] = (toi, pos, nrm, tri_n, index)
+    if best[0] is not None and best[1] is not None:
+        return best[0] if best[0][0] <= best[1][0] else best[1]
+    return best[0] if best[0] is not None else best[1]
+
+
+def capsule_overlap_all(tris, frm, radius, half_height, mask, max_hits):
+    """capsuleOverlapAll (:1119-1283) under the canonical rule: the max_hits deepest, deepest first, ties by index."""
+    up = v(0, 1, 0)
+    a0, b0 = add(frm, mul(up, half_height)), sub(frm, mul(up, half_height))
+    ext = (radius, radius, radius)
+    lo, hi = sub(_vmin(a0, b0), ext), add(_vmax(a0, b0), ext)
+    hits = []
+    for index, (v0, v1, v2, layer) in enumerate(tris):
+        if (int(layer) & int(mask)) == 0:
+            continue
+        if _disjoint(_vmin(v0, _vmin(v1, v2)), _vmax(v0, _vmax(v1, v2)), lo, hi):
+            continue
+        dist, seg_pt, tri_pt = segment_triangle_distance(frm, half_height, v0, v1, v2)
+        if dist >= radius:
+            continue
+        tri_normal = normalize(cross(sub(v1, v0), sub(v2, v0)))
+        n = tri_normal if dist < F(1e-6) else normalize(sub(seg_pt, tri_pt))
+        tri_n = neg(tri_normal) if dot(tri_normal, n) < ZERO else tri_normal
+        hits.append((radius - dist, tri_pt, n, tri_n, index))
+    hits.sort(key=lambda h: (-float(h[0]), h[4]))
+    return hits[:max_hits]
+
+
+# ---------------------------------------------------------------- Game/CollisionQuery.swift:331-417, 768-785, 916-978
+def build_soup(parts):
+    """TriangleMeshSet.rebuild for one set: world-space vertices = simd_mul(modelMatrix, (p, 1)) with the documented
+    column order ((c0*x + c1*y) + c2*z) + c3*1, triangles with |e1 x e2|^2 <= 1e-10 dropped, numbering = what is left.
+    parts: dicts with positions (n,3), indices, model (16 floats column-major), layer.  Returns (positions, triangles)
+    with triangles = [(i0, i1, i2, layer)]."""
+    positions, triangles = [], []
+    for prt in parts:
+        m = [F(x) for x in np.asarray(prt["model"], np.float32).reshape(-1)]
+        base = len(positions)
+        for p in np.asarray(prt["positions"], np.float32).reshape(-1, 3):
+            x, y, z = F(p[0]), F(p[1]), F(p[2])
+            positions.append(tuple(((m[r] * x + m[4 + r] * y) + m[8 + r] * z) + m[12 + r] * ONE for r in range(3)))
+        idx = np.asarray(prt["indices"], np.uint32).reshape(-1)
+        t = 0
+        while t + 2 < len(idx):
+            i0, i1, i2 = base + int(idx[t]), base + int(idx[t + 1]), base + int(idx[t + 2])
+            e1, e2 = sub(positions[i1], positions[i0]), sub(positions[i2], positions[i0])
+            if not length_squared(cross(e1, e2)) <= F(1e-10):
+                triangles.append((i0, i1, i2, int(prt["layer"])))
+            t += 3
+    return positions, triangles
+
+
+def raycast(tris, n_static, origin, direction, max_distance, mask):
+    """raycast (:768-785, 916-978) as the minimum over all triangles (canonical rule): rayTriangle two-sided with
+    eps 1e-6, accepted when t < closest (strict), per set, then chooseNearest.  Returns None or (t, index)."""
+    best = [None, None]
+    closest = [max_distance, max_distance]
+    for index, (v0, v1, v2, layer) in enumerate(tris):
+        which = 0 if index < n_static else 1
+        if (int(layer) & int(mask)) == 0:
+            continue
+        e1, e2 = sub(v1, v0), sub(v2, v0)
+        pvec = cross(direction, e2)
+        det = dot(e1, pvec)
+        if abs(det) < F(1e-6):
+            continue
+        inv_det = ONE / det
+        tvec = sub(origin, v0)
+        u = dot(tvec, pvec) * inv_det
+        if u < ZERO or u > ONE:
+            continue
+        qvec = cross(tvec, e1)
+        vv = dot(direction, qvec) * inv_det
+        if vv < ZERO or (u + vv) > ONE:
+            continue
+        t = dot(e2, qvec) * inv_det
+        if t >= ZERO and t < closest[which]:
+            closest[which] = t
+            best[which] = (t, index)
+    if best[0] is not None and best[1] is not None:
+        return best[0] if best[0][0] <= best[1][0] else best[1]
+    return best[0] if best[0] is not None else best[1]

@@ -620,3 +620,101 @@ def test_oracle_crowd_step_matches_independent_transliteration(orc, scenes):
         for s in (so, sp):
             s["velocity"][:, 0], s["velocity"][:, 2] = walk[:, 0], walk[:, 2]
     assert pairs > 10 * n
+
+
+def test_oracle_query_layer_matches_independent_brute_force(orc, scenes):
+    """capsuleCast / capsuleCastBlocking / capsuleCastGround / capsuleOverlapAll (CollisionQuery.swift:787-882, 980-1283:
+    swept box, layer mask, triangle-AABB test, blocking and ground filters, strict-< best, chooseNearest over the static
+    and dynamic sets): the oracle in canonical order against a brute-force Python version written separately, on the
+    mirror's hulls + floor with a dynamic box and mixed layers — bit for bit, including which triangle wins."""
+    import independent_narrow_phase as ind
+    rng = np.random.default_rng(123)
+    parts = scenes.mirror_scene(use_hulls=True)
+    bv, bi = scenes.box_mesh(3.0)
+    parts.append(scenes.part(bv, bi, scenes.trs_model((-9.0, -1.5, 6.5)), layer=4, is_dynamic=True, entity_id=77))
+    w = orc.OracleWorld(parts)
+    tris = []
+    for which in (0, 1):
+        soup = w.read_soup(which)
+        P, I, L = soup["positions"], soup["indices"], soup["layers"]
+        tris += [(tuple(P[a]), tuple(P[b]), tuple(P[c]), int(l)) for (a, b, c), l in zip(I, L)]
+    n_static = w.counts(0)["triangles"]
+    n = 1500
+    q = scenes.gen_casts(n, [-15, -3.5, -1], [-5, 4, 10], seed=8, len_range=(0.05, 4.0), expand=1.0)
+    q["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 1, 4, 0xFFFFFFFB]), n)
+    q["min_normal_y"] = 0.5
+    for mode, blocking, min_y in ((0, False, None), (1, True, None), (2, False, np.float32(0.5))):
+        ref = w.capsule_cast(q, mode, orc.ORDER_CANONICAL)
+        hits = 0
+        for i in range(n):
+            got = ind.capsule_cast(tris, n_static, tuple(q["from"][i]), tuple(q["delta"][i]), q["radius"][i],
+                                   q["half_height"][i], q["mask"][i], blocking, min_y)
+            if got is None:
+                assert ref["triangle_index"][i] == -1, (mode, i)
+                continue
+            hits += 1
+            assert ref["triangle_index"][i] == got[4], (mode, i)
+            assert np.float32(got[0]).tobytes() == ref["toi"][i].tobytes(), (mode, i)
+            for field, val in (("position", got[1]), ("normal", got[2]), ("triangle_normal", got[3])):
+                assert np.float32(val).tobytes() == ref[field][i].tobytes(), (mode, i, field)
+        assert hits > n // 10, mode
+    caps = scenes.gen_capsules(n, [-15, -3.5, -1], [-5, 2, 10], seed=9)
+    caps["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 1, 4]), n)
+    out, counts, _ = w.capsule_overlap_all(caps, 8, orc.ORDER_CANONICAL)
+    overlapping = 0
+    for i in range(n):
+        got = ind.capsule_overlap_all(tris, tuple(caps["from"][i]), caps["radius"][i], caps["half_height"][i], caps["mask"][i], 8)
+        assert counts[i] == len(got), i
+        overlapping += len(got) > 0
+        for k, h in enumerate(got):
+            r = out[i][k]
+            assert r["triangle_index"] == h[4] and np.float32(h[0]).tobytes() == r["depth"].tobytes(), (i, k)
+            for field, val in (("position", h[1]), ("normal", h[2]), ("triangle_normal", h[3])):
+                assert np.float32(val).tobytes() == r[field].tobytes(), (i, k, field)
+    assert overlapping > n // 20
+
+
+def test_oracle_soup_and_raycast_match_independent_brute_force(orc, scenes):
+    """TriangleMeshSet.rebuild (CollisionQuery.swift:331-417: world-space vertices, absolute area filter, numbering of the
+    survivors) and raycast (:768-785, 916-978, 1575-1601): the oracle's soup and its canonical-order ray results against
+    the separately written Python versions — positions and indices equal bit for bit, then every ray's winner and
+    distance.  The scene mixes a scaled + rotated part, a part whose small triangles fall under the area filter, a
+    dynamic part and per-ray masks."""
+    import independent_narrow_phase as ind
+    rng = np.random.default_rng(77)
+    bv, bi = scenes.box_mesh(2.0)
+    pv, pi = scenes.plane_mesh(30.0)
+    q = scenes.quat_angle_axis(0.7, (0.3, 1.0, -0.2))
+    tiny = np.concatenate([bv * 1e-3, bv + np.float32([4, 0, 0])]).astype(np.float32)  # first copy: area² << 1e-10
+    tiny_idx = np.concatenate([bi, bi + len(bv)]).astype(np.uint32)
+    parts = [scenes.part(pv, pi, scenes.trs_model((0, -2, 0)), layer=1, entity_id=1),
+             scenes.part(bv, bi, scenes.trs_model((1.5, 0.2, -1.0), q, (1.5, 0.75, 2.0)), layer=2, entity_id=2),
+             scenes.part(tiny, tiny_idx, scenes.trs_model((-3, 0, 2)), layer=4, entity_id=3),
+             scenes.part(bv, bi, scenes.trs_model((0, 1.0, 4.0), q), layer=8, is_dynamic=True, entity_id=4)]
+    w = orc.OracleWorld(parts)
+    tris = []
+    for which, dyn in ((0, False), (1, True)):
+        soup = w.read_soup(which)
+        mine_p, mine_t = ind.build_soup([p for p in parts if bool(p["is_dynamic"]) == dyn])
+        assert np.float32(mine_p).tobytes() == soup["positions"].tobytes(), which
+        assert [t[:3] for t in mine_t] == [tuple(int(x) for x in r) for r in soup["indices"]], which
+        assert [t[3] for t in mine_t] == [int(x) for x in soup["layers"]], which
+        tris += [(mine_p[a], mine_p[b], mine_p[c], l) for a, b, c, l in mine_t]
+    n_static = w.counts(0)["triangles"]
+    assert n_static == 2 + 12 + 12 and w.counts(1)["triangles"] == 12  # the 12 millimetre-box triangles are dropped
+    n = 3000
+    rays = scenes.gen_rays(n, [-6, -2, -6], [6, 3, 6], seed=5, max_distance=25.0, expand=2.0)
+    rays["direction"] *= rng.uniform(0.25, 3.0, (n, 1)).astype(np.float32)  # callee does not normalise (:768)
+    rays["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 1, 2, 8, 0xFFFFFFF7]), n)
+    ref = w.raycast(rays, orc.ORDER_CANONICAL)
+    hits = 0
+    for i in range(n):
+        got = ind.raycast(tris, n_static, tuple(rays["origin"][i]), tuple(rays["direction"][i]), rays["max_distance"][i],
+                          rays["mask"][i])
+        if got is None:
+            assert ref["triangle_index"][i] == -1, i
+            continue
+        hits += 1
+        assert ref["triangle_index"][i] == got[1], i
+        assert np.float32(got[0]).tobytes() == ref["distance"][i].tobytes(), i
+    assert hits > n // 4
