@@ -490,8 +490,13 @@ def run_c4(args):
     d_out = torch.empty(n * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=dev)
     stream = tstream.cuda_stream
 
+    gather = bool(args.gather) and ws > 1
+    d_all = torch.empty(n * ws * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=dev) if gather else None
+
     def step():
         world.capsule_cast_device(d_q.data_ptr(), n, cq.CAST_BLOCKING, d_out.data_ptr(), stream)
+        if gather:  # the one collective of the path: hit records of all ranks onto every rank, NCCL
+            cq.shard.gather_records(d_out, n * ws, cq.CAST_HIT.itemsize, out=d_all)
 
     for _ in range(args.warmup):
         step()
@@ -510,6 +515,18 @@ def run_c4(args):
     launches = world.stats()["kernel_launches"]
     ms = red(e0.elapsed_time(e1), dist.ReduceOp.MAX)
     value = n * ws * args.steps / (ms * 1e-3)
+    gather_ms = None
+    if gather:  # the collective alone, same buffers, max over ranks
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            cq.shard.gather_records(d_out, n * ws, cq.CAST_HIT.itemsize, out=d_all)
+        g1.record()
+        barrier()
+        gather_ms = red(g0.elapsed_time(g1), dist.ReduceOp.MAX) / args.steps
+        mine = d_all[rank * n * cq.CAST_HIT.itemsize:(rank + 1) * n * cq.CAST_HIT.itemsize]
+        assert bool(torch.equal(mine, d_out)), "gathered records differ from the local shard"
     world.set_counting(True)
     world.resetStats()
     step()
@@ -560,7 +577,10 @@ def run_c4(args):
                        "triangles": info["n_static_triangles"], "bvh_build_ms": info["build_ms"],
                        "world_create_s": t_create, "terrain_gen_s": t_gen, "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
                        "l2": "triangle SoA + nodes (%.0f MB) and queries exceed the 126 MB L2" % (info["n_static_triangles"] * 112 / 1e6),
-                       "e2e_matches_device_path": same},
+                       "e2e_matches_device_path": same,
+                       "gather": (f"all_gather_into_tensor (NCCL) of the {cq.CAST_HIT.itemsize} B hit records of all ranks inside "
+                                  f"the timed region; the collective alone: {gather_ms:.3f} ms/step") if gather else
+                                 "none (results stay on the owning GPU)"},
             "roofline": {"bound": "hbm", "achieved": algo / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": algo / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "k_capsule_cast", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo,
@@ -774,6 +794,8 @@ def main():
                     help="terrain mesh only: characters collide with each other; value = crowd footprint coverage (e.g. 0.1)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="c4, N > 1: all-gather the hit records of all ranks (NCCL) inside the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "c2":

@@ -16,7 +16,7 @@ import subprocess
 
 import numpy as np
 
-from . import scenes  # noqa: F401  (re-export)
+from . import scenes, shard  # noqa: F401  (re-export)
 from .service import ActiveChunkSet, CollisionQueryService, chunk_to_world, world_to_chunk  # noqa: E402,F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

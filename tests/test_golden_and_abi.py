@@ -137,27 +137,29 @@ def test_static_mesh_loader_errors(cq, tmp_path):
 _GLOO_WORKER = r"""
 import os, sys, importlib
 import numpy as np
+import torch
 import torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 from oracle import oracle as orc
 sc = importlib.import_module("swift-game-engine_b200.scenes")
+shard = importlib.import_module("swift-game-engine_b200.shard")
 dist.init_process_group("gloo")
 rank, ws = dist.get_rank(), dist.get_world_size()
-n = 3000
-pos, vel = sc.gen_c3_characters(n, seed=7)
-lo, hi = rank * n // ws, (rank + 1) * n // ws   # contiguous rank ranges, mesh replicated (SURVEY.md §8e)
 w = orc.OracleWorld(sc.mirror_scene(True))
-s = orc.init_states(pos[lo:hi], vel[lo:hi])
-w.move_and_slide(s, orc.default_params())
-mine = np.frombuffer(s.tobytes(), np.uint8)
-import torch
-parts = [torch.zeros((((r + 1) * n // ws) - (r * n // ws)) * orc.STATE.itemsize, dtype=torch.uint8) for r in range(ws)]
-dist.all_gather(parts, torch.from_numpy(mine.copy()))
-if rank == 0:
+for n in (3000, 2001, 1):   # equal shards (one all_gather_into_tensor), ragged shards, fewer units than ranks
+    pos, vel = sc.gen_c3_characters(n, seed=7)
+    lo, hi = shard.rank_range(n, rank, ws)   # contiguous rank ranges, mesh replicated (SURVEY.md §8e)
+    s = orc.init_states(pos[lo:hi], vel[lo:hi])
+    if hi > lo:
+        w.move_and_slide(s, orc.default_params())
+    mine = torch.from_numpy(np.frombuffer(s.tobytes(), np.uint8).copy())
+    got = shard.gather_records(mine, n, orc.STATE.itemsize)
     full = orc.init_states(pos, vel)
     w.move_and_slide(full, orc.default_params())
-    got = np.concatenate([p.numpy() for p in parts])
-    assert got.tobytes() == full.tobytes(), "sharded result differs from the single-rank result"
+    assert got.numpy().tobytes() == full.tobytes(), "sharded result differs from the single-rank result (n=%d)" % n
+    assert shard.records_from_bytes(got, orc.STATE)["position"].shape == (n, 3)
+assert sum(shard.shard_sizes(10, 4)) == 10 and shard.shard_sizes(2, 4).count(0) == 2
+if rank == 0:
     print("GLOO_OK")
 dist.destroy_process_group()
 """
