@@ -193,7 +193,11 @@ int cq_capsule_overlap_all_batch(cq_world *w, const cq_capsule *q, int32_t n, in
 
 /* Device-pointer twins: inputs/outputs already resident in HBM, enqueued on
  * `stream` (a cudaStream_t cast to void*; NULL = the world's own stream), no
- * synchronisation.  Same record layouts as above. */
+ * synchronisation.  Same record layouts as above.  Calls on one world may be
+ * enqueued on any number of streams (from one host thread at a time): the
+ * world's scratch blocks are handed from stream to stream behind events, so up
+ * to four launches overlap and further ones queue behind them.
+ * cq_world_update_transforms and cq_world_destroy wait for everything in flight. */
 int cq_raycast_device(cq_world *w, const cq_ray *d_rays, int32_t n, cq_ray_hit *d_out, void *stream);
 int cq_capsule_cast_device(cq_world *w, const cq_capsule_cast *d_q, int32_t n, int32_t mode,
                            cq_cast_hit *d_out, void *stream);

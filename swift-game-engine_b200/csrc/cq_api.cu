@@ -1,5 +1,6 @@
 // cq_api.cu — the C ABI of include/cq.h: world lifetime, transforms/refit, batch + device query
 // entry points, counters.  No CPU fallback anywhere: every path needs a usable CUDA device.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <chrono>
@@ -42,7 +43,38 @@ int *next_work_counter(cq_world *w, cudaStream_t st) {
     return p;
 }
 
-void *pool_node_scratch(cq_world *w, size_t warps) {
+int scratch_acquire(cq_world *w, ScratchBuf &b, cudaStream_t st) {
+    if (!b.ev) CQ_CUDA(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
+    if (b.recorded && b.last != st) CQ_CUDA(cudaStreamWaitEvent(st, b.ev, 0));
+    if (std::find(w->held.begin(), w->held.end(), &b) == w->held.end()) w->held.push_back(&b);
+    return CQ_OK;
+}
+
+int release_held(cq_world *w, cudaStream_t st) {
+    int rc = CQ_OK;
+    for (ScratchBuf *b : w->held) {
+        int r = check_cuda(cudaEventRecord(b->ev, st), "scratch release");
+        if (r != CQ_OK) rc = r;
+        b->last = st;
+        b->recorded = true;
+    }
+    w->held.clear();
+    return rc;
+}
+
+int finish_launch(cq_world *w, cudaStream_t st, const char *what) {
+    const int rc = check_cuda(cudaGetLastError(), what);
+    const int rr = release_held(w, st);
+    return rc != CQ_OK ? rc : rr;
+}
+
+static void destroy_scratch(ScratchBuf &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    if (b.ev) cudaEventDestroy(b.ev);
+    b = ScratchBuf();
+}
+
+void *pool_node_scratch(cq_world *w, size_t warps, cudaStream_t st) {
     size_t bytes = warps * (size_t)2048 /* CQ_NSCAP */ * sizeof(uint2);
     if (bytes > w->nodeScratch[0].cap) {
         // grow all four regions at once (a cudaMalloc inside a timed step costs milliseconds); growing frees the
@@ -51,7 +83,9 @@ void *pool_node_scratch(cq_world *w, size_t warps) {
         for (int k = 0; k < 4; k++)
             if (ensure_scratch(w->nodeScratch[k], bytes) != CQ_OK) return nullptr;
     }
-    return w->nodeScratch[w->nodeSeq++ & 3].ptr;
+    ScratchBuf &b = w->nodeScratch[w->nodeSeq++ & 3];
+    if (scratch_acquire(w, b, st) != CQ_OK) return nullptr;
+    return b.ptr;
 }
 
 static void make_view(cq_world *w) {
@@ -271,13 +305,13 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
 void cq_world_destroy(cq_world *w) {
     if (!w) return;
     cudaSetDevice(w->device);
-    if (w->stream) cudaStreamSynchronize(w->stream);
+    cudaDeviceSynchronize(); // *_device launches may still be in flight on the caller's streams
     for (int s = 0; s < 2; s++) free_set(w->set[s]);
     cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork);
-    cudaFree(w->in.ptr), cudaFree(w->out.ptr), cudaFree(w->aux.ptr), cudaFree(w->aux2.ptr);
-    for (int k = 0; k < 4; k++) cudaFree(w->nodeScratch[k].ptr), cudaFree(w->orderScratch[k].ptr);
-    cudaFree(w->agentScratch.ptr);
-    cudaFree(w->sepScratch.ptr);
+    destroy_scratch(w->in), destroy_scratch(w->out), destroy_scratch(w->aux), destroy_scratch(w->aux2);
+    for (int k = 0; k < 4; k++) destroy_scratch(w->nodeScratch[k]), destroy_scratch(w->orderScratch[k]);
+    destroy_scratch(w->agentScratch);
+    destroy_scratch(w->sepScratch);
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);
     if (w->stream) cudaStreamDestroy(w->stream);

@@ -893,6 +893,7 @@ const uint32_t *make_unit_order(cq_world *w, const void *dUnits, size_t stride, 
         for (int k = 0; k < 4; k++)
             if (ensure_scratch(w->orderScratch[k], words * 4) != CQ_OK) return nullptr;
     }
+    if (scratch_acquire(w, b, st) != CQ_OK) return nullptr;
     uint32_t *keys = (uint32_t *)b.ptr, *vals = keys + n, *keysTmp = vals + n, *valsTmp = keysTmp + n, *scratch = valsTmp + n;
     k_order_keys<<<cdiv(n, 256), 256, 0, st>>>((const unsigned char *)dUnits, stride, positionIsDouble ? 1 : 0, n, w->set[0].hdr,
                                                keys, vals);
@@ -1042,6 +1043,7 @@ int make_agent_grid(cq_world *w, const cq_character_state *dStates, int n, float
         CQ_CUDA(cudaDeviceSynchronize());
         CQ_TRY(ensure_scratch(w->agentScratch, bytes));
     }
+    CQ_TRY(scratch_acquire(w, w->agentScratch, st));
     float4 *pos = (float4 *)w->agentScratch.ptr, *vel = pos + n, *posS = vel + n, *velS = posS + n;
     int4 *rows = (int4 *)(velS + n);
     float4 *firstHit = (float4 *)(rows + 2 * (size_t)n);

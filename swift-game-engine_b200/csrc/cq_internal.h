@@ -51,6 +51,10 @@ struct DeviceSet {
 struct ScratchBuf {
     void *ptr = nullptr;
     size_t cap = 0;
+    // cross-stream reuse guard (scratch_acquire / release_held): completion of the last launch that used the block
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool recorded = false;
 };
 
 } // namespace cq
@@ -85,6 +89,7 @@ struct cq_world {
     cq::ScratchBuf agentScratch; // agent snapshot + grid of the move-and-slide call in flight (CQ_MAS_AGENTS)
     cq::ScratchBuf sepScratch;   // cq_agent_separation working set
     int occSep[2][2] = {};       // resident CTAs per SM of k_sep_turns / k_sep_post ([counting build])
+    std::vector<cq::ScratchBuf *> held; // scratch blocks acquired by the launch being enqueued (release_held)
 };
 
 namespace cq {
@@ -103,12 +108,21 @@ int check_cuda(cudaError_t e, const char *what);
     } while (0)
 
 int ensure_scratch(ScratchBuf &b, size_t bytes);
+// The world's scratch blocks (node stacks, unit order, agent grid, separation state) are shared by successive launches.
+// Launches on ONE stream are ordered by the stream; a launch on ANOTHER stream must wait until the previous user of
+// the block has finished.  scratch_acquire(b, st) inserts that wait and notes the block as held; the launcher calls
+// release_held(w, st) once everything that touches its blocks is enqueued (records the completion events).
+int scratch_acquire(cq_world *w, ScratchBuf &b, cudaStream_t st);
+int release_held(cq_world *w, cudaStream_t st);
+// end of every launcher: pick up the launch error of the kernel just enqueued, then release the held scratch blocks
+int finish_launch(cq_world *w, cudaStream_t st, const char *what);
 #define CQ_WORK_RING 256
 // zeroed work counter for the next persistent-kernel launch on `st` (nullptr on CUDA error)
 int *next_work_counter(cq_world *w, cudaStream_t st);
 // node-stack scratch for one persistent-kernel launch with `warps` warps (CQ_NSCAP uint2 entries per warp);
-// four regions are used round-robin so that up to four launches may be in flight.  nullptr on CUDA error.
-void *pool_node_scratch(cq_world *w, size_t warps);
+// four regions are used round-robin so that up to four launches on different streams run concurrently (a fifth
+// waits for the first, see scratch_acquire).  nullptr on CUDA error.
+void *pool_node_scratch(cq_world *w, size_t warps, cudaStream_t st);
 
 // cq_build.cu
 int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,

@@ -826,7 +826,7 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     if (!work) return CQ_ERR_CUDA;
     blocks = std::min((n + 3) / 4, numSms * blocksPerSm[ci]); // small batches: still fill the machine (>= 4 units per CTA)
     const int opw = pool_owners_per_warp(n, (long long)blocks * MAS_WARPS);
-    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * MAS_WARPS);
+    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * MAS_WARPS, st);
     if (!ns) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_inout, sizeof(cq_character_state), true, n, st);
     if (flags & CQ_MAS_AGENTS) {
@@ -836,7 +836,7 @@ int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const
     }
     kernel<<<blocks, MAS_THREADS, MAS_SMEM_BYTES, st>>>(w->view, d_inout, n, A, opw, ns, work, order, w->dCounters);
     w->launches++;
-    return check_cuda(cudaGetLastError(), "k_move_and_slide");
+    return finish_launch(w, st, "k_move_and_slide");
 }
 
 } // namespace cq

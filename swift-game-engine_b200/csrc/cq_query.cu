@@ -338,7 +338,7 @@ int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, 
     if (w->counting) k_raycast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_rays, n, d_out, work, order, w->dCounters);
     else k_raycast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_rays, n, d_out, work, order, w->dCounters);
     w->launches++;
-    return check_cuda(cudaGetLastError(), "k_raycast");
+    return finish_launch(w, st, "k_raycast");
 }
 
 #undef CQ_OCC_SLOT
@@ -364,12 +364,12 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
     const int opw = pool_owners_per_warp(n, (long long)blocks * CAST_WARPS);
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
-    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS);
+    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS, st);
     if (!ns) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_q, sizeof(cq_capsule_cast), false, n, st);
     kernel<<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, order, w->dCounters);
     w->launches++;
-    return check_cuda(cudaGetLastError(), "k_capsule_cast");
+    return finish_launch(w, st, "k_capsule_cast");
 }
 
 #undef CQ_OCC_SLOT
@@ -398,11 +398,11 @@ static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int ma
     const int opw = pool_owners_per_warp(n, (long long)blocks * CAST_WARPS);
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
-    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS);
+    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS, st);
     if (!ns) return CQ_ERR_CUDA;
     kernel<<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, maxHits, d_out, d_counts, d_overflow, opw, ns, work, w->dCounters);
     w->launches++;
-    return check_cuda(cudaGetLastError(), "k_capsule_overlap_pool");
+    return finish_launch(w, st, "k_capsule_overlap_pool");
 }
 
 int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, cudaStream_t st) {

@@ -637,6 +637,7 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
         CQ_CUDA(cudaDeviceSynchronize());
         CQ_TRY(ensure_scratch(w->sepScratch, bytes));
     }
+    CQ_TRY(scratch_acquire(w, w->sepScratch, st));
     float4 *pos = (float4 *)w->sepScratch.ptr, *vel = pos + n, *orig = vel + n, *posSave = orig + n, *velSave = posSave + n;
     int4 *rows = (int4 *)(velSave + n);
     int2 *cellRaw = (int2 *)(rows + 2 * (size_t)n), *cell0 = cellRaw + n;
@@ -655,7 +656,7 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
     const int postBlocksMax = sep_grid_blocks(w, postKernel, postSmem, w->occSep[1][ci]);
     if (!turnBlocksMax || !postBlocksMax) return CQ_ERR_CUDA;
     const int turnBlocks = std::min(cdiv(n, 4), turnBlocksMax), postBlocks = std::min(cdiv(n, 4), postBlocksMax);
-    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)std::max(turnBlocks, postBlocks) * SEP_WARPS);
+    uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)std::max(turnBlocks, postBlocks) * SEP_WARPS, st);
     if (!ns) return CQ_ERR_CUDA;
 
     const float cellSize = std::max(p.radius * 2 + sepMargin, 0.001f); // SYS:2180 (every agent has the controller radius)
@@ -743,7 +744,7 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
     void *args[] = {(void *)&w->view, (void *)&PA, (void *)&ns, (void *)&work, (void *)&w->dCounters};
     CQ_CUDA(cudaLaunchKernel(postKernel, dim3(postBlocks), dim3(SEP_THREADS), args, postSmem, st));
     w->launches++;
-    return check_cuda(cudaGetLastError(), "agent separation");
+    return finish_launch(w, st, "agent separation");
 }
 
 } // namespace cq

@@ -626,3 +626,49 @@ def test_full_size_c4_terrain_sweeps_properties(cq, orc, scenes):
     assert whole[pick].tobytes() == ref.tobytes()
     g.close()
     o.close()
+
+
+def test_device_entry_points_on_many_streams(cq, scenes):
+    """The *_device twins are asynchronous on the caller's stream and share the world's scratch blocks (node stacks, unit
+    order).  Eight streams each enqueue sweeps, rays and a move-and-slide step on ONE world without any synchronisation
+    in between: more launches in flight than scratch regions (4), so the cross-stream guard of `scratch_acquire` has to
+    order the reuse.  Every stream's results must equal the synchronous host-pointer calls byte for byte."""
+    import torch
+    parts = scenes.mirror_scene(use_hulls=False)
+    g = cq.CollisionQuery(parts)
+    lo, hi = scenes.scene_aabb(parts[1:])
+    dev = torch.device("cuda", 0)
+    n_streams, n = 8, 6000
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    casts = [scenes.gen_casts(n, lo, hi, seed=900 + k, radius=0.4 + 0.1 * k) for k in range(n_streams)]
+    rays = [scenes.gen_rays(4 * n, lo, hi, seed=950 + k) for k in range(n_streams)]
+    chars = []
+    for k in range(n_streams):
+        pos, vel = scenes.gen_c3_characters(n, seed=970 + k)
+        chars.append(cq.init_states(pos, vel))
+
+    def up(a):
+        return torch.from_numpy(np.frombuffer(a.tobytes(), np.uint8).copy()).to(dev)
+
+    d_casts, d_rays, d_chars = [up(a) for a in casts], [up(a) for a in rays], [up(a) for a in chars]
+    d_cast_out = [torch.zeros(n * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    d_ray_out = [torch.zeros(4 * n * cq.RAY_HIT.itemsize, dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    torch.cuda.synchronize()
+    params = cq.default_params()
+    for rep in range(2):  # the second round reuses every scratch region from another stream
+        for k in range(n_streams):
+            s = streams[(k + 3 * rep) % n_streams].cuda_stream
+            g.capsule_cast_device(d_casts[k].data_ptr(), n, cq.CAST_BLOCKING, d_cast_out[k].data_ptr(), s)
+            g.raycast_device(d_rays[k].data_ptr(), 4 * n, d_ray_out[k].data_ptr(), s)
+            if rep == 0:
+                g.move_and_slide_device(d_chars[k].data_ptr(), n, params, stream=s)
+    torch.cuda.synchronize()
+    for k in range(n_streams):
+        want = g.capsuleCastBlocking(casts[k])
+        assert d_cast_out[k].cpu().numpy().tobytes() == want.tobytes(), ("cast", k)
+        assert d_ray_out[k].cpu().numpy().tobytes() == g.raycast(rays[k]).tobytes(), ("ray", k)
+        ref = chars[k].copy()
+        g.move_and_slide(ref, params)
+        assert d_chars[k].cpu().numpy().tobytes() == ref.tobytes(), ("move_and_slide", k)
+        assert (want["triangle_index"] >= 0).sum() > n // 20
+    g.close()
