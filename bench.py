@@ -737,6 +737,25 @@ def run_c5(args):
     hits = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=cq.RAY_HIT)
     algo = n * 64 + 32 * ctr["nodes_visited"] + 52 * ctr["candidates"]
     peak, peak_src = load_peaks()
+    # e2e: the same step through the host-pointer API (refit + cq_raycast_batch, rays and hits in pinned host memory)
+    hr = cq.PinnedArray((n,), cq.RAY)
+    hr.array[:] = rays
+    ho = cq.PinnedArray((n,), cq.RAY_HIT)
+    L = cq.lib()
+
+    def step_host():
+        angle[0] += 1.0
+        rot = sc.quat_mul(sc.quat_angle_axis(np.radians(angle[0]), (0, 1, 0)), base_q)
+        world.update_transforms([mirror_id], [sc.trs_model(base_t, rot, base_s)])
+        rc = L.cq_raycast_batch(world.handle, hr.array.ctypes.data, n, ho.array.ctypes.data)
+        assert rc == 0
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    e2e_s = red(time.perf_counter() - t0, dist.ReduceOp.MAX)
     cpu_baseline = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
@@ -770,7 +789,11 @@ def run_c5(args):
                          "frac": algo / (ray_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "k_raycast", "kernel_ms": ray_ms, "algorithmic_bytes_per_launch": algo,
                          "per_query": {k: ctr[k] / n for k in ("nodes_visited", "candidates")}},
-            "cpu_baseline": cpu_baseline, "e2e": None, "gpu_launches": int(tot_launch), "clocks": clocks}))
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": n * ws * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n * cq.RAY.itemsize * ws,
+                    "d2h_bytes_per_step": n * cq.RAY_HIT.itemsize * ws, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "cq_world_update_transforms + cq_raycast_batch (host pointers, pinned)"},
+            "gpu_launches": int(tot_launch), "clocks": clocks}))
     world.close()
     return 0
 

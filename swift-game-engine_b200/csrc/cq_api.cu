@@ -228,52 +228,31 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
     if ((rc = check_cuda(cudaEventCreate(&w->evA), "event")) != CQ_OK) return fail(rc);
     if ((rc = check_cuda(cudaEventCreate(&w->evB), "event")) != CQ_OK) return fail(rc);
 
-    // host-side assembly of the two sets' input arrays (partitionEntities, CollisionQuery.swift:886-900)
-    std::vector<float4> localPos[2];
-    std::vector<uint32_t> idxIn[2], layerIn[2];
-    std::vector<int32_t> partIn[2];
-    std::vector<int> partTriStart[2]; // per part of the set, then the end
-    std::vector<int> partOfSet[2];
+    // host-side assembly of the two sets' input arrays (partitionEntities, CollisionQuery.swift:886-900): cq_assemble.h
+    SetPlan input[2];
+    std::vector<PartPlacement> place;
+    const PlanError bad = plan_upload(parts, n_parts, input, place);
+    if (bad.code != CQ_OK) {
+        if (bad.kind == 3)
+            set_error("cq_world_create: more than 2^31 vertices or indices in one triangle set (at part %d)", bad.part);
+        else
+            set_error("cq_world_create: part %d has invalid arrays", bad.part);
+        return fail(bad.code);
+    }
     std::vector<float> models((size_t)n_parts * 16);
     std::vector<float4> materials(n_parts);
     w->parts.resize(n_parts);
     for (int p = 0; p < n_parts; p++) {
         const cq_mesh_part &mp = parts[p];
-        if (mp.n_verts < 0 || mp.n_indices < 0 || (mp.n_verts > 0 && !mp.positions_xyz) || (mp.n_indices > 0 && !mp.indices)) {
-            set_error("cq_world_create: part %d has invalid arrays", p);
-            return fail(CQ_ERR_INVALID);
-        }
-        int s = mp.is_dynamic ? 1 : 0;
         PartInfo &pi = w->parts[p];
         pi.entityId = mp.entity_id;
-        pi.set = s;
+        pi.set = place[p].set;
+        pi.vertLo = place[p].vertLo, pi.vertHi = place[p].vertHi;
         pi.material = {mp.mu_s, mp.mu_k, mp.flatten_ground ? 1 : 0};
         pi.layer = mp.layer;
         memcpy(&models[(size_t)p * 16], mp.model, sizeof(float) * 16);
         materials[p] = make_float4(mp.mu_s, mp.mu_k, mp.flatten_ground ? 1.0f : 0.0f, 0.0f);
-        int baseVertex = (int)localPos[s].size();
-        pi.vertLo = baseVertex;
-        for (int v = 0; v < mp.n_verts; v++)
-            localPos[s].push_back(make_float4(mp.positions_xyz[3 * v], mp.positions_xyz[3 * v + 1], mp.positions_xyz[3 * v + 2],
-                                              __builtin_bit_cast(float, (int32_t)p)));
-        pi.vertHi = (int)localPos[s].size();
-        partTriStart[s].push_back((int)layerIn[s].size());
-        partOfSet[s].push_back(p);
-        int nt = mp.n_indices / 3; // `while tri + 2 < count` (CollisionQuery.swift:376)
-        for (int t = 0; t < nt; t++) {
-            for (int k = 0; k < 3; k++) {
-                uint32_t li = mp.indices[3 * t + k];
-                if (li >= (uint32_t)mp.n_verts) {
-                    set_error("cq_world_create: part %d index %u out of range (%d vertices)", p, li, mp.n_verts);
-                    return fail(CQ_ERR_INVALID);
-                }
-                idxIn[s].push_back((uint32_t)baseVertex + li);
-            }
-            layerIn[s].push_back(mp.layer);
-            partIn[s].push_back(p);
-        }
     }
-    for (int s = 0; s < 2; s++) partTriStart[s].push_back((int)layerIn[s].size());
 
     if ((rc = check_cuda(cudaMalloc((void **)&w->dModels, sizeof(float) * 16 * (size_t)std::max(n_parts, 1)), "models")) != CQ_OK)
         return fail(rc);
@@ -288,12 +267,22 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
     }
     w->buildMs = 0.0f; // accumulated by build_set: device time of the build kernels only
     for (int s = 0; s < 2; s++) {
-        rc = build_set(w, w->set[s], localPos[s], idxIn[s], layerIn[s], partIn[s], partTriStart[s]);
+        std::vector<int> &partTriStart = input[s].partTriStart; // in: before the degenerate filter; out: after
+        int badTri = -1;
+        rc = build_set(w, w->set[s], input[s], partTriStart, &badTri);
+        if (rc != CQ_OK && badTri >= 0) { // name the part and the first offending index of that triangle
+            const PartRow &row = input[s].rows[part_row_of(input[s].rows.data(), (int)input[s].rows.size(), badTri, true)];
+            const uint32_t *tri = parts[row.part].indices + 3 * (size_t)(badTri - row.triStart);
+            uint32_t li = tri[0];
+            for (int k = 2; k >= 0; k--)
+                if (tri[k] >= (uint32_t)row.nVerts) li = tri[k];
+            set_error("cq_world_create: part %d index %u out of range (%d vertices)", row.part, li, row.nVerts);
+        }
         if (rc != CQ_OK) return fail(rc);
-        for (size_t k = 0; k < partOfSet[s].size(); k++) {
-            PartInfo &pi = w->parts[partOfSet[s][k]];
-            pi.triLo = partTriStart[s][k];
-            pi.triHi = partTriStart[s][k + 1];
+        for (size_t k = 0; k < input[s].partOfSet.size(); k++) {
+            PartInfo &pi = w->parts[input[s].partOfSet[k]];
+            pi.triLo = partTriStart[k];
+            pi.triHi = partTriStart[k + 1];
         }
     }
     if ((rc = check_cuda(cudaStreamSynchronize(w->stream), "build")) != CQ_OK) return fail(rc);

@@ -39,6 +39,36 @@ __global__ void k_transform(const float4 *__restrict__ local, float4 *__restrict
     world[i] = transform_point(models + 16 * __float_as_int(p.w), p);
 }
 
+// ---- mesh upload, device half (cq_assemble.h): the raw arrays of the parts -> the set's input arrays
+// packed xyz -> float4 (x, y, z, bits(part index)): one vertex per thread, the 12-byte reads of a warp are contiguous
+__global__ void k_expand_verts(const float *__restrict__ raw, int nVerts, const PartRow *__restrict__ rows, int nRows,
+                               float4 *__restrict__ local) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nVerts) return;
+    const int r = part_row_of(rows, nRows, i, false);
+    local[i] = make_float4(raw[3 * (size_t)i], raw[3 * (size_t)i + 1], raw[3 * (size_t)i + 2], __int_as_float(rows[r].part));
+}
+
+// part-local indices -> set-global vertex ids (in place), layer and part word per triangle (CollisionQuery.swift:376-400);
+// an index outside its part's vertex range is clamped (so that nothing downstream reads out of bounds) and reported
+// through errTri = the smallest offending input triangle
+__global__ void k_expand_tris(uint32_t *__restrict__ idx, int nTrisIn, const PartRow *__restrict__ rows, int nRows,
+                              uint32_t *__restrict__ layer, int32_t *__restrict__ part, int *__restrict__ errTri) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTrisIn) return;
+    const PartRow row = rows[part_row_of(rows, nRows, t, true)];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint32_t li = idx[3 * (size_t)t + k];
+        if (li >= (uint32_t)row.nVerts) bad = true, li = 0;
+        idx[3 * (size_t)t + k] = (uint32_t)row.vertLo + li;
+    }
+    layer[t] = row.layer;
+    part[t] = row.part;
+    if (bad) atomicMin(errTri, t);
+}
+
 // keep flag: |cross(e1,e2)|^2 > 1e-10 in WORLD space (CollisionQuery.swift:383-389)
 __global__ void k_filter_flags(const float4 *__restrict__ world, const uint32_t *__restrict__ idxIn, int nTrisIn,
                                uint32_t *__restrict__ flags) {
@@ -731,12 +761,13 @@ template <class Fn> static size_t arena_layout(Fn fn) { // run the carving once 
     return a.off + 256;
 }
 
-int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,
-              const std::vector<uint32_t> &triLayerIn, const std::vector<int32_t> &triPartIn,
-              std::vector<int> &partTriStartIn /* in: first input triangle of each part of this set (+ end), out: filtered */) {
+int build_set(cq_world *w, DeviceSet &S, const SetPlan &in,
+              std::vector<int> &partTriStartIn /* in: first input triangle of each part of this set (+ end), out: filtered */,
+              int *badTriangle /* out: smallest input triangle with an index outside its part's vertices, or -1 */) {
     cudaStream_t st = w->stream;
-    S.nVerts = (int)localPos.size();
-    S.nTrisIn = (int)triLayerIn.size();
+    *badTriangle = -1;
+    S.nVerts = (int)in.nVerts;
+    S.nTrisIn = (int)in.nTris;
     const int nIn = S.nTrisIn;
     const int nCap = std::max(nIn, 1); // nTris (after the filter) <= nIn: size everything by the upper bound
     // ---- persistent arrays
@@ -769,7 +800,10 @@ int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, co
     // ---- temporaries
     uint32_t *dIdxIn, *dLayerIn, *dFlags, *dOffs, *dTileSums, *dTotal, *dKeys, *dKeysTmp, *dValsTmp, *dHist, *dGatherOut;
     int32_t *dPartIn, *dGatherPos;
-    int *dBounds;
+    int *dBounds, *dErrTri;
+    float *dRawPos;
+    PartRow *dRows;
+    const int nRows = (int)in.rows.size();
     const int np = (int)partTriStartIn.size();
     const size_t histWords = (size_t)4 * 256 * cdiv(nCap, RS_TILE) + 4 + 1024 + 1; // classic: 256*tiles; onesweep: 4x + extras
     auto carveTmp = [&](Arena &a) {
@@ -787,23 +821,46 @@ int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, co
         dBounds = a.take<int>(8);
         dGatherPos = a.take<int32_t>(std::max(np, 1));
         dGatherOut = a.take<uint32_t>(std::max(np, 1));
+        dRawPos = a.take<float>((size_t)3 * S.nVerts);
+        dRows = a.take<PartRow>(nRows);
+        dErrTri = a.take<int>(1);
     };
     Arena tmp;
     tmp.cap = arena_layout(carveTmp);
     CQ_CUDA(cudaMalloc((void **)&tmp.base, tmp.cap));
     carveTmp(tmp);
-    auto done = [&](int rc) {
-        cudaFree(tmp.base);
-        return rc;
-    };
-    // ---- upload
-    if (S.nVerts)
-        CQ_CUDA(cudaMemcpyAsync(S.localPos, localPos.data(), sizeof(float4) * (size_t)S.nVerts, cudaMemcpyHostToDevice, st));
+    struct TmpGuard { // the temporaries go away on every path out of this function
+        char *p;
+        ~TmpGuard() { cudaFree(p); }
+    } tmpGuard{tmp.base};
+    auto done = [&](int rc) { return rc; };
+    // ---- upload: the raw arrays as the plan says (large parts from the caller's memory, small ones staged), then expand
+    for (const UploadCopy &c : in.copies) {
+        if (c.kind == 0) {
+            const float *src = c.src ? (const float *)c.src : in.stagedPos.data() + 3 * c.stagedOffset;
+            CQ_CUDA(cudaMemcpyAsync(dRawPos + 3 * c.dstUnit, src, sizeof(float) * 3 * c.nUnits, cudaMemcpyHostToDevice, st));
+        } else {
+            const uint32_t *src = c.src ? (const uint32_t *)c.src : in.stagedIdx.data() + 3 * c.stagedOffset;
+            CQ_CUDA(cudaMemcpyAsync(dIdxIn + 3 * c.dstUnit, src, sizeof(uint32_t) * 3 * c.nUnits, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (nRows) CQ_CUDA(cudaMemcpyAsync(dRows, in.rows.data(), sizeof(PartRow) * (size_t)nRows, cudaMemcpyHostToDevice, st));
+    if (nIn && np) CQ_CUDA(cudaMemcpyAsync(dGatherPos, partTriStartIn.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, st));
+    if (S.nVerts) {
+        k_expand_verts<<<cdiv(S.nVerts, 256), 256, 0, st>>>(dRawPos, S.nVerts, dRows, nRows, S.localPos);
+        w->launches++;
+    }
     if (nIn) {
-        CQ_CUDA(cudaMemcpyAsync(dIdxIn, indicesIn.data(), sizeof(uint32_t) * 3 * (size_t)nIn, cudaMemcpyHostToDevice, st));
-        CQ_CUDA(cudaMemcpyAsync(dLayerIn, triLayerIn.data(), sizeof(uint32_t) * (size_t)nIn, cudaMemcpyHostToDevice, st));
-        CQ_CUDA(cudaMemcpyAsync(dPartIn, triPartIn.data(), sizeof(int32_t) * (size_t)nIn, cudaMemcpyHostToDevice, st));
-        if (np) CQ_CUDA(cudaMemcpyAsync(dGatherPos, partTriStartIn.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, st));
+        int errTri = INT32_MAX;
+        CQ_CUDA(cudaMemcpyAsync(dErrTri, &errTri, sizeof(int), cudaMemcpyHostToDevice, st));
+        k_expand_tris<<<cdiv(nIn, 256), 256, 0, st>>>(dIdxIn, nIn, dRows, nRows, dLayerIn, dPartIn, dErrTri);
+        w->launches++;
+        CQ_CUDA(cudaMemcpyAsync(&errTri, dErrTri, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaStreamSynchronize(st));
+        if (errTri != INT32_MAX) {
+            *badTriangle = errTri;
+            return done(CQ_ERR_INVALID);
+        }
     }
     // ---- kernels (timed: build_ms is device time of the build kernels, uploads and allocations excluded)
     cudaEvent_t e0, e1;

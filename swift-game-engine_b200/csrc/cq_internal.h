@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/cq.h"
+#include "cq_assemble.h"
 #include "cq_world.cuh"
 
 namespace cq {
@@ -125,9 +126,9 @@ int *next_work_counter(cq_world *w, cudaStream_t st);
 void *pool_node_scratch(cq_world *w, size_t warps, cudaStream_t st);
 
 // cq_build.cu
-int build_set(cq_world *w, DeviceSet &S, const std::vector<float4> &localPos, const std::vector<uint32_t> &indicesIn,
-              const std::vector<uint32_t> &triLayerIn, const std::vector<int32_t> &triPartIn,
-              std::vector<int> &keptPerPartPrefix /* out: filtered tri count per input part, by part index */);
+int build_set(cq_world *w, DeviceSet &S, const SetPlan &in /* upload plan of the set, cq_assemble.h */,
+              std::vector<int> &partTriStart /* in: first input triangle of each part of the set (+ end); out: after the filter */,
+              int *badTriangle /* out: smallest input triangle with an out-of-range index (CQ_ERR_INVALID), else -1 */);
 int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx);
 void free_set(DeviceSet &S);
 // Morton-sorted processing order of n work units whose position (3 floats or 3 doubles) sits at the start of each

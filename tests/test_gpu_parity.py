@@ -672,3 +672,56 @@ def test_device_entry_points_on_many_streams(cq, scenes):
         assert d_chars[k].cpu().numpy().tobytes() == ref.tobytes(), ("move_and_slide", k)
         assert (want["triangle_index"] >= 0).sum() > n // 20
     g.close()
+
+
+def test_mesh_upload_many_parts_and_index_errors(cq, orc, scenes):
+    """Mesh upload (csrc/cq_assemble.h + k_expand_verts / k_expand_tris): a world of 400 small parts (staged copies, both
+    sets, empty parts, trailing partial index triples) plus one part above the staging limit (copied straight from the
+    caller's arrays) must give the reference's soup — vertices, indices, layers, part of every triangle — and identical
+    query results; an index outside its part's vertex range is refused with the part and the index named, also when it
+    sits in the dynamic set or deep inside a large part, and leaves no half-built world behind."""
+    rng = np.random.default_rng(31)
+    bv, bi = scenes.box_mesh(1.0)
+    parts = []
+    for k in range(400):
+        pos = tuple(rng.uniform(-20, 20, 3))
+        idx = bi if k % 7 else np.concatenate([bi, bi[:2]])  # a trailing partial triple is ignored
+        v = bv if k % 11 else np.zeros((0, 3), np.float32)   # an entity without vertices ...
+        idx = idx if k % 11 else np.zeros(0, np.uint32)      # ... and without triangles
+        parts.append(scenes.part(v, idx, scenes.trs_model(pos, scale=tuple(rng.uniform(0.5, 3.0, 3))), layer=1 << (k % 5),
+                                 is_dynamic=(k % 3 == 0), entity_id=k))
+    tv, ti, _ = scenes.terrain_mesh(cells=130, cell=0.5)  # 17,161 vertices / 33,800 triangles: above CQ_STAGE_LIMIT
+    parts.insert(200, scenes.part(tv, ti, scenes.trs_model((0, -22, 0)), layer=32, entity_id=1000))
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    for which in (0, 1):
+        a, b = g.read_soup(which), o.read_soup(which)
+        assert a["positions"].tobytes() == b["positions"].tobytes() and np.array_equal(a["indices"], b["indices"])
+        assert np.array_equal(a["layers"], b["layers"]) and np.array_equal(a["parts"], b["parts"])
+    q = scenes.gen_casts(4000, [-20, -22, -20], [20, 20, 20], seed=4, len_range=(0.5, 6.0))
+    q["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 1, 6, 32]), len(q))
+    assert g.capsuleCast(q).tobytes() == o.capsule_cast(q, 0, orc.ORDER_CANONICAL).tobytes()
+    g.close()
+    o.close()
+
+    def refused(bad_parts, part, index, n_verts):
+        with pytest.raises(cq.CQError) as e:
+            cq.CollisionQuery(bad_parts)
+        assert f"part {part} index {index} out of range ({n_verts} vertices)" in str(e.value), str(e.value)
+
+    bad = [dict(p) for p in parts]
+    bad[5]["indices"] = bad[5]["indices"].copy()
+    bad[5]["indices"][4] = 8                      # box: 8 vertices -> 8 is the first invalid index
+    refused(bad, 5, 8, 8)
+    bad = [dict(p) for p in parts]
+    bad[3]["indices"] = bad[3]["indices"].copy()   # part 3 is in the dynamic set
+    bad[3]["indices"][10] = 4_000_000_000
+    refused(bad, 3, 4_000_000_000, 8)
+    bad = [dict(p) for p in parts]
+    bad[200]["indices"] = bad[200]["indices"].copy()
+    bad[200]["indices"][3 * 20_000 + 2] = len(tv)  # deep inside the directly copied part
+    bad[300]["indices"] = bad[300]["indices"].copy()
+    bad[300]["indices"][0] = 99                   # a later part is bad too: the first one is reported
+    refused(bad, 200, len(tv), len(tv))
+    g = cq.CollisionQuery(parts[:3])               # the library is still usable after the refusals
+    assert (g.info()["n_static_triangles"], g.info()["n_dynamic_triangles"]) == (24, 0)  # part 0 is an empty dynamic entity
+    g.close()
