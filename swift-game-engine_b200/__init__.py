@@ -21,7 +21,8 @@ from .service import ActiveChunkSet, CollisionQueryService, chunk_to_world, worl
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libcq.so")
+# CQ_LIB: another build of the same library (A/B runs of kernel variants: tools/ab_e2e.py, bench.py); build() then leaves it alone
+LIB_PATH = os.environ.get("CQ_LIB") or os.path.join(CSRC, "libcq.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "cq.h")
 
 # ---- record layouts of include/cq.h -------------------------------------------------------------
@@ -98,6 +99,8 @@ class CQError(RuntimeError):
 
 def build(force=False, verbose=False):
     """Compile csrc/libcq.so for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
+    if os.environ.get("CQ_LIB"):
+        return LIB_PATH
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
     srcs.append(HEADER)
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)

@@ -29,6 +29,12 @@ namespace cq {
 enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #define CQ_KIND_OVERLAP 3 /* query mode: two-deepest overlap (move-and-slide depenetration) */
 #define CQ_QCAP 256       /* pair-ring entries per warp */
+#ifndef CQ_EVAL_REPS
+#define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
+#endif
+#ifndef CQ_EVAL_KEEP
+#define CQ_EVAL_KEEP 0    /* with CQ_EVAL_REPS > 1: keep evaluating only while this many lanes hold a live pair */
+#endif
 #define CQ_NSCAP 2048     /* node-stack entries per warp (global memory; 32 concurrent walks x depth <= 64) */
 
 struct QShared { // one per owner lane, shared memory: what executors need + the query's result
@@ -505,7 +511,20 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         Commit cm;
         cm.kind = 0;
         bool retired = false;
+#if CQ_EVAL_REPS <= 1
         if (job.phase != PH_NONE) pool_eval<COUNT>(job, wp, cm, retired, ctr);
+#else
+        // Up to CQ_EVAL_REPS evaluations per trip while at least CQ_EVAL_KEEP lanes still hold a live pair: pickup, commit
+        // and the exit vote are then paid once per several evaluations.  Exact: a finished pair keeps its contribution
+        // in `cm` until the commit below, and a stale bestT only delays a prune (the commit compares again).
+#pragma unroll 1
+        for (int rep = 0; rep < CQ_EVAL_REPS; rep++) {
+            const bool go = job.phase != PH_NONE && !retired;
+            const uint32_t live = (uint32_t)__popc(__ballot_sync(0xffffffffu, go));
+            if (live == 0u || (rep > 0 && live < (uint32_t)CQ_EVAL_KEEP)) break;
+            if (go) pool_eval<COUNT>(job, wp, cm, retired, ctr);
+        }
+#endif
         pool_commit(wp, job, cm, retired, lane, ovl);
         if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE) && *wp.ntop == 0u && *wp.tail == *wp.head) break;
     }
