@@ -718,3 +718,97 @@ def test_oracle_soup_and_raycast_match_independent_brute_force(orc, scenes):
         assert ref["triangle_index"][i] == got[1], i
         assert np.float32(got[0]).tobytes() == ref["distance"][i].tobytes(), i
     assert hits > n // 4
+
+
+def test_oracle_reference_order_matches_independent_bvh_and_walks(orc, scenes):
+    """ORDER_REFERENCE — the tree- and order-dependent half of the reference's answers (which triangle wins an exact toi
+    tie, which maxHits overlaps are kept, which grazing ray hits its slab test culls) — against tests/independent_bvh.py:
+    the reference's median-split BVH (CollisionQuery.swift:577-670, preorder numbering, sort fallback), refit (:528-575),
+    and the three stack walks (right child first) transliterated separately.  Same node count, then every query's winner
+    and value bit for bit, before and after a refit of a dynamic and a static part (the refitted tree keeps its topology,
+    so a rebuild would answer differently)."""
+    import independent_bvh as ib
+    rng = np.random.default_rng(2024)
+    parts = scenes.c1_scene()
+    bv, bi = scenes.box_mesh(2.5)
+    q0 = scenes.quat_angle_axis(0.4, (0.2, 1.0, 0.1))
+    parts.append(scenes.part(bv, bi, scenes.trs_model((3.0, -1.5, 5.0), q0), layer=4, is_dynamic=True, entity_id=900))
+    parts.append(scenes.part(bv, bi, scenes.trs_model((-4.0, -2.0, -2.0)), layer=8, is_dynamic=True, entity_id=901))
+    for k, p in enumerate(parts):
+        p["entity_id"] = p.get("entity_id", k)
+    w = orc.OracleWorld(parts)
+    sets = [ib.TriangleSet([p for p in parts if not p["is_dynamic"]]), ib.TriangleSet([p for p in parts if p["is_dynamic"]])]
+    lo, hi = scenes.scene_aabb([p for p in parts[1:]])
+
+    def compare(tag, n_cast, n_cap, n_ray, seed):
+        for which in (0, 1):
+            c = w.counts(which)
+            assert c["triangles"] == len(sets[which].triangles) and c["nodes"] == len(sets[which].bvh.nodes), (tag, which)
+        q = scenes.gen_casts(n_cast, lo, hi, seed=seed, len_range=(0.05, 3.0), expand=1.0)
+        q["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 0xFFFFFFFF, 1, 12, 0xFFFFFFF3]), n_cast)
+        q["min_normal_y"] = 0.5
+        ties = 0
+        for mode, blocking, min_y in ((0, False, None), (1, True, None), (2, False, np.float32(0.5))):
+            ref = w.capsule_cast(q, mode, orc.ORDER_REFERENCE)
+            canon = w.capsule_cast(q, mode, orc.ORDER_CANONICAL)
+            hits = 0
+            for i in range(n_cast):
+                got = ib.capsule_cast(sets[0], sets[1], tuple(q["from"][i]), tuple(q["delta"][i]), q["radius"][i],
+                                      q["half_height"][i], q["mask"][i], blocking, min_y)
+                if got is None:
+                    assert ref["triangle_index"][i] == -1, (tag, mode, i)
+                    continue
+                hits += 1
+                assert ref["triangle_index"][i] == got[4], (tag, mode, i)
+                assert np.float32(got[0]).tobytes() == ref["toi"][i].tobytes(), (tag, mode, i)
+                for field, val in (("position", got[1]), ("normal", got[2]), ("triangle_normal", got[3])):
+                    assert np.float32(val).tobytes() == ref[field][i].tobytes(), (tag, mode, i, field)
+            assert hits > n_cast // 10, (tag, mode)
+            ties += int((ref["triangle_index"] != canon["triangle_index"]).sum())
+        caps = scenes.gen_capsules(n_cap, lo, hi, seed=seed + 1, expand=0.5)
+        caps["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 0xFFFFFFFF, 1, 12]), n_cap)
+        for max_hits in (2, 8):
+            out, counts, overflow = w.capsule_overlap_all(caps, max_hits, orc.ORDER_REFERENCE)
+            assert max_hits != 2 or overflow.sum() > 5, tag  # more overlaps than kept: the visiting order picks the survivors
+            some = 0
+            for i in range(n_cap):
+                got = ib.capsule_overlap_all(sets[0], sets[1], tuple(caps["from"][i]), caps["radius"][i], caps["half_height"][i],
+                                             caps["mask"][i], max_hits)
+                assert counts[i] == len(got), (tag, max_hits, i)
+                some += len(got) > 1
+                # WHICH hits are kept is decided by the visiting order; the oracle then emits them the way the reference's
+                # caller sorts them (Systems.swift:759, depth descending, stable)
+                got = sorted(got, key=lambda h: -float(h[0]))
+                for k, h in enumerate(got):
+                    r = out[i][k]
+                    assert r["triangle_index"] == h[4] and np.float32(h[0]).tobytes() == r["depth"].tobytes(), (tag, max_hits, i, k)
+                    assert np.float32(h[1]).tobytes() == r["position"].tobytes() and np.float32(h[2]).tobytes() == r["normal"].tobytes()
+            assert some > n_cap // 20, (tag, max_hits)
+        rays = scenes.gen_rays(n_ray, lo, hi, seed=seed + 2, max_distance=60.0, expand=2.0)
+        rays["direction"][: n_ray // 8, rng.integers(0, 3)] = 0  # axis-parallel rays: the FLT_MAX inverse of rayAABB
+        rays["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 0xFFFFFFFF, 1, 12]), n_ray)
+        ref = w.raycast(rays, orc.ORDER_REFERENCE)
+        hits = 0
+        for i in range(n_ray):
+            got = ib.raycast(sets[0], sets[1], tuple(rays["origin"][i]), tuple(rays["direction"][i]), rays["max_distance"][i],
+                             rays["mask"][i])
+            if got is None:
+                assert ref["triangle_index"][i] == -1, (tag, i)
+                continue
+            hits += 1
+            assert ref["triangle_index"][i] == got[1] and np.float32(got[0]).tobytes() == ref["distance"][i].tobytes(), (tag, i)
+        assert hits > n_ray // 4, tag
+        return ties
+
+    ties = compare("built", 500, 250, 1200, 11)
+    # refit: the first dynamic box turns and moves, the wall box (static set) slides sideways
+    dyn_parts = [p for p in parts if p["is_dynamic"]]
+    sta_parts = [p for p in parts if not p["is_dynamic"]]
+    m_dyn = scenes.trs_model((2.0, -1.0, 3.5), scenes.quat_angle_axis(1.1, (0.0, 1.0, 0.3)))
+    base_t, base_q, base_s = scenes.transform_from_matrix(sta_parts[1]["model"])
+    m_sta = scenes.trs_model((base_t[0] + 2.5, base_t[1], base_t[2] + 1.0), base_q, base_s)
+    w.update_transforms([dyn_parts[0]["entity_id"], sta_parts[1]["entity_id"]], [m_dyn, m_sta])
+    sets[1].update_transform(0, m_dyn)
+    sets[0].update_transform(1, m_sta)
+    ties += compare("refitted", 400, 200, 800, 21)
+    assert ties > 20  # the scene does produce exact-tie cases, so the visiting order was really exercised
