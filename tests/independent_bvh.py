@@ -256,6 +256,50 @@ def capsule_overlap_all(static, dynamic, frm, radius, half_height, mask, max_hit
     return hits
 
 
+def capsule_overlap_set(s, offset, frm, radius, half_height, mask):
+    """capsuleOverlapBVH (:1119-1199): the deepest overlap; `depth <= bestDepth` is skipped, so the first visited of equally
+    deep triangles stays.  bestDepth starts at 0."""
+    if s.bvh.root < 0:
+        return None
+    up = ind.v(0, 1, 0)
+    a0, b0 = ind.add(frm, ind.mul(up, half_height)), ind.sub(frm, ind.mul(up, half_height))
+    ext = (radius, radius, radius)
+    lo, hi = ind.sub(_vmin(a0, b0), ext), ind.add(_vmax(a0, b0), ext)
+    best, best_depth, stack = None, ZERO, [s.bvh.root]
+    while stack:
+        node = s.bvh.nodes[stack.pop()]
+        if _box_disjoint(node["bounds"], lo, hi):
+            continue
+        if node["left"] >= 0:
+            stack.append(node["left"])
+            stack.append(node["right"])
+            continue
+        for t in _leaf_triangles(s, node):
+            v0, v1, v2, layer = s.tri(t)
+            if (int(layer) & int(mask)) == 0 or _box_disjoint(s.aabbs[t], lo, hi):
+                continue
+            dist, seg_pt, tri_pt = ind.segment_triangle_distance(frm, half_height, v0, v1, v2)
+            if dist >= radius:
+                continue
+            depth = radius - dist
+            if depth <= best_depth:
+                continue
+            tri_normal = ind.normalize(ind.cross(ind.sub(v1, v0), ind.sub(v2, v0)))
+            n = tri_normal if dist < F(1e-6) else ind.normalize(ind.sub(seg_pt, tri_pt))
+            tri_n = ind.neg(tri_normal) if ind.dot(tri_normal, n) < ZERO else tri_normal
+            best_depth, best = depth, (depth, tri_pt, n, tri_n, t + offset)
+    return best
+
+
+def capsule_overlap(static, dynamic, frm, radius, half_height, mask):
+    """capsuleOverlap (:830-850): `a.depth >= b.depth` keeps the static hit."""
+    a = capsule_overlap_set(static, 0, frm, radius, half_height, mask)
+    b = capsule_overlap_set(dynamic, len(static.triangles), frm, radius, half_height, mask)
+    if a is not None and b is not None:
+        return a if a[0] >= b[0] else b
+    return a if a is not None else b
+
+
 def ray_aabb(origin, direction, bounds):
     """rayAABB (:1603-1631): slab test with 1/d, FLT_MAX for a zero component, no tmax < 0 rejection."""
     inv = [ONE / direction[k] if direction[k] != ZERO else FLT_MAX for k in range(3)]

@@ -784,6 +784,19 @@ def test_oracle_reference_order_matches_independent_bvh_and_walks(orc, scenes):
                     assert r["triangle_index"] == h[4] and np.float32(h[0]).tobytes() == r["depth"].tobytes(), (tag, max_hits, i, k)
                     assert np.float32(h[1]).tobytes() == r["position"].tobytes() and np.float32(h[2]).tobytes() == r["normal"].tobytes()
             assert some > n_cap // 20, (tag, max_hits)
+        single = w.capsule_overlap(caps, orc.ORDER_REFERENCE)  # capsuleOverlap: the deepest, first visited of equals
+        deep = 0
+        for i in range(n_cap):
+            got = ib.capsule_overlap(sets[0], sets[1], tuple(caps["from"][i]), caps["radius"][i], caps["half_height"][i],
+                                     caps["mask"][i])
+            if got is None:
+                assert single["triangle_index"][i] == -1, (tag, i)
+                continue
+            deep += 1
+            assert single["triangle_index"][i] == got[4] and np.float32(got[0]).tobytes() == single["depth"][i].tobytes(), (tag, i)
+            for field, val in (("position", got[1]), ("normal", got[2]), ("triangle_normal", got[3])):
+                assert np.float32(val).tobytes() == single[field][i].tobytes(), (tag, i, field)
+        assert deep > n_cap // 10, tag
         rays = scenes.gen_rays(n_ray, lo, hi, seed=seed + 2, max_distance=60.0, expand=2.0)
         rays["direction"][: n_ray // 8, rng.integers(0, 3)] = 0  # axis-parallel rays: the FLT_MAX inverse of rayAABB
         rays["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 0xFFFFFFFF, 1, 12]), n_ray)
