@@ -6,6 +6,7 @@
 // JSON numbers are parsed as doubles and narrowed to float, as Foundation's JSONDecoder does for Float.
 // Parts with invalid positions / no indices are skipped (the reference prints and continues, :53-61);
 // a missing file gives CQ_ERR_IO and malformed JSON CQ_ERR_PARSE where the reference returns nil.
+#include <cctype>
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
@@ -65,6 +66,8 @@ struct Parser {
                 case 'f': out += '\f'; break;
                 case 'u': { // keep BMP code points as UTF-8
                     if (end - p < 5) return fail("bad \\u escape");
+                    for (int k = 1; k <= 4; k++)
+                        if (!isxdigit((unsigned char)p[k])) return fail("bad \\u escape");
                     unsigned cp = (unsigned)strtoul(std::string(p + 1, p + 5).c_str(), nullptr, 16);
                     p += 4;
                     if (cp < 0x80) out += (char)cp;
@@ -89,12 +92,30 @@ struct Parser {
         p++;
         return true;
     }
+    // RFC 8259 number grammar only: -? (0 | [1-9][0-9]*) (. [0-9]+)? ([eE] [+-]? [0-9]+)?  — strtod alone would also take
+    // "inf", "nan", hex floats, a leading '+' or leading zeros, none of which JSONDecoder accepts
     bool parseNumber(double &out) {
+        const char *q = p;
+        if (q < end && *q == '-') q++;
+        if (q >= end || *q < '0' || *q > '9') return fail("expected number");
+        if (*q == '0') q++;
+        else
+            while (q < end && *q >= '0' && *q <= '9') q++;
+        if (q < end && *q == '.') {
+            q++;
+            if (q >= end || *q < '0' || *q > '9') return fail("bad number");
+            while (q < end && *q >= '0' && *q <= '9') q++;
+        }
+        if (q < end && (*q == 'e' || *q == 'E')) {
+            q++;
+            if (q < end && (*q == '+' || *q == '-')) q++;
+            if (q >= end || *q < '0' || *q > '9') return fail("bad number");
+            while (q < end && *q >= '0' && *q <= '9') q++;
+        }
         char *e = nullptr;
-        errno = 0;
-        out = strtod(p, &e);
-        if (e == p) return fail("expected number");
-        p = e;
+        out = strtod(p, &e); // the buffer is NUL-terminated (std::string); the token is a prefix strtod accepts in full
+        if (e != q) return fail("bad number");
+        p = q;
         return true;
     }
     bool parseValue(JValue &v, int depth) {
@@ -145,6 +166,14 @@ struct Parser {
                 v.numericArray = true;
                 while (true) {
                     ws();
+                    if (p < end && *p != '-' && (*p < '0' || *p > '9')) {
+                        // not a plain number array after all (only unknown keys can hold such a thing): carry on generically
+                        v.numericArray = false;
+                        v.items.resize(v.nums.size());
+                        for (size_t k = 0; k < v.nums.size(); k++) v.items[k].kind = JValue::Num, v.items[k].num = v.nums[k];
+                        v.nums.clear();
+                        break;
+                    }
                     double d;
                     if (!parseNumber(d)) return false;
                     v.nums.push_back(d);
@@ -259,8 +288,12 @@ int cq_static_mesh_load(const char *path, cq_static_mesh_asset **out) {
         return CQ_ERR_PARSE;
     }
     ps.ws();
+    if (ps.p != ps.end) { // JSONDecoder: "garbage at end"
+        cq::set_error("StaticMeshLoader: failed to load json: %s (trailing characters after the document)", path);
+        return CQ_ERR_PARSE;
+    }
     const JValue *version = root.get("version"), *meshes = root.get("meshes");
-    if (!version || version->kind != JValue::Num || !meshes || meshes->kind != JValue::Arr || (meshes->numericArray && !meshes->nums.empty())) {
+    if (!version || version->kind != JValue::Num || version->num != std::floor(version->num) /* `let version: Int` */ || !meshes || meshes->kind != JValue::Arr || (meshes->numericArray && !meshes->nums.empty())) {
         cq::set_error("StaticMeshLoader: failed to load json: %s (missing version/meshes)", path);
         return CQ_ERR_PARSE;
     }

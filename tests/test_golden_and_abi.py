@@ -134,6 +134,85 @@ def test_static_mesh_loader_errors(cq, tmp_path):
     assert np.array_equal(a.parts[0]["transform"], np.eye(4, dtype=np.float32).reshape(16))  # identity when not 16 values
 
 
+
+def _doc(positions="[0, 0, 0, 1, 0, 0, 0, 1, 0]", indices="[0, 1, 2]", version="1", extra="", tail=""):
+    return ('{"version": %s, %s"meshes": [{"name": "t", "transform": [], "mesh": {"positions": %s, "normals": [], '
+            '"uvs": [], "indices": %s}}]}%s' % (version, extra, positions, indices, tail))
+
+
+def test_static_mesh_loader_is_strict_json(cq, tmp_path):
+    """JSONDecoder semantics at the edges (StaticMeshLoader.swift:35-42: any decode error -> nil): numbers follow the
+    RFC 8259 grammar (no nan / inf / hex / leading '+' / leading zeros / bare '.'), nothing may follow the document,
+    `version` is an Int, indices are UInt32 — while unknown keys may hold anything, including arrays that start with a
+    number and go on with something else."""
+    f = tmp_path / "d.json"
+
+    def load(text):
+        f.write_text(text)
+        return cq.StaticMeshAsset(str(f))
+
+    for good in (_doc(), _doc(positions="[-0, 0.0, 0e0, 1E+0, 0, 0, 0, 1.0e-0, 0]"),
+                 _doc(extra='"extras": [1, "two", {"three": [3, [4, null, true]]}, -5.5e-1], '),
+                 _doc(extra='"n": null, "s": "a\\u00e9\\n\\"q\\"", "deep": [[[[[[[[1]]]]]]]], '),
+                 "  \n\t" + _doc(tail="  \n ")):
+        a = load(good)
+        assert len(a.parts) == 1 and a.parts[0]["indices"].tolist() == [0, 1, 2]
+    p = load(_doc(positions="[-0, 0.0, 0e0, 1E+0, 0, 0, 0, 1.0e-0, 0]")).parts[0]["positions"]
+    assert p.tolist() == [[0, 0, 0], [1, 0, 0], [0, 1, 0]] and np.signbit(p[0, 0])
+    for bad_number in ("nan", "NaN", "inf", "-inf", "Infinity", "+1", "01", "1.", ".5", "0x10", "1e", "1e+", "-", "1.e3", "--1"):
+        with pytest.raises(cq.CQError, match="-4"):
+            load(_doc(positions="[0, 0, 0, 1, 0, 0, 0, %s, 0]" % bad_number))
+        with pytest.raises(cq.CQError, match="-4"):
+            load(_doc(positions="[%s, 0, 0, 1, 0, 0, 0, 1, 0]" % bad_number))
+    for bad in (_doc(tail="x"), _doc(tail="{}"), _doc(version="1.5"), _doc(version='"1"'), _doc(indices="[0, 1, 2.5]"),
+                _doc(indices="[0, 1, -2]"), _doc(indices="[0, 1, 4294967296]"), _doc(indices='[0, 1, "2"]'),
+                _doc(positions="[0, 0, 0, 1, 0, 0, 0, 1, 0,]"), _doc(positions='"nope"'), _doc(extra='"s": "\\u12G4", '),
+                "[" * 100 + "]" * 100, '{"version": 1, "meshes": [' + "[" * 200 + "]" * 200 + "]}", "", "   ", "nul"):
+        with pytest.raises(cq.CQError, match="-4"):
+            load(bad)
+    assert load(_doc(indices="[0, 1, 4294967295]")).parts[0]["indices"].tolist() == [0, 1, 4294967295]  # the loader does not range-check
+
+
+def test_static_mesh_loader_survives_mutated_documents(cq, tmp_path):
+    """Robustness: 4,000 random byte-level mutations (flips, deletions, insertions of structural characters, truncations)
+    of a valid document either load or fail with CQ_ERR_PARSE — never anything else, never a crash — and whatever loads
+    is self-consistent (whole triangles of in-range floats)."""
+    rng = np.random.default_rng(7)
+    base = _doc(positions="[0.5, -1.25e1, 3, 1, 0, 0, 0, 1, 0, 2, 2, 2]", indices="[0, 1, 2, 2, 1, 3]",
+                extra='"collisionHullsNote": [1, "x"], ').replace(
+        '"indices": [0, 1, 2, 2, 1, 3]}', '"indices": [0, 1, 2, 2, 1, 3], "submeshes": [{"start": 0, "count": 6, "material": "m"}]}, '
+        '"collisionHulls": [{"positions": [0, 0, 0, 1, 0, 0, 0, 1, 0], "indices": [0, 1, 2]}]').encode()
+    f = tmp_path / "m.json"
+    f.write_bytes(base)
+    assert len(cq.StaticMeshAsset(str(f)).parts[0]["hulls"]) == 1
+    alphabet = b'{}[]",:.-+eE0123456789 \\ntu\x00\xff'
+    loaded = 0
+    for _ in range(4000):
+        doc = bytearray(base)
+        for _ in range(int(rng.integers(1, 4))):
+            kind, at = int(rng.integers(0, 4)), int(rng.integers(0, len(doc)))
+            if kind == 0:
+                doc[at] = alphabet[int(rng.integers(0, len(alphabet)))]
+            elif kind == 1:
+                del doc[at:at + int(rng.integers(1, 6))]
+            elif kind == 2:
+                doc[at:at] = bytes([alphabet[int(rng.integers(0, len(alphabet)))]])
+            else:
+                del doc[at:]
+            if not doc:
+                break
+        f.write_bytes(bytes(doc))
+        try:
+            a = cq.StaticMeshAsset(str(f))
+        except cq.CQError as e:
+            assert "libcq error -4" in str(e), str(e)
+            continue
+        loaded += 1
+        for part in a.parts:
+            assert part["positions"].shape[1] == 3 and len(part["positions"]) > 0 and len(part["indices"]) > 0
+    assert 0 < loaded < 4000
+
+
 _GLOO_WORKER = r"""
 import os, sys, importlib
 import numpy as np
