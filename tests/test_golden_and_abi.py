@@ -213,6 +213,49 @@ def test_static_mesh_loader_survives_mutated_documents(cq, tmp_path):
     assert 0 < loaded < 4000
 
 
+
+def test_fbx_regenerator_reproduces_shipped_asset_and_fixtures(cq, scenes, tmp_path):
+    """SURVEY.md §8f-1 (tools/fbx_to_static_mesh.py, build container only — it reads /root/reference): the Blender-free FBX
+    reader reproduces the one asset whose JSON ships (ornate_mirror: 14,246 triangles, local AABB, transform, and — with
+    Blender's quad-flip rule — more than 99.5% of the triangles as the same vertex-position triples), the committed Semla /
+    17-Cheese fixtures are what `--fixtures` generates (shorter-diagonal quads, round-1 files), and the JSON the tool writes
+    goes through the product's own loader unchanged."""
+    if not os.path.exists("/root/reference/ExternalResources/17-Cheese.fbx"):
+        pytest.skip("reference tree not present on this box")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fbx_to_static_mesh as fbx
+    assert fbx.validate_against_mirror()
+    mine = fbx.load_geometry(os.path.join(fbx.REF, "ornate-mirror/source/ornate_mirror.fbx"))[0]
+    ref = json.load(open("/root/reference/Game/ornate_mirror.static.json"))["meshes"][0]
+
+    from scipy.spatial import cKDTree
+    mine_pos = np.asarray(mine["positions"], np.float64).reshape(-1, 3)
+    tree = cKDTree(mine_pos)
+
+    def triangle_keys(pos, idx):  # order-free identity of a triangle: its corners as ids of the nearest regenerated vertex
+        d, ids = tree.query(np.asarray(pos, np.float64).reshape(-1, 3))
+        assert d.max() < 2e-5  # every shipped vertex position exists in the regenerated mesh (JSON text rounding only)
+        return {tuple(sorted(tri)) for tri in ids[np.asarray(idx).reshape(-1, 3)].tolist()}
+    a, b = triangle_keys(mine_pos, mine["indices"]), triangle_keys(ref["mesh"]["positions"], ref["mesh"]["indices"])
+    assert len(a & b) >= 0.995 * len(b), (len(a & b), len(a), len(b))  # the rest: n-gons, which Blender poly-fills
+    for name, rel in (("semla", "semla/source/Semla.fbx"), ("cheese", "17-Cheese.fbx")):
+        part = fbx.load_geometry(os.path.join(fbx.REF, rel), "shorter")
+        dst = tmp_path / (name + ".npz")
+        fbx.save_fixture(part, str(dst))
+        new, old = np.load(dst), np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        assert sorted(new.files) == sorted(old.files)
+        for k in new.files:
+            assert np.array_equal(new[k], old[k]), (name, k)
+    out = tmp_path / "semla.static.json"
+    assert fbx.main([os.path.join(fbx.REF, "semla/source/Semla.fbx"), str(out)]) == 0
+    loaded = cq.StaticMeshAsset(str(out)).parts[0]
+    fixture = scenes.load_asset_fixture("semla")  # same vertices and hulls; the quads' diagonals follow the Blender rule
+    assert np.array_equal(loaded["positions"], fixture["positions"]) and loaded["indices"].shape == fixture["indices"].shape
+    assert len(loaded["hulls"]) == len(fixture["hulls"]) >= 1
+    for (lp, li), (fp, fi) in zip(loaded["hulls"], fixture["hulls"]):
+        assert np.array_equal(lp, fp) and np.array_equal(li, fi)
+
+
 _GLOO_WORKER = r"""
 import os, sys, importlib
 import numpy as np

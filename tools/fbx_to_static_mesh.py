@@ -7,8 +7,9 @@ The reference produces its collision/render assets with a Blender script
 present under ExternalResources/.  This tool reads binary FBX (7.x) directly and emits the same schema
 (StaticMeshLoader.swift:168-197):
 
-  * mesh.positions / indices : FBX-space vertices verbatim, polygons triangulated (fan; for quads the
-    shorter diagonal, which matches Blender's choice on 14,188 of the 14,246 mirror triangles)
+  * mesh.positions / indices : FBX-space vertices verbatim, polygons triangulated (quads by Blender's own
+    quad-flip rule: 14,220 of the 14,246 triangles of the shipped mirror asset come out as the same position
+    triples; n-gons as a fan)
   * transform (row-major)    : Rx(+90 deg) . T . R . S with the centimetre -> metre factor, i.e. what Blender's
     importer puts in matrix_world for a Y-up file (validated against the shipped ornate_mirror.static.json:
     same triangle count, local AABB and transform)
@@ -125,7 +126,21 @@ def _props70(node):
 
 
 # ---------------------------------------------------------------- geometry
-def triangulate(verts, pvi):
+def quad_flips(v0, v1, v2, v3):
+    """Blender's loop-triangle rule for quads (BLI math_geom `is_quad_flip_v3_first_third_fast`, float32): a quad is cut along
+    its first diagonal v0-v2 — triangles (0,1,2) (0,2,3) — unless v1 and v3 lie on the same side of that diagonal
+    (dot(cross(v1-v0, v2-v0), cross(v3-v0, v2-v0)) > 0), in which case it is cut along v1-v3: (0,1,3) (1,2,3)."""
+    v0, v1, v2, v3 = (np.asarray(x, np.float32) for x in (v0, v1, v2, v3))
+    d02 = v2 - v0
+    return bool(np.dot(np.cross(v1 - v0, d02), np.cross(v3 - v0, d02)) > 0)
+
+
+def triangulate(verts, pvi, quad_rule="blender"):
+    """Polygons -> triangles.  quad_rule "blender": the rule above, which reproduces 14,220 of the 14,246 triangles of the
+    shipped ornate_mirror.static.json as the same position triples (the plain first-vertex fan: 14,188; the other 26 are
+    n-gons, which Blender poly-fills).  quad_rule "shorter": the shorter diagonal — what the committed Semla / 17-Cheese
+    fixtures of round 1 were generated with (7,532 of 14,246 on the mirror: same vertices, same surface up to the quads'
+    diagonals); kept so that `--fixtures` reproduces those files byte for byte."""
     tris, poly = [], []
     for idx in pvi:
         if idx < 0:
@@ -135,8 +150,11 @@ def triangulate(verts, pvi):
                 tris.append(poly)
             elif n == 4:
                 a, b, c, d = poly
-                # shorter diagonal (Blender's loop-triangle choice for non-planar quads, most of the time)
-                if np.sum((verts[a] - verts[c]) ** 2) <= np.sum((verts[b] - verts[d]) ** 2):
+                if quad_rule == "shorter":
+                    first = np.sum((verts[a] - verts[c]) ** 2) <= np.sum((verts[b] - verts[d]) ** 2)
+                else:
+                    first = not quad_flips(verts[a], verts[b], verts[c], verts[d])
+                if first:
                     tris += [[a, b, c], [a, c, d]]
                 else:
                     tris += [[a, b, d], [b, c, d]]
@@ -158,7 +176,7 @@ def euler_xyz_deg(r):
     return Rz @ Ry @ Rx  # FBX default rotation order eEulerXYZ
 
 
-def load_geometry(path):
+def load_geometry(path, quad_rule="blender"):
     root, version = read_fbx(path)
     gs = _props70(root.first("GlobalSettings"))
     up_axis = int(gs.get("UpAxis", [1])[0])
@@ -192,7 +210,7 @@ def load_geometry(path):
         else:
             A = np.eye(4)
         world = A @ U @ M
-        parts.append({"name": name, "positions": verts, "indices": triangulate(verts, pvi).reshape(-1),
+        parts.append({"name": name, "positions": verts, "indices": triangulate(verts, pvi, quad_rule).reshape(-1),
                       "transform": world, "up_axis": up_axis, "unit_scale": unit, "fbx_version": version})
     return parts
 
@@ -311,8 +329,10 @@ def validate_against_mirror():
 def main(argv):
     if argv[:1] == ["--fixtures"]:
         assert validate_against_mirror(), "FBX reader does not reproduce the shipped ornate_mirror asset"
-        save_fixture(load_geometry(os.path.join(REF, "semla/source/Semla.fbx")), os.path.join(ROOT, "tests/golden/semla.npz"))
-        save_fixture(load_geometry(os.path.join(REF, "17-Cheese.fbx")), os.path.join(ROOT, "tests/golden/cheese.npz"))
+        # round-1 fixtures: shorter-diagonal quads (see triangulate); regenerate with the Blender rule only together with a
+        # GPU run of the C2 / C5 tests, whose triangle counts and hit-rate thresholds are tied to these files
+        save_fixture(load_geometry(os.path.join(REF, "semla/source/Semla.fbx"), "shorter"), os.path.join(ROOT, "tests/golden/semla.npz"))
+        save_fixture(load_geometry(os.path.join(REF, "17-Cheese.fbx"), "shorter"), os.path.join(ROOT, "tests/golden/cheese.npz"))
         return 0
     if len(argv) != 2:
         print(__doc__)
