@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """Static code-size breakdown of one kernel by source file / function region (needs -lineinfo, which the Makefile passes).
 
-    python tools/sass_breakdown.py swift-game-engine_b200/csrc/cq_mas.o 'k_move_and_slideILb0ELb0ELb0E'
+    python tools/sass_breakdown.py swift-game-engine_b200/csrc/cq_mas.o 'k_move_and_slideILb0ELb0ELb0E' [ncu_source.csv]
 
 Extracts the sm_100a cubin from the object (cuobjdump -xelf), disassembles it with `nvdisasm --print-line-info`, and
 attributes every SASS instruction of the kernel whose mangled name contains the pattern to the innermost frame of its
-inline chain that is not a vector-algebra helper or a CUDA header.  Prints instructions and bytes (16 B each) per source file, per named line range (REGIONS
+inline chain that is not a vector-algebra helper or a CUDA header.  With a third argument — the CSV of
+`ncu -i report.ncu-rep --page source --csv` for the same kernel of the same binary — the per-instruction samples and
+executed counts of the report are joined on and summed per region (the join checks every opcode).  Prints instructions and bytes (16 B each) per source file, per named line range (REGIONS
 below: the pieces DESIGN.md §5.1 talks about), and the opcode mix of each region.  No GPU needed.
 """
 import collections
@@ -34,12 +36,31 @@ REGIONS = [
 ]
 
 
-def main(obj, pattern):
+def load_ncu(path):
+    """Rows of `ncu -i X.ncu-rep --page source --csv` (SASS view) of ONE kernel: per instruction, in address order."""
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr = rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for r in rows[2:]:
+        op = r[col["Source"]].split()
+        op = [t for t in op if not t.startswith("@")]
+        out.append({"op": op[0].split(".")[0] if op else "?", "samples": int(r[col["# Samples"]]),
+                    "inst": int(r[col["Instructions Executed"]]), "thread_inst": int(r[col["Thread Instructions Executed"]]),
+                    "no_inst": int(r[col["stall_no_inst"]]), "long_sb": int(r[col["stall_long_sb"]]),
+                    "wait": int(r[col["stall_wait"]]), "branch": int(r[col["stall_branch_resolving"]])})
+    return out
+
+
+def main(obj, pattern, ncu_csv=None):
     with tempfile.TemporaryDirectory() as tmp:
         subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, stdout=subprocess.DEVNULL)
         cubins = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
         text = subprocess.run(["nvdisasm", "--print-line-info-inline", os.path.join(tmp, cubins[0])], capture_output=True, text=True,
                               check=True).stdout
+    ncu = load_ncu(ncu_csv) if ncu_csv else None
+    dyn = collections.defaultdict(lambda: collections.Counter())
     in_kernel, chain, fresh = False, [("?", 0)], True
     per_file, per_region, mix = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
     total = 0
@@ -80,6 +101,13 @@ def main(obj, pattern):
         per_file[f] += 1
         per_region[label] += 1
         mix[label][op] += 1
+        if ncu is not None:
+            if total > len(ncu) or ncu[total - 1]["op"] != op:
+                sys.exit(f"the profile is not of this binary: instruction {total - 1} is {op} here, "
+                         f"{ncu[total - 1]['op'] if total <= len(ncu) else 'missing'} in the report")
+            for k, v in ncu[total - 1].items():
+                if k != "op":
+                    dyn[label][k] += v
     print(f"kernel matching {pattern!r}: {total} instructions = {total * 16 / 1024:.1f} KB")
     print("\nby source file:")
     for f, n in per_file.most_common():
@@ -90,7 +118,24 @@ def main(obj, pattern):
         print(f"  {n:6d}  {n * 16 / 1024:6.1f} KB  {lab}\n          {top}")
 
 
+    if ncu is not None:
+        if len(ncu) != total:
+            sys.exit(f"the profile is not of this binary: {len(ncu)} instructions in the report, {total} here")
+        tot = collections.Counter()
+        for d in dyn.values():
+            tot.update(d)
+        print("\ndynamic picture from the ncu report (same binary, joined instruction by instruction):")
+        print("  region: share of warp-stall samples | share of executed warp instructions | active lanes per instruction | "
+              "top stall reasons among its samples")
+        for lab, d in sorted(dyn.items(), key=lambda kv: -kv[1]["samples"]):
+            lanes = d["thread_inst"] / d["inst"] if d["inst"] else 0.0
+            s_ = max(d["samples"], 1)
+            print(f"  {100 * d['samples'] / tot['samples']:5.1f}%  {100 * d['inst'] / tot['inst']:5.1f}%  {lanes:5.1f}  {lab}\n"
+                  f"          no_instruction {100 * d['no_inst'] / s_:.0f}%, long_scoreboard {100 * d['long_sb'] / s_:.0f}%, "
+                  f"wait {100 * d['wait'] / s_:.0f}%, branch_resolving {100 * d['branch'] / s_:.0f}%")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) != 3:
+    if len(sys.argv) not in (3, 4):
         sys.exit(__doc__)
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:])
