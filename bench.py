@@ -18,7 +18,6 @@ replicated, no data-path collective (weak scaling); torch.distributed is used fo
 max-over-ranks only.
 """
 import argparse
-import ctypes as C
 import importlib
 import json
 import os
