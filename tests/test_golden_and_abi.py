@@ -313,6 +313,33 @@ def test_header_is_plain_c_and_cpp_mirror_compiles(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def test_native_example_links_and_fails_loudly_without_a_gpu(cq, scenes, tmp_path):
+    """examples/cq_walk.cpp — the boundary used from compiled host code (loader + cpp/CollisionQuery.hpp + libcq.so): it
+    must build and link with a plain g++, load an asset in the reference's schema, and, on a box without a CUDA device,
+    stop with the library's own error (exit 4) instead of computing anything on the CPU.  On a GPU box it runs the walk."""
+    cq.build()
+    exe = tmp_path / "cq_walk"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "examples", "cq_walk.cpp"), "-L" + cq.CSRC,
+                        "-lcq", "-Wl,-rpath," + cq.CSRC, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)], capture_output=True).returncode == 2
+    r = subprocess.run([str(exe), str(tmp_path / "missing.static.json")], capture_output=True, text=True)
+    assert r.returncode == 3 and "missing json" in r.stderr
+    asset = tmp_path / "ornate_mirror.static.json"
+    _write_static_json(str(asset), scenes.load_mirror_fixture())
+    r = subprocess.run([str(exe), str(asset), "256", "3"], capture_output=True, text=True, timeout=300)
+    assert "2 part(s), 78 triangles with the ground plane" in r.stdout
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        assert r.returncode == 0 and "256 characters x 3 steps" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 4 and "cq_world_create: CUDA error" in r.stderr, (r.returncode, r.stderr)
+
+
 class _RecorderWorld:
     """Stands in for the CUDA query object so the service policy can be tested without a GPU."""
     log = []
