@@ -423,3 +423,33 @@ def test_active_chunk_set_drives_rebuilds(cq, scenes):
     assert static == {3, 4, 5, 6, 7}
     acs.radius_chunks = -3  # max(radiusChunks, 0)
     assert acs.update((512.0 * 5, 0.0, 0.0), ents)[1] == {5}
+
+
+def test_transform_helpers_against_scipy(scenes):
+    """TransformComponent.modelMatrix = T * (R(quat) * S) (Components.swift:26-44) and the simd quaternion conventions of
+    SURVEY.md §A.1 as scenes.py restates them (host-only scene-recipe code shared by oracle and GPU): checked against
+    scipy's Rotation — rotation matrices, Hamilton products, angle-axis construction and the matrix -> (T, quat, S) round
+    trip used to re-pose the demo assets."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(17)
+    for _ in range(200):
+        axis = rng.standard_normal(3)
+        axis /= np.linalg.norm(axis)
+        angle = rng.uniform(-np.pi, np.pi)
+        q = scenes.quat_angle_axis(angle, axis)  # (ix, iy, iz, r) like simd_quatf
+        want = Rotation.from_rotvec(axis * angle)
+        assert np.allclose(np.asarray(q, np.float64), want.as_quat(), atol=1e-6) or np.allclose(-np.asarray(q, np.float64), want.as_quat(), atol=1e-6)
+        assert np.allclose(scenes.quat_to_mat3(q), want.as_matrix(), atol=1e-6)
+        q2 = scenes.quat_angle_axis(rng.uniform(-3, 3), (0.0, 1.0, 0.0))
+        prod = scenes.quat_mul(q, q2)
+        assert np.allclose(scenes.quat_to_mat3(prod), want.as_matrix() @ Rotation.from_quat(np.asarray(q2, np.float64)).as_matrix(), atol=1e-5)
+        t, s = rng.uniform(-20, 20, 3), rng.uniform(0.2, 8.0, 3)
+        m = scenes.trs_model(t, q, s).reshape(4, 4).T  # column-major flat -> m[row][col]
+        assert np.allclose(m[:3, :3], want.as_matrix() * s[None, :], atol=1e-5) and np.allclose(m[:3, 3], t, atol=1e-6)
+        assert np.allclose(m[3], [0, 0, 0, 1])
+        t2, q3, s2 = scenes.transform_from_matrix(scenes.trs_model(t, q, s))
+        assert np.allclose(t2, t, atol=1e-5) and np.allclose(s2, s, atol=1e-4)
+        assert np.allclose(scenes.quat_to_mat3(q3), want.as_matrix(), atol=1e-5)
+    # the loader's row-major file order -> simd's column-major (StaticMeshLoader.swift:127-134)
+    rowmajor = np.arange(16, dtype=np.float32)
+    assert np.array_equal(scenes.rowmajor_to_colmajor(rowmajor).reshape(4, 4), rowmajor.reshape(4, 4).T)
