@@ -17,23 +17,55 @@ import subprocess
 import sys
 import tempfile
 
-HELPER_LINES = 52  # cq_math.cuh:1-52 = f3 / d3 algebra (dot, cross, normalize ...): charged to the caller
-# (file suffix, first line, last line, label): line ranges of the current sources; refresh when the files move
-REGIONS = [
-    ("cq_math.cuh", 53, 150, "narrow phase: closest_point_on_triangle, segment_segment_dist2"),
-    ("cq_math.cuh", 151, 234, "narrow phase: vertical-axis specialisations (vseg_segment_dist2, segment-triangle intersect)"),
-    ("cq_math.cuh", 235, 285, "narrow phase: segment_triangle_distance body"),
-    ("cq_math.cuh", 286, 305, "ray_triangle"),
-    ("cq_math.cuh", 306, 10 ** 9, "capsule-capsule CCD (agents)"),
-    ("cq_pool.cuh", 188, 296, "pool: cooperative walk (pool_walk_round)"),
-    ("cq_pool.cuh", 297, 332, "pool: job pickup (pool_take_jobs)"),
-    ("cq_pool.cuh", 333, 410, "pool: pair state machine (pool_eval, without the distance function)"),
-    ("cq_pool.cuh", 411, 470, "pool: commit (pool_commit)"),
-    ("cq_pool.cuh", 471, 10 ** 9, "pool: main loop (pool_run)"),
-    ("cq_pool.cuh", 1, 187, "pool: posting queries (pool_post_*, roots)"),
-    ("cq_world.cuh", 1, 10 ** 9, "cq_world.cuh helpers"),
-    ("cq_mas.cu", 1, 10 ** 9, "controller logic (cq_mas.cu)"),
-]
+# the sources the object was built from (CQ_CSRC overrides: an object of an older commit needs that commit's line numbers)
+CSRC = os.environ.get("CQ_CSRC") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                 "swift-game-engine_b200", "csrc")
+
+
+def _line_of(file, needle):
+    """1-based line of the first line of csrc/<file> that contains `needle` (a function definition), or None."""
+    try:
+        for i, line in enumerate(open(os.path.join(CSRC, file)), 1):
+            if needle in line:
+                return i
+    except OSError:
+        pass
+    return None
+
+
+def _regions():
+    """(file suffix, first line, last line, label): the pieces DESIGN.md §5.1 talks about, located by the definitions
+    that open them so that the table follows the sources as they move."""
+    def cuts(file, marks):  # marks: (needle, label) in file order; a region runs up to the next mark that was found
+        found = [(ln, lab) for ln, lab in ((_line_of(file, nd), lab) for nd, lab in marks) if ln is not None]
+        found.sort()
+        out = []
+        for k, (ln, lab) in enumerate(found):
+            hi = found[k + 1][0] - 1 if k + 1 < len(found) else 10 ** 9
+            out.append((file, ln, hi, lab))
+        if found:
+            out.append((file, 1, found[0][0] - 1, "(head of %s)" % file))
+        return out
+    math = cuts("cq_math.cuh", [
+        ("float closest_point_on_triangle(", "narrow phase: closest_point_on_triangle, segment_segment_dist2"),
+        ("float vseg_segment_dist2(", "narrow phase: vertical-axis specialisations (vseg_segment_dist2, segment-triangle intersect)"),
+        ("float segment_triangle_distance(", "narrow phase: segment_triangle_distance body"),
+        ("bool ray_triangle(", "ray_triangle"),
+        ("bool clamp_interval(", "capsule-capsule CCD (agents)")])
+    pool = cuts("cq_pool.cuh", [
+        ("void pool_push_roots(", "pool: posting queries (pool_post_*, roots)"),
+        ("void pool_walk_round(", "pool: cooperative walk (pool_walk_round)"),
+        ("void pool_take_jobs(", "pool: job pickup (pool_take_jobs)"),
+        ("void pool_eval(", "pool: pair state machine (pool_eval, without the distance function)"),
+        ("struct OverlapTop2", "pool: commit (pool_commit)"),
+        ("void pool_run(", "pool: main loop (pool_run)")])
+    rest = [("cq_world.cuh", 1, 10 ** 9, "cq_world.cuh helpers"), ("cq_mas.cu", 1, 10 ** 9, "controller logic (cq_mas.cu)")]
+    return math + pool + rest
+
+
+REGIONS = _regions()
+# cq_math.cuh up to its first function region = f3 / d3 algebra (dot, cross, normalize ...): charged to the caller
+HELPER_LINES = (_line_of("cq_math.cuh", "float closest_point_on_triangle(") or 53) - 1
 
 
 def load_ncu(path):
