@@ -453,3 +453,29 @@ def test_transform_helpers_against_scipy(scenes):
     # the loader's row-major file order -> simd's column-major (StaticMeshLoader.swift:127-134)
     rowmajor = np.arange(16, dtype=np.float32)
     assert np.array_equal(scenes.rowmajor_to_colmajor(rowmajor).reshape(4, 4), rowmajor.reshape(4, 4).T)
+
+
+def test_sass_breakdown_tool_accounts_for_every_instruction(cq):
+    """tools/sass_breakdown.py (the evidence behind DESIGN.md §10's code-size and per-region tables): on the shipped
+    k_move_and_slide it must find every region by its function definition (no region may silently vanish when the sources
+    move) and its per-region counts must add up to the kernel's instruction count."""
+    import re
+    import shutil
+    if shutil.which("nvdisasm") is None or shutil.which("cuobjdump") is None:
+        pytest.skip("CUDA binary utilities not available")
+    cq.build()
+    obj = os.path.join(cq.CSRC, "cq_mas.o")
+    if not os.path.exists(obj):
+        pytest.skip("object files not kept on this box")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_breakdown.py"), obj, "k_move_and_slideILb0ELb0ELb0E"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    total = int(re.search(r"(\d+) instructions", r.stdout).group(1))
+    by_region = r.stdout.split("by region:")[1]
+    counts = [int(m.group(1)) for m in re.finditer(r"^\s+(\d+)\s+[\d.]+ KB  \S", by_region, re.M)]
+    assert total > 3000 and sum(counts) == total
+    for label in ("controller logic", "pool: posting queries", "pool: cooperative walk", "pool: job pickup", "pool: pair state machine",
+                  "pool: commit", "pool: main loop", "closest_point_on_triangle", "vertical-axis specialisations",
+                  "segment_triangle_distance body"):
+        assert label in by_region, label
+    assert "other:" not in by_region
