@@ -393,6 +393,95 @@ def test_collision_query_service_rebuild_vs_refit_policy(cq, scenes):
     assert _RecorderWorld.log[-1][0] == "build" and _RecorderWorld.log[-1][1] == [0, 1]
 
 
+_CPP_SERVICE_DRIVER = r"""
+#include <cstdio>
+#include "%(hdr)s"
+using namespace cqhost;
+struct Recorder {  // stands in for the CUDA query object (no device needed)
+    explicit Recorder(const std::vector<cq_mesh_part> &parts) {
+        std::printf("build");
+        for (auto &p : parts) std::printf(" %%u:%%d", p.entity_id, (int)p.is_dynamic);
+        std::printf("\n");
+    }
+    bool updateTransforms(const std::vector<uint32_t> &ids, const std::vector<float> &models) {
+        std::printf("refit");
+        for (auto id : ids) std::printf(" %%u", id);
+        std::printf(" | %%.9g %%.9g %%.9g\n", models[12], models[13], models[14]);
+        return true;
+    }
+};
+static const char *name(CollisionQueryServiceT<Recorder>::Action a) {
+    return a == CollisionQueryServiceT<Recorder>::Action::None ? "none" : a == CollisionQueryServiceT<Recorder>::Action::Refit ? "refit" : "rebuild";
+}
+int main() {
+    static const float quad[12] = {-5, 0, -5, 5, 0, -5, 5, 0, 5, -5, 0, 5};
+    static const uint32_t quadIdx[6] = {0, 2, 1, 0, 3, 2};
+    std::vector<MeshEntity> e(4);
+    for (int k = 0; k < 4; k++) e[k].id = k, e[k].positions = quad, e[k].n_verts = 4, e[k].indices = quadIdx, e[k].n_indices = 6;
+    e[0].bodyType = BodyType::Static;
+    e[1].bodyType = BodyType::Kinematic, e[1].translation = {0, 1, 0};
+    e[2].translation = {4, 1, 0};
+    e[3].collides = false;
+    CollisionQueryServiceT<Recorder> svc;
+    auto step = [&](const CollisionQueryServiceT<Recorder>::ActiveSet &a = std::nullopt) { svc.update(e, a); std::printf("-> %%s\n", name(svc.lastAction())); };
+    step();                                   // first update: rebuild
+    step();                                   // nothing changed
+    e[1].translation = {0, 1.5f, 0}; step();  // kinematic platform moved -> dynamic refit
+    e[2].rotation[1] = 0.14943813f, e[2].rotation[3] = 0.98877108f; step();  // body-less entity turned -> static refit
+    e[2].translation = {4, 1.0005f, 0}; step();  // squared delta 2.5e-7 <= 1e-6: below the threshold
+    e[2].dirty = true; step();
+    e[1].bodyType = BodyType::Dynamic; step();
+    e[3].collides = true; step();
+    e[0].n_indices = 3; step();
+    svc.markDirty(); step();
+    step(std::set<uint32_t>{0, 1});           // active set changed -> rebuild with the filtered entities
+    step(std::set<uint32_t>{0, 1});
+    // model matrix of a general TRS and the streaming set
+    MeshEntity t; t.translation = {1.5f, -2.25f, 3.0f}; t.scale = {2.0f, 0.5f, 1.25f};
+    t.rotation[0] = 0.18257419f, t.rotation[1] = 0.36514837f, t.rotation[2] = 0.54772256f, t.rotation[3] = 0.73029674f;
+    float m[16]; modelMatrix(t, m);
+    std::printf("model");
+    for (float v : m) std::printf(" %%.9g", v);
+    std::printf("\n");
+    std::vector<MeshEntity> far(3);
+    far[0].id = 10, far[0].translation = {255.9f, 0, 0};
+    far[1].id = 11, far[1].translation = {1300.0f, 0, 0};
+    far[2].id = 12, far[2].translation = {-1281.0f, 0, 600.0f};
+    const double player[3] = {10.0, 0.0, 0.0};
+    std::printf("active");
+    for (auto id : activeEntityIDs(player, far)) std::printf(" %%u", id);
+    std::printf("\n");
+    return 0;
+}
+"""
+
+
+def test_cpp_service_mirror_makes_the_reference_decisions(cq, scenes, tmp_path):
+    """cpp/CollisionQueryService.hpp — the compiled-language host mirror of SceneServices.swift:33-207 and of the streaming
+    active set: the scenario of the Python policy test above through the C++ class with a recorder in place of the CUDA
+    query object (no device needed), action by action; its modelMatrix against scenes.trs_model; chunk membership."""
+    src = tmp_path / "svc.cpp"
+    src.write_text(_CPP_SERVICE_DRIVER % {"hdr": os.path.join(ROOT, "swift-game-engine_b200", "cpp", "CollisionQueryService.hpp")})
+    exe = tmp_path / "svc"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines()
+    actions = [ln[3:] for ln in out if ln.startswith("-> ")]
+    assert actions == ["rebuild", "none", "refit", "refit", "none", "rebuild", "rebuild", "rebuild", "rebuild", "rebuild", "rebuild", "none"]
+    events = [ln for ln in out if ln.startswith(("build", "refit"))]
+    assert events[0] == "build 0:0 1:1 2:0"                      # entity 3 does not collide; the kinematic body is dynamic
+    assert events[1].startswith("refit 1 |") and events[2].startswith("refit 2 |")
+    assert events[1].split("|")[1].split() == ["0", "1.5", "0"]  # the refit carries the new model matrix
+    assert events[5] == "build 0:0 1:1 2:0 3:0"                  # entity 3 collides now
+    assert events[-1] == "build 0:0 1:1"                         # the active set filters the entities
+    model = np.float32([float(x) for x in next(ln for ln in out if ln.startswith("model")).split()[1:]])
+    want = scenes.trs_model((1.5, -2.25, 3.0), (0.18257419, 0.36514837, 0.54772256, 0.73029674), (2.0, 0.5, 1.25))
+    assert np.allclose(model, want, atol=1e-6)
+    # chunks of 512 m centred on multiples of 512, Chebyshev radius 2 around the player's chunk 0: x = 1300 is chunk 3 (out),
+    # x = -1281 is chunk -3 (out) ... -1281 + 256 = -1025 -> floor(-2.002) = -3
+    assert next(ln for ln in out if ln.startswith("active")).split()[1:] == ["10"]
+
+
 def test_active_chunk_set_drives_rebuilds(cq, scenes):
     """ActiveChunkSystem (Systems.swift:2354-2396) + WorldPosition.fromWorld (Components.swift:58-69): 512 m chunks
     centred on multiples of 512, Chebyshev radius 2; a player crossing a chunk border changes the active set, and the
