@@ -382,6 +382,30 @@ def run_ours(args):
                                pinned.array["position"]))
     grounded_frac = float(pinned.array["grounded"].mean())
     pinned.free()
+    # second e2e leg: the resident crowd (cq_crowd_*): records stay in HBM, a step moves 24 B of velocity in and 56 B of
+    # pose out per character.  Every step uploads the velocities the previous step's pose reported (the host-side
+    # steering systems would edit them in between; the buffer swap below stands for that).
+    crowd_e2e = None
+    if not args.separation:
+        crowd = cq.Crowd(world, np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE).copy())
+        h_vel = cq.PinnedArray((n, 3), np.float64)
+        h_pose = cq.PinnedArray((n,), cq.CROWD_POSE)
+        h_vel.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)["velocity"]
+        crowd.step(h_vel.array, params, DT, GRAVITY, mas_flags, pose_out=h_pose.array)  # warm
+        crowd.write(np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE).copy())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            crowd.step(h_vel.array, params, DT, GRAVITY, mas_flags, pose_out=h_pose.array)
+        crowd_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        crowd_e2e = {"value": n * world_size * e2e_steps / crowd_s, "unit": "queries/s",
+                     "h2d_bytes_per_step": n * 24 * world_size, "d2h_bytes_per_step": n * cq.CROWD_POSE.itemsize * world_size,
+                     "ms_per_step": crowd_s / e2e_steps * 1e3,
+                     "api": "cq_crowd_step (records resident in HBM; velocities in, poses out; pinned host buffers)"}
+        crowd.close()
+        h_vel.free()
+        h_pose.free()
 
     cpu_baseline = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
@@ -428,7 +452,8 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nbytes * world_size,
                     "d2h_bytes_per_step": nbytes * world_size, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "api": "cq_move_and_slide_batch (host pointers, pinned, chunked copy/compute overlap)"},
+                    "api": "cq_move_and_slide_batch (host pointers, pinned, chunked copy/compute overlap)",
+                    "resident_crowd": crowd_e2e},
             "gpu_launches": int(total_launches),
             "clocks": clocks,
         }

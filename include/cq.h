@@ -286,6 +286,41 @@ int cq_move_and_slide_device_ex(cq_world *w, cq_character_state *d_inout, int32_
                                 uint32_t flags, const cq_platform *platforms /* HOST pointer */,
                                 int32_t n_platforms, void *stream);
 
+/* ---- resident crowd ------------------------------------------------------
+ * The full-record calls above move 2 x 168 bytes per character per step across PCIe, which bounds them near 230 M
+ * characters/s per GPU whatever the kernel does.  A crowd keeps the records in HBM between steps — they are private to
+ * KinematicMoveStopSystem in the reference as well (CharacterControllerComponent, the contact-manifold cache) — and a
+ * step exchanges what the rest of the frame exchanges with that system: PhysicsBodyComponent.linearVelocity in (what
+ * GravitySystem / PhysicsIntentSystem left there, Systems.swift:228-233, 603-619), the pose out: 24 + 56 bytes per
+ * character instead of 336.  Results are those of cq_move_and_slide_batch_ex on the same records, bit for bit. */
+typedef struct cq_crowd cq_crowd;
+
+typedef struct cq_crowd_pose {
+    double position[3];
+    double velocity[3];
+    int32_t ground_triangle_index;
+    uint8_t grounded;
+    uint8_t grounded_near;
+    uint8_t ground_sliding;
+    uint8_t _pad;
+} cq_crowd_pose; /* 56 bytes */
+
+/* initial: n full records (host); the crowd lives on the world's device and must be destroyed before the world. */
+int cq_crowd_create(cq_world *w, const cq_character_state *initial, int32_t n, cq_crowd **out);
+void cq_crowd_destroy(cq_crowd *c);
+int32_t cq_crowd_size(const cq_crowd *c);
+/* One fixed step for every character.  velocity_in_xyz: n*3 doubles (host) written into the records first, NULL = keep
+ * the stored velocities; pose_out: n records (host), NULL = nothing is copied back.  Pinned host memory
+ * (cq_host_alloc) gives full PCIe bandwidth; copies and kernels of successive chunks overlap. */
+int cq_crowd_step(cq_crowd *c, const double *velocity_in_xyz, const cq_controller_params *params, float dt,
+                  const float gravity[3], uint32_t flags, const cq_platform *platforms, int32_t n_platforms,
+                  cq_crowd_pose *pose_out);
+/* Full records out of / into the crowd (host pointers, n records). */
+int cq_crowd_read(cq_crowd *c, cq_character_state *out);
+int cq_crowd_write(cq_crowd *c, const cq_character_state *in);
+/* The resident records (device pointer, n records) for the *_device entry points, e.g. cq_agent_separation_device. */
+cq_character_state *cq_crowd_device_states(cq_crowd *c);
+
 /* AgentSeparationSystem.fixedUpdate (Systems.swift:1906-2210) over the batch — every character a solid agent, entity
  * order = index order: `iterations` (reference default 2) sweeps of {rebuild the XZ grid with cell 2r + separation_margin,
  * resolve overlapping pairs SEQUENTIALLY in index order: positional correction split by inverse mass, closing velocity

@@ -46,6 +46,9 @@ STATE = np.dtype([("position", "<f8", 3), ("velocity", "<f8", 3), ("ground_norma
                   ("grounded", "u1"), ("grounded_near", "u1"), ("ground_sliding", "u1"), ("_pad", "u1", 5)])
 assert STATE.itemsize == 168 and CAST.itemsize == 40 and CAST_HIT.itemsize == 44 and RAY.itemsize == 32
 
+CROWD_POSE = np.dtype([("position", "<f8", 3), ("velocity", "<f8", 3), ("ground_triangle_index", "<i4"), ("grounded", "u1"),
+                       ("grounded_near", "u1"), ("ground_sliding", "u1"), ("_pad", "u1")])
+assert CROWD_POSE.itemsize == 56
 PLATFORM = np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("delta", "<f4", 3)])
 CAST_ALL, CAST_BLOCKING, CAST_GROUND = 0, 1, 2
 MAS_APPLY_GRAVITY = 1
@@ -89,6 +92,8 @@ EXPORTS = [
     "cq_move_and_slide_batch", "cq_move_and_slide_device", "cq_move_and_slide_batch_ex",
     "cq_move_and_slide_device_ex", "cq_agent_separation_batch", "cq_agent_separation_device",
     "cq_world_set_counting", "cq_world_read_counters",
+    "cq_crowd_create", "cq_crowd_destroy", "cq_crowd_size", "cq_crowd_step", "cq_crowd_read", "cq_crowd_write",
+    "cq_crowd_device_states",
     "cq_host_alloc", "cq_host_free", "cq_last_error", "cq_version",
 ]
 
@@ -157,6 +162,14 @@ def lib():
         L.cq_move_and_slide_device_ex.argtypes = [vp, vp, i32, vp, f32, vp, u32, vp, i32, vp]
         L.cq_agent_separation_batch.argtypes = [vp, vp, i32, vp, vp, i32, f32, f32, i32]
         L.cq_agent_separation_device.argtypes = [vp, vp, i32, vp, vp, i32, f32, f32, i32, vp]
+        L.cq_crowd_create.argtypes = [vp, vp, i32, C.POINTER(vp)]
+        L.cq_crowd_destroy.argtypes = [vp]
+        L.cq_crowd_size.argtypes = [vp]
+        L.cq_crowd_step.argtypes = [vp, vp, vp, f32, vp, u32, vp, i32, vp]
+        L.cq_crowd_read.argtypes = [vp, vp]
+        L.cq_crowd_write.argtypes = [vp, vp]
+        L.cq_crowd_device_states.argtypes = [vp]
+        L.cq_crowd_device_states.restype = vp
         L.cq_world_set_counting.argtypes = [vp, i32]
         L.cq_world_read_counters.argtypes = [vp, C.POINTER(Counters), i32]
         _lib = L
@@ -423,3 +436,55 @@ class CollisionQuery:
 
     def resetStats(self):
         self.stats(reset=True)
+
+
+class Crowd:
+    """Resident crowd (include/cq.h: cq_crowd_*): the character records live in HBM between steps; `step` moves
+    velocities in and poses out.  Same results as CollisionQuery.move_and_slide on the same records, bit for bit."""
+
+    def __init__(self, world, states):
+        assert states.dtype == STATE and states.flags["C_CONTIGUOUS"]
+        self._world = world  # keeps the world alive: a crowd must be destroyed before its world
+        h = C.c_void_p()
+        _check(lib().cq_crowd_create(world.handle, _ptr(states), len(states), C.byref(h)))
+        self._h = h
+        self.n = len(states)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cq_crowd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, velocity, params, dt=1.0 / 60.0, gravity=(0.0, -98.0, 0.0), flags=MAS_APPLY_GRAVITY, platforms=None,
+             pose_out=None):
+        """velocity: (n, 3) float64 array or None (keep the stored velocities); pose_out: CROWD_POSE array of n records
+        or None.  Returns pose_out."""
+        params = np.ascontiguousarray(params, PARAMS)
+        g = np.asarray(gravity, np.float32)
+        pl = np.ascontiguousarray(platforms if platforms is not None else np.zeros(0, PLATFORM), PLATFORM)
+        if velocity is not None:
+            assert velocity.dtype == np.float64 and velocity.shape == (self.n, 3) and velocity.flags["C_CONTIGUOUS"]
+        if pose_out is not None:
+            assert pose_out.dtype == CROWD_POSE and pose_out.shape == (self.n,) and pose_out.flags["C_CONTIGUOUS"]
+        _check(lib().cq_crowd_step(self._h, None if velocity is None else _ptr(velocity), _ptr(params), C.c_float(dt), _ptr(g),
+                                   flags, _ptr(pl) if len(pl) else None, len(pl), None if pose_out is None else _ptr(pose_out)))
+        return pose_out
+
+    def read(self):
+        out = np.zeros(self.n, STATE)
+        _check(lib().cq_crowd_read(self._h, _ptr(out)))
+        return out
+
+    def write(self, states):
+        assert states.dtype == STATE and states.shape == (self.n,) and states.flags["C_CONTIGUOUS"]
+        _check(lib().cq_crowd_write(self._h, _ptr(states)))
+
+    @property
+    def device_states(self):
+        return lib().cq_crowd_device_states(self._h)

@@ -192,7 +192,10 @@ __global__ void k_agent_first_hit(const cq_character_state *__restrict__ states,
 }
 
 enum { W_NONE = 0, W_DEPEN, W_SLIDE, W_SNAP, W_FALL, W_OFFSET };
-enum { NX_LOAD = 0, NX_DEPEN, NX_SLIDE, NX_SNAP, NX_FALL, NX_GATE, NX_OFFSET, NX_FINISH };
+enum { NX_LOAD = 0, NX_DEPEN, NX_SLIDE, NX_SNAP, NX_FALL, NX_GATE, NX_OFFSET, NX_FINISH, NX_POST };
+#ifndef CQ_SINGLE_POST
+#define CQ_SINGLE_POST 0 /* 1: every sweep of the controller is posted from ONE inlined pool_post_cast (round-2 A/B: code size) */
+#endif
 enum {
     F_WAS_G = 1, F_WAS_GN = 2, F_HAVE_LAST = 4, F_HAVE_CENTER = 8, F_GROUNDED = 16, F_GROUNDED_NEAR = 32,
     F_CAN_SNAP = 64, F_NEAR_GROUND = 128, F_PROBE_HIT = 256, F_DID_RESOLVE = 512
@@ -476,6 +479,11 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
     const cq_controller_params &P = A.p;
     const f3 down = {0.0f, -1.0f, 0.0f};
     int next = NX_LOAD;
+#if CQ_SINGLE_POST
+    f3 postFrom = {0.0f, 0.0f, 0.0f}, postDelta = {0.0f, 0.0f, 0.0f};
+    int postMode = CQ_MODE_ALL, postWait = W_NONE;
+    float postMinY = 0.0f;
+#endif
     // ---------------- consume
     switch (c.wait) {
     case W_DEPEN: { // DepenetrationResolver.resolve loop body after the overlap query (SYS:756-799)
@@ -678,30 +686,47 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             if (c.slideIt >= P.max_slide_iterations || c.slideLen < 1e-6f) { // SYS:1674-1676
                 next = NX_SNAP;
             } else {
+#if CQ_SINGLE_POST
+                postFrom = ld3(c.pos), postDelta = remaining, postMode = CQ_MODE_BLOCKING, postMinY = 0.0f, postWait = W_SLIDE;
+                next = NX_POST;
+#else
                 pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos), remaining, P.radius, P.half_height, P.collision_mask,
                                     CQ_MODE_BLOCKING, 0.0f, ctr);
                 c.wait = W_SLIDE;
                 return true;
+#endif
             }
         }
         if (next == NX_SNAP) {
             if (!(P.snap_distance > 0.0f)) { // SYS:845
                 next = NX_FALL;
             } else {
+#if CQ_SINGLE_POST
+                postFrom = ld3(c.pos), postDelta = down * P.snap_distance, postMode = CQ_MODE_GROUND, postMinY = P.min_ground_dot;
+                postWait = W_SNAP;
+                next = NX_POST;
+#else
                 pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos), down * P.snap_distance, P.radius, P.half_height,
                                     P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
                 c.wait = W_SNAP;
                 return true;
+#endif
             }
         }
         if (next == NX_FALL) {
             if (!(P.fall_probe_distance > 0.0f)) { // SYS:855
                 next = NX_GATE;
             } else {
+#if CQ_SINGLE_POST
+                postFrom = ld3(c.pos), postDelta = down * P.fall_probe_distance, postMode = CQ_MODE_GROUND;
+                postMinY = P.min_ground_dot, postWait = W_FALL;
+                next = NX_POST;
+#else
                 pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos), down * P.fall_probe_distance, P.radius, P.half_height,
                                     P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
                 c.wait = W_FALL;
                 return true;
+#endif
             }
         }
         if (next == NX_GATE) { // validity gates after the centre + fall casts (SYS:868-925)
@@ -743,11 +768,25 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             int oi = c.offsetIt;
             float ox = oi == 0 ? offset : (oi == 1 ? -offset : 0.0f);
             float oz = oi == 2 ? offset : (oi == 3 ? -offset : 0.0f);
+#if CQ_SINGLE_POST
+            postFrom = ld3(c.pos) + mk3(ox, 0.0f, oz), postDelta = down * P.snap_distance, postMode = CQ_MODE_GROUND;
+            postMinY = P.min_ground_dot, postWait = W_OFFSET;
+            next = NX_POST;
+#else
             pool_post_cast<COUNT>(W, wp, lane, s, ld3(c.pos) + mk3(ox, 0.0f, oz), down * P.snap_distance, P.radius, P.half_height,
                                 P.collision_mask, CQ_MODE_GROUND, P.min_ground_dot, ctr);
             c.wait = W_OFFSET;
             return true;
+#endif
         }
+#if CQ_SINGLE_POST
+        if (next == NX_POST) { // the one place a sweep is posted from: pool_post_cast is ~150 instructions per inlined copy
+            pool_post_cast<COUNT>(W, wp, lane, s, postFrom, postDelta, P.radius, P.half_height, P.collision_mask, postMode, postMinY,
+                                  ctr);
+            c.wait = postWait;
+            return true;
+        }
+#endif
         if (next == NX_FINISH) {
             mas_finish(c, W, A, states + c.charIndex, COUNT, ctr.evals);
             next = NX_LOAD;

@@ -32,6 +32,9 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
+#ifndef CQ_EARLY_PICKUP
+#define CQ_EARLY_PICKUP 0 /* 1: a second pickup right after the commit (round-2 A/B: hides the triangle fetch of a fresh pair) */
+#endif
 #ifndef CQ_EVAL_KEEP
 #define CQ_EVAL_KEEP 0    /* with CQ_EVAL_REPS > 1: keep evaluating only while this many lanes hold a live pair */
 #endif
@@ -526,6 +529,12 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         }
 #endif
         pool_commit(wp, job, cm, retired, lane, ovl);
+#if CQ_EARLY_PICKUP
+        // lanes whose pair just retired take their next pair NOW, so that its three triangle loads are in flight across the
+        // loop-back, the exit vote and the front-end test instead of stalling the first evaluation (terrain: 53% of the
+        // pair state machine's stall samples are long-scoreboard waits on exactly those loads)
+        if (*wp.tail != *wp.head) pool_take_jobs(W, wp, job, lane);
+#endif
         if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE) && *wp.ntop == 0u && *wp.tail == *wp.head) break;
     }
 }

@@ -146,6 +146,9 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 // walks the LBVH for it and pushes its candidate triangles into the warp's ring; all 32 lanes execute
 // the (sweep, triangle) pairs, one distance evaluation per trip.
 #define CAST_WARPS (Q_THREADS / 32)
+#ifndef CQ_UNIT_BATCH
+#define CQ_UNIT_BATCH 1 /* > 1: sweeps claimed per atomic by k_capsule_cast, with an L2 prefetch of their records (round-2 A/B) */
+#endif
 #ifndef CAST_MIN_BLOCKS
 #define CAST_MIN_BLOCKS 5 /* 96 registers: +9% on C4 against 4 CTAs/SM (107 registers); 6 CTAs/SM (80) gains nothing */
 #endif
@@ -162,6 +165,9 @@ __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(Wor
     pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS);
     Counters ctr = {0, 0, 0, 0};
     int cur = -1;
+#if CQ_UNIT_BATCH > 1
+    int batchNext = 0, batchEnd = 0; // [batchNext, batchEnd): positions in the processing order this owner has claimed
+#endif
     pool_run<COUNT, STAGED, 8>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         if (cur >= 0) { // write the finished hit
             cq_cast_hit h;
@@ -180,11 +186,31 @@ __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(Wor
             }
             out[cur] = h;
         }
+#if CQ_UNIT_BATCH > 1
+        // claim CQ_UNIT_BATCH sweeps per atomic and start their query records towards L2 right away: the chain
+        // atomic -> order[] -> query record is three dependent long-latency accesses, paid once per sweep on a single lane
+        // (C4: 8% of the kernel's stall samples sit in this fetch + posting, 64-78% of them long-scoreboard waits)
+        if (batchNext == batchEnd) {
+            batchNext = atomicAdd(workCounter, CQ_UNIT_BATCH);
+            batchEnd = min(batchNext + CQ_UNIT_BATCH, n);
+            if (batchNext >= n) {
+                batchNext = batchEnd = 0;
+                cur = -1;
+                return false;
+            }
+            for (int k = batchNext + 1; k < batchEnd; k++) {
+                const int id = order ? (int)order[k] : k;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(qs + id));
+            }
+        }
+        cur = batchNext++;
+#else
         cur = atomicAdd(workCounter, 1); // dynamic fetch of the next sweep
         if (cur >= n) {
             cur = -1;
             return false;
         }
+#endif
         if (order) cur = (int)order[cur]; // Morton-coherent processing order (big worlds)
         cq_capsule_cast c = qs[cur];
         pool_post_cast<COUNT>(W, wp, lane, mine, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,

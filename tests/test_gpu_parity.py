@@ -725,3 +725,60 @@ def test_mesh_upload_many_parts_and_index_errors(cq, orc, scenes):
     g = cq.CollisionQuery(parts[:3])               # the library is still usable after the refusals
     assert (g.info()["n_static_triangles"], g.info()["n_dynamic_triangles"]) == (24, 0)  # part 0 is an empty dynamic entity
     g.close()
+
+
+def test_resident_crowd_matches_full_record_steps(cq, scenes):
+    """cq_crowd_* (records resident in HBM, velocities in / poses out) against cq_move_and_slide_batch_ex on the same
+    records: every pose field after every step and all 168 bytes of every record at the end, bit for bit — with fresh
+    velocities, with kept velocities (NULL), with a pushing platform, with the characters colliding with each other
+    (CQ_MAS_AGENTS: one chunk, a second small crowd) and across the chunked pipeline (CQ_CHUNK-sized pieces on alternating streams)."""
+    parts = scenes.mirror_scene(use_hulls=True)
+    g = cq.CollisionQuery(parts)
+    rng = np.random.default_rng(12)
+    n = 300_000  # three 128 k chunks, the last one ragged
+    pos, vel = scenes.gen_c3_characters(n, seed=77)
+    ref = cq.init_states(pos, vel)
+    crowd = cq.Crowd(g, ref)
+    assert crowd.n == n and crowd.device_states
+    params = cq.default_params()
+    pose = np.zeros(n, cq.CROWD_POSE)
+    plat = np.zeros(1, cq.PLATFORM)
+    plat["aabb_min"], plat["aabb_max"], plat["delta"] = (-12, -3.2, 2), (-8, -2.9, 6), (0.05, 0.0, 0.02)
+    for step in range(6):
+        fresh = step % 3 != 2
+        flags = cq.MAS_APPLY_GRAVITY
+        platforms = plat if step == 3 else None
+        v = None
+        if fresh:  # what PhysicsIntentSystem would do between two steps: steer the current velocity
+            v = np.ascontiguousarray(ref["velocity"] + rng.normal(0.0, 0.5, (n, 3)) * [1.0, 0.0, 1.0])
+            ref["velocity"] = v
+        g.move_and_slide(ref, params, flags=flags, platforms=platforms)
+        crowd.step(v, params, flags=flags, platforms=platforms, pose_out=pose)
+        for f in ("position", "velocity", "ground_triangle_index", "grounded", "grounded_near", "ground_sliding"):
+            assert np.array_equal(pose[f], ref[f]), (step, f)
+    crowd.step(None, params, pose_out=None)  # nothing copied back
+    g.move_and_slide(ref, params)
+    assert crowd.read().tobytes() == ref.tobytes()
+    # write() replaces the records; an empty crowd is a no-op
+    fresh_states = cq.init_states(pos[::-1].copy(), vel[::-1].copy())
+    crowd.write(fresh_states)
+    crowd.step(None, params, pose_out=pose)
+    g.move_and_slide(fresh_states, params)
+    assert np.array_equal(pose["position"], fresh_states["position"]) and crowd.read().tobytes() == fresh_states.tobytes()
+    # characters that collide with each other: the whole crowd is one chunk
+    pos2, vel2 = scenes.gen_c3_characters(600, seed=78)
+    ref2 = cq.init_states(pos2, vel2)
+    crowd2, pose2 = cq.Crowd(g, ref2), np.zeros(600, cq.CROWD_POSE)
+    for step in range(4):
+        v = np.ascontiguousarray(ref2["velocity"] + rng.normal(0.0, 0.5, (600, 3)) * [1.0, 0.0, 1.0])
+        ref2["velocity"] = v
+        g.move_and_slide(ref2, params, flags=cq.MAS_APPLY_GRAVITY | cq.MAS_AGENTS)
+        crowd2.step(v, params, flags=cq.MAS_APPLY_GRAVITY | cq.MAS_AGENTS, pose_out=pose2)
+        assert np.array_equal(pose2["position"], ref2["position"]) and np.array_equal(pose2["velocity"], ref2["velocity"])
+    assert crowd2.read().tobytes() == ref2.tobytes()
+    crowd2.close()
+    empty = cq.Crowd(g, cq.init_states(np.zeros((0, 3), np.float32)))
+    empty.step(None, params)
+    empty.close()
+    crowd.close()
+    g.close()
