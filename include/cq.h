@@ -78,12 +78,43 @@ typedef struct cq_world_info {
     int32_t device;
     float build_ms;              /* device time of upload+filter+Morton+sort+tree+fit */
     float refit_ms;              /* device time of the last cq_world_update_transforms */
+    int32_t order;               /* CQ_ORDER_* the world was created with */
+    float ref_order_ms;          /* host time of the reference-order build (0 in canonical order) */
+    int32_t n_ref_nodes;         /* nodes of the reference's own tree, both sets (0 in canonical order) */
+    int32_t _reserved;
 } cq_world_info;
+
+/* Which of several EXACTLY equal candidates a query names.
+ *
+ * The reference walks its median-split BVH depth-first, right child first, and keeps the first triangle it visits on
+ * exactly equal keys: strict `<` on toi (CollisionQuery.swift:1084) and ray t (:944), strict `>` on depth (:1172);
+ * capsuleOverlapAll returns the first maxHits overlaps it visits (:1272-1274).  About a third of random sweeps against a
+ * closed mesh end on an edge or vertex shared by two triangles and tie bit-exactly, and the move-and-slide contact
+ * cache is keyed by triangle index (Systems.swift:1169-1204), so the choice is visible.
+ *
+ *  CQ_ORDER_REFERENCE (default): the library derives every triangle's visiting rank from the reference's own tree
+ *      (rebuilt on the host at world creation: swift-game-engine_b200/csrc/cq_reftree.h) and resolves ties / keeps the
+ *      first maxHits overlaps by that rank; raycasts walk that tree with the reference's own slab test, so even the
+ *      grazing hits its non-conservative test culls (:933, :1603-1631) come out the same.  Results equal the reference's
+ *      for the same entity order.  Costs host time at creation (about 2 s per 10 M triangles), none per query.
+ *  CQ_ORDER_CANONICAL: tree-independent rule — ties go to the smallest triangle index, capsuleOverlapAll keeps the
+ *      maxHits deepest (deepest first), a raycast returns the nearest triangle over ALL triangles.  No host build. */
+#define CQ_ORDER_REFERENCE 0
+#define CQ_ORDER_CANONICAL 1
+
+typedef struct cq_world_options {
+    int32_t order;        /* CQ_ORDER_* */
+    int32_t _reserved[7]; /* zero */
+} cq_world_options;
+void cq_world_options_default(cq_world_options *o);
 
 /* Replaces CollisionQuery.init(world:activeEntityIDs:) (CollisionQuery.swift:57-59
  * -> StaticTriMesh.init :717-726).  Parts are taken in the given order (the
- * oracle fixes entity order = ascending id; the reference iterates a Dictionary). */
+ * oracle fixes entity order = ascending id; the reference iterates a Dictionary).
+ * A triangle set holds at most 2^26 (67,108,864) triangles after the degenerate filter.
+ * cq_world_create = cq_world_create_ex with default options. */
 int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out);
+int cq_world_create_ex(const cq_mesh_part *parts, int32_t n_parts, const cq_world_options *options, cq_world **out);
 void cq_world_destroy(cq_world *w);
 int cq_world_get_info(const cq_world *w, cq_world_info *info);
 
@@ -179,15 +210,26 @@ typedef struct cq_overlap_hit { /* CapsuleOverlapHit, CollisionQuery.swift:45-52
     int32_t triangle_index; /* -1 = nil */
 } cq_overlap_hit;
 
+/* Per-query flags of the *_ex calls (one byte per query, may be NULL).
+ * CQ_HIT_TIE: another accepted candidate had exactly the winning toi / t / depth, i.e. the triangle named depends on the
+ * world's order rule (the "degenerate edge / vertex ties" of a closed mesh).  CQ_HIT_OVERFLOW: more than max_hits
+ * triangles overlapped (capsuleOverlapAll; the same information as its `overflow` array). */
+#define CQ_HIT_TIE 1
+#define CQ_HIT_OVERFLOW 2
+
 /* Host-pointer, synchronous batch calls (H2D, kernel, D2H inside the call). */
 int cq_raycast_batch(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out);
+int cq_raycast_batch_ex(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out, uint8_t *flags);
+int cq_capsule_cast_batch_ex(cq_world *w, const cq_capsule_cast *q, int32_t n, int32_t mode, cq_cast_hit *out,
+                             uint8_t *flags);
+int cq_capsule_overlap_batch_ex(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out, uint8_t *flags);
 int cq_capsule_cast_batch(cq_world *w, const cq_capsule_cast *q, int32_t n, int32_t mode,
                           cq_cast_hit *out);
 int cq_capsule_overlap_batch(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out);
-/* out = n * max_hits records, sorted deepest first (ties: smaller triangle index);
- * counts[i] = hits written for query i; overflow[i] (may be NULL) = 1 when more than
- * max_hits triangles overlapped (the reference then keeps its first max_hits in DFS
- * order, :1272-1274; this library keeps the deepest).  1 <= max_hits <= 8. */
+/* out = n * max_hits records; counts[i] = hits written for query i; overflow[i] (may be NULL) = 1 when more than
+ * max_hits triangles overlapped.  CQ_ORDER_REFERENCE: the first max_hits triangles the reference visits, in its
+ * visiting order (:1272-1274; its callers sort by depth themselves, Systems.swift:759).  CQ_ORDER_CANONICAL: the
+ * max_hits deepest, deepest first (ties: smaller triangle index).  1 <= max_hits <= 8. */
 int cq_capsule_overlap_all_batch(cq_world *w, const cq_capsule *q, int32_t n, int32_t max_hits,
                                  cq_overlap_hit *out, int32_t *counts, uint8_t *overflow);
 
@@ -206,11 +248,17 @@ int cq_capsule_overlap_device(cq_world *w, const cq_capsule *d_q, int32_t n, cq_
 int cq_capsule_overlap_all_device(cq_world *w, const cq_capsule *d_q, int32_t n, int32_t max_hits,
                                   cq_overlap_hit *d_out, int32_t *d_counts, uint8_t *d_overflow,
                                   void *stream);
+/* with per-query flags (device pointer, n bytes, may be NULL) */
+int cq_raycast_device_ex(cq_world *w, const cq_ray *d_rays, int32_t n, cq_ray_hit *d_out, uint8_t *d_flags, void *stream);
+int cq_capsule_cast_device_ex(cq_world *w, const cq_capsule_cast *d_q, int32_t n, int32_t mode, cq_cast_hit *d_out,
+                              uint8_t *d_flags, void *stream);
+int cq_capsule_overlap_device_ex(cq_world *w, const cq_capsule *d_q, int32_t n, cq_overlap_hit *d_out, uint8_t *d_flags,
+                                 void *stream);
 
 /* ---- move-and-slide ------------------------------------------------------
  * One call = one fixed step of KinematicMoveStopSystem.fixedUpdate's per-entity
- * body (Systems.swift:1842-1901) for n independent characters, without kinematic
- * platforms and agent hits (out of scope). */
+ * body (Systems.swift:1842-1901) for n characters.  Kinematic platforms: the *_ex
+ * variants below; agent hits between the characters: CQ_MAS_AGENTS. */
 
 typedef struct cq_controller_params { /* CharacterControllerComponent tunables, Components.swift:353-404 */
     float radius;               /* 1.5  */

@@ -67,7 +67,16 @@ class WorldInfo(C.Structure):
     _fields_ = [("n_static_triangles", C.c_int32), ("n_dynamic_triangles", C.c_int32),
                 ("n_static_vertices", C.c_int32), ("n_dynamic_vertices", C.c_int32),
                 ("n_static_nodes", C.c_int32), ("n_dynamic_nodes", C.c_int32), ("n_parts", C.c_int32),
-                ("device", C.c_int32), ("build_ms", C.c_float), ("refit_ms", C.c_float)]
+                ("device", C.c_int32), ("build_ms", C.c_float), ("refit_ms", C.c_float), ("order", C.c_int32),
+                ("ref_order_ms", C.c_float), ("n_ref_nodes", C.c_int32), ("_reserved", C.c_int32)]
+
+
+class WorldOptions(C.Structure):
+    _fields_ = [("order", C.c_int32), ("_reserved", C.c_int32 * 7)]
+
+
+ORDER_REFERENCE, ORDER_CANONICAL = 0, 1  # include/cq.h: which of several exactly equal candidates a query names
+HIT_TIE, HIT_OVERFLOW = 1, 2
 
 
 class Material(C.Structure):
@@ -83,11 +92,12 @@ class Counters(C.Structure):
 
 
 EXPORTS = [
-    "cq_world_create", "cq_world_destroy", "cq_world_get_info", "cq_world_update_transforms", "cq_world_read_soup",
+    "cq_world_create", "cq_world_create_ex", "cq_world_options_default", "cq_world_destroy", "cq_world_get_info", "cq_world_update_transforms", "cq_world_read_soup",
     "cq_world_triangle_material", "cq_static_mesh_load", "cq_static_mesh_free", "cq_static_mesh_part_count",
     "cq_static_mesh_part_name", "cq_static_mesh_part_transform", "cq_static_mesh_hull_count",
     "cq_static_mesh_geometry", "cq_raycast_batch", "cq_capsule_cast_batch", "cq_capsule_overlap_batch",
-    "cq_capsule_overlap_all_batch", "cq_raycast_device", "cq_capsule_cast_device", "cq_capsule_overlap_device",
+    "cq_capsule_overlap_all_batch", "cq_raycast_batch_ex", "cq_capsule_cast_batch_ex", "cq_capsule_overlap_batch_ex",
+    "cq_raycast_device_ex", "cq_capsule_cast_device_ex", "cq_capsule_overlap_device_ex", "cq_raycast_device", "cq_capsule_cast_device", "cq_capsule_overlap_device",
     "cq_capsule_overlap_all_device", "cq_controller_params_default", "cq_character_state_init",
     "cq_move_and_slide_batch", "cq_move_and_slide_device", "cq_move_and_slide_batch_ex",
     "cq_move_and_slide_device_ex", "cq_agent_separation_batch", "cq_agent_separation_device",
@@ -132,6 +142,14 @@ def lib():
         L.cq_host_alloc.argtypes = [C.c_size_t]
         L.cq_host_free.argtypes = [vp]
         L.cq_world_create.argtypes = [vp, i32, C.POINTER(vp)]
+        L.cq_world_create_ex.argtypes = [vp, i32, vp, C.POINTER(vp)]
+        L.cq_world_options_default.argtypes = [vp]
+        L.cq_raycast_batch_ex.argtypes = [vp, vp, i32, vp, vp]
+        L.cq_capsule_cast_batch_ex.argtypes = [vp, vp, i32, i32, vp, vp]
+        L.cq_capsule_overlap_batch_ex.argtypes = [vp, vp, i32, vp, vp]
+        L.cq_raycast_device_ex.argtypes = [vp, vp, i32, vp, vp, vp]
+        L.cq_capsule_cast_device_ex.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.cq_capsule_overlap_device_ex.argtypes = [vp, vp, i32, vp, vp, vp]
         L.cq_world_destroy.argtypes = [vp]
         L.cq_world_get_info.argtypes = [vp, C.POINTER(WorldInfo)]
         L.cq_world_update_transforms.argtypes = [vp, vp, vp, i32]
@@ -268,8 +286,11 @@ class CollisionQuery:
     Batch methods take numpy record arrays (host) and return numpy record arrays; `*_device` methods
     take raw device pointers (e.g. torch tensor .data_ptr()) and enqueue on a CUDA stream."""
 
-    def __init__(self, parts):
+    def __init__(self, parts, order=ORDER_REFERENCE):
+        """order: ORDER_REFERENCE (default: exact ties and overlap-all overflow resolved in the reference's own visiting
+        order, raycasts walk the reference's own tree) or ORDER_CANONICAL (tree-independent rule); include/cq.h."""
         self._keep = []
+        self.order = order
         arr = (MeshPart * max(len(parts), 1))()
         for i, p in enumerate(parts):
             pos = np.ascontiguousarray(p["positions"], np.float32).reshape(-1, 3)
@@ -289,7 +310,10 @@ class CollisionQuery:
             arr[i].is_dynamic = int(bool(p.get("is_dynamic", False)))
             arr[i].entity_id = int(p.get("entity_id", i))
         h = C.c_void_p()
-        _check(lib().cq_world_create(C.byref(arr), len(parts), C.byref(h)))
+        opt = WorldOptions()
+        lib().cq_world_options_default(C.byref(opt))
+        opt.order = int(order)
+        _check(lib().cq_world_create_ex(C.byref(arr), len(parts), C.byref(opt), C.byref(h)))
         self._h = h
         self._keep = []
 
@@ -341,32 +365,36 @@ class CollisionQuery:
     updateDynamicTransforms = update_transforms
 
     # raycast(origin:direction:maxDistance:mask:) (CollisionQuery.swift:85)
-    def raycast(self, rays):
+    def raycast(self, rays, with_flags=False):
+        """with_flags: also return the per-query HIT_* flag bytes (cq_raycast_batch_ex)."""
         rays = np.ascontiguousarray(rays, RAY)
         out = np.zeros(len(rays), RAY_HIT)
-        _check(lib().cq_raycast_batch(self._h, _ptr(rays), len(rays), _ptr(out)))
-        return out
+        flags = np.zeros(len(rays), np.uint8)
+        _check(lib().cq_raycast_batch_ex(self._h, _ptr(rays), len(rays), _ptr(out), _ptr(flags) if with_flags else None))
+        return (out, flags) if with_flags else out
 
-    def _cast(self, q, mode):
+    def _cast(self, q, mode, with_flags=False):
         q = np.ascontiguousarray(q, CAST)
         out = np.zeros(len(q), CAST_HIT)
-        _check(lib().cq_capsule_cast_batch(self._h, _ptr(q), len(q), mode, _ptr(out)))
-        return out
+        flags = np.zeros(len(q), np.uint8)
+        _check(lib().cq_capsule_cast_batch_ex(self._h, _ptr(q), len(q), mode, _ptr(out), _ptr(flags) if with_flags else None))
+        return (out, flags) if with_flags else out
 
-    def capsuleCast(self, q):  # CollisionQuery.swift:96
-        return self._cast(q, CAST_ALL)
+    def capsuleCast(self, q, with_flags=False):  # CollisionQuery.swift:96
+        return self._cast(q, CAST_ALL, with_flags)
 
-    def capsuleCastBlocking(self, q):  # CollisionQuery.swift:109
-        return self._cast(q, CAST_BLOCKING)
+    def capsuleCastBlocking(self, q, with_flags=False):  # CollisionQuery.swift:109
+        return self._cast(q, CAST_BLOCKING, with_flags)
 
-    def capsuleCastGround(self, q):  # CollisionQuery.swift:122 (minNormalY = q["min_normal_y"])
-        return self._cast(q, CAST_GROUND)
+    def capsuleCastGround(self, q, with_flags=False):  # CollisionQuery.swift:122 (minNormalY = q["min_normal_y"])
+        return self._cast(q, CAST_GROUND, with_flags)
 
-    def capsuleOverlap(self, q):  # CollisionQuery.swift:137
+    def capsuleOverlap(self, q, with_flags=False):  # CollisionQuery.swift:137
         q = np.ascontiguousarray(q, CAPSULE)
         out = np.zeros(len(q), OVERLAP_HIT)
-        _check(lib().cq_capsule_overlap_batch(self._h, _ptr(q), len(q), _ptr(out)))
-        return out
+        flags = np.zeros(len(q), np.uint8)
+        _check(lib().cq_capsule_overlap_batch_ex(self._h, _ptr(q), len(q), _ptr(out), _ptr(flags) if with_flags else None))
+        return (out, flags) if with_flags else out
 
     def capsuleOverlapAll(self, q, max_hits=8):  # CollisionQuery.swift:148
         q = np.ascontiguousarray(q, CAPSULE)

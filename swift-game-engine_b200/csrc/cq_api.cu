@@ -37,6 +37,15 @@ int ensure_scratch(ScratchBuf &b, size_t bytes) {
     return r;
 }
 
+int check_status(cq_world *w, const char *what) {
+    if (!w->hStatus) return CQ_OK;
+    const unsigned int v = *(volatile unsigned int *)w->hStatus;
+    if (v == 0) return CQ_OK;
+    *(volatile unsigned int *)w->hStatus = 0;
+    set_error("%s: traversal stack overflow on the device (status 0x%x): results of the call are incomplete", what, v);
+    return CQ_ERR_CUDA;
+}
+
 int *next_work_counter(cq_world *w, cudaStream_t st) {
     int *p = w->dWork + (w->workSeq++ % CQ_WORK_RING);
     if (check_cuda(cudaMemsetAsync(p, 0, sizeof(int), st), "work counter") != CQ_OK) return nullptr;
@@ -97,7 +106,13 @@ static void make_view(cq_world *w) {
         v.nodes4 = S.nodes4;
         v.hdr = S.hdr;
         v.triOffset = s == 0 ? 0 : w->set[0].nTris;
+        v.refNodes = S.refNodes;
+        v.refSlot = S.refSlot;
+        v.refHdr = S.refHdr ? S.refHdr : S.hdr; // an empty set has no reference tree: its LBVH header says "empty" too
     }
+    w->view.rank = w->order == CQ_ORDER_REFERENCE ? w->dRank : nullptr;
+    w->view.status = nullptr;
+    if (w->hStatus) cudaHostGetDevicePointer((void **)&w->view.status, w->hStatus, 0);
     w->view.materials = w->dMaterials;
     w->view.nParts = (int)w->parts.size();
     w->view.stagedLeaves = (w->set[0].nTris + w->set[1].nTris) >= 4096 ? 1 : 0;
@@ -114,9 +129,25 @@ using namespace cq;
 // PCIe is full duplex, so the wall time approaches max(H2D, kernels, D2H) instead of their sum.
 // Chunking adapts to the previous call of the same entry point: when that call was compute-bound (wall time
 // >> PCIe time of its bytes) the next one uses two chunks only, because every chunk kernel pays its own tail.
+// leave no copy in flight on the caller's memory when a batch call fails half-way
+static int fail_batch(cq_world *w, int rc) {
+    cudaStreamSynchronize(w->h2dStream);
+    cudaStreamSynchronize(w->copyStream[0]);
+    cudaStreamSynchronize(w->copyStream[1]);
+    cudaStreamSynchronize(w->d2hStream);
+    return rc;
+}
+#define CQ_CUDA_B(x)                                   \
+    do {                                               \
+        int _r = cq::check_cuda((x), #x);              \
+        if (_r != CQ_OK) return fail_batch(w, _r);     \
+    } while (0)
+
+// flagsHost (may be null): one byte per unit, produced by the launch into w->aux2 at the unit's index
 template <class In, class Out, class Launch>
 static int run_batch(cq_world *w, const In *in, size_t inStride, Out *out, size_t outStride, int n, Launch launch,
-                     bool inPlace = false, float *computeBoundHint = nullptr, bool singleChunk = false) {
+                     bool inPlace = false, float *computeBoundHint = nullptr, bool singleChunk = false,
+                     uint8_t *flagsHost = nullptr) {
     if (n <= 0) return CQ_OK;
     CQ_CUDA(cudaSetDevice(w->device));
     static const int CH = [] { // units per chunk of the copy/compute pipeline (CQ_CHUNK overrides, for tuning)
@@ -133,24 +164,29 @@ static int run_batch(cq_world *w, const In *in, size_t inStride, Out *out, size_
     int r;
     if ((r = ensure_scratch(w->in, (size_t)n * inStride)) != CQ_OK) return r;
     if (!inPlace && (r = ensure_scratch(w->out, (size_t)n * outStride)) != CQ_OK) return r;
+    if (flagsHost && (r = ensure_scratch(w->aux2, (size_t)n)) != CQ_OK) return r;
     int k = 0;
     for (int lo = 0; lo < n; lo += chunk, k++) {
         int cnt = std::min(chunk, n - lo);
         cudaStream_t cs = w->copyStream[k & 1]; // compute streams
         char *dIn = (char *)w->in.ptr + (size_t)lo * inStride;
         char *dOut = inPlace ? dIn : (char *)w->out.ptr + (size_t)lo * outStride;
-        CQ_CUDA(cudaMemcpyAsync(dIn, (const char *)in + (size_t)lo * inStride, (size_t)cnt * inStride, cudaMemcpyHostToDevice,
-                                w->h2dStream));
-        CQ_CUDA(cudaEventRecord(w->evIn[k], w->h2dStream));
-        CQ_CUDA(cudaStreamWaitEvent(cs, w->evIn[k], 0));
+        CQ_CUDA_B(cudaMemcpyAsync(dIn, (const char *)in + (size_t)lo * inStride, (size_t)cnt * inStride, cudaMemcpyHostToDevice,
+                                  w->h2dStream));
+        CQ_CUDA_B(cudaEventRecord(w->evIn[k], w->h2dStream));
+        CQ_CUDA_B(cudaStreamWaitEvent(cs, w->evIn[k], 0));
         r = launch(dIn, dOut, cnt, lo, cs);
-        if (r != CQ_OK) return r;
-        CQ_CUDA(cudaEventRecord(w->evDone[k], cs));
-        CQ_CUDA(cudaStreamWaitEvent(w->d2hStream, w->evDone[k], 0));
-        CQ_CUDA(cudaMemcpyAsync((char *)out + (size_t)lo * outStride, dOut, (size_t)cnt * outStride, cudaMemcpyDeviceToHost,
-                                w->d2hStream));
+        if (r != CQ_OK) return fail_batch(w, r);
+        CQ_CUDA_B(cudaEventRecord(w->evDone[k], cs));
+        CQ_CUDA_B(cudaStreamWaitEvent(w->d2hStream, w->evDone[k], 0));
+        CQ_CUDA_B(cudaMemcpyAsync((char *)out + (size_t)lo * outStride, dOut, (size_t)cnt * outStride, cudaMemcpyDeviceToHost,
+                                  w->d2hStream));
+        if (flagsHost)
+            CQ_CUDA_B(cudaMemcpyAsync(flagsHost + lo, (const uint8_t *)w->aux2.ptr + lo, (size_t)cnt, cudaMemcpyDeviceToHost,
+                                      w->d2hStream));
     }
     CQ_CUDA(cudaStreamSynchronize(w->d2hStream));
+    CQ_TRY(check_status(w, "batch call"));
     if (computeBoundHint) {
         double wallMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         double pcieMs = (double)n * (double)std::max(inStride, outStride) / 50.0e6; // ~50 GB/s per direction, duplex
@@ -200,16 +236,34 @@ void cq_character_state_init(cq_character_state *s, const float position[3], con
     s->ground_triangle_index = -1;
 }
 
+void cq_world_options_default(cq_world_options *o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->order = CQ_ORDER_REFERENCE;
+}
+
 int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) {
+    return cq_world_create_ex(parts, n_parts, nullptr, out);
+}
+
+int cq_world_create_ex(const cq_mesh_part *parts, int32_t n_parts, const cq_world_options *options, cq_world **out) {
     if (!out || n_parts < 0 || (n_parts > 0 && !parts)) {
         set_error("cq_world_create: invalid arguments");
         return CQ_ERR_INVALID;
     }
     *out = nullptr;
+    cq_world_options opt;
+    cq_world_options_default(&opt);
+    if (options) opt = *options;
+    if (opt.order != CQ_ORDER_REFERENCE && opt.order != CQ_ORDER_CANONICAL) {
+        set_error("cq_world_create: unknown order %d", opt.order);
+        return CQ_ERR_INVALID;
+    }
     int dev = 0;
     CQ_CUDA(cudaGetDevice(&dev));
     cq_world *w = new cq_world();
     w->device = dev;
+    w->order = opt.order;
     int rc = CQ_OK;
     auto fail = [&](int r) {
         cq_world_destroy(w);
@@ -261,6 +315,9 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
     if ((rc = check_cuda(cudaMalloc((void **)&w->dCounters, sizeof(unsigned long long) * 4), "counters")) != CQ_OK) return fail(rc);
     cudaMemsetAsync(w->dCounters, 0, sizeof(unsigned long long) * 4, w->stream);
     if ((rc = check_cuda(cudaMalloc((void **)&w->dWork, sizeof(int) * CQ_WORK_RING), "work counters")) != CQ_OK) return fail(rc);
+    if ((rc = check_cuda(cudaHostAlloc((void **)&w->hStatus, sizeof(unsigned int), cudaHostAllocMapped), "status word")) != CQ_OK)
+        return fail(rc);
+    *w->hStatus = 0;
     if (n_parts) {
         cudaMemcpyAsync(w->dModels, models.data(), sizeof(float) * 16 * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
         cudaMemcpyAsync(w->dMaterials, materials.data(), sizeof(float4) * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
@@ -286,6 +343,7 @@ int cq_world_create(const cq_mesh_part *parts, int32_t n_parts, cq_world **out) 
         }
     }
     if ((rc = check_cuda(cudaStreamSynchronize(w->stream), "build")) != CQ_OK) return fail(rc);
+    if (w->order == CQ_ORDER_REFERENCE && (rc = attach_ref_order(w)) != CQ_OK) return fail(rc);
     make_view(w);
     *out = w;
     return CQ_OK;
@@ -296,7 +354,8 @@ void cq_world_destroy(cq_world *w) {
     cudaSetDevice(w->device);
     cudaDeviceSynchronize(); // *_device launches may still be in flight on the caller's streams
     for (int s = 0; s < 2; s++) free_set(w->set[s]);
-    cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork);
+    cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork), cudaFree(w->dRank);
+    if (w->hStatus) cudaFreeHost(w->hStatus);
     destroy_scratch(w->in), destroy_scratch(w->out), destroy_scratch(w->aux), destroy_scratch(w->aux2);
     for (int k = 0; k < 4; k++) destroy_scratch(w->nodeScratch[k]), destroy_scratch(w->orderScratch[k]);
     destroy_scratch(w->agentScratch);
@@ -327,6 +386,10 @@ int cq_world_get_info(const cq_world *w, cq_world_info *info) {
     info->device = w->device;
     info->build_ms = w->buildMs;
     info->refit_ms = w->refitMs;
+    info->order = w->order;
+    info->ref_order_ms = w->refBuildMs;
+    info->n_ref_nodes = w->set[0].nRefInternal + w->set[0].nRefLeaves + w->set[1].nRefInternal + w->set[1].nRefLeaves;
+    info->_reserved = 0;
     return CQ_OK;
 }
 
@@ -337,6 +400,14 @@ int cq_world_update_transforms(cq_world *w, const uint32_t *entity_ids, const fl
     // must have finished reading the old boxes first.
     CQ_CUDA(cudaDeviceSynchronize());
     std::vector<int> changed[2];
+    for (int i = 0; i < n; i++) { // validate every id before anything is queued: a failed call changes nothing
+        bool known = false;
+        for (size_t p = 0; p < w->parts.size() && !known; p++) known = w->parts[p].entityId == entity_ids[i];
+        if (!known) {
+            set_error("cq_world_update_transforms: unknown entity id %u", entity_ids[i]);
+            return CQ_ERR_NOT_FOUND;
+        }
+    }
     for (int i = 0; i < n; i++) {
         bool found = false;
         for (size_t p = 0; p < w->parts.size(); p++) {
@@ -425,6 +496,7 @@ int cq_world_read_counters(cq_world *w, cq_counters *out, int32_t reset) {
     unsigned long long h[4];
     CQ_CUDA(cudaStreamSynchronize(w->stream));
     CQ_CUDA(cudaMemcpy(h, w->dCounters, sizeof(h), cudaMemcpyDeviceToHost));
+    CQ_TRY(check_status(w, "cq_world_read_counters"));
     out->nodes_visited = h[0];
     out->candidates = h[1];
     out->distance_evals = h[2];
@@ -440,17 +512,28 @@ int cq_world_read_counters(cq_world *w, cq_counters *out, int32_t reset) {
 // ---------------------------------------------------------------- device-pointer entry points
 static cudaStream_t pick_stream(cq_world *w, void *stream) { return stream ? (cudaStream_t)stream : w->stream; }
 
-int cq_raycast_device(cq_world *w, const cq_ray *d_rays, int32_t n, cq_ray_hit *d_out, void *stream) {
+int cq_raycast_device_ex(cq_world *w, const cq_ray *d_rays, int32_t n, cq_ray_hit *d_out, uint8_t *d_flags, void *stream) {
     if (!w || n < 0 || (n > 0 && (!d_rays || !d_out))) return CQ_ERR_INVALID;
-    return launch_raycast(w, d_rays, n, d_out, pick_stream(w, stream));
+    return launch_raycast(w, d_rays, n, d_out, d_flags, pick_stream(w, stream));
+}
+int cq_raycast_device(cq_world *w, const cq_ray *d_rays, int32_t n, cq_ray_hit *d_out, void *stream) {
+    return cq_raycast_device_ex(w, d_rays, n, d_out, nullptr, stream);
+}
+int cq_capsule_cast_device_ex(cq_world *w, const cq_capsule_cast *d_q, int32_t n, int32_t mode, cq_cast_hit *d_out,
+                              uint8_t *d_flags, void *stream) {
+    if (!w || n < 0 || mode < 0 || mode > 2 || (n > 0 && (!d_q || !d_out))) return CQ_ERR_INVALID;
+    return launch_cast(w, d_q, n, mode, d_out, d_flags, pick_stream(w, stream));
 }
 int cq_capsule_cast_device(cq_world *w, const cq_capsule_cast *d_q, int32_t n, int32_t mode, cq_cast_hit *d_out, void *stream) {
-    if (!w || n < 0 || mode < 0 || mode > 2 || (n > 0 && (!d_q || !d_out))) return CQ_ERR_INVALID;
-    return launch_cast(w, d_q, n, mode, d_out, pick_stream(w, stream));
+    return cq_capsule_cast_device_ex(w, d_q, n, mode, d_out, nullptr, stream);
+}
+int cq_capsule_overlap_device_ex(cq_world *w, const cq_capsule *d_q, int32_t n, cq_overlap_hit *d_out, uint8_t *d_flags,
+                                 void *stream) {
+    if (!w || n < 0 || (n > 0 && (!d_q || !d_out))) return CQ_ERR_INVALID;
+    return launch_overlap(w, d_q, n, d_out, d_flags, pick_stream(w, stream));
 }
 int cq_capsule_overlap_device(cq_world *w, const cq_capsule *d_q, int32_t n, cq_overlap_hit *d_out, void *stream) {
-    if (!w || n < 0 || (n > 0 && (!d_q || !d_out))) return CQ_ERR_INVALID;
-    return launch_overlap(w, d_q, n, d_out, pick_stream(w, stream));
+    return cq_capsule_overlap_device_ex(w, d_q, n, d_out, nullptr, stream);
 }
 int cq_capsule_overlap_all_device(cq_world *w, const cq_capsule *d_q, int32_t n, int32_t max_hits, cq_overlap_hit *d_out,
                                   int32_t *d_counts, uint8_t *d_overflow, void *stream) {
@@ -473,32 +556,46 @@ int cq_move_and_slide_device(cq_world *w, cq_character_state *d_inout, int32_t n
     return cq_move_and_slide_device_ex(w, d_inout, n, params, dt, gravity, flags, nullptr, 0, stream);
 }
 
-int cq_raycast_batch(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out) {
+int cq_raycast_batch_ex(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out, uint8_t *flags) {
     if (!w || n < 0 || (n > 0 && (!rays || !out))) return CQ_ERR_INVALID;
     CQ_CUDA(cudaStreamSynchronize(w->stream));
     return run_batch(w, rays, sizeof(cq_ray), out, sizeof(cq_ray_hit), n,
-                     [&](void *di, void *dout, int cnt, int, cudaStream_t st) {
-                         return launch_raycast(w, (const cq_ray *)di, cnt, (cq_ray_hit *)dout, st);
-                     });
+                     [&](void *di, void *dout, int cnt, int lo, cudaStream_t st) {
+                         return launch_raycast(w, (const cq_ray *)di, cnt, (cq_ray_hit *)dout,
+                                               flags ? (uint8_t *)w->aux2.ptr + lo : nullptr, st);
+                     },
+                     false, nullptr, false, flags);
+}
+int cq_raycast_batch(cq_world *w, const cq_ray *rays, int32_t n, cq_ray_hit *out) {
+    return cq_raycast_batch_ex(w, rays, n, out, nullptr);
 }
 
-int cq_capsule_cast_batch(cq_world *w, const cq_capsule_cast *q, int32_t n, int32_t mode, cq_cast_hit *out) {
+int cq_capsule_cast_batch_ex(cq_world *w, const cq_capsule_cast *q, int32_t n, int32_t mode, cq_cast_hit *out, uint8_t *flags) {
     if (!w || n < 0 || mode < 0 || mode > 2 || (n > 0 && (!q || !out))) return CQ_ERR_INVALID;
     CQ_CUDA(cudaStreamSynchronize(w->stream));
     return run_batch(w, q, sizeof(cq_capsule_cast), out, sizeof(cq_cast_hit), n,
-                     [&](void *di, void *dout, int cnt, int, cudaStream_t st) {
-                         return launch_cast(w, (const cq_capsule_cast *)di, cnt, mode, (cq_cast_hit *)dout, st);
+                     [&](void *di, void *dout, int cnt, int lo, cudaStream_t st) {
+                         return launch_cast(w, (const cq_capsule_cast *)di, cnt, mode, (cq_cast_hit *)dout,
+                                            flags ? (uint8_t *)w->aux2.ptr + lo : nullptr, st);
                      },
-                     false, &w->hintCast);
+                     false, &w->hintCast, false, flags);
+}
+int cq_capsule_cast_batch(cq_world *w, const cq_capsule_cast *q, int32_t n, int32_t mode, cq_cast_hit *out) {
+    return cq_capsule_cast_batch_ex(w, q, n, mode, out, nullptr);
 }
 
-int cq_capsule_overlap_batch(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out) {
+int cq_capsule_overlap_batch_ex(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out, uint8_t *flags) {
     if (!w || n < 0 || (n > 0 && (!q || !out))) return CQ_ERR_INVALID;
     CQ_CUDA(cudaStreamSynchronize(w->stream));
     return run_batch(w, q, sizeof(cq_capsule), out, sizeof(cq_overlap_hit), n,
-                     [&](void *di, void *dout, int cnt, int, cudaStream_t st) {
-                         return launch_overlap(w, (const cq_capsule *)di, cnt, (cq_overlap_hit *)dout, st);
-                     });
+                     [&](void *di, void *dout, int cnt, int lo, cudaStream_t st) {
+                         return launch_overlap(w, (const cq_capsule *)di, cnt, (cq_overlap_hit *)dout,
+                                               flags ? (uint8_t *)w->aux2.ptr + lo : nullptr, st);
+                     },
+                     false, nullptr, false, flags);
+}
+int cq_capsule_overlap_batch(cq_world *w, const cq_capsule *q, int32_t n, cq_overlap_hit *out) {
+    return cq_capsule_overlap_batch_ex(w, q, n, out, nullptr);
 }
 
 int cq_capsule_overlap_all_batch(cq_world *w, const cq_capsule *q, int32_t n, int32_t max_hits, cq_overlap_hit *out,

@@ -8,11 +8,13 @@
 // The tree differs from the reference's (allowed: capsule candidate sets are tree-independent,
 // SURVEY.md §A.4); triangle NUMBERING and world-space vertices are bit-identical to the reference's.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "cq_internal.h"
+#include "cq_reftree.h"
 
 namespace cq {
 
@@ -651,6 +653,7 @@ struct Arena {
 
 void free_set(DeviceSet &S) {
     cudaFree(S.arena);
+    cudaFree(S.refArena);
     S = DeviceSet();
 }
 
@@ -876,7 +879,11 @@ int build_set(cq_world *w, DeviceSet &S, const SetPlan &in,
         k_filter_flags<<<cdiv(nIn, 256), 256, 0, st>>>(S.worldPos, dIdxIn, nIn, dFlags);
         w->launches++;
         int r = exclusive_scan_u32(w, dFlags, nIn, dOffs, dTileSums, dTotal);
-        if (r != CQ_OK) return done(r);
+        if (r != CQ_OK) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return done(r);
+        }
         CQ_CUDA(cudaMemcpyAsync(dOffs + nIn, dTotal, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st)); // dOffs[nIn] = total
         if (np) {
             k_gather_u32<<<cdiv(np, 256), 256, 0, st>>>(dOffs, dGatherPos, np, dGatherOut);
@@ -889,6 +896,12 @@ int build_set(cq_world *w, DeviceSet &S, const SetPlan &in,
         for (int i = 0; i < np; i++) partTriStartIn[i] = (int)outv[i];
     } else {
         for (auto &v : partTriStartIn) v = 0;
+    }
+    if (total > (1u << 26)) { // ring entries and leaf references carry 26-bit triangle slots (cq_pool.cuh, cq_query.cu)
+        set_error("cq_world_create: %u triangles in one set after the degenerate filter; the limit is 2^26 = 67,108,864", total);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return done(CQ_ERR_INVALID);
     }
     S.nTris = (int)total;
     const int n = S.nTris;
@@ -1121,6 +1134,170 @@ int make_agent_grid(cq_world *w, const cq_character_state *dStates, int n, float
     return check_cuda(cudaGetLastError(), "agent grid");
 }
 
+// ---------------------------------------------------------------- reference order (cq_reftree.h)
+// Boxes of the reference's tree, bottom-up: one thread per leaf computes boundsForRange (CollisionQuery.swift:662-677)
+// from the leaf's triangles, writes it into its parent's child slot and climbs while it is the second child to arrive
+// (merge = component-wise min / max, :700-702 — exact, so the arrival order does not matter).  Arrival counters are
+// left at zero, so the same kernel serves every refit (BVH.refit :528-575 touches only the ancestors of moved leaves;
+// refitting everything gives the same boxes).
+__device__ __forceinline__ void ref_store_child_box(Node *nd, int which, f3 lo, f3 hi) { // keeps the refs in n0.w / n1.w
+    float *p = reinterpret_cast<float *>(nd);
+    float *l = p + (which ? 8 : 0), *h = p + (which ? 12 : 4);
+    l[0] = lo.x, l[1] = lo.y, l[2] = lo.z;
+    h[0] = hi.x, h[1] = hi.y, h[2] = hi.z;
+}
+
+__global__ void k_ref_fit(int nLeaves, const int32_t *__restrict__ leafRange, const int32_t *__restrict__ leafParent,
+                          const int32_t *__restrict__ nodeParent, const uint32_t *__restrict__ refSlot,
+                          const float4 *__restrict__ tv0, const float4 *__restrict__ tv1, const float4 *__restrict__ tv2,
+                          Node *nodes, int32_t *visit, SetHeader *hdr) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nLeaves) return;
+    const int range = leafRange[l], start = range >> 2, count = (range & 3) + 1;
+    f3 lo = {0, 0, 0}, hi = {0, 0, 0};
+    for (int k = 0; k < count; k++) {
+        const uint32_t slot = refSlot[start + k];
+        const f3 a = xyz(tv0[slot]), b = xyz(tv1[slot]), c = xyz(tv2[slot]);
+        const f3 tlo = vmin(a, vmin(b, c)), thi = vmax(a, vmax(b, c));
+        lo = k ? vmin(lo, tlo) : tlo;
+        hi = k ? vmax(hi, thi) : thi;
+    }
+    int pw = leafParent[l];
+    while (true) {
+        if (pw < 0) { // the root's own box lives in the header
+            hdr->lo[0] = lo.x, hdr->lo[1] = lo.y, hdr->lo[2] = lo.z;
+            hdr->hi[0] = hi.x, hdr->hi[1] = hi.y, hdr->hi[2] = hi.z;
+            return;
+        }
+        const int p = pw >> 1;
+        ref_store_child_box(nodes + p, pw & 1, lo, hi);
+        __threadfence();
+        if (atomicAdd(&visit[p], 1) == 0) return; // first arrival: the sibling subtree is not done yet
+        visit[p] = 0;
+        __threadfence();
+        const float4 *q = reinterpret_cast<const float4 *>(nodes + p);
+        const float4 l0 = __ldcg(q), h0 = __ldcg(q + 1), l1 = __ldcg(q + 2), h1 = __ldcg(q + 3);
+        lo = vmin(xyz(l0), xyz(l1));
+        hi = vmax(xyz(h0), xyz(h1));
+        pw = nodeParent[p];
+    }
+}
+
+static int ref_fit(cq_world *w, DeviceSet &S) {
+    if (!S.refArena || S.nRefLeaves <= 0) return CQ_OK;
+    k_ref_fit<<<cdiv(S.nRefLeaves, 256), 256, 0, w->stream>>>(S.nRefLeaves, S.refLeafRange, S.refLeafParent, S.refNodeParent,
+                                                             S.refSlot, S.tv0, S.tv1, S.tv2, S.refNodes, S.refVisit, S.refHdr);
+    w->launches++;
+    return check_cuda(cudaGetLastError(), "k_ref_fit");
+}
+
+static inline float int_bits_as_float(int v) {
+    float f;
+    memcpy(&f, &v, sizeof(f));
+    return f;
+}
+
+// Reference order: download the sets' triangle boxes, rebuild the reference's tree on the host (cq_reftree.h), upload
+// the visiting ranks (one global array, static set first like the reference's own merge of its two sets,
+// CollisionQuery.swift:990-1008) and the tree itself for the ray walk.
+int attach_ref_order(cq_world *w) {
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t st = w->stream;
+    const int nS = w->set[0].nTris, nD = w->set[1].nTris;
+    std::vector<int32_t> rankAll((size_t)nS + nD);
+    for (int s = 0; s < 2; s++) {
+        DeviceSet &S = w->set[s];
+        const int n = S.nTris;
+        if (n <= 0) continue;
+        // triangle boxes as the device computed them (leaf boxes of the sorted order) back in the soup's numbering
+        std::vector<float4> sLo(n), sHi(n), lo(n), hi(n);
+        std::vector<uint32_t> sorted(n), slotOf(n);
+        CQ_CUDA(cudaMemcpyAsync(sLo.data(), S.boxLo + (n - 1), sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaMemcpyAsync(sHi.data(), S.boxHi + (n - 1), sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaMemcpyAsync(sorted.data(), S.sortedTri, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CQ_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < n; k++) lo[sorted[k]] = sLo[k], hi[sorted[k]] = sHi[k], slotOf[sorted[k]] = (uint32_t)k;
+        RefTree T;
+        build_ref_tree(&lo[0].x, &hi[0].x, 4, n, T);
+        const int off = s == 0 ? 0 : nS;
+        for (int t = 0; t < n; t++) rankAll[(size_t)off + t] = off + T.rank[t];
+        // device form: internal nodes and leaves numbered separately
+        const int nNodes = (int)T.nodes.size();
+        std::vector<int32_t> idOf(nNodes);
+        int nInt = 0, nLeaf = 0;
+        for (int k = 0; k < nNodes; k++) idOf[k] = T.nodes[k].left >= 0 ? nInt++ : nLeaf++;
+        std::vector<Node> nodes(std::max(nInt, 1));
+        std::vector<int32_t> nodeParent(std::max(nInt, 1), -1), leafParent(std::max(nLeaf, 1), -1), leafRange(std::max(nLeaf, 1), 0);
+        std::vector<uint32_t> refSlot(n);
+        for (int p = 0; p < n; p++) refSlot[p] = slotOf[T.order[p]];
+        auto ref_of = [&](int k) { // reference to node k as a parent stores it
+            const RefNode &nd = T.nodes[k];
+            return nd.left >= 0 ? idOf[k] : ~((nd.start << 2) | (nd.count - 1));
+        };
+        int depthMax = 0; // the ray walk keeps one stack entry per level
+        for (int k = 0; k < nNodes; k++) {
+            if (T.nodes[k].left >= 0) continue;
+            int d = 0;
+            for (int q = T.nodes[k].parent; q >= 0; q = T.nodes[q].parent) d++;
+            depthMax = std::max(depthMax, d);
+        }
+        for (int k = 0; k < nNodes; k++) {
+            const RefNode &nd = T.nodes[k];
+            int pw = -1;
+            if (nd.parent >= 0) pw = (idOf[nd.parent] << 1) | (T.nodes[nd.parent].right == k ? 1 : 0);
+            if (nd.left >= 0) {
+                Node &o = nodes[idOf[k]];
+                o.n0 = make_float4(0, 0, 0, int_bits_as_float(ref_of(nd.left)));
+                o.n1 = make_float4(0, 0, 0, int_bits_as_float(ref_of(nd.right)));
+                o.n2 = make_float4(0, 0, 0, 0), o.n3 = make_float4(0, 0, 0, 0);
+                nodeParent[idOf[k]] = pw;
+            } else {
+                leafParent[idOf[k]] = pw;
+                leafRange[idOf[k]] = (nd.start << 2) | (nd.count - 1);
+            }
+        }
+        if (depthMax + 2 > CQ_STACK) {
+            set_error("cq_world_create: the reference tree of set %d is %d levels deep (limit %d); use CQ_ORDER_CANONICAL", s, depthMax,
+                      CQ_STACK - 2);
+            return CQ_ERR_INVALID;
+        }
+        auto carve = [&](Arena &a) {
+            S.refNodes = a.take<Node>(nInt);
+            S.refSlot = a.take<uint32_t>(n);
+            S.refNodeParent = a.take<int32_t>(nInt);
+            S.refLeafParent = a.take<int32_t>(nLeaf);
+            S.refLeafRange = a.take<int32_t>(nLeaf);
+            S.refVisit = a.take<int32_t>(nInt);
+            S.refHdr = a.take<SetHeader>(1);
+        };
+        Arena arena;
+        arena.cap = arena_layout(carve);
+        CQ_CUDA(cudaMalloc((void **)&arena.base, arena.cap));
+        S.refArena = arena.base;
+        carve(arena);
+        S.nRefInternal = nInt, S.nRefLeaves = nLeaf, S.refDepth = depthMax;
+        SetHeader h;
+        h.nTris = n;
+        h.rootRef = ref_of(0);
+        h.lo[0] = h.lo[1] = h.lo[2] = 0.0f, h.hi[0] = h.hi[1] = h.hi[2] = 0.0f;
+        CQ_CUDA(cudaMemcpyAsync(S.refNodes, nodes.data(), sizeof(Node) * (size_t)std::max(nInt, 1), cudaMemcpyHostToDevice, st));
+        CQ_CUDA(cudaMemcpyAsync(S.refSlot, refSlot.data(), sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CQ_CUDA(cudaMemcpyAsync(S.refNodeParent, nodeParent.data(), sizeof(int32_t) * (size_t)std::max(nInt, 1), cudaMemcpyHostToDevice, st));
+        CQ_CUDA(cudaMemcpyAsync(S.refLeafParent, leafParent.data(), sizeof(int32_t) * (size_t)std::max(nLeaf, 1), cudaMemcpyHostToDevice, st));
+        CQ_CUDA(cudaMemcpyAsync(S.refLeafRange, leafRange.data(), sizeof(int32_t) * (size_t)std::max(nLeaf, 1), cudaMemcpyHostToDevice, st));
+        CQ_CUDA(cudaMemsetAsync(S.refVisit, 0, sizeof(int32_t) * (size_t)std::max(nInt, 1), st));
+        CQ_CUDA(cudaMemcpyAsync(S.refHdr, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+        CQ_TRY(ref_fit(w, S));
+        CQ_CUDA(cudaStreamSynchronize(st)); // the host vectors above are the copies' sources
+    }
+    if (nS + nD > 0) {
+        CQ_CUDA(cudaMalloc((void **)&w->dRank, sizeof(int32_t) * (size_t)(nS + nD)));
+        CQ_CUDA(cudaMemcpy(w->dRank, rankAll.data(), sizeof(int32_t) * (size_t)(nS + nD), cudaMemcpyHostToDevice));
+    }
+    w->refBuildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return CQ_OK;
+}
+
 // TriangleMeshSet.updateTransforms + BVH.refit: re-transform the changed parts' vertices, regather the
 // sorted SoA, recompute every box bottom-up (same tree topology).  Asynchronous on the world stream.
 int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx) {
@@ -1132,7 +1309,8 @@ int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx) {
         k_transform<<<cdiv(nv, 256), 256, 0, st>>>(S.localPos, S.worldPos, w->dModels, p.vertLo, p.vertHi);
         w->launches++;
     }
-    return build_tree(w, S, nullptr);
+    CQ_TRY(build_tree(w, S, nullptr));
+    return ref_fit(w, S); // reference order: the reference's own tree keeps its topology too (BVH.refit)
 }
 
 } // namespace cq

@@ -47,6 +47,16 @@ struct DeviceSet {
     float4 *boxLo = nullptr, *boxHi = nullptr;      // 2nTris-1 subtree boxes (bottom-up scratch, kept for refit)
     int32_t *visit = nullptr;    // per internal node arrival counter
     SetHeader *hdr = nullptr;
+    // reference order (cq_reftree.h -> attach_ref_order): the reference's own tree, for the ray walk and its refit
+    void *refArena = nullptr;
+    int nRefInternal = 0, nRefLeaves = 0, refDepth = 0;
+    Node *refNodes = nullptr;          // internal nodes
+    uint32_t *refSlot = nullptr;       // triOrder position -> sorted slot
+    int32_t *refNodeParent = nullptr;  // per internal node: (parent << 1) | which child, -1 = root
+    int32_t *refLeafParent = nullptr;  // per leaf: same encoding
+    int32_t *refLeafRange = nullptr;   // per leaf: (start << 2) | (count - 1)
+    int32_t *refVisit = nullptr;       // per internal node arrival counter (left at zero by every fit)
+    SetHeader *refHdr = nullptr;
 };
 
 struct ScratchBuf {
@@ -64,6 +74,10 @@ struct ScratchBuf {
 
 struct cq_world {
     int device = 0;
+    int order = CQ_ORDER_REFERENCE; // tie / overflow rule of every query (include/cq.h)
+    int32_t *dRank = nullptr;       // reference order: global triangle index -> visiting rank
+    unsigned int *hStatus = nullptr; // status word, mapped host memory (WorldView::status is its device alias)
+    float refBuildMs = 0;           // host time of the reference-order build (download + tree + upload)
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream[2] = {nullptr, nullptr}; // the two alternating compute streams of the batch pipeline
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
@@ -77,7 +91,7 @@ struct cq_world {
     float buildMs = 0, refitMs = 0;
     int counting = 0;
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
-    int occ[6][4] = {}; // resident CTAs per SM of each persistent kernel ([counting + 2 * staged-walk variant])
+    int occ[6][4] = {}; // (raycast: [counting + 2 * reference-order walker]) // resident CTAs per SM of each persistent kernel ([counting + 2 * staged-walk variant])
     int numSms = 0;
     uint64_t launches = 0;
     cq::ScratchBuf nodeScratch[4], orderScratch[4];
@@ -109,6 +123,8 @@ int check_cuda(cudaError_t e, const char *what);
     } while (0)
 
 int ensure_scratch(ScratchBuf &b, size_t bytes);
+// after a synchronisation: has any kernel raised the world's status word since the last check?
+int check_status(cq_world *w, const char *what);
 // The world's scratch blocks (node stacks, unit order, agent grid, separation state) are shared by successive launches.
 // Launches on ONE stream are ordered by the stream; a launch on ANOTHER stream must wait until the previous user of
 // the block has finished.  scratch_acquire(b, st) inserts that wait and notes the block as held; the launcher calls
@@ -130,6 +146,8 @@ int build_set(cq_world *w, DeviceSet &S, const SetPlan &in /* upload plan of the
               std::vector<int> &partTriStart /* in: first input triangle of each part of the set (+ end); out: after the filter */,
               int *badTriangle /* out: smallest input triangle with an out-of-range index (CQ_ERR_INVALID), else -1 */);
 int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx);
+// reference order: rebuild the reference's tree on the host from the set's triangle boxes, upload rank + tree (cq_reftree.h)
+int attach_ref_order(cq_world *w);
 void free_set(DeviceSet &S);
 // Morton-sorted processing order of n work units whose position (3 floats or 3 doubles) sits at the start of each
 // `stride`-byte record; nullptr when ordering is not worthwhile (small world / batch) or on error
@@ -144,9 +162,10 @@ int sort_pairs_u32(cq_world *w, uint32_t *keys, uint32_t *vals, uint32_t *keysTm
                    size_t scratchWords, cudaStream_t st);
 
 // cq_query.cu
-int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, cudaStream_t st);
-int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st);
-int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, cudaStream_t st);
+// d_flags (may be nullptr): one CQ_HIT_* byte per query
+int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, uint8_t *d_flags, cudaStream_t st);
+int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, uint8_t *d_flags, cudaStream_t st);
+int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, uint8_t *d_flags, cudaStream_t st);
 int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,
                        uint8_t *d_overflow, cudaStream_t st);
 // cq_mas.cu

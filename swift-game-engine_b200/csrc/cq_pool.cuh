@@ -22,6 +22,7 @@
 // Results are deterministic: a cast's answer is the accepted pair with the smallest (toi, index), an
 // order-free reduction; commits are applied one lane at a time.
 #pragma once
+#include "../../include/cq.h"
 #include "cq_world.cuh"
 
 namespace cq {
@@ -32,18 +33,32 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
+#ifndef CQ_LOOKAHEAD
+#define CQ_LOOKAHEAD 0 /* 1: look-ahead prune of the conservative advancement (see pool_eval) */
+#endif
 #ifndef CQ_EARLY_PICKUP
 #define CQ_EARLY_PICKUP 0 /* 1: a second pickup right after the commit (round-2 A/B: hides the triangle fetch of a fresh pair) */
 #endif
 #ifndef CQ_EVAL_KEEP
 #define CQ_EVAL_KEEP 0    /* with CQ_EVAL_REPS > 1: keep evaluating only while this many lanes hold a live pair */
 #endif
-#define CQ_NSCAP 2048     /* node-stack entries per warp (global memory; 32 concurrent walks x depth <= 64) */
+#define CQ_NSCAP 2048     /* node-stack entries per warp (global memory; 32 concurrent walks) */
+// Stack budget.  A walk round with 32 poppers grows the stack by at most 32 x (4 - 1) = 96 entries; posting roots adds at
+// most 32 owners x 2 sets = 64.  Above CQ_NS_WIDE only ONE lane pops per round (depth-first), which grows the stack by
+// at most 3 per level below the popped entry: CQ_NS_DFS_RESERVE covers 48 four-wide levels (a binary LBVH over 2^26
+// triangles with 30-bit keys + index tie-breaks is at most 56 levels = 28 wide ones).  Owners post new queries only
+// below CQ_NS_POST.  Every push is still bounds-checked: an overflow drops the entry and raises the world's status word.
+#define CQ_NS_DFS_RESERVE 144
+#define CQ_NS_WIDE (CQ_NSCAP - CQ_NS_DFS_RESERVE - 96)
+#define CQ_NS_POST (CQ_NS_WIDE - 64)
 
 struct QShared { // one per owner lane, shared memory: what executors need + the query's result
-    float from[3], dir[3], delta[3];
-    float L, radius, hh, minNormalY, minAdvance;
-    int maxIter, mode;
+    float from[3], radius, hh;
+    // sweeps only.  An overlap query of the move-and-slide kernel reuses these ten words (ovl_words): the eight smallest
+    // visiting ranks seen, the number of overlapping triangles, and the rank limit of a second pass (reference order).
+    float dir[3], delta[3], L, minNormalY, minAdvance;
+    int maxIter;
+    int mode; // low byte: CQ_MODE_* / CQ_KIND_OVERLAP; CQ_QF_* flags above it
     float qlo[3], qhi[3]; // the query's (swept) AABB: node / triangle boxes are tested against it
     uint32_t mask;
     // result.  cast: rT/rTri/rPart + contact.  overlap: two deepest, d0=rT t0=rTri n0=rN | d1=rPos[0] t1=rPart n1=rTriN
@@ -52,6 +67,10 @@ struct QShared { // one per owner lane, shared memory: what executors need + the
     float rPos[3], rN[3], rTriN[3];
     int pending; // stack entries + pairs pushed for this query and not yet consumed; 0 = query complete
 };
+
+#define CQ_QF_TIE 0x100 /* another accepted candidate had exactly the best key: the answer depended on the order rule */
+__device__ __forceinline__ int *ovl_words(QShared &s) { return reinterpret_cast<int *>(s.dir); }
+enum { OVL_TOTAL = 8, OVL_LIMIT = 9 }; // ovl_words: [0..7] smallest ranks, [8] overlapping triangles, [9] rank limit (-1 none)
 
 struct QResult { // what owner logic reads back
     float bestT;
@@ -69,6 +88,9 @@ struct Job { // executor-side pair state (registers)
     int gid, part;
     float t, lastSafeT, lo, hi;
     int it, k;
+#if CQ_LOOKAHEAD
+    float margin; // slack of the look-ahead prune: float error of positions and distances at this query's scale
+#endif
 };
 
 struct Commit { // a finished pair's contribution, applied in the serialized commit step
@@ -85,12 +107,20 @@ struct WarpPool { // per-warp handles
     volatile uint32_t *ntop; // node-stack height   shared
     uint2 *nstack;           // [CQ_NSCAP] (owner<<2 | set<<1 | isLeaf, ref)   global (L2 resident)
     uint32_t *stage;         // [CQ_STAGE] triangles of the leaf ranges popped in this walk round   shared
+    const int32_t *rank;     // visiting rank per global triangle index (reference order) or nullptr (rank = index)
+    unsigned int *status;    // the world's status word (mapped host memory)
 };
+__device__ __forceinline__ bool pool_stack_room(const WarpPool &wp, uint32_t pos, uint32_t cnt) {
+    if (pos + cnt <= (uint32_t)CQ_NSCAP) return true;
+    atomicOr(wp.status, 1u);
+    return false;
+}
+__device__ __forceinline__ int pool_rank(const int32_t *rank, int gid) { return rank ? __ldg(rank + gid) : gid; }
 #define CQ_STAGE 128 /* 32 leaf ranges x <= 4 triangles */
 #define CQ_POOL_WORDS (CQ_QCAP + 3 + CQ_STAGE) /* shared words per warp besides QShared */
 
 __device__ __forceinline__ void pool_bind(WarpPool &wp, QShared *qsAll, uint32_t *words, uint2 *nodeScratch, int warp,
-                                          int warpsPerBlock) {
+                                          int warpsPerBlock, const int32_t *rank, unsigned int *status) {
     wp.qs = qsAll + warp * 32;
     wp.ring = words + warp * CQ_POOL_WORDS;
     wp.head = wp.ring + CQ_QCAP;
@@ -98,6 +128,8 @@ __device__ __forceinline__ void pool_bind(WarpPool &wp, QShared *qsAll, uint32_t
     wp.ntop = wp.ring + CQ_QCAP + 2;
     wp.stage = wp.ring + CQ_QCAP + 3;
     wp.nstack = nodeScratch + ((size_t)blockIdx.x * warpsPerBlock + warp) * CQ_NSCAP;
+    wp.rank = rank;
+    wp.status = status;
 }
 
 __device__ __forceinline__ void pool_read_result(const QShared &s, QResult &r) {
@@ -130,6 +162,10 @@ __device__ __forceinline__ void pool_push_roots(const WorldView &W, const WarpPo
         if (box_disjoint(mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), qlo, qhi)) continue;
         bool leaf = h.rootRef < 0;
         uint32_t pos = atomicAdd((uint32_t *)wp.ntop, 1u);
+        if (!pool_stack_room(wp, pos, 1u)) {
+            atomicSub((uint32_t *)wp.ntop, 1u);
+            continue;
+        }
         wp.nstack[pos] = make_uint2(((uint32_t)lane << 2) | ((uint32_t)set << 1) | (leaf ? 1u : 0u),
                                     (uint32_t)(leaf ? ~h.rootRef : h.rootRef));
         pushed++;
@@ -175,15 +211,13 @@ __device__ __forceinline__ void pool_post_cast(const WorldView &W, const WarpPoo
 // capsuleOverlapAll prologue — CollisionQuery.swift:1209-1216 (two deepest kept, Systems.swift:764-767)
 template <bool COUNT>
 __device__ __forceinline__ void pool_post_overlap(const WorldView &W, const WarpPool &wp, int lane, QShared &s, f3 from,
-                                                  float radius, float hh, uint32_t mask, Counters &ctr) {
+                                                  float radius, float hh, uint32_t mask, Counters &ctr, int rankLimit = -1) {
     s.mode = CQ_KIND_OVERLAP;
     store3s(s.from, from);
-    store3s(s.dir, mk3(0, 0, 0));
-    s.L = 0.0f;
     s.radius = radius;
     s.hh = hh;
-    s.minAdvance = 0.0f;
-    s.maxIter = 1;
+    ovl_words(s)[OVL_TOTAL] = 0;
+    ovl_words(s)[OVL_LIMIT] = rankLimit;
     s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));         // deepest
     s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0)); // second deepest
     f3 qlo, qhi;
@@ -201,7 +235,7 @@ __device__ __forceinline__ void pool_post_overlap(const WorldView &W, const Warp
 template <bool COUNT, bool STAGED>
 __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPool &wp, int lane, Counters &ctr) {
     const uint32_t top = *wp.ntop;
-    const uint32_t poppers = (top + 160u > (uint32_t)CQ_NSCAP) ? 1u : 32u; // nearly full: depth-first with one lane
+    const uint32_t poppers = top > (uint32_t)CQ_NS_WIDE ? 1u : 32u; // nearly full: depth-first with one lane
     const uint32_t k = min(top, poppers);
     uint2 e = make_uint2(0u, 0u);
     const bool have = (uint32_t)lane < k;
@@ -226,6 +260,11 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
         int cnt = (h0 ? 1 : 0) + (h1 ? 1 : 0) + (h2 ? 1 : 0) + (h3 ? 1 : 0);
         if (cnt) {
             uint32_t pos = atomicAdd((uint32_t *)wp.ntop, (uint32_t)cnt);
+            if (!pool_stack_room(wp, pos, (uint32_t)cnt)) {
+                atomicSub((uint32_t *)wp.ntop, (uint32_t)cnt);
+                h0 = h1 = h2 = h3 = false;
+                cnt = 0;
+            }
             const uint32_t tag = e.x & ~1u;
             if (h0) wp.nstack[pos++] = make_uint2(tag | (r0 < 0 ? 1u : 0u), (uint32_t)(r0 < 0 ? ~r0 : r0));
             if (h1) wp.nstack[pos++] = make_uint2(tag | (r1 < 0 ? 1u : 0u), (uint32_t)(r1 < 0 ? ~r1 : r1));
@@ -332,7 +371,10 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
             job.t = 0.0f;
             job.lastSafeT = 0.0f;
             job.it = 0;
-            job.phase = s.mode == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
+#if CQ_LOOKAHEAD
+            job.margin = 1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f;
+#endif
+            job.phase = (s.mode & 0xff) == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
         }
     }
     __syncwarp();
@@ -372,6 +414,15 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
             job.it++;
             // next trip: `for _ in 0..<maxIter { if t > maxDistance return nil ...`; prune: toi >= lastSafeT > bestT
             if (job.it >= job.maxIter || job.t > job.L || job.lastSafeT > bestT) retired = true;
+#if CQ_LOOKAHEAD
+            // Look-ahead prune (exact-safe): this was a true conservative-advancement step (advance = dist - r, not the
+            // minAdvance floor) and it lands beyond bestT by more than `margin`.  The capsule moves at unit speed, so
+            // the distance at any t <= bestT is at least dist - (t - lastSafeT) > r + margin: if the NEXT evaluation
+            // reports contact, every bisection point of refineTOI at or before bestT still evaluates to "no contact"
+            // (margin covers the float error of positions and distances), the refined toi ends beyond bestT and the
+            // hit is rejected by `toi < bestT` (:1084); contacts found later have lastSafeT > bestT anyway.
+            else if (dist - job.radius >= job.minAdvance && job.t > bestT + job.margin) retired = true;
+#endif
         }
     } else if (ph == PH_BIS) { // refineTOI bisection, :1379-1392 (threshold is radius, not radius+eps)
         if (dist <= job.radius) job.hi = tc;
@@ -392,7 +443,7 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
         f3 triN = triNormal;
         if (dot(triN, n) < 0.0f) triN = -triN;
         bool ok = true;
-        const int mode = s.mode;
+        const int mode = s.mode & 0xff;
         if (mode == CQ_MODE_BLOCKING) {
             f3 delta = mk3(s.delta[0], s.delta[1], s.delta[2]);
             ok = !(dot(delta, n) >= 0.0f) && !(dot(delta, triN) >= 0.0f);
@@ -419,12 +470,34 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
 
 // serialized commit: one finishing lane at a time updates its owner's record; pending counters drop
 // default overlap commit: the two deepest overlaps kept in the owner's QShared (move-and-slide depenetration)
+// Reference order (rank != nullptr): the reference's depenetration takes the first maxHits = 8 overlaps in visiting order,
+// sorts them by depth (stably) and uses one or two (Systems.swift:751-767).  A first pass keeps the two deepest of ALL
+// overlapping triangles (ties: smaller rank), counts them and remembers the eight smallest ranks; only when more than
+// eight triangles overlap does the owner post a second pass limited to those ranks (OVL_LIMIT).
 struct OverlapTop2 {
+    const int32_t *rank;
     __device__ __forceinline__ void operator()(QShared &s, float depth, int gid, uint32_t, f3 n) const {
+        const int rk = pool_rank(rank, gid);
+        if (rank) {
+            int *ov = ovl_words(s);
+            const int limit = ov[OVL_LIMIT];
+            if (limit >= 0) {
+                if (rk > limit) return; // second pass: beyond the first maxHits the reference visited
+            } else {
+                const int total = ov[OVL_TOTAL];
+                int pos = total < CQ_MAX_OVERLAP_HITS ? total : CQ_MAX_OVERLAP_HITS;
+                while (pos > 0 && ov[pos - 1] > rk) pos--;
+                if (pos < CQ_MAX_OVERLAP_HITS) {
+                    for (int k = total < CQ_MAX_OVERLAP_HITS - 1 ? total : CQ_MAX_OVERLAP_HITS - 1; k > pos; k--) ov[k] = ov[k - 1];
+                    ov[pos] = rk;
+                }
+                ov[OVL_TOTAL] = total + 1;
+            }
+        }
         float d0 = s.rT, d1 = s.rPos[0];
         int t0 = s.rTri, t1 = s.rPart;
-        bool before0 = t0 < 0 || depth > d0 || (depth == d0 && gid < t0);
-        bool before1 = t1 < 0 || depth > d1 || (depth == d1 && gid < t1);
+        bool before0 = t0 < 0 || depth > d0 || (depth == d0 && rk < pool_rank(rank, t0));
+        bool before1 = t1 < 0 || depth > d1 || (depth == d1 && rk < pool_rank(rank, t1));
         if (before0) {
             s.rPos[0] = d0, s.rPart = t0;
             store3s(s.rTriN, mk3(s.rN[0], s.rN[1], s.rN[2]));
@@ -451,7 +524,10 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                 float bestT = s.rT;
                 int bestTri = s.rTri;
                 bool better = cm.key < bestT;
-                bool tieWin = bestTri >= 0 && cm.key == bestT && job.gid < bestTri;
+                bool tie = bestTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited (:1084)
+                bool tieWin = tie && pool_rank(wp.rank, job.gid) < pool_rank(wp.rank, bestTri);
+                if (tie) s.mode |= CQ_QF_TIE;
+                if (better) s.mode &= ~CQ_QF_TIE;
                 if (better || tieWin) {
                     s.rT = cm.key;
                     s.rTri = job.gid;
@@ -503,7 +579,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         // 16; terrain +4%; C4 +1.6% with 8 but -2% with 16; the candidate-heavy render mesh loses 3% either way).
         const uint32_t idleNow = (uint32_t)__popc(__ballot_sync(0xffffffffu, job.phase == PH_NONE));
         if (*wp.tail == *wp.head && idleNow >= (uint32_t)FE_IDLE) {
-            if (alive && *(volatile int *)&mine.pending == 0) alive = advance(mine, ctr);
+            if (alive && *(volatile int *)&mine.pending == 0 && *wp.ntop <= (uint32_t)CQ_NS_POST) alive = advance(mine, ctr);
             __syncwarp();
             // cooperative walk: rounds until the ring holds ~3 trips of work (or the stack is empty)
             while (*wp.ntop != 0u && *wp.tail - *wp.head < 96u && *wp.tail - *wp.head + 128u <= (uint32_t)CQ_QCAP)

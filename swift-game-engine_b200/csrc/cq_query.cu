@@ -37,9 +37,11 @@ __device__ __forceinline__ f3 load3(const float *p) { return {p[0], p[1], p[2]};
 // the box test is conservative (see ray_box).
 template <bool COUNT>
 __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray *__restrict__ rays, int n,
-                                                       cq_ray_hit *__restrict__ out, int *workCounter,
-                                                       const uint32_t *__restrict__ order, unsigned long long *gctr) {
+                                                       cq_ray_hit *__restrict__ out, uint8_t *__restrict__ flagsOut,
+                                                       int *workCounter, const uint32_t *__restrict__ order,
+                                                       unsigned long long *gctr) {
     Counters ctr = {0, 0, 0, 0};
+    uint32_t tie = 0;
     int stack[CQ_STACK];
     int sp = 0, set = 2, leafPos = 0, leafEnd = 0, cur = -1;
     int bestTri = -1;
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
                         hres.triangle_index = -1;
                     }
                     out[cur] = hres;
+                    if (flagsOut) flagsOut[cur] = (uint8_t)tie;
                 }
                 cur = atomicAdd(workCounter, 1);
                 if (cur >= n) {
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
                     o = load3(r.origin), d = load3(r.direction);
                     closestT = r.max_distance;
                     mask = r.mask;
-                    bestTri = -1;
+                    bestTri = -1, tie = 0;
                     // CollisionQuery.swift:1606-1608: 1/d, or greatestFiniteMagnitude when d == 0
                     inv = mk3(d.x != 0.0f ? 1.0f / d.x : FLT_MAX, d.y != 0.0f ? 1.0f / d.y : FLT_MAX,
                               d.z != 0.0f ? 1.0f / d.z : FLT_MAX);
@@ -105,6 +108,8 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
                 float t;
                 if (ray_triangle(o, d, T, t)) {
                     int gid = triId + S.triOffset;
+                    if (bestTri >= 0 && t == closestT) tie = CQ_HIT_TIE;
+                    if (t < closestT) tie = 0;
                     if (t < closestT || (bestTri >= 0 && t == closestT && gid < bestTri)) {
                         closestT = t;
                         bestTri = gid;
@@ -141,6 +146,160 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
     flush_counters<COUNT>(ctr, gctr);
 }
 
+// ---------------------------------------------------------------- raycast in REFERENCE order
+// The reference's walk itself (CollisionQuery.swift:916-978) over the reference's own tree (cq_reftree.h, uploaded by
+// attach_ref_order): per set, closestT starts at maxDistance; pop a node, cull it when rayAABB (:1603-1631, restated
+// below with the same operations) misses or starts beyond closestT, test a leaf's triangles in triOrder with strict
+// `t < closestT`, push left then right.  The slab test of a child is evaluated when its parent is visited (a miss
+// never depends on closestT) and its tmin travels with the stack entry, so the `tmin > closestT` test happens at pop
+// time with the value closestT has THEN — the same nodes are culled as in the reference, including the grazing hits its
+// non-conservative slab test loses.  Static and dynamic sets are walked independently and merged with `<=` (:902-907).
+__device__ __forceinline__ bool ref_ray_aabb(f3 o, f3 inv, f3 lo, f3 hi, float &tminOut) {
+    float tmin = (lo.x - o.x) * inv.x, tmax = (hi.x - o.x) * inv.x;
+    if (tmin > tmax) {
+        float t = tmin;
+        tmin = tmax, tmax = t;
+    }
+    float tymin = (lo.y - o.y) * inv.y, tymax = (hi.y - o.y) * inv.y;
+    if (tymin > tymax) {
+        float t = tymin;
+        tymin = tymax, tymax = t;
+    }
+    if (tmin > tymax || tymin > tmax) return false;
+    tmin = tymin >= tmin ? tymin : tmin; // Swift max(x, y) = y >= x ? y : x ; min(x, y) = y < x ? y : x
+    tmax = tymax < tmax ? tymax : tmax;
+    float tzmin = (lo.z - o.z) * inv.z, tzmax = (hi.z - o.z) * inv.z;
+    if (tzmin > tzmax) {
+        float t = tzmin;
+        tzmin = tzmax, tzmax = t;
+    }
+    if (tmin > tzmax || tzmin > tmax) return false;
+    tminOut = tzmin >= tmin ? tzmin : tmin;
+    return true;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(Q_THREADS) k_raycast_ref(WorldView W, const cq_ray *__restrict__ rays, int n,
+                                                           cq_ray_hit *__restrict__ out, uint8_t *__restrict__ flagsOut,
+                                                           int *workCounter, const uint32_t *__restrict__ order,
+                                                           unsigned long long *gctr) {
+    Counters ctr = {0, 0, 0, 0};
+    int stackRef[CQ_STACK];
+    float stackT[CQ_STACK];
+    int sp = 0, set = 2, leafPos = 0, leafEnd = 0, cur = -1;
+    int bestTri = -1, setTri = -1;
+    float closestT = 0.0f, bestT = 0.0f, maxDist = 0.0f;
+    f3 o = {0, 0, 0}, d = {0, 0, 0}, inv = {0, 0, 0}, bestN = {0, 0, 0}, setN = {0, 0, 0};
+    uint32_t mask = 0, tie = 0, setTie = 0;
+    bool alive = true;
+    while (true) {
+        if (alive && leafPos >= leafEnd && sp == 0) {
+            // a set's walk is over: merge its hit (static wins `<=`, :902-907), then the next set or the next ray
+            if (setTri >= 0 && (bestTri < 0 || !(bestT <= closestT))) bestT = closestT, bestTri = setTri, bestN = setN, tie = setTie;
+            setTri = -1, setTie = 0;
+            if (set < 2) {
+                const SetHeader h = *(set ? W.set[1].refHdr : W.set[0].refHdr);
+                closestT = maxDist;
+                if (h.rootRef != CQ_REF_EMPTY) {
+                    if (COUNT) {
+                        ctr.queries++;
+                        ctr.nodes++;
+                    }
+                    float tmin;
+                    if (ref_ray_aabb(o, inv, mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), tmin)) {
+                        stackRef[sp] = h.rootRef < 0 ? ~((~h.rootRef) | (set << 30)) : (h.rootRef | (set << 30));
+                        stackT[sp++] = tmin;
+                    }
+                }
+                set++;
+            } else {
+                if (cur >= 0) {
+                    cq_ray_hit hres;
+                    if (bestTri >= 0) {
+                        hres.distance = bestT;
+                        store3(hres.position, o + d * bestT); // :962
+                        store3(hres.normal, bestN);
+                        hres.triangle_index = bestTri;
+                    } else {
+                        hres.distance = 0.0f;
+                        store3(hres.position, mk3(0, 0, 0));
+                        store3(hres.normal, mk3(0, 0, 0));
+                        hres.triangle_index = -1;
+                    }
+                    out[cur] = hres;
+                    if (flagsOut) flagsOut[cur] = (uint8_t)tie;
+                }
+                cur = atomicAdd(workCounter, 1);
+                if (cur >= n) {
+                    cur = -1;
+                    alive = false;
+                } else {
+                    if (order) cur = (int)order[cur];
+                    cq_ray r = rays[cur];
+                    o = load3(r.origin), d = load3(r.direction);
+                    maxDist = r.max_distance;
+                    mask = r.mask;
+                    bestTri = -1, setTri = -1, tie = 0;
+                    inv = mk3(d.x != 0.0f ? 1.0f / d.x : FLT_MAX, d.y != 0.0f ? 1.0f / d.y : FLT_MAX,
+                              d.z != 0.0f ? 1.0f / d.z : FLT_MAX); // :1606-1608
+                    set = 0;
+                }
+            }
+        } else if (alive && leafPos < leafEnd) { // triangle step, ascending triOrder positions (:938-940)
+            const int s1 = (leafPos >> 30) & 1, pos = leafPos & 0x3fffffff;
+            leafPos++;
+            const SetView &S = W.set[s1];
+            const int slot = (int)__ldg(S.refSlot + pos);
+            uint32_t layer;
+            int triId, part;
+            Tri T = load_tri(S, slot, layer, triId, part);
+            if ((layer & mask) != 0u) {
+                if (COUNT) ctr.cands++;
+                float t;
+                if (ray_triangle(o, d, T, t)) {
+                    if (t < closestT) { // strict: the first visited keeps an exact tie (:944)
+                        closestT = t;
+                        setTri = triId + S.triOffset;
+                        setTie = 0;
+                        f3 nrm = normalize(cross(T.v1 - T.v0, T.v2 - T.v0));
+                        setN = dot(nrm, d) > 0.0f ? -nrm : nrm;
+                    } else if (t == closestT && setTri >= 0) {
+                        setTie = CQ_HIT_TIE;
+                    }
+                }
+            }
+        } else if (alive) { // node step
+            --sp;
+            const int ref = stackRef[sp];
+            const float tminNode = stackT[sp];
+            if (!(tminNode > closestT)) { // :933, with the closestT of NOW
+                if (ref < 0) {
+                    int enc = ~ref;
+                    const int s1 = (enc >> 30) & 1;
+                    enc &= 0x3fffffff;
+                    leafPos = (enc >> 2) | (s1 << 30);
+                    leafEnd = leafPos + (enc & 3) + 1;
+                } else {
+                    const int s1 = (ref >> 30) & 1;
+                    const Node *nd = W.set[s1].refNodes + (ref & 0x3fffffff);
+                    float4 n0 = __ldg(&nd->n0), n1 = __ldg(&nd->n1), n2 = __ldg(&nd->n2), n3 = __ldg(&nd->n3);
+                    if (COUNT) ctr.nodes += 2;
+                    float t0, t1;
+                    const bool h0 = ref_ray_aabb(o, inv, xyz(n0), xyz(n1), t0); // left
+                    const bool h1 = ref_ray_aabb(o, inv, xyz(n2), xyz(n3), t1); // right
+                    int r0 = __float_as_int(n0.w), r1 = __float_as_int(n1.w);
+                    r0 = r0 < 0 ? ~((~r0) | (s1 << 30)) : (r0 | (s1 << 30));
+                    r1 = r1 < 0 ? ~((~r1) | (s1 << 30)) : (r1 | (s1 << 30));
+                    if (h0) stackRef[sp] = r0, stackT[sp++] = t0; // push left, then right: the right child is popped first (:965-966)
+                    if (h1) stackRef[sp] = r1, stackT[sp++] = t1;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !alive)) break;
+    }
+    flush_counters<COUNT>(ctr, gctr);
+}
+
 // ---------------------------------------------------------------- capsule cast (CollisionQuery.swift:787-828, 980-1117)
 // Warp-cooperative pool engine (cq_pool.cuh): every lane owns one sweep at a time (fetched dynamically),
 // walks the LBVH for it and pushes its candidate triangles into the warp's ring; all 32 lanes execute
@@ -154,7 +313,8 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast(WorldView W, const cq_ray
 #endif
 template <bool COUNT, bool STAGED>
 __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(WorldView W, const cq_capsule_cast *__restrict__ qs, int n,
-                                                               int mode, cq_cast_hit *__restrict__ out, int ownersPerWarp,
+                                                               int mode, cq_cast_hit *__restrict__ out,
+                                                               uint8_t *__restrict__ flagsOut, int ownersPerWarp,
                                                                uint2 *nodeScratch, int *workCounter,
                                                                const uint32_t *__restrict__ order,
                                                                unsigned long long *gctr) {
@@ -162,7 +322,7 @@ __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(Wor
     __shared__ uint32_t words[CQ_POOL_WORDS * CAST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpPool wp;
-    pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS);
+    pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS, W.rank, W.status);
     Counters ctr = {0, 0, 0, 0};
     int cur = -1;
 #if CQ_UNIT_BATCH > 1
@@ -185,6 +345,7 @@ __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(Wor
                 h.triangle_index = -1;
             }
             out[cur] = h;
+            if (flagsOut) flagsOut[cur] = (mine.mode & CQ_QF_TIE) ? CQ_HIT_TIE : 0;
         }
 #if CQ_UNIT_BATCH > 1
         // claim CQ_UNIT_BATCH sweeps per atomic and start their query records towards L2 right away: the chain
@@ -216,7 +377,7 @@ __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(Wor
         pool_post_cast<COUNT>(W, wp, lane, mine, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
                               c.min_normal_y, ct);
         return true;
-    }, OverlapTop2());
+    }, OverlapTop2{W.rank});
     flush_counters<COUNT>(ctr, gctr);
 }
 
@@ -237,36 +398,48 @@ __device__ __forceinline__ void write_overlap_nil(cq_overlap_hit &h) {
 
 // ---------------------------------------------------------------- capsule overlap / overlap-all
 // (CollisionQuery.swift:830-882, 1119-1283) on the pair pool: one distance evaluation per (capsule, triangle)
-// pair, shared by the warp.  The owner keeps the maxHits deepest overlaps as (depth, triangle, ring entry) in
-// shared memory — inserted in the serialized commit step, order (depth desc, index asc) — and, when its
-// query completes, re-evaluates those <= 8 winners to emit the full contact records (same arithmetic, so the
-// records are bit-identical to what the pair's executor saw).
-//   capsuleOverlap    = the deepest one (ties -> smallest index; the reference: first visited)
-//   capsuleOverlapAll = the maxHits deepest, deepest first — the order every caller in the reference sorts into
-//                       (Systems.swift:759); the reference returns its first maxHits in DFS order, identical
-//                       whenever <= maxHits triangles overlap, flagged `overflow` otherwise.
+// pair, shared by the warp.  The owner keeps its winners as (depth, rank, triangle, ring entry) in shared memory —
+// inserted in the serialized commit step — and, when its query completes, re-evaluates those <= 8 winners to emit the
+// full contact records (same arithmetic, so the records are bit-identical to what the pair's executor saw).
+//   capsuleOverlap    = the deepest one; exactly equal depths go to the smaller visiting rank (strict `>`, :1172)
+//   capsuleOverlapAll, reference order = the maxHits triangles the reference visits FIRST (:1272-1274), in that order
+//                     (its callers sort by depth themselves, Systems.swift:759);
+//                     canonical order = the maxHits deepest, deepest first.  Both agree as sets whenever at most
+//                     maxHits triangles overlap; `overflow` flags the queries where more do.
 struct OvlTop {
     float depth[CQ_MAX_OVERLAP_HITS];
+    int rank[CQ_MAX_OVERLAP_HITS];
     int gid[CQ_MAX_OVERLAP_HITS];
     uint32_t enc[CQ_MAX_OVERLAP_HITS];
-    int count, total, cap, _pad;
+    int count, total, cap, tie;
 };
 
 struct OverlapTopK {
     OvlTop *tops; // the warp's 32 records
+    const int32_t *rank;
+    bool byRank; // keep the smallest ranks (overlap-all in reference order) instead of the deepest
     __device__ __forceinline__ void operator()(QShared &, float depth, int gid, uint32_t enc, f3) const {
         OvlTop &t = tops[enc >> 27];
+        const int rk = pool_rank(rank, gid);
         t.total++;
         int pos = t.count;
-        while (pos > 0 && (t.depth[pos - 1] < depth || (t.depth[pos - 1] == depth && t.gid[pos - 1] > gid))) pos--;
+        if (byRank) {
+            while (pos > 0 && t.rank[pos - 1] > rk) pos--;
+        } else {
+            if (t.count > 0 && t.depth[0] == depth) t.tie = 1; // exactly as deep as the deepest so far
+            while (pos > 0 && (t.depth[pos - 1] < depth || (t.depth[pos - 1] == depth && t.rank[pos - 1] > rk))) pos--;
+            if (pos == 0 && t.count > 0 && t.depth[0] != depth) t.tie = 0; // a strictly deeper one: the old tie is moot
+        }
         if (pos >= t.cap) return;
         int last = t.count < t.cap ? t.count : t.cap - 1;
         for (int k = last; k > pos; k--) {
             t.depth[k] = t.depth[k - 1];
+            t.rank[k] = t.rank[k - 1];
             t.gid[k] = t.gid[k - 1];
             t.enc[k] = t.enc[k - 1];
         }
         t.depth[pos] = depth;
+        t.rank[pos] = rk;
         t.gid[pos] = gid;
         t.enc[pos] = enc;
         if (t.count < t.cap) t.count++;
@@ -301,7 +474,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
     __shared__ uint32_t words[CQ_POOL_WORDS * CAST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpPool wp;
-    pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS);
+    pool_bind(wp, qsAll, words, nodeScratch, warp, CAST_WARPS, W.rank, W.status);
     OvlTop &top = tops[threadIdx.x];
     Counters ctr = {0, 0, 0, 0};
     int cur = -1;
@@ -323,6 +496,8 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
             if (ALL) {
                 counts[cur] = top.count;
                 if (overflow) overflow[cur] = top.total > maxHits ? 1 : 0;
+            } else if (overflow) { // capsuleOverlap: the flags byte
+                overflow[cur] = top.tie ? CQ_HIT_TIE : 0;
             }
         }
         cur = atomicAdd(workCounter, 1);
@@ -332,10 +507,10 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
         }
         cq_capsule c = qs[cur];
         curFrom = load3(c.from), curR = c.radius, curHH = c.half_height;
-        top.count = 0, top.total = 0, top.cap = ALL ? maxHits : 1;
+        top.count = 0, top.total = 0, top.cap = ALL ? maxHits : 1, top.tie = 0;
         pool_post_overlap<COUNT>(W, wp, lane, mine, curFrom, curR, curHH, c.mask, ct);
         return true;
-    }, OverlapTopK{tops + warp * 32});
+    }, OverlapTopK{tops + warp * 32, W.rank, ALL && W.rank != nullptr});
     flush_counters<COUNT>(ctr, gctr);
 }
 
@@ -344,37 +519,39 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 #undef CQ_OCC_SLOT
 #define CQ_OCC_SLOT 1
-int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, cudaStream_t st) {
+int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, uint8_t *d_flags, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
     int *blocksPerSm = w->occ[CQ_OCC_SLOT]; int &numSms = w->numSms;
-    const int ci = w->counting ? 1 : 0;
+    const bool ref = w->order == CQ_ORDER_REFERENCE; // the reference's own walk over the reference's own tree
+    const int ci = (w->counting ? 1 : 0) + (ref ? 2 : 0);
+    using Kernel = void (*)(WorldView, const cq_ray *, int, cq_ray_hit *, uint8_t *, int *, const uint32_t *, unsigned long long *);
+    static const Kernel kernels[4] = {k_raycast<false>, k_raycast<true>, k_raycast_ref<false>, k_raycast_ref<true>};
+    const Kernel kernel = kernels[ci];
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;
         CQ_CUDA(cudaGetDeviceProperties(&prop, w->device));
         numSms = prop.multiProcessorCount;
         int b = 0;
-        if (ci) CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_raycast<true>, Q_THREADS, 0));
-        else CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_raycast<false>, Q_THREADS, 0));
+        CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, Q_THREADS, 0));
         blocksPerSm[ci] = b > 0 ? b : 1;
     }
     int blocks = std::min(cdiv(n, Q_THREADS), numSms * blocksPerSm[ci]); // one resident wave of persistent lanes
     int *work = next_work_counter(w, st);
     if (!work) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_rays, sizeof(cq_ray), false, n, st);
-    if (w->counting) k_raycast<true><<<blocks, Q_THREADS, 0, st>>>(w->view, d_rays, n, d_out, work, order, w->dCounters);
-    else k_raycast<false><<<blocks, Q_THREADS, 0, st>>>(w->view, d_rays, n, d_out, work, order, w->dCounters);
+    kernel<<<blocks, Q_THREADS, 0, st>>>(w->view, d_rays, n, d_out, d_flags, work, order, w->dCounters);
     w->launches++;
-    return finish_launch(w, st, "k_raycast");
+    return finish_launch(w, st, ref ? "k_raycast_ref" : "k_raycast");
 }
 
 #undef CQ_OCC_SLOT
 #define CQ_OCC_SLOT 2
-int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, cudaStream_t st) {
+int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cast_hit *d_out, uint8_t *d_flags, cudaStream_t st) {
     if (n <= 0) return CQ_OK;
     int *blocksPerSm = w->occ[CQ_OCC_SLOT]; int &numSms = w->numSms;
     const int ci = (w->counting ? 1 : 0) + 2 * (w->view.stagedLeaves ? 1 : 0);
-    using Kernel = void (*)(WorldView, const cq_capsule_cast *, int, int, cq_cast_hit *, int, uint2 *, int *, const uint32_t *,
-                            unsigned long long *);
+    using Kernel = void (*)(WorldView, const cq_capsule_cast *, int, int, cq_cast_hit *, uint8_t *, int, uint2 *, int *,
+                            const uint32_t *, unsigned long long *);
     static const Kernel kernels[4] = {k_capsule_cast<false, false>, k_capsule_cast<true, false>, k_capsule_cast<false, true>,
                                       k_capsule_cast<true, true>};
     const Kernel kernel = kernels[ci];
@@ -393,7 +570,7 @@ int launch_cast(cq_world *w, const cq_capsule_cast *d_q, int n, int mode, cq_cas
     uint2 *ns = (uint2 *)pool_node_scratch(w, (size_t)blocks * CAST_WARPS, st);
     if (!ns) return CQ_ERR_CUDA;
     const uint32_t *order = make_unit_order(w, d_q, sizeof(cq_capsule_cast), false, n, st);
-    kernel<<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, opw, ns, work, order, w->dCounters);
+    kernel<<<blocks, Q_THREADS, 0, st>>>(w->view, d_q, n, mode, d_out, d_flags, opw, ns, work, order, w->dCounters);
     w->launches++;
     return finish_launch(w, st, "k_capsule_cast");
 }
@@ -431,8 +608,8 @@ static int launch_overlap_pool(cq_world *w, const cq_capsule *d_q, int n, int ma
     return finish_launch(w, st, "k_capsule_overlap_pool");
 }
 
-int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, cudaStream_t st) {
-    return launch_overlap_pool<false>(w, d_q, n, 1, d_out, nullptr, nullptr, st);
+int launch_overlap(cq_world *w, const cq_capsule *d_q, int n, cq_overlap_hit *d_out, uint8_t *d_flags, cudaStream_t st) {
+    return launch_overlap_pool<false>(w, d_q, n, 1, d_out, nullptr, d_flags, st);
 }
 
 int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, cq_overlap_hit *d_out, int32_t *d_counts,

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_turns(WorldView W, const
     uint32_t *words = reinterpret_cast<uint32_t *>(sepSmem + (sizeof(SepCtx) + sizeof(QShared)) * SEP_THREADS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpPool wp;
-    pool_bind(wp, qsAll, words, nodeScratch, warp, SEP_WARPS);
+    pool_bind(wp, qsAll, words, nodeScratch, warp, SEP_WARPS, W.rank, W.status);
     SepCtx &c = ctxs[threadIdx.x];
     c.agent = -1;
     c.wait = SW_NONE;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_turns(WorldView W, const
         QResult r;
         pool_read_result(mine, r);
         return sep_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);
-    }, OverlapTop2());
+    }, OverlapTop2{W.rank});
     pool_flush_counters(ctr, gctr, COUNT);
 }
 
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_post(WorldView W, const 
     uint32_t *words = reinterpret_cast<uint32_t *>(sepSmem + (sizeof(PostCtx) + sizeof(QShared)) * SEP_THREADS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpPool wp;
-    pool_bind(wp, qsAll, words, nodeScratch, warp, SEP_WARPS);
+    pool_bind(wp, qsAll, words, nodeScratch, warp, SEP_WARPS, W.rank, W.status);
     PostCtx &c = ctxs[threadIdx.x];
     c.agent = -1;
     c.wait = PW_NONE;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_post(WorldView W, const 
         QResult r;
         pool_read_result(mine, r);
         return post_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);
-    }, OverlapTop2());
+    }, OverlapTop2{W.rank});
     pool_flush_counters(ctr, gctr, COUNT);
 }
 

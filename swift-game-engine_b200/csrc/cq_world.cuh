@@ -47,12 +47,25 @@ struct SetView {
     const Node4 *nodes4;
     const SetHeader *hdr;
     int triOffset; // added to triangle ids of this set (dynamic set: static count, CollisionQuery.swift:782)
+    // Reference order only (cq_reftree.h): the reference's own median-split tree as 64-byte nodes (child 0 = left,
+    // child 1 = right; a leaf reference ~((start << 2) | (count - 1)) names positions of refSlot), walked by the ray
+    // kernel exactly as CollisionQuery.swift:916-978 walks it.  refSlot: triOrder position -> slot of the sorted SoA.
+    const Node *refNodes;
+    const uint32_t *refSlot;
+    const SetHeader *refHdr;
 };
 
 struct WorldView {
     SetView set[2];
     const float4 *materials; // per part: (muS, muK, flattenGround, -)
     int nParts;
+    // Visiting rank of every triangle (global triangle index -> position in the reference's depth-first order, static
+    // set first), or nullptr in canonical order, where the rank of a triangle is its index.  Exact ties (equal toi /
+    // depth) go to the smaller rank; capsuleOverlapAll keeps the maxHits smallest ranks (CollisionQuery.swift:1272-1274).
+    const int32_t *rank;
+    // Device-visible status word in mapped host memory (zero = fine).  Bit 0: a warp's node stack would have overflowed
+    // (cq_pool.cuh) — the launch's results are incomplete; the next synchronising call reports CQ_ERR_CUDA.
+    unsigned int *status;
     int stagedLeaves; // which kernel variant the launchers pick: 1 = walk expands leaf ranges one triangle per lane
                       // (worlds that do not fit L1); the tiny-world variant keeps the shorter per-lane loop
 };

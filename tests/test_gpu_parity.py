@@ -1,7 +1,10 @@
 """GPU parity tests proper: the CUDA path (through the C ABI, libcq.so) against the CPU oracle on the
 same seeded inputs.  Bar (BASELINE.json north_star): hit / no-hit and triangle index bit-exact except
 flagged exact-tie cases; toi / normals / positions within 1e-4 rel, 1e-5 abs — in practice the two
-sides run the same IEEE op sequence, so the CANONICAL-order oracle must match BIT-EXACTLY on every field."""
+sides run the same IEEE op sequence, so the oracle must match BIT-EXACTLY on every field, ties included:
+a world created in CQ_ORDER_REFERENCE (the default) against the oracle's ORDER_REFERENCE (the reference's own
+BVH and depth-first visiting order), a CQ_ORDER_CANONICAL world against ORDER_CANONICAL.  The two order
+constants have the same values on both sides, so `g.order` is passed to the oracle."""
 import numpy as np
 import pytest
 
@@ -14,12 +17,15 @@ def _fields_equal(a, b, fields):
     return {f: bool(np.array_equal(a[f], b[f])) for f in fields}
 
 
-@pytest.fixture(scope="module", params=["hulls", "render"])
+@pytest.fixture(scope="module", params=["hulls-reference", "hulls-canonical", "render-reference", "render-canonical"])
 def world(request, cq, orc, scenes):
-    parts = scenes.mirror_scene(use_hulls=request.param == "hulls")
-    g = cq.CollisionQuery(parts)
+    name, order = request.param.split("-")
+    assert (cq.ORDER_REFERENCE, cq.ORDER_CANONICAL) == (orc.ORDER_REFERENCE, orc.ORDER_CANONICAL)
+    parts = scenes.mirror_scene(use_hulls=name == "hulls")
+    g = cq.CollisionQuery(parts, order=cq.ORDER_REFERENCE if order == "reference" else cq.ORDER_CANONICAL)
+    assert g.info()["order"] == g.order
     o = orc.OracleWorld(parts)
-    yield request.param, parts, g, o
+    yield name, parts, g, o
     g.close()
     o.close()
 
@@ -38,7 +44,7 @@ def test_soup_upload_matches_reference_rebuild(world):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_capsule_cast_bit_exact_vs_canonical_oracle(world, scenes, orc, mode):
+def test_capsule_cast_bit_exact_vs_oracle(world, cq, scenes, orc, mode):
     name, parts, g, o = world
     lo, hi = scenes.scene_aabb(parts[1:])
     n = 20000 if name == "hulls" else 3000
@@ -46,20 +52,25 @@ def test_capsule_cast_bit_exact_vs_canonical_oracle(world, scenes, orc, mode):
     q["delta"][:7] = 0  # zero-length sweeps -> nil (CollisionQuery.swift:988)
     q["mask"][7:40] = 1  # ground plane only
     q["mask"][40:60] = 2  # nothing on this layer
-    got = [g.capsuleCast, g.capsuleCastBlocking, g.capsuleCastGround][mode](q)
-    ref = o.capsule_cast(q, mode, orc.ORDER_CANONICAL)
+    got, flags = [g.capsuleCast, g.capsuleCastBlocking, g.capsuleCastGround][mode](q, with_flags=True)
+    ref = o.capsule_cast(q, mode, g.order)
     assert (got["triangle_index"][:7] == -1).all() and (got["triangle_index"][40:60] == -1).all()
     assert np.array_equal(got["triangle_index"], ref["triangle_index"])
     for f in ("toi", "position", "normal", "triangle_normal"):
         assert np.array_equal(got[f], ref[f]), f
     assert (got["triangle_index"] >= 0).sum() > n // 10
-    # against the reference's own visiting order: only exact-tie cases may name another triangle
-    ref2 = o.capsule_cast(q, mode, orc.ORDER_REFERENCE)
-    assert np.array_equal(got["triangle_index"] >= 0, ref2["triangle_index"] >= 0)
-    assert np.array_equal(got["toi"], ref2["toi"])  # the winning toi is order-independent
-    diff = got["triangle_index"] != ref2["triangle_index"]
-    # every index mismatch is an exact toi tie (degenerate edge/vertex contact)
-    assert np.array_equal(got["toi"][diff], ref2["toi"][diff])
+    # against the OTHER order rule: the winning toi is order-independent, only the triangle named on an exact tie may
+    # differ — and every such query carries the TIE flag (unflagged mismatches == 0)
+    other = o.capsule_cast(q, mode, orc.ORDER_CANONICAL if g.order == orc.ORDER_REFERENCE else orc.ORDER_REFERENCE)
+    assert np.array_equal(got["triangle_index"] >= 0, other["triangle_index"] >= 0)
+    assert np.array_equal(got["toi"], other["toi"])
+    diff = got["triangle_index"] != other["triangle_index"]
+    assert (flags[diff] & cq.HIT_TIE).all() and not (flags[got["triangle_index"] < 0]).any()
+    if name == "render":
+        assert diff.any() and (flags & cq.HIT_TIE).mean() > 0.05  # shared edges / vertices of a closed mesh tie all the time
+    st = orc.Stats()
+    o.capsule_cast(q, mode, g.order, 1, st)
+    assert int((flags & cq.HIT_TIE).astype(bool).sum()) == st.ties
 
 
 def test_capsule_overlap_bit_exact(world, scenes, orc):
@@ -67,8 +78,11 @@ def test_capsule_overlap_bit_exact(world, scenes, orc):
     lo, hi = scenes.scene_aabb(parts[1:])
     n = 20000 if name == "hulls" else 4000
     c = scenes.gen_capsules(n, lo, hi, seed=7)
-    got = g.capsuleOverlap(c)
-    ref = o.capsule_overlap(c, orc.ORDER_CANONICAL)
+    got, flags = g.capsuleOverlap(c, with_flags=True)
+    ref = o.capsule_overlap(c, g.order)
+    other = o.capsule_overlap(c, orc.ORDER_CANONICAL if g.order == orc.ORDER_REFERENCE else orc.ORDER_REFERENCE)
+    diff = got["triangle_index"] != other["triangle_index"]
+    assert np.array_equal(got["depth"], other["depth"]) and (flags[diff] & 1).all()
     for f in ("triangle_index", "depth", "position", "normal", "triangle_normal"):
         assert np.array_equal(got[f], ref[f]), f
     assert (got["triangle_index"] >= 0).sum() > n // 20
@@ -81,18 +95,21 @@ def test_capsule_overlap_all_bit_exact(world, scenes, orc):
     c = scenes.gen_capsules(n, lo, hi, seed=8)
     for max_hits in (8, 3):
         got, gcnt, gov = g.capsuleOverlapAll(c, max_hits)
-        ref, rcnt, rov = o.capsule_overlap_all(c, max_hits, orc.ORDER_CANONICAL)
+        ref, rcnt, rov = o.capsule_overlap_all(c, max_hits, g.order)
         assert np.array_equal(gcnt, rcnt) and np.array_equal(gov, rov)
         for f in ("triangle_index", "depth", "position", "normal", "triangle_normal"):
             assert np.array_equal(got[f], ref[f]), f
-        # reference order: same SET of triangles whenever it did not overflow
-        ref2, rcnt2, rov2 = o.capsule_overlap_all(c, max_hits, orc.ORDER_REFERENCE)
+        # the other order rule: same SET of triangles whenever it did not overflow
+        ref2, rcnt2, rov2 = o.capsule_overlap_all(c, max_hits, orc.ORDER_CANONICAL if g.order == orc.ORDER_REFERENCE
+                                                  else orc.ORDER_REFERENCE)
         ok = rov2 == 0
-        assert np.array_equal(gcnt[ok], rcnt2[ok])
+        assert np.array_equal(gov, rov2) and np.array_equal(gcnt[ok], rcnt2[ok])
         assert np.array_equal(np.sort(got["triangle_index"][ok], axis=1), np.sort(ref2["triangle_index"][ok], axis=1))
+        if name == "render" and max_hits == 3:
+            assert gov.sum() > 50  # the first-visited rule is really exercised
 
 
-def test_raycast_vs_oracle(world, scenes, orc):
+def test_raycast_vs_oracle(world, cq, scenes, orc):
     name, parts, g, o = world
     lo, hi = scenes.scene_aabb(parts)
     n = 20000 if name == "hulls" else 3000
@@ -100,18 +117,25 @@ def test_raycast_vs_oracle(world, scenes, orc):
     r["direction"][:100] *= 3.5  # direction is not normalised by the callee
     r["direction"][100:110, 0] = 0  # axis-parallel components -> 1/0 replacement path
     r["mask"][110:130] = 2
-    got = g.raycast(r)
-    ref = o.raycast(r, orc.ORDER_CANONICAL)  # brute force over all triangles
+    got, flags = g.raycast(r, with_flags=True)
+    ref = o.raycast(r, g.order)  # reference order: the reference's own walk; canonical: brute force over all triangles
     for f in ("triangle_index", "distance", "position", "normal"):
         assert np.array_equal(got[f], ref[f]), f
     assert (got["triangle_index"] >= 0).sum() > n // 10
-    ref2 = o.raycast(r, orc.ORDER_REFERENCE)
-    # the reference's own BVH walk may miss grazing hits its non-conservative slab test culls; it must
-    # never find something closer than the all-triangles minimum
-    both = (ref2["triangle_index"] >= 0) & (got["triangle_index"] >= 0)
-    assert (got["distance"][both] <= ref2["distance"][both]).all()
-    assert (np.array_equal(got["triangle_index"], ref2["triangle_index"])
-            or (got["triangle_index"] != ref2["triangle_index"]).mean() < 0.01)
+    # Classification of every difference between the two order rules (canonical = minimum over ALL triangles):
+    #   tie      same distance, another triangle                         -> must carry the TIE flag in the world that saw both
+    #   culled   the reference's walk lost a nearer / the only hit to its non-conservative slab test (:933, :1603-1631)
+    #   other    anything else — must not exist
+    can = got if g.order == orc.ORDER_CANONICAL else o.raycast(r, orc.ORDER_CANONICAL)
+    refo = got if g.order == orc.ORDER_REFERENCE else o.raycast(r, orc.ORDER_REFERENCE)
+    diff = can["triangle_index"] != refo["triangle_index"]
+    both = (can["triangle_index"] >= 0) & (refo["triangle_index"] >= 0)
+    tie = diff & both & (can["distance"] == refo["distance"])
+    culled = diff & (can["triangle_index"] >= 0) & ((refo["triangle_index"] < 0) | (refo["distance"] > can["distance"]))
+    assert not (diff & ~tie & ~culled).any()
+    assert diff.mean() < 0.01
+    if g.order == orc.ORDER_CANONICAL:
+        assert (flags[tie] & cq.HIT_TIE).all()
 
 
 def test_move_and_slide_bit_exact_multi_step(world, cq, scenes, orc):
@@ -129,7 +153,7 @@ def test_move_and_slide_bit_exact_multi_step(world, cq, scenes, orc):
     assert pg.tobytes() == po.tobytes()
     for step in range(6):
         g.move_and_slide(sg, pg)
-        o.move_and_slide(so, po, order=orc.ORDER_CANONICAL)
+        o.move_and_slide(so, po, order=g.order)
         for f in sg.dtype.names:
             if f == "_pad":
                 continue
@@ -147,7 +171,7 @@ def test_move_and_slide_human_scale_params(world, cq, scenes, orc):
     po = orc.default_params(radius=0.4, half_height=0.5, skin_width=0.08, fall_probe_distance=50.0)
     for step in range(4):
         g.move_and_slide(sg, pg, flags=0)
-        o.move_and_slide(so, po, flags=0, order=orc.ORDER_CANONICAL)
+        o.move_and_slide(so, po, flags=0, order=g.order)
     assert sg.tobytes() == so.tobytes()
 
 
@@ -171,9 +195,9 @@ def test_refit_matches_reference_update_transforms(cq, orc, scenes):
         gs, os_ = g.read_soup(1), o.read_soup(1)
         for k in ("positions", "aabbs"):
             assert np.array_equal(gs[k], os_[k]), (step, k)
-        got, ref = g.capsuleCast(qs), o.capsule_cast(qs, 0, orc.ORDER_CANONICAL)
+        got, ref = g.capsuleCast(qs), o.capsule_cast(qs, 0, g.order)
         assert got.tobytes() == ref.tobytes()
-        gr, rr = g.raycast(rays), o.raycast(rays, orc.ORDER_CANONICAL)
+        gr, rr = g.raycast(rays), o.raycast(rays, g.order)
         assert np.array_equal(gr["triangle_index"], rr["triangle_index"])
         assert np.array_equal(gr["distance"], rr["distance"])
     with pytest.raises(cq.CQError):
@@ -201,7 +225,7 @@ def test_empty_and_tiny_worlds(cq, orc, scenes):
         g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
         assert g.info()["n_static_triangles"] == o.counts(0)["triangles"]
         q = scenes.gen_casts(512, [-5, 0, -5], [5, 3, 5], seed=3, expand=1.0)
-        assert g.capsuleCast(q).tobytes() == o.capsule_cast(q, 0, orc.ORDER_CANONICAL).tobytes()
+        assert g.capsuleCast(q).tobytes() == o.capsule_cast(q, 0, g.order).tobytes()
         g.close()
         o.close()
 
@@ -218,7 +242,7 @@ def test_static_and_dynamic_sets_index_offset(cq, orc, scenes):
     inf = g.info()
     assert inf["n_static_triangles"] == 14 and inf["n_dynamic_triangles"] == 12
     q = scenes.gen_casts(4000, [-4, 0, -4], [8, 4, 4], seed=5, radius=0.5, half_height=0.5, expand=0.5)
-    got, ref = g.capsuleCast(q), o.capsule_cast(q, 0, orc.ORDER_CANONICAL)
+    got, ref = g.capsuleCast(q), o.capsule_cast(q, 0, g.order)
     assert got.tobytes() == ref.tobytes()
     assert (got["triangle_index"] >= 14).any()
     assert g.triangle_material(0)["mu_s"] == pytest.approx(0.8)
@@ -254,14 +278,12 @@ def test_terrain_lbvh_and_blocking_sweeps(cq, orc, scenes):
     assert np.array_equal(gs["positions"], os_["positions"]) and np.array_equal(gs["aabbs"], os_["aabbs"])
     for r, hh in ((0.4, 0.5), (1.5, 1.0)):
         q = scenes.gen_c4_casts(20000, half, seed=41, radius=r, half_height=hh)
-        got, ref = g.capsuleCastBlocking(q), o.capsule_cast(q, 1, orc.ORDER_CANONICAL)
+        got, ref = g.capsuleCastBlocking(q), o.capsule_cast(q, 1, g.order)
         assert got.tobytes() == ref.tobytes()
         assert (got["triangle_index"] >= 0).mean() > 0.2
     rays = scenes.gen_rays(20000, [-half, -10, -half], [half, 30, half], seed=42, expand=0.0)
-    gr, rr = g.raycast(rays), o.raycast(rays, orc.ORDER_REFERENCE)
-    assert (gr["triangle_index"] != rr["triangle_index"]).mean() < 0.002
-    both = (gr["triangle_index"] >= 0) & (rr["triangle_index"] >= 0)
-    assert (gr["distance"][both] <= rr["distance"][both]).all()
+    gr, rr = g.raycast(rays), o.raycast(rays, g.order)
+    assert gr.tobytes() == rr.tobytes() and (gr["triangle_index"] >= 0).mean() > 0.3
     # characters walking on the terrain, human scale
     x = np.random.default_rng(3).uniform(-half + 10, half - 10, (4096, 2))
     y = scenes.terrain_height(x[:, 0], x[:, 1]) + 0.9 + 0.3
@@ -271,7 +293,7 @@ def test_terrain_lbvh_and_blocking_sweeps(cq, orc, scenes):
     kw = dict(radius=0.4, half_height=0.5, skin_width=0.08)
     for _ in range(4):
         g.move_and_slide(sg, cq.default_params(**kw))
-        o.move_and_slide(so, orc.default_params(**kw), order=orc.ORDER_CANONICAL)
+        o.move_and_slide(so, orc.default_params(**kw), order=g.order)
     assert sg.tobytes() == so.tobytes()
     assert sg["grounded"].mean() > 0.8
     g.close()
@@ -295,7 +317,7 @@ def test_onesweep_sort_builds_the_same_tree_as_the_classic_sort(cq, orc, scenes,
         g.close()
     assert out["classic"] == out["onesweep"]
     o = orc.OracleWorld(parts)
-    assert out["onesweep"][0] == o.capsule_cast(q, 1, orc.ORDER_CANONICAL).tobytes()
+    assert out["onesweep"][0] == o.capsule_cast(q, 1, orc.ORDER_REFERENCE).tobytes()  # worlds default to reference order
 
 
 def test_c2_sweeps_against_semla(cq, orc, scenes):
@@ -306,14 +328,18 @@ def test_c2_sweeps_against_semla(cq, orc, scenes):
     assert g.info()["n_static_triangles"] == o.counts(0)["triangles"] == 50004
     lo, hi = scenes.scene_aabb(parts[1:])
     q = scenes.gen_casts(4096, lo, hi, seed=0xC0111DE2)
-    got = g.capsuleCast(q)
-    assert got.tobytes() == o.capsule_cast(q, 0, orc.ORDER_CANONICAL, 8).tobytes()
-    ref = o.capsule_cast(q, 0, orc.ORDER_REFERENCE, 8)
-    assert np.array_equal(got["toi"], ref["toi"]) and np.array_equal(got["triangle_index"] >= 0, ref["triangle_index"] >= 0)
+    got, flags = g.capsuleCast(q, with_flags=True)
+    assert got.tobytes() == o.capsule_cast(q, 0, g.order, 8).tobytes()  # the reference's own answers, ties included
+    can = o.capsule_cast(q, 0, orc.ORDER_CANONICAL, 8)
+    gc = cq.CollisionQuery(parts, order=cq.ORDER_CANONICAL)
+    assert gc.capsuleCast(q).tobytes() == can.tobytes()
+    gc.close()
+    diff = got["triangle_index"] != can["triangle_index"]
+    assert 0.1 < diff.mean() < 0.6 and (flags[diff] & cq.HIT_TIE).all()  # ~30% of these sweeps end on a shared edge / vertex
     assert (got["triangle_index"] >= 0).mean() > 0.4
     hq = scenes.gen_casts(4096, lo, hi, seed=5)
     gh, oh = cq.CollisionQuery(scenes.semla_scene(use_hulls=True)), orc.OracleWorld(scenes.semla_scene(use_hulls=True))
-    assert gh.capsuleCastBlocking(hq).tobytes() == oh.capsule_cast(hq, 1, orc.ORDER_CANONICAL).tobytes()
+    assert gh.capsuleCastBlocking(hq).tobytes() == oh.capsule_cast(hq, 1, gh.order).tobytes()
     for w in (g, o, gh, oh):
         w.close()
 
@@ -333,28 +359,30 @@ def test_c5_merged_scene_rays_and_refit(cq, orc, scenes):
         model = scenes.trs_model(t, rot, s)
         g.update_transforms([3], [model])
         o.update_transforms([3], [model])
-        gr, rr = g.raycast(rays), o.raycast(rays, orc.ORDER_REFERENCE, 8)
-        both = (gr["triangle_index"] >= 0) & (rr["triangle_index"] >= 0)
-        assert (gr["triangle_index"] != rr["triangle_index"]).mean() < 0.002
-        assert (gr["distance"][both] <= rr["distance"][both]).all()
+        gr, rr = g.raycast(rays), o.raycast(rays, g.order, 8)
+        assert gr.tobytes() == rr.tobytes()  # the reference's own walk over its refitted tree, grazing culls included
+        assert (gr["triangle_index"] >= 0).mean() > 0.2
     qs = scenes.gen_casts(1500, lo, hi, seed=9, expand=1.0)
-    assert g.capsuleCast(qs).tobytes() == o.capsule_cast(qs, 0, orc.ORDER_CANONICAL, 8).tobytes()
+    assert g.capsuleCast(qs).tobytes() == o.capsule_cast(qs, 0, g.order, 8).tobytes()
     g.close()
     o.close()
 
 
 def test_c1_trajectory_matches_golden(cq, scenes):
     """Config C1 on the GPU: 4 characters driven for 600 fixed steps over the demo's static world must reproduce
-    the committed golden trajectory (tests/golden/c1_trajectory.npz, canonical order) bit for bit."""
+    the committed golden trajectories (tests/golden/c1_trajectory.npz) bit for bit: the reference-order one in the
+    default order — the trajectory the reference itself walks, ties resolved by ITS visiting order, which the contact
+    cache keyed by triangle index makes visible from frame 203 on — and the canonical one in canonical order."""
     import os
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_trajectory.npz"))
-    g = cq.CollisionQuery(scenes.c1_scene())
-    s = cq.init_states(scenes.C1_STARTS)
-    p = cq.default_params()
-    rec = scenes.c1_run(lambda st: g.move_and_slide(st, p), s, 600, scenes.C1_SPEEDS)
-    for k in rec.dtype.names:
-        assert np.array_equal(rec[k], z[f"canonical_{k}"]), k
-    g.close()
+    for order, tag in ((cq.ORDER_REFERENCE, "reference"), (cq.ORDER_CANONICAL, "canonical")):
+        g = cq.CollisionQuery(scenes.c1_scene(), order=order)
+        s = cq.init_states(scenes.C1_STARTS)
+        p = cq.default_params()
+        rec = scenes.c1_run(lambda st: g.move_and_slide(st, p), s, 600, scenes.C1_SPEEDS)
+        for k in rec.dtype.names:
+            assert np.array_equal(rec[k], z[f"{tag}_{k}"]), (tag, k)
+        g.close()
 
 
 def test_parameter_edge_cases(cq, orc, scenes):
@@ -367,20 +395,20 @@ def test_parameter_edge_cases(cq, orc, scenes):
         q = scenes.gen_casts(3000, lo, hi, seed=int(r * 1000), radius=r, half_height=hh, len_range=(0.001, 1.0))
         for mode in (0, 1, 2):
             got = [g.capsuleCast, g.capsuleCastBlocking, g.capsuleCastGround][mode](q)
-            assert got.tobytes() == o.capsule_cast(q, mode, orc.ORDER_CANONICAL).tobytes(), (r, hh, mode)
+            assert got.tobytes() == o.capsule_cast(q, mode, g.order).tobytes(), (r, hh, mode)
     pos, vel = scenes.gen_c3_characters(1024, seed=5)
     for kw in (dict(max_slide_iterations=1), dict(snap_distance=0.0), dict(fall_probe_distance=0.0),
                dict(collision_mask=1), dict(collision_mask=1 << 4), dict(skin_width=0.0, ground_snap_skin=0.0)):
         sg, so = cq.init_states(pos, vel), orc.init_states(pos, vel)
         for _ in range(3):
             g.move_and_slide(sg, cq.default_params(**kw))
-            o.move_and_slide(so, orc.default_params(**kw), order=orc.ORDER_CANONICAL)
+            o.move_and_slide(so, orc.default_params(**kw), order=g.order)
         assert sg.tobytes() == so.tobytes(), kw
     rparts = scenes.mirror_scene(use_hulls=False)
     gr, orr = cq.CollisionQuery(rparts), orc.OracleWorld(rparts)
     c = scenes.gen_capsules(2000, lo, hi, seed=8, expand=0.2)
     got, cnt, ov = gr.capsuleOverlapAll(c, 8)
-    ref, rcnt, rov = orr.capsule_overlap_all(c, 8, orc.ORDER_CANONICAL)
+    ref, rcnt, rov = orr.capsule_overlap_all(c, 8, gr.order)
     assert ov.sum() > 100 and np.array_equal(ov, rov) and np.array_equal(cnt, rcnt) and got.tobytes() == ref.tobytes()
     for w in (g, o, gr, orr):
         w.close()
@@ -411,7 +439,7 @@ def test_kinematic_platforms_carry_and_push(cq, orc, scenes):
         o.update_transforms([1, 2], models)
         plats = np.concatenate([scenes.platform_record(bv, models[k], prev[k], cur[k]) for k in range(2)])
         g.move_and_slide(sg, cq.default_params(), platforms=plats)
-        o.move_and_slide(so, orc.default_params(), platforms=plats, order=orc.ORDER_CANONICAL)
+        o.move_and_slide(so, orc.default_params(), platforms=plats, order=g.order)
         assert sg.tobytes() == so.tobytes(), step
         prev = cur
     carried = sg["position"][:, 1] > 2.0
@@ -447,9 +475,9 @@ def test_agents_capsule_capsule_ccd(cq, orc, scenes):
     for step in range(8):
         ghost = so.copy()
         g.move_and_slide(sg, p, flags=cq.MAS_APPLY_GRAVITY | cq.MAS_AGENTS)
-        o.move_and_slide(so, p, flags=3, order=orc.ORDER_CANONICAL, n_threads=8)
+        o.move_and_slide(so, p, flags=3, order=g.order, n_threads=8)
         assert sg.tobytes() == so.tobytes(), step
-        o.move_and_slide(ghost, p, flags=1, order=orc.ORDER_CANONICAL, n_threads=8)
+        o.move_and_slide(ghost, p, flags=1, order=g.order, n_threads=8)
         agent_hits += int((ghost["position"] != so["position"]).any(axis=1).sum())
         for s in (sg, so):
             s["velocity"][:, 0] = walk[:, 0]
@@ -468,7 +496,7 @@ def test_agents_capsule_capsule_ccd(cq, orc, scenes):
     fg, fo = cq.init_states(fpos, fwalk), orc.init_states(fpos, fwalk)
     for step in range(3):
         g2.move_and_slide(fg, p, flags=3, platforms=plat)
-        o2.move_and_slide(fo, p, flags=3, platforms=plat, order=orc.ORDER_CANONICAL, n_threads=8)
+        o2.move_and_slide(fo, p, flags=3, platforms=plat, order=g2.order, n_threads=8)
         assert fg.tobytes() == fo.tobytes(), step
     assert (np.abs(fg["position"][:, 0] - fpos[:, 0]) > 2.5).sum() > 50  # many were carried several cells away
     g2.close()
@@ -477,7 +505,7 @@ def test_agents_capsule_capsule_ccd(cq, orc, scenes):
     one = cq.init_states(pos[:1], walk[:1])
     ref = orc.init_states(pos[:1], walk[:1])
     g.move_and_slide(one, p, flags=3)
-    o.move_and_slide(ref, p, flags=3, order=orc.ORDER_CANONICAL)
+    o.move_and_slide(ref, p, flags=3, order=g.order)
     assert one.tobytes() == ref.tobytes()
     g.move_and_slide(one[:0].copy(), p, flags=3)
     g.close()
@@ -512,10 +540,10 @@ def test_agent_separation_sequential_semantics(cq, orc, scenes):
     total_pairs = 0
     for step in range(5):
         g.move_and_slide(sg, p, flags=3)
-        o.move_and_slide(so, p, flags=3, order=orc.ORDER_CANONICAL, n_threads=8)
+        o.move_and_slide(so, p, flags=3, order=g.order, n_threads=8)
         assert sg.tobytes() == so.tobytes(), ("move", step)
         g.agent_separation(sg, p, mass_weight=mass)
-        total_pairs += o.agent_separation(so, p, mass_weight=mass, order=orc.ORDER_CANONICAL, n_threads=8)
+        total_pairs += o.agent_separation(so, p, mass_weight=mass, order=g.order, n_threads=8)
         assert sg.tobytes() == so.tobytes(), ("separation", step)
         for s in (sg, so):
             s["velocity"][:, 0] = walk[:, 0]
@@ -545,7 +573,7 @@ def test_agent_separation_sequential_semantics(cq, orc, scenes):
     for uq in (False, True):
         a, b = cq.init_states(rows), orc.init_states(rows)
         g2.agent_separation(a, p, mass_weight=dmass, iterations=2, use_query=uq)
-        o2.agent_separation(b, p, mass_weight=dmass, iterations=2, use_query=uq, order=orc.ORDER_CANONICAL)
+        o2.agent_separation(b, p, mass_weight=dmass, iterations=2, use_query=uq, order=g2.order)
         assert a.tobytes() == b.tobytes(), uq
         assert (a["position"][8::10, 0] > 2.0).all()  # every light agent was pushed more than two cells
     g2.close()
@@ -554,7 +582,7 @@ def test_agent_separation_sequential_semantics(cq, orc, scenes):
     order = np.argsort(sg["position"][:, 0], kind="stable")
     a, b = np.ascontiguousarray(sg[order]), np.ascontiguousarray(so[order])
     g.agent_separation(a, p, mass_weight=mass[order])
-    o.agent_separation(b, p, mass_weight=mass[order], order=orc.ORDER_CANONICAL, n_threads=8)
+    o.agent_separation(b, p, mass_weight=mass[order], order=g.order, n_threads=8)
     assert a.tobytes() == b.tobytes()
     g.close()
     o.close()
@@ -582,7 +610,7 @@ def test_full_size_c3_sharding_invariance_and_sampled_parity(cq, orc, scenes):
         g.move_and_slide(b, p)
         halves = np.concatenate([a, b])
         assert whole.tobytes() == halves.tobytes(), step
-        o.move_and_slide(sample, p, order=orc.ORDER_CANONICAL, n_threads=8)
+        o.move_and_slide(sample, p, order=g.order, n_threads=8)
         assert whole[pick].tobytes() == sample.tobytes(), step
     assert whole["grounded"].mean() > 0.99
     g.close()
@@ -622,7 +650,7 @@ def test_full_size_c4_terrain_sweeps_properties(cq, orc, scenes):
     assert (longer["triangle_index"][hit][same] == whole["triangle_index"][hit][same]).mean() > 0.999
     pick = np.sort(np.random.default_rng(23).choice(n, 20000, replace=False))
     o = orc.OracleWorld(parts)
-    ref = o.capsule_cast(np.ascontiguousarray(q[pick]), 1, orc.ORDER_CANONICAL, n_threads=8)
+    ref = o.capsule_cast(np.ascontiguousarray(q[pick]), 1, g.order, n_threads=8)
     assert whole[pick].tobytes() == ref.tobytes()
     g.close()
     o.close()
@@ -699,7 +727,7 @@ def test_mesh_upload_many_parts_and_index_errors(cq, orc, scenes):
         assert np.array_equal(a["layers"], b["layers"]) and np.array_equal(a["parts"], b["parts"])
     q = scenes.gen_casts(4000, [-20, -22, -20], [20, 20, 20], seed=4, len_range=(0.5, 6.0))
     q["mask"] = rng.choice(np.uint32([0xFFFFFFFF, 1, 6, 32]), len(q))
-    assert g.capsuleCast(q).tobytes() == o.capsule_cast(q, 0, orc.ORDER_CANONICAL).tobytes()
+    assert g.capsuleCast(q).tobytes() == o.capsule_cast(q, 0, g.order).tobytes()
     g.close()
     o.close()
 
