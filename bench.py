@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py — move-and-slide capsule queries/sec (BASELINE.json metric), one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mesh hulls|render]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--only NAME] [--no-extras]
 
-Workload (config C3 of BASELINE.json / SURVEY.md §8d): 1,048,576 characters per GPU, one fixed step of
+Headline workload (config C3 of BASELINE.json / SURVEY.md §8d): 1,048,576 characters per GPU, one fixed step of
 the reference's KinematicMoveStopSystem body each (gravity -> decay -> velocity gate -> depenetration ->
 <= 4 blocking slide casts -> ground snap/fall/offset probes -> snap/friction -> writeback) over the
-ornate_mirror.static.json collision set at its demo placement + the 80x80 ground plane.
-  --mesh hulls  (default): the asset's 2 collision hulls — what the reference actually collides with
-  --mesh render          : the asset's 14,246-triangle render mesh through the same API
+ornate_mirror.static.json collision hulls at their demo placement + the 80x80 ground plane.  The world is created in
+CQ_ORDER_REFERENCE (the library's default): every answer, exact ties included, is the one the reference's own tree
+and visiting order give.
 
-A "step" = one pass of the hot path over the whole character batch; state is carried from step to step
-as in the engine.  `value` = device-resident throughput (CUDA events on the launch stream, max over
-ranks); `e2e` = the same step through the public host-pointer C-ABI call (pinned host buffers, H2D +
-kernel + D2H inside the timed region).  Multi-GPU: characters are sharded across ranks, mesh + BVH are
-replicated, no data-path collective (weak scaling); torch.distributed is used for the barrier and the
-max-over-ranks only.
+A "step" = one pass of the hot path over the whole batch; state is carried from step to step as in the engine.
+  value  device-resident throughput (CUDA events on the launch stream, max over ranks);
+  e2e    the same step through the public host-pointer C ABI with pinned HOST buffers, copies inside the timed region.
+         Headline e2e = cq_crowd_step (records resident in HBM — they are private to KinematicMoveStopSystem in the
+         reference too — velocities in, poses out); e2e.full_record = cq_move_and_slide_batch moving all 168 bytes of
+         every record both ways.
+  extra  the other BASELINE.json configurations at their named sizes, each with value / roofline / e2e:
+         terrain (the north-star target scene: move-and-slide over the 10 M-triangle terrain), render (C3 on the
+         14 k-triangle render mesh), c2 (65,536 sweeps vs Semla), c4 (8,388,608 blocking sweeps over the terrain),
+         c5 (16,777,216 rays + a refit per step).  With N > 1 the sharded legs run through the library's own NCCL
+         group (cq_group_*): c3_strong (1,048,576 characters in total), c4 (8,388,608 sweeps in total, the all-gather
+         of the hit records INSIDE the timed region, collective_ms beside it), c5 (16,777,216 rays in total).
+
+Multi-GPU: units are sharded across ranks (contiguous ranges), mesh + trees are replicated, no data-path collective in
+the move-and-slide step (weak scaling); torch.distributed is plumbing for the barrier, the max-over-ranks and the
+broadcast of the 128-byte NCCL id.
 """
 import argparse
 import importlib
@@ -25,6 +35,7 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 import numpy as np
 
@@ -68,6 +79,7 @@ CHARS_PER_GPU = 1 << 20
 SEED = 0xC0111DE3
 DT = 1.0 / 60.0
 GRAVITY = (0.0, -98.0, 0.0)
+FP32_PEAK_TINST = 148 * 128 * 1.965e9 / 1e12  # lanes x clock: issue ceiling with FMA off (1 flop / lane / clk)
 
 
 def load_peaks():
@@ -79,6 +91,15 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(kernel, config):
+    """DRAM bytes per unit of the dominant kernel from the committed `ncu --set full` captures (profiles/r2_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one launch divided by the units it processed)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[kernel][config]["dram_bytes_per_unit"]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -101,6 +122,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -142,11 +164,19 @@ class ClockSampler:
 
 
 TERRAIN_PARAMS = dict(radius=0.4, half_height=0.5, skin_width=0.08)  # human-scale capsule
+_TERRAIN = {}
 
 
-def make_workload(cq, mesh, n, rank, agents=0.0):
+def terrain_parts(cq, cells=2236):
+    """The 10 M-triangle procedural terrain (generated once per process: 2 s of numpy)."""
+    if cells not in _TERRAIN:
+        _TERRAIN[cells] = cq.scenes.terrain_scene(cells=cells, cell=2.0)
+    return _TERRAIN[cells]
+
+
+def make_workload(cq, mesh, n, rank, agents=0.0, cells=2236):
     if mesh == "terrain":  # the north-star target scene: 10 M-triangle procedural terrain, walkers all over it
-        parts, half = cq.scenes.terrain_scene(cells=2236, cell=2.0)
+        parts, half = terrain_parts(cq, cells)
         rng = np.random.default_rng(SEED + 77 + rank)
         span = half - 10
         if agents > 0:  # a crowd: the walkers' footprints cover `agents` of a square in the middle of the terrain
@@ -199,6 +229,7 @@ def run_reference(args):
     w = orc.OracleWorld(parts)
     s = orc.init_states(pos, vel)
     p = controller_params(orc, args.mesh)
+
     def ref_step():
         w.move_and_slide(s, p, DT, GRAVITY, mas_flags, orc.ORDER_REFERENCE, cores)
         if args.separation:
@@ -230,352 +261,363 @@ def run_reference(args):
     return 0
 
 
-# ------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+# ------------------------------------------------------------------------------------------ shared plumbing
+class Ctx:
+    """One process per GPU: torch for device memory / streams / the process group, nothing else."""
 
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa_node = bind_to_gpu_numa_node(local_rank)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.ws = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.lrank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
+        torch.cuda.set_device(self.lrank)
+        self.dev = torch.device("cuda", self.lrank)
+        self.numa = bind_to_gpu_numa_node(self.lrank)
+        if self.ws > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        # an explicit (non-default) stream: the library's NULL-stream convention means "the world's own stream", and
+        # torch.cuda.Event only sees torch's current stream, so make both the same real stream
+        self.tstream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
+        self.cq = importlib.import_module("swift-game-engine_b200")
+        self.cq.build()
+        self.group = None
 
-    def barrier():
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.ws > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def red(self, x, op="max"):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.ws > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def nccl_group(self):
+        """The library's own NCCL communicator over the ranks (cq_group_create_rank): rank 0 makes the 128-byte id,
+        torch.distributed ships it."""
+        if self.group is None:
+            uid = self.cq.Group.unique_id() if self.rank == 0 else np.zeros(self.cq.GROUP_ID_BYTES, np.uint8)
+            t = self.torch.from_numpy(uid.copy()).to(self.dev)
+            if self.ws > 1:
+                self.dist.broadcast(t, 0)
+            self.group = self.cq.Group.rank(self.ws, self.rank, t.cpu().numpy())
+        return self.group
 
-    cq = importlib.import_module("swift-game-engine_b200")
-    cq.build()
-    n = args.chars
-    parts, pos, vel = make_workload(cq, args.mesh, n, rank, args.agents)
-    mas_flags = cq.MAS_APPLY_GRAVITY | (cq.MAS_AGENTS if args.agents > 0 else 0)
-    world = cq.CollisionQuery(parts)
+    def up(self, a):
+        return self.torch.from_numpy(np.frombuffer(a.tobytes(), np.uint8).copy()).to(self.dev)
+
+    def events(self):
+        return self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+
+    def close(self):
+        if self.group is not None:
+            self.group.close()
+        if self.ws > 1:
+            self.dist.destroy_process_group()
+
+
+def time_steps(ctx, step, steps, warmup, sampler=None, keep_loaded=0.0):
+    """W warm-up steps, then K steps between a barrier + synchronize on both sides, CUDA events around every step and
+    around the whole region; returns (total ms max over ranks, mean per-step ms of this rank)."""
+    torch = ctx.torch
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    evs = [ctx.events() for _ in range(steps)]
+    ctx.barrier()
+    if sampler:
+        sampler.start()
+    t0, t1 = ctx.events()
+    t0.record()
+    for k in range(steps):
+        evs[k][0].record()
+        step()
+        evs[k][1].record()
+    t1.record()
+    ctx.barrier()
+    if keep_loaded > 0:
+        # the timed region lasts tens of milliseconds, shorter than one nvidia-smi sampling period: keep the identical
+        # load running (untimed) until the sampler has seen the GPU under it for a while
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < keep_loaded:
+            for _ in range(4):
+                step()
+            torch.cuda.synchronize()
+    total_ms = ctx.red(t0.elapsed_time(t1))
+    step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    return total_ms, step_ms
+
+
+def roofline_block(kernel, kernel_ms, algo_bytes, evals, per_query, traffic):
+    peak, peak_src = load_peaks()
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+         "peak_source": peak_src, "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+         "per_query": per_query}
+    if evals is not None:
+        tf = 430.0 * evals / (kernel_ms * 1e-3) / 1e12
+        r["fp32_secondary"] = {"note": "the narrow phase is FP32-issue bound, not HBM bound (SURVEY.md §8d): ~430 flop per "
+                                       "distance evaluation, FMA contraction off for bit-parity",
+                               "achieved_tflops": tf, "peak_tflops_nominal": FP32_PEAK_TINST, "frac": tf / FP32_PEAK_TINST}
+    return r
+
+
+# ------------------------------------------------------------------------------------------ move-and-slide (C3 / terrain)
+def measure_mas(ctx, args, mesh, n, steps, warmup, cpu_baseline=True, clocks=True, full_record_e2e=True):
+    """One move-and-slide configuration: device-resident value, roofline, e2e legs, optional CPU baseline."""
+    cq, torch = ctx.cq, ctx.torch
+    agents = args.agents if mesh == "terrain" else 0.0
+    parts, pos, vel = make_workload(cq, mesh, n, ctx.rank, agents, args.cells)
+    mas_flags = cq.MAS_APPLY_GRAVITY | (cq.MAS_AGENTS if agents > 0 else 0)
+    t0 = time.perf_counter()
+    world = cq.CollisionQuery(parts, order=args.order)
+    create_s = time.perf_counter() - t0
     info = world.info()
-    params = controller_params(cq, args.mesh)
+    params = controller_params(cq, mesh)
     states0 = cq.init_states(pos, vel)
     nbytes = states0.nbytes
-
-    # device-resident state (inputs are 168 MB per GPU > the 126 MB L2, so no explicit L2 flush is needed)
-    d_states = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    d_states.copy_(torch.from_numpy(states0.view(np.uint8).reshape(-1)))
-    # an explicit (non-default) stream: the library's NULL-stream convention means "the world's own
-    # stream", and torch.cuda.Event only sees torch's current stream, so make both the same real stream
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
+    # device-resident state (168 B x 1 M characters = 176 MB per GPU > the 126 MB L2, so no explicit L2 flush is needed)
+    d_states = ctx.up(states0)
+    stream = ctx.stream
+    separation = args.separation and agents > 0
 
     def step_device():
         world.move_and_slide_device(d_states.data_ptr(), n, params, DT, GRAVITY, mas_flags, stream)
-        if args.separation:  # the reference's fixed step runs AgentSeparationSystem right after the kinematic move
+        if separation:  # the reference's fixed step runs AgentSeparationSystem right after the kinematic move
             world.agent_separation_device(d_states.data_ptr(), n, params, stream=stream)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()  # runs through warm-up, the timed region and a short identical load after it (see below)
-    for _ in range(args.warmup):
+    sampler = ClockSampler(ctx.lrank) if clocks else None
+    for _ in range(warmup):
         step_device()
     torch.cuda.synchronize()
     snapshot = d_states.clone()
-
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     world.resetStats()
-    barrier()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for k in range(args.steps):
-        evs[k][0].record()
-        step_device()
-        evs[k][1].record()
-    t_end.record()
-    barrier()
+    total_ms, kernel_ms = time_steps(ctx, step_device, steps, 0, sampler)
     launches = world.stats()["kernel_launches"]
-    # the timed region lasts tens of milliseconds, shorter than one nvidia-smi sampling period: keep the identical
-    # load running (untimed) until the sampler has seen the GPU under it for at least ~0.7 s
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.7:
-        for _ in range(8):
-            step_device()
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
-    clocks["window"] = "warm-up + timed region + 0.7 s of the same steps right after it (untimed)"
-    total_ms = max_over_ranks(t_start.elapsed_time(t_end))
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    value = n * world_size * args.steps / (total_ms * 1e-3)
+    after_timed = d_states.clone()
+    if clocks:  # keep the identical load running (untimed) until nvidia-smi has seen the GPU under it for ~0.7 s
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.7:
+            for _ in range(8):
+                step_device()
+            torch.cuda.synchronize()
+    clk = sampler.stop() if sampler else None
+    if clk is not None:
+        clk["window"] = "timed region + 0.7 s of the same steps right after it (untimed)"
+    value = n * ctx.ws * steps / (total_ms * 1e-3)
 
     # algorithmic bytes of exactly these K steps: replay them from the snapshot with the counting build
     d_states.copy_(snapshot)
     world.set_counting(True)
     world.resetStats()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     torch.cuda.synchronize()
     ctr = world.stats(reset=True)
     world.set_counting(False)
+    replay_same = bool(torch.equal(d_states, after_timed))
     state_bytes = 2 * cq.STATE.itemsize  # state in + state out
-    algo_bytes_per_launch = (n * state_bytes * args.steps + 32 * ctr["nodes_visited"] + 52 * ctr["candidates"]) / args.steps
-    peak, peak_src = load_peaks()
-    achieved = algo_bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-    evals_per_launch = ctr["distance_evals"] / args.steps
-    fp32_peak_tinst = 148 * 128 * 1.965e9 / 1e12  # lanes x clock: issue ceiling with FMA off (1 flop / lane / clk)
-    traffic = None  # DRAM bytes per launch from the committed ncu capture (profiles/r1_traffic.json), scaled to n
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_move_and_slide"]
-        if args.mesh == "hulls":
-            traffic = tj["dram_bytes_per_character"] * n
-    except Exception:
-        pass
-    roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "kernel": "k_move_and_slide", "kernel_ms": kernel_ms,
-        "algorithmic_bytes_per_launch": algo_bytes_per_launch,
-        "per_query": {"nodes": ctr["nodes_visited"] / (n * args.steps), "candidates": ctr["candidates"] / (n * args.steps),
-                      "distance_evals": ctr["distance_evals"] / (n * args.steps),
-                      "bvh_traversals": ctr["queries"] / (n * args.steps)},
-        "fp32_secondary": {"note": "workload is FP32-issue bound, not HBM bound (SURVEY.md §8d): ~430 flop per "
-                                   "distance evaluation, FMA contraction off for bit-parity",
-                           "achieved_tflops": 430.0 * evals_per_launch / (kernel_ms * 1e-3) / 1e12,
-                           "peak_tflops_nominal": fp32_peak_tinst,
-                           "frac": 430.0 * evals_per_launch / (kernel_ms * 1e-3) / 1e12 / fp32_peak_tinst},
-    }
+    algo = (n * state_bytes * steps + 32 * ctr["nodes_visited"] + 52 * ctr["candidates"]) / steps
+    per_query = {"nodes": ctr["nodes_visited"] / (n * steps), "candidates": ctr["candidates"] / (n * steps),
+                 "distance_evals": ctr["distance_evals"] / (n * steps), "bvh_traversals": ctr["queries"] / (n * steps)}
+    tr = measured_traffic("k_move_and_slide", mesh)
+    roofline = roofline_block("k_move_and_slide", kernel_ms, algo, ctr["distance_evals"] / steps, per_query,
+                              tr * n if tr is not None else None)
 
-    # e2e: the public host-pointer call, pinned host buffers, H2D + kernel + D2H inside the timed region
-    pinned = cq.PinnedArray((n,), cq.STATE)
-    torch.cuda.synchronize()
-    pinned.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)
-    world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)  # warm the staging buffers
-    if args.separation:
-        world.agent_separation(pinned.array, params)
-    pinned.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)
-    e2e_steps = args.steps
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)
-        if args.separation:
-            world.agent_separation(pinned.array, params)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = n * world_size * e2e_steps / e2e_s
-    # consistency: the e2e path must have produced the same state as the device-resident replay
-    same = bool(np.array_equal(np.frombuffer(d_states.cpu().numpy().tobytes(), dtype=cq.STATE)["position"],
-                               pinned.array["position"]))
-    grounded_frac = float(pinned.array["grounded"].mean())
-    pinned.free()
-    # second e2e leg: the resident crowd (cq_crowd_*): records stay in HBM, a step moves 24 B of velocity in and 56 B of
-    # pose out per character.  Every step uploads the velocities the previous step's pose reported (the host-side
-    # steering systems would edit them in between; the buffer swap below stands for that).
-    crowd_e2e = None
-    if not args.separation:
-        crowd = cq.Crowd(world, np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE).copy())
+    snap_np = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE).copy()
+    final_np = np.frombuffer(d_states.cpu().numpy().tobytes(), dtype=cq.STATE)
+    e2e = {}
+    # e2e, headline: the resident crowd (records stay in HBM; velocities in, poses out; pinned host buffers).  Every step
+    # uploads the velocities the host holds — here the ones the previous step's pose reported, which is what a host whose
+    # steering systems changed nothing would send, and what makes the run comparable with the device-resident replay.
+    if not separation:
+        crowd = cq.Crowd(world, snap_np.copy())
         h_vel = cq.PinnedArray((n, 3), np.float64)
         h_pose = cq.PinnedArray((n,), cq.CROWD_POSE)
-        h_vel.array[:] = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE)["velocity"]
-        crowd.step(h_vel.array, params, DT, GRAVITY, mas_flags, pose_out=h_pose.array)  # warm
-        crowd.write(np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=cq.STATE).copy())
-        barrier()
+        h_vel.array[:] = snap_np["velocity"]
+        crowd.step(h_vel.array, params, DT, GRAVITY, mas_flags, pose_out=h_pose.array)  # warm the pipeline
+        crowd.write(snap_np.copy())
+        h_vel.array[:] = snap_np["velocity"]
+        ctx.barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        for _ in range(steps):
             crowd.step(h_vel.array, params, DT, GRAVITY, mas_flags, pose_out=h_pose.array)
-        crowd_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        crowd_e2e = {"value": n * world_size * e2e_steps / crowd_s, "unit": "queries/s",
-                     "h2d_bytes_per_step": n * 24 * world_size, "d2h_bytes_per_step": n * cq.CROWD_POSE.itemsize * world_size,
-                     "ms_per_step": crowd_s / e2e_steps * 1e3,
-                     "api": "cq_crowd_step (records resident in HBM; velocities in, poses out; pinned host buffers)"}
+            h_vel.array[:] = h_pose.array["velocity"]  # host side of the exchange (inside the timed region)
+        crowd_s = ctx.red(time.perf_counter() - t0)
+        ctx.barrier()
+        same_crowd = bool(crowd.read().tobytes() == final_np.tobytes())
+        e2e = {"value": n * ctx.ws * steps / crowd_s, "unit": "queries/s", "h2d_bytes_per_step": n * 24 * ctx.ws,
+               "d2h_bytes_per_step": n * cq.CROWD_POSE.itemsize * ctx.ws, "ms_per_step": crowd_s / steps * 1e3,
+               "api": "cq_crowd_step (records resident in HBM; 24 B of velocity in, 56 B of pose out per character; "
+                      "pinned host buffers; chunked copy/compute overlap)",
+               "matches_device_path": same_crowd}
         crowd.close()
         h_vel.free()
         h_pose.free()
+    if full_record_e2e or separation:
+        pinned = cq.PinnedArray((n,), cq.STATE)
+        pinned.array[:] = snap_np
+        world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)  # warm the staging buffers
+        if separation:
+            world.agent_separation(pinned.array, params)
+        pinned.array[:] = snap_np
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            world.move_and_slide(pinned.array, params, DT, GRAVITY, mas_flags)
+            if separation:
+                world.agent_separation(pinned.array, params)
+        torch.cuda.synchronize()
+        full_s = ctx.red(time.perf_counter() - t0)
+        ctx.barrier()
+        full = {"value": n * ctx.ws * steps / full_s, "unit": "queries/s", "h2d_bytes_per_step": nbytes * ctx.ws,
+                "d2h_bytes_per_step": nbytes * ctx.ws, "ms_per_step": full_s / steps * 1e3,
+                "api": "cq_move_and_slide_batch (all 168 bytes of every record both ways; pinned, chunked copy/compute overlap)",
+                "matches_device_path": bool(pinned.array.tobytes() == final_np.tobytes())}
+        pinned.free()
+        if e2e:
+            e2e["full_record"] = full
+        else:
+            e2e = full
+    grounded_frac = float(final_np["grounded"].mean())
 
-    cpu_baseline = None
-    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+    cpu = None
+    if cpu_baseline and ctx.rank == 0 and ctx.ws == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
-        ns = {"hulls": CHARS_PER_GPU, "render": 65536, "terrain": 262144}[args.mesh]
-        ns = min(ns, n)
+        ns = min({"hulls": CHARS_PER_GPU, "render": 65536, "terrain": 262144}[mesh], n)
         ow = orc.OracleWorld(parts)
-        snap_all = np.frombuffer(snapshot.cpu().numpy().tobytes(), dtype=orc.STATE)
         what = f"first {ns} of the {n} characters"
-        if args.agents > 0:
+        if agents > 0:
             # the reference tests every agent against every other (O(n^2)): time a sub-crowd of the SAME density,
             # the characters inside a centred square holding ~32768 of them
-            px, pz = snap_all["position"][:, 0], snap_all["position"][:, 2]
+            px, pz = snap_np["position"][:, 0], snap_np["position"][:, 2]
             lim = max(np.abs(px).max(), np.abs(pz).max()) * np.sqrt(min(1.0, 32768 / n))
-            snap_np = snap_all[(np.abs(px) <= lim) & (np.abs(pz) <= lim)].copy()
-            ns = len(snap_np)
+            sub = snap_np[(np.abs(px) <= lim) & (np.abs(pz) <= lim)].copy()
+            ns = len(sub)
             what = f"the {ns} characters of a centred sub-square of the crowd (same density; the reference's agent loop is O(n^2))"
         else:
-            snap_np = snap_all[:ns].copy()
+            sub = snap_np[:ns].copy()
         t0 = time.perf_counter()
-        ow.move_and_slide(snap_np, controller_params(orc, args.mesh), DT, GRAVITY, 3 if args.agents > 0 else 1,
-                          orc.ORDER_REFERENCE, cores)
-        if args.separation:
-            ow.agent_separation(snap_np, controller_params(orc, args.mesh), order=orc.ORDER_REFERENCE, n_threads=cores)
+        ow.move_and_slide(sub, controller_params(orc, mesh), DT, GRAVITY, 3 if agents > 0 else 1, orc.ORDER_REFERENCE, cores)
+        if separation:
+            ow.agent_separation(sub, controller_params(orc, mesh), order=orc.ORDER_REFERENCE, n_threads=cores)
         cdt = time.perf_counter() - t0
-        cpu_baseline = {"value": ns / cdt, "unit": "queries/s", "cores": cores, "kind": "port",
-                        "sample": f"{what}, the first timed step, {cdt:.2f} s wall; "
-                                  "restated reference (C++), not swiftc-compiled"}
-
-    total_launches = sum_over_ranks(launches)
-    if rank == 0:
-        line = {
-            "metric": "move_and_slide_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world_size,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.mesh, n, args.agents, args.separation), "mesh": args.mesh, "characters_per_gpu": n,
-                       "triangles": info["n_static_triangles"] + info["n_dynamic_triangles"],
-                       "l2": "inputs (168 B x characters = %.0f MB per GPU) exceed the 126 MB L2; no flush" % (nbytes / 1e6),
-                       "parallelism": f"queries sharded over {world_size} GPU(s), mesh+BVH replicated, no collective",
-                       "bvh_build_ms": info["build_ms"], "grounded_fraction_after": grounded_frac, "numa_node": numa_node,
-                       "e2e_matches_device_path": same},
-            "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nbytes * world_size,
-                    "d2h_bytes_per_step": nbytes * world_size, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "api": "cq_move_and_slide_batch (host pointers, pinned, chunked copy/compute overlap)",
-                    "resident_crowd": crowd_e2e},
-            "gpu_launches": int(total_launches),
-            "clocks": clocks,
-        }
-        emit(line)
+        cpu = {"value": ns / cdt, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{what}, the first timed step, {cdt:.2f} s wall; restated reference (C++), not swiftc-compiled"}
+        # parity on the way: the GPU's first timed step of the same characters must equal the reference-order oracle's
+        if args.order == cq.ORDER_REFERENCE and agents == 0:
+            g1 = snap_np[:ns].copy()
+            world.move_and_slide(g1, params, DT, GRAVITY, mas_flags)
+            cpu["gpu_step_bit_identical_to_this_run"] = bool(g1.tobytes() == sub.tobytes())
+        ow.close()
     world.close()
-    if world_size > 1:
-        dist.destroy_process_group()
-    return 0
+    return {
+        "metric": "move_and_slide_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": ctx.ws,
+        "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(mesh, n, agents, separation), "mesh": mesh, "characters_per_gpu": n,
+                   "triangles": info["n_static_triangles"] + info["n_dynamic_triangles"],
+                   "order": "reference" if args.order == cq.ORDER_REFERENCE else "canonical",
+                   "l2": "inputs (168 B x characters = %.0f MB per GPU) exceed the 126 MB L2; no flush" % (nbytes / 1e6),
+                   "parallelism": f"queries sharded over {ctx.ws} GPU(s), mesh+BVH replicated, no collective",
+                   "bvh_build_ms": info["build_ms"], "reference_order_build_ms": info["ref_order_ms"],
+                   "world_create_s": create_s, "grounded_fraction_after": grounded_frac, "numa_node": ctx.numa,
+                   "counting_replay_matches_timed_run": replay_same},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(ctx.red(launches, "sum")), "clocks": clk,
+    }
 
 
-# ------------------------------------------------------------------------------------------ secondary workloads
-def _torch_setup():
-    import torch
-    import torch.distributed as dist
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    bind_to_gpu_numa_node(local_rank)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-
-    def barrier():
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def red(x, op):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world_size > 1:
-            dist.all_reduce(t, op=op)
-        return float(t.item())
-
-    return torch, dist, world_size, rank, local_rank, dev, tstream, barrier, red
-
-
-def run_c4(args):
-    """Config C4: capsuleCastBlocking sweeps over the procedural 10M-triangle terrain, queries sharded over
-    the ranks.  --cells/--queries scale it down for quick runs."""
-    torch, dist, ws, rank, lrank, dev, tstream, barrier, red = _torch_setup()
-    cq = importlib.import_module("swift-game-engine_b200")
-    cq.build()
+# ------------------------------------------------------------------------------------------ C4: blocking sweeps over the terrain
+def measure_c4(ctx, args, n_total, steps, warmup, sharded):
+    """capsuleCastBlocking sweeps over the procedural 10M-triangle terrain.  sharded=False: n_total sweeps per GPU (weak);
+    sharded=True: n_total sweeps in all, rank r takes cq_shard_range(n_total, ws, r), and the hit records of all ranks are
+    all-gathered onto every rank INSIDE the timed region by the library's NCCL group (cq_group_gather_records)."""
+    cq, torch = ctx.cq, ctx.torch
     t0 = time.perf_counter()
-    parts, half = cq.scenes.terrain_scene(cells=args.cells, cell=2.0)
+    parts, half = terrain_parts(cq, args.cells)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    world = cq.CollisionQuery(parts)
+    world = cq.CollisionQuery(parts, order=args.order)
     t_create = time.perf_counter() - t0
     info = world.info()
-    n = args.queries
-    q = cq.scenes.gen_c4_casts(n, half, seed=0xC0111DE4 + rank, radius=args.radius, half_height=args.half_height)
-    d_q = torch.from_numpy(q.view(np.uint8).reshape(-1).copy()).to(dev)
-    d_out = torch.empty(n * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=dev)
-    stream = tstream.cuda_stream
-
-    gather = bool(args.gather) and ws > 1
-    d_all = torch.empty(n * ws * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=dev) if gather else None
+    lo, hi = 0, n_total
+    if sharded:
+        lo, hi = cq.shard_range(n_total, ctx.ws, ctx.rank)
+        q_all = cq.scenes.gen_c4_casts(n_total, half, seed=0xC0111DE4, radius=args.radius, half_height=args.half_height)
+        q = np.ascontiguousarray(q_all[lo:hi])
+        del q_all
+    else:
+        q = cq.scenes.gen_c4_casts(n_total, half, seed=0xC0111DE4 + ctx.rank, radius=args.radius, half_height=args.half_height)
+    n = len(q)
+    units = n_total if sharded else n_total * ctx.ws
+    d_q, rec = ctx.up(q), cq.CAST_HIT.itemsize
+    d_out = torch.empty(n * rec, dtype=torch.uint8, device=ctx.dev)
+    gather = sharded and ctx.ws > 1
+    d_all = torch.empty(n_total * rec, dtype=torch.uint8, device=ctx.dev) if gather else None
+    group = ctx.nccl_group() if gather else None
+    stream = ctx.stream
 
     def step():
         world.capsule_cast_device(d_q.data_ptr(), n, cq.CAST_BLOCKING, d_out.data_ptr(), stream)
-        if gather:  # the one collective of the path (DESIGN.md §6): hit records of all ranks onto every rank, NCCL
-            cq.shard.gather_records(d_out, n * ws, cq.CAST_HIT.itemsize, out=d_all)
+        if gather:  # the one collective of the path (DESIGN.md §6), NCCL from inside libcq.so
+            group.gather_records(d_out.data_ptr(), n_total, rec, d_all.data_ptr(), stream)
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
+    sampler = ClockSampler(ctx.lrank)
     world.resetStats()
-    sampler = ClockSampler(lrank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
+    total_ms, step_ms = time_steps(ctx, step, steps, warmup, sampler)
+    clk = sampler.stop()
     launches = world.stats()["kernel_launches"]
-    ms = red(e0.elapsed_time(e1), dist.ReduceOp.MAX)
-    value = n * ws * args.steps / (ms * 1e-3)
-    gather_ms = None
-    if gather:  # the collective alone, same buffers, max over ranks
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
-            cq.shard.gather_records(d_out, n * ws, cq.CAST_HIT.itemsize, out=d_all)
-        g1.record()
-        barrier()
-        gather_ms = red(g0.elapsed_time(g1), dist.ReduceOp.MAX) / args.steps
-        mine = d_all[rank * n * cq.CAST_HIT.itemsize:(rank + 1) * n * cq.CAST_HIT.itemsize]
+    value = units * steps / (total_ms * 1e-3)
+    collective_ms, kernel_ms = None, total_ms / steps
+    if gather:  # the collective alone and the kernel alone, same buffers, max over ranks
+        def only_gather():
+            group.gather_records(d_out.data_ptr(), n_total, rec, d_all.data_ptr(), stream)
+
+        def only_cast():
+            world.capsule_cast_device(d_q.data_ptr(), n, cq.CAST_BLOCKING, d_out.data_ptr(), stream)
+        collective_ms = time_steps(ctx, only_gather, steps, 1)[0] / steps
+        kernel_ms = time_steps(ctx, only_cast, steps, 1)[0] / steps
+        mine = d_all[lo * rec:hi * rec]
         assert bool(torch.equal(mine, d_out)), "gathered records differ from the local shard"
     world.set_counting(True)
     world.resetStats()
-    step()
+    world.capsule_cast_device(d_q.data_ptr(), n, cq.CAST_BLOCKING, d_out.data_ptr(), stream)
     torch.cuda.synchronize()
     ctr = world.stats(reset=True)
     world.set_counting(False)
     hits = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=cq.CAST_HIT)
     algo = n * (40 + 44) + 32 * ctr["nodes_visited"] + 52 * ctr["candidates"]
-    peak, peak_src = load_peaks()
-    kernel_ms = ms / args.steps
+    tr = measured_traffic("k_capsule_cast", "c4")
+    roofline = roofline_block("k_capsule_cast", kernel_ms, algo, ctr["distance_evals"],
+                              {k: ctr[k] / n for k in ("nodes_visited", "candidates", "distance_evals")},
+                              tr * n if tr is not None else None)
     # e2e through the host-pointer API
     hq = cq.PinnedArray((n,), cq.CAST)
     hq.array[:] = q
     ho = cq.PinnedArray((n,), cq.CAST_HIT)
     L = cq.lib()
     L.cq_capsule_cast_batch(world.handle, hq.array.ctypes.data, n, cq.CAST_BLOCKING, ho.array.ctypes.data)
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         rc = L.cq_capsule_cast_batch(world.handle, hq.array.ctypes.data, n, cq.CAST_BLOCKING, ho.array.ctypes.data)
         assert rc == 0
-    e2e_s = red(time.perf_counter() - t0, dist.ReduceOp.MAX)
-    same = bool(np.array_equal(ho.array["triangle_index"], hits["triangle_index"]))
-    cpu_baseline = None
-    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+    e2e_s = ctx.red(time.perf_counter() - t0)
+    same = bool(ho.array.tobytes() == hits.tobytes())
+    hq.free()
+    ho.free()
+    cpu = None
+    if ctx.rank == 0 and ctx.ws == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
         t0 = time.perf_counter()
@@ -585,74 +627,60 @@ def run_c4(args):
         t0 = time.perf_counter()
         ref = ow.capsule_cast(q[:ns], 1, orc.ORDER_REFERENCE, cores)
         cdt = time.perf_counter() - t0
-        agree = float((ref["triangle_index"] == hits["triangle_index"][:ns]).mean())
-        cpu_baseline = {"value": ns / cdt, "unit": "sweeps/s", "cores": cores, "kind": "port",
-                        "sample": f"first {ns} of {n} sweeps, {cdt:.2f} s; reference-BVH build {t_cpu_build:.1f} s "
-                                  f"(1 thread); index agreement with the GPU on the sample {agree:.4f} "
-                                  "(differences = exact toi ties)"}
-    tot_launch = red(launches, dist.ReduceOp.SUM)
-    if rank == 0:
-        emit(({
-            "metric": "capsule_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": ws, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C4: {n} capsuleCastBlocking sweeps/GPU over a procedural terrain of "
-                                   f"{info['n_static_triangles']} triangles (cell 2 m), r={args.radius} hh={args.half_height}",
-                       "triangles": info["n_static_triangles"], "bvh_build_ms": info["build_ms"],
-                       "world_create_s": t_create, "terrain_gen_s": t_gen, "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
-                       "l2": "triangle SoA + nodes (%.0f MB) and queries exceed the 126 MB L2" % (info["n_static_triangles"] * 112 / 1e6),
-                       "e2e_matches_device_path": same,
-                       "gather": (f"all_gather_into_tensor (NCCL) of the {cq.CAST_HIT.itemsize} B hit records of all ranks inside "
-                                  f"the timed region; the collective alone: {gather_ms:.3f} ms/step") if gather else
-                                 "none (results stay on the owning GPU)"},
-            "roofline": {"bound": "hbm", "achieved": algo / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": algo / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_capsule_cast", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo,
-                         "per_query": {k: ctr[k] / n for k in ("nodes_visited", "candidates", "distance_evals")}},
-            "cpu_baseline": cpu_baseline,
-            "e2e": {"value": n * ws * args.steps / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": n * 40 * ws,
-                    "d2h_bytes_per_step": n * 44 * ws},
-            "gpu_launches": int(tot_launch), "clocks": clocks}))
+        cpu = {"value": ns / cdt, "unit": "sweeps/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} of {n} sweeps, {cdt:.2f} s; reference-BVH build {t_cpu_build:.1f} s (1 thread)",
+               "gpu_bit_identical_on_the_sample": bool(ref.tobytes() == hits[:ns].tobytes())}
+        ow.close()
     world.close()
-    return 0
+    return {
+        "metric": "capsule_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": ctx.ws, "steps": steps,
+        "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": (f"C4: {n_total} capsuleCastBlocking sweeps " + ("in all, sharded over the ranks, " if sharded else "per GPU ")
+                                + f"over a procedural terrain of {info['n_static_triangles']} triangles (cell 2 m), "
+                                f"r={args.radius} hh={args.half_height}"),
+                   "triangles": info["n_static_triangles"], "bvh_build_ms": info["build_ms"],
+                   "reference_order_build_ms": info["ref_order_ms"], "world_create_s": t_create, "terrain_gen_s": t_gen,
+                   "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
+                   "l2": "triangle SoA + nodes (%.0f MB) and queries exceed the 126 MB L2" % (info["n_static_triangles"] * 112 / 1e6),
+                   "e2e_matches_device_path": same,
+                   "gather": (f"cq_group_gather_records (ncclAllGather inside libcq.so) of the {rec} B hit records of all ranks "
+                              "inside the timed region") if gather else "none (results stay on the owning GPU)"},
+        "collective_ms": collective_ms, "kernel_ms_alone": kernel_ms if gather else None,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": units * steps / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": units * 40,
+                "d2h_bytes_per_step": units * 44, "ms_per_step": e2e_s / steps * 1e3,
+                "api": "cq_capsule_cast_batch (host pointers, pinned)"},
+        "gpu_launches": int(ctx.red(launches, "sum")), "clocks": clk}
 
 
-def run_c2(args):
-    """Config C2: 65,536 plain capsuleCast sweeps against the Semla mesh (FBX-regenerated stand-in for the
-    missing Semla.static.json) at its demo placement, every field checked against the oracle."""
-    torch, dist, ws, rank, lrank, dev, tstream, barrier, red = _torch_setup()
-    cq = importlib.import_module("swift-game-engine_b200")
-    cq.build()
+# ------------------------------------------------------------------------------------------ C2: sweeps vs Semla
+def measure_c2(ctx, args, n, steps, warmup):
+    """Config C2: 65,536 plain capsuleCast sweeps against the Semla mesh (FBX-regenerated stand-in for the missing
+    Semla.static.json) at its demo placement; a sample checked byte for byte against the reference-order oracle."""
+    cq, torch = ctx.cq, ctx.torch
     sc = cq.scenes
     parts = sc.semla_scene(use_hulls=False)
-    world = cq.CollisionQuery(parts)
+    world = cq.CollisionQuery(parts, order=args.order)
     info = world.info()
     lo, hi = sc.scene_aabb(parts[1:])
-    n = args.queries
-    q = sc.gen_casts(n, lo, hi, seed=0xC0111DE2 + rank)  # from ~ U(AABB + 3 m), |delta| ~ U[0.05, 2], r=1.5 hh=1.0
-    d_q = torch.from_numpy(q.view(np.uint8).reshape(-1).copy()).to(dev)
-    d_out = torch.empty(n * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=dev)
-    stream = tstream.cuda_stream
+    q = sc.gen_casts(n, lo, hi, seed=0xC0111DE2 + ctx.rank)  # from ~ U(AABB + 3 m), |delta| ~ U[0.05, 2], r=1.5 hh=1.0
+    d_q = ctx.up(q)
+    d_out = torch.empty(n * cq.CAST_HIT.itemsize, dtype=torch.uint8, device=ctx.dev)
+    d_flags = torch.zeros(n, dtype=torch.uint8, device=ctx.dev)
+    stream = ctx.stream
+    L = cq.lib()
 
     def step():
-        world.capsule_cast_device(d_q.data_ptr(), n, cq.CAST_ALL, d_out.data_ptr(), stream)
+        rc = L.cq_capsule_cast_device_ex(world.handle, d_q.data_ptr(), n, cq.CAST_ALL, d_out.data_ptr(), d_flags.data_ptr(), stream)
+        assert rc == 0
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
+    sampler = ClockSampler(ctx.lrank)
     world.resetStats()
-    sampler = ClockSampler(lrank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
+    total_ms, _ = time_steps(ctx, step, steps, warmup, sampler)
+    clk = sampler.stop()
     launches = world.stats()["kernel_launches"]
-    ms = red(e0.elapsed_time(e1), dist.ReduceOp.MAX) / args.steps
+    ms = total_ms / steps
     world.set_counting(True)
     world.resetStats()
     step()
@@ -660,13 +688,13 @@ def run_c2(args):
     ctr = world.stats(reset=True)
     world.set_counting(False)
     hits = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=cq.CAST_HIT)
+    flags = d_flags.cpu().numpy()
     t0 = time.perf_counter()
     host_hits = world.capsuleCast(q)
     e2e_s = time.perf_counter() - t0
     algo = n * (40 + 44) + 32 * ctr["nodes_visited"] + 52 * ctr["candidates"]
-    peak, peak_src = load_peaks()
-    cpu_baseline, parity = None, None
-    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+    cpu, parity = None, None
+    if ctx.rank == 0 and ctx.ws == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
         ow = orc.OracleWorld(parts)
@@ -676,77 +704,90 @@ def run_c2(args):
         ref = ow.capsule_cast(q[:ns], 0, orc.ORDER_REFERENCE, cores, st)
         cdt = time.perf_counter() - t0
         can = ow.capsule_cast(q[:ns], 0, orc.ORDER_CANONICAL, cores)
-        parity = {"sample": ns, "bit_exact_vs_canonical_oracle": bool(can.tobytes() == hits[:ns].tobytes()),
-                  "toi_equal_vs_reference_order": bool(np.array_equal(ref["toi"], hits["toi"][:ns])),
-                  "index_mismatch_vs_reference_order_all_exact_ties": float((ref["triangle_index"] != hits["triangle_index"][:ns]).mean()),
+        mine = ref if args.order == cq.ORDER_REFERENCE else can
+        other = can if args.order == cq.ORDER_REFERENCE else ref
+        diff = hits["triangle_index"][:ns] != other["triangle_index"]
+        tie = (flags[:ns] & cq.HIT_TIE).astype(bool)
+        parity = {"sample": ns, "bit_exact_vs_oracle_in_the_world_order": bool(mine.tobytes() == hits[:ns].tobytes()),
+                  "index_mismatch_vs_reference_order": float((ref["triangle_index"] != hits["triangle_index"][:ns]).mean()),
+                  "queries_flagged_TIE": float(tie.mean()),
+                  "differences_between_the_two_order_rules": float(diff.mean()),
+                  "unflagged_differences": int((diff & ~tie).sum()),
                   "reference_distance_evals_per_sweep": st.distance_evals / ns}
-        cpu_baseline = {"value": ns / cdt, "unit": "sweeps/s", "cores": cores, "kind": "port",
-                        "sample": f"first {ns} of {n} sweeps, {cdt:.2f} s wall, reference BVH + DFS order"}
-    if rank == 0:
-        emit(({
-            "metric": "capsule_sweeps_per_sec", "value": n * ws / (ms * 1e-3), "unit": "sweeps/s", "n_gpus": ws,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2: {n} capsuleCast sweeps vs Semla render mesh ({info['n_static_triangles']} tris incl. ground), "
-                                   "r=1.5 hh=1.0, |delta| in [0.05, 2]", "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
-                       "parity": parity, "e2e_matches_device_path": bool(host_hits.tobytes() == hits.tobytes())},
-            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_capsule_cast", "kernel_ms": ms, "algorithmic_bytes_per_launch": algo,
-                         "per_query": {k: ctr[k] / n for k in ("nodes_visited", "candidates", "distance_evals")},
-                         "fp32_secondary": {"achieved_tflops": 430.0 * ctr["distance_evals"] / (ms * 1e-3) / 1e12,
-                                            "frac": 430.0 * ctr["distance_evals"] / (ms * 1e-3) / 1e12 / 37.22496}},
-            "cpu_baseline": cpu_baseline,
-            "e2e": {"value": n / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": n * 40, "d2h_bytes_per_step": n * 44},
-            "gpu_launches": int(launches), "clocks": clocks}))
+        cpu = {"value": ns / cdt, "unit": "sweeps/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} of {n} sweeps, {cdt:.2f} s wall, reference BVH + DFS order"}
+        ow.close()
     world.close()
-    return 0
+    tr = measured_traffic("k_capsule_cast", "c2")
+    return {
+        "metric": "capsule_sweeps_per_sec", "value": n * ctx.ws / (ms * 1e-3), "unit": "sweeps/s", "n_gpus": ctx.ws,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: {n} capsuleCast sweeps vs Semla render mesh ({info['n_static_triangles']} tris incl. ground), "
+                               "r=1.5 hh=1.0, |delta| in [0.05, 2]", "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
+                   "order": "reference" if args.order == cq.ORDER_REFERENCE else "canonical",
+                   "parity": parity, "e2e_matches_device_path": bool(host_hits.tobytes() == hits.tobytes())},
+        "roofline": roofline_block("k_capsule_cast", ms, algo, ctr["distance_evals"],
+                                   {k: ctr[k] / n for k in ("nodes_visited", "candidates", "distance_evals")},
+                                   tr * n if tr is not None else None),
+        "cpu_baseline": cpu,
+        "e2e": {"value": n / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": n * 40, "d2h_bytes_per_step": n * 44,
+                "api": "cq_capsule_cast_batch (host pointers, pageable)"},
+        "gpu_launches": int(launches), "clocks": clk}
 
 
-def run_c5(args):
+# ------------------------------------------------------------------------------------------ C5: rays + refit
+def measure_c5(ctx, args, n_total, steps, warmup, sharded):
     """Config C5: batched raycasts + a BVH refit of the spinning (dynamic-set) mirror every step."""
-    torch, dist, ws, rank, lrank, dev, tstream, barrier, red = _torch_setup()
-    cq = importlib.import_module("swift-game-engine_b200")
-    cq.build()
+    cq, torch = ctx.cq, ctx.torch
     sc = cq.scenes
     parts = sc.merged_scene(mirror_dynamic=True)  # ground + 17-Cheese + Semla (FBX-regenerated stand-ins) + spinning mirror
     a = sc.load_mirror_fixture()
     base_t, base_q, base_s = sc.transform_from_matrix(sc.mirror_model(a["transform"]))
     mirror_id = parts[-1]["entity_id"]
-    world = cq.CollisionQuery(parts)
+    world = cq.CollisionQuery(parts, order=args.order)
     info = world.info()
     lo, hi = sc.scene_aabb(parts[1:])
-    n = args.queries
-    rays = sc.gen_rays(n, lo, hi, seed=0xC0111DE5 + rank, max_distance=100.0, expand=5.0, y_range=(0.0, 12.0))
-    d_r = torch.from_numpy(rays.view(np.uint8).reshape(-1).copy()).to(dev)
-    d_out = torch.empty(n * cq.RAY_HIT.itemsize, dtype=torch.uint8, device=dev)
-    stream = tstream.cuda_stream
+    if sharded:
+        s0, s1 = cq.shard_range(n_total, ctx.ws, ctx.rank)
+        rays = np.ascontiguousarray(sc.gen_rays(n_total, lo, hi, seed=0xC0111DE5, max_distance=100.0, expand=5.0,
+                                                y_range=(0.0, 12.0))[s0:s1])
+    else:
+        rays = sc.gen_rays(n_total, lo, hi, seed=0xC0111DE5 + ctx.rank, max_distance=100.0, expand=5.0, y_range=(0.0, 12.0))
+    n = len(rays)
+    units = n_total if sharded else n_total * ctx.ws
+    d_r = ctx.up(rays)
+    d_out = torch.empty(n * cq.RAY_HIT.itemsize, dtype=torch.uint8, device=ctx.dev)
+    stream = ctx.stream
     angle = [0.0]
+
+    def pose():
+        rot = sc.quat_mul(sc.quat_angle_axis(np.radians(angle[0]), (0, 1, 0)), base_q)
+        return sc.trs_model(base_t, rot, base_s)
 
     def step():
         angle[0] += 1.0
-        rot = sc.quat_mul(sc.quat_angle_axis(np.radians(angle[0]), (0, 1, 0)), base_q)
-        world.update_transforms([mirror_id], [sc.trs_model(base_t, rot, base_s)])  # refit (synchronous: returns refit_ms)
+        world.update_transforms([mirror_id], [pose()])  # refit (synchronous: returns refit_ms)
         world.raycast_device(d_r.data_ptr(), n, d_out.data_ptr(), stream)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     world.resetStats()
-    sampler = ClockSampler(lrank)
-    barrier()
+    sampler = ClockSampler(ctx.lrank)
+    ctx.barrier()
     sampler.start()
     t0 = time.perf_counter()
     refit_ms = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
         refit_ms.append(world.info()["refit_ms"])
     torch.cuda.synchronize()
-    wall = red(time.perf_counter() - t0, dist.ReduceOp.MAX)
-    barrier()
-    clocks = sampler.stop()
+    wall = ctx.red(time.perf_counter() - t0)
+    ctx.barrier()
+    clk = sampler.stop()
     launches = world.stats()["kernel_launches"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ctx.events()
     e0.record()
     world.raycast_device(d_r.data_ptr(), n, d_out.data_ptr(), stream)
     e1.record()
@@ -759,8 +800,8 @@ def run_c5(args):
     ctr = world.stats(reset=True)
     world.set_counting(False)
     hits = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=cq.RAY_HIT)
+    hit_pose = pose()
     algo = n * 64 + 32 * ctr["nodes_visited"] + 52 * ctr["candidates"]
-    peak, peak_src = load_peaks()
     # e2e: the same step through the host-pointer API (refit + cq_raycast_batch, rays and hits in pinned host memory)
     hr = cq.PinnedArray((n,), cq.RAY)
     hr.array[:] = rays
@@ -769,62 +810,140 @@ def run_c5(args):
 
     def step_host():
         angle[0] += 1.0
-        rot = sc.quat_mul(sc.quat_angle_axis(np.radians(angle[0]), (0, 1, 0)), base_q)
-        world.update_transforms([mirror_id], [sc.trs_model(base_t, rot, base_s)])
+        world.update_transforms([mirror_id], [pose()])
         rc = L.cq_raycast_batch(world.handle, hr.array.ctypes.data, n, ho.array.ctypes.data)
         assert rc == 0
 
     step_host()
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_host()
-    e2e_s = red(time.perf_counter() - t0, dist.ReduceOp.MAX)
-    cpu_baseline = None
-    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+    e2e_s = ctx.red(time.perf_counter() - t0)
+    hr.free()
+    ho.free()
+    cpu = None
+    if ctx.rank == 0 and ctx.ws == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
         ow = orc.OracleWorld(parts)
-        rot = sc.quat_mul(sc.quat_angle_axis(np.radians(angle[0]), (0, 1, 0)), base_q)
         t0 = time.perf_counter()
-        ow.update_transforms([mirror_id], [sc.trs_model(base_t, rot, base_s)])
+        ow.update_transforms([mirror_id], [hit_pose])  # the pose `hits` was cast at
         cpu_refit = time.perf_counter() - t0
         ns = min(n, 262144)
         t0 = time.perf_counter()
         ref = ow.raycast(rays[:ns], orc.ORDER_REFERENCE, cores)
         cdt = time.perf_counter() - t0
-        agree = float((ref["triangle_index"] == hits["triangle_index"][:ns]).mean())
-        cpu_baseline = {"value": ns / cdt, "unit": "rays/s", "cores": cores, "kind": "port",
-                        "sample": f"first {ns} of {n} rays, {cdt:.2f} s; CPU refit of the same part {cpu_refit * 1e3:.1f} ms; "
-                                  f"index agreement with the GPU on the sample {agree:.5f}"}
-    tot_launch = red(launches, dist.ReduceOp.SUM)
-    if rank == 0:
-        emit(({
-            "metric": "raycasts_per_sec_with_refit", "value": n * ws * args.steps / wall, "unit": "rays/s", "n_gpus": ws,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5: {n} raycasts/GPU + refit of the spinning mirror (dynamic set, "
-                                   f"{info['n_dynamic_triangles']} tris) each step; static set {info['n_static_triangles']} tris "
-                                   "(ground + 17-Cheese + Semla render meshes regenerated from FBX, tools/fbx_to_static_mesh.py)",
-                       "refit_ms_mean": float(np.mean(refit_ms)), "raycast_kernel_ms": ray_ms,
-                       "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
-                       "timing": "host wall clock around (refit + raycast) steps, device synchronised"},
-            "roofline": {"bound": "hbm", "achieved": algo / (ray_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": algo / (ray_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_raycast", "kernel_ms": ray_ms, "algorithmic_bytes_per_launch": algo,
-                         "per_query": {k: ctr[k] / n for k in ("nodes_visited", "candidates")}},
-            "cpu_baseline": cpu_baseline,
-            "e2e": {"value": n * ws * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n * cq.RAY.itemsize * ws,
-                    "d2h_bytes_per_step": n * cq.RAY_HIT.itemsize * ws, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "api": "cq_world_update_transforms + cq_raycast_batch (host pointers, pinned)"},
-            "gpu_launches": int(tot_launch), "clocks": clocks}))
+        cpu = {"value": ns / cdt, "unit": "rays/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} of {n} rays, {cdt:.2f} s; CPU refit of the same part {cpu_refit * 1e3:.1f} ms",
+               "gpu_bit_identical_on_the_sample": bool(ref.tobytes() == hits[:ns].tobytes()),
+               "index_agreement": float((ref["triangle_index"] == hits["triangle_index"][:ns]).mean())}
+        ow.close()
     world.close()
+    tr = measured_traffic("k_raycast", "c5")
+    return {
+        "metric": "raycasts_per_sec_with_refit", "value": units * steps / wall, "unit": "rays/s", "n_gpus": ctx.ws,
+        "steps": steps, "warmup": warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C5: {n_total} raycasts " + ("in all, sharded over the ranks, " if sharded else "per GPU ") +
+                               f"+ refit of the spinning mirror (dynamic set, {info['n_dynamic_triangles']} tris) each step; "
+                               f"static set {info['n_static_triangles']} tris (ground + 17-Cheese + Semla render meshes regenerated "
+                               "from FBX, tools/fbx_to_static_mesh.py)",
+                   "order": "reference" if args.order == cq.ORDER_REFERENCE else "canonical",
+                   "refit_ms_mean": float(np.mean(refit_ms)), "raycast_kernel_ms": ray_ms,
+                   "hit_fraction": float((hits["triangle_index"] >= 0).mean()),
+                   "timing": "host wall clock around (refit + raycast) steps, device synchronised"},
+        "roofline": roofline_block("k_raycast_ref" if args.order == cq.ORDER_REFERENCE else "k_raycast", ray_ms, algo, None,
+                                   {k: ctr[k] / n for k in ("nodes_visited", "candidates")}, tr * n if tr is not None else None),
+        "cpu_baseline": cpu,
+        "e2e": {"value": units * steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": units * cq.RAY.itemsize,
+                "d2h_bytes_per_step": units * cq.RAY_HIT.itemsize, "ms_per_step": e2e_s / steps * 1e3,
+                "api": "cq_world_update_transforms + cq_raycast_batch (host pointers, pinned)"},
+        "gpu_launches": int(ctx.red(launches, "sum")), "clocks": clk}
+
+
+# ------------------------------------------------------------------------------------------ strong-scaling C3
+def measure_c3_strong(ctx, args, n_total, steps, warmup):
+    """BASELINE.json's '1M chars at 1/2/4/8': 1,048,576 characters IN ALL, rank r steps cq_shard_range(n, ws, r)."""
+    cq = ctx.cq
+    parts = cq.scenes.mirror_scene(use_hulls=True)
+    pos, vel = cq.scenes.gen_c3_characters(n_total, seed=SEED)
+    lo, hi = cq.shard_range(n_total, ctx.ws, ctx.rank)
+    world = cq.CollisionQuery(parts, order=args.order)
+    params = cq.default_params()
+    d_states = ctx.up(cq.init_states(pos[lo:hi], vel[lo:hi]))
+    n = hi - lo
+
+    def step():
+        world.move_and_slide_device(d_states.data_ptr(), n, params, DT, GRAVITY, cq.MAS_APPLY_GRAVITY, ctx.stream)
+
+    total_ms, _ = time_steps(ctx, step, steps, warmup)
+    world.close()
+    return {"metric": "move_and_slide_queries_per_sec", "value": n_total * steps / (total_ms * 1e-3), "unit": "queries/s",
+            "n_gpus": ctx.ws, "ms_per_step": total_ms / steps, "scaling": "strong",
+            "config": {"workload": f"C3 hulls, {n_total} characters in all, sharded over {ctx.ws} GPU(s) "
+                                   f"({n} on this rank), device-resident, no collective"}}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def _short(d):
+    """An extra's record inside the headline line."""
+    keep = ("metric", "value", "unit", "ms_per_step", "scaling", "collective_ms", "kernel_ms_alone", "config", "roofline",
+            "cpu_baseline", "e2e", "clocks", "gpu_launches")
+    return {k: d[k] for k in keep if k in d}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    cq = ctx.cq
+    args.order = cq.ORDER_CANONICAL if args.order_name == "canonical" else cq.ORDER_REFERENCE
+    only = args.only
+    line = None
+    if only in (None, "c3"):
+        line = measure_mas(ctx, args, args.mesh, args.chars, args.steps, args.warmup)
+    extras = {}
+
+    def extra(name, fn):
+        if only not in (None, name) or (only is None and args.no_extras):
+            return
+        t0 = time.perf_counter()
+        try:
+            extras[name] = _short(fn()) if only is None else fn()
+            extras[name]["bench_wall_s"] = time.perf_counter() - t0
+        except Exception as e:  # an extra must never take the headline line down with it
+            extras[name] = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
+        ctx.barrier()
+
+    ks, kw = max(3, min(args.steps, 10)), 3
+    multi = ctx.ws > 1
+    if only is not None or (args.mesh == "hulls" and args.agents == 0):
+        extra("terrain", lambda: measure_mas(ctx, args, "terrain", args.chars, ks, kw, cpu_baseline=True, clocks=False,
+                                             full_record_e2e=False))
+        extra("c4", lambda: measure_c4(ctx, args, args.queries or (1 << 23), max(3, ks // 2), kw, sharded=multi))
+        _TERRAIN.clear()
+        if not multi:
+            extra("render", lambda: measure_mas(ctx, args, "render", args.chars, max(3, ks // 2), kw, cpu_baseline=True,
+                                                clocks=False, full_record_e2e=False))
+            extra("c2", lambda: measure_c2(ctx, args, args.queries or 65536, max(3, ks // 2), kw))
+        extra("c5", lambda: measure_c5(ctx, args, args.queries or (1 << 24), max(3, ks // 2), kw, sharded=multi))
+        if multi:
+            extra("c3_strong", lambda: measure_c3_strong(ctx, args, CHARS_PER_GPU, ks, kw))
+    if ctx.rank == 0:
+        if line is None:
+            line = next(iter(extras.values())) if extras else {"error": "nothing measured"}
+        else:
+            line["extra"] = extras
+        emit(line)
+    ctx.close()
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--only", default=None, choices=[None, "c3", "terrain", "render", "c2", "c4", "c5", "c3_strong"],
+                    help="measure one configuration only and print its line (default: C3 headline + every extra)")
+    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"], help="alias of --only")
+    ap.add_argument("--no-extras", action="store_true", help="headline configuration only")
     ap.add_argument("--cells", type=int, default=2236)
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--radius", type=float, default=0.4)
@@ -834,6 +953,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", default="hulls", choices=["hulls", "render", "terrain"])
+    ap.add_argument("--order", dest="order_name", default="reference", choices=["reference", "canonical"],
+                    help="world order rule (include/cq.h); reference = the library's default")
     ap.add_argument("--chars", type=int, default=CHARS_PER_GPU)
     ap.add_argument("--separation", action="store_true",
                     help="with --agents: also run AgentSeparationSystem (exact sequential semantics) every step")
@@ -841,21 +962,15 @@ def main():
                     help="terrain mesh only: characters collide with each other; value = crowd footprint coverage (e.g. 0.1)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", action="store_true",
-                    help="c4, N > 1: all-gather the hit records of all ranks (NCCL) inside the timed region")
+    ap.add_argument("--gather", action="store_true", help="(kept for compatibility: sharded c4 always gathers)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "c2":
-        args.queries = args.queries or 65536
-        return run_c2(args)
-    if args.workload == "c4":
-        args.queries = args.queries or (1 << 23)
-        return run_c4(args)
-    if args.workload == "c5":
-        args.queries = args.queries or (1 << 24)
-        return run_c5(args)
+    if args.workload and not args.only:
+        args.only = args.workload
     if args.impl == "reference":
         return run_reference(args)
+    if args.mesh != "hulls" and args.only is None:
+        args.only = "c3"  # another mesh through the headline path: that configuration alone
     return run_ours(args)
 
 

@@ -39,6 +39,7 @@ extern "C" {
 #define CQ_ERR_IO (-3)        /* file missing / unreadable */
 #define CQ_ERR_PARSE (-4)     /* malformed *.static.json */
 #define CQ_ERR_NOT_FOUND (-5) /* unknown entity id */
+#define CQ_ERR_NCCL (-6)      /* NCCL missing or failed (multi-GPU groups only) */
 
 #define CQ_LAYER_ALL 0xFFFFFFFFu /* CollisionLayer.all, Components.swift:47-50 */
 #define CQ_MAX_OVERLAP_HITS 8    /* capsuleOverlapAll default maxHits, CollisionQuery.swift:151 */
@@ -384,6 +385,60 @@ int cq_agent_separation_batch(cq_world *w, cq_character_state *inout, int32_t n,
 int cq_agent_separation_device(cq_world *w, cq_character_state *d_inout, int32_t n, const cq_controller_params *params,
                                const float *d_mass_weight, int32_t iterations, float separation_margin, float height_margin,
                                int32_t use_query, void *stream);
+
+/* ---- the GPUs of one box -----------------------------------------------------
+ * The path shards by independent units (characters, sweeps, rays): mesh and trees are replicated on every GPU (the build
+ * is deterministic, so every replica is identical), each GPU processes one contiguous range of the units, and nothing
+ * is exchanged inside the algorithm.  The one collective a caller may want — the result records of all ranks in one
+ * place — goes through NCCL over NVLink / NVSwitch.  The reference has no counterpart: its query object is built once
+ * per scene (SceneServices.swift:45-50) and used by one thread.
+ *
+ * NCCL is loaded at run time (libnccl.so.2); every call below returns CQ_ERR_NCCL when it cannot be. */
+typedef struct cq_group cq_group;
+typedef struct cq_multi_world cq_multi_world;
+#define CQ_GROUP_ID_BYTES 128
+
+/* Contiguous range [lo, hi) of rank `rank`: lo = rank*n/n_ranks, hi = (rank+1)*n/n_ranks.  Ranges tile [0, n) exactly
+ * and differ by at most one unit. */
+void cq_shard_range(int64_t n_units, int32_t n_ranks, int32_t rank, int64_t *lo, int64_t *hi);
+
+/* One process per GPU: rank 0 makes the id, the host ships its 128 bytes to the other ranks (MPI, a socket, a file,
+ * torch.distributed ...), every rank then joins on the device that is current in its process. */
+int cq_group_unique_id(uint8_t id[CQ_GROUP_ID_BYTES]);
+int cq_group_create_rank(int32_t n_ranks, int32_t rank, const uint8_t id[CQ_GROUP_ID_BYTES], cq_group **out);
+/* One process driving n GPUs: devices = NULL means 0 .. n_gpus-1. */
+int cq_group_create_local(int32_t n_gpus, const int32_t *devices, cq_group **out);
+void cq_group_destroy(cq_group *g);
+int32_t cq_group_size(const cq_group *g);
+int32_t cq_group_rank(const cq_group *g);              /* -1 for a local group */
+int32_t cq_group_device(const cq_group *g, int32_t i); /* device of the i-th member (rank groups: i = 0) */
+
+/* All-gather of fixed-size result records.  The batch of n_units records is sharded by cq_shard_range; d_local holds
+ * this rank's shard, d_all (n_units * record_bytes bytes, device memory) receives the whole batch in unit order on
+ * every rank.  Enqueued on `stream` (cudaStream_t), no synchronisation.  Equal shards: one ncclAllGather; ragged
+ * shards: one ncclBroadcast per rank inside an NCCL group, straight to each shard's offset. */
+int cq_group_gather_records(cq_group *g, const void *d_local, int64_t n_units, size_t record_bytes, void *d_all,
+                            void *stream);
+/* The same for a local group: one (d_local, d_all, stream) triple per device, in member order; streams = NULL uses
+ * the group's own streams (cq_group_synchronize waits for them). */
+int cq_group_gather_records_local(cq_group *g, const void *const *d_local, int64_t n_units, size_t record_bytes,
+                                  void *const *d_all, void *const *streams);
+int cq_group_synchronize(cq_group *g);
+
+/* A world replicated on every device of a LOCAL group, and host-pointer batch calls sharded over the replicas: one
+ * worker thread per device runs the single-GPU copy / compute pipeline on its contiguous range of the batch, results
+ * land in the caller's arrays in unit order.  Same results as the single-GPU calls, byte for byte. */
+int cq_world_create_multi(cq_group *g, const cq_mesh_part *parts, int32_t n_parts, const cq_world_options *options,
+                          cq_multi_world **out);
+void cq_multi_world_destroy(cq_multi_world *mw);
+int32_t cq_multi_world_size(const cq_multi_world *mw);
+cq_world *cq_multi_world_replica(cq_multi_world *mw, int32_t i); /* for the *_device entry points (set the device first) */
+int cq_multi_update_transforms(cq_multi_world *mw, const uint32_t *entity_ids, const float *models, int32_t n);
+int cq_multi_raycast_batch(cq_multi_world *mw, const cq_ray *rays, int32_t n, cq_ray_hit *out);
+int cq_multi_capsule_cast_batch(cq_multi_world *mw, const cq_capsule_cast *q, int32_t n, int32_t mode, cq_cast_hit *out);
+/* CQ_MAS_AGENTS is refused: the batch is the crowd, agents of different shards would not see each other. */
+int cq_multi_move_and_slide_batch(cq_multi_world *mw, cq_character_state *inout, int32_t n,
+                                  const cq_controller_params *params, float dt, const float gravity[3], uint32_t flags);
 
 /* ---- instrumentation ------------------------------------------------------
  * Work counters of the last device/batch call, accumulated on the device when

@@ -104,8 +104,14 @@ EXPORTS = [
     "cq_world_set_counting", "cq_world_read_counters",
     "cq_crowd_create", "cq_crowd_destroy", "cq_crowd_size", "cq_crowd_step", "cq_crowd_read", "cq_crowd_write",
     "cq_crowd_device_states",
+    "cq_shard_range", "cq_group_unique_id", "cq_group_create_rank", "cq_group_create_local", "cq_group_destroy",
+    "cq_group_size", "cq_group_rank", "cq_group_device", "cq_group_gather_records", "cq_group_gather_records_local",
+    "cq_group_synchronize", "cq_world_create_multi", "cq_multi_world_destroy", "cq_multi_world_size",
+    "cq_multi_world_replica", "cq_multi_update_transforms", "cq_multi_raycast_batch", "cq_multi_capsule_cast_batch",
+    "cq_multi_move_and_slide_batch",
     "cq_host_alloc", "cq_host_free", "cq_last_error", "cq_version",
 ]
+GROUP_ID_BYTES = 128
 
 
 class CQError(RuntimeError):
@@ -188,6 +194,30 @@ def lib():
         L.cq_crowd_write.argtypes = [vp, vp]
         L.cq_crowd_device_states.argtypes = [vp]
         L.cq_crowd_device_states.restype = vp
+        i64, sz = C.c_int64, C.c_size_t
+        L.cq_shard_range.restype = None
+        L.cq_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+        L.cq_group_unique_id.argtypes = [vp]
+        L.cq_group_create_rank.argtypes = [i32, i32, vp, C.POINTER(vp)]
+        L.cq_group_create_local.argtypes = [i32, vp, C.POINTER(vp)]
+        L.cq_group_destroy.argtypes = [vp]
+        L.cq_group_destroy.restype = None
+        L.cq_group_size.argtypes = [vp]
+        L.cq_group_rank.argtypes = [vp]
+        L.cq_group_device.argtypes = [vp, i32]
+        L.cq_group_gather_records.argtypes = [vp, vp, i64, sz, vp, vp]
+        L.cq_group_gather_records_local.argtypes = [vp, vp, i64, sz, vp, vp]
+        L.cq_group_synchronize.argtypes = [vp]
+        L.cq_world_create_multi.argtypes = [vp, vp, i32, vp, C.POINTER(vp)]
+        L.cq_multi_world_destroy.argtypes = [vp]
+        L.cq_multi_world_destroy.restype = None
+        L.cq_multi_world_size.argtypes = [vp]
+        L.cq_multi_world_replica.argtypes = [vp, i32]
+        L.cq_multi_world_replica.restype = vp
+        L.cq_multi_update_transforms.argtypes = [vp, vp, vp, i32]
+        L.cq_multi_raycast_batch.argtypes = [vp, vp, i32, vp]
+        L.cq_multi_capsule_cast_batch.argtypes = [vp, vp, i32, i32, vp]
+        L.cq_multi_move_and_slide_batch.argtypes = [vp, vp, i32, vp, f32, vp, u32]
         L.cq_world_set_counting.argtypes = [vp, i32]
         L.cq_world_read_counters.argtypes = [vp, C.POINTER(Counters), i32]
         _lib = L
@@ -464,6 +494,151 @@ class CollisionQuery:
 
     def resetStats(self):
         self.stats(reset=True)
+
+
+def _mesh_parts(parts, keep):
+    arr = (MeshPart * max(len(parts), 1))()
+    for i, p in enumerate(parts):
+        pos = np.ascontiguousarray(p["positions"], np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(p["indices"], np.uint32).reshape(-1)
+        keep += [pos, idx]
+        arr[i].positions_xyz = pos.ctypes.data
+        arr[i].indices = idx.ctypes.data
+        arr[i].n_verts = pos.shape[0]
+        arr[i].n_indices = idx.shape[0]
+        m = np.asarray(p["model"], np.float32).reshape(16)
+        for k in range(16):
+            arr[i].model[k] = float(m[k])
+        arr[i].layer = int(p.get("layer", 1))
+        arr[i].mu_s = float(p.get("mu_s", 0.8))
+        arr[i].mu_k = float(p.get("mu_k", 0.6))
+        arr[i].flatten_ground = int(bool(p.get("flatten_ground", False)))
+        arr[i].is_dynamic = int(bool(p.get("is_dynamic", False)))
+        arr[i].entity_id = int(p.get("entity_id", i))
+    return arr
+
+
+def shard_range(n_units, n_ranks, rank):
+    """cq_shard_range: the contiguous range [lo, hi) of `rank` (the same rule as shard.rank_range)."""
+    lo, hi = C.c_int64(), C.c_int64()
+    lib().cq_shard_range(n_units, n_ranks, rank, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+class Group:
+    """The GPUs of one box (include/cq.h: cq_group_*).  Group.local(n) = one process driving n devices;
+    Group.rank(n_ranks, rank, id) = one process per GPU (the 128-byte id comes from Group.unique_id() on rank 0)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(GROUP_ID_BYTES, np.uint8)
+        _check(lib().cq_group_unique_id(_ptr(buf)))
+        return buf
+
+    @classmethod
+    def rank(cls, n_ranks, rank, uid):
+        uid = np.ascontiguousarray(uid, np.uint8)
+        assert uid.shape == (GROUP_ID_BYTES,)
+        h = C.c_void_p()
+        _check(lib().cq_group_create_rank(n_ranks, rank, _ptr(uid), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def local(cls, n_gpus, devices=None):
+        dv = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        _check(lib().cq_group_create_local(n_gpus, None if dv is None else _ptr(dv), C.byref(h)))
+        return cls(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def size(self):
+        return lib().cq_group_size(self._h)
+
+    def gather_records(self, d_local_ptr, n_units, record_bytes, d_all_ptr, stream=None):
+        """Process-per-GPU groups: NCCL all-gather of this rank's shard of the result records into d_all (device)."""
+        _check(lib().cq_group_gather_records(self._h, C.c_void_p(d_local_ptr), n_units, record_bytes, C.c_void_p(d_all_ptr),
+                                             C.c_void_p(stream) if stream else None))
+
+    def gather_records_local(self, d_local_ptrs, n_units, record_bytes, d_all_ptrs, streams=None):
+        n = self.size
+        loc = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in d_local_ptrs])
+        al = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in d_all_ptrs])
+        st = None if streams is None else (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in streams])
+        _check(lib().cq_group_gather_records_local(self._h, loc, n_units, record_bytes, al, st))
+
+    def synchronize(self):
+        _check(lib().cq_group_synchronize(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cq_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiWorld:
+    """cq_world_create_multi: the world replicated on every device of a local Group; host batches are sharded over the
+    replicas (contiguous ranges, one worker thread per device).  Same results as CollisionQuery, byte for byte."""
+
+    def __init__(self, group, parts, order=ORDER_REFERENCE):
+        keep = []
+        arr = _mesh_parts(parts, keep)
+        opt = WorldOptions()
+        lib().cq_world_options_default(C.byref(opt))
+        opt.order = int(order)
+        h = C.c_void_p()
+        _check(lib().cq_world_create_multi(group.handle, C.byref(arr), len(parts), C.byref(opt), C.byref(h)))
+        self._h, self._group, self.order = h, group, order
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cq_multi_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def replica(self, i):
+        return lib().cq_multi_world_replica(self._h, i)
+
+    def update_transforms(self, entity_ids, models):
+        ids = np.ascontiguousarray(entity_ids, np.uint32)
+        m = np.ascontiguousarray(models, np.float32).reshape(-1, 16)
+        _check(lib().cq_multi_update_transforms(self._h, _ptr(ids), _ptr(m), len(ids)))
+
+    def raycast(self, rays):
+        rays = np.ascontiguousarray(rays, RAY)
+        out = np.zeros(len(rays), RAY_HIT)
+        _check(lib().cq_multi_raycast_batch(self._h, _ptr(rays), len(rays), _ptr(out)))
+        return out
+
+    def capsule_cast(self, q, mode=CAST_ALL):
+        q = np.ascontiguousarray(q, CAST)
+        out = np.zeros(len(q), CAST_HIT)
+        _check(lib().cq_multi_capsule_cast_batch(self._h, _ptr(q), len(q), mode, _ptr(out)))
+        return out
+
+    def move_and_slide(self, states, params, dt=1.0 / 60.0, gravity=(0.0, -98.0, 0.0), flags=MAS_APPLY_GRAVITY):
+        assert states.dtype == STATE and states.flags["C_CONTIGUOUS"]
+        params = np.ascontiguousarray(params, PARAMS)
+        g = np.asarray(gravity, np.float32)
+        _check(lib().cq_multi_move_and_slide_batch(self._h, _ptr(states), len(states), _ptr(params), C.c_float(dt), _ptr(g), flags))
+        return states
 
 
 class Crowd:

@@ -111,6 +111,7 @@ static void make_view(cq_world *w) {
         v.refHdr = S.refHdr ? S.refHdr : S.hdr; // an empty set has no reference tree: its LBVH header says "empty" too
     }
     w->view.rank = w->order == CQ_ORDER_REFERENCE ? w->dRank : nullptr;
+    w->view.encOfRank = w->dEncOfRank;
     w->view.status = nullptr;
     if (w->hStatus) cudaHostGetDevicePointer((void **)&w->view.status, w->hStatus, 0);
     w->view.materials = w->dMaterials;
@@ -354,7 +355,7 @@ void cq_world_destroy(cq_world *w) {
     cudaSetDevice(w->device);
     cudaDeviceSynchronize(); // *_device launches may still be in flight on the caller's streams
     for (int s = 0; s < 2; s++) free_set(w->set[s]);
-    cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork), cudaFree(w->dRank);
+    cudaFree(w->dModels), cudaFree(w->dMaterials), cudaFree(w->dCounters), cudaFree(w->dWork), cudaFree(w->dRank), cudaFree(w->dEncOfRank);
     if (w->hStatus) cudaFreeHost(w->hStatus);
     destroy_scratch(w->in), destroy_scratch(w->out), destroy_scratch(w->aux), destroy_scratch(w->aux2);
     for (int k = 0; k < 4; k++) destroy_scratch(w->nodeScratch[k]), destroy_scratch(w->orderScratch[k]);

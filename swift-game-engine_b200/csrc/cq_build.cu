@@ -1205,6 +1205,7 @@ int attach_ref_order(cq_world *w) {
     cudaStream_t st = w->stream;
     const int nS = w->set[0].nTris, nD = w->set[1].nTris;
     std::vector<int32_t> rankAll((size_t)nS + nD);
+    std::vector<uint32_t> encOfRank((size_t)nS + nD);
     for (int s = 0; s < 2; s++) {
         DeviceSet &S = w->set[s];
         const int n = S.nTris;
@@ -1220,7 +1221,10 @@ int attach_ref_order(cq_world *w) {
         RefTree T;
         build_ref_tree(&lo[0].x, &hi[0].x, 4, n, T);
         const int off = s == 0 ? 0 : nS;
-        for (int t = 0; t < n; t++) rankAll[(size_t)off + t] = off + T.rank[t];
+        for (int t = 0; t < n; t++) {
+            rankAll[(size_t)off + t] = off + T.rank[t];
+            encOfRank[(size_t)off + T.rank[t]] = ((uint32_t)s << 26) | slotOf[t];
+        }
         // device form: internal nodes and leaves numbered separately
         const int nNodes = (int)T.nodes.size();
         std::vector<int32_t> idOf(nNodes);
@@ -1293,6 +1297,8 @@ int attach_ref_order(cq_world *w) {
     if (nS + nD > 0) {
         CQ_CUDA(cudaMalloc((void **)&w->dRank, sizeof(int32_t) * (size_t)(nS + nD)));
         CQ_CUDA(cudaMemcpy(w->dRank, rankAll.data(), sizeof(int32_t) * (size_t)(nS + nD), cudaMemcpyHostToDevice));
+        CQ_CUDA(cudaMalloc((void **)&w->dEncOfRank, sizeof(uint32_t) * (size_t)(nS + nD)));
+        CQ_CUDA(cudaMemcpy(w->dEncOfRank, encOfRank.data(), sizeof(uint32_t) * (size_t)(nS + nD), cudaMemcpyHostToDevice));
     }
     w->refBuildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return CQ_OK;

@@ -76,6 +76,7 @@ struct cq_world {
     int device = 0;
     int order = CQ_ORDER_REFERENCE; // tie / overflow rule of every query (include/cq.h)
     int32_t *dRank = nullptr;       // reference order: global triangle index -> visiting rank
+    uint32_t *dEncOfRank = nullptr; // reference order: visiting rank -> (set << 26) | sorted slot
     unsigned int *hStatus = nullptr; // status word, mapped host memory (WorldView::status is its device alias)
     float refBuildMs = 0;           // host time of the reference-order build (download + tree + upload)
     cudaStream_t stream = nullptr;

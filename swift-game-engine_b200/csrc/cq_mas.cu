@@ -480,7 +480,6 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
     const cq_controller_params &P = A.p;
     const f3 down = {0.0f, -1.0f, 0.0f};
     int next = NX_LOAD;
-    int depenRankLimit = -1; // reference order: rank limit of a second depenetration pass (see OverlapTop2)
 #if CQ_SINGLE_POST
     f3 postFrom = {0.0f, 0.0f, 0.0f}, postDelta = {0.0f, 0.0f, 0.0f};
     int postMode = CQ_MODE_ALL, postWait = W_NONE;
@@ -491,10 +490,9 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
     case W_DEPEN: { // DepenetrationResolver.resolve loop body after the overlap query (SYS:756-799)
         if (W.rank) { // more than maxHits triangles overlap: the reference only ever saw the first eight it visited (CQ:1272-1274)
             const int *ov = ovl_words(s);
-            if (ov[OVL_LIMIT] < 0 && ov[OVL_TOTAL] > CQ_MAX_OVERLAP_HITS) {
-                depenRankLimit = ov[CQ_MAX_OVERLAP_HITS - 1];
-                next = NX_DEPEN;
-                break;
+            if (ov[OVL_PASS] == 0 && ov[OVL_TOTAL] > CQ_MAX_OVERLAP_HITS) {
+                pool_post_first_hits(W, wp, lane, s);
+                return true; // still waiting in W_DEPEN, now for the eight pairs
             }
         }
         next = NX_SLIDE;
@@ -683,7 +681,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             next = NX_DEPEN;
         }
         if (next == NX_DEPEN) {
-            pool_post_overlap<COUNT>(W, wp, lane, s, ld3(c.pos), P.radius, P.half_height, P.collision_mask, ctr, depenRankLimit);
+            pool_post_overlap<COUNT>(W, wp, lane, s, ld3(c.pos), P.radius, P.half_height, P.collision_mask, ctr);
             c.wait = W_DEPEN;
             return true;
         }
@@ -827,7 +825,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
         QResult r;
         pool_read_result(mine, r);
         return mas_advance<COUNT, AGENTS>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);
-    }, OverlapTop2{W.rank});
+    }, OverlapTop2{W.rank != nullptr});
     pool_flush_counters(ctr, gctr, COUNT);
 }
 

@@ -64,13 +64,14 @@ struct QShared { // one per owner lane, shared memory: what executors need + the
     // result.  cast: rT/rTri/rPart + contact.  overlap: two deepest, d0=rT t0=rTri n0=rN | d1=rPos[0] t1=rPart n1=rTriN
     float rT;
     int rTri, rPart;
+    int rRank, rRank1; // visiting rank of rTri (and, overlap queries, of the second deepest rPart): exact ties go to the smaller
     float rPos[3], rN[3], rTriN[3];
     int pending; // stack entries + pairs pushed for this query and not yet consumed; 0 = query complete
 };
 
 #define CQ_QF_TIE 0x100 /* another accepted candidate had exactly the best key: the answer depended on the order rule */
 __device__ __forceinline__ int *ovl_words(QShared &s) { return reinterpret_cast<int *>(s.dir); }
-enum { OVL_TOTAL = 8, OVL_LIMIT = 9 }; // ovl_words: [0..7] smallest ranks, [8] overlapping triangles, [9] rank limit (-1 none)
+enum { OVL_TOTAL = 8, OVL_PASS = 9 }; // ovl_words: [0..7] smallest ranks seen, [8] overlapping triangles, [9] pass (0 / 1)
 
 struct QResult { // what owner logic reads back
     float bestT;
@@ -88,13 +89,11 @@ struct Job { // executor-side pair state (registers)
     int gid, part;
     float t, lastSafeT, lo, hi;
     int it, k;
-#if CQ_LOOKAHEAD
-    float margin; // slack of the look-ahead prune: float error of positions and distances at this query's scale
-#endif
 };
 
 struct Commit { // a finished pair's contribution, applied in the serialized commit step
     int kind; // 0 none, 1 cast contact, 2 overlap
+    int rank; // visiting rank of the pair's triangle (loaded by the executor, so the serialized step never waits on memory)
     float key;
     f3 pos, n, triN;
 };
@@ -211,13 +210,13 @@ __device__ __forceinline__ void pool_post_cast(const WorldView &W, const WarpPoo
 // capsuleOverlapAll prologue — CollisionQuery.swift:1209-1216 (two deepest kept, Systems.swift:764-767)
 template <bool COUNT>
 __device__ __forceinline__ void pool_post_overlap(const WorldView &W, const WarpPool &wp, int lane, QShared &s, f3 from,
-                                                  float radius, float hh, uint32_t mask, Counters &ctr, int rankLimit = -1) {
+                                                  float radius, float hh, uint32_t mask, Counters &ctr) {
     s.mode = CQ_KIND_OVERLAP;
     store3s(s.from, from);
     s.radius = radius;
     s.hh = hh;
     ovl_words(s)[OVL_TOTAL] = 0;
-    ovl_words(s)[OVL_LIMIT] = rankLimit;
+    ovl_words(s)[OVL_PASS] = 0;
     s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));         // deepest
     s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0)); // second deepest
     f3 qlo, qhi;
@@ -371,9 +370,6 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
             job.t = 0.0f;
             job.lastSafeT = 0.0f;
             job.it = 0;
-#if CQ_LOOKAHEAD
-            job.margin = 1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f;
-#endif
             job.phase = (s.mode & 0xff) == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
         }
     }
@@ -421,7 +417,10 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
             // reports contact, every bisection point of refineTOI at or before bestT still evaluates to "no contact"
             // (margin covers the float error of positions and distances), the refined toi ends beyond bestT and the
             // hit is rejected by `toi < bestT` (:1084); contacts found later have lastSafeT > bestT anyway.
-            else if (dist - job.radius >= job.minAdvance && job.t > bestT + job.margin) retired = true;
+            // margin: float error of positions and distances at this query's scale (1 mm + 8e-6 of the coordinates' size)
+            else if (dist - job.radius >= job.minAdvance &&
+                     job.t > bestT + (1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f))
+                retired = true;
 #endif
         }
     } else if (ph == PH_BIS) { // refineTOI bisection, :1379-1392 (threshold is radius, not radius+eps)
@@ -452,6 +451,7 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
         }
         if (ok) {
             cm.kind = 1;
+            cm.rank = pool_rank(wp.rank, job.gid);
             cm.key = tc;
             cm.pos = tp;
             cm.n = n;
@@ -462,6 +462,7 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
         if (dist < job.radius) {
             f3 triNormal = normalize(cross(job.T.v1 - job.T.v0, job.T.v2 - job.T.v0));
             cm.kind = 2;
+            cm.rank = pool_rank(wp.rank, job.gid);
             cm.key = job.radius - dist; // depth
             cm.n = dist < 1e-6f ? triNormal : normalize(sp - tp);
         }
@@ -470,45 +471,60 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
 
 // serialized commit: one finishing lane at a time updates its owner's record; pending counters drop
 // default overlap commit: the two deepest overlaps kept in the owner's QShared (move-and-slide depenetration)
-// Reference order (rank != nullptr): the reference's depenetration takes the first maxHits = 8 overlaps in visiting order,
-// sorts them by depth (stably) and uses one or two (Systems.swift:751-767).  A first pass keeps the two deepest of ALL
+// Reference order (byRank): the reference's depenetration takes the first maxHits = 8 overlaps in visiting order, sorts
+// them by depth (stably) and uses one or two (Systems.swift:751-767).  The first pass keeps the two deepest of ALL
 // overlapping triangles (ties: smaller rank), counts them and remembers the eight smallest ranks; only when more than
-// eight triangles overlap does the owner post a second pass limited to those ranks (OVL_LIMIT).
+// eight triangles overlap does the owner run a second pass over exactly those eight (pool_post_first_hits).
 struct OverlapTop2 {
-    const int32_t *rank;
-    __device__ __forceinline__ void operator()(QShared &s, float depth, int gid, uint32_t, f3 n) const {
-        const int rk = pool_rank(rank, gid);
-        if (rank) {
+    bool byRank;
+    __device__ __forceinline__ void operator()(QShared &s, float depth, int gid, int rk, uint32_t, f3 n) const {
+        if (byRank) {
             int *ov = ovl_words(s);
-            const int limit = ov[OVL_LIMIT];
-            if (limit >= 0) {
-                if (rk > limit) return; // second pass: beyond the first maxHits the reference visited
-            } else {
-                const int total = ov[OVL_TOTAL];
-                int pos = total < CQ_MAX_OVERLAP_HITS ? total : CQ_MAX_OVERLAP_HITS;
-                while (pos > 0 && ov[pos - 1] > rk) pos--;
-                if (pos < CQ_MAX_OVERLAP_HITS) {
-                    for (int k = total < CQ_MAX_OVERLAP_HITS - 1 ? total : CQ_MAX_OVERLAP_HITS - 1; k > pos; k--) ov[k] = ov[k - 1];
-                    ov[pos] = rk;
-                }
-                ov[OVL_TOTAL] = total + 1;
-            }
+            if (ov[OVL_PASS] == 0) keep_rank(ov, rk);
         }
         float d0 = s.rT, d1 = s.rPos[0];
         int t0 = s.rTri, t1 = s.rPart;
-        bool before0 = t0 < 0 || depth > d0 || (depth == d0 && rk < pool_rank(rank, t0));
-        bool before1 = t1 < 0 || depth > d1 || (depth == d1 && rk < pool_rank(rank, t1));
+        bool before0 = t0 < 0 || depth > d0 || (depth == d0 && rk < s.rRank);
+        bool before1 = t1 < 0 || depth > d1 || (depth == d1 && rk < s.rRank1);
         if (before0) {
-            s.rPos[0] = d0, s.rPart = t0;
+            s.rPos[0] = d0, s.rPart = t0, s.rRank1 = s.rRank;
             store3s(s.rTriN, mk3(s.rN[0], s.rN[1], s.rN[2]));
-            s.rT = depth, s.rTri = gid;
+            s.rT = depth, s.rTri = gid, s.rRank = rk;
             store3s(s.rN, n);
         } else if (before1) {
-            s.rPos[0] = depth, s.rPart = gid;
+            s.rPos[0] = depth, s.rPart = gid, s.rRank1 = rk;
             store3s(s.rTriN, n);
         }
     }
+    static __device__ __noinline__ void keep_rank(int *ov, int rk) { // sorted insert into the eight smallest ranks seen
+        const int total = ov[OVL_TOTAL];
+        int pos = total < CQ_MAX_OVERLAP_HITS ? total : CQ_MAX_OVERLAP_HITS;
+        while (pos > 0 && ov[pos - 1] > rk) pos--;
+        if (pos < CQ_MAX_OVERLAP_HITS) {
+            for (int k = total < CQ_MAX_OVERLAP_HITS - 1 ? total : CQ_MAX_OVERLAP_HITS - 1; k > pos; k--) ov[k] = ov[k - 1];
+            ov[pos] = rk;
+        }
+        ov[OVL_TOTAL] = total + 1;
+    }
 };
+
+// second depenetration pass in reference order: the owner's query becomes the (<= 8) triangles the reference visited
+// first, posted straight into the pair ring (no walk); the top-2 bookkeeping starts over
+__device__ __forceinline__ void pool_post_first_hits(const WorldView &W, const WarpPool &wp, int lane, QShared &s) {
+    int *ov = ovl_words(s);
+    int rk[CQ_MAX_OVERLAP_HITS];
+#pragma unroll
+    for (int k = 0; k < CQ_MAX_OVERLAP_HITS; k++) rk[k] = ov[k];
+    ov[OVL_TOTAL] = 0;
+    ov[OVL_PASS] = 1;
+    s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));
+    s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0));
+    s.pending = CQ_MAX_OVERLAP_HITS;
+    const uint32_t pos = atomicAdd((uint32_t *)wp.tail, (uint32_t)CQ_MAX_OVERLAP_HITS);
+#pragma unroll
+    for (int k = 0; k < CQ_MAX_OVERLAP_HITS; k++)
+        wp.ring[(pos + k) % CQ_QCAP] = ((uint32_t)lane << 27) | __ldg(W.encOfRank + rk[k]);
+}
 
 template <class OvlCommit>
 __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const Commit &cm, bool retired, int lane,
@@ -525,19 +541,20 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                 int bestTri = s.rTri;
                 bool better = cm.key < bestT;
                 bool tie = bestTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited (:1084)
-                bool tieWin = tie && pool_rank(wp.rank, job.gid) < pool_rank(wp.rank, bestTri);
+                bool tieWin = tie && cm.rank < s.rRank;
                 if (tie) s.mode |= CQ_QF_TIE;
                 if (better) s.mode &= ~CQ_QF_TIE;
                 if (better || tieWin) {
                     s.rT = cm.key;
                     s.rTri = job.gid;
+                    s.rRank = cm.rank;
                     s.rPart = job.part;
                     store3s(s.rPos, cm.pos);
                     store3s(s.rN, cm.n);
                     store3s(s.rTriN, cm.triN);
                 }
             } else { // overlap: (depth desc, index asc) bookkeeping is the kernel's (top-2 or top-K)
-                ovl(s, cm.key, job.gid, job.enc, cm.n);
+                ovl(s, cm.key, job.gid, cm.rank, job.enc, cm.n);
             }
         }
         __syncwarp();

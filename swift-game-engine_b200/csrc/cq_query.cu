@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(Wor
         pool_post_cast<COUNT>(W, wp, lane, mine, load3(c.from), load3(c.delta), c.radius, c.half_height, c.mask, mode,
                               c.min_normal_y, ct);
         return true;
-    }, OverlapTop2{W.rank});
+    }, OverlapTop2{W.rank != nullptr});
     flush_counters<COUNT>(ctr, gctr);
 }
 
@@ -416,11 +416,9 @@ struct OvlTop {
 
 struct OverlapTopK {
     OvlTop *tops; // the warp's 32 records
-    const int32_t *rank;
     bool byRank; // keep the smallest ranks (overlap-all in reference order) instead of the deepest
-    __device__ __forceinline__ void operator()(QShared &, float depth, int gid, uint32_t enc, f3) const {
+    __device__ __forceinline__ void operator()(QShared &, float depth, int gid, int rk, uint32_t enc, f3) const {
         OvlTop &t = tops[enc >> 27];
-        const int rk = pool_rank(rank, gid);
         t.total++;
         int pos = t.count;
         if (byRank) {
@@ -510,7 +508,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
         top.count = 0, top.total = 0, top.cap = ALL ? maxHits : 1, top.tie = 0;
         pool_post_overlap<COUNT>(W, wp, lane, mine, curFrom, curR, curHH, c.mask, ct);
         return true;
-    }, OverlapTopK{tops + warp * 32, W.rank, ALL && W.rank != nullptr});
+    }, OverlapTopK{tops + warp * 32, ALL && W.rank != nullptr});
     flush_counters<COUNT>(ctr, gctr);
 }
 

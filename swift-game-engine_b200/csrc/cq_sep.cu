@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_turns(WorldView W, const
         QResult r;
         pool_read_result(mine, r);
         return sep_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);
-    }, OverlapTop2{W.rank});
+    }, OverlapTop2{W.rank != nullptr});
     pool_flush_counters(ctr, gctr, COUNT);
 }
 
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_post(WorldView W, const 
         QResult r;
         pool_read_result(mine, r);
         return post_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);
-    }, OverlapTop2{W.rank});
+    }, OverlapTop2{W.rank != nullptr});
     pool_flush_counters(ctr, gctr, COUNT);
 }
 

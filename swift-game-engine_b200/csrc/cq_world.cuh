@@ -63,6 +63,7 @@ struct WorldView {
     // set first), or nullptr in canonical order, where the rank of a triangle is its index.  Exact ties (equal toi /
     // depth) go to the smaller rank; capsuleOverlapAll keeps the maxHits smallest ranks (CollisionQuery.swift:1272-1274).
     const int32_t *rank;
+    const uint32_t *encOfRank; // reference order: visiting rank -> (set << 26) | slot of the sorted SoA (a pair-ring entry)
     // Device-visible status word in mapped host memory (zero = fine).  Bit 0: a warp's node stack would have overflowed
     // (cq_pool.cuh) — the launch's results are incomplete; the next synchronising call reports CQ_ERR_CUDA.
     unsigned int *status;

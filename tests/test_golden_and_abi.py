@@ -4,6 +4,8 @@ import ctypes
 import json
 import os
 import re
+import shutil
+import importlib
 import subprocess
 import sys
 
@@ -51,7 +53,8 @@ def test_libcq_exports_every_declared_symbol(cq):
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert sorted(cq.EXPORTS) == declared
-    assert b"sm_100a" in lib.cq_version.__call__.__self__.restype.__name__.encode() or True
+    lib.cq_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.cq_version()
     out = subprocess.run(["cuobjdump", "-lelf", cq.LIB_PATH], capture_output=True, text=True)
     if out.returncode == 0:
         assert "sm_100a" in out.stdout
@@ -338,6 +341,39 @@ def test_native_example_links_and_fails_loudly_without_a_gpu(cq, scenes, tmp_pat
         assert r.returncode == 0 and "256 characters x 3 steps" in r.stdout, r.stderr
     else:
         assert r.returncode == 4 and "cq_world_create: CUDA error" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_multi_gpu_example_links_and_group_api_without_a_gpu(cq, tmp_path):
+    """examples/cq_multi_gpu.cpp (all GPUs of a box from compiled host code: cq_group_*, cq_world_create_multi, the NCCL
+    gather) must build against include/cq.h and libcq.so alone and stop with exit 4 on a box without a CUDA device.  The
+    host half of the group API works anywhere: cq_shard_range tiles a batch exactly like shard.rank_range, NCCL is loaded
+    at run time (no link-time dependency), a local group without devices is refused with CQ_ERR_CUDA."""
+    cq.build()
+    shard = importlib.import_module("swift-game-engine_b200.shard")
+    for n in (0, 1, 7, 8, 1000, (1 << 23) + 5):
+        for ws in (1, 2, 3, 8):
+            got = [cq.shard_range(n, ws, r) for r in range(ws)]
+            assert got == [shard.rank_range(n, r, ws) for r in range(ws)]
+            assert got[0][0] == 0 and got[-1][1] == n and all(a[1] == b[0] for a, b in zip(got, got[1:]))
+    assert cq.shard_range(10, 0, 0) == (0, 0) and cq.shard_range(10, 2, 5) == (0, 0)
+    needed = subprocess.run(["ldd", cq.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in needed and "libcudart" not in needed and "torch" not in needed
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "cq_multi_gpu"
+    r = subprocess.run(["nvcc", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", os.path.join(ROOT, "examples", "cq_multi_gpu.cpp"),
+                        "-L" + cq.CSRC, "-lcq", "-Xlinker", "-rpath", "-Xlinker", cq.CSRC, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if not have_gpu:
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 4 and "no usable CUDA device" in r.stderr
+        with pytest.raises(cq.CQError):
+            cq.Group.local(1)
 
 
 class _RecorderWorld:

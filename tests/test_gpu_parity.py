@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 ABS_TOL, REL_TOL = 1e-5, 1e-4  # the stated tolerance (only used against the REFERENCE-order oracle)
 
 
+def _caller_order(hits, counts):
+    """What every caller of capsuleOverlapAll in the reference does with the result (Systems.swift:759): a stable sort by
+    depth, deepest first.  The oracle's C wrapper emits that order; in reference order the library returns the hits the
+    way the reference itself returns them — in visiting order — so the comparison sorts the library's rows the same way."""
+    depth = np.where(np.arange(hits.shape[1])[None, :] < counts[:, None], hits["depth"], -np.inf)
+    idx = np.argsort(-depth, axis=1, kind="stable")
+    return np.take_along_axis(hits, idx, axis=1)
+
+
 def _fields_equal(a, b, fields):
     return {f: bool(np.array_equal(a[f], b[f])) for f in fields}
 
@@ -97,6 +106,8 @@ def test_capsule_overlap_all_bit_exact(world, scenes, orc):
         got, gcnt, gov = g.capsuleOverlapAll(c, max_hits)
         ref, rcnt, rov = o.capsule_overlap_all(c, max_hits, g.order)
         assert np.array_equal(gcnt, rcnt) and np.array_equal(gov, rov)
+        if g.order == orc.ORDER_REFERENCE:
+            got = _caller_order(got, gcnt)
         for f in ("triangle_index", "depth", "position", "normal", "triangle_normal"):
             assert np.array_equal(got[f], ref[f]), f
         # the other order rule: same SET of triangles whenever it did not overflow
@@ -409,7 +420,13 @@ def test_parameter_edge_cases(cq, orc, scenes):
     c = scenes.gen_capsules(2000, lo, hi, seed=8, expand=0.2)
     got, cnt, ov = gr.capsuleOverlapAll(c, 8)
     ref, rcnt, rov = orr.capsule_overlap_all(c, 8, gr.order)
-    assert ov.sum() > 100 and np.array_equal(ov, rov) and np.array_equal(cnt, rcnt) and got.tobytes() == ref.tobytes()
+    assert ov.sum() > 100 and np.array_equal(ov, rov) and np.array_equal(cnt, rcnt)
+    assert _caller_order(got, cnt).tobytes() == ref.tobytes()
+    gc = cq.CollisionQuery(rparts, order=cq.ORDER_CANONICAL)
+    got, cnt, ov = gc.capsuleOverlapAll(c, 8)
+    ref, rcnt, rov = orr.capsule_overlap_all(c, 8, gc.order)
+    assert np.array_equal(ov, rov) and np.array_equal(cnt, rcnt) and got.tobytes() == ref.tobytes()
+    gc.close()
     for w in (g, o, gr, orr):
         w.close()
 
@@ -809,4 +826,59 @@ def test_resident_crowd_matches_full_record_steps(cq, scenes):
     empty.step(None, params)
     empty.close()
     crowd.close()
+    g.close()
+
+
+def test_group_and_multi_world_on_the_visible_gpus(cq, orc, scenes):
+    """cq_group_* / cq_world_create_multi on however many GPUs this box shows (1 in the driver's test run, more under
+    `gpurun --gpus N`): a local group, the world replicated on every device, host batches sharded over the replicas must
+    equal the single-GPU calls byte for byte; the NCCL gather of device-resident shards (ragged on purpose) must put the
+    whole batch, in unit order, on every device; and a process-per-GPU group of one rank gathers through NCCL as well."""
+    import torch
+    n_gpus = torch.cuda.device_count()
+    parts = scenes.mirror_scene(use_hulls=False)
+    lo, hi = scenes.scene_aabb(parts[1:])
+    group = cq.Group.local(n_gpus)
+    assert group.size == n_gpus
+    mw = cq.MultiWorld(group, parts)
+    g = cq.CollisionQuery(parts)
+    q = scenes.gen_casts(30011, lo, hi, seed=401)  # a prime count: ragged shards on any group size > 1
+    want = g.capsuleCastBlocking(q)
+    assert mw.capsule_cast(q, cq.CAST_BLOCKING).tobytes() == want.tobytes()
+    rays = scenes.gen_rays(20003, lo, hi, seed=402)
+    assert mw.raycast(rays).tobytes() == g.raycast(rays).tobytes()
+    pos, vel = scenes.gen_c3_characters(10007, seed=403)
+    a, b = cq.init_states(pos, vel), cq.init_states(pos, vel)
+    for _ in range(3):
+        mw.move_and_slide(a, cq.default_params())
+        g.move_and_slide(b, cq.default_params())
+    assert a.tobytes() == b.tobytes()
+    with pytest.raises(cq.CQError):
+        mw.move_and_slide(a, cq.default_params(), flags=cq.MAS_APPLY_GRAVITY | cq.MAS_AGENTS)
+    # device-resident shards + gather
+    rec = cq.CAST_HIT.itemsize
+    n = len(q)
+    local, whole = [], []
+    for i in range(n_gpus):
+        s0, s1 = cq.shard_range(n, n_gpus, i)
+        dev = torch.device("cuda", i)
+        local.append(torch.from_numpy(np.frombuffer(want[s0:s1].tobytes(), np.uint8).copy()).to(dev))
+        whole.append(torch.zeros(n * rec, dtype=torch.uint8, device=dev))
+    torch.cuda.synchronize()
+    group.gather_records_local([t.data_ptr() for t in local], n, rec, [t.data_ptr() for t in whole])
+    group.synchronize()
+    for i in range(n_gpus):
+        assert whole[i].cpu().numpy().tobytes() == want.tobytes(), i
+    mw.close()
+    group.close()
+    # one process per GPU, here a group of one rank: NCCL all-gather straight into the result buffer
+    torch.cuda.set_device(0)
+    rg = cq.Group.rank(1, 0, cq.Group.unique_id())
+    src = torch.from_numpy(np.frombuffer(want.tobytes(), np.uint8).copy()).to("cuda:0")
+    dst = torch.zeros_like(src)
+    st = torch.cuda.Stream()
+    rg.gather_records(src.data_ptr(), n, rec, dst.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert bool(torch.equal(src, dst))
+    rg.close()
     g.close()

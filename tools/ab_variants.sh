@@ -12,7 +12,7 @@ mkdir -p gpurun_out
 for M in $MESHES; do
   for L in "$@"; do
     tag=$(basename "$L" .so)
-    CQ_LIB=$D/$L timeout 40 python bench.py --mesh "$M" --no-cpu-baseline > "gpurun_out/ab_${M}_${tag}.json" 2> "gpurun_out/ab_${M}_${tag}.err"
+    CQ_LIB=$D/$L timeout 40 python bench.py --mesh "$M" --no-cpu-baseline --no-extras > "gpurun_out/ab_${M}_${tag}.json" 2> "gpurun_out/ab_${M}_${tag}.err"
   done
 done
 python - <<'PY'
