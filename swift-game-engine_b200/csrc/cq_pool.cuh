@@ -110,6 +110,9 @@ struct WarpPool { // per-warp handles
     unsigned int *status;    // the world's status word (mapped host memory)
 };
 __device__ __forceinline__ bool pool_stack_room(const WarpPool &wp, uint32_t pos, uint32_t cnt) {
+#ifdef CQ_AB_NOGUARD
+    return true;
+#endif
     if (pos + cnt <= (uint32_t)CQ_NSCAP) return true;
     atomicOr(wp.status, 1u);
     return false;
@@ -475,55 +478,58 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
 // them by depth (stably) and uses one or two (Systems.swift:751-767).  The first pass keeps the two deepest of ALL
 // overlapping triangles (ties: smaller rank), counts them and remembers the eight smallest ranks; only when more than
 // eight triangles overlap does the owner run a second pass over exactly those eight (pool_post_first_hits).
+// Out of line on purpose: overlap commits are rare (a character that starts a step inside geometry) while the commit step
+// sits in the steady-state loop whose code size decides the small-scene throughput — inlined, this
+// bookkeeping made the loop 4 KB longer and the hulls step 12% slower.
+static __device__ __noinline__ void overlap_top2_commit(QShared &s, float depth, int gid, int rk, f3 n, bool byRank) {
+    if (byRank) {
+        int *ov = ovl_words(s);
+        if (ov[OVL_PASS] == 0) { // first pass: count, and keep the eight smallest ranks seen (sorted insert)
+            const int total = ov[OVL_TOTAL];
+            int pos = total < CQ_MAX_OVERLAP_HITS ? total : CQ_MAX_OVERLAP_HITS;
+            while (pos > 0 && ov[pos - 1] > rk) pos--;
+            if (pos < CQ_MAX_OVERLAP_HITS) {
+#pragma unroll 1
+                for (int k = total < CQ_MAX_OVERLAP_HITS - 1 ? total : CQ_MAX_OVERLAP_HITS - 1; k > pos; k--) ov[k] = ov[k - 1];
+                ov[pos] = rk;
+            }
+            ov[OVL_TOTAL] = total + 1;
+        }
+    }
+    float d0 = s.rT, d1 = s.rPos[0];
+    int t0 = s.rTri, t1 = s.rPart;
+    bool before0 = t0 < 0 || depth > d0 || (depth == d0 && rk < s.rRank);
+    bool before1 = t1 < 0 || depth > d1 || (depth == d1 && rk < s.rRank1);
+    if (before0) {
+        s.rPos[0] = d0, s.rPart = t0, s.rRank1 = s.rRank;
+        store3s(s.rTriN, mk3(s.rN[0], s.rN[1], s.rN[2]));
+        s.rT = depth, s.rTri = gid, s.rRank = rk;
+        store3s(s.rN, n);
+    } else if (before1) {
+        s.rPos[0] = depth, s.rPart = gid, s.rRank1 = rk;
+        store3s(s.rTriN, n);
+    }
+}
 struct OverlapTop2 {
     bool byRank;
     __device__ __forceinline__ void operator()(QShared &s, float depth, int gid, int rk, uint32_t, f3 n) const {
-        if (byRank) {
-            int *ov = ovl_words(s);
-            if (ov[OVL_PASS] == 0) keep_rank(ov, rk);
-        }
-        float d0 = s.rT, d1 = s.rPos[0];
-        int t0 = s.rTri, t1 = s.rPart;
-        bool before0 = t0 < 0 || depth > d0 || (depth == d0 && rk < s.rRank);
-        bool before1 = t1 < 0 || depth > d1 || (depth == d1 && rk < s.rRank1);
-        if (before0) {
-            s.rPos[0] = d0, s.rPart = t0, s.rRank1 = s.rRank;
-            store3s(s.rTriN, mk3(s.rN[0], s.rN[1], s.rN[2]));
-            s.rT = depth, s.rTri = gid, s.rRank = rk;
-            store3s(s.rN, n);
-        } else if (before1) {
-            s.rPos[0] = depth, s.rPart = gid, s.rRank1 = rk;
-            store3s(s.rTriN, n);
-        }
-    }
-    static __device__ __noinline__ void keep_rank(int *ov, int rk) { // sorted insert into the eight smallest ranks seen
-        const int total = ov[OVL_TOTAL];
-        int pos = total < CQ_MAX_OVERLAP_HITS ? total : CQ_MAX_OVERLAP_HITS;
-        while (pos > 0 && ov[pos - 1] > rk) pos--;
-        if (pos < CQ_MAX_OVERLAP_HITS) {
-            for (int k = total < CQ_MAX_OVERLAP_HITS - 1 ? total : CQ_MAX_OVERLAP_HITS - 1; k > pos; k--) ov[k] = ov[k - 1];
-            ov[pos] = rk;
-        }
-        ov[OVL_TOTAL] = total + 1;
+        overlap_top2_commit(s, depth, gid, rk, n, byRank);
     }
 };
 
 // second depenetration pass in reference order: the owner's query becomes the (<= 8) triangles the reference visited
 // first, posted straight into the pair ring (no walk); the top-2 bookkeeping starts over
-__device__ __forceinline__ void pool_post_first_hits(const WorldView &W, const WarpPool &wp, int lane, QShared &s) {
+static __device__ __noinline__ void pool_post_first_hits(const uint32_t *__restrict__ encOfRank, uint32_t *ring, volatile uint32_t *tail,
+                                                         int lane, QShared &s) {
     int *ov = ovl_words(s);
-    int rk[CQ_MAX_OVERLAP_HITS];
-#pragma unroll
-    for (int k = 0; k < CQ_MAX_OVERLAP_HITS; k++) rk[k] = ov[k];
+    const uint32_t pos = atomicAdd((uint32_t *)tail, (uint32_t)CQ_MAX_OVERLAP_HITS);
+#pragma unroll 1
+    for (int k = 0; k < CQ_MAX_OVERLAP_HITS; k++) ring[(pos + k) % CQ_QCAP] = ((uint32_t)lane << 27) | __ldg(encOfRank + ov[k]);
     ov[OVL_TOTAL] = 0;
     ov[OVL_PASS] = 1;
     s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));
     s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0));
     s.pending = CQ_MAX_OVERLAP_HITS;
-    const uint32_t pos = atomicAdd((uint32_t *)wp.tail, (uint32_t)CQ_MAX_OVERLAP_HITS);
-#pragma unroll
-    for (int k = 0; k < CQ_MAX_OVERLAP_HITS; k++)
-        wp.ring[(pos + k) % CQ_QCAP] = ((uint32_t)lane << 27) | __ldg(W.encOfRank + rk[k]);
 }
 
 template <class OvlCommit>
@@ -531,6 +537,7 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                                             OvlCommit ovl) {
     uint32_t fin = __ballot_sync(0xffffffffu, retired);
     uint32_t todo = __ballot_sync(0xffffffffu, retired && cm.kind != 0);
+#pragma unroll 1
     while (todo) {
         int l = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -542,8 +549,10 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                 bool better = cm.key < bestT;
                 bool tie = bestTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited (:1084)
                 bool tieWin = tie && cm.rank < s.rRank;
+#ifndef CQ_AB_NOTIE
                 if (tie) s.mode |= CQ_QF_TIE;
                 if (better) s.mode &= ~CQ_QF_TIE;
+#endif
                 if (better || tieWin) {
                     s.rT = cm.key;
                     s.rTri = job.gid;

@@ -300,6 +300,211 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast_ref(WorldView W, const cq
     flush_counters<COUNT>(ctr, gctr);
 }
 
+// ---------------------------------------------------------------- raycast, phase-voted (both order rules)
+// ncu on the one-step-per-trip kernels above (profiles/r2_c5_raycast_v12_summary.txt): 7.2 of 32 lanes active per warp
+// instruction, 65% of the stall samples long-scoreboard.  A ray of C5 takes ~8 node steps, ~1.4 triangle steps and one
+// finish + fetch; with one step of whatever kind per trip every trip pays for all three bodies while each is populated
+// by a third of the lanes or fewer.  Here the three bodies are PHASES of the warp:
+//   refill    finished lanes write their hit and fetch the next ray — only when at least RAY_REFILL_MIN lanes are idle
+//             (or nobody has anything else to do), so the long, latency-heavy body runs for many lanes at once;
+//   nodes     lanes with a non-empty stack pop / test / push, and the phase REPEATS while at least RAY_NODE_MIN lanes
+//             still want a node step: the dependent node fetches of most of the warp are in flight together;
+//   triangles lanes holding a leaf range test their next triangle, repeated while RAY_TRI_MIN lanes have one.
+// Every phase runs at least once per round when any lane wants it, so progress never depends on the thresholds.
+// The per-ray logic is exactly that of k_raycast (canonical: nearest over all triangles, conservative padded slabs,
+// ties to the smaller index) and k_raycast_ref (the reference's walk over the reference's tree, its own slab test,
+// tmin re-tested at pop time, sets walked independently and merged with `<=`).
+#ifndef RAY_REFILL_MIN
+#define RAY_REFILL_MIN 8
+#endif
+#ifndef RAY_NODE_MIN
+#define RAY_NODE_MIN 12
+#endif
+#ifndef RAY_TRI_MIN
+#define RAY_TRI_MIN 8
+#endif
+template <bool COUNT, bool REF>
+__global__ void __launch_bounds__(Q_THREADS) k_raycast_phased(WorldView W, const cq_ray *__restrict__ rays, int n,
+                                                              cq_ray_hit *__restrict__ out, uint8_t *__restrict__ flagsOut,
+                                                              int *workCounter, const uint32_t *__restrict__ order,
+                                                              unsigned long long *gctr) {
+    Counters ctr = {0, 0, 0, 0};
+    int stackRef[CQ_STACK];
+    float stackT[REF ? CQ_STACK : 1];
+    int sp = 0, set = 2, leafPos = 0, leafEnd = 0, cur = -1;
+    int bestTri = -1, setTri = -1;
+    float closestT = 0.0f, bestT = 0.0f, maxDist = 0.0f;
+    f3 o = {0, 0, 0}, d = {0, 0, 0}, inv = {0, 0, 0}, bestN = {0, 0, 0}, setN = {0, 0, 0};
+    uint32_t mask = 0, tie = 0, setTie = 0;
+    bool alive = true;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        // ---------------- refill / set transitions: lanes whose stack and leaf range are empty
+        const bool idle = alive && sp == 0 && leafPos >= leafEnd;
+        const uint32_t idleMask = __ballot_sync(0xffffffffu, idle);
+        const uint32_t busyMask = __ballot_sync(0xffffffffu, alive && !idle);
+        if (idleMask != 0u && (__popc(idleMask) >= RAY_REFILL_MIN || busyMask == 0u)) {
+            if (idle) {
+                if (REF) { // the set just walked: merge its hit (static wins `<=`, :902-907)
+                    if (setTri >= 0 && (bestTri < 0 || !(bestT <= closestT))) bestT = closestT, bestTri = setTri, bestN = setN, tie = setTie;
+                    setTri = -1, setTie = 0;
+                }
+                // one atomic per warp: the lanes that need a new ray take consecutive positions of the processing order
+                const bool finished = set >= 2; // (also true on a lane's first trip)
+                const uint32_t takers = __ballot_sync(idleMask, finished);
+                if (finished) {
+                    if (cur >= 0) { // write the finished ray
+                        cq_ray_hit hres;
+                        const float tHit = REF ? bestT : closestT;
+                        if (bestTri >= 0) {
+                            hres.distance = tHit;
+                            store3(hres.position, o + d * tHit); // :962
+                            store3(hres.normal, bestN);
+                            hres.triangle_index = bestTri;
+                        } else {
+                            hres.distance = 0.0f;
+                            store3(hres.position, mk3(0, 0, 0));
+                            store3(hres.normal, mk3(0, 0, 0));
+                            hres.triangle_index = -1;
+                        }
+                        out[cur] = hres;
+                        if (flagsOut) flagsOut[cur] = (uint8_t)tie;
+                    }
+                    int base = 0;
+                    const int leader = __ffs(takers) - 1;
+                    if (lane == leader) base = atomicAdd(workCounter, __popc(takers));
+                    base = __shfl_sync(takers, base, leader);
+                    cur = base + __popc(takers & ((1u << lane) - 1u));
+                    if (cur >= n) {
+                        cur = -1;
+                        alive = false;
+                    } else {
+                        if (order) cur = (int)order[cur];
+                        cq_ray r = rays[cur];
+                        o = load3(r.origin), d = load3(r.direction);
+                        maxDist = r.max_distance;
+                        closestT = maxDist;
+                        mask = r.mask;
+                        bestTri = -1, setTri = -1, tie = 0, setTie = 0;
+                        inv = mk3(d.x != 0.0f ? 1.0f / d.x : FLT_MAX, d.y != 0.0f ? 1.0f / d.y : FLT_MAX,
+                                  d.z != 0.0f ? 1.0f / d.z : FLT_MAX); // :1606-1608
+                        set = 0;
+                    }
+                }
+                // Roots.  Reference order walks one set at a time (closestT starts over at maxDistance, :921): push the next
+                // set's root and stop.  Canonical order pushes both roots at once, the dynamic one first so that the static
+                // set is popped first.
+                while (alive && set < 2 && (!REF || sp == 0)) {
+                    const int s1 = REF ? set : 1 - set;
+                    const SetHeader h = *(REF ? (s1 ? W.set[1].refHdr : W.set[0].refHdr) : (s1 ? W.set[1].hdr : W.set[0].hdr));
+                    if (REF) closestT = maxDist;
+                    set++;
+                    if (h.rootRef == CQ_REF_EMPTY) continue;
+                    if (COUNT) {
+                        ctr.queries++;
+                        ctr.nodes++;
+                    }
+                    const f3 lo = mk3(h.lo[0], h.lo[1], h.lo[2]), hi = mk3(h.hi[0], h.hi[1], h.hi[2]);
+                    const int tagged = h.rootRef < 0 ? ~((~h.rootRef) | (s1 << 30)) : (h.rootRef | (s1 << 30)); // bit 30 = set
+                    if (REF) {
+                        float tmin;
+                        if (ref_ray_aabb(o, inv, lo, hi, tmin)) stackRef[sp] = tagged, stackT[sp++] = tmin;
+                    } else if (ray_box(o, inv, lo, hi, closestT)) {
+                        stackRef[sp++] = tagged;
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !alive)) break;
+        // ---------------- node phase
+        while (true) {
+            const bool wantN = alive && sp > 0 && leafPos >= leafEnd;
+            const uint32_t nMask = __ballot_sync(0xffffffffu, wantN);
+            if (nMask == 0u) break;
+            if (wantN) {
+                --sp;
+                const int ref = stackRef[sp];
+                bool visit = true;
+                if (REF) visit = !(stackT[sp] > closestT); // :933, with the closestT of NOW
+                if (visit) {
+                    if (ref < 0) {
+                        int enc = ~ref;
+                        const int s1 = (enc >> 30) & 1;
+                        enc &= 0x3fffffff;
+                        leafPos = (enc >> 2) | (s1 << 30);
+                        leafEnd = leafPos + (enc & 3) + 1;
+                    } else {
+                        const int s1 = (ref >> 30) & 1;
+                        const Node *nd = (REF ? W.set[s1].refNodes : W.set[s1].nodes) + (ref & 0x3fffffff);
+                        const float4 n0 = __ldg(&nd->n0), n1 = __ldg(&nd->n1), n2 = __ldg(&nd->n2), n3 = __ldg(&nd->n3);
+                        if (COUNT) ctr.nodes += 2;
+                        int r0 = __float_as_int(n0.w), r1 = __float_as_int(n1.w);
+                        r0 = r0 < 0 ? ~((~r0) | (s1 << 30)) : (r0 | (s1 << 30));
+                        r1 = r1 < 0 ? ~((~r1) | (s1 << 30)) : (r1 | (s1 << 30));
+                        if (REF) {
+                            float t0, t1;
+                            const bool h0 = ref_ray_aabb(o, inv, xyz(n0), xyz(n1), t0); // left
+                            const bool h1 = ref_ray_aabb(o, inv, xyz(n2), xyz(n3), t1); // right
+                            if (h0) stackRef[sp] = r0, stackT[sp++] = t0; // push left, then right: right is popped first (:965-966)
+                            if (h1) stackRef[sp] = r1, stackT[sp++] = t1;
+                        } else {
+                            const bool h0 = ray_box(o, inv, xyz(n0), xyz(n1), closestT);
+                            const bool h1 = ray_box(o, inv, xyz(n2), xyz(n3), closestT);
+                            if (h1) stackRef[sp++] = r1;
+                            if (h0) stackRef[sp++] = r0;
+                        }
+                    }
+                }
+            }
+            if (__popc(nMask) < RAY_NODE_MIN) break;
+        }
+        // ---------------- triangle phase
+        while (true) {
+            const bool wantT = alive && leafPos < leafEnd;
+            const uint32_t tMask = __ballot_sync(0xffffffffu, wantT);
+            if (tMask == 0u) break;
+            if (wantT) {
+                const int s1 = (leafPos >> 30) & 1, pos = leafPos & 0x3fffffff;
+                leafPos++;
+                const SetView &S = W.set[s1];
+                const int slot = REF ? (int)__ldg(S.refSlot + pos) : pos; // reference order: ascending triOrder positions (:938-940)
+                uint32_t layer;
+                int triId, part;
+                Tri T = load_tri(S, slot, layer, triId, part);
+                if ((layer & mask) != 0u) {
+                    if (COUNT) ctr.cands++;
+                    float t;
+                    if (ray_triangle(o, d, T, t)) {
+                        const int gid = triId + S.triOffset;
+                        if (REF) {
+                            if (t < closestT) { // strict: the first visited keeps an exact tie (:944)
+                                closestT = t;
+                                setTri = gid;
+                                setTie = 0;
+                                f3 nrm = normalize(cross(T.v1 - T.v0, T.v2 - T.v0));
+                                setN = dot(nrm, d) > 0.0f ? -nrm : nrm;
+                            } else if (t == closestT && setTri >= 0) {
+                                setTie = CQ_HIT_TIE;
+                            }
+                        } else {
+                            if (bestTri >= 0 && t == closestT) tie = CQ_HIT_TIE;
+                            if (t < closestT) tie = 0;
+                            if (t < closestT || (bestTri >= 0 && t == closestT && gid < bestTri)) {
+                                closestT = t;
+                                bestTri = gid;
+                                f3 nrm = normalize(cross(T.v1 - T.v0, T.v2 - T.v0)); // :960-961
+                                bestN = dot(nrm, d) > 0.0f ? -nrm : nrm;
+                            }
+                        }
+                    }
+                }
+            }
+            if (__popc(tMask) < RAY_TRI_MIN) break;
+        }
+    }
+    flush_counters<COUNT>(ctr, gctr);
+}
+
 // ---------------------------------------------------------------- capsule cast (CollisionQuery.swift:787-828, 980-1117)
 // Warp-cooperative pool engine (cq_pool.cuh): every lane owns one sweep at a time (fetched dynamically),
 // walks the LBVH for it and pushes its candidate triangles into the warp's ring; all 32 lanes execute
@@ -523,7 +728,11 @@ int launch_raycast(cq_world *w, const cq_ray *d_rays, int n, cq_ray_hit *d_out, 
     const bool ref = w->order == CQ_ORDER_REFERENCE; // the reference's own walk over the reference's own tree
     const int ci = (w->counting ? 1 : 0) + (ref ? 2 : 0);
     using Kernel = void (*)(WorldView, const cq_ray *, int, cq_ray_hit *, uint8_t *, int *, const uint32_t *, unsigned long long *);
-    static const Kernel kernels[4] = {k_raycast<false>, k_raycast<true>, k_raycast_ref<false>, k_raycast_ref<true>};
+    static const bool stepwise = getenv("CQ_RAY_STEPWISE") != nullptr; // the older one-step-per-trip kernels (A/B)
+    static const Kernel phased[4] = {k_raycast_phased<false, false>, k_raycast_phased<true, false>, k_raycast_phased<false, true>,
+                                     k_raycast_phased<true, true>};
+    static const Kernel kernels_old[4] = {k_raycast<false>, k_raycast<true>, k_raycast_ref<false>, k_raycast_ref<true>};
+    const Kernel *kernels = stepwise ? kernels_old : phased;
     const Kernel kernel = kernels[ci];
     if (!blocksPerSm[ci]) {
         cudaDeviceProp prop;
