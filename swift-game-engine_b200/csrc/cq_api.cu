@@ -105,6 +105,7 @@ static void make_view(cq_world *w) {
         v.nodes = S.nodes;
         v.nodes4 = S.nodes4;
         v.hdr = S.hdr;
+        v.triPart = S.triPart;
         v.triOffset = s == 0 ? 0 : w->set[0].nTris;
         v.refNodes = S.refNodes;
         v.refSlot = S.refSlot;

@@ -464,15 +464,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint32_t *__restri
 // ---------------------------------------------------------------- gather into the sorted float4 SoA
 __global__ void k_gather_sorted(const uint32_t *__restrict__ sortedTri, int nTris, const float4 *__restrict__ world,
                                 const uint32_t *__restrict__ idx, const uint32_t *__restrict__ layer,
-                                const int32_t *__restrict__ part, float4 *__restrict__ tv0, float4 *__restrict__ tv1,
-                                float4 *__restrict__ tv2) {
+                                const int32_t *__restrict__ rank /* global index -> visiting rank, or null */, int triOffset,
+                                float4 *__restrict__ tv0, float4 *__restrict__ tv1, float4 *__restrict__ tv2) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nTris) return;
     uint32_t t = sortedTri[s];
     float4 a = world[idx[3 * t]], b = world[idx[3 * t + 1]], c = world[idx[3 * t + 2]];
     a.w = __uint_as_float(layer[t]);
     b.w = __int_as_float((int)t);
-    c.w = __int_as_float(part[t]);
+    c.w = __int_as_float(rank ? rank[triOffset + (int)t] : triOffset + (int)t); // canonical order: rank = global index
     tv0[s] = a;
     tv1[s] = b;
     tv2[s] = c;
@@ -732,8 +732,10 @@ static int build_tree(cq_world *w, DeviceSet &S, const uint32_t *sortedKeys /* m
     cudaStream_t st = w->stream;
     int n = S.nTris;
     if (n > 0) {
-        k_gather_sorted<<<cdiv(n, 256), 256, 0, st>>>(S.sortedTri, n, S.worldPos, S.indices, S.triLayer, S.triPart, S.tv0,
-                                                      S.tv1, S.tv2);
+        const int triOffset = &S == &w->set[1] ? w->set[0].nTris : 0;
+        k_gather_sorted<<<cdiv(n, 256), 256, 0, st>>>(S.sortedTri, n, S.worldPos, S.indices, S.triLayer,
+                                                      w->order == CQ_ORDER_REFERENCE ? w->dRank : nullptr, triOffset, S.tv0, S.tv1,
+                                                      S.tv2);
         w->launches++;
         if (n > 1) {
             if (sortedKeys) {
@@ -1300,6 +1302,15 @@ int attach_ref_order(cq_world *w) {
         CQ_CUDA(cudaMalloc((void **)&w->dEncOfRank, sizeof(uint32_t) * (size_t)(nS + nD)));
         CQ_CUDA(cudaMemcpy(w->dEncOfRank, encOfRank.data(), sizeof(uint32_t) * (size_t)(nS + nD), cudaMemcpyHostToDevice));
     }
+    // the ranks travel in tv2.w: rewrite the sorted SoA now that they are known (it was gathered with rank = index)
+    for (int s = 0; s < 2; s++) {
+        DeviceSet &S = w->set[s];
+        if (S.nTris <= 0) continue;
+        k_gather_sorted<<<cdiv(S.nTris, 256), 256, 0, st>>>(S.sortedTri, S.nTris, S.worldPos, S.indices, S.triLayer, w->dRank,
+                                                            s == 0 ? 0 : nS, S.tv0, S.tv1, S.tv2);
+        w->launches++;
+    }
+    CQ_CUDA(cudaStreamSynchronize(st));
     w->refBuildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return CQ_OK;
 }

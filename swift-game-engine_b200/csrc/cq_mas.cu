@@ -615,7 +615,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             st3(c.cNormal, q.bestN);
             st3(c.cTriNormal, q.bestTriN);
             c.cTri = q.bestTri;
-            c.cPart = q.bestPart;
+            c.cPart = world_part_of(W, q.bestTri);
         }
         // Dead-query elimination (exact): the fall probe only feeds state.distance (SYS:864), and that field is
         // overwritten by centerHit.toi as soon as the guard `centerHit.toi <= snapDistance` passes (SYS:868-880).
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     c.wait = W_NONE;
     c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT, STAGED, 16>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED, 16, false>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return mas_advance<COUNT, AGENTS>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);

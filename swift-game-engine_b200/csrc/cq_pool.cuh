@@ -33,9 +33,6 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
-#ifndef CQ_LOOKAHEAD
-#define CQ_LOOKAHEAD 0 /* 1: look-ahead prune of the conservative advancement (see pool_eval) */
-#endif
 #ifndef CQ_EARLY_PICKUP
 #define CQ_EARLY_PICKUP 0 /* 1: a second pickup right after the commit (round-2 A/B: hides the triangle fetch of a fresh pair) */
 #endif
@@ -47,7 +44,8 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 // most 32 owners x 2 sets = 64.  Above CQ_NS_WIDE only ONE lane pops per round (depth-first), which grows the stack by
 // at most 3 per level below the popped entry: CQ_NS_DFS_RESERVE covers 48 four-wide levels (a binary LBVH over 2^26
 // triangles with 30-bit keys + index tie-breaks is at most 56 levels = 28 wide ones).  Owners post new queries only
-// below CQ_NS_POST.  Every push is still bounds-checked: an overflow drops the entry and raises the world's status word.
+// below CQ_NS_POST.  Should a lone popper still not find room, the walk round drops the children and raises the world's
+// status word (one warp-uniform test per round, nothing per push).
 #define CQ_NS_DFS_RESERVE 144
 #define CQ_NS_WIDE (CQ_NSCAP - CQ_NS_DFS_RESERVE - 96)
 #define CQ_NS_POST (CQ_NS_WIDE - 64)
@@ -86,14 +84,13 @@ struct Job { // executor-side pair state (registers)
     float L, radius, hh, minAdvance;
     int maxIter;
     Tri T;
-    int gid, part;
+    int gid, rank; // global triangle index; visiting rank (tv2.w)
     float t, lastSafeT, lo, hi;
     int it, k;
 };
 
 struct Commit { // a finished pair's contribution, applied in the serialized commit step
     int kind; // 0 none, 1 cast contact, 2 overlap
-    int rank; // visiting rank of the pair's triangle (loaded by the executor, so the serialized step never waits on memory)
     float key;
     f3 pos, n, triN;
 };
@@ -109,14 +106,7 @@ struct WarpPool { // per-warp handles
     const int32_t *rank;     // visiting rank per global triangle index (reference order) or nullptr (rank = index)
     unsigned int *status;    // the world's status word (mapped host memory)
 };
-__device__ __forceinline__ bool pool_stack_room(const WarpPool &wp, uint32_t pos, uint32_t cnt) {
-#ifdef CQ_AB_NOGUARD
-    return true;
-#endif
-    if (pos + cnt <= (uint32_t)CQ_NSCAP) return true;
-    atomicOr(wp.status, 1u);
-    return false;
-}
+
 __device__ __forceinline__ int pool_rank(const int32_t *rank, int gid) { return rank ? __ldg(rank + gid) : gid; }
 #define CQ_STAGE 128 /* 32 leaf ranges x <= 4 triangles */
 #define CQ_POOL_WORDS (CQ_QCAP + 3 + CQ_STAGE) /* shared words per warp besides QShared */
@@ -163,11 +153,7 @@ __device__ __forceinline__ void pool_push_roots(const WorldView &W, const WarpPo
         }
         if (box_disjoint(mk3(h.lo[0], h.lo[1], h.lo[2]), mk3(h.hi[0], h.hi[1], h.hi[2]), qlo, qhi)) continue;
         bool leaf = h.rootRef < 0;
-        uint32_t pos = atomicAdd((uint32_t *)wp.ntop, 1u);
-        if (!pool_stack_room(wp, pos, 1u)) {
-            atomicSub((uint32_t *)wp.ntop, 1u);
-            continue;
-        }
+        uint32_t pos = atomicAdd((uint32_t *)wp.ntop, 1u); // (room for 64 roots is what CQ_NS_POST keeps free)
         wp.nstack[pos] = make_uint2(((uint32_t)lane << 2) | ((uint32_t)set << 1) | (leaf ? 1u : 0u),
                                     (uint32_t)(leaf ? ~h.rootRef : h.rootRef));
         pushed++;
@@ -238,6 +224,10 @@ template <bool COUNT, bool STAGED>
 __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPool &wp, int lane, Counters &ctr) {
     const uint32_t top = *wp.ntop;
     const uint32_t poppers = top > (uint32_t)CQ_NS_WIDE ? 1u : 32u; // nearly full: depth-first with one lane
+    // warp-uniform overflow guard: a lone popper replaces its entry by at most four.  Should even that not fit, the
+    // children are dropped and the world's status word is raised (the call then fails with CQ_ERR_CUDA).
+    const bool full = top + 3u > (uint32_t)CQ_NSCAP;
+    if (full && lane == 0) atomicOr(wp.status, 1u);
     const uint32_t k = min(top, poppers);
     uint2 e = make_uint2(0u, 0u);
     const bool have = (uint32_t)lane < k;
@@ -259,14 +249,9 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
         bool h0 = !box_disjoint(xyz(q0), xyz(q1), qlo, qhi), h1 = !box_disjoint(xyz(q2), xyz(q3), qlo, qhi);
         bool h2 = !box_disjoint(xyz(q4), xyz(q5), qlo, qhi), h3 = !box_disjoint(xyz(q6), xyz(q7), qlo, qhi);
         if (COUNT) ctr.nodes += 2 + (r2 != CQ_REF_EMPTY) + (r3 != CQ_REF_EMPTY);
-        int cnt = (h0 ? 1 : 0) + (h1 ? 1 : 0) + (h2 ? 1 : 0) + (h3 ? 1 : 0);
+        int cnt = full ? 0 : (h0 ? 1 : 0) + (h1 ? 1 : 0) + (h2 ? 1 : 0) + (h3 ? 1 : 0);
         if (cnt) {
             uint32_t pos = atomicAdd((uint32_t *)wp.ntop, (uint32_t)cnt);
-            if (!pool_stack_room(wp, pos, (uint32_t)cnt)) {
-                atomicSub((uint32_t *)wp.ntop, (uint32_t)cnt);
-                h0 = h1 = h2 = h3 = false;
-                cnt = 0;
-            }
             const uint32_t tag = e.x & ~1u;
             if (h0) wp.nstack[pos++] = make_uint2(tag | (r0 < 0 ? 1u : 0u), (uint32_t)(r0 < 0 ? ~r0 : r0));
             if (h1) wp.nstack[pos++] = make_uint2(tag | (r1 < 0 ? 1u : 0u), (uint32_t)(r1 < 0 ? ~r1 : r1));
@@ -369,7 +354,7 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
             float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
             job.T.v0 = xyz(a), job.T.v1 = xyz(b), job.T.v2 = xyz(c);
             job.gid = __float_as_int(b.w) + (set ? W.set[1].triOffset : 0);
-            job.part = __float_as_int(c.w);
+            job.rank = __float_as_int(c.w);
             job.t = 0.0f;
             job.lastSafeT = 0.0f;
             job.it = 0;
@@ -382,7 +367,11 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
 
 // one distance evaluation + the pair's state transition.  `retired` = the pair is finished (with or
 // without a contribution in `cm`).
-template <bool COUNT>
+// LOOKAHEAD: the look-ahead prune below.  Measured on one box (profiles/r2_lookahead_ab.txt): the batched sweep kernel gains
+// where candidates are many (C2: distance evaluations per sweep 5352 -> 4108, 32.8 -> 28.1 ms) and loses 1% on C4; the
+// move-and-slide kernel LOSES 3-5% on the hulls and terrain scenes (few candidates per query, the extra compares and the
+// longer loop body cost more than the 1.5% of evaluations they save), so only the query kernels instantiate it.
+template <bool COUNT, bool LOOKAHEAD>
 __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &cm, bool &retired, Counters &ctr) {
     const int ph = job.phase;
     const QShared &s = wp.qs[job.owner];
@@ -413,7 +402,6 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
             job.it++;
             // next trip: `for _ in 0..<maxIter { if t > maxDistance return nil ...`; prune: toi >= lastSafeT > bestT
             if (job.it >= job.maxIter || job.t > job.L || job.lastSafeT > bestT) retired = true;
-#if CQ_LOOKAHEAD
             // Look-ahead prune (exact-safe): this was a true conservative-advancement step (advance = dist - r, not the
             // minAdvance floor) and it lands beyond bestT by more than `margin`.  The capsule moves at unit speed, so
             // the distance at any t <= bestT is at least dist - (t - lastSafeT) > r + margin: if the NEXT evaluation
@@ -421,10 +409,9 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
             // (margin covers the float error of positions and distances), the refined toi ends beyond bestT and the
             // hit is rejected by `toi < bestT` (:1084); contacts found later have lastSafeT > bestT anyway.
             // margin: float error of positions and distances at this query's scale (1 mm + 8e-6 of the coordinates' size)
-            else if (dist - job.radius >= job.minAdvance &&
+            else if (LOOKAHEAD && dist - job.radius >= job.minAdvance &&
                      job.t > bestT + (1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f))
                 retired = true;
-#endif
         }
     } else if (ph == PH_BIS) { // refineTOI bisection, :1379-1392 (threshold is radius, not radius+eps)
         if (dist <= job.radius) job.hi = tc;
@@ -454,7 +441,6 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
         }
         if (ok) {
             cm.kind = 1;
-            cm.rank = pool_rank(wp.rank, job.gid);
             cm.key = tc;
             cm.pos = tp;
             cm.n = n;
@@ -465,7 +451,6 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
         if (dist < job.radius) {
             f3 triNormal = normalize(cross(job.T.v1 - job.T.v0, job.T.v2 - job.T.v0));
             cm.kind = 2;
-            cm.rank = pool_rank(wp.rank, job.gid);
             cm.key = job.radius - dist; // depth
             cm.n = dist < 1e-6f ? triNormal : normalize(sp - tp);
         }
@@ -548,22 +533,19 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                 int bestTri = s.rTri;
                 bool better = cm.key < bestT;
                 bool tie = bestTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited (:1084)
-                bool tieWin = tie && cm.rank < s.rRank;
-#ifndef CQ_AB_NOTIE
+                bool tieWin = tie && job.rank < s.rRank;
                 if (tie) s.mode |= CQ_QF_TIE;
                 if (better) s.mode &= ~CQ_QF_TIE;
-#endif
                 if (better || tieWin) {
                     s.rT = cm.key;
                     s.rTri = job.gid;
-                    s.rRank = cm.rank;
-                    s.rPart = job.part;
+                    s.rRank = job.rank;
                     store3s(s.rPos, cm.pos);
                     store3s(s.rN, cm.n);
                     store3s(s.rTriN, cm.triN);
                 }
             } else { // overlap: (depth desc, index asc) bookkeeping is the kernel's (top-2 or top-K)
-                ovl(s, cm.key, job.gid, cm.rank, job.enc, cm.n);
+                ovl(s, cm.key, job.gid, job.rank, job.enc, cm.n);
             }
         }
         __syncwarp();
@@ -582,7 +564,7 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
 // `ownersPerWarp` (1..32): how many lanes of each warp take the owner role.  Small batches of heavy units
 // use fewer owners per warp so that every owner still processes several units (dynamic fetch then balances
 // the warps against each other) while all 32 lanes keep executing pairs.
-template <bool COUNT, bool STAGED, int FE_IDLE, class Advance, class OvlCommit>
+template <bool COUNT, bool STAGED, int FE_IDLE, bool LOOKAHEAD, class Advance, class OvlCommit>
 __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp, int lane, int ownersPerWarp, Counters &ctr,
                                          Advance advance, OvlCommit ovl) {
     QShared &mine = wp.qs[lane];
@@ -617,7 +599,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         cm.kind = 0;
         bool retired = false;
 #if CQ_EVAL_REPS <= 1
-        if (job.phase != PH_NONE) pool_eval<COUNT>(job, wp, cm, retired, ctr);
+        if (job.phase != PH_NONE) pool_eval<COUNT, LOOKAHEAD>(job, wp, cm, retired, ctr);
 #else
         // Up to CQ_EVAL_REPS evaluations per trip while at least CQ_EVAL_KEEP lanes still hold a live pair: pickup, commit
         // and the exit vote are then paid once per several evaluations.  Exact: a finished pair keeps its contribution
@@ -627,7 +609,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
             const bool go = job.phase != PH_NONE && !retired;
             const uint32_t live = (uint32_t)__popc(__ballot_sync(0xffffffffu, go));
             if (live == 0u || (rep > 0 && live < (uint32_t)CQ_EVAL_KEEP)) break;
-            if (go) pool_eval<COUNT>(job, wp, cm, retired, ctr);
+            if (go) pool_eval<COUNT, LOOKAHEAD>(job, wp, cm, retired, ctr);
         }
 #endif
         pool_commit(wp, job, cm, retired, lane, ovl);

@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(Q_THREADS, CAST_MIN_BLOCKS) k_capsule_cast(Wor
 #if CQ_UNIT_BATCH > 1
     int batchNext = 0, batchEnd = 0; // [batchNext, batchEnd): positions in the processing order this owner has claimed
 #endif
-    pool_run<COUNT, STAGED, 8>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED, 8, true>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         if (cur >= 0) { // write the finished hit
             cq_cast_hit h;
             if (mine.rTri >= 0) {
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(Q_THREADS, 4) k_capsule_overlap_pool(WorldView
     int cur = -1;
     f3 curFrom = {0, 0, 0};
     float curR = 0.0f, curHH = 0.0f;
-    pool_run<COUNT, STAGED, 8>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED, 8, true>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         if (cur >= 0) { // emit the finished query
             const int stride = ALL ? maxHits : 1;
             for (int k = 0; k < stride; k++) {

@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_turns(WorldView W, const
     c.agent = -1;
     c.wait = SW_NONE;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT, true, 8>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, true, 8, false>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return sep_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);
@@ -524,7 +524,8 @@ __device__ __forceinline__ bool post_advance(PostCtx &c, const QResult &q, QShar
             S.grounded = 1;
             S.grounded_near = q.bestT <= smax(P.ground_snap_skin, P.skin_width) ? 1 : 0;
             bool flatten = false;
-            if (q.bestPart >= 0 && q.bestPart < W.nParts) flatten = __ldg(W.materials + q.bestPart).z != 0.0f;
+            const int hitPart = world_part_of(W, q.bestTri);
+            if (hitPart >= 0 && hitPart < W.nParts) flatten = __ldg(W.materials + hitPart).z != 0.0f;
             f3 gn = flatten ? mk3(0, 1, 0) : q.bestTriN;
             S.ground_normal[0] = gn.x, S.ground_normal[1] = gn.y, S.ground_normal[2] = gn.z;
             S.ground_triangle_index = q.bestTri;
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 4) k_sep_post(WorldView W, const 
     c.agent = -1;
     c.wait = PW_NONE;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT, true, 8>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, true, 8, false>(W, wp, lane, 32, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return post_advance<COUNT>(c, r, mine, wp, lane, W, A, workCounter, ct);

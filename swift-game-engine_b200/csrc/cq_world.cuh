@@ -4,7 +4,9 @@
 // HBM layout of one triangle set (static or dynamic, CollisionQuery.swift:710-711):
 //   tv0/tv1/tv2 : float4 SoA, one entry per triangle in MORTON (leaf) order
 //        tv0 = (v0.xyz, bits(layer))      tv1 = (v1.xyz, bits(triangle id in the filtered soup))
-//        tv2 = (v2.xyz, bits(part index -> material))
+//        tv2 = (v2.xyz, bits(visiting rank)) — the global position of the triangle in the order rule of the world:
+//              the reference's depth-first visiting rank (CQ_ORDER_REFERENCE) or simply its global index (canonical).
+//              Exact ties go to the smaller rank; it travels with the triangle so that no query ever loads it separately.
 //   nodes       : 64-byte LBVH node = the AABBs of BOTH children + their references, so one
 //                 node fetch (4 x LDG.128) tests two boxes:
 //        n0 = (lo0.xyz, bits(ref0))  n1 = (hi0.xyz, bits(ref1))  n2 = (lo1.xyz, -)  n3 = (hi1.xyz, -)
@@ -46,6 +48,7 @@ struct SetView {
     const Node *nodes;
     const Node4 *nodes4;
     const SetHeader *hdr;
+    const int32_t *triPart; // per triangle of the set (soup numbering): index of the part (entity) it came from -> material
     int triOffset; // added to triangle ids of this set (dynamic set: static count, CollisionQuery.swift:782)
     // Reference order only (cq_reftree.h): the reference's own median-split tree as 64-byte nodes (child 0 = left,
     // child 1 = right; a leaf reference ~((start << 2) | (count - 1)) names positions of refSlot), walked by the ray
@@ -103,12 +106,19 @@ __device__ __forceinline__ bool box_disjoint(f3 lo, f3 hi, f3 qlo, f3 qhi) { // 
     return hi.x < qlo.x || lo.x > qhi.x || hi.y < qlo.y || lo.y > qhi.y || hi.z < qlo.z || lo.z > qhi.z;
 }
 
-__device__ __forceinline__ Tri load_tri(const SetView &s, int i, uint32_t &layer, int &triId, int &part) {
+__device__ __forceinline__ Tri load_tri(const SetView &s, int i, uint32_t &layer, int &triId, int &rank) {
     float4 a = __ldg(s.tv0 + i), b = __ldg(s.tv1 + i), c = __ldg(s.tv2 + i);
     layer = __float_as_uint(a.w);
     triId = __float_as_int(b.w);
-    part = __float_as_int(c.w);
+    rank = __float_as_int(c.w);
     return Tri{xyz(a), xyz(b), xyz(c)};
+}
+
+// part (entity) of a global triangle index: TriangleMeshSet.materialForTriangle's lookup (CollisionQuery.swift:464-469)
+__device__ __forceinline__ int world_part_of(const WorldView &W, int gid) {
+    if (gid < 0) return -1;
+    const int off = W.set[1].triOffset;
+    return gid >= off ? __ldg(W.set[1].triPart + (gid - off)) : __ldg(W.set[0].triPart + gid);
 }
 
 #define CQ_MODE_ALL 0
