@@ -42,7 +42,8 @@ int check_status(cq_world *w, const char *what) {
     const unsigned int v = *(volatile unsigned int *)w->hStatus;
     if (v == 0) return CQ_OK;
     *(volatile unsigned int *)w->hStatus = 0;
-    set_error("%s: traversal stack overflow on the device (status 0x%x): results of the call are incomplete", what, v);
+    set_error("%s: device status 0x%x (%s%s): results of the call are incomplete", what, v,
+              (v & 1u) ? "traversal stack overflow " : "", (v & 2u) ? "sort look-back watchdog fired" : "");
     return CQ_ERR_CUDA;
 }
 
@@ -320,6 +321,7 @@ int cq_world_create_ex(const cq_mesh_part *parts, int32_t n_parts, const cq_worl
     if ((rc = check_cuda(cudaHostAlloc((void **)&w->hStatus, sizeof(unsigned int), cudaHostAllocMapped), "status word")) != CQ_OK)
         return fail(rc);
     *w->hStatus = 0;
+    cudaHostGetDevicePointer((void **)&w->view.status, w->hStatus, 0);
     if (n_parts) {
         cudaMemcpyAsync(w->dModels, models.data(), sizeof(float) * 16 * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
         cudaMemcpyAsync(w->dMaterials, materials.data(), sizeof(float4) * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);

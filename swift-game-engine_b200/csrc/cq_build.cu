@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint32_t *__restri
                                                         uint32_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut,
                                                         int n, int shift, const uint32_t *__restrict__ digitBase /* [256] */,
                                                         volatile uint32_t *status /* [nTiles][256] */, uint32_t *ticket,
-                                                        int *errorFlag) {
+                                                        int *errorFlag, unsigned int *worldStatus) {
     __shared__ uint32_t wh[RS_WARPS][256];
     __shared__ uint32_t sTile;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint32_t *__restri
             while ((s & (OS_FLAG_AGG | OS_FLAG_INC)) == 0u) {
                 if (++spins > (1u << 26)) { // watchdog: never hang the device
                     *errorFlag = 1;
+                    if (worldStatus) atomicOr(worldStatus, 2u); // asynchronous callers: reported at the next synchronising call
                     break;
                 }
                 s = *p;
@@ -707,7 +708,7 @@ static int radix_sort_pairs_onesweep(cq_world *w, uint32_t *keys, uint32_t *vals
     uint32_t *kin = keys, *vin = vals, *kout = keysTmp, *vout = valsTmp;
     for (int pass = 0; pass < 4; pass++) {
         k_os_pass<<<nTiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, pass * 8, hist + pass * 256,
-                                                 status + (size_t)pass * nTiles * 256, tickets + pass, err);
+                                                 status + (size_t)pass * nTiles * 256, tickets + pass, err, w->view.status);
         w->launches++;
         std::swap(kin, kout);
         std::swap(vin, vout);

@@ -490,7 +490,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
     case W_DEPEN: { // DepenetrationResolver.resolve loop body after the overlap query (SYS:756-799)
         if (W.rank) { // more than maxHits triangles overlap: the reference only ever saw the first eight it visited (CQ:1272-1274)
             const int *ov = ovl_words(s);
-            if (ov[OVL_PASS] == 0 && ov[OVL_TOTAL] > CQ_MAX_OVERLAP_HITS) {
+            if (ov[OVL_TOTAL] > CQ_MAX_OVERLAP_HITS) { // (-1 after the second pass)
                 pool_post_first_hits(W.encOfRank, wp.ring, wp.tail, lane, s);
                 return true; // still waiting in W_DEPEN, now for the eight pairs
             }

@@ -33,6 +33,9 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
+#ifndef CQ_PLANE_CULL
+#define CQ_PLANE_CULL 0 /* 1: plane-separation retire after a candidate's first evaluation (see pool_eval) */
+#endif
 #ifndef CQ_EARLY_PICKUP
 #define CQ_EARLY_PICKUP 0 /* 1: a second pickup right after the commit (round-2 A/B: hides the triangle fetch of a fresh pair) */
 #endif
@@ -65,11 +68,16 @@ struct QShared { // one per owner lane, shared memory: what executors need + the
     int rRank, rRank1; // visiting rank of rTri (and, overlap queries, of the second deepest rPart): exact ties go to the smaller
     float rPos[3], rN[3], rTriN[3];
     int pending; // stack entries + pairs pushed for this query and not yet consumed; 0 = query complete
+#ifdef CQ_AB_PAD39
+    int _padOdd; // 39 words: an odd stride spreads the 32 owners' records over all shared-memory banks
+#endif
 };
 
 #define CQ_QF_TIE 0x100 /* another accepted candidate had exactly the best key: the answer depended on the order rule */
 __device__ __forceinline__ int *ovl_words(QShared &s) { return reinterpret_cast<int *>(s.dir); }
-enum { OVL_TOTAL = 8, OVL_PASS = 9 }; // ovl_words: [0..7] smallest ranks seen, [8] overlapping triangles, [9] pass (0 / 1)
+// ovl_words: [0..7] the eight smallest ranks seen so far (unsorted), [8] overlapping triangles counted (-1 = second pass: nothing
+// is counted or kept), [9] the largest of the eight kept ranks (valid once eight are kept)
+enum { OVL_TOTAL = 8, OVL_MAXRANK = 9 };
 
 struct QResult { // what owner logic reads back
     float bestT;
@@ -205,7 +213,6 @@ __device__ __forceinline__ void pool_post_overlap(const WorldView &W, const Warp
     s.radius = radius;
     s.hh = hh;
     ovl_words(s)[OVL_TOTAL] = 0;
-    ovl_words(s)[OVL_PASS] = 0;
     s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));         // deepest
     s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0)); // second deepest
     f3 qlo, qhi;
@@ -402,6 +409,26 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
             job.it++;
             // next trip: `for _ in 0..<maxIter { if t > maxDistance return nil ...`; prune: toi >= lastSafeT > bestT
             if (job.it >= job.maxIter || job.t > job.L || job.lastSafeT > bestT) retired = true;
+#if CQ_PLANE_CULL
+            // Plane-separation retire (exact-safe), once per candidate after its first evaluation: the triangle lies in its
+            // plane, so the segment-triangle distance is at least the distance of the capsule's axis to that plane.  The
+            // endpoints' signed plane distances are linear in t; if both endpoints stay on one side over the rest of the
+            // sweep that can still matter, [0, min(L, bestT + margin)], by more than r + margin, no evaluation there can
+            // report contact (margin covers the float error of positions and distances, as in the look-ahead prune) and
+            // contacts after bestT are rejected by `toi < bestT` anyway: the reference's loop would only creep along
+            // (e.g. a walker over the ground plane: L / max(skin, minAdvance) evaluations that all say "no contact").
+            else if (job.it == 1) {
+                const f3 n = cross(job.T.v1 - job.T.v0, job.T.v2 - job.T.v0);
+                const f3 c0 = job.from - job.T.v0;
+                const float margin = 1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f;
+                const float tEnd = smin(job.L, bestT + margin);
+                const float sc = dot(n, c0), sh = n.y * job.hh, rate = dot(n, job.dir) * tEnd;
+                const float a0 = sc + sh, b0 = sc - sh, a1 = a0 + rate, b1 = b0 + rate;
+                const float lo = smin(smin(a0, b0), smin(a1, b1)), hi = smax(smax(a0, b0), smax(a1, b1));
+                const float need = (job.radius + margin) * (job.radius + margin) * dot(n, n);
+                if ((lo > 0.0f && lo * lo > need) || (hi < 0.0f && hi * hi > need)) retired = true;
+            }
+#endif
             // Look-ahead prune (exact-safe): this was a true conservative-advancement step (advance = dist - r, not the
             // minAdvance floor) and it lands beyond bestT by more than `margin`.  The capsule moves at unit speed, so
             // the distance at any t <= bestT is at least dist - (t - lastSafeT) > r + margin: if the NEXT evaluation
@@ -463,20 +490,37 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
 // them by depth (stably) and uses one or two (Systems.swift:751-767).  The first pass keeps the two deepest of ALL
 // overlapping triangles (ties: smaller rank), counts them and remembers the eight smallest ranks; only when more than
 // eight triangles overlap does the owner run a second pass over exactly those eight (pool_post_first_hits).
-// Out of line on purpose: overlap commits are rare (a character that starts a step inside geometry) while the commit step
-// sits in the steady-state loop whose code size decides the small-scene throughput — inlined, this
-// bookkeeping made the loop 4 KB longer and the hulls step 12% slower.
-static __device__ __noinline__ void overlap_top2_commit(QShared &s, float depth, int gid, int rk, f3 n, bool byRank) {
+// Out of line on purpose: overlap commits are rare in the scenes the kernel is tuned on (a character that starts a step
+// inside geometry) while the commit step sits in the steady-state loop whose code size decides the small-scene throughput
+//  — inlined, this bookkeeping made the loop 4 KB longer and the hulls step 12% slower.
+#ifdef CQ_AB_INLINE_OVL
+#define CQ_OVL_INLINE __forceinline__
+#else
+#define CQ_OVL_INLINE __noinline__
+#endif
+static __device__ CQ_OVL_INLINE void overlap_top2_commit(QShared &s, float depth, int gid, int rk, f3 n, bool byRank) {
     if (byRank) {
         int *ov = ovl_words(s);
-        if (ov[OVL_PASS] == 0) { // first pass: count, and keep the eight smallest ranks seen (sorted insert)
-            const int total = ov[OVL_TOTAL];
-            int pos = total < CQ_MAX_OVERLAP_HITS ? total : CQ_MAX_OVERLAP_HITS;
-            while (pos > 0 && ov[pos - 1] > rk) pos--;
-            if (pos < CQ_MAX_OVERLAP_HITS) {
+        const int total = ov[OVL_TOTAL];
+        if (total >= 0) { // first pass: count, and keep the eight smallest ranks seen (unsorted list + its maximum)
+            if (total < CQ_MAX_OVERLAP_HITS) {
+                ov[total] = rk;
+                if (total == CQ_MAX_OVERLAP_HITS - 1) {
+                    int mx = ov[0];
 #pragma unroll 1
-                for (int k = total < CQ_MAX_OVERLAP_HITS - 1 ? total : CQ_MAX_OVERLAP_HITS - 1; k > pos; k--) ov[k] = ov[k - 1];
-                ov[pos] = rk;
+                    for (int k = 1; k < CQ_MAX_OVERLAP_HITS; k++) mx = max(mx, ov[k]);
+                    ov[OVL_MAXRANK] = mx;
+                }
+            } else if (rk < ov[OVL_MAXRANK]) { // replaces the largest kept rank
+                const int out = ov[OVL_MAXRANK];
+                int mx = rk;
+#pragma unroll 1
+                for (int k = 0; k < CQ_MAX_OVERLAP_HITS; k++) {
+                    int v = ov[k];
+                    if (v == out) ov[k] = v = rk;
+                    mx = max(mx, v);
+                }
+                ov[OVL_MAXRANK] = mx;
             }
             ov[OVL_TOTAL] = total + 1;
         }
@@ -510,8 +554,7 @@ static __device__ __noinline__ void pool_post_first_hits(const uint32_t *__restr
     const uint32_t pos = atomicAdd((uint32_t *)tail, (uint32_t)CQ_MAX_OVERLAP_HITS);
 #pragma unroll 1
     for (int k = 0; k < CQ_MAX_OVERLAP_HITS; k++) ring[(pos + k) % CQ_QCAP] = ((uint32_t)lane << 27) | __ldg(encOfRank + ov[k]);
-    ov[OVL_TOTAL] = 0;
-    ov[OVL_PASS] = 1;
+    ov[OVL_TOTAL] = -1; // second pass
     s.rT = 0.0f, s.rTri = -1, store3s(s.rN, mk3(0, 0, 0));
     s.rPos[0] = 0.0f, s.rPart = -1, store3s(s.rTriN, mk3(0, 0, 0));
     s.pending = CQ_MAX_OVERLAP_HITS;
@@ -534,8 +577,10 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                 bool better = cm.key < bestT;
                 bool tie = bestTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited (:1084)
                 bool tieWin = tie && job.rank < s.rRank;
+#ifndef CQ_AB_NOTIE
                 if (tie) s.mode |= CQ_QF_TIE;
                 if (better) s.mode &= ~CQ_QF_TIE;
+#endif
                 if (better || tieWin) {
                     s.rT = cm.key;
                     s.rTri = job.gid;

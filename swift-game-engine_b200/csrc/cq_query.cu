@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast_ref(WorldView W, const cq
 #ifndef RAY_REFILL_MIN
 #define RAY_REFILL_MIN 8
 #endif
-#ifndef RAY_NODE_MIN
-#define RAY_NODE_MIN 12
+#ifndef RAY_NODE_MIN /* measured on C5, one box: reference order 12 -> 3.18 ms, 16 -> 3.00, 20 -> 2.94, 24 -> 3.00; canonical order */
+#define RAY_NODE_MIN (REF ? 20 : 12) /* 12 -> 2.01 ms, 16 -> 2.01, 20 -> 2.05 (the reference's binary tree takes more node steps per ray) */
 #endif
 #ifndef RAY_TRI_MIN
 #define RAY_TRI_MIN 8

@@ -10,23 +10,44 @@ import simd
 
 public final class CollisionQuery {
     private var handle: OpaquePointer?
+    /// Set membership as the library sees it (cq_mesh_part.is_dynamic): updateStaticTransforms / updateDynamicTransforms
+    /// only move entities of their own set, like TriangleMeshSet.updateTransforms, which skips entities without a slice
+    /// in the addressed set (CollisionQuery.swift:427).
+    private var dynamicIDs: Set<UInt32> = []
+    private var knownIDs: Set<UInt32> = []
+    /// Text of the last library error (cq_last_error()); nil when the last call succeeded.  The reference reports failure
+    /// through Optionals only, so every query keeps answering nil on error and this is where the reason can be read.
+    public private(set) var lastError: String?
 
-    public init(world: World, activeEntityIDs: Set<UInt32>? = nil) {
-        var keepAlive: [Any] = []
-        var parts = CollisionQuery.makeParts(world: world, activeEntityIDs: activeEntityIDs, keepAlive: &keepAlive)
+    /// `referenceOrder`: exact ties and capsuleOverlapAll overflow resolved in the reference's own visiting order
+    /// (CQ_ORDER_REFERENCE, the library's default); false selects the tree-independent rule (include/cq.h).
+    public init(world: World, activeEntityIDs: Set<UInt32>? = nil, referenceOrder: Bool = true) {
+        let built = CollisionQuery.makeParts(world: world, activeEntityIDs: activeEntityIDs)
+        var parts = built.parts
+        // the library copies everything it needs during cq_world_create: point the parts at the arrays only for the call
+        var options = cq_world_options()
+        cq_world_options_default(&options)
+        options.order = referenceOrder ? Int32(CQ_ORDER_REFERENCE) : Int32(CQ_ORDER_CANONICAL)
         var h: OpaquePointer?
-        _ = cq_world_create(&parts, Int32(parts.count), &h)   // on failure `handle` stays nil: every query answers nil
-        handle = h
+        let rc: Int32 = CollisionQuery.withArrays(built.positions, built.indices, &parts) {
+            cq_world_create_ex(&parts, Int32(parts.count), &options, &h)
+        }
+        handle = rc == CQ_OK ? h : nil // on failure every query answers nil (no CPU fallback exists)
+        lastError = rc == CQ_OK ? nil : String(cString: cq_last_error())
+        for p in built.parts {
+            knownIDs.insert(p.entity_id)
+            if p.is_dynamic != 0 { dynamicIDs.insert(p.entity_id) }
+        }
     }
 
     deinit { cq_world_destroy(handle) }
 
     public func updateStaticTransforms(world: World, entities: [Entity], activeEntityIDs: Set<UInt32>? = nil) {
-        update(world: world, entities: entities, activeEntityIDs: activeEntityIDs)
+        update(world: world, entities: entities.filter { !dynamicIDs.contains($0.id) }, activeEntityIDs: activeEntityIDs)
     }
 
     public func updateDynamicTransforms(world: World, entities: [Entity], activeEntityIDs: Set<UInt32>? = nil) {
-        update(world: world, entities: entities, activeEntityIDs: activeEntityIDs)
+        update(world: world, entities: entities.filter { dynamicIDs.contains($0.id) }, activeEntityIDs: activeEntityIDs)
     }
 
     public func raycast(origin: SIMD3<Float>, direction: SIMD3<Float>, maxDistance: Float,
@@ -143,35 +164,40 @@ public final class CollisionQuery {
         var ids: [UInt32] = []
         var models: [Float] = []
         for e in filtered {
-            guard let t = tStore[e] else { continue }
+            guard let t = tStore[e], knownIDs.contains(e.id) else { continue } // `guard let slice = slices[e] else { continue }`
             ids.append(e.id)
             let m = t.modelMatrix
             for c in [m.columns.0, m.columns.1, m.columns.2, m.columns.3] { models += [c.x, c.y, c.z, c.w] }
         }
-        _ = cq_world_update_transforms(handle, ids, models, Int32(ids.count))
+        if ids.isEmpty { return }
+        let rc = cq_world_update_transforms(handle, ids, models, Int32(ids.count))
+        lastError = rc == CQ_OK ? nil : String(cString: cq_last_error())
     }
 
     /// Entities with Transform + StaticMesh (collides), ascending id (the reference iterates a Dictionary, i.e. in
     /// per-process random order — World.swift:99-118; the library fixes the order so triangle numbering is stable).
-    private static func makeParts(world: World, activeEntityIDs: Set<UInt32>?, keepAlive: inout [Any]) -> [cq_mesh_part] {
+    /// Geometry is returned as plain Swift arrays; `withArrays` lends their storage to the C structs for one call.
+    /// StaticMeshComponent.triangleMaterials (per-triangle materials, CollisionQuery.swift:364-369) cannot be expressed
+    /// through cq_mesh_part (one material per part; no scene of the reference sets them): asserted nil here.
+    private static func makeParts(world: World, activeEntityIDs: Set<UInt32>?)
+        -> (parts: [cq_mesh_part], positions: [[Float]], indices: [[UInt32]]) {
         let tStore = world.store(TransformComponent.self)
         let mStore = world.store(StaticMeshComponent.self)
         let pStore = world.store(PhysicsBodyComponent.self)
         var parts: [cq_mesh_part] = []
+        var positions: [[Float]] = []
+        var indices: [[UInt32]] = []
         let entities = world.query(TransformComponent.self, StaticMeshComponent.self).sorted { $0.id < $1.id }
         for e in entities {
             if let active = activeEntityIDs, !active.contains(e.id) { continue }
             guard let t = tStore[e], let m = mStore[e], m.collides else { continue }
+            assert(m.triangleMaterials == nil, "per-triangle materials are not supported by cq_mesh_part")
             let mesh = m.collisionMesh ?? m.mesh
-            let pos = UnsafeMutablePointer<Float>.allocate(capacity: mesh.streams.positions.count * 3)
-            for (i, p) in mesh.streams.positions.enumerated() { pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z }
+            var pos: [Float] = []
+            pos.reserveCapacity(mesh.streams.positions.count * 3)
+            for p in mesh.streams.positions { pos += [p.x, p.y, p.z] }
             let idx32: [UInt32] = mesh.indices16?.map { UInt32($0) } ?? mesh.indices32 ?? []
-            let idx = UnsafeMutablePointer<UInt32>.allocate(capacity: max(idx32.count, 1))
-            idx.initialize(from: idx32, count: idx32.count)
-            keepAlive.append(pos); keepAlive.append(idx)
             var part = cq_mesh_part()
-            part.positions_xyz = UnsafePointer(pos)
-            part.indices = UnsafePointer(idx)
             part.n_verts = Int32(mesh.streams.positions.count)
             part.n_indices = Int32(idx32.count)
             let mm = t.modelMatrix
@@ -187,7 +213,25 @@ public final class CollisionQuery {
             part.is_dynamic = (pStore[e].map { $0.bodyType != .static } ?? false) ? 1 : 0
             part.entity_id = e.id
             parts.append(part)
+            positions.append(pos)
+            indices.append(idx32)
         }
-        return parts
+        return (parts, positions, indices)
+    }
+
+    /// Runs `body` with every part pointing at its arrays' storage (valid only inside the call; nothing is leaked).
+    private static func withArrays<R>(_ positions: [[Float]], _ indices: [[UInt32]], _ parts: inout [cq_mesh_part],
+                                      _ body: () -> R) -> R {
+        func go(_ k: Int) -> R {
+            if k == parts.count { return body() }
+            return positions[k].withUnsafeBufferPointer { pp in
+                indices[k].withUnsafeBufferPointer { ip in
+                    parts[k].positions_xyz = pp.baseAddress
+                    parts[k].indices = ip.baseAddress
+                    return go(k + 1)
+                }
+            }
+        }
+        return go(0)
     }
 }

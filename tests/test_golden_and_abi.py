@@ -221,8 +221,8 @@ def test_fbx_regenerator_reproduces_shipped_asset_and_fixtures(cq, scenes, tmp_p
     """SURVEY.md §8f-1 (tools/fbx_to_static_mesh.py, build container only — it reads /root/reference): the Blender-free FBX
     reader reproduces the one asset whose JSON ships (ornate_mirror: 14,246 triangles, local AABB, transform, and — with
     Blender's quad-flip rule — more than 99.5% of the triangles as the same vertex-position triples), the committed Semla /
-    17-Cheese fixtures are what `--fixtures` generates (shorter-diagonal quads, round-1 files), and the JSON the tool writes
-    goes through the product's own loader unchanged."""
+    17-Cheese fixtures are what `--fixtures` generates under that same Blender rule (Semla's FBX is all triangles, so only
+    17-Cheese's quads depend on it), and the JSON the tool writes goes through the product's own loader unchanged."""
     if not os.path.exists("/root/reference/ExternalResources/17-Cheese.fbx"):
         pytest.skip("reference tree not present on this box")
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -242,7 +242,7 @@ def test_fbx_regenerator_reproduces_shipped_asset_and_fixtures(cq, scenes, tmp_p
     a, b = triangle_keys(mine_pos, mine["indices"]), triangle_keys(ref["mesh"]["positions"], ref["mesh"]["indices"])
     assert len(a & b) >= 0.995 * len(b), (len(a & b), len(a), len(b))  # the rest: n-gons, which Blender poly-fills
     for name, rel in (("semla", "semla/source/Semla.fbx"), ("cheese", "17-Cheese.fbx")):
-        part = fbx.load_geometry(os.path.join(fbx.REF, rel), "shorter")
+        part = fbx.load_geometry(os.path.join(fbx.REF, rel), "blender")
         dst = tmp_path / (name + ".npz")
         fbx.save_fixture(part, str(dst))
         new, old = np.load(dst), np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))

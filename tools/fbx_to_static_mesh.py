@@ -20,7 +20,7 @@ Regenerated assets are stand-ins, not the original blobs: vertex order (hence tr
 from what Blender's exporter would write because it re-indexes on (position, normal, uv).
 
   python tools/fbx_to_static_mesh.py <in.fbx> <out.static.json>            # the reference's schema
-  python tools/fbx_to_static_mesh.py --fixtures [shorter|blender]           # tests/golden/{semla,cheese}.npz (default: the round-1 rule)
+  python tools/fbx_to_static_mesh.py --fixtures [blender|shorter]           # tests/golden/{semla,cheese}.npz (default: Blender's quad rule)
 """
 import json
 import os
@@ -328,11 +328,9 @@ def validate_against_mirror():
 
 def main(argv):
     if argv[:1] == ["--fixtures"]:
-        rule = argv[1] if len(argv) > 1 else "shorter"  # `--fixtures blender` regenerates them under Blender's quad rule
-        assert rule in ("shorter", "blender")
+        rule = argv[1] if len(argv) > 1 else "blender"  # the committed fixtures follow Blender's quad rule (round 2);
+        assert rule in ("shorter", "blender")           # `--fixtures shorter` reproduces the round-1 files
         assert validate_against_mirror(), "FBX reader does not reproduce the shipped ornate_mirror asset"
-        # round-1 fixtures: shorter-diagonal quads (see triangulate); regenerate with the Blender rule only together with a
-        # GPU run of the C2 / C5 tests, whose triangle counts and hit-rate thresholds are tied to these files
         save_fixture(load_geometry(os.path.join(REF, "semla/source/Semla.fbx"), rule), os.path.join(ROOT, "tests/golden/semla.npz"))
         save_fixture(load_geometry(os.path.join(REF, "17-Cheese.fbx"), rule), os.path.join(ROOT, "tests/golden/cheese.npz"))
         return 0

@@ -24,6 +24,11 @@ run c2 --only c2 --steps 3 --warmup 3
 run c2canon --only c2 --steps 3 --warmup 3 --order canonical
 old c4 --workload c4 --steps 5 --warmup 3
 run c4 --only c4 --steps 5 --warmup 3
+D=swift-game-engine_b200/csrc
+for L in libcq $(cd $D && ls libcq_ray_*.so | sed 's/\.so$//'); do
+  CQ_LIB=$D/$L.so timeout 200 python bench.py --only c5 --steps 5 --warmup 3 --no-cpu-baseline > $O/r2c5_ab_c5_$L.json 2> $O/r2c5_ab_c5_$L.err
+  CQ_LIB=$D/$L.so timeout 200 python bench.py --only c5 --steps 5 --warmup 3 --no-cpu-baseline --order canonical > $O/r2c5_ab_c5canon_$L.json 2> $O/r2c5_ab_c5canon_$L.err
+done
 python - <<'PY'
 import glob, json
 for f in sorted(glob.glob("gpurun_out/r2c5_ab_*.json")):
