@@ -33,9 +33,6 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
-#ifndef CQ_PLANE_CULL
-#define CQ_PLANE_CULL 0 /* 1: plane-separation retire after a candidate's first evaluation (see pool_eval) */
-#endif
 #ifndef CQ_EARLY_PICKUP
 #define CQ_EARLY_PICKUP 0 /* 1: a second pickup right after the commit (round-2 A/B: hides the triangle fetch of a fresh pair) */
 #endif
@@ -68,9 +65,6 @@ struct QShared { // one per owner lane, shared memory: what executors need + the
     int rRank, rRank1; // visiting rank of rTri (and, overlap queries, of the second deepest rPart): exact ties go to the smaller
     float rPos[3], rN[3], rTriN[3];
     int pending; // stack entries + pairs pushed for this query and not yet consumed; 0 = query complete
-#ifdef CQ_AB_PAD39
-    int _padOdd; // 39 words: an odd stride spreads the 32 owners' records over all shared-memory banks
-#endif
 };
 
 #define CQ_QF_TIE 0x100 /* another accepted candidate had exactly the best key: the answer depended on the order rule */
@@ -409,26 +403,6 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
             job.it++;
             // next trip: `for _ in 0..<maxIter { if t > maxDistance return nil ...`; prune: toi >= lastSafeT > bestT
             if (job.it >= job.maxIter || job.t > job.L || job.lastSafeT > bestT) retired = true;
-#if CQ_PLANE_CULL
-            // Plane-separation retire (exact-safe), once per candidate after its first evaluation: the triangle lies in its
-            // plane, so the segment-triangle distance is at least the distance of the capsule's axis to that plane.  The
-            // endpoints' signed plane distances are linear in t; if both endpoints stay on one side over the rest of the
-            // sweep that can still matter, [0, min(L, bestT + margin)], by more than r + margin, no evaluation there can
-            // report contact (margin covers the float error of positions and distances, as in the look-ahead prune) and
-            // contacts after bestT are rejected by `toi < bestT` anyway: the reference's loop would only creep along
-            // (e.g. a walker over the ground plane: L / max(skin, minAdvance) evaluations that all say "no contact").
-            else if (job.it == 1) {
-                const f3 n = cross(job.T.v1 - job.T.v0, job.T.v2 - job.T.v0);
-                const f3 c0 = job.from - job.T.v0;
-                const float margin = 1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f;
-                const float tEnd = smin(job.L, bestT + margin);
-                const float sc = dot(n, c0), sh = n.y * job.hh, rate = dot(n, job.dir) * tEnd;
-                const float a0 = sc + sh, b0 = sc - sh, a1 = a0 + rate, b1 = b0 + rate;
-                const float lo = smin(smin(a0, b0), smin(a1, b1)), hi = smax(smax(a0, b0), smax(a1, b1));
-                const float need = (job.radius + margin) * (job.radius + margin) * dot(n, n);
-                if ((lo > 0.0f && lo * lo > need) || (hi < 0.0f && hi * hi > need)) retired = true;
-            }
-#endif
             // Look-ahead prune (exact-safe): this was a true conservative-advancement step (advance = dist - r, not the
             // minAdvance floor) and it lands beyond bestT by more than `margin`.  The capsule moves at unit speed, so
             // the distance at any t <= bestT is at least dist - (t - lastSafeT) > r + margin: if the NEXT evaluation
@@ -493,12 +467,7 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
 // Out of line on purpose: overlap commits are rare in the scenes the kernel is tuned on (a character that starts a step
 // inside geometry) while the commit step sits in the steady-state loop whose code size decides the small-scene throughput
 //  — inlined, this bookkeeping made the loop 4 KB longer and the hulls step 12% slower.
-#ifdef CQ_AB_INLINE_OVL
-#define CQ_OVL_INLINE __forceinline__
-#else
-#define CQ_OVL_INLINE __noinline__
-#endif
-static __device__ CQ_OVL_INLINE void overlap_top2_commit(QShared &s, float depth, int gid, int rk, f3 n, bool byRank) {
+static __device__ __noinline__ void overlap_top2_commit(QShared &s, float depth, int gid, int rk, f3 n, bool byRank) {
     if (byRank) {
         int *ov = ovl_words(s);
         const int total = ov[OVL_TOTAL];
@@ -577,10 +546,8 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                 bool better = cm.key < bestT;
                 bool tie = bestTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited (:1084)
                 bool tieWin = tie && job.rank < s.rRank;
-#ifndef CQ_AB_NOTIE
                 if (tie) s.mode |= CQ_QF_TIE;
                 if (better) s.mode &= ~CQ_QF_TIE;
-#endif
                 if (better || tieWin) {
                     s.rT = cm.key;
                     s.rTri = job.gid;
@@ -632,7 +599,18 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         // 16; terrain +4%; C4 +1.6% with 8 but -2% with 16; the candidate-heavy render mesh loses 3% either way).
         const uint32_t idleNow = (uint32_t)__popc(__ballot_sync(0xffffffffu, job.phase == PH_NONE));
         if (*wp.tail == *wp.head && idleNow >= (uint32_t)FE_IDLE) {
-            if (alive && *(volatile int *)&mine.pending == 0 && *wp.ntop <= (uint32_t)CQ_NS_POST) alive = advance(mine, ctr);
+            // The owners' logic runs only when enough owners are ready (or nothing at all is left to execute), so that the
+            // divergent front end serves many owners per pass.  Measured on one box (profiles/r2_ab_same_box.txt, call 7):
+            // with 24 of 32 the render-mesh step (heavy queries, owners rarely ready together) gains 23% (21.98 -> 17.88 ms),
+            // the terrain step is unchanged, the hulls step loses 0.8% — hence only the staged-walk variant (worlds of
+            // >= 4096 triangles) of the move-and-slide kernel waits; the plain query kernels own few units per warp.
+            const bool ready = alive && *(volatile int *)&mine.pending == 0 && *wp.ntop <= (uint32_t)CQ_NS_POST;
+            bool go = ready;
+            if (FE_IDLE >= 16 && STAGED) { // (compile-time)
+                const uint32_t nReady = (uint32_t)__popc(__ballot_sync(0xffffffffu, ready));
+                go = ready && (nReady >= 24u || (idleNow == 32u && *wp.ntop == 0u));
+            }
+            if (go) alive = advance(mine, ctr);
             __syncwarp();
             // cooperative walk: rounds until the ring holds ~3 trips of work (or the stack is empty)
             while (*wp.ntop != 0u && *wp.tail - *wp.head < 96u && *wp.tail - *wp.head + 128u <= (uint32_t)CQ_QCAP)
