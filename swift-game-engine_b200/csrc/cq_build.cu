@@ -571,10 +571,14 @@ __global__ void k_depth_parity(int nInternal, const int32_t *__restrict__ parent
 }
 
 // collapse: wide node i = binary node i (even depth) with its internal children replaced by THEIR children
+__device__ __forceinline__ void collapse4_node(int i, const Node *nodes, Node4 *nodes4);
 __global__ void k_collapse4(int nInternal, const Node *__restrict__ nodes, const uint8_t *__restrict__ parity,
                             Node4 *__restrict__ nodes4) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nInternal || parity[i]) return;
+    collapse4_node(i, nodes, nodes4);
+}
+__device__ __forceinline__ void collapse4_node(int i, const Node *nodes, Node4 *nodes4) {
     Node nb = nodes[i];
     float4 lo[4], hi[4];
     int ref[4];
@@ -633,6 +637,126 @@ __global__ void k_header(int n, const float4 *__restrict__ boxLo, const float4 *
         h.hi[0] = hi.x, h.hi[1] = hi.y, h.hi[2] = hi.z;
     }
     *hdr = h;
+}
+
+// ---------------------------------------------------------------- dirty-subtree refit (BVH.refit, CollisionQuery.swift:528-575)
+// The reference recomputes the leaves of the updated triangles and then only their ancestors, deepest first.  Here: one
+// thread per updated triangle rewrites its slot of the sorted SoA and its leaf box and MARKS its ancestors — `expect[p]`
+// counts the dirty children of p (1 or 2); the thread that finds p already marked stops, so every dirty edge is counted
+// once.  A second launch climbs: the last of a node's expected arrivals recomputes it from its children's boxes (the
+// clean child's box is still valid), re-collapses the 4-wide node when the depth is even, resets the counters and goes on.
+// Same min / max arithmetic as the full fit, so the boxes are identical; cost O(updated triangles x depth).
+__global__ void k_invert_sorted(const uint32_t *__restrict__ sortedTri, int n, uint32_t *__restrict__ slotOfTri) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) slotOfTri[sortedTri[s]] = (uint32_t)s;
+}
+
+__global__ void k_refit_mark(int triLo, int triHi, const uint32_t *__restrict__ slotOfTri, int n,
+                             const float4 *__restrict__ world, const uint32_t *__restrict__ idx, float4 *tv0, float4 *tv1,
+                             float4 *tv2, const int32_t *__restrict__ parent, float4 *boxLo, float4 *boxHi, int32_t *expect) {
+    const int t = triLo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triHi) return;
+    const int slot = (int)slotOfTri[t];
+    const float4 a = world[idx[3 * t]], b = world[idx[3 * t + 1]], c = world[idx[3 * t + 2]];
+    float4 o0 = tv0[slot], o1 = tv1[slot], o2 = tv2[slot]; // the w words (layer, triangle id, rank) stay
+    o0.x = a.x, o0.y = a.y, o0.z = a.z, o1.x = b.x, o1.y = b.y, o1.z = b.z, o2.x = c.x, o2.y = c.y, o2.z = c.z;
+    tv0[slot] = o0, tv1[slot] = o1, tv2[slot] = o2;
+    const f3 lo = vmin(xyz(a), vmin(xyz(b), xyz(c))), hi = vmax(xyz(a), vmax(xyz(b), xyz(c)));
+    int node = (n - 1) + slot;
+    boxLo[node] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    boxHi[node] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    if (n == 1) return;
+    for (int p = parent[node]; p >= 0; p = parent[p])
+        if (atomicAdd(&expect[p], 1) != 0) break; // p was already marked through its other child
+}
+
+__global__ void k_refit_climb(int triLo, int triHi, const uint32_t *__restrict__ slotOfTri, int n, Node *nodes,
+                              const int32_t *__restrict__ parent, float4 *boxLo, float4 *boxHi, int32_t *visit, int32_t *expect,
+                              const uint8_t *__restrict__ parity, Node4 *nodes4) {
+    const int t = triLo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triHi || n == 1) return;
+    __threadfence();
+    int p = parent[(n - 1) + (int)slotOfTri[t]];
+    while (p >= 0) {
+        if (atomicAdd(&visit[p], 1) + 1 < *(volatile int32_t *)&expect[p]) return; // a dirty sibling subtree is not done yet
+        __threadfence();
+        Node nd = nodes[p];
+        const int lb = __float_as_int(nd.n2.w), rb = __float_as_int(nd.n3.w);
+        const float4 l0 = __ldcg(boxLo + lb), h0 = __ldcg(boxHi + lb), l1 = __ldcg(boxLo + rb), h1 = __ldcg(boxHi + rb);
+        nd.n0 = make_float4(l0.x, l0.y, l0.z, nd.n0.w);
+        nd.n1 = make_float4(h0.x, h0.y, h0.z, nd.n1.w);
+        nd.n2 = make_float4(l1.x, l1.y, l1.z, nd.n2.w);
+        nd.n3 = make_float4(h1.x, h1.y, h1.z, nd.n3.w);
+        nodes[p] = nd;
+        boxLo[p] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
+        boxHi[p] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
+        visit[p] = 0, expect[p] = 0; // clean for the next refit
+        __threadfence();
+        // 4-wide nodes: an even-depth node absorbs its internal (odd-depth) children, which are final by now
+        if (!parity[p]) collapse4_node(p, nodes, nodes4);
+        __threadfence();
+        p = parent[p];
+    }
+}
+
+// the same two steps on the reference's tree (reference order): leaves hold <= 4 triangles; a leaf is refitted by the
+// thread of its FIRST triangle in triOrder that belongs to the updated range (ties: the lowest position wins the CAS)
+__device__ __forceinline__ void ref_store_child_box(Node *nd, int which, f3 lo, f3 hi);
+__global__ void k_ref_refit_mark(int triLo, int triHi, const int32_t *__restrict__ leafOfTri, const int32_t *__restrict__ leafRange,
+                                 const int32_t *__restrict__ leafParent, const int32_t *__restrict__ nodeParent,
+                                 const uint32_t *__restrict__ refSlot, const float4 *__restrict__ tv0,
+                                 const float4 *__restrict__ tv1, const float4 *__restrict__ tv2, Node *nodes, int32_t *leafMark,
+                                 int32_t *expect, SetHeader *hdr) {
+    const int t = triLo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triHi) return;
+    const int l = leafOfTri[t];
+    if (atomicExch(&leafMark[l], 1) != 0) return; // another triangle of the same leaf got here first
+    const int range = leafRange[l], start = range >> 2, count = (range & 3) + 1;
+    f3 lo = {0, 0, 0}, hi = {0, 0, 0};
+    for (int k = 0; k < count; k++) {
+        const uint32_t slot = refSlot[start + k];
+        const f3 a = xyz(tv0[slot]), b = xyz(tv1[slot]), c = xyz(tv2[slot]);
+        const f3 tlo = vmin(a, vmin(b, c)), thi = vmax(a, vmax(b, c));
+        lo = k ? vmin(lo, tlo) : tlo;
+        hi = k ? vmax(hi, thi) : thi;
+    }
+    int pw = leafParent[l];
+    if (pw < 0) {
+        hdr->lo[0] = lo.x, hdr->lo[1] = lo.y, hdr->lo[2] = lo.z;
+        hdr->hi[0] = hi.x, hdr->hi[1] = hi.y, hdr->hi[2] = hi.z;
+        return;
+    }
+    ref_store_child_box(nodes + (pw >> 1), pw & 1, lo, hi);
+    for (; pw >= 0; pw = nodeParent[pw >> 1])
+        if (atomicAdd(&expect[pw >> 1], 1) != 0) break;
+}
+
+__global__ void k_ref_refit_climb(int triLo, int triHi, const int32_t *__restrict__ leafOfTri, const int32_t *__restrict__ leafParent,
+                                  const int32_t *__restrict__ nodeParent, Node *nodes, int32_t *leafMark, int32_t *visit,
+                                  int32_t *expect, SetHeader *hdr) {
+    const int t = triLo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triHi) return;
+    const int l = leafOfTri[t];
+    if (atomicExch(&leafMark[l], 0) != 1) return; // one climber per marked leaf; the mark is cleared on the way
+    __threadfence();
+    int pw = leafParent[l];
+    while (pw >= 0) {
+        const int p = pw >> 1;
+        if (atomicAdd(&visit[p], 1) + 1 < *(volatile int32_t *)&expect[p]) return;
+        visit[p] = 0, expect[p] = 0;
+        __threadfence();
+        const float4 *q = reinterpret_cast<const float4 *>(nodes + p);
+        const float4 l0 = __ldcg(q), h0 = __ldcg(q + 1), l1 = __ldcg(q + 2), h1 = __ldcg(q + 3);
+        const f3 lo = vmin(xyz(l0), xyz(l1)), hi = vmax(xyz(h0), xyz(h1));
+        pw = nodeParent[p];
+        if (pw < 0) {
+            hdr->lo[0] = lo.x, hdr->lo[1] = lo.y, hdr->lo[2] = lo.z;
+            hdr->hi[0] = hi.x, hdr->hi[1] = hi.y, hdr->hi[2] = hi.z;
+            return;
+        }
+        ref_store_child_box(nodes + (pw >> 1), pw & 1, lo, hi);
+        __threadfence();
+    }
 }
 
 // ---------------------------------------------------------------- host orchestration
@@ -747,6 +871,7 @@ static int build_tree(cq_world *w, DeviceSet &S, const uint32_t *sortedKeys /* m
         }
         k_fit<<<cdiv(n, 256), 256, 0, st>>>(n, S.tv0, S.tv1, S.tv2, S.nodes, S.parent, S.boxLo, S.boxHi, S.visit);
         w->launches++;
+        if (n > 1) CQ_CUDA(cudaMemsetAsync(S.visit, 0, sizeof(int32_t) * (size_t)(n - 1), st)); // clean for a dirty-subtree refit
         if (n > 1) {
             if (sortedKeys) { // topology is new: depth parities
                 k_depth_parity<<<cdiv(n - 1, 256), 256, 0, st>>>(n - 1, S.parent, S.depthParity);
@@ -797,6 +922,8 @@ int build_set(cq_world *w, DeviceSet &S, const SetPlan &in,
         S.boxLo = a.take<float4>((size_t)2 * nCap);
         S.boxHi = a.take<float4>((size_t)2 * nCap);
         S.visit = a.take<int32_t>(nCap);
+        S.expect = a.take<int32_t>(nCap);
+        S.slotOfTri = a.take<uint32_t>(nCap);
     };
     Arena arena;
     arena.cap = arena_layout(carve);
@@ -918,6 +1045,11 @@ int build_set(cq_world *w, DeviceSet &S, const SetPlan &in,
         rc = use_classic_sort() ? radix_sort_pairs_classic(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist)
                                 : radix_sort_pairs_onesweep(w, dKeys, S.sortedTri, dKeysTmp, dValsTmp, n, dHist, histWords);
         if (rc == CQ_OK) rc = build_tree(w, S, dKeys);
+        if (rc == CQ_OK) { // for the dirty-subtree refit: where every triangle sits, and clean marking counters
+            k_invert_sorted<<<cdiv(n, 256), 256, 0, st>>>(S.sortedTri, n, S.slotOfTri);
+            w->launches++;
+            rc = check_cuda(cudaMemsetAsync(S.expect, 0, sizeof(int32_t) * (size_t)n, st), "expect");
+        }
     } else {
         rc = build_tree(w, S, nullptr);
     }
@@ -1237,6 +1369,7 @@ int attach_ref_order(cq_world *w) {
         std::vector<int32_t> nodeParent(std::max(nInt, 1), -1), leafParent(std::max(nLeaf, 1), -1), leafRange(std::max(nLeaf, 1), 0);
         std::vector<uint32_t> refSlot(n);
         for (int p = 0; p < n; p++) refSlot[p] = slotOf[T.order[p]];
+        std::vector<int32_t> leafOfTri(n);
         auto ref_of = [&](int k) { // reference to node k as a parent stores it
             const RefNode &nd = T.nodes[k];
             return nd.left >= 0 ? idOf[k] : ~((nd.start << 2) | (nd.count - 1));
@@ -1261,6 +1394,7 @@ int attach_ref_order(cq_world *w) {
             } else {
                 leafParent[idOf[k]] = pw;
                 leafRange[idOf[k]] = (nd.start << 2) | (nd.count - 1);
+                for (int q = nd.start; q < nd.start + nd.count; q++) leafOfTri[T.order[q]] = idOf[k];
             }
         }
         if (depthMax + 2 > CQ_STACK) {
@@ -1275,6 +1409,9 @@ int attach_ref_order(cq_world *w) {
             S.refLeafParent = a.take<int32_t>(nLeaf);
             S.refLeafRange = a.take<int32_t>(nLeaf);
             S.refVisit = a.take<int32_t>(nInt);
+            S.refExpect = a.take<int32_t>(nInt);
+            S.refLeafMark = a.take<int32_t>(nLeaf);
+            S.refLeafOfTri = a.take<int32_t>(n);
             S.refHdr = a.take<SetHeader>(1);
         };
         Arena arena;
@@ -1293,6 +1430,9 @@ int attach_ref_order(cq_world *w) {
         CQ_CUDA(cudaMemcpyAsync(S.refLeafParent, leafParent.data(), sizeof(int32_t) * (size_t)std::max(nLeaf, 1), cudaMemcpyHostToDevice, st));
         CQ_CUDA(cudaMemcpyAsync(S.refLeafRange, leafRange.data(), sizeof(int32_t) * (size_t)std::max(nLeaf, 1), cudaMemcpyHostToDevice, st));
         CQ_CUDA(cudaMemsetAsync(S.refVisit, 0, sizeof(int32_t) * (size_t)std::max(nInt, 1), st));
+        CQ_CUDA(cudaMemsetAsync(S.refExpect, 0, sizeof(int32_t) * (size_t)std::max(nInt, 1), st));
+        CQ_CUDA(cudaMemsetAsync(S.refLeafMark, 0, sizeof(int32_t) * (size_t)std::max(nLeaf, 1), st));
+        CQ_CUDA(cudaMemcpyAsync(S.refLeafOfTri, leafOfTri.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
         CQ_CUDA(cudaMemcpyAsync(S.refHdr, &h, sizeof(h), cudaMemcpyHostToDevice, st));
         CQ_TRY(ref_fit(w, S));
         CQ_CUDA(cudaStreamSynchronize(st)); // the host vectors above are the copies' sources
@@ -1316,19 +1456,50 @@ int attach_ref_order(cq_world *w) {
     return CQ_OK;
 }
 
-// TriangleMeshSet.updateTransforms + BVH.refit: re-transform the changed parts' vertices, regather the
-// sorted SoA, recompute every box bottom-up (same tree topology).  Asynchronous on the world stream.
+// TriangleMeshSet.updateTransforms + BVH.refit: re-transform the changed parts' vertices, then
+//   * few triangles moved (less than a quarter of the set): the dirty-subtree refit above — the updated triangles' slots,
+//     their leaves and only the ancestors of those, in the LBVH, its 4-wide collapse and (reference order) the reference's
+//     own tree, like BVH.refit (CollisionQuery.swift:528-575);
+//   * otherwise: regather the whole sorted SoA and recompute every box bottom-up (same topology).
+// Both give the same boxes (min / max are exact).  Asynchronous on the world stream.
 int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx) {
     cudaStream_t st = w->stream;
+    long long moved = 0;
     for (int pi : partIdx) {
         const PartInfo &p = w->parts[pi];
         int nv = p.vertHi - p.vertLo;
+        moved += p.triHi - p.triLo;
         if (nv <= 0) continue;
         k_transform<<<cdiv(nv, 256), 256, 0, st>>>(S.localPos, S.worldPos, w->dModels, p.vertLo, p.vertHi);
         w->launches++;
     }
-    CQ_TRY(build_tree(w, S, nullptr));
-    return ref_fit(w, S); // reference order: the reference's own tree keeps its topology too (BVH.refit)
+    static const bool forceFull = getenv("CQ_REFIT_FULL") != nullptr; // A/B and the test that both paths agree
+    if (forceFull || moved * 4 >= (long long)S.nTris) {
+        CQ_TRY(build_tree(w, S, nullptr));
+        return ref_fit(w, S); // reference order: the reference's own tree keeps its topology too (BVH.refit)
+    }
+    const int n = S.nTris;
+    for (int pi : partIdx) {
+        const PartInfo &p = w->parts[pi];
+        const int cnt = p.triHi - p.triLo;
+        if (cnt <= 0) continue;
+        k_refit_mark<<<cdiv(cnt, 256), 256, 0, st>>>(p.triLo, p.triHi, S.slotOfTri, n, S.worldPos, S.indices, S.tv0, S.tv1, S.tv2,
+                                                      S.parent, S.boxLo, S.boxHi, S.expect);
+        k_refit_climb<<<cdiv(cnt, 256), 256, 0, st>>>(p.triLo, p.triHi, S.slotOfTri, n, S.nodes, S.parent, S.boxLo, S.boxHi, S.visit,
+                                                       S.expect, S.depthParity, S.nodes4);
+        w->launches += 2;
+        if (S.refArena && S.nRefLeaves > 0) {
+            k_ref_refit_mark<<<cdiv(cnt, 256), 256, 0, st>>>(p.triLo, p.triHi, S.refLeafOfTri, S.refLeafRange, S.refLeafParent,
+                                                              S.refNodeParent, S.refSlot, S.tv0, S.tv1, S.tv2, S.refNodes,
+                                                              S.refLeafMark, S.refExpect, S.refHdr);
+            k_ref_refit_climb<<<cdiv(cnt, 256), 256, 0, st>>>(p.triLo, p.triHi, S.refLeafOfTri, S.refLeafParent, S.refNodeParent,
+                                                               S.refNodes, S.refLeafMark, S.refVisit, S.refExpect, S.refHdr);
+            w->launches += 2;
+        }
+    }
+    k_header<<<1, 32, 0, st>>>(n, S.boxLo, S.boxHi, S.hdr);
+    w->launches++;
+    return check_cuda(cudaGetLastError(), "dirty refit");
 }
 
 } // namespace cq

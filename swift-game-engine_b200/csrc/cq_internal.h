@@ -46,6 +46,8 @@ struct DeviceSet {
     int32_t *rangeLo = nullptr, *rangeHi = nullptr; // per internal node
     float4 *boxLo = nullptr, *boxHi = nullptr;      // 2nTris-1 subtree boxes (bottom-up scratch, kept for refit)
     int32_t *visit = nullptr;    // per internal node arrival counter
+    int32_t *expect = nullptr;   // dirty-subtree refit: dirty children per internal node (zero between refits)
+    uint32_t *slotOfTri = nullptr; // soup triangle id -> slot of the sorted SoA
     SetHeader *hdr = nullptr;
     // reference order (cq_reftree.h -> attach_ref_order): the reference's own tree, for the ray walk and its refit
     void *refArena = nullptr;
@@ -56,6 +58,9 @@ struct DeviceSet {
     int32_t *refLeafParent = nullptr;  // per leaf: same encoding
     int32_t *refLeafRange = nullptr;   // per leaf: (start << 2) | (count - 1)
     int32_t *refVisit = nullptr;       // per internal node arrival counter (left at zero by every fit)
+    int32_t *refExpect = nullptr;      // dirty-subtree refit: dirty children per internal node
+    int32_t *refLeafMark = nullptr;    // dirty-subtree refit: per leaf, claimed by one of its updated triangles
+    int32_t *refLeafOfTri = nullptr;   // soup triangle id -> leaf of the reference's tree
     SetHeader *refHdr = nullptr;
 };
 

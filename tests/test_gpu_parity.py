@@ -882,3 +882,49 @@ def test_group_and_multi_world_on_the_visible_gpus(cq, orc, scenes):
     assert bool(torch.equal(src, dst))
     rg.close()
     g.close()
+
+
+@pytest.mark.parametrize("order", ["reference", "canonical"])
+def test_dirty_subtree_refit_of_small_parts(cq, orc, scenes, order):
+    """updateStaticTransforms / updateDynamicTransforms of ONE small entity inside larger sets (BVH.refit,
+    CollisionQuery.swift:528-575: only the ancestors of the moved leaves): the library's dirty-subtree path (fewer than a
+    quarter of a set's triangles moved) must leave exactly the boxes and answers a full refit / the reference leaves — the
+    LBVH, its 4-wide collapse and, in reference order, the reference's own tree that the ray kernel walks."""
+    tv, ti, half = scenes.terrain_mesh(cells=120, cell=1.0)
+    bv, bi = scenes.box_mesh(3.0)
+    rng = np.random.default_rng(5)
+    parts = [scenes.part(tv, ti, entity_id=0)]
+    spots = rng.uniform(-40, 40, (9, 2))
+    for k, (x, z) in enumerate(spots):
+        y = float(scenes.terrain_height(np.float32([x]), np.float32([z]))[0]) + 1.0
+        parts.append(scenes.part(bv, bi, scenes.trs_model((x, y, z)), is_dynamic=(k >= 6), layer=2, entity_id=1 + k))
+    g = cq.CollisionQuery(parts, order=cq.ORDER_REFERENCE if order == "reference" else cq.ORDER_CANONICAL)
+    o = orc.OracleWorld(parts)
+    lo, hi = np.float32([-55, -10, -55]), np.float32([55, 20, 55])
+    casts = scenes.gen_casts(6000, lo, hi, seed=61, radius=0.6, half_height=0.7, expand=0.0)
+    rays = scenes.gen_rays(12000, lo, hi, seed=62, expand=0.0)
+    caps = scenes.gen_capsules(4000, lo, hi, seed=63, expand=0.0)
+    for step in range(1, 5):
+        moved = {2: 2, 8: 8} if step % 2 else {3: 3, 7: 7, 9: 9}  # a static and a dynamic box (ids), alternating
+        ids, models = [], []
+        for eid in moved:
+            x, z = spots[eid - 1] + rng.uniform(-3, 3, 2)
+            y = float(scenes.terrain_height(np.float32([x]), np.float32([z]))[0]) + 1.0 + 0.3 * step
+            ids.append(eid)
+            models.append(scenes.trs_model((x, y, z), scenes.quat_angle_axis(0.4 * step, (0, 1, 0))))
+        g.update_transforms(ids, models)
+        o.update_transforms(ids, models)
+        assert o.check_bvh(0) and o.check_bvh(1)
+        for which in (0, 1):
+            a, b = g.read_soup(which), o.read_soup(which)
+            assert np.array_equal(a["positions"], b["positions"]) and np.array_equal(a["aabbs"], b["aabbs"]), (step, which)
+        assert g.capsuleCastBlocking(casts).tobytes() == o.capsule_cast(casts, 1, g.order).tobytes(), step
+        assert g.raycast(rays).tobytes() == o.raycast(rays, g.order).tobytes(), step
+        got, cnt, ov = g.capsuleOverlapAll(caps, 8)
+        ref, rcnt, rov = o.capsule_overlap_all(caps, 8, g.order)
+        if g.order == orc.ORDER_REFERENCE:
+            got = _caller_order(got, cnt)
+        assert np.array_equal(cnt, rcnt) and got.tobytes() == ref.tobytes(), step
+    assert (g.raycast(rays)["triangle_index"] >= g.info()["n_static_triangles"]).any()  # dynamic boxes are really hit
+    g.close()
+    o.close()
