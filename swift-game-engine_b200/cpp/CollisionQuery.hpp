@@ -48,8 +48,13 @@ struct CapsuleOverlapHit { // CollisionQuery.swift:45-52
 class CollisionQuery {
   public:
     // init(world:activeEntityIDs:) — the caller flattens its (Transform, StaticMesh, body type) entities into parts
-    explicit CollisionQuery(const std::vector<cq_mesh_part> &parts) {
-        if (cq_world_create(parts.data(), (int32_t)parts.size(), &w_) != CQ_OK)
+    // referenceOrder (default): exact ties, capsuleOverlapAll overflow and grazing rays come out as in the reference's own
+    // tree and visiting order (CQ_ORDER_REFERENCE, include/cq.h); false = the tree-independent rule, no host build.
+    explicit CollisionQuery(const std::vector<cq_mesh_part> &parts, bool referenceOrder = true) {
+        cq_world_options opt;
+        cq_world_options_default(&opt);
+        opt.order = referenceOrder ? CQ_ORDER_REFERENCE : CQ_ORDER_CANONICAL;
+        if (cq_world_create_ex(parts.data(), (int32_t)parts.size(), &opt, &w_) != CQ_OK)
             throw std::runtime_error(std::string("cq_world_create: ") + cq_last_error());
     }
     ~CollisionQuery() { cq_world_destroy(w_); }

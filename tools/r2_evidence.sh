@@ -5,6 +5,21 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
+timeout 300 python __graft_entry__.py smoke > $O/r2ev_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/r2ev_smoke.log
+( time timeout 900 python bench.py --steps 20 --warmup 5 > $O/r2ev_bench_default.json 2> $O/r2ev_bench_default.err ) 2> $O/r2ev_bench_default.time
+echo "bench default rc=$?"; tail -3 $O/r2ev_bench_default.time
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2ev_bench_reference.json 2>/dev/null; echo "reference arm rc=$?"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r2ev_bench_default.json").read().strip().splitlines()[-1])
+print("headline %.1f M/s %.3f ms  e2e %.1f M/s (%.2f ms) match %s  full %.1f M/s (%.2f ms)  replay %s  frac %.3f fp32 %.3f" % (d["value"]/1e6, d["ms_per_step"], d["e2e"]["value"]/1e6,
+      d["e2e"]["ms_per_step"], d["e2e"]["matches_device_path"], d["e2e"]["full_record"]["value"]/1e6, d["e2e"]["full_record"]["ms_per_step"], d["config"]["counting_replay_matches_timed_run"],
+      d["roofline"]["frac"], d["roofline"]["fp32_secondary"]["frac"]))
+for k, x in d["extra"].items():
+    if "error" in x: print("  ", k, "ERROR", x["error"], x.get("trace","")[-300:]); continue
+    print("   extra %-8s %.1f M/s  %.3f ms/step  frac %.3f  e2e %.1f M/s  wall %.1f s  cpu %s" % (k, x["value"]/1e6, x["ms_per_step"], x["roofline"]["frac"] if "roofline" in x else -1,
+          (x.get("e2e") or {}).get("value", 0)/1e6, x.get("bench_wall_s", 0), {kk: v for kk, v in (x.get("cpu_baseline") or {}).items() if kk not in ("sample", "unit", "kind")}))
+PY
 cap() { # tag, kernel regex, skip, count, command...
   local tag=$1 rx=$2 skip=$3 cnt=$4; shift 4
   "$@" > $O/r2ev_${tag}_plain.log 2>&1 && \
