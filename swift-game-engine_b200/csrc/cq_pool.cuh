@@ -529,18 +529,30 @@ static __device__ __noinline__ void pool_post_first_hits(const uint32_t *__restr
     s.pending = CQ_MAX_OVERLAP_HITS;
 }
 
+// Commit of the finished pairs.  Contributions to DIFFERENT owners touch different records and commute; contributions to
+// the same owner are order-free reductions (smallest (toi, rank); deepest two / smallest ranks; counts).  So the lanes are
+// grouped by owner (__match_any_sync) and round r commits the r-th member of every group at once: the number of serialized
+// rounds is the largest group, not the number of finishing lanes.  Cast contributions that can no longer win (toi already
+// beyond the owner's best — which only ever decreases) are dropped before the rounds.  ncu on C2, where most candidates of
+// a fat capsule hit, had the lane-at-a-time version at 30% of the kernel's stall samples (profiles/r2_by_region.txt).
 template <class OvlCommit>
 __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const Commit &cm, bool retired, int lane,
                                             OvlCommit ovl) {
-    uint32_t fin = __ballot_sync(0xffffffffu, retired);
-    uint32_t todo = __ballot_sync(0xffffffffu, retired && cm.kind != 0);
+    bool mine = retired && cm.kind != 0;
+    if (mine && cm.kind == 1) mine = !(cm.key > *(volatile const float *)&wp.qs[job.owner].rT);
+#ifdef CQ_COMMIT_SERIAL
+    uint32_t todo = __ballot_sync(0xffffffffu, mine);
+    int myRound = __popc(todo & ((1u << lane) - 1u)); // one lane per round
+#else
+    const uint32_t todo = __ballot_sync(0xffffffffu, mine);
+    int myRound = 0;
+    if (mine) myRound = __popc(__match_any_sync(todo, job.owner) & ((1u << lane) - 1u)); // my place among my owner's lanes
+#endif
 #pragma unroll 1
-    while (todo) {
-        int l = __ffs(todo) - 1;
-        todo &= todo - 1;
-        if (lane == l) {
+    for (int round = 0; __any_sync(0xffffffffu, mine && myRound >= round); round++) {
+        if (mine && myRound == round) {
             QShared &s = wp.qs[job.owner];
-            if (cm.kind == 1) { // accepted candidate with the smallest (toi, index) wins (:1084,1098 + tie rule)
+            if (cm.kind == 1) { // accepted candidate with the smallest (toi, rank) wins (:1084,1098 + the order rule)
                 float bestT = s.rT;
                 int bestTri = s.rTri;
                 bool better = cm.key < bestT;
@@ -556,7 +568,7 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                     store3s(s.rN, cm.n);
                     store3s(s.rTriN, cm.triN);
                 }
-            } else { // overlap: (depth desc, index asc) bookkeeping is the kernel's (top-2 or top-K)
+            } else { // overlap: the bookkeeping is the kernel's (two deepest + first-visited list, or top-K)
                 ovl(s, cm.key, job.gid, job.rank, job.enc, cm.n);
             }
         }
@@ -566,7 +578,6 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
         atomicSub(&wp.qs[job.owner].pending, 1);
         job.phase = PH_NONE;
     }
-    (void)fin;
     __syncwarp();
 }
 

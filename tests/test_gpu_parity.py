@@ -928,3 +928,69 @@ def test_dirty_subtree_refit_of_small_parts(cq, orc, scenes, order):
     assert (g.raycast(rays)["triangle_index"] >= g.info()["n_static_triangles"]).any()  # dynamic boxes are really hit
     g.close()
     o.close()
+
+
+def test_full_size_c2_every_sweep_against_the_reference_order(cq, orc, scenes):
+    """BASELINE config C2 at its full size: all 65,536 sweeps against the Semla mesh, every byte of every hit record equal
+    to the reference-order oracle's (which walks the reference's own BVH in its own order) — ties included — and every
+    difference to the canonical rule carries the TIE flag."""
+    parts = scenes.semla_scene(use_hulls=False)
+    g, o = cq.CollisionQuery(parts), orc.OracleWorld(parts)
+    lo, hi = scenes.scene_aabb(parts[1:])
+    q = scenes.gen_casts(65536, lo, hi, seed=0xC0111DE2)
+    got, flags = g.capsuleCast(q, with_flags=True)
+    ref = o.capsule_cast(q, 0, orc.ORDER_REFERENCE, 8)
+    assert got.tobytes() == ref.tobytes()
+    can = o.capsule_cast(q, 0, orc.ORDER_CANONICAL, 8)
+    diff = got["triangle_index"] != can["triangle_index"]
+    assert 0.2 < diff.mean() < 0.4 and (flags[diff] & cq.HIT_TIE).all() and np.array_equal(got["toi"], can["toi"])
+    g.close()
+    o.close()
+
+
+def test_full_size_c5_rays_properties(cq, orc, scenes):
+    """BASELINE config C5 at its full size (16,777,216 rays against the three meshes merged, the mirror in the dynamic
+    set), through size-independent properties in both order rules: (1) idempotence; (2) sharding invariance (two halves =
+    the whole batch); (3) a hit stays the hit when maxDistance is cut to just beyond it and disappears when cut to just
+    before it; (4) the canonical answer is never farther than the reference-order one, and where the two rules name
+    different triangles it is an exact tie or a hit the reference's slab test lost; (5) a 100 k sample is byte-identical to
+    the oracle in the world's order after a refit of the mirror."""
+    parts = scenes.merged_scene(mirror_dynamic=True)
+    a = scenes.load_mirror_fixture()
+    t, q0, s = scenes.transform_from_matrix(scenes.mirror_model(a["transform"]))
+    model = scenes.trs_model(t, scenes.quat_mul(scenes.quat_angle_axis(np.radians(17.0), (0, 1, 0)), q0), s)
+    lo, hi = scenes.scene_aabb(parts[1:])
+    n = 1 << 24
+    rays = scenes.gen_rays(n, lo, hi, seed=0xC0111DE5, max_distance=100.0, expand=5.0, y_range=(0.0, 12.0))
+    out = {}
+    o = orc.OracleWorld(parts)
+    o.update_transforms([parts[-1]["entity_id"]], [model])
+    pick = np.sort(np.random.default_rng(29).choice(n, 100_000, replace=False))
+    for order in (cq.ORDER_REFERENCE, cq.ORDER_CANONICAL):
+        g = cq.CollisionQuery(parts, order=order)
+        g.update_transforms([parts[-1]["entity_id"]], [model])
+        whole = g.raycast(rays)
+        assert whole.tobytes() == g.raycast(rays).tobytes()
+        halves = np.concatenate([g.raycast(np.ascontiguousarray(rays[: n // 2])), g.raycast(np.ascontiguousarray(rays[n // 2:]))])
+        assert whole.tobytes() == halves.tobytes()
+        hit = whole["triangle_index"] >= 0
+        assert 0.2 < hit.mean() < 0.8
+        sub = np.flatnonzero(hit)[:: 64]
+        near, far = rays[sub].copy(), rays[sub].copy()
+        far["max_distance"] = whole["distance"][sub] * np.float32(1.001) + np.float32(1e-4)
+        near["max_distance"] = whole["distance"][sub] * np.float32(0.999) - np.float32(1e-4)
+        kept = g.raycast(far)
+        assert np.array_equal(kept["triangle_index"], whole["triangle_index"][sub]) and np.array_equal(kept["distance"], whole["distance"][sub])
+        cut = g.raycast(near)
+        assert ((cut["triangle_index"] < 0) | (cut["distance"] < whole["distance"][sub])).all()
+        assert whole[pick].tobytes() == o.raycast(np.ascontiguousarray(rays[pick]), order, 8).tobytes()
+        out[order] = whole
+        g.close()
+    ref, can = out[cq.ORDER_REFERENCE], out[cq.ORDER_CANONICAL]
+    both = (ref["triangle_index"] >= 0) & (can["triangle_index"] >= 0)
+    assert (can["distance"][both] <= ref["distance"][both]).all() and not ((ref["triangle_index"] >= 0) & (can["triangle_index"] < 0)).any()
+    diff = ref["triangle_index"] != can["triangle_index"]
+    tie = diff & both & (ref["distance"] == can["distance"])
+    lost = diff & (can["triangle_index"] >= 0) & ((ref["triangle_index"] < 0) | (ref["distance"] > can["distance"]))
+    assert not (diff & ~tie & ~lost).any() and diff.mean() < 0.01
+    o.close()
