@@ -368,7 +368,7 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
 
 // one distance evaluation + the pair's state transition.  `retired` = the pair is finished (with or
 // without a contribution in `cm`).
-// LOOKAHEAD: the look-ahead prune below.  Measured on one box (profiles/r2_lookahead_ab.txt): the batched sweep kernel gains
+// LOOKAHEAD: the look-ahead prune below.  Measured on one box (profiles/r2_ab_same_box.txt): the batched sweep kernel gains
 // where candidates are many (C2: distance evaluations per sweep 5352 -> 4108, 32.8 -> 28.1 ms) and loses 1% on C4; the
 // move-and-slide kernel LOSES 3-5% on the hulls and terrain scenes (few candidates per query, the extra compares and the
 // longer loop body cost more than the 1.5% of evaluations they save), so only the query kernels instantiate it.
@@ -382,20 +382,25 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
     if (COUNT) ctr.evals++;
     float dist = segment_triangle_distance<true>(center, job.hh, job.T, sp, tp);
     const float bestT = *(volatile const float *)&s.rT; // shared across the query's pairs
+    // A contact whose toi is bounded below by `tLow` cannot win when tLow > bestT.  LOOKAHEAD kernels also retire the pair
+    // when it can at best TIE (tLow == bestT) behind an earlier-visited best whose tie is already on record: neither the
+    // answer nor its CQ_HIT_TIE flag can change.  (A capsule that starts a sweep inside the mesh meets dozens of toi == 0
+    // contacts, two evaluations each: C2.)
+    auto hopeless = [&](float tLow) {
+        if (tLow > bestT) return true;
+        if (!LOOKAHEAD || tLow != bestT) return false;
+        return (*(volatile const int *)&s.mode & CQ_QF_TIE) != 0 && job.rank > *(volatile const int *)&s.rRank;
+    };
     if (ph == PH_ADV) { // sweepCapsuleTriangle loop body, CollisionQuery.swift:1303-1356
         if (dist <= job.radius + 1e-5f) {
             float c0 = smax(0.0f, smin(job.lastSafeT, job.L)); // refineTOI prologue, :1371-1377
             float c1 = smax(0.0f, smin(job.t, job.L));
             job.lo = smin(c0, c1);
             job.hi = smax(c0, c1);
-            if (job.hi - job.lo < 1e-5f) {
-                if (job.hi > bestT) retired = true;
-                else job.phase = PH_FIN;
-            } else {
-                job.k = 0;
-                if (job.lo > bestT) retired = true;
-                else job.phase = PH_BIS;
-            }
+            const bool fin = job.hi - job.lo < 1e-5f;
+            job.k = 0;
+            if (hopeless(fin ? job.hi : job.lo)) retired = true;
+            else job.phase = fin ? PH_FIN : PH_BIS;
         } else {
             job.lastSafeT = job.t;
             float advance = smax(dist - job.radius, job.minAdvance);
@@ -419,7 +424,7 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
         else job.lo = tc;
         job.k++;
         if (job.k == 10) {
-            if (job.hi > bestT) retired = true;
+            if (hopeless(job.hi)) retired = true;
             else job.phase = PH_FIN;
         } else if (job.lo > bestT) {
             retired = true;
@@ -458,7 +463,7 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
     }
 }
 
-// serialized commit: one finishing lane at a time updates its owner's record; pending counters drop
+// (the commit step itself is pool_commit below)
 // default overlap commit: the two deepest overlaps kept in the owner's QShared (move-and-slide depenetration)
 // Reference order (byRank): the reference's depenetration takes the first maxHits = 8 overlaps in visiting order, sorts
 // them by depth (stably) and uses one or two (Systems.swift:751-767).  The first pass keeps the two deepest of ALL
@@ -535,28 +540,71 @@ static __device__ __noinline__ void pool_post_first_hits(const uint32_t *__restr
 // rounds is the largest group, not the number of finishing lanes.  Cast contributions that can no longer win (toi already
 // beyond the owner's best — which only ever decreases) are dropped before the rounds.  ncu on C2, where most candidates of
 // a fat capsule hit, had the lane-at-a-time version at 30% of the kernel's stall samples (profiles/r2_by_region.txt).
-template <class OvlCommit>
+#ifndef CQ_COMMIT_REDUCE_MAS
+#define CQ_COMMIT_REDUCE_MAS 0 /* 1: the move-and-slide kernels settle sweep hits with warp reductions too (A/B) */
+#endif
+
+// Commit step: the lanes that finished a pair this trip hand their contribution to the owner's record; pending counters drop.
+// Lanes are grouped by owner (one MATCH); round r serves the r-th finishing lane of every owner at once.
+// REDUCE (the query kernels): sweep hits (:1084,1098 + the order rule — the accepted candidate with the smallest (toi, rank)
+// wins) are settled among the finishing lanes of an owner with two warp reductions, so that ONE lane per owner touches the
+// record and no rounds are needed for sweeps.  Lane-at-a-time rounds cost the C2 kernel 8.3 rounds per trip: a capsule that
+// starts inside the mesh collects dozens of toi == 0 hits, all exact ties that each took a round to compare ranks
+// (profiles/r2_by_region.txt).  A contribution already behind the owner's best is dropped before anything else.
+template <bool REDUCE, class OvlCommit>
 __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const Commit &cm, bool retired, int lane,
                                             OvlCommit ovl) {
-    bool mine = retired && cm.kind != 0;
-    if (mine && cm.kind == 1) mine = !(cm.key > *(volatile const float *)&wp.qs[job.owner].rT);
-#ifdef CQ_COMMIT_SERIAL
-    uint32_t todo = __ballot_sync(0xffffffffu, mine);
-    int myRound = __popc(todo & ((1u << lane) - 1u)); // one lane per round
-#else
+    const uint32_t retMask = __ballot_sync(0xffffffffu, retired);
+    if (retMask == 0u) return; // (warp-uniform) nothing finished this trip
+    bool cast = retired && cm.kind == 1;
+    if (cast) cast = !(cm.key > *(volatile const float *)&wp.qs[job.owner].rT);
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t sameOwner = retired ? __match_any_sync(retMask, job.owner) : 0u; // the finishing lanes of my owner
+    bool mine = retired && cm.kind == 2;
+    if (REDUCE) {
+        const uint32_t castMask = __ballot_sync(0xffffffffu, cast);
+        if (cast) {
+            const uint32_t grp = sameOwner & castMask;
+            const uint32_t kb = __float_as_uint(cm.key + 0.0f); // toi >= 0: the bit pattern orders like the value
+            const bool atMin = kb == __reduce_min_sync(grp, kb);
+            const uint32_t rmin = __reduce_min_sync(grp, atMin ? (uint32_t)job.rank : 0xffffffffu);
+            const bool tiedInGroup = __popc(__ballot_sync(grp, atMin)) > 1;
+            if (atMin && (uint32_t)job.rank == rmin) {
+                QShared &s = wp.qs[job.owner];
+                const float bestT = s.rT;
+                const bool better = cm.key < bestT;
+                const bool tie = s.rTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited
+                const bool tieWin = tie && job.rank < s.rRank;
+                int mode = s.mode;
+                if (better) mode &= ~CQ_QF_TIE;
+                if (tie || ((better || tieWin) && tiedInGroup)) mode |= CQ_QF_TIE;
+                s.mode = mode;
+                if (better || tieWin) {
+                    s.rT = cm.key;
+                    s.rTri = job.gid;
+                    s.rRank = job.rank;
+                    store3s(s.rPos, cm.pos);
+                    store3s(s.rN, cm.n);
+                    store3s(s.rTriN, cm.triN);
+                }
+            }
+        }
+    } else {
+        mine = mine || cast;
+    }
+    // Overlaps: the bookkeeping is the kernel's (two deepest + first-visited list, or top-K) and is order-free, but a
+    // read-modify-write of the owner's record, hence the rounds.
     const uint32_t todo = __ballot_sync(0xffffffffu, mine);
-    int myRound = 0;
-    if (mine) myRound = __popc(__match_any_sync(todo, job.owner) & ((1u << lane) - 1u)); // my place among my owner's lanes
-#endif
+    const int myRound = __popc(sameOwner & todo & below); // my place among my owner's lanes
 #pragma unroll 1
     for (int round = 0; __any_sync(0xffffffffu, mine && myRound >= round); round++) {
         if (mine && myRound == round) {
             QShared &s = wp.qs[job.owner];
-            if (cm.kind == 1) { // accepted candidate with the smallest (toi, rank) wins (:1084,1098 + the order rule)
+            if (!REDUCE && cm.kind == 1) {
                 float bestT = s.rT;
                 int bestTri = s.rTri;
                 bool better = cm.key < bestT;
-                bool tie = bestTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited (:1084)
+                bool tie = bestTri >= 0 && cm.key == bestT;
                 bool tieWin = tie && job.rank < s.rRank;
                 if (tie) s.mode |= CQ_QF_TIE;
                 if (better) s.mode &= ~CQ_QF_TIE;
@@ -568,14 +616,14 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
                     store3s(s.rN, cm.n);
                     store3s(s.rTriN, cm.triN);
                 }
-            } else { // overlap: the bookkeeping is the kernel's (two deepest + first-visited list, or top-K)
+            } else {
                 ovl(s, cm.key, job.gid, job.rank, job.enc, cm.n);
             }
         }
         __syncwarp();
     }
     if (retired) {
-        atomicSub(&wp.qs[job.owner].pending, 1);
+        if ((sameOwner & below) == 0u) atomicSub(&wp.qs[job.owner].pending, __popc(sameOwner)); // one lane per owner
         job.phase = PH_NONE;
     }
     __syncwarp();
@@ -646,7 +694,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
             if (go) pool_eval<COUNT, LOOKAHEAD>(job, wp, cm, retired, ctr);
         }
 #endif
-        pool_commit(wp, job, cm, retired, lane, ovl);
+        pool_commit<LOOKAHEAD || CQ_COMMIT_REDUCE_MAS>(wp, job, cm, retired, lane, ovl);
 #if CQ_EARLY_PICKUP
         // lanes whose pair just retired take their next pair NOW, so that its three triangle loads are in flight across the
         // loop-back, the exit vote and the front-end test instead of stalling the first evaluation (terrain: 53% of the
