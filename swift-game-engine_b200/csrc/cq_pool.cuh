@@ -541,7 +541,7 @@ static __device__ __noinline__ void pool_post_first_hits(const uint32_t *__restr
 // beyond the owner's best — which only ever decreases) are dropped before the rounds.  ncu on C2, where most candidates of
 // a fat capsule hit, had the lane-at-a-time version at 30% of the kernel's stall samples (profiles/r2_by_region.txt).
 #ifndef CQ_COMMIT_REDUCE_MAS
-#define CQ_COMMIT_REDUCE_MAS 0 /* 1: the move-and-slide kernels settle sweep hits with warp reductions too (A/B) */
+#define CQ_COMMIT_REDUCE_MAS 0 /* 1: every move-and-slide kernel settles sweep hits with warp reductions (A/B) */
 #endif
 
 // Commit step: the lanes that finished a pair this trip hand their contribution to the owner's record; pending counters drop.
@@ -551,6 +551,10 @@ static __device__ __noinline__ void pool_post_first_hits(const uint32_t *__restr
 // record and no rounds are needed for sweeps.  Lane-at-a-time rounds cost the C2 kernel 8.3 rounds per trip: a capsule that
 // starts inside the mesh collects dozens of toi == 0 hits, all exact ties that each took a round to compare ranks
 // (profiles/r2_by_region.txt).  A contribution already behind the owner's best is dropped before anything else.
+// Measured on one box (profiles/r2_ab_same_box.txt, calls 9-10): C2 28.1 -> 16.7 ms (with the tie-aware prune of pool_eval);
+// in the move-and-slide kernel the reductions gain 3.6% on the render mesh and 1.2% on the terrain but cost the hulls step
+// 4% (0.7 KB more code in the steady-state loop), so only its staged-walk variant (worlds of >= 4096 triangles) uses them;
+// owner-grouped rounds alone gained the hulls step 2% over lane-at-a-time rounds.
 template <bool REDUCE, class OvlCommit>
 __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const Commit &cm, bool retired, int lane,
                                             OvlCommit ovl) {
@@ -694,7 +698,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
             if (go) pool_eval<COUNT, LOOKAHEAD>(job, wp, cm, retired, ctr);
         }
 #endif
-        pool_commit<LOOKAHEAD || CQ_COMMIT_REDUCE_MAS>(wp, job, cm, retired, lane, ovl);
+        pool_commit<LOOKAHEAD || (STAGED && FE_IDLE >= 16) || CQ_COMMIT_REDUCE_MAS>(wp, job, cm, retired, lane, ovl);
 #if CQ_EARLY_PICKUP
         // lanes whose pair just retired take their next pair NOW, so that its three triangle loads are in flight across the
         // loop-back, the exit vote and the front-end test instead of stalling the first evaluation (terrain: 53% of the

@@ -55,7 +55,9 @@ def main():
         for name, r in (("generated", rays), ("sorted", srt)):
             d_r = torch.from_numpy(r.view(np.uint8).reshape(-1)).to(dev)
             d_out = torch.empty(n * cq.RAY_HIT.itemsize, dtype=torch.uint8, device=dev)
-            s = torch.cuda.current_stream().cuda_stream
+            ts = torch.cuda.Stream(device=dev)
+            torch.cuda.set_stream(ts)
+            s = ts.cuda_stream
             for _ in range(3):
                 world.raycast_device(d_r.data_ptr(), n, d_out.data_ptr(), s)
             torch.cuda.synchronize()
