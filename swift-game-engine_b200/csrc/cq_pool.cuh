@@ -33,9 +33,6 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
-#ifndef CQ_EARLY_PICKUP
-#define CQ_EARLY_PICKUP 0 /* 1: a second pickup right after the commit (round-2 A/B: hides the triangle fetch of a fresh pair) */
-#endif
 #ifndef CQ_EVAL_KEEP
 #define CQ_EVAL_KEEP 0    /* with CQ_EVAL_REPS > 1: keep evaluating only while this many lanes hold a live pair */
 #endif
@@ -330,40 +327,78 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
     __syncwarp();
 }
 
-// job pickup: idle lanes take ring entries, ranked by ballot
+// job pickup: idle lanes take ring entries, ranked by ballot.
+// LOOKAHEAD kernels drop a sweep candidate right here, before its first distance evaluation, when it cannot matter
+// (both exact-safe, same argument as the look-ahead prune of pool_eval):
+//  (a) the owner's best toi is 0 with a tie already on record and this triangle is visited later than the best: every toi
+//      is >= 0, so it could only tie behind it;
+//  (b) the distance from the capsule's axis at t = 0 to the triangle's BOX exceeds radius + bestT + margin: the capsule
+//      moves at unit speed, so no contact exists at or before bestT.
+// A lane that dropped its candidate takes another one (up to four pickups per trip), so that drops do not leave lanes idle
+// through the evaluation.  C2 (profiles/r2_ab_same_box.txt, call 11).
+#ifndef CQ_PICKUP_DROP
+#define CQ_PICKUP_DROP 1 /* 0: no drops at pickup (A/B) */
+#endif
+template <bool LOOKAHEAD_>
 __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPool &wp, Job &job, int lane) {
-    uint32_t idle = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
-    uint32_t h = *wp.head, avail = *wp.tail - h;
-    if (job.phase == PH_NONE) {
-        uint32_t rank = __popc(idle & ((1u << lane) - 1u));
-        if (rank < avail) {
-            uint32_t e = wp.ring[(h + rank) % CQ_QCAP];
-            int owner = e >> 27, set = (e >> 26) & 1, slot = e & 0x3ffffffu;
-            const QShared &s = wp.qs[owner];
-            job.owner = owner;
-            job.enc = e;
-            job.from = mk3(s.from[0], s.from[1], s.from[2]);
-            job.dir = mk3(s.dir[0], s.dir[1], s.dir[2]);
-            job.L = s.L;
-            job.radius = s.radius;
-            job.hh = s.hh;
-            job.minAdvance = s.minAdvance;
-            job.maxIter = s.maxIter;
-            const float4 *p0 = set ? W.set[1].tv0 : W.set[0].tv0;
-            const float4 *p1 = set ? W.set[1].tv1 : W.set[0].tv1;
-            const float4 *p2 = set ? W.set[1].tv2 : W.set[0].tv2;
-            float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
-            job.T.v0 = xyz(a), job.T.v1 = xyz(b), job.T.v2 = xyz(c);
-            job.gid = __float_as_int(b.w) + (set ? W.set[1].triOffset : 0);
-            job.rank = __float_as_int(c.w);
-            job.t = 0.0f;
-            job.lastSafeT = 0.0f;
-            job.it = 0;
-            job.phase = (s.mode & 0xff) == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
+    constexpr bool LOOKAHEAD = LOOKAHEAD_ && CQ_PICKUP_DROP;
+#pragma unroll 1
+    for (int rep = 0; rep < (LOOKAHEAD ? 4 : 1); rep++) {
+        uint32_t idle = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
+        uint32_t h = *wp.head, avail = *wp.tail - h;
+        bool dropped = false;
+        if (job.phase == PH_NONE) {
+            uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            if (rank < avail) {
+                uint32_t e = wp.ring[(h + rank) % CQ_QCAP];
+                int owner = e >> 27, set = (e >> 26) & 1, slot = e & 0x3ffffffu;
+                QShared &s = wp.qs[owner];
+                job.owner = owner;
+                job.enc = e;
+                job.from = mk3(s.from[0], s.from[1], s.from[2]);
+                job.dir = mk3(s.dir[0], s.dir[1], s.dir[2]);
+                job.L = s.L;
+                job.radius = s.radius;
+                job.hh = s.hh;
+                job.minAdvance = s.minAdvance;
+                job.maxIter = s.maxIter;
+                const float4 *p0 = set ? W.set[1].tv0 : W.set[0].tv0;
+                const float4 *p1 = set ? W.set[1].tv1 : W.set[0].tv1;
+                const float4 *p2 = set ? W.set[1].tv2 : W.set[0].tv2;
+                float4 a = __ldg(p0 + slot), b = __ldg(p1 + slot), c = __ldg(p2 + slot);
+                job.T.v0 = xyz(a), job.T.v1 = xyz(b), job.T.v2 = xyz(c);
+                job.gid = __float_as_int(b.w) + (set ? W.set[1].triOffset : 0);
+                job.rank = __float_as_int(c.w);
+                job.t = 0.0f;
+                job.lastSafeT = 0.0f;
+                job.it = 0;
+                const int mode = s.mode;
+                job.phase = (mode & 0xff) == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
+                if (LOOKAHEAD && job.phase == PH_ADV) {
+                    const float bestT = *(volatile const float *)&s.rT;
+                    if (bestT == 0.0f) dropped = (mode & CQ_QF_TIE) != 0 && job.rank > *(volatile const int *)&s.rRank;
+                    if (!dropped) {
+                        const f3 tlo = vmin(job.T.v0, vmin(job.T.v1, job.T.v2)), thi = vmax(job.T.v0, vmax(job.T.v1, job.T.v2));
+                        const float dx = smax(smax(tlo.x - job.from.x, job.from.x - thi.x), 0.0f);
+                        const float dz = smax(smax(tlo.z - job.from.z, job.from.z - thi.z), 0.0f);
+                        const float dy = smax(smax(tlo.y - (job.from.y + job.hh), (job.from.y - job.hh) - thi.y), 0.0f);
+                        const float reach = job.radius + bestT +
+                                            (1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f);
+                        dropped = dx * dx + dy * dy + dz * dz > reach * reach * 1.0001f;
+                    }
+                    if (dropped) {
+                        job.phase = PH_NONE;
+                        atomicSub(&s.pending, 1);
+                    }
+                }
+            }
         }
+        __syncwarp();
+        if (lane == 0) *wp.head = h + min((uint32_t)__popc(idle), avail);
+        if (!LOOKAHEAD) break;
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, dropped) || (uint32_t)__popc(idle) >= avail) break; // nobody freed a lane / ring is empty
     }
-    __syncwarp();
-    if (lane == 0) *wp.head = h + min((uint32_t)__popc(idle), avail);
 }
 
 // one distance evaluation + the pair's state transition.  `retired` = the pair is finished (with or
@@ -680,7 +715,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
                 pool_walk_round<COUNT, STAGED>(W, wp, lane, ctr);
         }
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
-        pool_take_jobs(W, wp, job, lane);
+        pool_take_jobs<LOOKAHEAD>(W, wp, job, lane);
         Commit cm;
         cm.kind = 0;
         bool retired = false;
@@ -699,12 +734,6 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         }
 #endif
         pool_commit<LOOKAHEAD || (STAGED && FE_IDLE >= 16) || CQ_COMMIT_REDUCE_MAS>(wp, job, cm, retired, lane, ovl);
-#if CQ_EARLY_PICKUP
-        // lanes whose pair just retired take their next pair NOW, so that its three triangle loads are in flight across the
-        // loop-back, the exit vote and the front-end test instead of stalling the first evaluation (terrain: 53% of the
-        // pair state machine's stall samples are long-scoreboard waits on exactly those loads)
-        if (*wp.tail != *wp.head) pool_take_jobs(W, wp, job, lane);
-#endif
         if (__all_sync(0xffffffffu, !alive && job.phase == PH_NONE) && *wp.ntop == 0u && *wp.tail == *wp.head) break;
     }
 }
