@@ -363,6 +363,7 @@ void cq_world_destroy(cq_world *w) {
     destroy_scratch(w->in), destroy_scratch(w->out), destroy_scratch(w->aux), destroy_scratch(w->aux2);
     for (int k = 0; k < 4; k++) destroy_scratch(w->nodeScratch[k]), destroy_scratch(w->orderScratch[k]);
     destroy_scratch(w->agentScratch);
+    sep_graphs_destroy(w);
     destroy_scratch(w->sepScratch);
     if (w->evA) cudaEventDestroy(w->evA);
     if (w->evB) cudaEventDestroy(w->evB);

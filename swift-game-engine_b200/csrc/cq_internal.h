@@ -110,6 +110,7 @@ struct cq_world {
     cq::ScratchBuf agentScratch; // agent snapshot + grid of the move-and-slide call in flight (CQ_MAS_AGENTS)
     cq::ScratchBuf sepScratch;   // cq_agent_separation working set
     int occSep[2][2] = {};       // resident CTAs per SM of k_sep_turns / k_sep_post ([counting build])
+    void *sepGraphs = nullptr;   // instantiated round-loop graphs of cq_agent_separation (cq_sep.cu: SepGraphCache)
     std::vector<cq::ScratchBuf *> held; // scratch blocks acquired by the launch being enqueued (release_held)
 };
 
@@ -178,6 +179,7 @@ int launch_overlap_all(cq_world *w, const cq_capsule *d_q, int n, int maxHits, c
 int launch_move_and_slide(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p, float dt,
                           const float g[3], uint32_t flags, const cq_platform *platforms, int nPlatforms, cudaStream_t st);
 // cq_sep.cu
+void sep_graphs_destroy(cq_world *w);
 int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p,
                             const float *d_massWeight, int iterations, float sepMargin, float heightMargin, int useQuery,
                             cudaStream_t st);

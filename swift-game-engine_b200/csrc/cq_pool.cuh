@@ -33,6 +33,9 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
+#ifndef CQ_PICKUP_DROP
+#define CQ_PICKUP_DROP 1 /* 0: sweeps keep every candidate of the whole sweep's box (no bestT-based drops in walk / pickup; A/B) */
+#endif
 #ifndef CQ_EVAL_KEEP
 #define CQ_EVAL_KEEP 0    /* with CQ_EVAL_REPS > 1: keep evaluating only while this many lanes hold a live pair */
 #endif
@@ -218,7 +221,34 @@ __device__ __forceinline__ void pool_post_overlap(const WorldView &W, const Warp
 // query box, and push what survives — internal children / leaf ranges back on the stack, candidate triangles
 // (layer mask + triangle AABB passed, CollisionQuery.swift:1057-1065) into the pair ring.  One round of the walk
 // for the whole warp costs what one step of a single lane's walk used to cost.
-template <bool COUNT, bool STAGED>
+// Sweep with a hit on record (LOOKAHEAD kernels): only contacts at or before bestT can still matter, and the capsule moves at
+// unit speed, so the walk may use the box of the capsule swept over [0, bestT] (plus the float margin of the look-ahead
+// prune) instead of the whole sweep's box.  Returns false when the query is not such a sweep (the caller keeps qlo/qhi).
+__device__ __forceinline__ bool sweep_reach(const QShared &s, float &bestT, float &margin) {
+    if ((s.mode & 0xff) == CQ_KIND_OVERLAP || *(volatile const int *)&s.rTri < 0) return false;
+    bestT = *(volatile const float *)&s.rT;
+    margin = 1e-3f + (fabsf(s.from[0]) + fabsf(s.from[1]) + fabsf(s.from[2]) + s.L) * 8e-6f;
+    return true;
+}
+__device__ __forceinline__ void sweep_reach_box(const QShared &s, float bestT, float margin, f3 &qlo, f3 &qhi) {
+    const f3 a = mk3(s.from[0], s.from[1], s.from[2]);
+    const f3 b = a + mk3(s.dir[0], s.dir[1], s.dir[2]) * (bestT + margin);
+    const f3 ext = mk3(s.radius + margin, s.radius + s.hh + margin, s.radius + margin);
+    qlo = vmax(qlo, vmin(a, b) - ext); // (never wider than the whole sweep's box)
+    qhi = vmin(qhi, vmax(a, b) + ext);
+}
+// The triangle-level form: (a) best toi 0 with a tie on record and this triangle visited later than the best — it could
+// only tie behind it; (b) the capsule's axis at t = 0 is farther from the triangle's box than radius + bestT + margin.
+__device__ __forceinline__ bool sweep_cannot_matter(const QShared &s, float bestT, float margin, f3 tlo, f3 thi, int rank) {
+    if (bestT == 0.0f && (*(volatile const int *)&s.mode & CQ_QF_TIE) != 0 && rank > *(volatile const int *)&s.rRank) return true;
+    const float dx = smax(smax(tlo.x - s.from[0], s.from[0] - thi.x), 0.0f);
+    const float dz = smax(smax(tlo.z - s.from[2], s.from[2] - thi.z), 0.0f);
+    const float dy = smax(smax(tlo.y - (s.from[1] + s.hh), (s.from[1] - s.hh) - thi.y), 0.0f);
+    const float reach = s.radius + bestT + margin;
+    return dx * dx + dy * dy + dz * dz > reach * reach * 1.0001f;
+}
+
+template <bool COUNT, bool STAGED, bool LOOKAHEAD>
 __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPool &wp, int lane, Counters &ctr) {
     const uint32_t top = *wp.ntop;
     const uint32_t poppers = top > (uint32_t)CQ_NS_WIDE ? 1u : 32u; // nearly full: depth-first with one lane
@@ -237,7 +267,11 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
     if (have && !isLeaf) { // 4-wide internal node: test up to four children
         const int owner = e.x >> 2, set = (e.x >> 1) & 1;
         QShared &s = wp.qs[owner];
-        const f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
+        f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
+        if (LOOKAHEAD && CQ_PICKUP_DROP) {
+            float bestT, margin;
+            if (sweep_reach(s, bestT, margin)) sweep_reach_box(s, bestT, margin, qlo, qhi);
+        }
         int net = -1; // this entry is consumed
         const Node4 *n = (set ? W.set[1].nodes4 : W.set[0].nodes4) + e.y;
         float4 q0 = __ldg(&n->q[0]), q1 = __ldg(&n->q[1]), q2 = __ldg(&n->q[2]), q3 = __ldg(&n->q[3]);
@@ -318,6 +352,10 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
             f3 v0 = xyz(a), v1 = xyz(b), v2 = xyz(c);
             f3 tlo = vmin(v0, vmin(v1, v2)), thi = vmax(v0, vmax(v1, v2));
             if (box_disjoint(tlo, thi, qlo, qhi)) continue; // :1060-1065
+            if (LOOKAHEAD && CQ_PICKUP_DROP) {
+                float bestT, margin;
+                if (sweep_reach(s, bestT, margin) && sweep_cannot_matter(s, bestT, margin, tlo, thi, __float_as_int(c.w))) continue;
+            }
             if (COUNT) ctr.cands++;
             uint32_t pos = atomicAdd((uint32_t *)wp.tail, 1u);
             wp.ring[pos % CQ_QCAP] = item;
@@ -336,9 +374,6 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
 //      moves at unit speed, so no contact exists at or before bestT.
 // A lane that dropped its candidate takes another one (up to four pickups per trip), so that drops do not leave lanes idle
 // through the evaluation.  C2 (profiles/r2_ab_same_box.txt, call 11).
-#ifndef CQ_PICKUP_DROP
-#define CQ_PICKUP_DROP 1 /* 0: no drops at pickup (A/B) */
-#endif
 template <bool LOOKAHEAD_>
 __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPool &wp, Job &job, int lane) {
     constexpr bool LOOKAHEAD = LOOKAHEAD_ && CQ_PICKUP_DROP;
@@ -375,17 +410,10 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
                 const int mode = s.mode;
                 job.phase = (mode & 0xff) == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
                 if (LOOKAHEAD && job.phase == PH_ADV) {
-                    const float bestT = *(volatile const float *)&s.rT;
-                    if (bestT == 0.0f) dropped = (mode & CQ_QF_TIE) != 0 && job.rank > *(volatile const int *)&s.rRank;
-                    if (!dropped) {
-                        const f3 tlo = vmin(job.T.v0, vmin(job.T.v1, job.T.v2)), thi = vmax(job.T.v0, vmax(job.T.v1, job.T.v2));
-                        const float dx = smax(smax(tlo.x - job.from.x, job.from.x - thi.x), 0.0f);
-                        const float dz = smax(smax(tlo.z - job.from.z, job.from.z - thi.z), 0.0f);
-                        const float dy = smax(smax(tlo.y - (job.from.y + job.hh), (job.from.y - job.hh) - thi.y), 0.0f);
-                        const float reach = job.radius + bestT +
-                                            (1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f);
-                        dropped = dx * dx + dy * dy + dz * dz > reach * reach * 1.0001f;
-                    }
+                    float bestT, margin;
+                    if (sweep_reach(s, bestT, margin))
+                        dropped = sweep_cannot_matter(s, bestT, margin, vmin(job.T.v0, vmin(job.T.v1, job.T.v2)),
+                                                      vmax(job.T.v0, vmax(job.T.v1, job.T.v2)), job.rank);
                     if (dropped) {
                         job.phase = PH_NONE;
                         atomicSub(&s.pending, 1);
@@ -712,7 +740,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
             __syncwarp();
             // cooperative walk: rounds until the ring holds ~3 trips of work (or the stack is empty)
             while (*wp.ntop != 0u && *wp.tail - *wp.head < 96u && *wp.tail - *wp.head + 128u <= (uint32_t)CQ_QCAP)
-                pool_walk_round<COUNT, STAGED>(W, wp, lane, ctr);
+                pool_walk_round<COUNT, STAGED, LOOKAHEAD>(W, wp, lane, ctr);
         }
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
         pool_take_jobs<LOOKAHEAD>(W, wp, job, lane);

@@ -16,7 +16,9 @@
 // The world casts inside a turn (SYS:1994-2033) and the per-agent slide + ground snap afterwards (SYS:2043-2117) run on
 // the warp-cooperative pair pool (cq_pool.cuh), like every other capsule query of the library.
 #include "cq_pool.cuh"
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "cq_internal.h"
 
@@ -202,6 +204,24 @@ __global__ void k_sep_round_end(int *qcount, int *flags, int *work) { // the con
     flags[1] += *qcount;
     *qcount = 0;
     *work = 0;
+}
+
+// The same inside the CUDA-graph WHILE node that runs the rounds of a sweep on the device (sep_rounds_graph below).  The
+// body of the loop holds two rounds (the queues swap roles); its last node decides whether the body runs again: turns
+// remain, no agent drifted out of the safety radius, and the pass retired at least one turn.
+// flags: [0] drift violation, [1] processed turns, [2] processed at the end of the previous pass, [3] stalled, [4] rounds
+__global__ void k_sep_round_end_dev(int *qcount, int *flags, int *work, int n, int last, cudaGraphConditionalHandle loop) {
+    flags[1] += *qcount;
+    flags[4] += 1;
+    *qcount = 0;
+    *work = 0;
+    if (last) {
+        const int processed = flags[1];
+        int go = processed < n && !flags[0];
+        if (go && processed == flags[2]) flags[3] = 1, go = 0;
+        flags[2] = processed;
+        cudaGraphSetConditional(loop, go ? 1u : 0u);
+    }
 }
 
 // ---------------------------------------------------------------- turns (AgentSeparationResolver.resolve, SYS:1946-2041)
@@ -625,6 +645,120 @@ static int sep_grid_blocks(cq_world *w, const void *kernel, size_t smem, int &ca
     return w->numSms * cache;
 }
 
+// The rounds of one sweep as ONE graph launch: a WHILE node whose body is two rounds (turns -> release -> round end, with
+// the queues in either role); k_sep_round_end_dev sets the loop condition, so the host neither launches rounds nor reads
+// progress back while the schedule runs (round 1 read it back every 8 rounds).  Instantiated graphs are kept per world,
+// keyed by every launch parameter (the node-scratch block rotates over four buffers, hence a few entries).
+struct SepGraph {
+    std::vector<unsigned char> key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t used = 0;
+};
+struct SepGraphCache {
+    std::vector<SepGraph> items;
+    uint64_t tick = 0;
+};
+
+void sep_graphs_destroy(cq_world *w) {
+    SepGraphCache *c = (SepGraphCache *)w->sepGraphs;
+    if (!c) return;
+    for (SepGraph &g : c->items) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    delete c;
+    w->sepGraphs = nullptr;
+}
+
+struct SepRoundsLaunch {
+    const void *turnKernel;
+    int turnBlocks, releaseBlocks;
+    size_t turnSmem;
+    WorldView view;
+    SepArgs A; // queue / qcount are filled per half
+    uint2 *ns;
+    int *work;
+    unsigned long long *counters;
+    int *queue[2], *qcount;
+    const uint32_t *keys, *vals;
+    const int2 *cell0;
+    const SepGridParams *gp;
+    int n, D;
+    int *cnt, *flags;
+};
+
+static int sep_rounds_graph(cq_world *w, SepRoundsLaunch &L, cudaGraphExec_t *out) {
+    if (!w->sepGraphs) w->sepGraphs = new SepGraphCache();
+    SepGraphCache &cache = *(SepGraphCache *)w->sepGraphs;
+    L.A.queue = nullptr, L.A.qcount = nullptr;
+    std::vector<unsigned char> key(sizeof(L));
+    memcpy(key.data(), &L, sizeof(L)); // (L is memset before it is filled: padding compares equal)
+    for (SepGraph &g : cache.items)
+        if (g.key == key) {
+            g.used = ++cache.tick;
+            *out = g.exec;
+            return CQ_OK;
+        }
+    if (cache.items.size() >= 8) { // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < cache.items.size(); i++)
+            if (cache.items[i].used < cache.items[lru].used) lru = i;
+        cudaGraphExecDestroy(cache.items[lru].exec);
+        cudaGraphDestroy(cache.items[lru].graph);
+        cache.items.erase(cache.items.begin() + lru);
+    }
+    SepGraph g;
+    g.key = key;
+    CQ_CUDA(cudaGraphCreate(&g.graph, 0));
+    cudaGraphConditionalHandle loop;
+    CQ_CUDA(cudaGraphConditionalHandleCreate(&loop, g.graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = loop;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t whileNode;
+    CQ_CUDA(cudaGraphAddNode(&whileNode, g.graph, nullptr, 0, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    cudaGraphNode_t prev = nullptr;
+    for (int half = 0; half < 2; half++) {
+        int *q = L.queue[half], *qn = L.queue[half ^ 1];
+        int *qc = L.qcount + half, *qcn = L.qcount + (half ^ 1);
+        SepArgs A = L.A;
+        A.queue = q, A.qcount = qc;
+        cudaGraphNode_t node;
+        cudaKernelNodeParams kp = {};
+        void *turnArgs[] = {(void *)&L.view, (void *)&A, (void *)&L.ns, (void *)&L.work, (void *)&L.counters};
+        kp.func = (void *)L.turnKernel;
+        kp.gridDim = dim3(L.turnBlocks), kp.blockDim = dim3(SEP_THREADS);
+        kp.sharedMemBytes = (unsigned)L.turnSmem;
+        kp.kernelParams = turnArgs;
+        CQ_CUDA(cudaGraphAddKernelNode(&node, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
+        prev = node;
+        void *relArgs[] = {(void *)&q, (void *)&qc, (void *)&L.keys, (void *)&L.vals, (void *)&L.cell0, (void *)&L.gp,
+                           (void *)&L.n, (void *)&L.D, (void *)&L.cnt, (void *)&qn, (void *)&qcn};
+        kp = cudaKernelNodeParams{};
+        kp.func = (void *)k_sep_release;
+        kp.gridDim = dim3(L.releaseBlocks), kp.blockDim = dim3(256);
+        kp.kernelParams = relArgs;
+        CQ_CUDA(cudaGraphAddKernelNode(&node, body, &prev, 1, &kp));
+        prev = node;
+        int last = half;
+        void *endArgs[] = {(void *)&qc, (void *)&L.flags, (void *)&L.work, (void *)&L.n, (void *)&last, (void *)&loop};
+        kp = cudaKernelNodeParams{};
+        kp.func = (void *)k_sep_round_end_dev;
+        kp.gridDim = dim3(1), kp.blockDim = dim3(1);
+        kp.kernelParams = endArgs;
+        CQ_CUDA(cudaGraphAddKernelNode(&node, body, &prev, 1, &kp));
+        prev = node;
+    }
+    CQ_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+    g.used = ++cache.tick;
+    cache.items.push_back(g);
+    *out = g.exec;
+    return CQ_OK;
+}
+
 int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, const cq_controller_params &p,
                             const float *d_massWeight, int iterations, float sepMargin, float heightMargin, int useQuery,
                             cudaStream_t st) {
@@ -671,6 +805,9 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
     A.useQuery = useQuery, A.n = n;
     A.pos = pos, A.vel = vel, A.cell0 = cell0, A.keys = keys, A.sidx = vals, A.rows = rows, A.gp = gp, A.flags = flags;
 
+    // CQ_SEP_HOST_ROUNDS=1: launch the rounds from the host, progress read back every 8 rounds (the round-1 schedule; A/B)
+    const char *hr = getenv("CQ_SEP_HOST_ROUNDS");
+    const bool hostRounds = hr && hr[0] == '1';
     for (int it = 0; it < iterations; it++) {
         // grid.rebuild(agents) (SYS:1931-1937): cells of the CURRENT positions; a stable sort keeps each cell's list in
         // ascending agent index = the reference's append order
@@ -692,8 +829,19 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
             CQ_CUDA(cudaMemsetAsync(qcount, 0, sizeof(int) * 3, st)); // both queue counters + the work counter
             k_sep_count_blockers<<<cdiv(n, 256), 256, 0, st>>>(keys, vals, cell0, gp, n, D, cnt, queueA, qcount);
             w->launches++;
+            if (!hostRounds) { // the rounds run as a device-side loop
+                SepRoundsLaunch L;
+                memset(&L, 0, sizeof(L));
+                L.turnKernel = turnKernel, L.turnBlocks = turnBlocks, L.releaseBlocks = std::min(cdiv(n, 64), 148 * 8);
+                L.turnSmem = turnSmem, L.view = w->view, L.A = A, L.ns = ns, L.work = work, L.counters = w->dCounters;
+                L.queue[0] = queueA, L.queue[1] = queueB, L.qcount = qcount;
+                L.keys = keys, L.vals = vals, L.cell0 = cell0, L.gp = gp, L.n = n, L.D = D, L.cnt = cnt, L.flags = flags;
+                cudaGraphExec_t exec = nullptr;
+                CQ_TRY(sep_rounds_graph(w, L, &exec));
+                CQ_CUDA(cudaGraphLaunch(exec, st));
+            }
             int processed = 0, lastProcessed = -1, round = 0;
-            while (processed < n) {
+            while (hostRounds && processed < n) {
                 for (int k = 0; k < 8; k++, round++) {
                     int *q = (round & 1) ? queueB : queueA, *qn = (round & 1) ? queueA : queueB;
                     int *qc = qcount + (round & 1), *qcn = qcount + ((round & 1) ^ 1);
@@ -715,10 +863,18 @@ int launch_agent_separation(cq_world *w, cq_character_state *d_inout, int n, con
                 }
                 lastProcessed = processed;
             }
-            int hostFlag = 0, gridErr = 0;
-            CQ_CUDA(cudaMemcpyAsync(&hostFlag, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+            int hostFlags[5] = {0, 0, 0, 0, 0}, gridErr = 0;
+            CQ_CUDA(cudaMemcpyAsync(hostFlags, flags, sizeof(hostFlags), cudaMemcpyDeviceToHost, st));
             CQ_CUDA(cudaMemcpyAsync(&gridErr, &gp->err, sizeof(int), cudaMemcpyDeviceToHost, st));
             CQ_CUDA(cudaStreamSynchronize(st));
+            const int hostFlag = hostFlags[0];
+            if (!hostRounds) {
+                w->launches += 3 * (uint64_t)hostFlags[4];
+                if (!hostFlag && !gridErr && hostFlags[3]) {
+                    set_error("cq_agent_separation: the turn schedule stalled at %d of %d agents", hostFlags[1], n);
+                    return CQ_ERR_CUDA;
+                }
+            }
             if (gridErr) {
                 set_error("cq_agent_separation: the crowd spans more than 2^31 grid cells of %.3f m", cellSize);
                 return CQ_ERR_INVALID;
