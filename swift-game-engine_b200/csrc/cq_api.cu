@@ -42,8 +42,9 @@ int check_status(cq_world *w, const char *what) {
     const unsigned int v = *(volatile unsigned int *)w->hStatus;
     if (v == 0) return CQ_OK;
     *(volatile unsigned int *)w->hStatus = 0;
-    set_error("%s: device status 0x%x (%s%s): results of the call are incomplete", what, v,
-              (v & 1u) ? "traversal stack overflow " : "", (v & 2u) ? "sort look-back watchdog fired" : "");
+    set_error("%s: device status 0x%x (%s%s%s): results of the call are incomplete", what, v,
+              (v & 1u) ? "traversal stack overflow " : "", (v & 2u) ? "sort look-back watchdog fired " : "",
+              (v & 4u) ? "pair-pool watchdog fired" : "");
     return CQ_ERR_CUDA;
 }
 

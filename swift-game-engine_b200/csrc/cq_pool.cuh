@@ -80,15 +80,18 @@ struct QResult { // what owner logic reads back
 };
 
 struct Job { // executor-side pair state (registers)
-    int phase, owner;
+    // Everything here stays live across the distance function, whose own working set fills the register file: values
+    // that are only needed between evaluations (|delta|, minAdvance, maxIter) are re-read from the owner's QShared, and
+    // the phases share slots — round 2's terrain capture showed 11% of the stall samples on reloads of spilled pair state
+    // that the node / triangle traffic had evicted from L1 (profiles/r2_by_region.txt).
+    int phase;
     uint32_t enc; // ring entry (owner | set | slot): lets an owner reload a winning triangle later
-    f3 from, dir;
-    float L, radius, hh, minAdvance;
-    int maxIter;
+    float radius, hh;
     Tri T;
-    int gid, rank; // global triangle index; visiting rank (tv2.w)
-    float t, lastSafeT, lo, hi;
-    int it, k;
+    int gid, rank;      // global triangle index; visiting rank (tv2.w)
+    float t, lastSafeT; // PH_ADV: conservative advancement.  PH_BIS / PH_FIN: refineTOI's hi (in t) and lo (in lastSafeT)
+    int it;             // PH_ADV: iterations done.  PH_BIS: bisection steps done
+    __device__ __forceinline__ int owner() const { return (int)(enc >> 27); }
 };
 
 struct Commit { // a finished pair's contribution, applied in the serialized commit step
@@ -103,6 +106,7 @@ struct WarpPool { // per-warp handles
     volatile uint32_t *head; // pairs consumed      shared
     volatile uint32_t *tail; // pairs produced      shared
     volatile uint32_t *ntop; // node-stack height   shared
+    volatile uint32_t *fePasses; // front-end passes of this launch (watchdog)   shared
     uint2 *nstack;           // [CQ_NSCAP] (owner<<2 | set<<1 | isLeaf, ref)   global (L2 resident)
     uint32_t *stage;         // [CQ_STAGE] triangles of the leaf ranges popped in this walk round   shared
     const int32_t *rank;     // visiting rank per global triangle index (reference order) or nullptr (rank = index)
@@ -111,7 +115,7 @@ struct WarpPool { // per-warp handles
 
 __device__ __forceinline__ int pool_rank(const int32_t *rank, int gid) { return rank ? __ldg(rank + gid) : gid; }
 #define CQ_STAGE 128 /* 32 leaf ranges x <= 4 triangles */
-#define CQ_POOL_WORDS (CQ_QCAP + 3 + CQ_STAGE) /* shared words per warp besides QShared */
+#define CQ_POOL_WORDS (CQ_QCAP + 4 + CQ_STAGE) /* shared words per warp besides QShared */
 
 __device__ __forceinline__ void pool_bind(WarpPool &wp, QShared *qsAll, uint32_t *words, uint2 *nodeScratch, int warp,
                                           int warpsPerBlock, const int32_t *rank, unsigned int *status) {
@@ -120,7 +124,8 @@ __device__ __forceinline__ void pool_bind(WarpPool &wp, QShared *qsAll, uint32_t
     wp.head = wp.ring + CQ_QCAP;
     wp.tail = wp.ring + CQ_QCAP + 1;
     wp.ntop = wp.ring + CQ_QCAP + 2;
-    wp.stage = wp.ring + CQ_QCAP + 3;
+    wp.fePasses = wp.ring + CQ_QCAP + 3;
+    wp.stage = wp.ring + CQ_QCAP + 4;
     wp.nstack = nodeScratch + ((size_t)blockIdx.x * warpsPerBlock + warp) * CQ_NSCAP;
     wp.rank = rank;
     wp.status = status;
@@ -388,15 +393,9 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
                 uint32_t e = wp.ring[(h + rank) % CQ_QCAP];
                 int owner = e >> 27, set = (e >> 26) & 1, slot = e & 0x3ffffffu;
                 QShared &s = wp.qs[owner];
-                job.owner = owner;
                 job.enc = e;
-                job.from = mk3(s.from[0], s.from[1], s.from[2]);
-                job.dir = mk3(s.dir[0], s.dir[1], s.dir[2]);
-                job.L = s.L;
                 job.radius = s.radius;
                 job.hh = s.hh;
-                job.minAdvance = s.minAdvance;
-                job.maxIter = s.maxIter;
                 const float4 *p0 = set ? W.set[1].tv0 : W.set[0].tv0;
                 const float4 *p1 = set ? W.set[1].tv1 : W.set[0].tv1;
                 const float4 *p2 = set ? W.set[1].tv2 : W.set[0].tv2;
@@ -438,9 +437,11 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
 template <bool COUNT, bool LOOKAHEAD>
 __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &cm, bool &retired, Counters &ctr) {
     const int ph = job.phase;
-    const QShared &s = wp.qs[job.owner];
-    float tc = ph == PH_ADV ? job.t : (ph == PH_BIS ? 0.5f * (job.lo + job.hi) : job.hi);
-    f3 center = ph == PH_OVL ? job.from : job.from + job.dir * tc;
+    const QShared &s = wp.qs[job.owner()];
+    float &hi = job.t, &lo = job.lastSafeT; // (slots shared between the phases, see Job)
+    float tc = ph == PH_ADV ? job.t : (ph == PH_BIS ? 0.5f * (lo + hi) : hi);
+    f3 center = mk3(s.from[0], s.from[1], s.from[2]);
+    if (ph != PH_OVL) center = center + mk3(s.dir[0], s.dir[1], s.dir[2]) * tc;
     f3 sp, tp;
     if (COUNT) ctr.evals++;
     float dist = segment_triangle_distance<true>(center, job.hh, job.T, sp, tp);
@@ -456,21 +457,23 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
     };
     if (ph == PH_ADV) { // sweepCapsuleTriangle loop body, CollisionQuery.swift:1303-1356
         if (dist <= job.radius + 1e-5f) {
-            float c0 = smax(0.0f, smin(job.lastSafeT, job.L)); // refineTOI prologue, :1371-1377
-            float c1 = smax(0.0f, smin(job.t, job.L));
-            job.lo = smin(c0, c1);
-            job.hi = smax(c0, c1);
-            const bool fin = job.hi - job.lo < 1e-5f;
-            job.k = 0;
-            if (hopeless(fin ? job.hi : job.lo)) retired = true;
+            const float L = s.L;
+            float c0 = smax(0.0f, smin(job.lastSafeT, L)); // refineTOI prologue, :1371-1377
+            float c1 = smax(0.0f, smin(job.t, L));
+            lo = smin(c0, c1);
+            hi = smax(c0, c1);
+            const bool fin = hi - lo < 1e-5f;
+            job.it = 0; // (now the bisection counter)
+            if (hopeless(fin ? hi : lo)) retired = true;
             else job.phase = fin ? PH_FIN : PH_BIS;
         } else {
             job.lastSafeT = job.t;
-            float advance = smax(dist - job.radius, job.minAdvance);
-            job.t += advance <= 0.0f ? job.minAdvance : advance;
+            const float minAdvance = s.minAdvance, L = s.L;
+            float advance = smax(dist - job.radius, minAdvance);
+            job.t += advance <= 0.0f ? minAdvance : advance;
             job.it++;
             // next trip: `for _ in 0..<maxIter { if t > maxDistance return nil ...`; prune: toi >= lastSafeT > bestT
-            if (job.it >= job.maxIter || job.t > job.L || job.lastSafeT > bestT) retired = true;
+            if (job.it >= s.maxIter || job.t > L || job.lastSafeT > bestT) retired = true;
             // Look-ahead prune (exact-safe): this was a true conservative-advancement step (advance = dist - r, not the
             // minAdvance floor) and it lands beyond bestT by more than `margin`.  The capsule moves at unit speed, so
             // the distance at any t <= bestT is at least dist - (t - lastSafeT) > r + margin: if the NEXT evaluation
@@ -478,25 +481,25 @@ __device__ __forceinline__ void pool_eval(Job &job, const WarpPool &wp, Commit &
             // (margin covers the float error of positions and distances), the refined toi ends beyond bestT and the
             // hit is rejected by `toi < bestT` (:1084); contacts found later have lastSafeT > bestT anyway.
             // margin: float error of positions and distances at this query's scale (1 mm + 8e-6 of the coordinates' size)
-            else if (LOOKAHEAD && dist - job.radius >= job.minAdvance &&
-                     job.t > bestT + (1e-3f + (fabsf(job.from.x) + fabsf(job.from.y) + fabsf(job.from.z) + job.L) * 8e-6f))
+            else if (LOOKAHEAD && dist - job.radius >= minAdvance &&
+                     job.t > bestT + (1e-3f + (fabsf(s.from[0]) + fabsf(s.from[1]) + fabsf(s.from[2]) + L) * 8e-6f))
                 retired = true;
         }
     } else if (ph == PH_BIS) { // refineTOI bisection, :1379-1392 (threshold is radius, not radius+eps)
-        if (dist <= job.radius) job.hi = tc;
-        else job.lo = tc;
-        job.k++;
-        if (job.k == 10) {
-            if (hopeless(job.hi)) retired = true;
+        if (dist <= job.radius) hi = tc;
+        else lo = tc;
+        job.it++;
+        if (job.it == 10) {
+            if (hopeless(hi)) retired = true;
             else job.phase = PH_FIN;
-        } else if (job.lo > bestT) {
+        } else if (lo > bestT) {
             retired = true;
         }
     } else if (ph == PH_FIN) { // contact at tHit = hi, :1325-1346; acceptance filters of :1087-1097
         retired = true;
         f3 triNormal = normalize(cross(job.T.v1 - job.T.v0, job.T.v2 - job.T.v0));
         f3 n;
-        if (dist < 1e-6f) n = dot(triNormal, job.dir) > 0.0f ? -triNormal : triNormal;
+        if (dist < 1e-6f) n = dot(triNormal, mk3(s.dir[0], s.dir[1], s.dir[2])) > 0.0f ? -triNormal : triNormal;
         else n = normalize(sp - tp);
         f3 triN = triNormal;
         if (dot(triN, n) < 0.0f) triN = -triN;
@@ -624,9 +627,9 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
     const uint32_t retMask = __ballot_sync(0xffffffffu, retired);
     if (retMask == 0u) return; // (warp-uniform) nothing finished this trip
     bool cast = retired && cm.kind == 1;
-    if (cast) cast = !(cm.key > *(volatile const float *)&wp.qs[job.owner].rT);
+    if (cast) cast = !(cm.key > *(volatile const float *)&wp.qs[job.owner()].rT);
     const uint32_t below = (1u << lane) - 1u;
-    const uint32_t sameOwner = retired ? __match_any_sync(retMask, job.owner) : 0u; // the finishing lanes of my owner
+    const uint32_t sameOwner = retired ? __match_any_sync(retMask, job.owner()) : 0u; // the finishing lanes of my owner
     bool mine = retired && cm.kind == 2;
     if (REDUCE) {
         const uint32_t castMask = __ballot_sync(0xffffffffu, cast);
@@ -637,7 +640,7 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
             const uint32_t rmin = __reduce_min_sync(grp, atMin ? (uint32_t)job.rank : 0xffffffffu);
             const bool tiedInGroup = __popc(__ballot_sync(grp, atMin)) > 1;
             if (atMin && (uint32_t)job.rank == rmin) {
-                QShared &s = wp.qs[job.owner];
+                QShared &s = wp.qs[job.owner()];
                 const float bestT = s.rT;
                 const bool better = cm.key < bestT;
                 const bool tie = s.rTri >= 0 && cm.key == bestT; // exactly equal toi: the reference keeps the first it visited
@@ -666,7 +669,7 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
 #pragma unroll 1
     for (int round = 0; __any_sync(0xffffffffu, mine && myRound >= round); round++) {
         if (mine && myRound == round) {
-            QShared &s = wp.qs[job.owner];
+            QShared &s = wp.qs[job.owner()];
             if (!REDUCE && cm.kind == 1) {
                 float bestT = s.rT;
                 int bestTri = s.rTri;
@@ -690,7 +693,7 @@ __device__ __forceinline__ void pool_commit(const WarpPool &wp, Job &job, const 
         __syncwarp();
     }
     if (retired) {
-        if ((sameOwner & below) == 0u) atomicSub(&wp.qs[job.owner].pending, __popc(sameOwner)); // one lane per owner
+        if ((sameOwner & below) == 0u) atomicSub(&wp.qs[job.owner()].pending, __popc(sameOwner)); // one lane per owner
         job.phase = PH_NONE;
     }
     __syncwarp();
@@ -712,12 +715,13 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         *wp.head = 0;
         *wp.tail = 0;
         *wp.ntop = 0;
+        *wp.fePasses = 0;
     }
     Job job;
     job.phase = PH_NONE;
     bool alive = lane < ownersPerWarp;
     __syncwarp();
-    for (uint32_t trip = 0; trip < (1u << 26); trip++) { // (the bound is a watchdog; the loop exits through the vote)
+    for (;;) { // (exits through the vote at the bottom, or through the watchdog on the front-end passes)
         // The front end (owners' unit logic + walk rounds) runs only when the pair ring has run dry AND at least FE_IDLE
         // lanes have nothing to execute: the divergent unit logic then runs for many owners at once, and — what matters
         // most on small scenes — its ~40 KB of code passes through the instruction caches far less often, evicting the
@@ -725,6 +729,16 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
         // 16; terrain +4%; C4 +1.6% with 8 but -2% with 16; the candidate-heavy render mesh loses 3% either way).
         const uint32_t idleNow = (uint32_t)__popc(__ballot_sync(0xffffffffu, job.phase == PH_NONE));
         if (*wp.tail == *wp.head && idleNow >= (uint32_t)FE_IDLE) {
+            // Watchdog.  Every pair retires within maxIter + 12 trips and the ring only drains between front-end passes, so a
+            // loop that does not end must keep coming through here; counted in shared memory (a counter in a register would
+            // be one more value kept alive across the distance function, i.e. one more spill).
+            const uint32_t passes = *wp.fePasses;
+            if (passes > (1u << 24)) {
+                if (lane == 0) atomicOr(wp.status, 4u);
+                break;
+            }
+            __syncwarp();
+            if (lane == 0) *wp.fePasses = passes + 1u;
             // The owners' logic runs only when enough owners are ready (or nothing at all is left to execute), so that the
             // divergent front end serves many owners per pass.  Measured on one box (profiles/r2_ab_same_box.txt, call 7):
             // with 24 of 32 the render-mesh step (heavy queries, owners rarely ready together) gains 23% (21.98 -> 17.88 ms),
