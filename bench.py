@@ -416,7 +416,7 @@ def measure_mas(ctx, args, mesh, n, steps, warmup, cpu_baseline=True, clocks=Tru
 
     # algorithmic bytes of exactly these K steps: replay them from the snapshot with the counting build
     d_states.copy_(snapshot)
-    world.set_counting(True)
+    world.set_counting(cq.COUNT_PATH)
     world.resetStats()
     for _ in range(steps):
         step_device()
@@ -596,7 +596,7 @@ def measure_c4(ctx, args, n_total, steps, warmup, sharded):
         kernel_ms = time_steps(ctx, only_cast, steps, 1)[0] / steps
         mine = d_all[lo * rec:hi * rec]
         assert bool(torch.equal(mine, d_out)), "gathered records differ from the local shard"
-    world.set_counting(True)
+    world.set_counting(cq.COUNT_PATH)
     world.resetStats()
     world.capsule_cast_device(d_q.data_ptr(), n, cq.CAST_BLOCKING, d_out.data_ptr(), stream)
     torch.cuda.synchronize()
@@ -688,7 +688,7 @@ def measure_c2(ctx, args, n, steps, warmup):
     clk = sampler.stop()
     launches = world.stats()["kernel_launches"]
     ms = total_ms / steps
-    world.set_counting(True)
+    world.set_counting(cq.COUNT_PATH)
     world.resetStats()
     step()
     torch.cuda.synchronize()
@@ -800,7 +800,7 @@ def measure_c5(ctx, args, n_total, steps, warmup, sharded):
     e1.record()
     torch.cuda.synchronize()
     ray_ms = e0.elapsed_time(e1)
-    world.set_counting(True)
+    world.set_counting(cq.COUNT_PATH)
     world.resetStats()
     world.raycast_device(d_r.data_ptr(), n, d_out.data_ptr(), stream)
     torch.cuda.synchronize()

@@ -451,7 +451,15 @@ typedef struct cq_counters {
     uint64_t distance_evals;   /* segmentTriangleDistance evaluations actually executed */
     uint64_t kernel_launches;  /* kernels launched by this library since the last reset */
 } cq_counters;
-int cq_world_set_counting(cq_world *w, int32_t enabled);
+/* mode: CQ_COUNT_OFF; CQ_COUNT_REFERENCE — `candidates` equals the reference's capsuleCandidateCount (a counting launch
+ * then queues every candidate of the whole sweep's box, as the reference does; results are the same, the launch is slower);
+ * CQ_COUNT_PATH — the counters of the path as shipped: sweeps that already hold a hit cull nodes and triangles against the
+ * box of the capsule swept to that hit and drop candidates that cannot matter before evaluating them, so `nodes_visited`,
+ * `candidates` and `distance_evals` are what the kernel really touched (bench.py's roofline figures use this mode). */
+#define CQ_COUNT_OFF 0
+#define CQ_COUNT_REFERENCE 1
+#define CQ_COUNT_PATH 2
+int cq_world_set_counting(cq_world *w, int32_t mode);
 int cq_world_read_counters(cq_world *w, cq_counters *out, int32_t reset);
 
 /* pinned host memory for the batch calls (optional; plain malloc'ed memory works too) */

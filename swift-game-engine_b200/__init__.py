@@ -76,6 +76,7 @@ class WorldOptions(C.Structure):
 
 
 ORDER_REFERENCE, ORDER_CANONICAL = 0, 1  # include/cq.h: which of several exactly equal candidates a query names
+COUNT_OFF, COUNT_REFERENCE, COUNT_PATH = 0, 1, 2  # include/cq.h: cq_world_set_counting modes
 HIT_TIE, HIT_OVERFLOW = 1, 2
 
 
@@ -484,8 +485,10 @@ class CollisionQuery:
                                        C.c_void_p(stream) if stream else None))
 
     # CollisionQuery.stats / resetStats (CollisionQuery.swift:61-67)
-    def set_counting(self, enabled):
-        _check(lib().cq_world_set_counting(self._h, int(bool(enabled))))
+    def set_counting(self, mode):
+        """False / COUNT_OFF; True / COUNT_REFERENCE: `candidates` equals the reference's capsuleCandidateCount;
+        COUNT_PATH: the counters of the path as shipped (bestT-based culling active) — see cq.h."""
+        _check(lib().cq_world_set_counting(self._h, int(mode)))
 
     def stats(self, reset=False):
         c = Counters()

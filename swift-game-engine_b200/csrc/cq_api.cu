@@ -120,6 +120,7 @@ static void make_view(cq_world *w) {
     w->view.materials = w->dMaterials;
     w->view.nParts = (int)w->parts.size();
     w->view.stagedLeaves = (w->set[0].nTris + w->set[1].nTris) >= 4096 ? 1 : 0;
+    w->view.refStats = w->countRef;
 }
 
 } // namespace cq
@@ -490,9 +491,11 @@ int cq_world_triangle_material(const cq_world *w, int32_t triangle_index, cq_mat
     return CQ_OK;
 }
 
-int cq_world_set_counting(cq_world *w, int32_t enabled) {
-    if (!w) return CQ_ERR_INVALID;
-    w->counting = enabled ? 1 : 0;
+int cq_world_set_counting(cq_world *w, int32_t mode) {
+    if (!w || mode < CQ_COUNT_OFF || mode > CQ_COUNT_PATH) return CQ_ERR_INVALID;
+    w->counting = mode != CQ_COUNT_OFF ? 1 : 0;
+    w->countRef = mode == CQ_COUNT_REFERENCE ? 1 : 0;
+    w->view.refStats = w->countRef;
     return CQ_OK;
 }
 

@@ -96,6 +96,7 @@ struct cq_world {
     cq::WorldView view;
     float buildMs = 0, refitMs = 0;
     int counting = 0;
+    int countRef = 0; // counting mode CQ_COUNT_REFERENCE
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
     int occ[6][4] = {}; // (raycast: [counting + 2 * reference-order walker]) // resident CTAs per SM of each persistent kernel ([counting + 2 * staged-walk variant])
     int numSms = 0;

@@ -273,7 +273,7 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
         const int owner = e.x >> 2, set = (e.x >> 1) & 1;
         QShared &s = wp.qs[owner];
         f3 qlo = mk3(s.qlo[0], s.qlo[1], s.qlo[2]), qhi = mk3(s.qhi[0], s.qhi[1], s.qhi[2]);
-        if (LOOKAHEAD && CQ_PICKUP_DROP) {
+        if (LOOKAHEAD && CQ_PICKUP_DROP && !(COUNT && W.refStats)) {
             float bestT, margin;
             if (sweep_reach(s, bestT, margin)) sweep_reach_box(s, bestT, margin, qlo, qhi);
         }
@@ -357,7 +357,7 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
             f3 v0 = xyz(a), v1 = xyz(b), v2 = xyz(c);
             f3 tlo = vmin(v0, vmin(v1, v2)), thi = vmax(v0, vmax(v1, v2));
             if (box_disjoint(tlo, thi, qlo, qhi)) continue; // :1060-1065
-            if (LOOKAHEAD && CQ_PICKUP_DROP) {
+            if (LOOKAHEAD && CQ_PICKUP_DROP && !(COUNT && W.refStats)) {
                 float bestT, margin;
                 if (sweep_reach(s, bestT, margin) && sweep_cannot_matter(s, bestT, margin, tlo, thi, __float_as_int(c.w))) continue;
             }
@@ -379,11 +379,14 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
 //      moves at unit speed, so no contact exists at or before bestT.
 // A lane that dropped its candidate takes another one (up to four pickups per trip), so that drops do not leave lanes idle
 // through the evaluation.  C2 (profiles/r2_ab_same_box.txt, call 11).
-template <bool LOOKAHEAD_>
-__device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPool &wp, Job &job, int lane) {
+// OVLDROP (the staged-walk move-and-slide kernel): an overlap candidate is dropped when the kernel's bookkeeping says it cannot
+// matter (OverlapTop2::cannot_matter: reference order, eight overlaps on record, this triangle visited after all of them).
+template <bool COUNT, bool LOOKAHEAD_, bool OVLDROP_, class OvlCommit>
+__device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPool &wp, Job &job, int lane, const OvlCommit &ovl) {
     constexpr bool LOOKAHEAD = LOOKAHEAD_ && CQ_PICKUP_DROP;
+    constexpr bool OVLDROP = OVLDROP_ && CQ_PICKUP_DROP;
 #pragma unroll 1
-    for (int rep = 0; rep < (LOOKAHEAD ? 4 : 1); rep++) {
+    for (int rep = 0; rep < (LOOKAHEAD || OVLDROP ? 4 : 1); rep++) {
         uint32_t idle = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
         uint32_t h = *wp.head, avail = *wp.tail - h;
         bool dropped = false;
@@ -408,21 +411,22 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
                 job.it = 0;
                 const int mode = s.mode;
                 job.phase = (mode & 0xff) == CQ_KIND_OVERLAP ? PH_OVL : PH_ADV;
-                if (LOOKAHEAD && job.phase == PH_ADV) {
+                if (LOOKAHEAD && job.phase == PH_ADV && !(COUNT && W.refStats)) {
                     float bestT, margin;
                     if (sweep_reach(s, bestT, margin))
                         dropped = sweep_cannot_matter(s, bestT, margin, vmin(job.T.v0, vmin(job.T.v1, job.T.v2)),
                                                       vmax(job.T.v0, vmax(job.T.v1, job.T.v2)), job.rank);
-                    if (dropped) {
-                        job.phase = PH_NONE;
-                        atomicSub(&s.pending, 1);
-                    }
+                }
+                if (OVLDROP && job.phase == PH_OVL) dropped = ovl.cannot_matter(s, job.rank);
+                if ((LOOKAHEAD || OVLDROP) && dropped) {
+                    job.phase = PH_NONE;
+                    atomicSub(&s.pending, 1);
                 }
             }
         }
         __syncwarp();
         if (lane == 0) *wp.head = h + min((uint32_t)__popc(idle), avail);
-        if (!LOOKAHEAD) break;
+        if (!LOOKAHEAD && !OVLDROP) break;
         __syncwarp();
         if (!__any_sync(0xffffffffu, dropped) || (uint32_t)__popc(idle) >= avail) break; // nobody freed a lane / ring is empty
     }
@@ -581,6 +585,14 @@ static __device__ __noinline__ void overlap_top2_commit(QShared &s, float depth,
 }
 struct OverlapTop2 {
     bool byRank;
+    // Reference order, eight overlaps on record: a triangle the reference visits after all eight cannot be among the first
+    // eight, whether it overlaps or not.  (The count then stays short of the true total, but not below eight, and whenever
+    // it is exactly eight the two deepest seen are the two deepest of exactly those eight.)
+    __device__ __forceinline__ bool cannot_matter(QShared &s, int rk) const {
+        if (!byRank) return false;
+        const volatile int *ov = ovl_words(s);
+        return ov[OVL_TOTAL] >= CQ_MAX_OVERLAP_HITS && rk > ov[OVL_MAXRANK];
+    }
     __device__ __forceinline__ void operator()(QShared &s, float depth, int gid, int rk, uint32_t, f3 n) const {
         overlap_top2_commit(s, depth, gid, rk, n, byRank);
     }
@@ -757,7 +769,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
                 pool_walk_round<COUNT, STAGED, LOOKAHEAD>(W, wp, lane, ctr);
         }
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
-        pool_take_jobs<LOOKAHEAD>(W, wp, job, lane);
+        pool_take_jobs<COUNT, LOOKAHEAD, STAGED && FE_IDLE >= 16>(W, wp, job, lane, ovl);
         Commit cm;
         cm.kind = 0;
         bool retired = false;

@@ -622,6 +622,7 @@ struct OvlTop {
 struct OverlapTopK {
     OvlTop *tops; // the warp's 32 records
     bool byRank; // keep the smallest ranks (overlap-all in reference order) instead of the deepest
+    __device__ __forceinline__ bool cannot_matter(QShared &, int) const { return false; } // (the overflow flag needs every overlap)
     __device__ __forceinline__ void operator()(QShared &, float depth, int gid, int rk, uint32_t enc, f3) const {
         OvlTop &t = tops[enc >> 27];
         t.total++;

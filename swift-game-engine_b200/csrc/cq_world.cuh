@@ -70,6 +70,7 @@ struct WorldView {
     // Device-visible status word in mapped host memory (zero = fine).  Bit 0: a warp's node stack would have overflowed
     // (cq_pool.cuh) — the launch's results are incomplete; the next synchronising call reports CQ_ERR_CUDA.
     unsigned int *status;
+    int refStats;     // counting launches only (CQ_COUNT_REFERENCE): no bestT-based culling, `candidates` = capsuleCandidateCount
     int stagedLeaves; // which kernel variant the launchers pick: 1 = walk expands leaf ranges one triangle per lane
                       // (worlds that do not fit L1); the tiny-world variant keeps the shorter per-lane loop
 };
