@@ -386,7 +386,7 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
     constexpr bool LOOKAHEAD = LOOKAHEAD_ && CQ_PICKUP_DROP;
     constexpr bool OVLDROP = OVLDROP_ && CQ_PICKUP_DROP;
 #pragma unroll 1
-    for (int rep = 0; rep < (LOOKAHEAD || OVLDROP ? 4 : 1); rep++) {
+    for (int rep = 0; rep < (LOOKAHEAD ? 4 : 1); rep++) { // (an overlap drop is rare: its lane simply idles one trip)
         uint32_t idle = __ballot_sync(0xffffffffu, job.phase == PH_NONE);
         uint32_t h = *wp.head, avail = *wp.tail - h;
         bool dropped = false;
@@ -426,7 +426,7 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
         }
         __syncwarp();
         if (lane == 0) *wp.head = h + min((uint32_t)__popc(idle), avail);
-        if (!LOOKAHEAD && !OVLDROP) break;
+        if (!LOOKAHEAD) break;
         __syncwarp();
         if (!__any_sync(0xffffffffu, dropped) || (uint32_t)__popc(idle) >= avail) break; // nobody freed a lane / ring is empty
     }
