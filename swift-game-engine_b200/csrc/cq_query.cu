@@ -323,15 +323,46 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast_ref(WorldView W, const cq
 #ifndef RAY_TRI_MIN
 #define RAY_TRI_MIN 8
 #endif
+#ifndef RAY_SMEM_STACK
+#define RAY_SMEM_STACK (REF ? 20 : 24) /* entries per lane in shared memory (the rest of CQ_STACK in local memory) */
+#endif
 template <bool COUNT, bool REF>
 __global__ void __launch_bounds__(Q_THREADS) k_raycast_phased(WorldView W, const cq_ray *__restrict__ rays, int n,
                                                               cq_ray_hit *__restrict__ out, uint8_t *__restrict__ flagsOut,
                                                               int *workCounter, const uint32_t *__restrict__ order,
                                                               unsigned long long *gctr) {
     Counters ctr = {0, 0, 0, 0};
-    int stackRef[CQ_STACK];
-    float stackT[REF ? CQ_STACK : 1];
-    int sp = 0, set = 2, leafPos = 0, leafEnd = 0, cur = -1;
+    // Traversal stack: the first RAY_SMEM_STACK entries of every lane live in shared memory ([entry][thread]: a warp's
+    // accesses fall into 32 different banks whatever the lanes' depths), deeper entries in local memory.  With the whole
+    // stack in local memory the two loads of a pop were the kernel's top long-scoreboard stall (15% of the samples of
+    // profiles/r2_ray_c5_ref_summary.txt's capture): rays and triangles stream through L1 and keep evicting it.
+    int sp = 0;
+    __shared__ int sRef[RAY_SMEM_STACK][Q_THREADS];
+    __shared__ float sT[REF ? RAY_SMEM_STACK : 1][Q_THREADS];
+    int deepRef[CQ_STACK - RAY_SMEM_STACK];
+    float deepT[REF ? CQ_STACK - RAY_SMEM_STACK : 1];
+    const int tid = threadIdx.x;
+    auto push = [&](int ref, float t) {
+        if (sp < RAY_SMEM_STACK) {
+            sRef[sp][tid] = ref;
+            if (REF) sT[sp][tid] = t;
+        } else {
+            deepRef[sp - RAY_SMEM_STACK] = ref;
+            if (REF) deepT[sp - RAY_SMEM_STACK] = t;
+        }
+        sp++;
+    };
+    auto pop = [&](int &ref, float &t) {
+        --sp;
+        if (sp < RAY_SMEM_STACK) {
+            ref = sRef[sp][tid];
+            if (REF) t = sT[sp][tid];
+        } else {
+            ref = deepRef[sp - RAY_SMEM_STACK];
+            if (REF) t = deepT[sp - RAY_SMEM_STACK];
+        }
+    };
+    int set = 2, leafPos = 0, leafEnd = 0, cur = -1;
     int bestTri = -1, setTri = -1;
     float closestT = 0.0f, bestT = 0.0f, maxDist = 0.0f;
     f3 o = {0, 0, 0}, d = {0, 0, 0}, inv = {0, 0, 0}, bestN = {0, 0, 0}, setN = {0, 0, 0};
@@ -408,9 +439,9 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast_phased(WorldView W, const
                     const int tagged = h.rootRef < 0 ? ~((~h.rootRef) | (s1 << 30)) : (h.rootRef | (s1 << 30)); // bit 30 = set
                     if (REF) {
                         float tmin;
-                        if (ref_ray_aabb(o, inv, lo, hi, tmin)) stackRef[sp] = tagged, stackT[sp++] = tmin;
+                        if (ref_ray_aabb(o, inv, lo, hi, tmin)) push(tagged, tmin);
                     } else if (ray_box(o, inv, lo, hi, closestT)) {
-                        stackRef[sp++] = tagged;
+                        push(tagged, 0.0f);
                     }
                 }
             }
@@ -422,10 +453,11 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast_phased(WorldView W, const
             const uint32_t nMask = __ballot_sync(0xffffffffu, wantN);
             if (nMask == 0u) break;
             if (wantN) {
-                --sp;
-                const int ref = stackRef[sp];
+                int ref;
+                float tNear = 0.0f;
+                pop(ref, tNear);
                 bool visit = true;
-                if (REF) visit = !(stackT[sp] > closestT); // :933, with the closestT of NOW
+                if (REF) visit = !(tNear > closestT); // :933, with the closestT of NOW
                 if (visit) {
                     if (ref < 0) {
                         int enc = ~ref;
@@ -445,13 +477,13 @@ __global__ void __launch_bounds__(Q_THREADS) k_raycast_phased(WorldView W, const
                             float t0, t1;
                             const bool h0 = ref_ray_aabb(o, inv, xyz(n0), xyz(n1), t0); // left
                             const bool h1 = ref_ray_aabb(o, inv, xyz(n2), xyz(n3), t1); // right
-                            if (h0) stackRef[sp] = r0, stackT[sp++] = t0; // push left, then right: right is popped first (:965-966)
-                            if (h1) stackRef[sp] = r1, stackT[sp++] = t1;
+                            if (h0) push(r0, t0); // push left, then right: right is popped first (:965-966)
+                            if (h1) push(r1, t1);
                         } else {
                             const bool h0 = ray_box(o, inv, xyz(n0), xyz(n1), closestT);
                             const bool h1 = ray_box(o, inv, xyz(n2), xyz(n3), closestT);
-                            if (h1) stackRef[sp++] = r1;
-                            if (h0) stackRef[sp++] = r0;
+                            if (h1) push(r1, 0.0f);
+                            if (h0) push(r0, 0.0f);
                         }
                     }
                 }

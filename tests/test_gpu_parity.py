@@ -261,7 +261,7 @@ def test_static_and_dynamic_sets_index_offset(cq, orc, scenes):
     o.close()
 
 
-def test_counters_match_reference_stats(world, scenes, orc):
+def test_counters_match_reference_stats(world, cq, scenes, orc):
     """capsuleCandidateCount (CollisionQuery.swift:1066) is tree-independent: the GPU's candidate counter
     must equal the reference's on the same batch."""
     name, parts, g, o = world
@@ -269,14 +269,23 @@ def test_counters_match_reference_stats(world, scenes, orc):
     q = scenes.gen_casts(2000, lo, hi, seed=31)
     st = orc.Stats()
     o.capsule_cast(q, 0, orc.ORDER_REFERENCE, 1, st)
-    g.set_counting(True)
+    g.set_counting(cq.COUNT_REFERENCE)
     g.resetStats()
-    g.capsuleCast(q)
+    ref_mode = g.capsuleCast(q)
     c = g.stats()
-    g.set_counting(False)
     assert c["candidates"] == st.candidates
     assert 0 < c["distance_evals"] <= st.distance_evals  # exact-safe pruning only removes work
     assert c["nodes_visited"] > 0 and c["kernel_launches"] >= 1
+    # the path as shipped: sweeps that hold a hit cull against the capsule swept to that hit and drop candidates that cannot
+    # matter — fewer nodes, candidates and evaluations, the same answers
+    g.set_counting(cq.COUNT_PATH)
+    g.resetStats()
+    path_mode = g.capsuleCast(q)
+    p = g.stats()
+    g.set_counting(False)
+    assert path_mode.tobytes() == ref_mode.tobytes() == g.capsuleCast(q).tobytes()
+    assert 0 < p["candidates"] <= c["candidates"] and p["nodes_visited"] <= c["nodes_visited"]
+    assert 0 < p["distance_evals"] <= c["distance_evals"]
 
 
 def test_terrain_lbvh_and_blocking_sweeps(cq, orc, scenes):
