@@ -35,8 +35,9 @@ cap cast_c2 k_capsule_cast 3 1 python bench.py --no-cpu-baseline --only c2 --ste
 cap ray_c5_ref k_raycast 3 1 python bench.py --no-cpu-baseline --only c5 --steps 1 --warmup 3
 cap ray_c5_canon k_raycast 3 1 python bench.py --no-cpu-baseline --only c5 --steps 1 --warmup 3 --order canonical
 cap overlap_all k_capsule_overlap_pool 1 1 python tools/profile_extra.py overlap
-cap sep_turns k_sep_turns 40 2 python tools/profile_extra.py separation
-cap sep_post k_sep_post 1 1 python tools/profile_extra.py separation
+# (the rounds of a sweep normally run inside a CUDA-graph WHILE node; for the profiler they are launched from the host — same kernels)
+cap sep_turns k_sep_turns 40 2 env CQ_SEP_HOST_ROUNDS=1 python tools/profile_extra.py separation
+cap sep_post k_sep_post 1 1 env CQ_SEP_HOST_ROUNDS=1 python tools/profile_extra.py separation
 cap build_onesweep k_os_pass 4 2 python tools/profile_extra.py build
 cap build_karras "k_karras|k_fit|k_collapse4|k_morton" 4 4 python tools/profile_extra.py build
 H="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline"
