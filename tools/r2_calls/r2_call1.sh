@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 1: merged resident crowd + compile-time variants A/B + the ncu captures round 1 left out
 # (k_capsule_cast on C2, k_raycast on C5).  Everything lands in gpurun_out/r2c1_*.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

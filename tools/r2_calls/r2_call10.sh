@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 10: warp-reduced sweep commit + tie-aware prune (query kernels), reduce in the move-and-slide kernels as a
 # variant (redmas), full parity, and the ray-sort probe.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 11: drops at pickup (tie-hopeless / box lower bound) in the query kernels against the build without them,
 # parity, the ray-sort probe, and a probe of CUDA-graph WHILE nodes (device-side round loop for agent separation).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 12: slim pair state (libcq) against the build before it (libcq_fat); walk-level bestT culling (both builds);
 # agent-separation rounds as a device-side WHILE graph against the host-driven schedule (CQ_SEP_HOST_ROUNDS=1); parity.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 13: overlap drops at pickup in the staged move-and-slide kernel (libcq) against the previous commit
 # (libcq_prev); counting modes (reference stats / path counters); parity.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

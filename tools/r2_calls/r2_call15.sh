@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 15: ray traversal stack in shared memory (libcq) against the local-memory stack (libcq_prev); overlap drop
 # without the retry loop on terrain / render; parity.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU call 2: reference-order parity (default build), look-ahead prune variant (parity + A/B).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

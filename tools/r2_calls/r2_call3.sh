@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 3: parity after the commit / second-pass rework, the new bench line with extras, A/B of the look-ahead
 # prune and of the two order rules, the multi-GPU example on one GPU, launch list of the headline command.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

@@ -2,7 +2,7 @@
 # Round-2 GPU call 4: where did the hulls step lose 10%?  Same-box A/B of: the round-1 code (+SINGLE_POST) as control,
 # the current default, and builds without the tie flag / without the stack guards / with the look-ahead prune; the
 # phase-voted ray kernel against the stepwise ones in both orders; parity of everything the ray kernel touches.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 5: rank carried in tv2.w + warp-uniform stack guard + look-ahead in the query kernels only.
 # Full GPU parity, then the same-box A/B against the round-1 code (.ab_old = round 1 + SINGLE_POST), then the bench line.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q -rf --no-header > $O/r2c5_pytest.log 2>&1

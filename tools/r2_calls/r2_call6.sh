@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 6: parity of the default build and of the plane-separation variant; same-box A/B of the remaining
 # suspects for the 3-5% the step lost against round 1 (tie flag, record stride, inlined overlap commit) and of the variant.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

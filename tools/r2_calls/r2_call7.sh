@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 7: FE_READY (run the owners' logic only when enough owners are ready) A/B on the move-and-slide scenes,
 # with parity of the best-looking variant.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc

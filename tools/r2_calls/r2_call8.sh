@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU call 8: parity incl. the dirty-subtree refit; default build after the readiness rule; refit cost on a big set.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q -rf --no-header > $O/r2c8_pytest.log 2>&1

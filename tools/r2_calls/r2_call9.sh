@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 9: owner-grouped commit against the lane-at-a-time commit (same box), full parity incl. the new
 # full-size C2 / C5 tests.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 D=swift-game-engine_b200/csrc
