@@ -54,6 +54,7 @@ def _regions():
         ("bool clamp_interval(", "capsule-capsule CCD (agents)")])
     pool = cuts("cq_pool.cuh", [
         ("void pool_push_roots(", "pool: posting queries (pool_post_*, roots)"),
+        ("bool sweep_reach(", "pool: sweeps holding a hit: reach box / cannot-matter tests (called from the walk and the pickup)"),
         ("void pool_walk_round(", "pool: cooperative walk (pool_walk_round)"),
         ("void pool_take_jobs(", "pool: job pickup (pool_take_jobs)"),
         ("void pool_eval(", "pool: pair state machine (pool_eval, without the distance function)"),
