@@ -83,7 +83,7 @@ struct Job { // executor-side pair state (registers)
     // Everything here stays live across the distance function, whose own working set fills the register file: values
     // that are only needed between evaluations (|delta|, minAdvance, maxIter) are re-read from the owner's QShared, and
     // the phases share slots — round 2's terrain capture showed 11% of the stall samples on reloads of spilled pair state
-    // that the node / triangle traffic had evicted from L1 (profiles/r2_by_region.txt).
+    // that the node / triangle traffic had evicted from L1 (profiles/r2_by_region_midround.txt).
     int phase;
     uint32_t enc; // ring entry (owner | set | slot): lets an owner reload a winning triangle later
     float radius, hh;
@@ -612,23 +612,20 @@ static __device__ __noinline__ void pool_post_first_hits(const uint32_t *__restr
     s.pending = CQ_MAX_OVERLAP_HITS;
 }
 
-// Commit of the finished pairs.  Contributions to DIFFERENT owners touch different records and commute; contributions to
-// the same owner are order-free reductions (smallest (toi, rank); deepest two / smallest ranks; counts).  So the lanes are
-// grouped by owner (__match_any_sync) and round r commits the r-th member of every group at once: the number of serialized
-// rounds is the largest group, not the number of finishing lanes.  Cast contributions that can no longer win (toi already
-// beyond the owner's best — which only ever decreases) are dropped before the rounds.  ncu on C2, where most candidates of
-// a fat capsule hit, had the lane-at-a-time version at 30% of the kernel's stall samples (profiles/r2_by_region.txt).
 #ifndef CQ_COMMIT_REDUCE_MAS
 #define CQ_COMMIT_REDUCE_MAS 0 /* 1: every move-and-slide kernel settles sweep hits with warp reductions (A/B) */
 #endif
 
 // Commit step: the lanes that finished a pair this trip hand their contribution to the owner's record; pending counters drop.
-// Lanes are grouped by owner (one MATCH); round r serves the r-th finishing lane of every owner at once.
+// Contributions to DIFFERENT owners touch different records and commute; contributions to the same owner are order-free
+// reductions (smallest (toi, rank); deepest two / smallest ranks; counts).  So the lanes are grouped by owner (one MATCH) and
+// round r serves the r-th finishing lane of every owner at once: the serialized rounds are the largest group, not the
+// number of finishing lanes.
 // REDUCE (the query kernels): sweep hits (:1084,1098 + the order rule — the accepted candidate with the smallest (toi, rank)
 // wins) are settled among the finishing lanes of an owner with two warp reductions, so that ONE lane per owner touches the
 // record and no rounds are needed for sweeps.  Lane-at-a-time rounds cost the C2 kernel 8.3 rounds per trip: a capsule that
 // starts inside the mesh collects dozens of toi == 0 hits, all exact ties that each took a round to compare ranks
-// (profiles/r2_by_region.txt).  A contribution already behind the owner's best is dropped before anything else.
+// (profiles/r2_by_region_midround.txt).  A contribution already behind the owner's best is dropped before anything else.
 // Measured on one box (profiles/r2_ab_same_box.txt, calls 9-10): C2 28.1 -> 16.7 ms (with the tie-aware prune of pool_eval);
 // in the move-and-slide kernel the reductions gain 3.6% on the render mesh and 1.2% on the terrain but cost the hulls step
 // 4% (0.7 KB more code in the steady-state loop), so only its staged-walk variant (worlds of >= 4096 triangles) uses them;
