@@ -103,10 +103,27 @@ typedef struct cq_world_info {
 #define CQ_ORDER_REFERENCE 0
 #define CQ_ORDER_CANONICAL 1
 
+/* StaticMeshComponent.triangleMaterials (Components.swift:323-351): surface materials per triangle of one part.  As in
+ * TriangleMeshSet.rebuild (CollisionQuery.swift:363-369) the array is used only when `n` equals the part's triangle count
+ * (n_indices / 3, before the degenerate filter) and silently ignored otherwise; triangles the filter drops take their
+ * entry with them.  The arrays are copied by cq_world_create_ex. */
+typedef struct cq_surface_material { /* SurfaceMaterial, Components.swift:704-716 */
+    float mu_s, mu_k;
+    uint8_t flatten_ground;
+    uint8_t _pad[3];
+} cq_surface_material; /* 12 bytes */
+typedef struct cq_triangle_materials {
+    uint32_t entity_id; /* the part (cq_mesh_part.entity_id) */
+    int32_t n;
+    const cq_surface_material *materials;
+} cq_triangle_materials;
+
 typedef struct cq_world_options {
-    int32_t order;        /* CQ_ORDER_* */
-    int32_t _reserved[7]; /* zero */
-} cq_world_options;
+    int32_t order;                                   /* CQ_ORDER_* */
+    int32_t n_triangle_materials;                    /* entries of triangle_materials (0: every part uses its own material) */
+    const cq_triangle_materials *triangle_materials; /* per-triangle materials of some parts, or NULL */
+    int32_t _reserved[4];                            /* zero */
+} cq_world_options; /* 32 bytes, as before the two fields were carved out of the reserved words */
 void cq_world_options_default(cq_world_options *o);
 
 /* Replaces CollisionQuery.init(world:activeEntityIDs:) (CollisionQuery.swift:57-59

@@ -215,6 +215,7 @@ struct PartCopy { // what the oracle keeps of a StaticMeshComponent + TransformC
     float model[16];
     uint32_t layer;
     Material material;
+    std::vector<Material> triangleMaterials; // StaticMeshComponent.triangleMaterials (may be empty = nil)
     bool isDynamic;
     uint32_t entityId;
     int partIndex;
@@ -253,9 +254,11 @@ struct TriangleMeshSet {
                 positions.push_back(transformPoint(e->model, f3(e->positions[3 * i], e->positions[3 * i + 1],
                                                                 e->positions[3 * i + 2])));
             const std::vector<uint32_t> &local = e->indices;
+            const size_t triCount = local.size() / 3;
+            const bool perTri = !e->triangleMaterials.empty() && e->triangleMaterials.size() == triCount; // CQ:365-369
             int indexStart = (int)indices.size();
             int triStart = (int)triangleAABBs.size();
-            size_t tri = 0;
+            size_t tri = 0, triLocal = 0;
             while (tri + 2 < local.size()) {
                 int i0 = (int)((uint32_t)baseVertex + local[tri]);
                 int i1 = (int)((uint32_t)baseVertex + local[tri + 1]);
@@ -264,16 +267,18 @@ struct TriangleMeshSet {
                 F3 e1 = p1 - p0, e2 = p2 - p0;
                 if (length_squared(cross(e1, e2)) <= areaEps) { // CQ:385
                     tri += 3;
+                    triLocal += 1;
                     continue;
                 }
                 indices.push_back((uint32_t)i0);
                 indices.push_back((uint32_t)i1);
                 indices.push_back((uint32_t)i2);
                 triangleAABBs.push_back({vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))});
-                triangleMaterials.push_back(e->material);
+                triangleMaterials.push_back(perTri ? e->triangleMaterials[triLocal] : e->material); // triSource[triLocal], CQ:396
                 triangleLayers.push_back(e->layer);
                 triangleParts.push_back(e->partIndex);
                 tri += 3;
+                triLocal += 1;
             }
             int indexEnd = (int)indices.size(), triEnd = (int)triangleAABBs.size();
             if (indexEnd > indexStart && triEnd > triStart)
@@ -1804,7 +1809,17 @@ struct orc_world {
 
 extern "C" {
 
-orc_world *orc_world_create(const orc_part *parts, int32_t n_parts) { // StaticTriMesh.init CQ:717-726
+orc_world *orc_world_create(const orc_part *parts, int32_t n_parts) { return orc_world_create_ex(parts, n_parts, nullptr, 0); }
+
+void orc_world_triangle_material(const orc_world *w, int32_t triangle_index, float out[3]) { // CQ:464-469 over both sets (:782,1004)
+    const int nStatic = (int)w->mesh.staticSet.triangleAABBs.size();
+    const Material m = triangle_index >= nStatic ? w->mesh.dynamicSet.materialForTriangle(triangle_index - nStatic)
+                                                  : w->mesh.staticSet.materialForTriangle(triangle_index);
+    out[0] = m.muS, out[1] = m.muK, out[2] = m.flatten ? 1.0f : 0.0f;
+}
+
+orc_world *orc_world_create_ex(const orc_part *parts, int32_t n_parts, const orc_triangle_materials *tri_materials,
+                               int32_t n_tri_materials) { // StaticTriMesh.init CQ:717-726
     orc_world *w = new orc_world();
     w->parts.resize(n_parts);
     for (int i = 0; i < n_parts; i++) {
@@ -1817,6 +1832,14 @@ orc_world *orc_world_create(const orc_part *parts, int32_t n_parts) { // StaticT
         pc.isDynamic = parts[i].is_dynamic != 0;
         pc.entityId = parts[i].entity_id;
         pc.partIndex = i;
+        for (int k = 0; k < n_tri_materials; k++)
+            if (tri_materials[k].entity_id == pc.entityId && tri_materials[k].n > 0 && tri_materials[k].materials) {
+                pc.triangleMaterials.clear();
+                for (int t = 0; t < tri_materials[k].n; t++) {
+                    const orc_surface_material &m = tri_materials[k].materials[t];
+                    pc.triangleMaterials.push_back({m.mu_s, m.mu_k, m.flatten_ground != 0});
+                }
+            }
     }
     std::vector<const PartCopy *> statics, dynamics; // partitionEntities CQ:886-900
     for (const PartCopy &pc : w->parts) (pc.isDynamic ? dynamics : statics).push_back(&pc);

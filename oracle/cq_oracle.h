@@ -85,6 +85,14 @@ typedef struct orc_stats {
 #define ORC_ORDER_CANONICAL 1
 
 orc_world *orc_world_create(const orc_part *parts, int32_t n_parts);
+/* StaticMeshComponent.triangleMaterials of some parts: used when n == the part's triangle count, ignored otherwise
+ * (CollisionQuery.swift:363-369). */
+typedef struct orc_surface_material { float mu_s, mu_k; uint8_t flatten_ground; uint8_t _pad[3]; } orc_surface_material;
+typedef struct orc_triangle_materials { uint32_t entity_id; int32_t n; const orc_surface_material *materials; } orc_triangle_materials;
+orc_world *orc_world_create_ex(const orc_part *parts, int32_t n_parts, const orc_triangle_materials *tri_materials,
+                               int32_t n_tri_materials);
+/* TriangleMeshSet.materialForTriangle (CollisionQuery.swift:464-469) of a global triangle index: out = mu_s, mu_k, flatten */
+void orc_world_triangle_material(const orc_world *w, int32_t triangle_index, float out[3]);
 void orc_world_destroy(orc_world *w);
 /* which: 0 static, 1 dynamic. out[0]=n_vertices out[1]=n_triangles out[2]=n_bvh_nodes */
 void orc_world_counts(const orc_world *w, int32_t which, int32_t out[3]);

@@ -72,6 +72,9 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.orc_world_create.restype = C.c_void_p
         L.orc_world_create.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_world_create_ex.restype = C.c_void_p
+        L.orc_world_create_ex.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+        L.orc_world_triangle_material.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_destroy.argtypes = [C.c_void_p]
         L.orc_world_counts.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_read_soup.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
@@ -134,6 +137,13 @@ def init_states(positions, velocities=None):
     return s
 
 
+_SURFACE_MATERIAL = np.dtype([("mu_s", "<f4"), ("mu_k", "<f4"), ("flatten_ground", "u1"), ("_pad", "u1", (3,))])
+
+
+class _TriangleMaterials(C.Structure):
+    _fields_ = [("entity_id", C.c_uint32), ("n", C.c_int32), ("materials", C.c_void_p)]
+
+
 class OracleWorld:
     """parts: list of dicts {positions (V,3) f32, indices (I,) u32, model (16,) f32 column-major, layer,
     mu_s, mu_k, flatten_ground, is_dynamic, entity_id}."""
@@ -158,7 +168,18 @@ class OracleWorld:
             arr[i].flatten_ground = int(bool(p.get("flatten_ground", False)))
             arr[i].is_dynamic = int(bool(p.get("is_dynamic", False)))
             arr[i].entity_id = int(p.get("entity_id", i))
-        self._h = lib().orc_world_create(C.byref(arr), len(parts))
+        per_tri = []
+        for i, p in enumerate(parts):  # StaticMeshComponent.triangleMaterials: (T, 3) rows of mu_s, mu_k, flatten_ground
+            if p.get("triangle_materials") is not None:
+                rows = np.asarray(p["triangle_materials"], np.float32).reshape(-1, 3)
+                mats = np.zeros(len(rows), _SURFACE_MATERIAL)
+                mats["mu_s"], mats["mu_k"], mats["flatten_ground"] = rows[:, 0], rows[:, 1], rows[:, 2] != 0
+                per_tri.append((int(p.get("entity_id", i)), mats))
+        tm = (_TriangleMaterials * max(len(per_tri), 1))()
+        for k, (eid, mats) in enumerate(per_tri):
+            self._keep.append(mats)
+            tm[k].entity_id, tm[k].n, tm[k].materials = eid, len(mats), mats.ctypes.data
+        self._h = lib().orc_world_create_ex(C.byref(arr), len(parts), C.byref(tm), len(per_tri))
 
     def close(self):
         if self._h:
@@ -170,6 +191,11 @@ class OracleWorld:
             self.close()
         except Exception:
             pass
+
+    def triangle_material(self, triangle_index):
+        out = np.zeros(3, np.float32)
+        lib().orc_world_triangle_material(self._h, int(triangle_index), out.ctypes.data)
+        return {"mu_s": float(out[0]), "mu_k": float(out[1]), "flatten_ground": bool(out[2])}
 
     def counts(self, which=0):
         out = np.zeros(3, np.int32)

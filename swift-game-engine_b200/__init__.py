@@ -71,8 +71,42 @@ class WorldInfo(C.Structure):
                 ("ref_order_ms", C.c_float), ("n_ref_nodes", C.c_int32), ("_reserved", C.c_int32)]
 
 
+class TriangleMaterials(C.Structure):  # cq_triangle_materials
+    _fields_ = [("entity_id", C.c_uint32), ("n", C.c_int32), ("materials", C.c_void_p)]
+
+
 class WorldOptions(C.Structure):
-    _fields_ = [("order", C.c_int32), ("_reserved", C.c_int32 * 7)]
+    _fields_ = [("order", C.c_int32), ("n_triangle_materials", C.c_int32), ("triangle_materials", C.c_void_p),
+                ("_reserved", C.c_int32 * 4)]
+
+
+# cq_surface_material: StaticMeshComponent.triangleMaterials entries (a part dict may carry "triangle_materials": (T, 3)
+# rows of mu_s, mu_k, flatten_ground — used when T equals the part's triangle count, ignored otherwise, as the reference does)
+SURFACE_MATERIAL = np.dtype([("mu_s", "<f4"), ("mu_k", "<f4"), ("flatten_ground", "u1"), ("_pad", "u1", (3,))])
+
+
+def _world_options(parts, order, keep):
+    """cq_world_options for `parts`: the order rule + the per-triangle materials some part dicts carry."""
+    opt = WorldOptions()
+    lib().cq_world_options_default(C.byref(opt))
+    opt.order = int(order)
+    per_tri = [(int(p.get("entity_id", i)), surface_materials(p["triangle_materials"]))
+               for i, p in enumerate(parts) if p.get("triangle_materials") is not None]
+    if per_tri:
+        tm = (TriangleMaterials * len(per_tri))()
+        for k, (eid, mats) in enumerate(per_tri):
+            keep.append(mats)
+            tm[k].entity_id, tm[k].n, tm[k].materials = eid, len(mats), mats.ctypes.data
+        keep.append(tm)
+        opt.n_triangle_materials, opt.triangle_materials = len(per_tri), C.addressof(tm)
+    return opt
+
+
+def surface_materials(rows):
+    rows = np.asarray(rows, np.float32).reshape(-1, 3)
+    out = np.zeros(len(rows), SURFACE_MATERIAL)
+    out["mu_s"], out["mu_k"], out["flatten_ground"] = rows[:, 0], rows[:, 1], rows[:, 2] != 0
+    return out
 
 
 ORDER_REFERENCE, ORDER_CANONICAL = 0, 1  # include/cq.h: which of several exactly equal candidates a query names
@@ -341,9 +375,7 @@ class CollisionQuery:
             arr[i].is_dynamic = int(bool(p.get("is_dynamic", False)))
             arr[i].entity_id = int(p.get("entity_id", i))
         h = C.c_void_p()
-        opt = WorldOptions()
-        lib().cq_world_options_default(C.byref(opt))
-        opt.order = int(order)
+        opt = _world_options(parts, order, self._keep)
         _check(lib().cq_world_create_ex(C.byref(arr), len(parts), C.byref(opt), C.byref(h)))
         self._h = h
         self._keep = []
@@ -598,9 +630,7 @@ class MultiWorld:
     def __init__(self, group, parts, order=ORDER_REFERENCE):
         keep = []
         arr = _mesh_parts(parts, keep)
-        opt = WorldOptions()
-        lib().cq_world_options_default(C.byref(opt))
-        opt.order = int(order)
+        opt = _world_options(parts, order, keep)
         h = C.c_void_p()
         _check(lib().cq_world_create_multi(group.handle, C.byref(arr), len(parts), C.byref(opt), C.byref(h)))
         self._h, self._group, self.order = h, group, order

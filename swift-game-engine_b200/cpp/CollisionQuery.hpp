@@ -50,10 +50,15 @@ class CollisionQuery {
     // init(world:activeEntityIDs:) — the caller flattens its (Transform, StaticMesh, body type) entities into parts
     // referenceOrder (default): exact ties, capsuleOverlapAll overflow and grazing rays come out as in the reference's own
     // tree and visiting order (CQ_ORDER_REFERENCE, include/cq.h); false = the tree-independent rule, no host build.
-    explicit CollisionQuery(const std::vector<cq_mesh_part> &parts, bool referenceOrder = true) {
+    // triangleMaterials: StaticMeshComponent.triangleMaterials of the parts that have them (used when there is one entry per
+    // triangle of the part, ignored otherwise — CollisionQuery.swift:363-369); the library copies them.
+    explicit CollisionQuery(const std::vector<cq_mesh_part> &parts, bool referenceOrder = true,
+                            const std::vector<cq_triangle_materials> &triangleMaterials = {}) {
         cq_world_options opt;
         cq_world_options_default(&opt);
         opt.order = referenceOrder ? CQ_ORDER_REFERENCE : CQ_ORDER_CANONICAL;
+        opt.n_triangle_materials = (int32_t)triangleMaterials.size();
+        opt.triangle_materials = triangleMaterials.empty() ? nullptr : triangleMaterials.data();
         if (cq_world_create_ex(parts.data(), (int32_t)parts.size(), &opt, &w_) != CQ_OK)
             throw std::runtime_error(std::string("cq_world_create: ") + cq_last_error());
     }

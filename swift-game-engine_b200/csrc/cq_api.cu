@@ -108,6 +108,7 @@ static void make_view(cq_world *w) {
         v.nodes4 = S.nodes4;
         v.hdr = S.hdr;
         v.triPart = S.triPart;
+        v.triMat = S.triMat;
         v.triOffset = s == 0 ? 0 : w->set[0].nTris;
         v.refNodes = S.refNodes;
         v.refSlot = S.refSlot;
@@ -119,6 +120,7 @@ static void make_view(cq_world *w) {
     if (w->hStatus) cudaHostGetDevicePointer((void **)&w->view.status, w->hStatus, 0);
     w->view.materials = w->dMaterials;
     w->view.nParts = (int)w->parts.size();
+    w->view.nMaterials = (int)std::max(w->hMaterials.size(), w->parts.size());
     w->view.stagedLeaves = (w->set[0].nTris + w->set[1].nTris) >= 4096 ? 1 : 0;
     w->view.refStats = w->countRef;
 }
@@ -300,6 +302,36 @@ int cq_world_create_ex(const cq_mesh_part *parts, int32_t n_parts, const cq_worl
     }
     std::vector<float> models((size_t)n_parts * 16);
     std::vector<float4> materials(n_parts);
+    // per-triangle materials (options->triangle_materials): rows appended to the table after the parts' own rows; a part
+    // whose array does not have exactly one entry per triangle keeps its own material (CollisionQuery.swift:365-369)
+    std::vector<int32_t> matIn[2];
+    if (opt.n_triangle_materials > 0) {
+        if (!opt.triangle_materials) {
+            set_error("cq_world_create_ex: n_triangle_materials = %d without an array", opt.n_triangle_materials);
+            return fail(CQ_ERR_INVALID);
+        }
+        for (int k = 0; k < opt.n_triangle_materials; k++) {
+            const cq_triangle_materials &tm = opt.triangle_materials[k];
+            for (int s = 0; s < 2; s++)
+                for (const PartRow &row : input[s].rows) {
+                    if (parts[row.part].entity_id != tm.entity_id || tm.n != row.nTris || row.nTris == 0) continue;
+                    if (!tm.materials) {
+                        set_error("cq_world_create_ex: triangle_materials[%d] has no array", k);
+                        return fail(CQ_ERR_INVALID);
+                    }
+                    if (matIn[s].empty()) { // default: every input triangle points at its part's row
+                        matIn[s].resize(input[s].nTris);
+                        for (const PartRow &r : input[s].rows) std::fill_n(matIn[s].begin() + r.triStart, r.nTris, r.part);
+                    }
+                    const int32_t base = (int32_t)materials.size();
+                    for (int t = 0; t < row.nTris; t++) {
+                        const cq_surface_material &m = tm.materials[t];
+                        materials.push_back(make_float4(m.mu_s, m.mu_k, m.flatten_ground ? 1.0f : 0.0f, 0.0f));
+                        matIn[s][(size_t)row.triStart + t] = base + t;
+                    }
+                }
+        }
+    }
     w->parts.resize(n_parts);
     for (int p = 0; p < n_parts; p++) {
         const cq_mesh_part &mp = parts[p];
@@ -315,8 +347,10 @@ int cq_world_create_ex(const cq_mesh_part *parts, int32_t n_parts, const cq_worl
 
     if ((rc = check_cuda(cudaMalloc((void **)&w->dModels, sizeof(float) * 16 * (size_t)std::max(n_parts, 1)), "models")) != CQ_OK)
         return fail(rc);
-    if ((rc = check_cuda(cudaMalloc((void **)&w->dMaterials, sizeof(float4) * (size_t)std::max(n_parts, 1)), "materials")) != CQ_OK)
+    if ((rc = check_cuda(cudaMalloc((void **)&w->dMaterials, sizeof(float4) * std::max(materials.size(), (size_t)1)), "materials")) != CQ_OK)
         return fail(rc);
+    w->hMaterials.resize(materials.size());
+    for (size_t k = 0; k < materials.size(); k++) w->hMaterials[k] = {materials[k].x, materials[k].y, materials[k].z != 0.0f ? 1 : 0};
     if ((rc = check_cuda(cudaMalloc((void **)&w->dCounters, sizeof(unsigned long long) * 4), "counters")) != CQ_OK) return fail(rc);
     cudaMemsetAsync(w->dCounters, 0, sizeof(unsigned long long) * 4, w->stream);
     if ((rc = check_cuda(cudaMalloc((void **)&w->dWork, sizeof(int) * CQ_WORK_RING), "work counters")) != CQ_OK) return fail(rc);
@@ -326,13 +360,13 @@ int cq_world_create_ex(const cq_mesh_part *parts, int32_t n_parts, const cq_worl
     cudaHostGetDevicePointer((void **)&w->view.status, w->hStatus, 0);
     if (n_parts) {
         cudaMemcpyAsync(w->dModels, models.data(), sizeof(float) * 16 * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
-        cudaMemcpyAsync(w->dMaterials, materials.data(), sizeof(float4) * (size_t)n_parts, cudaMemcpyHostToDevice, w->stream);
+        cudaMemcpyAsync(w->dMaterials, materials.data(), sizeof(float4) * materials.size(), cudaMemcpyHostToDevice, w->stream);
     }
     w->buildMs = 0.0f; // accumulated by build_set: device time of the build kernels only
     for (int s = 0; s < 2; s++) {
         std::vector<int> &partTriStart = input[s].partTriStart; // in: before the degenerate filter; out: after
         int badTri = -1;
-        rc = build_set(w, w->set[s], input[s], partTriStart, &badTri);
+        rc = build_set(w, w->set[s], input[s], partTriStart, &badTri, matIn[s].empty() ? nullptr : matIn[s].data());
         if (rc != CQ_OK && badTri >= 0) { // name the part and the first offending index of that triangle
             const PartRow &row = input[s].rows[part_row_of(input[s].rows.data(), (int)input[s].rows.size(), badTri, true)];
             const uint32_t *tri = parts[row.part].indices + 3 * (size_t)(badTri - row.triStart);
@@ -349,6 +383,13 @@ int cq_world_create_ex(const cq_mesh_part *parts, int32_t n_parts, const cq_worl
         }
     }
     if ((rc = check_cuda(cudaStreamSynchronize(w->stream), "build")) != CQ_OK) return fail(rc);
+    for (int s = 0; s < 2; s++)
+        if (w->set[s].triMat && w->set[s].nTris > 0) { // host copy for cq_world_triangle_material
+            w->hTriMat[s].resize((size_t)w->set[s].nTris);
+            if ((rc = check_cuda(cudaMemcpy(w->hTriMat[s].data(), w->set[s].triMat, sizeof(int32_t) * (size_t)w->set[s].nTris,
+                                            cudaMemcpyDeviceToHost), "triangle materials")) != CQ_OK)
+                return fail(rc);
+        }
     if (w->order == CQ_ORDER_REFERENCE && (rc = attach_ref_order(w)) != CQ_OK) return fail(rc);
     make_view(w);
     *out = w;
@@ -481,6 +522,14 @@ int cq_world_read_soup(const cq_world *w, int32_t which, float *positions_xyz, u
 int cq_world_triangle_material(const cq_world *w, int32_t triangle_index, cq_material *out) {
     if (!w || !out) return CQ_ERR_INVALID;
     *out = {0.8f, 0.6f, 0}; // SurfaceMaterial.default
+    if (triangle_index >= 0) { // a set with per-triangle materials: the triangle's own row of the table
+        const int off = w->set[0].nTris, s = triangle_index >= off ? 1 : 0, local = s ? triangle_index - off : triangle_index;
+        if (!w->hTriMat[s].empty() && local < (int)w->hTriMat[s].size()) {
+            const int32_t row = w->hTriMat[s][(size_t)local];
+            if (row >= 0 && row < (int32_t)w->hMaterials.size()) *out = w->hMaterials[(size_t)row];
+            return CQ_OK;
+        }
+    }
     for (const PartInfo &p : w->parts) {
         int off = p.set == 0 ? 0 : w->set[0].nTris;
         if (triangle_index >= p.triLo + off && triangle_index < p.triHi + off) {

@@ -177,6 +177,12 @@ __global__ void k_compact(const uint32_t *__restrict__ flags, const uint32_t *__
     partOut[o] = partIn[t];
 }
 
+__global__ void k_compact_i32(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ offs, int nTrisIn,
+                              const int32_t *__restrict__ in, int32_t *__restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nTrisIn && flags[t]) out[offs[t]] = in[t];
+}
+
 __global__ void k_gather_u32(const uint32_t *__restrict__ src, const int32_t *__restrict__ pos, int n,
                              uint32_t *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -777,6 +783,7 @@ struct Arena {
 };
 
 void free_set(DeviceSet &S) {
+    cudaFree(S.triMat);
     cudaFree(S.arena);
     cudaFree(S.refArena);
     S = DeviceSet();
@@ -894,7 +901,8 @@ template <class Fn> static size_t arena_layout(Fn fn) { // run the carving once 
 
 int build_set(cq_world *w, DeviceSet &S, const SetPlan &in,
               std::vector<int> &partTriStartIn /* in: first input triangle of each part of this set (+ end), out: filtered */,
-              int *badTriangle /* out: smallest input triangle with an index outside its part's vertices, or -1 */) {
+              int *badTriangle /* out: smallest input triangle with an index outside its part's vertices, or -1 */,
+              const int32_t *matIn /* host, per input triangle: row of the material table, or nullptr */) {
     cudaStream_t st = w->stream;
     *badTriangle = -1;
     S.nVerts = (int)in.nVerts;
@@ -1038,6 +1046,23 @@ int build_set(cq_world *w, DeviceSet &S, const SetPlan &in,
     int rc = CQ_OK;
     if (n > 0) {
         k_compact<<<cdiv(nIn, 256), 256, 0, st>>>(dFlags, dOffs, nIn, dIdxIn, dLayerIn, dPartIn, S.indices, S.triLayer, S.triPart);
+        if (matIn) { // per-triangle materials: the rows travel through the same compaction (triSource[triLocal], :363-396)
+            int32_t *dMatIn = nullptr;
+            CQ_CUDA(cudaMalloc((void **)&dMatIn, sizeof(int32_t) * (size_t)nIn));
+            int r = check_cuda(cudaMalloc((void **)&S.triMat, sizeof(int32_t) * (size_t)n), "triangle materials");
+            if (r == CQ_OK) r = check_cuda(cudaMemcpyAsync(dMatIn, matIn, sizeof(int32_t) * (size_t)nIn, cudaMemcpyHostToDevice, st), "triangle materials");
+            if (r == CQ_OK) {
+                k_compact_i32<<<cdiv(nIn, 256), 256, 0, st>>>(dFlags, dOffs, nIn, dMatIn, S.triMat);
+                w->launches++;
+                r = check_cuda(cudaStreamSynchronize(st), "triangle materials");
+            }
+            cudaFree(dMatIn);
+            if (r != CQ_OK) {
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+                return done(r);
+            }
+        }
         k_init_bounds<<<1, 32, 0, st>>>(dBounds);
         k_centroid_bounds<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds);
         k_morton<<<cdiv(n, 256), 256, 0, st>>>(S.worldPos, S.indices, n, dBounds, dKeys, S.sortedTri);

@@ -35,6 +35,7 @@ struct DeviceSet {
     uint32_t *indices = nullptr;  // 3 per triangle, set-global vertex ids
     uint32_t *triLayer = nullptr;
     int32_t *triPart = nullptr;
+    int32_t *triMat = nullptr; // per triangle: row of the material table, only when a part of the set has per-triangle materials (own allocation)
     // sorted (Morton) order
     uint32_t *sortedTri = nullptr; // slot -> soup triangle id
     float4 *tv0 = nullptr, *tv1 = nullptr, *tv2 = nullptr;
@@ -97,6 +98,9 @@ struct cq_world {
     float buildMs = 0, refitMs = 0;
     int counting = 0;
     int countRef = 0; // counting mode CQ_COUNT_REFERENCE
+    // material table: one row per part, then the per-triangle rows of the parts that brought their own (triangleMaterials)
+    std::vector<cq_material> hMaterials;
+    std::vector<int32_t> hTriMat[2]; // host copy of DeviceSet::triMat (cq_world_triangle_material)
     unsigned long long *dCounters = nullptr; // 4 x u64: nodes, cands, evals, queries
     int occ[6][4] = {}; // (raycast: [counting + 2 * reference-order walker]) // resident CTAs per SM of each persistent kernel ([counting + 2 * staged-walk variant])
     int numSms = 0;
@@ -152,7 +156,8 @@ void *pool_node_scratch(cq_world *w, size_t warps, cudaStream_t st);
 // cq_build.cu
 int build_set(cq_world *w, DeviceSet &S, const SetPlan &in /* upload plan of the set, cq_assemble.h */,
               std::vector<int> &partTriStart /* in: first input triangle of each part of the set (+ end); out: after the filter */,
-              int *badTriangle /* out: smallest input triangle with an out-of-range index (CQ_ERR_INVALID), else -1 */);
+              int *badTriangle /* out: smallest input triangle with an out-of-range index (CQ_ERR_INVALID), else -1 */,
+              const int32_t *matIn = nullptr /* host, per INPUT triangle: row of the material table, or nullptr (row = part) */);
 int refit_set(cq_world *w, DeviceSet &S, const std::vector<int> &partIdx);
 // reference order: rebuild the reference's tree on the host from the set's triangle boxes, upload rank + tree (cq_reftree.h)
 int attach_ref_order(cq_world *w);

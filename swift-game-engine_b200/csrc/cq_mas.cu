@@ -395,7 +395,7 @@ __device__ __forceinline__ void mas_finish(CharCtx &c, const WorldView &W, const
                 gNormal = normalize(prevNormal * (1.0f - blend) + gNormal * blend);
             }
         }
-        if (c.cPart >= 0 && c.cPart < W.nParts) {
+        if (c.cPart >= 0 && c.cPart < W.nMaterials) { // (cPart: row of the material table)
             float4 m = __ldg(W.materials + c.cPart);
             matMuS = m.x, matMuK = m.y, matFlatten = m.z != 0.0f;
         }
@@ -615,7 +615,7 @@ __device__ __forceinline__ bool mas_advance(CharCtx &c, const QResult &q, QShare
             st3(c.cNormal, q.bestN);
             st3(c.cTriNormal, q.bestTriN);
             c.cTri = q.bestTri;
-            c.cPart = world_part_of(W, q.bestTri);
+            c.cPart = world_material_row(W, q.bestTri);
         }
         // Dead-query elimination (exact): the fall probe only feeds state.distance (SYS:864), and that field is
         // overwritten by centerHit.toi as soon as the guard `centerHit.toi <= snapDistance` passes (SYS:868-880).

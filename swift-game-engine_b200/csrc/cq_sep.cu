@@ -544,8 +544,8 @@ __device__ __forceinline__ bool post_advance(PostCtx &c, const QResult &q, QShar
             S.grounded = 1;
             S.grounded_near = q.bestT <= smax(P.ground_snap_skin, P.skin_width) ? 1 : 0;
             bool flatten = false;
-            const int hitPart = world_part_of(W, q.bestTri);
-            if (hitPart >= 0 && hitPart < W.nParts) flatten = __ldg(W.materials + hitPart).z != 0.0f;
+            const int row = world_material_row(W, q.bestTri);
+            if (row >= 0 && row < W.nMaterials) flatten = __ldg(W.materials + row).z != 0.0f;
             f3 gn = flatten ? mk3(0, 1, 0) : q.bestTriN;
             S.ground_normal[0] = gn.x, S.ground_normal[1] = gn.y, S.ground_normal[2] = gn.z;
             S.ground_triangle_index = q.bestTri;

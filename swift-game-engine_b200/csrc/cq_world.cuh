@@ -49,6 +49,7 @@ struct SetView {
     const Node4 *nodes4;
     const SetHeader *hdr;
     const int32_t *triPart; // per triangle of the set (soup numbering): index of the part (entity) it came from -> material
+    const int32_t *triMat;  // per triangle: row of the material table, or nullptr = the part's own row (no per-triangle materials)
     int triOffset; // added to triangle ids of this set (dynamic set: static count, CollisionQuery.swift:782)
     // Reference order only (cq_reftree.h): the reference's own median-split tree as 64-byte nodes (child 0 = left,
     // child 1 = right; a leaf reference ~((start << 2) | (count - 1)) names positions of refSlot), walked by the ray
@@ -60,8 +61,9 @@ struct SetView {
 
 struct WorldView {
     SetView set[2];
-    const float4 *materials; // per part: (muS, muK, flattenGround, -)
+    const float4 *materials; // (muS, muK, flattenGround, -): one row per part, then the rows of per-triangle materials
     int nParts;
+    int nMaterials;
     // Visiting rank of every triangle (global triangle index -> position in the reference's depth-first order, static
     // set first), or nullptr in canonical order, where the rank of a triangle is its index.  Exact ties (equal toi /
     // depth) go to the smaller rank; capsuleOverlapAll keeps the maxHits smallest ranks (CollisionQuery.swift:1272-1274).
@@ -115,11 +117,13 @@ __device__ __forceinline__ Tri load_tri(const SetView &s, int i, uint32_t &layer
     return Tri{xyz(a), xyz(b), xyz(c)};
 }
 
-// part (entity) of a global triangle index: TriangleMeshSet.materialForTriangle's lookup (CollisionQuery.swift:464-469)
-__device__ __forceinline__ int world_part_of(const WorldView &W, int gid) {
+// row of the material table of a global triangle index (TriangleMeshSet.triangleMaterials[index], :464-469), -1 = default
+__device__ __forceinline__ int world_material_row(const WorldView &W, int gid) {
     if (gid < 0) return -1;
     const int off = W.set[1].triOffset;
-    return gid >= off ? __ldg(W.set[1].triPart + (gid - off)) : __ldg(W.set[0].triPart + gid);
+    const SetView &S = gid >= off ? W.set[1] : W.set[0];
+    const int local = gid >= off ? gid - off : gid;
+    return S.triMat ? __ldg(S.triMat + local) : __ldg(S.triPart + local);
 }
 
 #define CQ_MODE_ALL 0

@@ -29,8 +29,17 @@ public final class CollisionQuery {
         cq_world_options_default(&options)
         options.order = referenceOrder ? Int32(CQ_ORDER_REFERENCE) : Int32(CQ_ORDER_CANONICAL)
         var h: OpaquePointer?
-        let rc: Int32 = CollisionQuery.withArrays(built.positions, built.indices, &parts) {
-            cq_world_create_ex(&parts, Int32(parts.count), &options, &h)
+        // StaticMeshComponent.triangleMaterials (CollisionQuery.swift:363-369): handed over per part; the library applies the
+        // reference's rule (used when there is one entry per triangle, ignored otherwise)
+        var perTri: [cq_triangle_materials] = []
+        let rc: Int32 = CollisionQuery.withMaterialArrays(built.triangleMaterials, &perTri) {
+            perTri.withUnsafeBufferPointer { tm in
+                options.n_triangle_materials = Int32(tm.count)
+                options.triangle_materials = tm.baseAddress
+                return CollisionQuery.withArrays(built.positions, built.indices, &parts) {
+                    cq_world_create_ex(&parts, Int32(parts.count), &options, &h)
+                }
+            }
         }
         handle = rc == CQ_OK ? h : nil // on failure every query answers nil (no CPU fallback exists)
         lastError = rc == CQ_OK ? nil : String(cString: cq_last_error())
@@ -177,21 +186,27 @@ public final class CollisionQuery {
     /// Entities with Transform + StaticMesh (collides), ascending id (the reference iterates a Dictionary, i.e. in
     /// per-process random order — World.swift:99-118; the library fixes the order so triangle numbering is stable).
     /// Geometry is returned as plain Swift arrays; `withArrays` lends their storage to the C structs for one call.
-    /// StaticMeshComponent.triangleMaterials (per-triangle materials, CollisionQuery.swift:364-369) cannot be expressed
-    /// through cq_mesh_part (one material per part; no scene of the reference sets them): asserted nil here.
+    /// StaticMeshComponent.triangleMaterials (per-triangle materials, CollisionQuery.swift:363-369) travel beside the parts
+    /// as (entity id, materials) pairs and reach the library through cq_world_options.triangle_materials.
     private static func makeParts(world: World, activeEntityIDs: Set<UInt32>?)
-        -> (parts: [cq_mesh_part], positions: [[Float]], indices: [[UInt32]]) {
+        -> (parts: [cq_mesh_part], positions: [[Float]], indices: [[UInt32]],
+            triangleMaterials: [(UInt32, [cq_surface_material])]) {
         let tStore = world.store(TransformComponent.self)
         let mStore = world.store(StaticMeshComponent.self)
         let pStore = world.store(PhysicsBodyComponent.self)
         var parts: [cq_mesh_part] = []
         var positions: [[Float]] = []
         var indices: [[UInt32]] = []
+        var triangleMaterials: [(UInt32, [cq_surface_material])] = []
         let entities = world.query(TransformComponent.self, StaticMeshComponent.self).sorted { $0.id < $1.id }
         for e in entities {
             if let active = activeEntityIDs, !active.contains(e.id) { continue }
             guard let t = tStore[e], let m = mStore[e], m.collides else { continue }
-            assert(m.triangleMaterials == nil, "per-triangle materials are not supported by cq_mesh_part")
+            if let perTri = m.triangleMaterials {
+                triangleMaterials.append((e.id, perTri.map {
+                    cq_surface_material(mu_s: $0.muS, mu_k: $0.muK, flatten_ground: $0.flattenGround ? 1 : 0, _pad: (0, 0, 0))
+                }))
+            }
             let mesh = m.collisionMesh ?? m.mesh
             var pos: [Float] = []
             pos.reserveCapacity(mesh.streams.positions.count * 3)
@@ -216,7 +231,22 @@ public final class CollisionQuery {
             positions.append(pos)
             indices.append(idx32)
         }
-        return (parts, positions, indices)
+        return (parts, positions, indices, triangleMaterials)
+    }
+
+    /// Runs `body` with `out` holding one cq_triangle_materials per entry, pointing at that entry's storage (valid only
+    /// inside the call).
+    private static func withMaterialArrays<R>(_ lists: [(UInt32, [cq_surface_material])], _ out: inout [cq_triangle_materials],
+                                              _ body: () -> R) -> R {
+        func go(_ k: Int) -> R {
+            if k == lists.count { return body() }
+            return lists[k].1.withUnsafeBufferPointer { mp in
+                out.append(cq_triangle_materials(entity_id: lists[k].0, n: Int32(mp.count), materials: mp.baseAddress))
+                return go(k + 1)
+            }
+        }
+        out.removeAll()
+        return go(0)
     }
 
     /// Runs `body` with every part pointing at its arrays' storage (valid only inside the call; nothing is leaked).

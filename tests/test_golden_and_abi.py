@@ -65,6 +65,8 @@ def test_record_layouts_match_header(cq):
     assert cq.CAST_HIT.itemsize == 44 and cq.OVERLAP_HIT.itemsize == 44 and cq.RAY.itemsize == 32
     assert cq.RAY_HIT.itemsize == 32 and cq.CAPSULE.itemsize == 24
     assert ctypes.sizeof(cq.MeshPart) == 112
+    # the per-triangle materials were carved out of the reserved words of cq_world_options: its size must not move
+    assert ctypes.sizeof(cq.WorldOptions) == 32 and cq.SURFACE_MATERIAL.itemsize == 12 and ctypes.sizeof(cq.TriangleMaterials) == 16
 
 
 def test_no_cpu_fallback_without_gpu(cq):
@@ -310,7 +312,7 @@ def test_header_is_plain_c_and_cpp_mirror_compiles(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     src = tmp_path / "use.cpp"
-    src.write_text('#include "%s"\nint main(){ cqhost::Float3 a{0,0,0}; (void)a; return sizeof(cq_character_state)==168 ? 0 : 1; }\n'
+    src.write_text('#include "%s"\nint main(){ cqhost::Float3 a{0,0,0}; (void)a; static_assert(sizeof(cq_world_options) == 32 && sizeof(cq_surface_material) == 12 && sizeof(cq_triangle_materials) == 16, "ABI"); return sizeof(cq_character_state)==168 ? 0 : 1; }\n'
                    % os.path.join(ROOT, "swift-game-engine_b200", "cpp", "CollisionQuery.hpp"))
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

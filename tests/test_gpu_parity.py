@@ -1003,3 +1003,58 @@ def test_full_size_c5_rays_properties(cq, orc, scenes):
     lost = diff & (can["triangle_index"] >= 0) & ((ref["triangle_index"] < 0) | (ref["distance"] > can["distance"]))
     assert not (diff & ~tie & ~lost).any() and diff.mean() < 0.01
     o.close()
+
+
+@pytest.mark.gpu
+def test_per_triangle_materials_match_the_oracle(cq, orc, scenes):
+    """StaticMeshComponent.triangleMaterials (CollisionQuery.swift:363-396, 464-469) through cq_world_options: random
+    friction / flattenGround per triangle of a rolling terrain (static set) and of a tilted dynamic slab, one part whose
+    array has the wrong length (ignored, as in the reference), degenerate triangles that take their entries with them.
+    materialForTriangle and 40 move-and-slide steps (slope friction + flattened normals read the material of the ground
+    triangle) must equal the oracle's field for field, in both order rules."""
+    rng = np.random.default_rng(77)
+    tparts, half = scenes.terrain_scene(cells=48, cell=2.0)
+    terr = dict(tparts[0])
+    nt = len(terr["indices"]) // 3
+
+    def rows(n):
+        return np.stack([rng.uniform(0.0, 1.2, n), rng.uniform(0.0, 0.9, n), rng.integers(0, 2, n)], 1).astype(np.float32)
+
+    terr["triangle_materials"] = rows(nt)
+    sv = np.array([[-6, 0, -6], [6, 0, -6], [-6, 0, 6], [6, 0, 6], [0, 0, -6]], np.float32)
+    si = np.array([0, 2, 1, 0, 1, 4, 1, 2, 3], np.uint32)  # (0,1,4) is collinear: dropped by the filter
+    tilt = scenes.quat_angle_axis(np.radians(30.0), (0, 0, 1))
+    slab = dict(scenes.part(sv, si, scenes.trs_model((10.0, 14.0, 10.0), tilt), is_dynamic=True, entity_id=5, mu_s=0.2, mu_k=0.1),
+                triangle_materials=np.float32([[0.05, 0.02, 0], [9, 9, 1], [2.5, 2.0, 0]]))  # icy | (dropped) | sticky
+    wrong = dict(scenes.part(sv, si, scenes.trs_model((-12.0, 15.0, -8.0)), entity_id=6, mu_s=0.33, mu_k=0.22),
+                 triangle_materials=rows(2))  # 2 entries for 3 triangles
+    parts = [terr, slab, wrong]
+    pos = np.stack([rng.uniform(-30, 30, 3000), np.zeros(3000), rng.uniform(-30, 30, 3000)], 1).astype(np.float32)
+    pos[:, 1] = scenes.terrain_height(pos[:, 0], pos[:, 2]) + 2.6
+    pos[:200] = np.float32([10, 17.0, 10]) + rng.uniform(-4, 4, (200, 3)).astype(np.float32) * np.float32([1, 0.1, 1])
+    pos[200:300] = np.float32([-12, 17.8, -8]) + rng.uniform(-4, 4, (100, 3)).astype(np.float32) * np.float32([1, 0.05, 1])
+    vel = np.zeros_like(pos)
+    vel[300:, 0], vel[300:, 2] = rng.uniform(-6, 6, 2700), rng.uniform(-6, 6, 2700)
+    for order in (cq.ORDER_REFERENCE, cq.ORDER_CANONICAL):
+        g, o = cq.CollisionQuery(parts, order=order), orc.OracleWorld(parts)
+        inf = g.info()
+        n_all = inf["n_static_triangles"] + inf["n_dynamic_triangles"]
+        assert inf["n_dynamic_triangles"] == 2 and inf["n_static_triangles"] == nt + 2
+        for t in list(range(0, n_all, 97)) + [nt - 1, nt, nt + 1, n_all - 2, n_all - 1, n_all, n_all + 5]:
+            a, b = g.triangle_material(t), o.triangle_material(t)
+            assert a["mu_s"] == b["mu_s"] and a["mu_k"] == b["mu_k"] and a["flatten_ground"] == b["flatten_ground"], (t, a, b)
+        sg, so = cq.init_states(pos, vel), orc.init_states(pos, vel)
+        pg, po = cq.default_params(), orc.default_params()
+        slid = np.zeros(len(pos), bool)
+        for step in range(40):
+            g.move_and_slide(sg, pg)
+            o.move_and_slide(so, po, order=order)
+            for f in sg.dtype.names:
+                if f != "_pad":
+                    assert np.array_equal(sg[f], so[f]), (order, step, f, int((sg[f] != so[f]).sum()))
+            slid |= sg["ground_sliding"] > 0
+        assert sg["grounded"].mean() > 0.6 and slid[:200].any() and not slid[:200].all()  # icy and sticky halves of the slab
+        flat = sg["grounded"].astype(bool) & (np.abs(sg["ground_normal"][:, 1] - 1.0) < 1e-7)
+        assert flat.any() and (~flat & sg["grounded"].astype(bool)).any()  # flattened and unflattened ground normals both occur
+        g.close()
+        o.close()

@@ -825,3 +825,38 @@ def test_oracle_reference_order_matches_independent_bvh_and_walks(orc, scenes):
     sets[0].update_transform(1, m_sta)
     ties += compare("refitted", 400, 200, 800, 21)
     assert ties > 20  # the scene does produce exact-tie cases, so the visiting order was really exercised
+
+
+def test_per_triangle_materials_follow_the_reference_rules(orc, scenes):
+    """StaticMeshComponent.triangleMaterials (CollisionQuery.swift:363-396): used when there is exactly one entry per
+    triangle of the part (counted BEFORE the degenerate filter), ignored otherwise; a triangle the filter drops takes its
+    entry with it; materialForTriangle indexes the filtered soup, static set first, default material out of range."""
+    v = np.array([[0, 0, 0], [4, 0, 0], [0, 0, 4], [4, 0, 4], [8, 0, 0]], np.float32)
+    idx = np.array([0, 2, 1, 0, 1, 4, 1, 2, 3], np.uint32)  # the middle triangle (0,1,4) is collinear: the filter drops it
+    rows = np.array([[0.9, 0.7, 0], [0.5, 0.5, 1], [0.1, 0.05, 1]], np.float32)
+    w = orc.OracleWorld([dict(scenes.part(v, idx, entity_id=7), triangle_materials=rows),
+                         dict(scenes.part(v + np.float32([0, 5, 0]), idx[[0, 1, 2, 6, 7, 8]], entity_id=8, mu_s=0.3, mu_k=0.2,
+                                          is_dynamic=True), triangle_materials=rows)])  # 3 entries for 2 triangles: ignored
+    assert w.counts(0)["triangles"] == 2 and w.counts(1)["triangles"] == 2
+    m = [w.triangle_material(t) for t in range(5)]
+    assert m[0]["mu_s"] == pytest.approx(0.9) and not m[0]["flatten_ground"]
+    assert m[1]["mu_s"] == pytest.approx(0.1) and m[1]["mu_k"] == pytest.approx(0.05) and m[1]["flatten_ground"]
+    assert m[2]["mu_s"] == pytest.approx(0.3) and m[3]["mu_k"] == pytest.approx(0.2)  # the part's own material
+    assert m[4]["mu_s"] == pytest.approx(0.8) and m[4]["mu_k"] == pytest.approx(0.6)  # SurfaceMaterial.default
+
+
+def test_per_triangle_friction_decides_who_slides(orc, scenes):
+    """SlopeFriction.apply (Systems.swift:965-1021) reads the material of the ground triangle: on one 27-degree slope a
+    character standing on a sticky triangle stays, one standing on an icy triangle slides downhill."""
+    s, L = np.float32(0.5), 40.0  # y = 0.5 * x
+    v = np.array([[-L, -L * s, -L], [L, L * s, -L], [-L, -L * s, 0], [L, L * s, 0], [-L, -L * s, L], [L, L * s, L]], np.float32)
+    idx = np.array([0, 2, 1, 1, 2, 3, 2, 4, 3, 3, 4, 5], np.uint32)  # z < 0: triangles 0,1; z > 0: triangles 2,3
+    rows = np.array([[5.0, 5.0, 0], [5.0, 5.0, 0], [0.0, 0.0, 0], [0.0, 0.0, 0]], np.float32)
+    w = orc.OracleWorld([dict(scenes.part(v, idx, entity_id=0), triangle_materials=rows)])
+    p = orc.default_params()
+    st = orc.init_states([[0, 3.2, -10], [0, 3.2, 10]])
+    for _ in range(40):
+        w.move_and_slide(st, p, order=orc.ORDER_REFERENCE)
+    assert st["grounded"].all() and st["ground_triangle_index"].tolist() == [1, 2]
+    sticky, icy = st["position"][0], st["position"][1]
+    assert abs(sticky[0]) < 0.05 and icy[0] < -5.0, (sticky, icy)
