@@ -193,6 +193,9 @@ __global__ void k_agent_first_hit(const cq_character_state *__restrict__ states,
 
 enum { W_NONE = 0, W_DEPEN, W_SLIDE, W_SNAP, W_FALL, W_OFFSET };
 enum { NX_LOAD = 0, NX_DEPEN, NX_SLIDE, NX_SNAP, NX_FALL, NX_GATE, NX_OFFSET, NX_FINISH, NX_POST };
+#ifndef CQ_MAS_FE_IDLE
+#define CQ_MAS_FE_IDLE 16 /* idle lanes that open the front end (cq_pool.cuh: pool_run); >= 16 also selects the readiness rule */
+#endif
 #ifndef CQ_SINGLE_POST
 #define CQ_SINGLE_POST 1 /* every sweep of the controller is posted from ONE inlined pool_post_cast: 7 KB less code in the front end
                             (measured, same box: hulls 432 -> 440 M/s, terrain 282 -> 285 M/s); 0 = one copy per posting state */
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(MAS_THREADS, MAS_MIN_BLOCKS) k_move_and_slide(
     c.wait = W_NONE;
     c.flags = 0;
     Counters ctr = {0, 0, 0, 0};
-    pool_run<COUNT, STAGED, 16, false>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
+    pool_run<COUNT, STAGED, CQ_MAS_FE_IDLE, false>(W, wp, lane, ownersPerWarp, ctr, [&](QShared &mine, Counters &ct) {
         QResult r;
         pool_read_result(mine, r);
         return mas_advance<COUNT, AGENTS>(c, r, mine, wp, lane, W, A, states, n, workCounter, order, ct);

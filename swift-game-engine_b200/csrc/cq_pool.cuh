@@ -33,6 +33,9 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
+#ifndef CQ_WALK_FILL
+#define CQ_WALK_FILL 96 /* walk rounds run until the pair ring holds this many pairs (about three trips of work) */
+#endif
 #ifndef CQ_PICKUP_DROP
 #define CQ_PICKUP_DROP 1 /* 0: sweeps keep every candidate of the whole sweep's box (no bestT-based drops in walk / pickup; A/B) */
 #endif
@@ -762,7 +765,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
             if (go) alive = advance(mine, ctr);
             __syncwarp();
             // cooperative walk: rounds until the ring holds ~3 trips of work (or the stack is empty)
-            while (*wp.ntop != 0u && *wp.tail - *wp.head < 96u && *wp.tail - *wp.head + 128u <= (uint32_t)CQ_QCAP)
+            while (*wp.ntop != 0u && *wp.tail - *wp.head < (uint32_t)CQ_WALK_FILL && *wp.tail - *wp.head + 128u <= (uint32_t)CQ_QCAP)
                 pool_walk_round<COUNT, STAGED, LOOKAHEAD>(W, wp, lane, ctr);
         }
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
