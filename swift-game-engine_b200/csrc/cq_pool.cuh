@@ -382,8 +382,9 @@ __device__ __forceinline__ void pool_walk_round(const WorldView &W, const WarpPo
 //      moves at unit speed, so no contact exists at or before bestT.
 // A lane that dropped its candidate takes another one (up to four pickups per trip), so that drops do not leave lanes idle
 // through the evaluation.  C2 (profiles/r2_ab_same_box.txt, call 11).
-// OVLDROP (the staged-walk move-and-slide kernel): an overlap candidate is dropped when the kernel's bookkeeping says it cannot
-// matter (OverlapTop2::cannot_matter: reference order, eight overlaps on record, this triangle visited after all of them).
+// OVLDROP (the staged-walk move-and-slide kernel and the query kernels): an overlap candidate is dropped when the kernel's
+// bookkeeping says it cannot matter (OverlapTop2::cannot_matter: reference order, eight overlaps on record, this triangle
+// visited after all of them; OverlapTopK::cannot_matter: the same once the overflow of capsuleOverlapAll is established).
 template <bool COUNT, bool LOOKAHEAD_, bool OVLDROP_, class OvlCommit>
 __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPool &wp, Job &job, int lane, const OvlCommit &ovl) {
     constexpr bool LOOKAHEAD = LOOKAHEAD_ && CQ_PICKUP_DROP;
@@ -420,7 +421,7 @@ __device__ __forceinline__ void pool_take_jobs(const WorldView &W, const WarpPoo
                         dropped = sweep_cannot_matter(s, bestT, margin, vmin(job.T.v0, vmin(job.T.v1, job.T.v2)),
                                                       vmax(job.T.v0, vmax(job.T.v1, job.T.v2)), job.rank);
                 }
-                if (OVLDROP && job.phase == PH_OVL) dropped = ovl.cannot_matter(s, job.rank);
+                if (OVLDROP && job.phase == PH_OVL && !(COUNT && W.refStats)) dropped = ovl.cannot_matter(s, job.rank, e);
                 if ((LOOKAHEAD || OVLDROP) && dropped) {
                     job.phase = PH_NONE;
                     atomicSub(&s.pending, 1);
@@ -591,7 +592,7 @@ struct OverlapTop2 {
     // Reference order, eight overlaps on record: a triangle the reference visits after all eight cannot be among the first
     // eight, whether it overlaps or not.  (The count then stays short of the true total, but not below eight, and whenever
     // it is exactly eight the two deepest seen are the two deepest of exactly those eight.)
-    __device__ __forceinline__ bool cannot_matter(QShared &s, int rk) const {
+    __device__ __forceinline__ bool cannot_matter(QShared &s, int rk, uint32_t) const {
         if (!byRank) return false;
         const volatile int *ov = ovl_words(s);
         return ov[OVL_TOTAL] >= CQ_MAX_OVERLAP_HITS && rk > ov[OVL_MAXRANK];
@@ -769,7 +770,7 @@ __device__ __forceinline__ void pool_run(const WorldView &W, const WarpPool &wp,
                 pool_walk_round<COUNT, STAGED, LOOKAHEAD>(W, wp, lane, ctr);
         }
         // executor: idle lanes take pairs; every lane holding a pair does ONE distance evaluation
-        pool_take_jobs<COUNT, LOOKAHEAD, STAGED && FE_IDLE >= 16>(W, wp, job, lane, ovl);
+        pool_take_jobs<COUNT, LOOKAHEAD, (STAGED && FE_IDLE >= 16) || LOOKAHEAD>(W, wp, job, lane, ovl);
         Commit cm;
         cm.kind = 0;
         bool retired = false;

@@ -654,7 +654,14 @@ struct OvlTop {
 struct OverlapTopK {
     OvlTop *tops; // the warp's 32 records
     bool byRank; // keep the smallest ranks (overlap-all in reference order) instead of the deepest
-    __device__ __forceinline__ bool cannot_matter(QShared &, int) const { return false; } // (the overflow flag needs every overlap)
+    // capsuleOverlapAll in reference order keeps the maxHits overlaps visited first (:1272-1274).  Once MORE than maxHits
+    // overlaps are on record the count (= maxHits) and the overflow flag are settled, and a triangle visited after all the
+    // kept ones cannot enter the list whether it overlaps or not: it is not evaluated.
+    __device__ __forceinline__ bool cannot_matter(QShared &, int rk, uint32_t enc) const {
+        if (!byRank) return false;
+        const OvlTop &t = tops[enc >> 27];
+        return t.total > t.cap && rk > t.rank[t.cap - 1];
+    }
     __device__ __forceinline__ void operator()(QShared &, float depth, int gid, int rk, uint32_t enc, f3) const {
         OvlTop &t = tops[enc >> 27];
         t.total++;

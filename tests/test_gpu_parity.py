@@ -5,6 +5,8 @@ sides run the same IEEE op sequence, so the oracle must match BIT-EXACTLY on eve
 a world created in CQ_ORDER_REFERENCE (the default) against the oracle's ORDER_REFERENCE (the reference's own
 BVH and depth-first visiting order), a CQ_ORDER_CANONICAL world against ORDER_CANONICAL.  The two order
 constants have the same values on both sides, so `g.order` is passed to the oracle."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -1058,3 +1060,12 @@ def test_per_triangle_materials_match_the_oracle(cq, orc, scenes):
         assert flat.any() and (~flat & sg["grounded"].astype(bool)).any()  # flattened and unflattened ground normals both occur
         g.close()
         o.close()
+    # a count without an array is refused with a message, not read
+    keep = []
+    arr = cq._mesh_parts([wrong], keep)
+    opt = cq.WorldOptions()
+    cq.lib().cq_world_options_default(ctypes.byref(opt))
+    opt.n_triangle_materials = 1
+    h = ctypes.c_void_p()
+    rc = cq.lib().cq_world_create_ex(ctypes.byref(arr), 1, ctypes.byref(opt), ctypes.byref(h))
+    assert rc != 0 and not h.value and b"triangle_materials" in cq.lib().cq_last_error()
