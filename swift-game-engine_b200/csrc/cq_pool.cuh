@@ -33,8 +33,11 @@ enum { PH_NONE = 0, PH_ADV = 1, PH_BIS = 2, PH_FIN = 3, PH_OVL = 4 };
 #ifndef CQ_EVAL_REPS
 #define CQ_EVAL_REPS 1    /* distance evaluations per main-loop trip (see pool_run) */
 #endif
-#ifndef CQ_WALK_FILL
-#define CQ_WALK_FILL 96 /* walk rounds run until the pair ring holds this many pairs (about three trips of work) */
+#ifndef CQ_WALK_FILL /* walk rounds run until the pair ring holds this many pairs.  Swept on one box after the slim pair state
+                        (profiles/r2_ab_same_box.txt, call 20; 96 everywhere before): the move-and-slide kernels gain 0.3-0.8% with a
+                        fuller ring (a round always leaves room for 128 more, so 160 means "up to 128"), the query kernels
+                        2.8% on C2 with a shorter one (fresher bestT for the culling of the next walk rounds; C4 unchanged) */
+#define CQ_WALK_FILL (LOOKAHEAD ? 64 : 160)
 #endif
 #ifndef CQ_PICKUP_DROP
 #define CQ_PICKUP_DROP 1 /* 0: sweeps keep every candidate of the whole sweep's box (no bestT-based drops in walk / pickup; A/B) */

@@ -4,6 +4,7 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
+timeout 1800 python -m pytest tests -m gpu -q -rf --no-header > $O/r2fin_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/r2fin_pytest.log
 timeout 300 python __graft_entry__.py smoke > $O/r2fin_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/r2fin_smoke.log | cut -c1-200
 ( time timeout 900 python bench.py --steps 20 --warmup 5 > $O/r2fin_bench_default.json 2> $O/r2fin_bench_default.err ) 2> $O/r2fin_bench_default.time
 echo "bench default rc=$?"; tail -3 $O/r2fin_bench_default.time
