@@ -119,7 +119,12 @@ int cq_crowd_step(cq_crowd *c, const double *velocity_in_xyz, const cq_controlle
         return v >= 1024 ? v : (1 << 17);
     }();
     int nChunks = (n + CH - 1) / CH;
-    if (c->hint > 3.0f && nChunks > 2) nChunks = 2; // compute bound last time: every chunk kernel pays its own tail
+    static const float HINT = [] { // wall / PCIe-time ratio above which the step counts as compute bound (CQ_CROWD_HINT overrides)
+        const char *e = getenv("CQ_CROWD_HINT");
+        const float v = e ? (float)atof(e) : 0.0f;
+        return v > 0.0f ? v : 3.0f;
+    }();
+    if (c->hint > HINT && nChunks > 2) nChunks = 2; // compute bound last time: every chunk kernel pays its own tail
     if (nChunks > CQ_PIPE_EVENTS) nChunks = CQ_PIPE_EVENTS;
     if (flags & CQ_MAS_AGENTS) nChunks = 1; // the characters interact: all velocities must be in place before the kernel starts
     const auto t0 = std::chrono::steady_clock::now();
