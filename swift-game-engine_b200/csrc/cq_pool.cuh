@@ -17,10 +17,12 @@
 //    owner's record.  The best accepted toi of the query is shared, so the exact-safe prune
 //    `lastSafeT > bestT` works across lanes;
 //  * a query completes when its walk is finished and its pending-pair counter is back to zero.
-// The main loop is: owner logic -> owner traversal/push -> job pickup (ballot ranked) -> ONE distance
-// evaluation on every lane that holds a pair -> serialized commit -> warp-uniform exit test.
-// Results are deterministic: a cast's answer is the accepted pair with the smallest (toi, index), an
-// order-free reduction; commits are applied one lane at a time.
+// The main loop is: [front end, only when the ring is dry and enough lanes idle: owner logic -> cooperative walk /
+// push] -> job pickup (ballot ranked; query kernels drop candidates that cannot matter) -> ONE distance
+// evaluation on every lane that holds a pair -> commit per owner (warp reductions / grouped rounds, pool_commit)
+// -> warp-uniform exit test.
+// Results are deterministic: a cast's answer is the accepted pair with the smallest (toi, visiting rank), an
+// order-free reduction, whatever the order in which the lanes finish.
 #pragma once
 #include "../../include/cq.h"
 #include "cq_world.cuh"
